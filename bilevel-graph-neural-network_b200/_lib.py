@@ -1,0 +1,162 @@
+"""ctypes binding of the C-ABI in include/bignn_b200.h.
+
+The shared library (`_C/libbignn_b200.so`, built in-tree by `build()` /
+`__graft_entry__.build()` with nvcc for sm_100a) is the ONLY compute backend of
+this package: there is no CPU or eager-PyTorch fallback.  A missing library is
+an ImportError at first use, a failed call a RuntimeError carrying the library's
+own error string.
+"""
+import ctypes
+import os
+import subprocess
+import threading
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, 'csrc')
+LIB_DIR = os.path.join(HERE, '_C')
+LIB_PATH = os.path.join(LIB_DIR, 'libbignn_b200.so')
+HEADER = os.path.join(ROOT, 'include', 'bignn_b200.h')
+
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
+              '-shared', '-Xcompiler', '-fPIC']
+
+# name -> (restype, argument codes): p pointer, i int32, l int64, f float; a trailing
+# 's' marks the stream argument, filled in from torch's current stream.
+SIGNATURES = {
+    'bignn_abi_version': ('i', ''),
+    'bignn_error_string': ('z', 'i'),
+    'bignn_launch_count': ('l', ''),
+    'bignn_merge_build_workspace_bytes': ('l', 'i'),
+    'bignn_merge_build': ('i', 'pppp' 'i' 'p' 'i' 'pp' 'ppp' 'ppp' 'ii' 'pl' 's'),
+    'bignn_gcn_dinv': ('i', 'ppips'),
+    'bignn_spmm_f32': ('i', 'pp' 'pl' 'pl' 'iiif' 'ppi' 's'),
+    'bignn_gemm_workspace_bytes': ('l', 'iiii'),
+    'bignn_gemm_f32': ('i', 'iiiii' 'pl' 'pl' 'pl' 'pi' 'pl' 's'),
+    'bignn_colsum_workspace_bytes': ('l', 'ii'),
+    'bignn_colsum_f32': ('i', 'pliip' 'pl' 's'),
+    'bignn_act_bwd_f32': ('i', 'ppplis'),
+    'bignn_bn_workspace_bytes': ('l', 'iii'),
+    'bignn_bn_seg_fwd': ('i', 'plpl' 'piii' 'pp' 'ff' 'ppp' 'pp' 'pl' 's'),
+    'bignn_bn_eval_fwd': ('i', 'plpl' 'ii' 'pp' 'f' 'pp' 's'),
+    'bignn_bn_seg_bwd': ('i', 'plplpl' 'piii' 'ppp' 'pp' 'pl' 's'),
+    'bignn_readout_fwd': ('i', 'pl' 'pii' 'i' 'p' 'pli' 's'),
+    'bignn_readout_bwd': ('i', 'pli' 'p' 'pii' 'i' 'pl' 'i' 's'),
+    'bignn_pair_gather_norm_fwd': ('i', 'pl' 'pii' 'pl' 'p' 's'),
+    'bignn_pair_gather_norm_bwd': ('i', 'pl' 'pii' 'pl' 'p' 'pl' 's'),
+    'bignn_bce_fwd': ('i', 'ppips'),
+    'bignn_bce_bwd': ('i', 'ppipps'),
+    'bignn_bce_logits_fwd': ('i', 'ppips'),
+    'bignn_bce_logits_bwd': ('i', 'ppipps'),
+}
+
+_CT = {'p': ctypes.c_void_p, 'i': ctypes.c_int32, 'l': ctypes.c_int64, 'f': ctypes.c_float,
+       's': ctypes.c_void_p, 'z': ctypes.c_char_p}
+
+_lib = None
+_lock = threading.Lock()
+_backend_override = None     # tests only: an object with .call(name, *args)
+
+
+def sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith('.cu'))
+
+
+def needs_build():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = sources() + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith('.cuh')] + [HEADER]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    """nvcc cross-compiles every kernel for sm_100a into the in-tree .so (no GPU needed)."""
+    if not force and not needs_build():
+        return LIB_PATH
+    os.makedirs(LIB_DIR, exist_ok=True)
+    nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+    if not os.path.exists(nvcc):
+        nvcc = 'nvcc'
+    tmp = LIB_PATH + '.tmp.%d' % os.getpid()
+    cmd = [nvcc] + NVCC_FLAGS + ['-o', tmp] + sources()
+    if verbose:
+        print(' '.join(cmd))
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True)
+    if r.returncode != 0:
+        raise RuntimeError('nvcc failed:\n' + r.stdout)
+    os.replace(tmp, LIB_PATH)
+    return LIB_PATH
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                'bignn_b200: CUDA library {} is missing -- run `python -c "import __graft_entry__ as g; '
+                'g.build()"` (nvcc, sm_100a). There is no CPU fallback.'.format(LIB_PATH))
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)        # AttributeError if the symbol is not exported
+            fn.restype = _CT[res]
+            fn.argtypes = [_CT[c] for c in args]
+        if lib.bignn_abi_version() != 1:
+            raise ImportError('bignn_b200: ABI version mismatch')
+        _lib = lib
+    return _lib
+
+
+def error_string(code):
+    return load().bignn_error_string(int(code)).decode()
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, torch.Tensor):
+        return a.data_ptr() if a.numel() > 0 else None
+    return int(a)
+
+
+def call(name, *args):
+    """Invoke a C-ABI entry point.  Tensors become raw pointers; the stream argument
+    is torch's current CUDA stream.  Non-zero status -> RuntimeError."""
+    if _backend_override is not None:
+        return _backend_override.call(name, *args)
+    lib = load()
+    res, codes = SIGNATURES[name]
+    n = len(codes) - (1 if codes.endswith('s') else 0)
+    if len(args) != n:
+        raise TypeError('{} expects {} arguments, got {}'.format(name, n, len(args)))
+    cargs = []
+    for c, a in zip(codes, args):
+        cargs.append(_ptr(a) if c == 'p' else a)
+    if codes.endswith('s'):
+        cargs.append(torch.cuda.current_stream().cuda_stream)
+    out = getattr(lib, name)(*cargs)
+    if res == 'i' and name != 'bignn_abi_version' and out != 0:
+        raise RuntimeError('{} failed with status {}: {}'.format(name, out, error_string(out)))
+    return out
+
+
+def launch_count():
+    if _backend_override is not None:
+        return 0
+    return int(load().bignn_launch_count())
+
+
+def require_device(*tensors):
+    """Every operand of the product path must live on a CUDA device."""
+    if _backend_override is not None:
+        return
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError('bignn_b200 runs on CUDA devices only (got a {} tensor); '
+                               'there is no CPU path'.format(t.device))

@@ -1,0 +1,270 @@
+// Segmented train-mode BatchNorm1d (see include/bignn_b200.h); replaces
+// torch.nn.BatchNorm1d at model/layers.py:57 for a whole all-drug pass at once:
+// segment s = rows [seg_row_ptr[s], seg_row_ptr[s+1]) = one 128-graph chunk of
+// src/train.py:62-71, normalised with its own batch statistics.
+//
+// Deterministic two-level reductions (no float atomics): each (segment, part)
+// CTA accumulates sum / sum-of-squares in fp64 over its contiguous row range,
+// a finalize kernel adds the parts in part order.  Running buffers are advanced
+// sequentially in segment order in fp64 (as torch's CPU kernel does) so the 11
+// momentum updates per step of the reference are reproduced.
+// HBM-bound: forward reads X twice (stats, apply) and writes Y once.
+#include "common.cuh"
+
+namespace bignn {
+
+constexpr int BN_ROWS = 8;
+
+__device__ __forceinline__ void part_range(const int32_t* __restrict__ seg_row_ptr, int s, int p, int parts,
+                                           int& r0, int& r1, int& n) {
+  const int a = seg_row_ptr[s], b = seg_row_ptr[s + 1];
+  n = b - a;
+  r0 = a + (int)(((int64_t)n * p) / parts);
+  r1 = a + (int)(((int64_t)n * (p + 1)) / parts);
+}
+
+// ws_a[(s*parts+p)*C+c] = sum_r f(r,c), ws_b = sum_r g(r,c)
+// STATS: f = x, g = x*x.   BWD: f = dy, g = dy * (x-mean)*rstd
+template <bool BWD>
+__global__ void __launch_bounds__(256)
+k_bn_reduce_part(const float* __restrict__ X, int64_t ldx, const float* __restrict__ dY, int64_t lddy,
+                 const int32_t* __restrict__ seg_row_ptr, int C, int parts,
+                 const float* __restrict__ mean, const float* __restrict__ rstd,
+                 double* __restrict__ ws_a, double* __restrict__ ws_b) {
+  __shared__ double ra[BN_ROWS][33];
+  __shared__ double rb[BN_ROWS][33];
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+  const int c = blockIdx.y * 32 + tx;
+  const int s = blockIdx.x / parts, p = blockIdx.x % parts;
+  int r0, r1, n;
+  part_range(seg_row_ptr, s, p, parts, r0, r1, n);
+  double a = 0.0, b = 0.0;
+  if (c < C) {
+    float mu = 0.f, rs = 0.f;
+    if (BWD) { mu = mean[(int64_t)s * C + c]; rs = rstd[(int64_t)s * C + c]; }
+    for (int r = r0 + ty; r < r1; r += BN_ROWS) {
+      const float x = __ldg(X + (int64_t)r * ldx + c);
+      if (BWD) {
+        const float g = __ldg(dY + (int64_t)r * lddy + c);
+        a += (double)g;
+        b += (double)g * (double)((x - mu) * rs);
+      } else {
+        a += (double)x;
+        b += (double)x * (double)x;
+      }
+    }
+  }
+  ra[ty][tx] = a;
+  rb[ty][tx] = b;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    double ta = 0.0, tb = 0.0;
+#pragma unroll
+    for (int i = 0; i < BN_ROWS; ++i) { ta += ra[i][tx]; tb += rb[i][tx]; }
+    ws_a[(int64_t)blockIdx.x * C + c] = ta;
+    ws_b[(int64_t)blockIdx.x * C + c] = tb;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_bn_finalize(const double* __restrict__ ws_a, const double* __restrict__ ws_b,
+              const int32_t* __restrict__ seg_row_ptr, int S, int C, int parts, float eps,
+              float* __restrict__ mean, float* __restrict__ rstd,
+              double* __restrict__ mean_d, double* __restrict__ varu_d) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)S * C) return;
+  const int s = (int)(i / C), c = (int)(i % C);
+  const int n = seg_row_ptr[s + 1] - seg_row_ptr[s];
+  double a = 0.0, b = 0.0;
+  for (int p = 0; p < parts; ++p) {
+    a += ws_a[((int64_t)s * parts + p) * C + c];
+    b += ws_b[((int64_t)s * parts + p) * C + c];
+  }
+  double mu = 0.0, var = 0.0;
+  if (n > 0) {
+    mu = a / n;
+    var = b / n - mu * mu;
+    if (var < 0.0) var = 0.0;
+  }
+  mean[i] = (float)mu;
+  rstd[i] = n > 0 ? (float)(1.0 / sqrt(var + (double)eps)) : 0.f;
+  mean_d[i] = mu;
+  varu_d[i] = n > 1 ? var * ((double)n / (double)(n - 1)) : var;
+}
+
+__global__ void __launch_bounds__(256)
+k_bn_running(const double* __restrict__ mean_d, const double* __restrict__ varu_d,
+             const int32_t* __restrict__ seg_row_ptr, int S, int C, double momentum,
+             float* __restrict__ running_mean, float* __restrict__ running_var,
+             int64_t* __restrict__ nbt) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    float rm = running_mean[c], rv = running_var[c];
+    for (int s = 0; s < S; ++s) {
+      if (seg_row_ptr[s + 1] - seg_row_ptr[s] <= 0) continue;
+      rm = (float)(momentum * mean_d[(int64_t)s * C + c] + (1.0 - momentum) * (double)rm);
+      rv = (float)(momentum * varu_d[(int64_t)s * C + c] + (1.0 - momentum) * (double)rv);
+    }
+    running_mean[c] = rm;
+    running_var[c] = rv;
+  }
+  if (c == 0 && nbt) {
+    int64_t k = 0;
+    for (int s = 0; s < S; ++s) k += (seg_row_ptr[s + 1] - seg_row_ptr[s] > 0);
+    *nbt += k;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_bn_apply(const float* __restrict__ X, int64_t ldx, float* __restrict__ Y, int64_t ldy,
+           const int32_t* __restrict__ seg_row_ptr, int C, int parts,
+           const float* __restrict__ gamma, const float* __restrict__ beta,
+           const float* __restrict__ mean, const float* __restrict__ rstd) {
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+  const int c = blockIdx.y * 32 + tx;
+  const int s = blockIdx.x / parts, p = blockIdx.x % parts;
+  int r0, r1, n;
+  part_range(seg_row_ptr, s, p, parts, r0, r1, n);
+  if (c >= C) return;
+  const float alpha = rstd[(int64_t)s * C + c] * (gamma ? gamma[c] : 1.f);
+  const float bt = (beta ? beta[c] : 0.f) - mean[(int64_t)s * C + c] * alpha;
+  for (int r = r0 + ty; r < r1; r += BN_ROWS)
+    Y[(int64_t)r * ldy + c] = fmaf(__ldg(X + (int64_t)r * ldx + c), alpha, bt);
+}
+
+__global__ void __launch_bounds__(256)
+k_bn_eval(const float* __restrict__ X, int64_t ldx, float* __restrict__ Y, int64_t ldy, int rows, int C,
+          const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+          const float* __restrict__ rm, const float* __restrict__ rv) {
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+  const int c = blockIdx.y * 32 + tx;
+  if (c >= C) return;
+  const float alpha = (float)(1.0 / sqrt((double)rv[c] + (double)eps)) * (gamma ? gamma[c] : 1.f);
+  const float bt = (beta ? beta[c] : 0.f) - rm[c] * alpha;
+  for (int r = blockIdx.x * BN_ROWS + ty; r < rows; r += gridDim.x * BN_ROWS)
+    Y[(int64_t)r * ldy + c] = fmaf(__ldg(X + (int64_t)r * ldx + c), alpha, bt);
+}
+
+// per segment sums of the backward reduction; also the parameter gradients
+__global__ void __launch_bounds__(256)
+k_bn_bwd_finalize(const double* __restrict__ ws_a, const double* __restrict__ ws_b, int S, int C, int parts,
+                  double* __restrict__ seg_a, double* __restrict__ seg_b) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)S * C) return;
+  const int s = (int)(i / C), c = (int)(i % C);
+  double a = 0.0, b = 0.0;
+  for (int p = 0; p < parts; ++p) {
+    a += ws_a[((int64_t)s * parts + p) * C + c];
+    b += ws_b[((int64_t)s * parts + p) * C + c];
+  }
+  seg_a[i] = a;
+  seg_b[i] = b;
+}
+
+__global__ void __launch_bounds__(256)
+k_bn_bwd_params(const double* __restrict__ seg_a, const double* __restrict__ seg_b, int S, int C,
+                float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double a = 0.0, b = 0.0;
+  for (int s = 0; s < S; ++s) { a += seg_a[(int64_t)s * C + c]; b += seg_b[(int64_t)s * C + c]; }
+  if (dbeta) dbeta[c] = (float)a;
+  if (dgamma) dgamma[c] = (float)b;
+}
+
+__global__ void __launch_bounds__(256)
+k_bn_bwd_apply(const float* __restrict__ X, int64_t ldx, const float* __restrict__ dY, int64_t lddy,
+               float* __restrict__ dX, int64_t lddx, const int32_t* __restrict__ seg_row_ptr, int C, int parts,
+               const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
+               const double* __restrict__ seg_a, const double* __restrict__ seg_b) {
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+  const int c = blockIdx.y * 32 + tx;
+  const int s = blockIdx.x / parts, p = blockIdx.x % parts;
+  int r0, r1, n;
+  part_range(seg_row_ptr, s, p, parts, r0, r1, n);
+  if (c >= C || n <= 0) return;
+  const float mu = mean[(int64_t)s * C + c], rs = rstd[(int64_t)s * C + c];
+  const float gmean = (float)(seg_a[(int64_t)s * C + c] / n);
+  const float dgn = (float)(seg_b[(int64_t)s * C + c] / n);
+  const float scale = rs * (gamma ? gamma[c] : 1.f);
+  for (int r = r0 + ty; r < r1; r += BN_ROWS) {
+    const float xhat = (__ldg(X + (int64_t)r * ldx + c) - mu) * rs;
+    const float g = __ldg(dY + (int64_t)r * lddy + c);
+    dX[(int64_t)r * lddx + c] = (g - gmean - xhat * dgn) * scale;
+  }
+}
+
+}  // namespace bignn
+
+using namespace bignn;
+
+extern "C" int64_t bignn_bn_workspace_bytes(int32_t S, int32_t C, int32_t parts) {
+  if (S <= 0 || C <= 0 || parts <= 0) return 0;
+  return (int64_t)sizeof(double) * (2 * (int64_t)S * parts * C + 2 * (int64_t)S * C);
+}
+
+extern "C" int bignn_bn_seg_fwd(const float* X, int64_t ldx, float* Y, int64_t ldy, const int32_t* seg_row_ptr,
+                                int32_t S, int32_t C, int32_t parts, const float* gamma, const float* beta,
+                                float eps, float momentum, float* running_mean, float* running_var,
+                                int64_t* num_batches_tracked, float* mean, float* rstd, void* workspace,
+                                int64_t workspace_bytes, void* stream) {
+  if (S < 0 || C < 0 || parts <= 0) return BIGNN_EINVAL;
+  if (S == 0 || C == 0) return 0;
+  if (!X || !Y || !seg_row_ptr || !mean || !rstd || ldx < C || ldy < C) return BIGNN_EINVAL;
+  if ((int64_t)S * parts > 2147483647LL) return BIGNN_EINVAL;
+  if (!workspace || workspace_bytes < bignn_bn_workspace_bytes(S, C, parts)) return BIGNN_EWORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  double* ws_a = (double*)workspace;
+  double* ws_b = ws_a + (int64_t)S * parts * C;
+  double* mean_d = ws_b + (int64_t)S * parts * C;
+  double* varu_d = mean_d + (int64_t)S * C;
+  dim3 grid(S * parts, ceil_div(C, 32));
+  k_bn_reduce_part<false><<<grid, 256, 0, st>>>(X, ldx, nullptr, 0, seg_row_ptr, C, parts, nullptr, nullptr, ws_a, ws_b);
+  k_bn_finalize<<<(int)ceil_div<int64_t>((int64_t)S * C, 256), 256, 0, st>>>(ws_a, ws_b, seg_row_ptr, S, C, parts, eps, mean, rstd, mean_d, varu_d);
+  BIGNN_LAUNCH_COUNT(2);
+  if (running_mean && running_var) {
+    k_bn_running<<<ceil_div(C, 256), 256, 0, st>>>(mean_d, varu_d, seg_row_ptr, S, C, (double)momentum, running_mean, running_var, num_batches_tracked);
+    BIGNN_LAUNCH_COUNT(1);
+  }
+  k_bn_apply<<<grid, 256, 0, st>>>(X, ldx, Y, ldy, seg_row_ptr, C, parts, gamma, beta, mean, rstd);
+  BIGNN_LAUNCH_COUNT(1);
+  return last_launch_status();
+}
+
+extern "C" int bignn_bn_eval_fwd(const float* X, int64_t ldx, float* Y, int64_t ldy, int32_t rows, int32_t C,
+                                 const float* gamma, const float* beta, float eps, const float* running_mean,
+                                 const float* running_var, void* stream) {
+  if (rows < 0 || C < 0) return BIGNN_EINVAL;
+  if (rows == 0 || C == 0) return 0;
+  if (!X || !Y || !running_mean || !running_var || ldx < C || ldy < C) return BIGNN_EINVAL;
+  int gx = ceil_div(rows, BN_ROWS);
+  const int cap = sm_count() * 8;
+  if (gx > cap) gx = cap;
+  dim3 grid(gx, ceil_div(C, 32));
+  k_bn_eval<<<grid, 256, 0, (cudaStream_t)stream>>>(X, ldx, Y, ldy, rows, C, gamma, beta, eps, running_mean, running_var);
+  BIGNN_LAUNCH_COUNT(1);
+  return last_launch_status();
+}
+
+extern "C" int bignn_bn_seg_bwd(const float* X, int64_t ldx, const float* dY, int64_t lddy, float* dX,
+                                int64_t lddx, const int32_t* seg_row_ptr, int32_t S, int32_t C, int32_t parts,
+                                const float* gamma, const float* mean, const float* rstd, float* dgamma,
+                                float* dbeta, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (S < 0 || C < 0 || parts <= 0) return BIGNN_EINVAL;
+  if (S == 0 || C == 0) return 0;
+  if (!X || !dY || !dX || !seg_row_ptr || !mean || !rstd || ldx < C || lddy < C || lddx < C) return BIGNN_EINVAL;
+  if ((int64_t)S * parts > 2147483647LL) return BIGNN_EINVAL;
+  if (!workspace || workspace_bytes < bignn_bn_workspace_bytes(S, C, parts)) return BIGNN_EWORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  double* ws_a = (double*)workspace;
+  double* ws_b = ws_a + (int64_t)S * parts * C;
+  double* seg_a = ws_b + (int64_t)S * parts * C;
+  double* seg_b = seg_a + (int64_t)S * C;
+  dim3 grid(S * parts, ceil_div(C, 32));
+  k_bn_reduce_part<true><<<grid, 256, 0, st>>>(X, ldx, dY, lddy, seg_row_ptr, C, parts, mean, rstd, ws_a, ws_b);
+  k_bn_bwd_finalize<<<(int)ceil_div<int64_t>((int64_t)S * C, 256), 256, 0, st>>>(ws_a, ws_b, S, C, parts, seg_a, seg_b);
+  k_bn_bwd_params<<<ceil_div(C, 256), 256, 0, st>>>(seg_a, seg_b, S, C, dgamma, dbeta);
+  k_bn_bwd_apply<<<grid, 256, 0, st>>>(X, ldx, dY, lddy, dX, lddx, seg_row_ptr, C, parts, gamma, mean, rstd, seg_a, seg_b);
+  BIGNN_LAUNCH_COUNT(4);
+  return last_launch_status();
+}

@@ -1,0 +1,137 @@
+// Segment readout: atoms -> one embedding row per drug (see include/bignn_b200.h).
+// Replaces torch-scatter scatter_mean / scatter_add at model/layers_aggregation.py:17-19,
+// 34-41 and the per-row Python scatter into init_x at :70-74.
+// One sub-warp (L lanes x 128-bit) per graph; rows are added in ascending order
+// (the reference's sequential scatter_add order), 4 independent loads in flight.
+// Algorithmic bytes: 4*D*A read + 4*D*G written + 4*(G+1).
+#include "common.cuh"
+
+namespace bignn {
+
+template <int L>
+__global__ void __launch_bounds__(256)
+k_readout_fwd_v4(const float* __restrict__ X, int64_t ldx, const int32_t* __restrict__ seg_ptr, int G, int D4,
+                 int style, const int32_t* __restrict__ dst_row, float* __restrict__ out, int64_t ldo) {
+  const int gpb = blockDim.x / L;
+  const int sub = threadIdx.x / L, lane = threadIdx.x % L;
+  for (int g = blockIdx.x * gpb + sub; g < G; g += gridDim.x * gpb) {
+    const int r0 = __ldg(seg_ptr + g), r1 = __ldg(seg_ptr + g + 1);
+    const int n = r1 - r0;
+    const int64_t orow = dst_row ? dst_row[g] : g;
+    for (int q = lane; q < D4; q += L) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      int r = r0;
+      for (; r + 4 <= r1; r += 4) {
+        const float4 v0 = ldg4(X + (int64_t)(r + 0) * ldx + 4 * q);
+        const float4 v1 = ldg4(X + (int64_t)(r + 1) * ldx + 4 * q);
+        const float4 v2 = ldg4(X + (int64_t)(r + 2) * ldx + 4 * q);
+        const float4 v3 = ldg4(X + (int64_t)(r + 3) * ldx + 4 * q);
+        acc.x = (((acc.x + v0.x) + v1.x) + v2.x) + v3.x;
+        acc.y = (((acc.y + v0.y) + v1.y) + v2.y) + v3.y;
+        acc.z = (((acc.z + v0.z) + v1.z) + v2.z) + v3.z;
+        acc.w = (((acc.w + v0.w) + v1.w) + v2.w) + v3.w;
+      }
+      for (; r < r1; ++r) {
+        const float4 v = ldg4(X + (int64_t)r * ldx + 4 * q);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      if (style == BIGNN_READOUT_MEAN) {
+        const float cnt = (float)(n > 1 ? n : 1);      // count.clamp(min=1)
+        acc.x = __fdiv_rn(acc.x, cnt); acc.y = __fdiv_rn(acc.y, cnt);
+        acc.z = __fdiv_rn(acc.z, cnt); acc.w = __fdiv_rn(acc.w, cnt);
+      }
+      st4(out + orow * ldo + 4 * q, acc);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_readout_fwd_scalar(const float* __restrict__ X, int64_t ldx, const int32_t* __restrict__ seg_ptr, int G, int D,
+                     int style, const int32_t* __restrict__ dst_row, float* __restrict__ out, int64_t ldo) {
+  const int gpb = blockDim.x / 32;
+  const int sub = threadIdx.x / 32, lane = threadIdx.x % 32;
+  for (int g = blockIdx.x * gpb + sub; g < G; g += gridDim.x * gpb) {
+    const int r0 = seg_ptr[g], r1 = seg_ptr[g + 1];
+    const int n = r1 - r0;
+    const int64_t orow = dst_row ? dst_row[g] : g;
+    for (int q = lane; q < D; q += 32) {
+      float acc = 0.f;
+      for (int r = r0; r < r1; ++r) acc += __ldg(X + (int64_t)r * ldx + q);
+      if (style == BIGNN_READOUT_MEAN) acc = __fdiv_rn(acc, (float)(n > 1 ? n : 1));
+      out[orow * ldo + q] = acc;
+    }
+  }
+}
+
+// dX[r, :] (+)= dOut[dst_row[g], :] / n      for every row r of graph g
+__global__ void __launch_bounds__(256)
+k_readout_bwd(const float* __restrict__ dOut, int64_t ldo, const int32_t* __restrict__ dst_row,
+              const int32_t* __restrict__ seg_ptr, int G, int D, int style, float* __restrict__ dX, int64_t lddx,
+              int accumulate) {
+  const int gpb = blockDim.x / 32;
+  const int sub = threadIdx.x / 32, lane = threadIdx.x % 32;
+  for (int g = blockIdx.x * gpb + sub; g < G; g += gridDim.x * gpb) {
+    const int r0 = seg_ptr[g], r1 = seg_ptr[g + 1];
+    const int n = r1 - r0;
+    const int64_t orow = dst_row ? dst_row[g] : g;
+    const float cnt = (float)(n > 1 ? n : 1);
+    for (int q = lane; q < D; q += 32) {
+      float v = __ldg(dOut + orow * ldo + q);
+      if (style == BIGNN_READOUT_MEAN) v = __fdiv_rn(v, cnt);
+      for (int r = r0; r < r1; ++r) {
+        float* p = dX + (int64_t)r * lddx + q;
+        *p = accumulate ? (*p + v) : v;
+      }
+    }
+  }
+}
+
+}  // namespace bignn
+
+using namespace bignn;
+
+extern "C" int bignn_readout_fwd(const float* X, int64_t ldx, const int32_t* seg_ptr, int32_t G, int32_t D,
+                                 int32_t style, const int32_t* dst_row, float* out, int64_t ldo,
+                                 int32_t col_off, void* stream) {
+  if (G < 0 || D < 0 || col_off < 0) return BIGNN_EINVAL;
+  if (G == 0 || D == 0) return 0;
+  if (!X || !seg_ptr || !out || ldx < D || ldo < col_off + D) return BIGNN_EINVAL;
+  if (style != BIGNN_READOUT_SUM && style != BIGNN_READOUT_MEAN) return BIGNN_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* o = out + col_off;
+  const int cap = sm_count() * 8;
+  const bool vec = (D % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0) && aligned16(X) && aligned16(o);
+  if (vec) {
+    const int d4 = D / 4;
+    if (d4 <= 16) {
+      int grid = ceil_div(G, 16);
+      if (grid > cap) grid = cap;
+      k_readout_fwd_v4<16><<<grid, 256, 0, st>>>(X, ldx, seg_ptr, G, d4, style, dst_row, o, ldo);
+    } else {
+      int grid = ceil_div(G, 8);
+      if (grid > cap) grid = cap;
+      k_readout_fwd_v4<32><<<grid, 256, 0, st>>>(X, ldx, seg_ptr, G, d4, style, dst_row, o, ldo);
+    }
+  } else {
+    int grid = ceil_div(G, 8);
+    if (grid > cap) grid = cap;
+    k_readout_fwd_scalar<<<grid, 256, 0, st>>>(X, ldx, seg_ptr, G, D, style, dst_row, o, ldo);
+  }
+  BIGNN_LAUNCH_COUNT(1);
+  return last_launch_status();
+}
+
+extern "C" int bignn_readout_bwd(const float* dOut, int64_t ldo, int32_t col_off, const int32_t* dst_row,
+                                 const int32_t* seg_ptr, int32_t G, int32_t D, int32_t style, float* dX,
+                                 int64_t lddx, int32_t accumulate, void* stream) {
+  if (G < 0 || D < 0 || col_off < 0) return BIGNN_EINVAL;
+  if (G == 0 || D == 0) return 0;
+  if (!dOut || !seg_ptr || !dX || lddx < D || ldo < col_off + D) return BIGNN_EINVAL;
+  if (style != BIGNN_READOUT_SUM && style != BIGNN_READOUT_MEAN) return BIGNN_EINVAL;
+  int grid = ceil_div(G, 8);
+  const int cap = sm_count() * 8;
+  if (grid > cap) grid = cap;
+  k_readout_bwd<<<grid, 256, 0, (cudaStream_t)stream>>>(dOut + col_off, ldo, dst_row, seg_ptr, G, D, style, dX, lddx, accumulate);
+  BIGNN_LAUNCH_COUNT(1);
+  return last_launch_status();
+}

@@ -1,0 +1,15 @@
+"""LoadInteractionGraph (model/layers_load_interaction_graph.py:7-21): hands the upper
+level its graph.  The reference rebuilds a PyG `Data` from networkx every forward; the
+train interaction graph never changes, so the CSR lives in HBM and only `x` is attached."""
+import torch.nn as nn
+
+
+class LoadInteractionGraph(nn.Module):
+    def __init__(self):
+        super().__init__()
+
+    def forward(self, x, batch_data, model):
+        assert hasattr(batch_data, 'interaction_combo_nxgraph')
+        ig = batch_data.interaction_combo_nxgraph
+        batch_data.merge_higher_level['merge'] = ig
+        return ig.init_x

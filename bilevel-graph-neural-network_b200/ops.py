@@ -1,0 +1,330 @@
+"""Operators of the Bi-GNN path: thin torch-tensor wrappers over the C-ABI plus the
+`torch.autograd.Function`s that give them a backward.  torch is plumbing here
+(device memory, streams, autograd tape); every arithmetic step is a kernel of
+`csrc/` reached through `_lib.call`.
+"""
+import torch
+
+from . import _lib
+
+ACT_CODES = {'identity': 0, 'relu': 1, 'sigmoid': 2, 'tanh': 3}
+SPMM_SUM, SPMM_GIN, SPMM_GCN = 0, 1, 2
+READOUT_CODES = {'sum': 0, 'avg_pool': 1}
+
+
+def act_code(name):
+    if name not in ACT_CODES:
+        raise ValueError('Unknown activation function {}'.format(name))
+    return ACT_CODES[name]
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        raise TypeError('bignn_b200 computes in fp32, got {}'.format(t.dtype))
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+class CSR(object):
+    """int32 CSR of a symmetric graph on the device (+ cached GCN deg^-1/2)."""
+
+    def __init__(self, row_ptr, col_idx, n_rows):
+        self.row_ptr, self.col_idx, self.n_rows = row_ptr, col_idx, int(n_rows)
+        self._dinv = None
+
+    @property
+    def nnz(self):
+        return int(self.col_idx.numel())
+
+    def dinv(self):
+        if self._dinv is None:
+            d = torch.empty(self.n_rows, dtype=torch.float32, device=self.row_ptr.device)
+            _lib.call('bignn_gcn_dinv', self.row_ptr, self.col_idx, self.n_rows, d)
+            self._dinv = d
+        return self._dinv
+
+
+# ----------------------------------------------------------------------------- raw ops
+def spmm(csr, x, mode, self_coef=0.0, dinv=None, bias=None, act=0, out=None):
+    x = _f32c(x)
+    _lib.require_device(x, csr.row_ptr)
+    n, d = csr.n_rows, x.shape[1]
+    y = out if out is not None else torch.empty((n, d), dtype=torch.float32, device=x.device)
+    _lib.call('bignn_spmm_f32', csr.row_ptr, csr.col_idx, x, x.stride(0), y, y.stride(0), n, d,
+              int(mode), float(self_coef), dinv, bias, int(act))
+    return y
+
+
+def gemm(a, b, ta=False, tb=False, bias=None, act=0, out=None):
+    """C = act(op(a) op(b) + bias);  op(a) is [M,K], op(b) is [K,N]."""
+    a, b = _f32c(a), _f32c(b)
+    _lib.require_device(a, b)
+    M, K = (a.shape[1], a.shape[0]) if ta else (a.shape[0], a.shape[1])
+    K2, N = (b.shape[1], b.shape[0]) if tb else (b.shape[0], b.shape[1])
+    if K != K2:
+        raise ValueError('gemm: inner dimensions differ ({} vs {})'.format(K, K2))
+    c = out if out is not None else torch.empty((M, N), dtype=torch.float32, device=a.device)
+    wsb = _lib.call('bignn_gemm_workspace_bytes', M, N, K, int(ta))
+    ws = _ws(wsb, a.device) if wsb > 0 else None
+    _lib.call('bignn_gemm_f32', int(ta), int(tb), M, N, K, a, a.stride(0), b, b.stride(0),
+              c, c.stride(0), bias, int(act), ws, int(wsb))
+    return c
+
+
+def colsum(x):
+    x = _f32c(x)
+    _lib.require_device(x)
+    rows, cols = x.shape
+    out = torch.empty(cols, dtype=torch.float32, device=x.device)
+    wsb = _lib.call('bignn_colsum_workspace_bytes', rows, cols)
+    ws = _ws(wsb, x.device)
+    _lib.call('bignn_colsum_f32', x, x.stride(0), rows, cols, out, ws, int(wsb))
+    return out
+
+
+def act_bwd(y, dy, act):
+    if act == 0:
+        return dy
+    y, dy = _f32c(y), _f32c(dy)
+    dx = torch.empty_like(dy)
+    _lib.call('bignn_act_bwd_f32', y, dy, dx, dy.numel(), int(act))
+    return dx
+
+
+def bn_parts(S, rows):
+    """Row parts per segment so that S*parts CTAs cover the SMs a few times."""
+    if S <= 0:
+        return 1
+    want = max(1, (148 * 4) // S)
+    by_rows = max(1, (rows // max(S, 1)) // 64)
+    return int(max(1, min(want, by_rows, 256)))
+
+
+# ----------------------------------------------------------------------------- autograd
+class _GinAggregate(torch.autograd.Function):
+    """z_i = (1+eps) x_i + sum_{j in N(i)} x_j  (PyG GINConv aggregation, App. A.1).
+    The graph is symmetric, so the backward is the same SpMM on the gradient."""
+
+    @staticmethod
+    def forward(ctx, x, csr, eps):
+        ctx.csr, ctx.eps = csr, float(eps)
+        return spmm(csr, x, SPMM_GIN, 1.0 + float(eps))
+
+    @staticmethod
+    def backward(ctx, dz):
+        return spmm(ctx.csr, dz, SPMM_GIN, 1.0 + ctx.eps), None, None
+
+
+class _GcnPropagate(torch.autograd.Function):
+    """u = act(D^-1/2 (A+I) D^-1/2 h + bias)  (PyG GCNConv propagate + model/layers.py:55)."""
+
+    @staticmethod
+    def forward(ctx, h, bias, csr, act):
+        u = spmm(csr, h, SPMM_GCN, 0.0, csr.dinv(), bias, act)
+        ctx.csr, ctx.act, ctx.has_bias = csr, act, bias is not None
+        ctx.save_for_backward(u)
+        return u
+
+    @staticmethod
+    def backward(ctx, du):
+        (u,) = ctx.saved_tensors
+        g = act_bwd(u, du, ctx.act)
+        dbias = colsum(g) if ctx.has_bias and ctx.needs_input_grad[1] else None
+        dh = spmm(ctx.csr, g, SPMM_GCN, 0.0, ctx.csr.dinv(), None, 0) if ctx.needs_input_grad[0] else None
+        return dh, dbias, None, None
+
+
+class _SumRows(torch.autograd.Function):
+    """out_i = sum_{e in rows(i)} x_e over an arbitrary (non-symmetric) CSR; used to add the
+    per-entry row gradients of the pair decoder per drug, deterministically."""
+
+    @staticmethod
+    def forward(ctx, x, csr):
+        return spmm(csr, x, SPMM_SUM)
+
+    @staticmethod
+    def backward(ctx, g):
+        raise NotImplementedError
+
+
+class _LinearAct(torch.autograd.Function):
+    """y = act(x W^T + b) (layout 'oi', nn.Linear) or act(x W + b) (layout 'io', PyG)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act, layout):
+        y = gemm(x, weight, False, layout == 'oi', bias, act)
+        ctx.act, ctx.layout = act, layout
+        ctx.save_for_backward(x, weight, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, y = ctx.saved_tensors
+        g = act_bwd(y, dy, ctx.act)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm(g, weight, False, ctx.layout == 'io')
+        if ctx.needs_input_grad[1]:
+            dw = gemm(g, x, True, False) if ctx.layout == 'oi' else gemm(x, g, True, False)
+        if ctx.needs_input_grad[2]:
+            db = colsum(g)
+        return dx, dw, db, None, None
+
+
+class _SegBatchNorm(torch.autograd.Function):
+    """Train-mode BatchNorm1d with independent statistics per row segment."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, seg_row_ptr, S, running_mean, running_var, nbt, eps, momentum):
+        x = _f32c(x)
+        _lib.require_device(x)
+        rows, C = x.shape
+        parts = bn_parts(S, rows)
+        y = torch.empty_like(x)
+        mean = torch.empty((S, C), dtype=torch.float32, device=x.device)
+        rstd = torch.empty((S, C), dtype=torch.float32, device=x.device)
+        wsb = _lib.call('bignn_bn_workspace_bytes', S, C, parts)
+        ws = _ws(wsb, x.device)
+        _lib.call('bignn_bn_seg_fwd', x, x.stride(0), y, y.stride(0), seg_row_ptr, S, C, parts, gamma, beta,
+                  float(eps), float(momentum), running_mean, running_var, nbt, mean, rstd, ws, int(wsb))
+        ctx.S, ctx.parts, ctx.seg = S, parts, seg_row_ptr
+        ctx.save_for_backward(x, gamma, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, mean, rstd = ctx.saved_tensors
+        dy = _f32c(dy)
+        rows, C = x.shape
+        dx = torch.empty_like(x)
+        dgamma = torch.empty(C, dtype=torch.float32, device=x.device)
+        dbeta = torch.empty(C, dtype=torch.float32, device=x.device)
+        wsb = _lib.call('bignn_bn_workspace_bytes', ctx.S, C, ctx.parts)
+        ws = _ws(wsb, x.device)
+        _lib.call('bignn_bn_seg_bwd', x, x.stride(0), dy, dy.stride(0), dx, dx.stride(0), ctx.seg, ctx.S, C,
+                  ctx.parts, gamma, mean, rstd, dgamma, dbeta, ws, int(wsb))
+        return dx, dgamma, dbeta, None, None, None, None, None, None, None
+
+
+class _Readout(torch.autograd.Function):
+    """Multi-scale segment readout: out[dst_row[g], l*D:(l+1)*D] = pool_l(acts_l[seg g])."""
+
+    @staticmethod
+    def forward(ctx, seg_ptr, G, style, dst_row, out_rows, *acts):
+        acts = [_f32c(a) for a in acts]
+        _lib.require_device(*acts)
+        D = acts[0].shape[1]
+        L = len(acts)
+        alloc = torch.zeros if dst_row is not None else torch.empty
+        out = alloc((out_rows, L * D), dtype=torch.float32, device=acts[0].device)
+        for l, a in enumerate(acts):
+            _lib.call('bignn_readout_fwd', a, a.stride(0), seg_ptr, G, D, style, dst_row, out, out.stride(0), l * D)
+        ctx.seg, ctx.G, ctx.style, ctx.dst_row, ctx.D = seg_ptr, G, style, dst_row, D
+        ctx.rows = [a.shape[0] for a in acts]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = _f32c(dout)
+        grads = []
+        for l, rows in enumerate(ctx.rows):
+            if not ctx.needs_input_grad[5 + l]:
+                grads.append(None)
+                continue
+            dx = torch.empty((rows, ctx.D), dtype=torch.float32, device=dout.device)
+            _lib.call('bignn_readout_bwd', dout, dout.stride(0), l * ctx.D, ctx.dst_row, ctx.seg, ctx.G, ctx.D,
+                      ctx.style, dx, dx.stride(0), 0)
+            grads.append(dx)
+        return (None, None, None, None, None) + tuple(grads)
+
+
+class _PairGatherNorm(torch.autograd.Function):
+    """z[p] = [normalize(h[ids[p,0]]) || normalize(h[ids[p,1]])]; the backward adds the
+    per-entry gradients per drug through the entry CSR (deterministic, no atomics)."""
+
+    @staticmethod
+    def forward(ctx, h, ids, entry_csr):
+        h = _f32c(h)
+        _lib.require_device(h, ids)
+        P, D = ids.shape[0], h.shape[1]
+        z = torch.empty((P, 2 * D), dtype=torch.float32, device=h.device)
+        nrm = torch.empty((P, 2), dtype=torch.float32, device=h.device)
+        _lib.call('bignn_pair_gather_norm_fwd', h, h.stride(0), ids, P, D, z, z.stride(0), nrm)
+        ctx.entry_csr = entry_csr
+        ctx.save_for_backward(h, ids, nrm)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        h, ids, nrm = ctx.saved_tensors
+        dz = _f32c(dz)
+        P, D = ids.shape[0], h.shape[1]
+        drows = torch.empty((2 * P, D), dtype=torch.float32, device=h.device)
+        _lib.call('bignn_pair_gather_norm_bwd', h, h.stride(0), ids, P, D, dz, dz.stride(0), nrm, drows,
+                  drows.stride(0))
+        dh = spmm(ctx.entry_csr, drows, SPMM_SUM)
+        return dh, None, None
+
+
+class _BCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, y, logits):
+        pred = _f32c(pred).view(-1)
+        y = _f32c(y).view(-1)
+        _lib.require_device(pred, y)
+        loss = torch.empty((), dtype=torch.float32, device=pred.device)
+        _lib.call('bignn_bce_logits_fwd' if logits else 'bignn_bce_fwd', pred, y, pred.numel(), loss)
+        ctx.logits = logits
+        ctx.save_for_backward(pred, y)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        pred, y = ctx.saved_tensors
+        dloss = _f32c(dloss)
+        dp = torch.empty_like(pred)
+        _lib.call('bignn_bce_logits_bwd' if ctx.logits else 'bignn_bce_bwd', pred, y, pred.numel(), dloss, dp)
+        return dp, None, None
+
+
+def gin_aggregate(x, csr, eps=0.0):
+    return _GinAggregate.apply(x, csr, eps)
+
+
+def gcn_propagate(h, bias, csr, act=0):
+    return _GcnPropagate.apply(h, bias, csr, act)
+
+
+def linear_act(x, weight, bias=None, act=0, layout='oi'):
+    return _LinearAct.apply(x, weight, bias, act, layout)
+
+
+def seg_batch_norm(x, gamma, beta, seg_row_ptr, S, running_mean, running_var, nbt, eps=1e-5, momentum=0.1):
+    return _SegBatchNorm.apply(x, gamma, beta, seg_row_ptr, S, running_mean, running_var, nbt, eps, momentum)
+
+
+def bn_eval(x, gamma, beta, running_mean, running_var, eps=1e-5):
+    x = _f32c(x)
+    _lib.require_device(x)
+    y = torch.empty_like(x)
+    _lib.call('bignn_bn_eval_fwd', x, x.stride(0), y, y.stride(0), x.shape[0], x.shape[1], gamma, beta,
+              float(eps), running_mean, running_var)
+    return y
+
+
+def readout(acts, seg_ptr, G, style='avg_pool', dst_row=None, out_rows=None):
+    if style not in READOUT_CODES:
+        raise NotImplementedError('{} is not implemented'.format(style))
+    return _Readout.apply(seg_ptr, int(G), READOUT_CODES[style], dst_row,
+                          int(out_rows if out_rows is not None else G), *acts)
+
+
+def pair_gather_norm(h, ids, entry_csr):
+    return _PairGatherNorm.apply(h, ids, entry_csr)
+
+
+def bce(pred, y, logits=False):
+    return _BCE.apply(pred, y, logits)

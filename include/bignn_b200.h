@@ -1,0 +1,199 @@
+/*
+ * bignn_b200.h -- C-ABI of the B200-native Bi-GNN bi-level message-passing path.
+ *
+ * Drop-in boundary: the Python layer classes behind the reference's
+ * model/layers_factory.py:179-190 `layer_ctors` registry call ONLY these entry
+ * points (through ctypes).  Plain pointers and sizes, no torch
+ * types.  Rules that hold for every function:
+ *   - all pointers are DEVICE pointers unless the name ends in _host;
+ *   - nothing is allocated inside: outputs and workspaces are caller-owned
+ *     (query sizes with the *_workspace_bytes functions);
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*), nothing
+ *     synchronises, so every call is CUDA-graph capturable;
+ *   - the return value is 0 on success, a positive cudaError_t, or a negative
+ *     BIGNN_E* code for argument errors (bignn_error_string() explains both);
+ *   - indices are int32 (CSR); int64 appears only in the COO `edge_index` view
+ *     the reference API exposes (src/merged_graph.py:60);
+ *   - features are fp32, row-major, leading dimension given in ELEMENTS.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative
+ * to the reference tree).
+ */
+#ifndef BIGNN_B200_H_
+#define BIGNN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BIGNN_ABI_VERSION 1
+
+/* argument errors */
+#define BIGNN_EINVAL   (-1)   /* bad size / null pointer / unsupported flag */
+#define BIGNN_EALIGN   (-2)   /* pointer or leading dimension not aligned as required */
+#define BIGNN_EWORKSPACE (-3) /* workspace too small */
+
+/* activations (model/layers_util.py:60-76 create_act) */
+#define BIGNN_ACT_IDENTITY 0
+#define BIGNN_ACT_RELU     1
+#define BIGNN_ACT_SIGMOID  2
+#define BIGNN_ACT_TANH     3
+
+/* spmm modes */
+#define BIGNN_SPMM_SUM   0  /* y_i = sum_{j in N(i)} x_j                                  */
+#define BIGNN_SPMM_GIN   1  /* y_i = self_coef*x_i + sum_{j in N(i), j!=i} x_j            (PyG GINConv)  */
+#define BIGNN_SPMM_GCN   2  /* y_i = sum_{j!=i} dinv_i dinv_j x_j + dinv_i^2 x_i (+bias)  (PyG GCNConv)  */
+
+/* readout styles (model/layers_aggregation.py:14-19) */
+#define BIGNN_READOUT_SUM  0
+#define BIGNN_READOUT_MEAN 1
+
+int bignn_abi_version(void);
+const char* bignn_error_string(int code);
+/* number of kernels launched by this library since load (bench.py gpu_launches) */
+int64_t bignn_launch_count(void);
+
+/* ---------------------------------------------------------------------------
+ * Merged-batch / CSR construction on the device.
+ * Replaces: src/batch.py:105-144 (_merge_into_one_graph), model/layers_util.py:100-166
+ * (convert_nx_to_pyg_graph / create_edge_index, per graph per step on the host) and
+ * src/merged_graph.py:27-96 (MergedGraphData.from_data_list).
+ *
+ * Packed dataset (resident in HBM, uploaded once): atom_ptr[N+1]; nbr_ptr[sumA+1]
+ * and nbr_idx[nnz] = per-graph LOCAL neighbour ids, atoms ascending, neighbours
+ * ascending (== the lexicographically sorted directed COO the reference builds);
+ * x_all[sumA, F].
+ * `rows[G]` = dataset rows of the graphs to merge, in merged order.
+ * Outputs (sizes A = sum of atoms, E = sum of directed edges, both known to the
+ * caller from its host copy of the pointers):
+ *   seg_ptr[G+1]  node offset of graph g   (reference ind_list[g] = (seg_ptr[g], seg_ptr[g+1]))
+ *   edge_ptr[G+1] edge offset of graph g   (reference edge_ind_list)
+ *   row_ptr[A+1], col_idx[E]               merged CSR (== COO sorted by (row,col))
+ *   batch[A]      graph id of every node   (reference `batch`, int32 here)
+ *   x[A, F]       gathered features        (may be NULL to skip)
+ *   edge_index_i64[2, E], batch_i64[A]     optional reference-typed views (NULL to skip)
+ * ------------------------------------------------------------------------- */
+int64_t bignn_merge_build_workspace_bytes(int32_t G);
+int bignn_merge_build(const int32_t* atom_ptr, const int32_t* nbr_ptr, const int32_t* nbr_idx,
+                      const float* x_all, int32_t F,
+                      const int32_t* rows, int32_t G,
+                      int32_t* seg_ptr, int32_t* edge_ptr,
+                      int32_t* row_ptr, int32_t* col_idx, int32_t* batch,
+                      float* x, int64_t* edge_index_i64, int64_t* batch_i64,
+                      int32_t A, int32_t E,
+                      void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Deterministic row-parallel segment SpMM (sub-warp per row, 128-bit gathers,
+ * neighbours accumulated in ascending order, no atomics).
+ * Replaces: PyG MessagePassing.propagate = index_select + torch-scatter scatter_add
+ * reached from model/layers.py:52-54 (GINConv / GCNConv), and -- because every
+ * graph on this path is symmetric -- its backward as well.
+ * dinv (GCN mode) = (1 + #non-self neighbours)^-1/2 from bignn_gcn_dinv.
+ * act is applied after bias (GCN forward: act(conv(x)) of model/layers.py:55).
+ * ------------------------------------------------------------------------- */
+int bignn_gcn_dinv(const int32_t* row_ptr, const int32_t* col_idx, int32_t n_rows,
+                   float* dinv, void* stream);
+int bignn_spmm_f32(const int32_t* row_ptr, const int32_t* col_idx,
+                   const float* X, int64_t ldx, float* Y, int64_t ldy,
+                   int32_t n_rows, int32_t D, int32_t mode, float self_coef,
+                   const float* dinv, const float* bias, int32_t act, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Dense fp32 transforms:  C[M,N] = act(op(A)[M,K] * op(B)[K,N] + bias[N])
+ * op(A) = A (ta=0, A is [M,K]) or A^T (ta=1, A is [K,M]); same for B.
+ * Replaces: nn.Linear inside the GIN MLP (model/layers.py:26-30) and MLP
+ * (model/layers_util.py:28-33), `x @ weight` of GCNConv/GATConv, and their
+ * autograd backward (dX = dY W, dW = dY^T X with a deterministic split-K over the
+ * row dimension).  fp32 FMA accumulation -- the 1e-5 parity target rules out
+ * single-pass TF32.
+ * ------------------------------------------------------------------------- */
+int64_t bignn_gemm_workspace_bytes(int32_t M, int32_t N, int32_t K, int32_t ta);
+int bignn_gemm_f32(int32_t ta, int32_t tb, int32_t M, int32_t N, int32_t K,
+                   const float* A, int64_t lda, const float* B, int64_t ldb,
+                   float* C, int64_t ldc, const float* bias, int32_t act,
+                   void* workspace, int64_t workspace_bytes, void* stream);
+/* column sums out[c] = sum_r X[r,c]  (bias gradients), deterministic */
+int64_t bignn_colsum_workspace_bytes(int32_t rows, int32_t cols);
+int bignn_colsum_f32(const float* X, int64_t ldx, int32_t rows, int32_t cols, float* out,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+/* dX = dY * act'(Y) elementwise from the activation OUTPUT Y (relu/sigmoid/tanh/identity) */
+int bignn_act_bwd_f32(const float* Y, const float* dY, float* dX, int64_t n, int32_t act,
+                      void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Segmented train-mode BatchNorm1d: rows [seg_row_ptr[s], seg_row_ptr[s+1]) form
+ * one independent batch (one 128-graph chunk of the all-drug pass, src/train.py:62-71),
+ * so a whole all-drug pass is normalised in one launch with the reference's
+ * per-chunk statistics.  Replaces torch.nn.BatchNorm1d at model/layers.py:57.
+ * Statistics are accumulated in fp64, biased variance for normalisation;
+ * running buffers are updated sequentially in segment order with the unbiased
+ * variance (momentum, as torch).  mean/rstd are [S, C] and are what backward needs.
+ * ------------------------------------------------------------------------- */
+int64_t bignn_bn_workspace_bytes(int32_t S, int32_t C, int32_t parts);
+int bignn_bn_seg_fwd(const float* X, int64_t ldx, float* Y, int64_t ldy,
+                     const int32_t* seg_row_ptr, int32_t S, int32_t C, int32_t parts,
+                     const float* gamma, const float* beta, float eps, float momentum,
+                     float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                     float* mean, float* rstd,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+/* eval mode: normalise with the running buffers (one launch, no statistics) */
+int bignn_bn_eval_fwd(const float* X, int64_t ldx, float* Y, int64_t ldy, int32_t rows, int32_t C,
+                      const float* gamma, const float* beta, float eps,
+                      const float* running_mean, const float* running_var, void* stream);
+/* dX, and dgamma/dbeta ACCUMULATED over segments in segment order (written, not added) */
+int bignn_bn_seg_bwd(const float* X, int64_t ldx, const float* dY, int64_t lddy,
+                     float* dX, int64_t lddx,
+                     const int32_t* seg_row_ptr, int32_t S, int32_t C, int32_t parts,
+                     const float* gamma, const float* mean, const float* rstd,
+                     float* dgamma, float* dbeta,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Segment readout (atoms -> one row per drug), rows summed in ascending order.
+ * Replaces torch-scatter scatter_mean / scatter_add at
+ * model/layers_aggregation.py:17-19,34-41 and the per-row Python scatter into
+ * init_x at :70-74 (dst_row[g] = gs_map row; NULL = identity).
+ * out[dst_row[g], col_off : col_off+D] = pool(X[seg_ptr[g]:seg_ptr[g+1], :]).
+ * ------------------------------------------------------------------------- */
+int bignn_readout_fwd(const float* X, int64_t ldx, const int32_t* seg_ptr, int32_t G, int32_t D,
+                      int32_t style, const int32_t* dst_row,
+                      float* out, int64_t ldo, int32_t col_off, void* stream);
+int bignn_readout_bwd(const float* dOut, int64_t ldo, int32_t col_off, const int32_t* dst_row,
+                      const int32_t* seg_ptr, int32_t G, int32_t D, int32_t style,
+                      float* dX, int64_t lddx, int32_t accumulate, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Pair decoder front end: Z[p, 0:D] = H[id1[p]]/max(|H[id1[p]]|,1e-12), Z[p, D:2D]
+ * likewise for id2 (F.normalize + gather + concat of model/layers_link_pred.py:44-61;
+ * only the gathered rows are normalised -- same values).  inv_norm[P,2] is saved
+ * for backward.  Backward produces per-entry row gradients dRows[2P, D]
+ * (entry e = 2p+side) which the caller sums per drug with bignn_spmm_f32(SUM)
+ * over the entry CSR -- deterministic, no atomics.
+ * ------------------------------------------------------------------------- */
+int bignn_pair_gather_norm_fwd(const float* H, int64_t ldh, const int32_t* ids /*[P,2]*/,
+                               int32_t P, int32_t D, float* Z, int64_t ldz, float* inv_norm,
+                               void* stream);
+int bignn_pair_gather_norm_bwd(const float* H, int64_t ldh, const int32_t* ids, int32_t P, int32_t D,
+                               const float* dZ, int64_t lddz, const float* inv_norm,
+                               float* dRows, int64_t lddr, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Loss heads (model/layers.py:66-89): nn.BCELoss (mean, log clamped at -100) on the
+ * sigmoid outputs of LinkPred (model/layers_link_pred.py:65; the sigmoid itself is
+ * the activation epilogue of the last decoder GEMM), and nn.BCEWithLogitsLoss.
+ * *loss is a device scalar; bwd takes the upstream scalar gradient *dloss (device).
+ * ------------------------------------------------------------------------- */
+int bignn_bce_fwd(const float* pred, const float* y, int32_t P, float* loss, void* stream);
+int bignn_bce_bwd(const float* pred, const float* y, int32_t P, const float* dloss, float* dpred,
+                  void* stream);
+int bignn_bce_logits_fwd(const float* x, const float* y, int32_t P, float* loss, void* stream);
+int bignn_bce_logits_bwd(const float* x, const float* y, int32_t P, const float* dloss, float* dx,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BIGNN_B200_H_ */

@@ -1,0 +1,215 @@
+"""TEST INFRASTRUCTURE ONLY: a torch-CPU stand-in for the C-ABI entry points, used by the
+`-m "not gpu"` tests to exercise the HOST logic of bignn_b200 (argument plumbing, autograd
+wiring, chunk/segment bookkeeping) in a container without a GPU.  It is injected with
+`install()` into `bignn_b200._lib` by tests only; the product never imports it, and on a GPU
+box the real library is the only backend (tests marked `gpu` never install it).
+It doubles as an executable statement of what each entry point of include/bignn_b200.h
+must compute."""
+import torch
+
+
+def _rows(t, ld, n, d):
+    return torch.as_strided(t, (n, d), (ld, 1), t.storage_offset()) if t.dim() != 2 or t.stride(0) != ld else t[:n, :d]
+
+
+ACTS = {0: lambda v: v, 1: torch.relu, 2: torch.sigmoid, 3: torch.tanh}
+
+
+class Fake(object):
+    def call(self, name, *a):
+        return getattr(self, name)(*a)
+
+    def bignn_merge_build_workspace_bytes(self, G):
+        return 16
+
+    def bignn_gemm_workspace_bytes(self, M, N, K, ta):
+        return 0
+
+    def bignn_colsum_workspace_bytes(self, r, c):
+        return 16
+
+    def bignn_bn_workspace_bytes(self, S, C, parts):
+        return 16
+
+    def bignn_merge_build(self, atom_ptr, nbr_ptr, nbr_idx, x_all, F, rows, G, seg_ptr, edge_ptr, row_ptr,
+                          col_idx, batch, x, ei, b64, A, E, ws, wsb):
+        cn = ce = 0
+        for g in range(G):
+            r = int(rows[g])
+            a0, a1 = int(atom_ptr[r]), int(atom_ptr[r + 1])
+            e0, e1 = int(nbr_ptr[a0]), int(nbr_ptr[a1])
+            n, e = a1 - a0, e1 - e0
+            seg_ptr[g], edge_ptr[g] = cn, ce
+            row_ptr[cn:cn + n] = nbr_ptr[a0:a1] - e0 + ce
+            col_idx[ce:ce + e] = nbr_idx[e0:e1] + cn
+            if batch is not None:
+                batch[cn:cn + n] = g
+            if b64 is not None:
+                b64[cn:cn + n] = g
+            if x is not None:
+                x[cn:cn + n] = x_all[a0:a1]
+            if ei is not None:
+                cnt = (nbr_ptr[a0 + 1:a1 + 1] - nbr_ptr[a0:a1]).long()
+                ei[0, ce:ce + e] = torch.repeat_interleave(torch.arange(n), cnt) + cn
+                ei[1, ce:ce + e] = nbr_idx[e0:e1].long() + cn
+            cn += n
+            ce += e
+        seg_ptr[G], edge_ptr[G], row_ptr[cn] = cn, ce, ce
+        return 0
+
+    @staticmethod
+    def _coo(row_ptr, col_idx, n):
+        cnt = (row_ptr[1:n + 1] - row_ptr[:n]).long()
+        return torch.repeat_interleave(torch.arange(n), cnt), col_idx.long()
+
+    def bignn_gcn_dinv(self, row_ptr, col_idx, n, dinv):
+        r, c = self._coo(row_ptr, col_idx, n)
+        deg = torch.ones(n).index_add_(0, r[r != c], torch.ones(int((r != c).sum())))
+        dinv.copy_(deg.pow(-0.5))
+        return 0
+
+    def bignn_spmm_f32(self, row_ptr, col_idx, X, ldx, Y, ldy, n, D, mode, self_coef, dinv, bias, act):
+        r, c = self._coo(row_ptr, col_idx, n)
+        if mode != 0:
+            keep = r != c
+            r, c = r[keep], c[keep]
+        src = X[c][:, :D]
+        if mode == 2:
+            src = (dinv[c] * dinv[r]).view(-1, 1) * src
+        out = torch.zeros(n, D).index_add_(0, r, src)
+        if mode == 1:
+            out = self_coef * X[:n, :D] + out
+        elif mode == 2:
+            out = out + (dinv[:n] * dinv[:n]).view(-1, 1) * X[:n, :D]
+        if bias is not None:
+            out = out + bias
+        Y[:n, :D] = ACTS[act](out)
+        return 0
+
+    def bignn_gemm_f32(self, ta, tb, M, N, K, A, lda, B, ldb, C, ldc, bias, act, ws, wsb):
+        a = A.t() if ta else A
+        b = B.t() if tb else B
+        out = a @ b
+        if bias is not None:
+            out = out + bias
+        C[:M, :N] = ACTS[act](out)
+        return 0
+
+    def bignn_colsum_f32(self, X, ldx, rows, cols, out, ws, wsb):
+        out.copy_(X.double().sum(0).float())
+        return 0
+
+    def bignn_act_bwd_f32(self, Y, dY, dX, n, act):
+        if act == 1:
+            dX.copy_(dY * (Y > 0))
+        elif act == 2:
+            dX.copy_(dY * ((1 - Y) * Y))
+        elif act == 3:
+            dX.copy_(dY * (1 - Y * Y))
+        else:
+            dX.copy_(dY)
+        return 0
+
+    def bignn_bn_seg_fwd(self, X, ldx, Y, ldy, seg, S, C, parts, gamma, beta, eps, mom, rm, rv, nbt, mean, rstd,
+                         ws, wsb):
+        for s in range(S):
+            a, b = int(seg[s]), int(seg[s + 1])
+            x = X[a:b].double()
+            n = b - a
+            mu = x.mean(0)
+            var = (x * x).mean(0) - mu * mu
+            mean[s] = mu.float()
+            rstd[s] = (1.0 / torch.sqrt(var + eps)).float()
+            if rm is not None:
+                rm.copy_((mom * mu + (1 - mom) * rm.double()).float())
+                rv.copy_((mom * var * n / max(n - 1, 1) + (1 - mom) * rv.double()).float())
+                if nbt is not None:
+                    nbt += 1
+            alpha = rstd[s] * gamma
+            Y[a:b] = X[a:b] * alpha + (beta - mean[s] * alpha)
+        return 0
+
+    def bignn_bn_eval_fwd(self, X, ldx, Y, ldy, rows, C, gamma, beta, eps, rm, rv):
+        alpha = (1.0 / torch.sqrt(rv.double() + eps)).float() * gamma
+        Y.copy_(X * alpha + (beta - rm * alpha))
+        return 0
+
+    def bignn_bn_seg_bwd(self, X, ldx, dY, lddy, dX, lddx, seg, S, C, parts, gamma, mean, rstd, dgamma, dbeta,
+                         ws, wsb):
+        dg = torch.zeros(C, dtype=torch.float64)
+        db = torch.zeros(C, dtype=torch.float64)
+        for s in range(S):
+            a, b = int(seg[s]), int(seg[s + 1])
+            n = b - a
+            xhat = (X[a:b] - mean[s]) * rstd[s]
+            g = dY[a:b]
+            sa = g.double().sum(0)
+            sb = (g.double() * xhat.double()).sum(0)
+            db += sa
+            dg += sb
+            dX[a:b] = (g - (sa / n).float() - xhat * (sb / n).float()) * (rstd[s] * gamma)
+        dgamma.copy_(dg.float())
+        dbeta.copy_(db.float())
+        return 0
+
+    def bignn_readout_fwd(self, X, ldx, seg, G, D, style, dst_row, out, ldo, col_off):
+        for g in range(G):
+            a, b = int(seg[g]), int(seg[g + 1])
+            v = X[a:b, :D].sum(0)
+            if style == 1:
+                v = v / max(b - a, 1)
+            out[int(dst_row[g]) if dst_row is not None else g, col_off:col_off + D] = v
+        return 0
+
+    def bignn_readout_bwd(self, dOut, ldo, col_off, dst_row, seg, G, D, style, dX, lddx, accumulate):
+        for g in range(G):
+            a, b = int(seg[g]), int(seg[g + 1])
+            v = dOut[int(dst_row[g]) if dst_row is not None else g, col_off:col_off + D]
+            if style == 1:
+                v = v / max(b - a, 1)
+            if accumulate:
+                dX[a:b, :D] += v
+            else:
+                dX[a:b, :D] = v
+        return 0
+
+    def bignn_pair_gather_norm_fwd(self, H, ldh, ids, P, D, Z, ldz, nrm):
+        h = H[ids.long().view(-1)]
+        n = h.norm(dim=1).clamp(min=1e-12)
+        nrm.view(-1).copy_(n)
+        Z.copy_((h / n.view(-1, 1)).view(P, 2 * D))
+        return 0
+
+    def bignn_pair_gather_norm_bwd(self, H, ldh, ids, P, D, dZ, lddz, nrm, dRows, lddr):
+        h = H[ids.long().view(-1)]
+        n = nrm.view(-1, 1)
+        zh = h / n
+        dz = dZ.reshape(2 * P, D)
+        dRows.copy_((dz - zh * (dz * zh).sum(1, keepdim=True)) / n)
+        return 0
+
+    def bignn_bce_fwd(self, pred, y, P, loss):
+        loss.copy_(torch.nn.functional.binary_cross_entropy(pred, y))
+        return 0
+
+    def bignn_bce_bwd(self, pred, y, P, dloss, dpred):
+        dpred.copy_(dloss / P * (pred - y) / ((1 - pred) * pred).clamp(min=1e-12))
+        return 0
+
+    def bignn_bce_logits_fwd(self, x, y, P, loss):
+        loss.copy_(torch.nn.functional.binary_cross_entropy_with_logits(x, y))
+        return 0
+
+    def bignn_bce_logits_bwd(self, x, y, P, dloss, dx):
+        dx.copy_((torch.sigmoid(x) - y) * dloss / P)
+        return 0
+
+
+def install():
+    import bignn_b200
+    bignn_b200._lib._backend_override = Fake()
+
+
+def uninstall():
+    import bignn_b200
+    bignn_b200._lib._backend_override = None

@@ -1,0 +1,317 @@
+"""Parity tests proper (`-m gpu`): every C-ABI entry point, called through the real CUDA
+library on a B200, against the CPU oracle (oracle/bignn_oracle.py, plain torch fp32/fp64) on the
+same seeded inputs.  Integer/index outputs must be bit-exact; fp32 outputs are compared with the
+tolerance written at each assert."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import bignn_b200 as B
+from bignn_b200 import ops
+from oracle import bignn_oracle as O
+
+DEV = 'cuda:0'
+
+
+def rel(a, b):
+    a = np.asarray(a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else a, np.float64)
+    b = np.asarray(b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.fixture(scope='module')
+def data(golden_dir):
+    assert torch.cuda.is_available()
+    B._lib.load()
+    B.set_flags(B.make_flags(device=DEV))
+    return B.BiGNNData.from_npz(os.path.join(golden_dir, 'drugbank_packed.npz'), device=DEV)
+
+
+def random_sym_csr(n, avg_deg, seed, self_loops=False):
+    rng = np.random.default_rng(seed)
+    m = int(n * avg_deg / 2)
+    a = rng.integers(0, n, m)
+    b = rng.integers(0, n, m)
+    if not self_loops:
+        keep = a != b
+        a, b = a[keep], b[keep]
+    key = np.unique(np.concatenate([a * n + b, b * n + a]))
+    row, col = key // n, key % n
+    return row, col
+
+
+# ----------------------------------------------------------------------------- merge
+@pytest.mark.parametrize('chunk', [0, 10])
+def test_merge_build_bit_exact_vs_reference_chunks(data, drugbank, step_golden, chunk):
+    z = step_golden
+    gids = z['chunk%d/gids' % chunk]
+    rows = [data.gs_map[int(g)] for g in gids]
+    m = B.MergedGraph(data.packed, rows)
+    assert np.array_equal(m.edge_index.cpu().numpy(), z['chunk%d/edge_index' % chunk].astype(np.int64))
+    assert np.array_equal(m.batch.cpu().numpy(), z['chunk%d/batch' % chunk].astype(np.int64))
+    assert np.array_equal(m.x.cpu().numpy(), z['chunk%d/x_u8' % chunk].astype(np.float32))
+    il = z['chunk%d/ind_list' % chunk]
+    assert np.array_equal(m.seg_ptr.cpu().numpy(), np.concatenate([il[:, 0], il[-1:, 1]]))
+    el = z['chunk%d/edge_ind_list' % chunk]
+    assert np.array_equal(m.edge_ptr.cpu().numpy(), np.concatenate([el[:, 0], el[-1:, 1]]))
+    assert np.array_equal(np.diff(m.seg_ptr.cpu().numpy()), z['chunk%d/graph_sizes' % chunk])
+
+
+@pytest.mark.parametrize('G,seed', [(1, 0), (2, 1), (1309, 2), (1025, 3), (5000, 4), (70000, 5)])
+def test_merge_build_bit_exact_vs_oracle(data, drugbank, G, seed):
+    rng = np.random.default_rng(seed)
+    rows = rng.integers(0, drugbank.N, G) if G != 1309 else np.arange(1309)
+    m = B.MergedGraph(data.packed, rows)
+    o = O.merge_graphs(drugbank, drugbank.gids[rows])
+    assert np.array_equal(m.edge_index.cpu().numpy(), o['edge_index'])
+    assert np.array_equal(m.batch.cpu().numpy(), o['batch'])
+    assert np.array_equal(m.x.cpu().numpy(), o['x'])
+    assert np.array_equal(m.seg_ptr.cpu().numpy()[:-1], o['ind_list'][:, 0])
+    assert np.array_equal(m.edge_ptr.cpu().numpy()[:-1], o['edge_ind_list'][:, 0])
+    # CSR view == sorted COO
+    rp = m.row_ptr.cpu().numpy()
+    assert rp[0] == 0 and rp[-1] == m.E
+    assert np.array_equal(np.repeat(np.arange(m.A), np.diff(rp)), o['edge_index'][0])
+    assert np.array_equal(m.col_idx.cpu().numpy(), o['edge_index'][1])
+
+
+def test_merge_build_empty(data):
+    m = B.MergedGraph(data.packed, [])
+    assert m.A == 0 and m.E == 0
+    assert m.seg_ptr.cpu().tolist() == [0] and m.row_ptr.cpu().tolist() == [0]
+
+
+# ----------------------------------------------------------------------------- spmm
+def csr_from_coo(row, col, n):
+    ptr = np.zeros(n + 1, np.int64)
+    np.add.at(ptr, row + 1, 1)
+    return ops.CSR(torch.as_tensor(np.cumsum(ptr).astype(np.int32)).to(DEV),
+                   torch.as_tensor(col.astype(np.int32)).to(DEV), n)
+
+
+@pytest.mark.parametrize('n,deg,D,self_loops', [(1000, 2.2, 64, False), (777, 2.2, 49, False), (500, 40, 320, False),
+                                                (300, 5, 32, True), (200, 3, 16, False), (100, 3, 7, True),
+                                                (64, 6, 512, False), (64, 6, 516, False), (50, 4, 130, False)])
+def test_spmm_gin_bit_exact(n, deg, D, self_loops):
+    row, col = random_sym_csr(n, deg, n + D, self_loops)
+    csr = csr_from_coo(row, col, n)
+    g = torch.Generator().manual_seed(D)
+    x = torch.randn(n, D, generator=g)
+    ei = torch.from_numpy(np.stack([row, col]))
+    keep = ei[0] != ei[1]
+    agg = torch.zeros(n, D).index_add_(0, ei[1][keep], x[ei[0][keep]])
+    want = 1.25 * x + agg
+    got = ops.spmm(csr, x.to(DEV), ops.SPMM_GIN, 1.25)
+    # same neighbour order, unfused adds: identical bits
+    assert torch.equal(got.cpu(), want)
+    got_sum = ops.spmm(csr, x.to(DEV), ops.SPMM_SUM)
+    assert torch.equal(got_sum.cpu(), torch.zeros(n, D).index_add_(0, ei[1], x[ei[0]]))
+
+
+@pytest.mark.parametrize('D,act', [(64, 'relu'), (64, 'identity'), (49, 'tanh'), (320, 'sigmoid')])
+def test_spmm_gcn_vs_oracle(data, drugbank, D, act):
+    g = torch.Generator().manual_seed(D)
+    n = drugbank.N
+    h = torch.randn(n, D, generator=g)
+    bias = torch.randn(D, generator=g)
+    P = {'l.conv.weight': torch.eye(D), 'l.conv.bias': bias}
+    ei = torch.from_numpy(np.stack([drugbank.ddi_row, drugbank.ddi_col]))
+    want = O._act(act, O.gcn_conv(h, ei, P, 'l'))
+    csr = data.interaction_combo_nxgraph.csr
+    got = ops.spmm(csr, h.to(DEV), ops.SPMM_GCN, 0.0, csr.dinv(), bias.to(DEV), ops.act_code(act))
+    assert rel(got, want) < 2e-6
+    # deg^-1/2 itself is bit-exact
+    row, col = ei
+    deg = torch.zeros(n).index_add_(0, row, torch.ones(row.shape[0])) + 1
+    assert torch.equal(csr.dinv().cpu(), deg.pow(-0.5))
+
+
+def test_spmm_is_its_own_transpose_at_scale():
+    """size-independent property on a >L2 operand: <y, A x> == <A y, x> for a symmetric graph,
+    and A*ones == degree (+ self coefficient) exactly."""
+    n, D = 2_000_000, 64
+    row, col = random_sym_csr(n, 2.2, 7)
+    csr = csr_from_coo(row, col, n)
+    g = torch.Generator(device=DEV).manual_seed(1)
+    x = torch.randn(n, D, device=DEV, generator=g)
+    y = torch.randn(n, D, device=DEV, generator=g)
+    ax = ops.spmm(csr, x, ops.SPMM_GIN, 1.0)
+    ay = ops.spmm(csr, y, ops.SPMM_GIN, 1.0)
+    a = (y.double() * ax.double()).sum().item()
+    b = (ay.double() * x.double()).sum().item()
+    assert abs(a - b) < 1e-9 * max(1.0, abs(a))
+    ones = torch.ones(n, D, device=DEV)
+    deg = torch.as_tensor(np.bincount(row, minlength=n).astype(np.float32)).to(DEV)
+    assert torch.equal(ops.spmm(csr, ones, ops.SPMM_GIN, 1.0), (deg + 1).view(-1, 1).expand(n, D))
+
+
+# ----------------------------------------------------------------------------- dense
+@pytest.mark.parametrize('ta,tb,M,N,K', [(0, 1, 3712, 64, 49), (0, 1, 3712, 64, 64), (0, 0, 1309, 64, 320),
+                                         (0, 0, 100, 49, 64), (0, 1, 128, 16, 128), (0, 1, 128, 1, 2),
+                                         (1, 0, 64, 49, 36816), (1, 0, 320, 64, 1309), (1, 1, 33, 17, 65),
+                                         (0, 1, 1, 1, 1), (1, 0, 64, 64, 700)])
+def test_gemm_vs_torch(ta, tb, M, N, K):
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn((K, M) if ta else (M, K), generator=g)
+    b = torch.randn((N, K) if tb else (K, N), generator=g)
+    bias = torch.randn(N, generator=g)
+    want = (a.double().t() if ta else a.double()) @ (b.double().t() if tb else b.double())
+    got = ops.gemm(a.to(DEV), b.to(DEV), bool(ta), bool(tb))
+    # fp32 FMA accumulation against an fp64 product: K * 2^-24 worst case, sqrt(K) typical
+    assert rel(got, want) < 2e-6 * max(1.0, np.sqrt(K) / 8)
+    got2 = ops.gemm(a.to(DEV), b.to(DEV), bool(ta), bool(tb), bias.to(DEV), ops.ACT_CODES['relu'])
+    assert rel(got2, torch.relu(want + bias.double())) < 2e-6 * max(1.0, np.sqrt(K) / 8)
+
+
+def test_gemm_is_deterministic_with_split_k():
+    g = torch.Generator().manual_seed(0)
+    a = torch.randn(36816, 64, generator=g).to(DEV)
+    b = torch.randn(36816, 49, generator=g).to(DEV)
+    r1 = ops.gemm(a, b, True, False)
+    r2 = ops.gemm(a, b, True, False)
+    assert torch.equal(r1, r2)
+
+
+def test_colsum_and_act_bwd():
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(36816, 64, generator=g)
+    assert rel(ops.colsum(x.to(DEV)), x.double().sum(0)) < 1e-6
+    x = torch.randn(5, 3, generator=g)
+    assert rel(ops.colsum(x.to(DEV)), x.double().sum(0)) < 1e-6
+    for name in ('relu', 'sigmoid', 'tanh', 'identity'):
+        pre = torch.randn(1000, 64, generator=g, requires_grad=True)
+        y = O._act(name, pre)
+        dy = torch.randn(1000, 64, generator=g)
+        y.backward(dy)
+        got = ops.act_bwd(y.detach().to(DEV), dy.to(DEV), ops.act_code(name))
+        assert rel(got, pre.grad) < 1e-6
+
+
+def test_linear_act_autograd():
+    g = torch.Generator().manual_seed(5)
+    for layout in ('oi', 'io'):
+        x = torch.randn(3040, 49, generator=g, requires_grad=True)
+        w = torch.randn((64, 49) if layout == 'oi' else (49, 64), generator=g, requires_grad=True)
+        b = torch.randn(64, generator=g, requires_grad=True)
+        y = torch.relu((x @ w.t() if layout == 'oi' else x @ w) + b)
+        dy = torch.randn(3040, 64, generator=g)
+        y.backward(dy)
+        xd, wd, bd = (t.detach().to(DEV).requires_grad_(True) for t in (x, w, b))
+        yd = ops.linear_act(xd, wd, bd, ops.ACT_CODES['relu'], layout)
+        yd.backward(dy.to(DEV))
+        assert rel(yd, y) < 2e-6
+        assert rel(xd.grad, x.grad) < 5e-6
+        assert rel(wd.grad, w.grad) < 5e-6
+        assert rel(bd.grad, b.grad) < 5e-6
+
+
+# ----------------------------------------------------------------------------- batch norm
+@pytest.mark.parametrize('sizes,C', [([3712, 3040, 817], 64), ([1309], 64), ([5, 2, 900, 33], 49), ([200000], 64)])
+def test_seg_batch_norm_vs_torch(sizes, C):
+    g = torch.Generator().manual_seed(len(sizes) * 100 + C)
+    n = sum(sizes)
+    x = (torch.randn(n, C, generator=g) * 2 + 1).relu()
+    gamma = torch.rand(C, generator=g) + 0.5
+    beta = torch.randn(C, generator=g)
+    dy = torch.randn(n, C, generator=g)
+    ptr = np.concatenate([[0], np.cumsum(sizes)])
+    # reference: torch BatchNorm1d applied chunk by chunk, in order
+    bn = torch.nn.BatchNorm1d(C)
+    with torch.no_grad():
+        bn.weight.copy_(gamma)
+        bn.bias.copy_(beta)
+    xr = x.clone().requires_grad_(True)
+    outs = [bn(xr[ptr[i]:ptr[i + 1]]) for i in range(len(sizes))]
+    want = torch.cat(outs)
+    want.backward(dy)
+    rm = torch.zeros(C, device=DEV)
+    rv = torch.ones(C, device=DEV)
+    nbt = torch.zeros((), dtype=torch.int64, device=DEV)
+    xd = x.to(DEV).requires_grad_(True)
+    gd = gamma.to(DEV).requires_grad_(True)
+    bd = beta.to(DEV).requires_grad_(True)
+    seg = torch.as_tensor(ptr.astype(np.int32)).to(DEV)
+    got = ops.seg_batch_norm(xd, gd, bd, seg, len(sizes), rm, rv, nbt)
+    got.backward(dy.to(DEV))
+    assert rel(got, want) < 2e-6
+    assert rel(rm, bn.running_mean) < 1e-6 and rel(rv, bn.running_var) < 1e-6
+    assert int(nbt) == int(bn.num_batches_tracked)
+    assert rel(xd.grad, xr.grad) < 2e-5
+    assert rel(gd.grad, bn.weight.grad) < 5e-6 and rel(bd.grad, bn.bias.grad) < 5e-6
+    # eval mode
+    bn.eval()
+    assert rel(ops.bn_eval(x.to(DEV), gd.detach(), bd.detach(), rm, rv), bn(x)) < 2e-6
+
+
+# ----------------------------------------------------------------------------- readout
+@pytest.mark.parametrize('style', ['avg_pool', 'sum'])
+@pytest.mark.parametrize('D', [64, 49])
+def test_readout_vs_oracle(data, drugbank, style, D):
+    rows = np.arange(200)
+    m = B.MergedGraph(data.packed, rows)
+    g = torch.Generator().manual_seed(D)
+    acts = [torch.randn(m.A, D, generator=g, requires_grad=True) for _ in range(3)]
+    batch = torch.from_numpy(np.repeat(np.arange(200), np.diff(m.seg_ptr_host)))
+    want = O.readout(acts, batch, 200, style)
+    dout = torch.randn(200, 3 * D, generator=g)
+    want.backward(dout)
+    actd = [a.detach().to(DEV).requires_grad_(True) for a in acts]
+    got = ops.readout(actd, m.seg_ptr, 200, style)
+    got.backward(dout.to(DEV))
+    assert rel(got, want) < 1e-6
+    for a, b in zip(actd, acts):
+        assert rel(a.grad, b.grad) < 1e-6
+    # scatter to dataset rows
+    perm = torch.randperm(300, generator=g)[:200]
+    got2 = ops.readout([a.detach() for a in actd], m.seg_ptr, 200, style,
+                       perm.to(torch.int32).to(DEV), 300)
+    assert torch.equal(got2[perm.to(DEV)], got.detach())
+
+
+# ----------------------------------------------------------------------------- decoder
+def test_pair_decoder_and_bce_vs_torch():
+    g = torch.Generator().manual_seed(11)
+    N, D, P = 1309, 64, 128
+    h = torch.randn(N, D, generator=g, requires_grad=True)
+    ids = torch.randint(0, 120, (P, 2), generator=g)           # heavy row reuse, like a pair batch
+    y = (torch.rand(P, generator=g) > 0.5).float()
+    w = torch.randn(1, 2 * D, generator=g) * 0.1
+    hn = torch.nn.functional.normalize(h, p=2, dim=1)
+    z = torch.cat([hn[ids[:, 0]], hn[ids[:, 1]]], 1)
+    pred = torch.sigmoid(z @ w.t()).view(-1)
+    loss = torch.nn.functional.binary_cross_entropy(pred, y)
+    loss.backward()
+    hd = h.detach().to(DEV).requires_grad_(True)
+    ecsr = B.graph.entry_csr(ids.numpy(), N, DEV)
+    zd = ops.pair_gather_norm(hd, ids.to(torch.int32).to(DEV), ecsr)
+    pd = ops.linear_act(zd, w.to(DEV), None, ops.ACT_CODES['sigmoid'], 'oi')
+    ld = ops.bce(pd.view(-1), y.to(DEV))
+    ld.backward()
+    assert rel(zd, z) < 1e-6
+    assert abs(float(ld) - float(loss)) < 1e-6
+    assert rel(hd.grad, h.grad) < 5e-6
+    # BCEWithLogits
+    x = torch.randn(P, generator=g, requires_grad=True)
+    l2 = torch.nn.functional.binary_cross_entropy_with_logits(x, y)
+    l2.backward()
+    xd = x.detach().to(DEV).requires_grad_(True)
+    l2d = ops.bce(xd, y.to(DEV), logits=True)
+    l2d.backward()
+    assert abs(float(l2d) - float(l2)) < 1e-6 and rel(xd.grad, x.grad) < 1e-6
+
+
+# ----------------------------------------------------------------------------- errors
+def test_argument_errors_raise():
+    with pytest.raises(RuntimeError):
+        ops.spmm(ops.CSR(torch.zeros(2, dtype=torch.int32), torch.zeros(1, dtype=torch.int32), 1),
+                 torch.zeros(1, 4), ops.SPMM_SUM)                      # CPU tensors: no CPU path
+    csr = ops.CSR(torch.zeros(2, dtype=torch.int32, device=DEV), torch.zeros(1, dtype=torch.int32, device=DEV), 1)
+    with pytest.raises(RuntimeError):
+        B._lib.call('bignn_spmm_f32', csr.row_ptr, csr.col_idx, torch.zeros(1, 4, device=DEV), 4,
+                    torch.zeros(1, 4, device=DEV), 4, 1, 4, 9, 0.0, None, None, 0)   # bad mode
+    with pytest.raises(ValueError):
+        ops.act_code('swish')

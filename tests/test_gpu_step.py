@@ -1,0 +1,120 @@
+"""Full Bi-GNN (GIN lower + GCN upper) train step on the GPU against the reference-generated
+golden vectors (DrugBank fold 1) and the fp64 oracle.
+
+Tolerances: forward quantities 1e-5 relative (max-norm).  Gradients: the reference's own fp32
+gradients sit up to 3.5e-4 from an fp64 run of the same code in the lower layers (ill-conditioned
+through five BatchNorms; measured in this test), so an fp32 path with another summation order
+cannot be within 1e-5 of them.  The gate is therefore: error against the fp64 oracle no larger
+than 3x the reference's own fp32 error against it (+1e-5), per parameter, on the layer's
+gradient scale."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import bignn_b200 as B
+from oracle import bignn_oracle as O
+
+DEV = 'cuda:0'
+
+
+def rel(a, b):
+    a = np.asarray(a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else a, np.float64)
+    b = np.asarray(b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.fixture(scope='module')
+def world(golden_dir, step_golden):
+    B._lib.load()
+    B.set_flags(B.make_flags(device=DEV))
+    data = B.BiGNNData.from_npz(os.path.join(golden_dir, 'drugbank_packed.npz'), device=DEV)
+    model = B.Model(data).to(DEV)
+    z = step_golden
+    sd = {k[4:]: torch.from_numpy(np.asarray(z[k])) for k in z.files if k.startswith('sd0/')}
+    for k in z.files:
+        if k.startswith('sd_init/'):
+            sd[k[len('sd_init/'):]] = torch.from_numpy(np.asarray(z[k]))
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected
+    return data, model
+
+
+def run_step(data, model, z):
+    model.train()
+    model.zero_grad()
+    B.train._get_initial_embd(data, model)
+    bd = B.BatchData(z['positive_gids'], data, sampled_gids=z['sampled_gids'], is_train=False, merge_graphs=False)
+    bd.batch_gids = z['batch_gids']
+    bd.pair_list = [B.batch.PairRecord(int(l), tuple(g)) for l, g in zip(z['y_true'], z['batch_gids'].tolist())]
+    bd.batch_interaction_inds = [data.gs_map[g] for g in bd.batch_gids.flatten().tolist()]
+    model.use_layers = 'higher_layers'
+    loss = model(bd)
+    return bd, loss
+
+
+def test_step_forward_and_gradients(world, step_golden, drugbank, gin_gcn_specs):
+    z = step_golden
+    data, model = world
+    n0 = B._lib.launch_count()
+    bd, loss = run_step(data, model, z)
+    init_x = data.interaction_combo_nxgraph.init_x
+    assert rel(init_x, z['init_x']) < 1e-5
+    for l in range(3):
+        assert rel(model.acts[l + 2], z['upper/act%d' % (l + 2)]) < 1e-5
+    assert rel(model.acts[-2].view(-1), z['pair_preds']) < 1e-5
+    assert abs(float(loss) - float(z['loss'])) < 1e-5
+    loss.backward()
+    assert B._lib.launch_count() - n0 > 100          # the CUDA library did the work
+    # fp64 ground truth from the oracle
+    sd = O.state_from_npz(z, 'sd0/')
+    om = O.OracleModel(gin_gcn_specs, sd, dtype=torch.float64)
+    _, _, _, l64 = O.train_step_forward(om, drugbank, z['batch_gids'], z['y_true'])
+    l64.backward()
+    g64 = {k: v.grad.numpy() for k, v in om.params().items()}
+    scale = {}
+    for k, g in g64.items():
+        lid = k.split('.')[1]
+        scale[lid] = max(scale.get(lid, 0.0), float(np.abs(g).max()))
+    worst = 0.0
+    for k, p in model.named_parameters():
+        if not k.startswith('layers.'):
+            continue
+        s = scale[k.split('.')[1]]
+        ours = float(np.abs(p.grad.double().cpu().numpy() - g64[k]).max()) / s
+        ref = float(np.abs(z['grad/' + k].astype(np.float64) - g64[k]).max()) / s
+        worst = max(worst, ours)
+        assert ours <= 3.0 * ref + 1e-5, (k, ours, ref)
+    # upper level + decoder are well conditioned: plain 1e-5 against the reference's fp32
+    for k, p in model.named_parameters():
+        if k.startswith('layers.') and int(k.split('.')[1]) >= 7:
+            s = scale[k.split('.')[1]]
+            assert float(np.abs(p.grad.double().cpu().numpy() - z['grad/' + k]).max()) / s < 1e-5, k
+    sdm = model.state_dict()
+    for k in z.files:
+        if k.startswith('sd1/') and 'running' in k:
+            assert rel(sdm[k[4:]], z[k]) < 1e-5, k
+        if k.startswith('sd1/') and 'num_batches' in k:
+            assert int(sdm[k[4:]]) == int(z[k])
+
+
+def test_lower_chunk_activations(world, step_golden):
+    """per-layer activations of the last (29-graph) chunk and pooled rows of the first."""
+    z = step_golden
+    data, model = world
+    model.train()
+    model.use_layers = 'lower_layers'
+    for c in (0, 10):
+        gids = z['chunk%d/batch_gids' % c]
+        bd = B.BatchData(gids, data, is_train=False, ignore_pairs=True)
+        data.interaction_combo_nxgraph.init_x = torch.zeros((data.N, 320), device=DEV)
+        out = model(bd)
+        if c == 10:
+            for l in range(5):
+                assert rel(model.acts[l + 1], z['chunk10/act%d' % (l + 1)]) < 1e-5
+            assert rel(out, z['chunk10/act6']) < 1e-5
+        else:
+            assert rel(out, z['chunk0/pooled']) < 1e-5
