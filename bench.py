@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py -- train drug-pairs/sec of the Bi-GNN step on B200 (+ segment-SpMM HBM roofline).
+
+  python bench.py --gpus N --steps K --warmup W            # this framework (CUDA, sm_100a)
+  python bench.py --impl reference --steps K --warmup W    # CPU port of the reference path
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'train drug-pairs/sec'
+UNIT = 'pairs/s'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='drugcombo_shape')
+    ap.add_argument('--seed', type=int, default=0)
+    ap.add_argument('--no-graph', action='store_true', help='eager launches instead of CUDA-graph replay')
+    ap.add_argument('--no-l2-flush', action='store_true')
+    ap.add_argument('--cpu-sample-steps', type=int, default=6)
+    ap.add_argument('--spmm-rows', type=int, default=8_000_000, help='rows of the >L2 segment-SpMM roofline case')
+    return ap.parse_args()
+
+
+def workload_config(name):
+    from bignn_b200 import synthetic as S
+    w = S.WORKLOADS[name]
+    return dict(workload='Bi-GNN (GIN x5 lower, multi-scale mean readout, GCN x3 upper, MLP scorer, BCE, Adam) '
+                         'on a synthetic dataset of {} shape'.format(name),
+                name=name, drugs=w['N'], ddi_edges=w['M'], mean_atoms=w['mean_atoms'],
+                node_feat=int(sum(w['groups'])), pos_pairs_per_step=64, neg_pairs_per_step=64,
+                lower_chunk_graphs=128)
+
+
+def make_workload(name, seed):
+    from bignn_b200 import synthetic as S
+    return S.bignn_workload(seed=seed, **S.WORKLOADS[name])
+
+
+def layer_specs():
+    import bignn_b200 as B
+    f = B.make_flags()
+    return [getattr(f, 'layer_%d' % i) for i in range(1, f.layer_num + 1)]
+
+
+# --------------------------------------------------------------------------- reference arm
+def run_reference(args, sample_steps=None, quiet=False):
+    """The reference path on the host cores: oracle/bignn_oracle.py (CPU port; the reference is
+    pure Python over un-vendored wheels and cannot travel to the GPU box)."""
+    import torch
+    from oracle import bignn_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    w = make_workload(args.workload, args.seed)
+    ds = O.PackedDataset(w)
+    specs = O.parse_specs(layer_specs())
+    state = O.init_params(specs, ds.num_node_feat, seed=8)
+    tr = O.OracleTrainer(ds, specs, state, 64)
+    np.random.seed(8)
+    torch.manual_seed(8)
+    steps = args.steps if sample_steps is None else sample_steps
+    warm = min(args.warmup, 2) if sample_steps is not None else args.warmup
+    for _ in range(warm):
+        tr.step()
+    t0 = time.perf_counter()
+    pairs = 0
+    for _ in range(steps):
+        _, p = tr.step()
+        pairs += p
+    dt = time.perf_counter() - t0
+    return dict(value=pairs / dt, ms_per_step=1e3 * dt / steps, cores=cores, steps=steps,
+                sample='{} full train steps of the same workload ({} pairs/step), torch CPU fp32, {} threads'.format(
+                    steps, pairs // max(steps, 1), cores))
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler(object):
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, universal_newlines=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i] == 'Active' for r in self.rows)]
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=reasons, samples=len(sm))
+
+
+# --------------------------------------------------------------------------- our arm
+def spmm_roofline(torch, B, rows, peaks, device):
+    """Segment SpMM (GIN aggregation, D=64) on a molecule-like merged graph larger than L2:
+    achieved = algorithmic bytes / CUDA-event time per launch."""
+    from bignn_b200 import ops, synthetic as S
+    G = rows // 30
+    atom_ptr, nbr_ptr, nbr_idx, _ = S.molecule_graphs(G, 30.0, seed=3)
+    A = int(atom_ptr[-1])
+    col = nbr_idx.astype(np.int64) + np.repeat(atom_ptr[:-1].astype(np.int64), np.diff(atom_ptr))[
+        np.repeat(np.arange(A), np.diff(nbr_ptr))]
+    csr = ops.CSR(torch.as_tensor(nbr_ptr).to(device), torch.as_tensor(col.astype(np.int32)).to(device), A)
+    D = 64
+    x = torch.randn(A, D, device=device)
+    y = torch.empty_like(x)
+    for _ in range(3):
+        ops.spmm(csr, x, ops.SPMM_GIN, 1.0, out=y)
+    reps = 10
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in evs:
+        a.record()
+        ops.spmm(csr, x, ops.SPMM_GIN, 1.0, out=y)
+        b.record()
+    torch.cuda.synchronize()
+    ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    nnz = csr.nnz
+    alg = 4.0 * D * A * 2 + 4.0 * nnz + 4.0 * (A + 1)
+    ach = alg / (ms * 1e-3) / 1e9
+    peak = peaks.get('hbm_gbs', 6650.0)
+    return dict(kernel='k_spmm_v4<16,1,GIN> (bignn_spmm_f32)', bound='hbm', achieved=ach, peak=peak, unit='GB/s',
+                frac=ach / peak, traffic=None, rows=A, nnz=nnz, D=D, ms_per_launch=ms,
+                algorithmic_bytes=alg, peak_source='MEASURED_PEAKS.json' if 'hbm_gbs' in peaks else 'fallback 6650')
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import bignn_b200 as B
+    from bignn_b200.engine import BiGNNEngine
+
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    dev = 'cuda:%d' % local
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device(dev))
+    B._lib.load()
+    peaks = {}
+    pk = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+
+    B.set_flags(B.make_flags(device=dev))
+    w = make_workload(args.workload, args.seed)
+    data = B.BiGNNData(w['gids'], w['atom_ptr'], w['nbr_ptr'], w['nbr_idx'], w['x_u8'].astype(np.float32),
+                       w['ddi_row'], w['ddi_col'], w['train_pairs'], w['pair_keys'], w['pair_labels'], 2, dev)
+    torch.manual_seed(8)
+    np.random.seed(8 + rank)
+    model = B.Model(data).to(dev)
+    model.train()
+    eng = BiGNNEngine(data, model, use_cuda_graph=not args.no_graph)
+    sampler = B.RandomSampler(data, 64)
+
+    flush = None if args.no_l2_flush else torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up through the public API (also captures the CUDA graph)
+    for _ in range(max(args.warmup, 3)):
+        st = eng.train_step(sampler)
+    eng.read_loss(st)
+    l0 = B._lib.launch_count()
+    eager_probe = BiGNNEngine(data, model, optimizer=eng.optimizer, use_cuda_graph=False) if False else None
+    del eager_probe
+
+    clocks = ClockSampler(local)
+    clocks.start()
+
+    # ---- (1) device-resident: inputs already staged in HBM, K replays, events per step
+    st, P = eng.stage_pairs(eng.last_batch.batch_gids, [p.true_label for p in eng.last_batch.pair_list])
+    eng.step_staged(st, P)
+    barrier()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    graph, sb, _ = eng._graphs[P] if not args.no_graph else (None, eng.last_static_batch, None)
+    for a, b in evs:
+        if flush is not None:
+            flush.fill_(1.0)
+        a.record()
+        if graph is not None:
+            graph.replay()
+        else:
+            eng._device_step(sb)
+        b.record()
+    barrier()
+    dev_ms = float(sum(a.elapsed_time(b) for a, b in evs))
+    pairs_dev = P * args.steps
+
+    # ---- (2) end to end through the public API: host sampling, pinned H2D, step, loss D2H
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    pairs_e2e = 0
+    slots = []
+    for _ in range(args.steps):
+        if flush is not None:
+            flush.fill_(1.0)
+        st = eng.train_step(sampler)
+        pairs_e2e += eng.last_batch.batch_gids.shape[0]
+        slots.append(st)
+        if len(slots) >= 3:
+            eng.read_loss(slots.pop(0))
+    losses = [eng.read_loss(s) for s in slots]
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    clk = clocks.stop()
+
+    # ---- max over ranks, whole-job aggregates
+    t = torch.tensor([dev_ms, e2e_ms, float(pairs_dev), float(pairs_e2e)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tm = t.clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ts = t.clone()
+        dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+        dev_ms, e2e_ms = float(tm[0]), float(tm[1])
+        pairs_dev, pairs_e2e = float(ts[2]), float(ts[3])
+    launches_per_step = getattr(eng, 'launches_per_step', None)
+
+    if rank != 0:
+        return None
+    out = dict(metric=METRIC, value=pairs_dev / (dev_ms * 1e-3), unit=UNIT, n_gpus=world, steps=args.steps,
+               warmup=max(args.warmup, 3), ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling='weak',
+               vs_baseline=None, dtype='f32', data='synthetic', impl='ours',
+               config=dict(workload_config(args.workload), l2='flushed between timed steps (256 MiB write)'
+                           if flush is not None else 'not flushed (working set < L2)',
+                           cuda_graph=not args.no_graph,
+                           parallelism='replicas' if world > 1 else 'single'),
+               e2e=dict(value=pairs_e2e / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=eng.h2d_bytes_per_step,
+                        d2h_bytes_per_step=eng.d2h_bytes_per_step, ms_per_step=e2e_ms / args.steps,
+                        wall_ms_per_step=wall_ms / args.steps),
+               clocks=clk, last_loss=losses[-1] if losses else None)
+    return out, (torch, B, peaks, dev, eng, data, model)
+
+
+def kernel_profile(torch, B, eng, steps=3):
+    """Per-entry-point device time of one eager step (CUDA events around every C-ABI call on the
+    launching stream) -- finds the dominant kernel and its average launch duration."""
+    lib = B._lib
+    rec = []
+    orig = lib.call
+
+    def timed(name, *a):
+        if name.endswith('_bytes') or name in ('bignn_abi_version', 'bignn_launch_count'):
+            return orig(name, *a)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = orig(name, *a)
+        e1.record()
+        rec.append((name, e0, e1, a))
+        return r
+    sb = eng.last_static_batch
+    n0 = lib.launch_count()
+    eng._device_step(sb)           # eager warm-up of this path
+    launches_per_step = lib.launch_count() - n0
+    lib.call = timed
+    ops_mod = B.ops
+    try:
+        for _ in range(steps):
+            eng._device_step(sb)
+        torch.cuda.synchronize()
+    finally:
+        lib.call = orig
+    agg = {}
+    for name, e0, e1, a in rec:
+        key = name
+        if name == 'bignn_spmm_f32':
+            key = 'bignn_spmm_f32[mode={},D={},rows={}]'.format(a[8], a[7], a[6])
+        elif name == 'bignn_gemm_f32':
+            key = 'bignn_gemm_f32[ta={},tb={},M={},N={},K={}]'.format(*a[:5])
+        d = agg.setdefault(key, [0.0, 0])
+        d[0] += e0.elapsed_time(e1)
+        d[1] += 1
+    total = sum(v[0] for v in agg.values())
+    rows = sorted(((k, v[0] / steps, v[1] // steps, v[0] / v[1]) for k, v in agg.items()), key=lambda r: -r[1])
+    return dict(total_ms_per_step=total / steps, launches_per_step=launches_per_step,
+                top=[dict(entry=k, ms_per_step=round(ms, 5), calls_per_step=c, ms_per_call=round(avg, 5),
+                          share=round(ms / (total / steps), 4)) for k, ms, c, avg in rows[:12]])
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get('RANK', 0))
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        r = run_reference(args)
+        cfg = workload_config(args.workload)
+        out = dict(metric=METRIC, value=r['value'], unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                   ms_per_step=r['ms_per_step'], higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
+                   data='synthetic', impl='reference', config=cfg,
+                   cpu_baseline=dict(value=r['value'], unit=UNIT, cores=r['cores'], kind='port', sample=r['sample']),
+                   e2e=dict(value=r['value'], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        print(json.dumps(out))
+        return
+    res = run_ours(args)
+    if res is None:
+        return
+    out, (torch, B, peaks, dev, eng, data, model) = res
+    prof = kernel_profile(torch, B, eng)
+    out['gpu_launches'] = int(prof['launches_per_step'] * args.steps)
+    out['kernel_profile'] = prof
+    if args.gpus == 1:
+        out['roofline'] = spmm_roofline(torch, B, args.spmm_rows, peaks, dev)
+        cpu_args = argparse.Namespace(**vars(args))
+        r = run_reference(cpu_args, sample_steps=args.cpu_sample_steps)
+        out['cpu_baseline'] = dict(value=r['value'], unit=UNIT, cores=r['cores'], kind='port', sample=r['sample'],
+                                   ms_per_step=r['ms_per_step'])
+    print(json.dumps(out))
+
+
+if __name__ == '__main__':
+    main()

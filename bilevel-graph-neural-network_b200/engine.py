@@ -1,0 +1,265 @@
+"""BiGNNEngine: one Bi-GNN train step as a single batched, CUDA-graph-captured pass.
+
+Same arithmetic as the reference-sequenced driver in train.py (and therefore as
+src/train.py:75-108,177-182), re-organised for the GPU:
+
+  * the all-drug lower pass (src/train.py:48-72: 11 chunks x 5 layers on DrugBank) runs as ONE
+    merged graph over every drug; BatchNorm keeps the reference's per-chunk statistics through
+    the segmented kernels (`chunk_row_ptr`), so results equal the chunk-by-chunk loop;
+  * the readout writes the pooled rows straight into init_x[gs_map[gid]] (dst_row) instead of
+    128 Python row copies per chunk (model/layers_aggregation.py:70-74);
+  * per-step inputs (pair rows, labels, decoder entry CSR) live in static device buffers fed
+    from pinned host memory, and forward + backward + Adam are replayed as one CUDA graph.
+"""
+import numpy as np
+import torch
+
+from . import ops
+from .batch import BatchData, unique_graphs_in_order
+from .config import get_flags
+from .graph import MergedGraph
+from .ops import CSR
+from .train import all_drug_chunks
+
+
+class _StaticPairBatch(object):
+    """The pair batch as the upper-level layers see it (LinkPred / Loss), backed by static
+    device buffers so that a captured graph can be replayed on new pairs."""
+
+    def __init__(self, data, P, device):
+        self.dataset = data
+        self.P = P
+        N = data.N
+        self.interaction_combo_nxgraph = data.interaction_combo_nxgraph
+        self.merge_data = {}
+        self.merge_higher_level = {}
+        self.ids = torch.zeros((P, 2), dtype=torch.int32, device=device)
+        self.y = torch.zeros(P, dtype=torch.float32, device=device)
+        self.e_ptr = torch.zeros(N + 1, dtype=torch.int32, device=device)
+        self.e_idx = torch.zeros(2 * P, dtype=torch.int32, device=device)
+        self.entry_csr = CSR(self.e_ptr, self.e_idx, N)
+        self.batch_gids = np.zeros((P, 2), np.int64)
+        self.preds = None
+
+    def y_true_device(self):
+        return self.y
+
+    def pair_rows_device(self, n_rows, higher=True, unique=True):
+        return self.ids, self.entry_csr
+
+    def assign_link_preds(self, pair_preds):
+        self.preds = pair_preds.detach()
+
+
+class _Staging(object):
+    """Pinned host buffers for one step's inputs (+ the loss read-back)."""
+
+    def __init__(self, P, N):
+        pin = dict(pin_memory=True)
+        self.ids = torch.zeros((P, 2), dtype=torch.int32, **pin)
+        self.y = torch.zeros(P, dtype=torch.float32, **pin)
+        self.e_ptr = torch.zeros(N + 1, dtype=torch.int32, **pin)
+        self.e_idx = torch.zeros(2 * P, dtype=torch.int32, **pin)
+        self.loss = torch.zeros((), dtype=torch.float32, **pin)
+        self.event = torch.cuda.Event()
+        self.busy = False
+
+    def nbytes_in(self):
+        return sum(t.numel() * t.element_size() for t in (self.ids, self.y, self.e_ptr, self.e_idx))
+
+
+class BiGNNEngine(object):
+    def __init__(self, data, model, optimizer=None, lr=None, use_cuda_graph=True, rebuild_each_step=True,
+                 n_staging=4):
+        flags = get_flags()
+        assert flags.lower_level_layers and flags.higher_level_layers, 'engine runs the Bi-GNN mode'
+        self.data, self.model = data, model
+        self.device = data.device
+        self.use_cuda_graph = use_cuda_graph
+        self.rebuild_each_step = rebuild_each_step
+        self.optimizer = optimizer if optimizer is not None else torch.optim.Adam(
+            model.parameters(), lr=flags.lr if lr is None else lr, capturable=use_cuda_graph)
+        # ---- static all-drug merged graph: chunk schedule of src/train.py:52-71
+        gids = list(data.gs_map.keys())
+        rows, chunk_ptr = [], [0]
+        for pairs in all_drug_chunks(gids, flags.batch_size):
+            order = unique_graphs_in_order(pairs)
+            rows.extend(data.gs_map[g] for g in order.keys())
+            chunk_ptr.append(len(rows))
+        rows = np.asarray(rows, np.int64)
+        self.merged = MergedGraph(data.packed, rows, chunk_graph_ptr=chunk_ptr)
+        # a drug that appears in two chunks is overwritten by the later one in the reference
+        # (layers_aggregation.py:72-74); earlier duplicates go to a trash row N
+        dst = rows.copy()
+        seen = set()
+        for i in range(len(rows) - 1, -1, -1):
+            if rows[i] in seen:
+                dst[i] = data.N
+            seen.add(rows[i])
+        self.dst_row = torch.as_tensor(dst.astype(np.int32)).to(self.device)
+        self._lower_bd = type('LowerBatch', (), {})()
+        self._lower_bd.merge_data = {'merge': self.merged}
+        self._lower_bd.merge_higher_level = {}
+        self._lower_bd.dataset = data
+        agg = model.lower_layers[-1]
+        self._agg_style, self._multi = agg.style, agg.concat_multi_scale
+        self._graphs = {}          # P -> (graph, static batch, loss tensor)
+        self._stagings = {}
+        self._n_staging = n_staging
+        self._step_idx = 0
+        self.h2d_bytes_per_step = 0
+        self.d2h_bytes_per_step = 4
+
+    # ------------------------------------------------------------------ device work
+    def lower_pass(self):
+        """All drugs through the lower level -> init_x [N(+1), L*D] (with autograd history)."""
+        m, model = self.merged, self.model
+        if self.rebuild_each_step:
+            m.build()
+        acts, h = [], m.x
+        for layer in model.init_layers:
+            h = layer(h, self._lower_bd, model)
+            acts.append(h)
+        pooled = ops.readout(acts if self._multi else [h], m.seg_ptr, m.G, self._agg_style,
+                             self.dst_row, self.data.N + 1)
+        return pooled, acts
+
+    def forward(self, pair_batch):
+        model = self.model
+        pooled, _ = self.lower_pass()
+        ig = self.data.interaction_combo_nxgraph
+        ig.init_x = pooled[:self.data.N]
+        model.use_layers = 'higher_layers'
+        model.acts = [None]
+        for layer in model.higher_level_layers:
+            model.acts.append(layer(model.acts[-1], pair_batch, model))
+        return model.acts[-1]
+
+    def _device_step(self, pair_batch):
+        self.optimizer.zero_grad(set_to_none=True)
+        loss = self.forward(pair_batch)
+        loss.backward()
+        self.optimizer.step()
+        ig = self.data.interaction_combo_nxgraph
+        ig.init_x = ig.init_x.detach()
+        return loss.detach()
+
+    # ------------------------------------------------------------------ capture
+    def _snapshot(self):
+        snap = {'model': {k: v.detach().clone() for k, v in self.model.state_dict().items()}}
+        return snap
+
+    def _restore(self, snap):
+        with torch.no_grad():
+            for k, v in self.model.state_dict().items():
+                v.copy_(snap['model'][k])
+            for st in self.optimizer.state.values():
+                for v in st.values():
+                    if isinstance(v, torch.Tensor):
+                        v.zero_()
+
+    def _capture(self, P):
+        sb = _StaticPairBatch(self.data, P, self.device)
+        # a valid dummy batch for warm-up: pairs (0,1) with label 0
+        sb.ids[:, 1] = 1
+        e_ptr = np.zeros(self.data.N + 1, np.int64)
+        e_ptr[1:] = P
+        e_ptr[2:] = 2 * P
+        sb.e_ptr.copy_(torch.as_tensor(e_ptr.astype(np.int32)))
+        sb.e_idx.copy_(torch.as_tensor(np.concatenate([np.arange(0, 2 * P, 2), np.arange(1, 2 * P, 2)]).astype(np.int32)))
+        had_state = len(self.optimizer.state) > 0
+        snap = self._snapshot()
+        opt_snap = None
+        if had_state:
+            opt_snap = [{k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in st.items()}
+                        for st in self.optimizer.state.values()]
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                self._device_step(sb)
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        self.optimizer.zero_grad(set_to_none=True)
+        with torch.cuda.graph(g):
+            loss = self._device_step(sb)
+        # undo the warm-up steps: parameters, BN buffers and Adam moments back to where they were
+        self._restore(snap)
+        if opt_snap is not None:
+            with torch.no_grad():
+                for st, old in zip(self.optimizer.state.values(), opt_snap):
+                    for k, v in st.items():
+                        if isinstance(v, torch.Tensor):
+                            v.copy_(old[k])
+        torch.cuda.synchronize()
+        self._graphs[P] = (g, sb, loss)
+        return self._graphs[P]
+
+    # ------------------------------------------------------------------ host side of a step
+    def _staging(self, P):
+        key = P
+        if key not in self._stagings:
+            self._stagings[key] = [_Staging(P, self.data.N) for _ in range(self._n_staging)]
+        st = self._stagings[key][self._step_idx % self._n_staging]
+        if st.busy:
+            st.event.synchronize()
+            st.busy = False
+        return st
+
+    def stage_pairs(self, batch_gids, labels):
+        """Host -> pinned staging: pair rows (gs_map), labels and the decoder's entry CSR."""
+        gs_map = self.data.gs_map
+        flat = np.fromiter((gs_map[g] for g in np.asarray(batch_gids).reshape(-1).tolist()), np.int64)
+        P = flat.shape[0] // 2
+        st = self._staging(P)
+        st.ids.numpy()[:] = flat.reshape(P, 2)
+        st.y.numpy()[:] = labels
+        order = np.argsort(flat, kind='stable')
+        cnt = np.bincount(flat, minlength=self.data.N)
+        ep = st.e_ptr.numpy()
+        ep[0] = 0
+        np.cumsum(cnt, out=ep[1:])
+        st.e_idx.numpy()[:] = order
+        return st, P
+
+    def step_staged(self, st, P):
+        """Runs one train step on staged inputs; returns the staging slot whose `.loss`
+        holds the loss once `.event` has completed (read it with `read_loss`)."""
+        if self.use_cuda_graph:
+            entry = self._graphs.get(P) or self._capture(P)
+            g, sb, loss = entry
+        else:
+            sb = self._graphs.get(('eager', P))
+            if sb is None:
+                sb = self._graphs[('eager', P)] = _StaticPairBatch(self.data, P, self.device)
+        sb.ids.copy_(st.ids, non_blocking=True)
+        sb.y.copy_(st.y, non_blocking=True)
+        sb.e_ptr.copy_(st.e_ptr, non_blocking=True)
+        sb.e_idx.copy_(st.e_idx, non_blocking=True)
+        if self.use_cuda_graph:
+            g.replay()
+        else:
+            loss = self._device_step(sb)
+        st.loss.copy_(loss, non_blocking=True)
+        st.event.record()
+        st.busy = True
+        self._step_idx += 1
+        self.h2d_bytes_per_step = st.nbytes_in()
+        self.last_static_batch = sb
+        return st
+
+    @staticmethod
+    def read_loss(st):
+        st.event.synchronize()
+        st.busy = False
+        return float(st.loss)
+
+    def train_step(self, sampler):
+        """Public API: sample (host, bit-exact with the reference), stage, run, return the
+        staging slot (loss is read back asynchronously)."""
+        batch_gids, sampled_gids, _ = sampler.sample_next_training_batch()
+        bd = BatchData(batch_gids, self.data, sampled_gids=sampled_gids, is_train=True, merge_graphs=False)
+        labels = np.asarray([p.true_label for p in bd.pair_list], np.float32)
+        st, P = self.stage_pairs(bd.batch_gids, labels)
+        self.last_batch = bd
+        return self.step_staged(st, P)

@@ -569,3 +569,38 @@ def adam_step(P, state, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
             bc2 = 1 - betas[1] ** t
             denom = (s.sqrt() / math.sqrt(bc2)).add_(eps)
             v.addcdiv_(m, denom, value=-lr / bc1)
+
+
+class OracleTrainer(object):
+    """The reference's hot loop body (src/train.py:136-141) over this port, for the CPU
+    baseline: per step the all-drug lower pass (per-graph conversion + merge + 5 layers per
+    chunk), positive/negative sampling, the upper pass, backward and Adam."""
+
+    def __init__(self, ds, specs, state, batch_size=64, dtype=torch.float32):
+        from torch.utils.data import DataLoader
+        self.ds, self.bs = ds, batch_size
+        self.model = OracleModel(specs, state, dtype)
+        self.adam = {}
+        self.items = torch.as_tensor(np.asarray(sorted(map(tuple, ds.train_pairs.tolist())), np.int64))
+        self.loader = DataLoader(self.items, batch_size=batch_size, shuffle=True)
+        self.it = iter(self.loader)
+        self.edge_set = set(zip(ds.ddi_row.tolist(), ds.ddi_col.tolist()))
+
+    def sample(self):
+        try:
+            pos = next(self.it)
+        except StopIteration:
+            self.it = iter(self.loader)
+            pos = next(self.it)
+        pos = pos.numpy()
+        neg = sample_negative_pairs(self.ds, pos, np.unique(pos), self.edge_set)
+        gids = np.concatenate([pos, neg]) if len(neg) else pos
+        return gids, pair_labels(self.ds, gids)
+
+    def step(self):
+        self.model.zero_grad()
+        gids, y = self.sample()
+        _, _, _, loss = train_step_forward(self.model, self.ds, gids, y, self.bs)
+        loss.backward()
+        adam_step(self.model.P, self.adam)
+        return float(loss.detach()), len(gids)

@@ -143,7 +143,7 @@ def test_spmm_is_its_own_transpose_at_scale():
     ay = ops.spmm(csr, y, ops.SPMM_GIN, 1.0)
     a = (y.double() * ax.double()).sum().item()
     b = (ay.double() * x.double()).sum().item()
-    assert abs(a - b) < 1e-9 * max(1.0, abs(a))
+    assert abs(a - b) < 1e-6 * max(1.0, abs(a))      # both sides are sums of fp32-rounded rows
     ones = torch.ones(n, D, device=DEV)
     deg = torch.as_tensor(np.bincount(row, minlength=n).astype(np.float32)).to(DEV)
     assert torch.equal(ops.spmm(csr, ones, ops.SPMM_GIN, 1.0), (deg + 1).view(-1, 1).expand(n, D))
