@@ -33,6 +33,8 @@ SIGNATURES = {
     'bignn_merge_build': ('i', 'pppp' 'i' 'p' 'i' 'pp' 'ppp' 'ppp' 'ii' 'pl' 's'),
     'bignn_gcn_dinv': ('i', 'ppips'),
     'bignn_spmm_f32': ('i', 'pp' 'pl' 'pl' 'iiif' 'ppi' 's'),
+    'bignn_spmm_planned_workspace_bytes': ('l', 'ii'),
+    'bignn_spmm_planned_f32': ('i', 'pp' 'ppii' 'pi' 'pl' 'pl' 'iiif' 'ppi' 'pl' 's'),
     'bignn_gemm_workspace_bytes': ('l', 'iiii'),
     'bignn_gemm_f32': ('i', 'iiiii' 'pl' 'pl' 'pl' 'pi' 'pl' 's'),
     'bignn_colsum_workspace_bytes': ('l', 'ii'),

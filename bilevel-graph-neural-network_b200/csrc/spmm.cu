@@ -24,13 +24,79 @@ __device__ __forceinline__ void acc_add_scaled(float4& a, float w, const float4&
   a.z = __fadd_rn(a.z, __fmul_rn(w, v.z)); a.w = __fadd_rn(a.w, __fmul_rn(w, v.w));
 }
 
+// neighbours [k0,k1) of `row` accumulated in ascending order into acc[NV]
+template <int L, int NV, int MODE>
+__device__ __forceinline__ void accumulate_range(float4 (&acc)[NV], int k0, int k1, int row, int lane, int D4,
+                                                 float di, const int32_t* __restrict__ col_idx,
+                                                 const float* __restrict__ X, int64_t ldx,
+                                                 const float* __restrict__ dinv) {
+  constexpr int U = 4;  // neighbours gathered per step
+  for (int k = k0; k < k1; k += U) {
+    int c[U];
+    float w[U];
+    float4 val[U][NV];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      c[u] = (k + u < k1) ? __ldg(col_idx + k + u) : -1;
+      if (MODE != BIGNN_SPMM_SUM && c[u] == row) c[u] = -1;  // remove_self_loops
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (MODE == BIGNN_SPMM_GCN) w[u] = c[u] >= 0 ? __fmul_rn(__ldg(dinv + c[u]), di) : 0.f;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int q = lane + v * L;
+        val[u][v] = (c[u] >= 0 && q < D4) ? ldg4(X + (int64_t)c[u] * ldx + 4 * q) : f4zero();
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (c[u] >= 0) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          if (MODE == BIGNN_SPMM_GCN) acc_add_scaled(acc[v], w[u], val[u][v]);
+          else acc_add(acc[v], val[u][v]);
+        }
+      }
+    }
+  }
+}
+
+// self term, bias, activation, store
+template <int L, int NV, int MODE>
+__device__ __forceinline__ void finish_row(float4 (&acc)[NV], int row, int lane, int D4, float self_coef, float di,
+                                           const float* __restrict__ X, int64_t ldx, float* __restrict__ Y,
+                                           int64_t ldy, const float* __restrict__ bias, int act) {
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int q = lane + v * L;
+    if (q >= D4) continue;
+    float4 a = acc[v];
+    if (MODE == BIGNN_SPMM_GIN) {
+      const float4 s = ldg4(X + (int64_t)row * ldx + 4 * q);
+      a.x = __fadd_rn(__fmul_rn(self_coef, s.x), a.x); a.y = __fadd_rn(__fmul_rn(self_coef, s.y), a.y);
+      a.z = __fadd_rn(__fmul_rn(self_coef, s.z), a.z); a.w = __fadd_rn(__fmul_rn(self_coef, s.w), a.w);
+    } else if (MODE == BIGNN_SPMM_GCN) {
+      const float4 s = ldg4(X + (int64_t)row * ldx + 4 * q);
+      acc_add_scaled(a, __fmul_rn(di, di), s);       // self loop is the last COO entry
+    }
+    if (bias) {
+      const float4 b = ldg4(bias + 4 * q);
+      a.x = __fadd_rn(a.x, b.x); a.y = __fadd_rn(a.y, b.y); a.z = __fadd_rn(a.z, b.z); a.w = __fadd_rn(a.w, b.w);
+    }
+    if (act != BIGNN_ACT_IDENTITY) {
+      a.x = apply_act(a.x, act); a.y = apply_act(a.y, act); a.z = apply_act(a.z, act); a.w = apply_act(a.w, act);
+    }
+    st4(Y + (int64_t)row * ldy + 4 * q, a);
+  }
+}
+
 template <int L, int NV, int MODE>
 __global__ void __launch_bounds__(256)
 k_spmm_v4(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx,
           const float* __restrict__ X, int64_t ldx, float* __restrict__ Y, int64_t ldy,
           int n_rows, int D4, float self_coef, const float* __restrict__ dinv,
           const float* __restrict__ bias, int act) {
-  constexpr int U = 4;  // neighbours gathered per step
   const int rpb = blockDim.x / L;
   const int sub = threadIdx.x / L;
   const int lane = threadIdx.x % L;
@@ -41,57 +107,75 @@ k_spmm_v4(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col_i
     for (int v = 0; v < NV; ++v) acc[v] = f4zero();
     float di = 0.f;
     if (MODE == BIGNN_SPMM_GCN) di = __ldg(dinv + row);
-    for (int k = k0; k < k1; k += U) {
-      int c[U];
-      float w[U];
-      float4 val[U][NV];
+    accumulate_range<L, NV, MODE>(acc, k0, k1, row, lane, D4, di, col_idx, X, ldx, dinv);
+    finish_row<L, NV, MODE>(acc, row, lane, D4, self_coef, di, X, ldx, Y, ldy, bias, act);
+  }
+}
+
+// ---- long-row variant: work items of at most `seg` neighbours --------------------------------
+// item i covers neighbours [row_ptr[r] + c*seg, ...) of row r = item_row[i], c = i - item_ptr[r].
+// Rows with one item are finished in place; rows with several items leave per-item partial sums in
+// `partial` and are finished by k_spmm_multi_v4, which adds the partials in item order
+// (deterministic, no atomics).  Keeps a 190k-neighbour hub row from serialising on one sub-warp.
+template <int L, int NV, int MODE>
+__global__ void __launch_bounds__(256)
+k_spmm_items_v4(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx,
+                const int32_t* __restrict__ item_ptr, const int32_t* __restrict__ item_row, int n_items, int seg,
+                const float* __restrict__ X, int64_t ldx, float* __restrict__ Y, int64_t ldy,
+                int D4, float self_coef, const float* __restrict__ dinv, const float* __restrict__ bias, int act,
+                float* __restrict__ partial) {
+  const int ipb = blockDim.x / L;
+  const int sub = threadIdx.x / L;
+  const int lane = threadIdx.x % L;
+  for (int item = blockIdx.x * ipb + sub; item < n_items; item += gridDim.x * ipb) {
+    const int row = __ldg(item_row + item);
+    const int i0 = __ldg(item_ptr + row), i1 = __ldg(item_ptr + row + 1);
+    const int rk1 = __ldg(row_ptr + row + 1);
+    const int k0 = __ldg(row_ptr + row) + (item - i0) * seg;
+    const int k1 = min(k0 + seg, rk1);
+    float4 acc[NV];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        c[u] = (k + u < k1) ? __ldg(col_idx + k + u) : -1;
-        if (MODE != BIGNN_SPMM_SUM && c[u] == row) c[u] = -1;  // remove_self_loops
-      }
+    for (int v = 0; v < NV; ++v) acc[v] = f4zero();
+    float di = 0.f;
+    if (MODE == BIGNN_SPMM_GCN) di = __ldg(dinv + row);
+    accumulate_range<L, NV, MODE>(acc, k0, k1, row, lane, D4, di, col_idx, X, ldx, dinv);
+    if (i1 - i0 == 1) {
+      finish_row<L, NV, MODE>(acc, row, lane, D4, self_coef, di, X, ldx, Y, ldy, bias, act);
+    } else {
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (MODE == BIGNN_SPMM_GCN) w[u] = c[u] >= 0 ? __fmul_rn(__ldg(dinv + c[u]), di) : 0.f;
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-          const int q = lane + v * L;
-          val[u][v] = (c[u] >= 0 && q < D4) ? ldg4(X + (int64_t)c[u] * ldx + 4 * q) : f4zero();
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (c[u] >= 0) {
-#pragma unroll
-          for (int v = 0; v < NV; ++v) {
-            if (MODE == BIGNN_SPMM_GCN) acc_add_scaled(acc[v], w[u], val[u][v]);
-            else acc_add(acc[v], val[u][v]);
-          }
-        }
+      for (int v = 0; v < NV; ++v) {
+        const int q = lane + v * L;
+        if (q < D4) st4(partial + ((int64_t)item * D4 + q) * 4, acc[v]);
       }
     }
+  }
+}
+
+template <int L, int NV, int MODE>
+__global__ void __launch_bounds__(256)
+k_spmm_multi_v4(const int32_t* __restrict__ item_ptr, const int32_t* __restrict__ multi_rows, int n_multi,
+                const float* __restrict__ X, int64_t ldx, float* __restrict__ Y, int64_t ldy,
+                int D4, float self_coef, const float* __restrict__ dinv, const float* __restrict__ bias, int act,
+                const float* __restrict__ partial) {
+  const int rpb = blockDim.x / L;
+  const int sub = threadIdx.x / L;
+  const int lane = threadIdx.x % L;
+  for (int m = blockIdx.x * rpb + sub; m < n_multi; m += gridDim.x * rpb) {
+    const int row = __ldg(multi_rows + m);
+    const int i0 = __ldg(item_ptr + row), i1 = __ldg(item_ptr + row + 1);
+    float4 acc[NV];
 #pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      const int q = lane + v * L;
-      if (q >= D4) continue;
-      float4 a = acc[v];
-      if (MODE == BIGNN_SPMM_GIN) {
-        const float4 s = ldg4(X + (int64_t)row * ldx + 4 * q);
-        a.x = __fadd_rn(__fmul_rn(self_coef, s.x), a.x); a.y = __fadd_rn(__fmul_rn(self_coef, s.y), a.y);
-        a.z = __fadd_rn(__fmul_rn(self_coef, s.z), a.z); a.w = __fadd_rn(__fmul_rn(self_coef, s.w), a.w);
-      } else if (MODE == BIGNN_SPMM_GCN) {
-        const float4 s = ldg4(X + (int64_t)row * ldx + 4 * q);
-        acc_add_scaled(a, __fmul_rn(di, di), s);       // self loop is the last COO entry
+    for (int v = 0; v < NV; ++v) acc[v] = f4zero();
+    for (int it = i0; it < i1; ++it) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int q = lane + v * L;
+        if (q < D4) acc_add(acc[v], ldg4(partial + ((int64_t)it * D4 + q) * 4));
       }
-      if (bias) {
-        const float4 b = ldg4(bias + 4 * q);
-        a.x = __fadd_rn(a.x, b.x); a.y = __fadd_rn(a.y, b.y); a.z = __fadd_rn(a.z, b.z); a.w = __fadd_rn(a.w, b.w);
-      }
-      if (act != BIGNN_ACT_IDENTITY) {
-        a.x = apply_act(a.x, act); a.y = apply_act(a.y, act); a.z = apply_act(a.z, act); a.w = apply_act(a.w, act);
-      }
-      st4(Y + (int64_t)row * ldy + 4 * q, a);
     }
+    float di = 0.f;
+    if (MODE == BIGNN_SPMM_GCN) di = __ldg(dinv + row);
+    finish_row<L, NV, MODE>(acc, row, lane, D4, self_coef, di, X, ldx, Y, ldy, bias, act);
   }
 }
 
@@ -217,6 +301,40 @@ static int launch_mode(const int32_t* row_ptr, const int32_t* col_idx, const flo
   return last_launch_status();
 }
 
+
+template <int MODE>
+static int launch_planned(const int32_t* row_ptr, const int32_t* col_idx, const int32_t* item_ptr,
+                          const int32_t* item_row, int n_items, int seg, const int32_t* multi_rows, int n_multi,
+                          const float* X, int64_t ldx, float* Y, int64_t ldy, int D, float self_coef,
+                          const float* dinv, const float* bias, int act, float* partial, cudaStream_t st) {
+  const int cap = sm_count() * 8;
+  const int d4 = D / 4;
+#define BIGNN_PLANNED(L, NV)                                                                          \
+  {                                                                                                   \
+    const int per = 256 / L;                                                                          \
+    int grid = ceil_div(n_items, per);                                                                \
+    if (grid > cap) grid = cap;                                                                       \
+    k_spmm_items_v4<L, NV, MODE><<<grid, 256, 0, st>>>(row_ptr, col_idx, item_ptr, item_row, n_items, seg, X, \
+                                                       ldx, Y, ldy, d4, self_coef, dinv, bias, act, partial); \
+    BIGNN_LAUNCH_COUNT(1);                                                                            \
+    if (n_multi > 0) {                                                                                \
+      int g2 = ceil_div(n_multi, per);                                                                \
+      if (g2 > cap) g2 = cap;                                                                         \
+      k_spmm_multi_v4<L, NV, MODE><<<g2, 256, 0, st>>>(item_ptr, multi_rows, n_multi, X, ldx, Y, ldy, d4,     \
+                                                       self_coef, dinv, bias, act, partial);          \
+      BIGNN_LAUNCH_COUNT(1);                                                                          \
+    }                                                                                                 \
+  }
+  if (d4 <= 8) BIGNN_PLANNED(8, 1)
+  else if (d4 <= 16) BIGNN_PLANNED(16, 1)
+  else if (d4 <= 32) BIGNN_PLANNED(32, 1)
+  else if (d4 <= 64) BIGNN_PLANNED(32, 2)
+  else if (d4 <= 96) BIGNN_PLANNED(32, 3)
+  else BIGNN_PLANNED(32, 4)
+#undef BIGNN_PLANNED
+  return last_launch_status();
+}
+
 }  // namespace bignn
 
 using namespace bignn;
@@ -247,6 +365,38 @@ extern "C" int bignn_spmm_f32(const int32_t* row_ptr, const int32_t* col_idx, co
     case BIGNN_SPMM_SUM: return launch_mode<BIGNN_SPMM_SUM>(row_ptr, col_idx, X, ldx, Y, ldy, n_rows, D, self_coef, dinv, bias, act, st);
     case BIGNN_SPMM_GIN: return launch_mode<BIGNN_SPMM_GIN>(row_ptr, col_idx, X, ldx, Y, ldy, n_rows, D, self_coef, dinv, bias, act, st);
     case BIGNN_SPMM_GCN: return launch_mode<BIGNN_SPMM_GCN>(row_ptr, col_idx, X, ldx, Y, ldy, n_rows, D, self_coef, dinv, bias, act, st);
+    default: return BIGNN_EINVAL;
+  }
+}
+
+extern "C" int64_t bignn_spmm_planned_workspace_bytes(int32_t n_items, int32_t D) {
+  if (n_items <= 0 || D <= 0) return 0;
+  return (int64_t)n_items * D * sizeof(float);
+}
+
+extern "C" int bignn_spmm_planned_f32(const int32_t* row_ptr, const int32_t* col_idx, const int32_t* item_ptr,
+                                      const int32_t* item_row, int32_t n_items, int32_t seg,
+                                      const int32_t* multi_rows, int32_t n_multi, const float* X, int64_t ldx,
+                                      float* Y, int64_t ldy, int32_t n_rows, int32_t D, int32_t mode,
+                                      float self_coef, const float* dinv, const float* bias, int32_t act,
+                                      void* workspace, int64_t workspace_bytes, void* stream) {
+  if (n_rows < 0 || D < 0 || n_items < 0 || n_multi < 0 || seg <= 0 || !row_ptr) return BIGNN_EINVAL;
+  if (n_rows == 0 || D == 0) return 0;
+  if (!X || !Y || !item_ptr || !item_row || ldx < D || ldy < D || D > 512) return BIGNN_EINVAL;
+  if (n_multi > 0 && !multi_rows) return BIGNN_EINVAL;
+  if (mode == BIGNN_SPMM_GCN && !dinv) return BIGNN_EINVAL;
+  if (act < 0 || act > BIGNN_ACT_TANH) return BIGNN_EINVAL;
+  if ((D % 4) || (ldx % 4) || (ldy % 4) || !aligned16(X) || !aligned16(Y) || (bias && !aligned16(bias)) ||
+      (workspace && !aligned16(workspace)))
+    return BIGNN_EALIGN;
+  if (n_multi > 0 && (!workspace || workspace_bytes < bignn_spmm_planned_workspace_bytes(n_items, D)))
+    return BIGNN_EWORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* partial = (float*)workspace;
+  switch (mode) {
+    case BIGNN_SPMM_SUM: return launch_planned<BIGNN_SPMM_SUM>(row_ptr, col_idx, item_ptr, item_row, n_items, seg, multi_rows, n_multi, X, ldx, Y, ldy, D, self_coef, dinv, bias, act, partial, st);
+    case BIGNN_SPMM_GIN: return launch_planned<BIGNN_SPMM_GIN>(row_ptr, col_idx, item_ptr, item_row, n_items, seg, multi_rows, n_multi, X, ldx, Y, ldy, D, self_coef, dinv, bias, act, partial, st);
+    case BIGNN_SPMM_GCN: return launch_planned<BIGNN_SPMM_GCN>(row_ptr, col_idx, item_ptr, item_row, n_items, seg, multi_rows, n_multi, X, ldx, Y, ldy, D, self_coef, dinv, bias, act, partial, st);
     default: return BIGNN_EINVAL;
   }
 }

@@ -133,7 +133,7 @@ class InteractionGraph(object):
         np.add.at(ptr, row + 1, 1)
         ptr = np.cumsum(ptr)
         dev = torch.device(device)
-        self.csr = CSR(_i32(ptr, dev), _i32(col, dev), self.n)
+        self.csr = CSR(_i32(ptr, dev), _i32(col, dev), self.n, row_ptr_host=ptr)
         self.bn_row_ptr = _i32([0, self.n], dev)     # the whole graph is one BatchNorm batch
         self.init_x = x                              # [n, D] node features (pooled drug embeddings)
         self.edge_attr = None

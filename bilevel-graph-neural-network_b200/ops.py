@@ -28,12 +28,39 @@ def _ws(nbytes, device):
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
 
-class CSR(object):
-    """int32 CSR of a symmetric graph on the device (+ cached GCN deg^-1/2)."""
+LONG_ROW_SEG = 128     # neighbours per work item of the long-row SpMM variant
 
-    def __init__(self, row_ptr, col_idx, n_rows):
+
+class RowPlan(object):
+    """Work-item split of a skewed CSR (host-built once for a static graph)."""
+
+    def __init__(self, row_ptr_host, device, seg=LONG_ROW_SEG):
+        import numpy as np
+        deg = np.diff(np.asarray(row_ptr_host, np.int64))
+        items = np.maximum(1, -(-deg // seg))
+        ptr = np.concatenate([[0], np.cumsum(items)])
+        self.seg = int(seg)
+        self.n_items = int(ptr[-1])
+        multi = np.nonzero(items > 1)[0]
+        self.n_multi = int(multi.shape[0])
+        as_dev = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32)).to(device)
+        self.item_ptr = as_dev(ptr)
+        self.item_row = as_dev(np.repeat(np.arange(deg.shape[0]), items))
+        self.multi_rows = as_dev(multi) if self.n_multi else None
+
+
+class CSR(object):
+    """int32 CSR of a symmetric graph on the device (+ cached GCN deg^-1/2, + an optional
+    long-row work-item plan when the host knows the degree distribution is skewed)."""
+
+    def __init__(self, row_ptr, col_idx, n_rows, row_ptr_host=None):
         self.row_ptr, self.col_idx, self.n_rows = row_ptr, col_idx, int(n_rows)
         self._dinv = None
+        self.plan = None
+        if row_ptr_host is not None and len(row_ptr_host) > 1:
+            import numpy as np
+            if int(np.diff(np.asarray(row_ptr_host, np.int64)).max()) > LONG_ROW_SEG:
+                self.plan = RowPlan(row_ptr_host, row_ptr.device)
 
     @property
     def nnz(self):
@@ -53,6 +80,14 @@ def spmm(csr, x, mode, self_coef=0.0, dinv=None, bias=None, act=0, out=None):
     _lib.require_device(x, csr.row_ptr)
     n, d = csr.n_rows, x.shape[1]
     y = out if out is not None else torch.empty((n, d), dtype=torch.float32, device=x.device)
+    pl = csr.plan
+    if pl is not None and d % 4 == 0 and d <= 512:
+        wsb = _lib.call('bignn_spmm_planned_workspace_bytes', pl.n_items, d) if pl.n_multi else 0
+        ws = _ws(wsb, x.device) if wsb else None
+        _lib.call('bignn_spmm_planned_f32', csr.row_ptr, csr.col_idx, pl.item_ptr, pl.item_row, pl.n_items, pl.seg,
+                  pl.multi_rows, pl.n_multi, x, x.stride(0), y, y.stride(0), n, d, int(mode), float(self_coef),
+                  dinv, bias, int(act), ws, int(wsb))
+        return y
     _lib.call('bignn_spmm_f32', csr.row_ptr, csr.col_idx, x, x.stride(0), y, y.stride(0), n, d,
               int(mode), float(self_coef), dinv, bias, int(act))
     return y

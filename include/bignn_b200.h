@@ -101,6 +101,21 @@ int bignn_spmm_f32(const int32_t* row_ptr, const int32_t* col_idx,
                    int32_t n_rows, int32_t D, int32_t mode, float self_coef,
                    const float* dinv, const float* bias, int32_t act, void* stream);
 
+/* Long-row variant for skewed graphs (interaction graphs with hub drugs): the caller splits every
+ * row into work items of at most `seg` neighbours -- item_ptr[n_rows+1] (items per row, prefix sum,
+ * every row has >= 1 item), item_row[n_items], multi_rows[n_multi] = rows with more than one item.
+ * Items are processed by independent sub-warps; rows with several items are finished by a second
+ * kernel that adds the per-item partial sums in item order (deterministic).  Requires D % 4 == 0,
+ * D <= 512 and 16-byte aligned operands. */
+int64_t bignn_spmm_planned_workspace_bytes(int32_t n_items, int32_t D);
+int bignn_spmm_planned_f32(const int32_t* row_ptr, const int32_t* col_idx,
+                           const int32_t* item_ptr, const int32_t* item_row, int32_t n_items, int32_t seg,
+                           const int32_t* multi_rows, int32_t n_multi,
+                           const float* X, int64_t ldx, float* Y, int64_t ldy,
+                           int32_t n_rows, int32_t D, int32_t mode, float self_coef,
+                           const float* dinv, const float* bias, int32_t act,
+                           void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------
  * Dense fp32 transforms:  C[M,N] = act(op(A)[M,K] * op(B)[K,N] + bias[N])
  * op(A) = A (ta=0, A is [M,K]) or A^T (ta=1, A is [K,M]); same for B.

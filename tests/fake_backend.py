@@ -86,6 +86,13 @@ class Fake(object):
         Y[:n, :D] = ACTS[act](out)
         return 0
 
+    def bignn_spmm_planned_workspace_bytes(self, n_items, D):
+        return 16
+
+    def bignn_spmm_planned_f32(self, row_ptr, col_idx, item_ptr, item_row, n_items, seg, multi_rows, n_multi,
+                               X, ldx, Y, ldy, n, D, mode, self_coef, dinv, bias, act, ws, wsb):
+        return self.bignn_spmm_f32(row_ptr, col_idx, X, ldx, Y, ldy, n, D, mode, self_coef, dinv, bias, act)
+
     def bignn_gemm_f32(self, ta, tb, M, N, K, A, lda, B, ldb, C, ldc, bias, act, ws, wsb):
         a = A.t() if ta else A
         b = B.t() if tb else B

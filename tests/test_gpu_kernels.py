@@ -130,6 +130,42 @@ def test_spmm_gcn_vs_oracle(data, drugbank, D, act):
     assert torch.equal(csr.dinv().cpu(), deg.pow(-0.5))
 
 
+@pytest.mark.parametrize('mode', ['gin', 'gcn', 'sum'])
+def test_spmm_long_rows_planned(mode):
+    """hub rows (degree >> 128) go through the work-item variant; same result as the oracle."""
+    n, D = 3000, 64
+    rng = np.random.default_rng(5)
+    hub = np.concatenate([np.zeros(2500, np.int64), np.ones(700, np.int64), rng.integers(0, n, 20000)])
+    oth = np.concatenate([rng.integers(1, n, 2500), rng.integers(2, n, 700), rng.integers(0, n, 20000)])
+    keep = hub != oth
+    key = np.unique(np.concatenate([hub[keep] * n + oth[keep], oth[keep] * n + hub[keep]]))
+    row, col = key // n, key % n
+    ptr = np.zeros(n + 1, np.int64)
+    np.add.at(ptr, row + 1, 1)
+    ptr = np.cumsum(ptr)
+    csr = ops.CSR(torch.as_tensor(ptr.astype(np.int32)).to(DEV), torch.as_tensor(col.astype(np.int32)).to(DEV), n,
+                  row_ptr_host=ptr)
+    assert csr.plan is not None and csr.plan.n_multi >= 2
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(n, D, generator=g)
+    ei = torch.from_numpy(np.stack([row, col]))
+    if mode == 'gin':
+        want = 1.5 * x.double() + torch.zeros(n, D, dtype=torch.float64).index_add_(0, ei[1], x.double()[ei[0]])
+        got = ops.spmm(csr, x.to(DEV), ops.SPMM_GIN, 1.5)
+    elif mode == 'sum':
+        want = torch.zeros(n, D, dtype=torch.float64).index_add_(0, ei[1], x.double()[ei[0]])
+        got = ops.spmm(csr, x.to(DEV), ops.SPMM_SUM)
+    else:
+        bias = torch.randn(D, generator=g)
+        P = {'l.conv.weight': torch.eye(D, dtype=torch.float64), 'l.conv.bias': bias.double()}
+        want = torch.relu(O.gcn_conv(x.double(), ei, P, 'l'))
+        got = ops.spmm(csr, x.to(DEV), ops.SPMM_GCN, 0.0, csr.dinv(), bias.to(DEV), 1)
+    assert rel(got, want) < 2e-6
+    assert torch.equal(got, ops.spmm(csr, x.to(DEV), {'gin': 1, 'sum': 0, 'gcn': 2}[mode],
+                                     1.5 if mode == 'gin' else 0.0, csr.dinv() if mode == 'gcn' else None,
+                                     bias.to(DEV) if mode == 'gcn' else None, 1 if mode == 'gcn' else 0))  # deterministic
+
+
 def test_spmm_is_its_own_transpose_at_scale():
     """size-independent property on a >L2 operand: <y, A x> == <A y, x> for a symmetric graph,
     and A*ones == degree (+ self coefficient) exactly."""
@@ -220,14 +256,15 @@ def test_seg_batch_norm_vs_torch(sizes, C):
     dy = torch.randn(n, C, generator=g)
     ptr = np.concatenate([[0], np.cumsum(sizes)])
     # reference: torch BatchNorm1d applied chunk by chunk, in order
-    bn = torch.nn.BatchNorm1d(C)
+    # (in fp64: torch's own fp32 CPU kernel is 3.5e-5 off an fp64 run at n = 200 000)
+    bn = torch.nn.BatchNorm1d(C).double()
     with torch.no_grad():
         bn.weight.copy_(gamma)
         bn.bias.copy_(beta)
-    xr = x.clone().requires_grad_(True)
+    xr = x.double().requires_grad_(True)
     outs = [bn(xr[ptr[i]:ptr[i + 1]]) for i in range(len(sizes))]
     want = torch.cat(outs)
-    want.backward(dy)
+    want.backward(dy.double())
     rm = torch.zeros(C, device=DEV)
     rv = torch.ones(C, device=DEV)
     nbt = torch.zeros((), dtype=torch.int64, device=DEV)
@@ -244,7 +281,7 @@ def test_seg_batch_norm_vs_torch(sizes, C):
     assert rel(gd.grad, bn.weight.grad) < 5e-6 and rel(bd.grad, bn.bias.grad) < 5e-6
     # eval mode
     bn.eval()
-    assert rel(ops.bn_eval(x.to(DEV), gd.detach(), bd.detach(), rm, rv), bn(x)) < 2e-6
+    assert rel(ops.bn_eval(x.to(DEV), gd.detach(), bd.detach(), rm, rv), bn(x.double())) < 2e-6
 
 
 # ----------------------------------------------------------------------------- readout
