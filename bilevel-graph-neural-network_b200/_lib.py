@@ -41,7 +41,8 @@ SIGNATURES = {
     'bignn_colsum_f32': ('i', 'pliip' 'pl' 's'),
     'bignn_act_bwd_f32': ('i', 'ppplis'),
     'bignn_bn_workspace_bytes': ('l', 'iii'),
-    'bignn_bn_seg_fwd': ('i', 'plpl' 'piii' 'pp' 'ff' 'ppp' 'pp' 'pl' 's'),
+    'bignn_bn_seg_fwd': ('i', 'plpl' 'piii' 'pp' 'ff' 'ppp' 'pp' 'p' 'pl' 's'),
+    'bignn_bn_running_update': ('i', 'ppiifppp' 's'),
     'bignn_bn_eval_fwd': ('i', 'plpl' 'ii' 'pp' 'f' 'pp' 's'),
     'bignn_bn_seg_bwd': ('i', 'plplpl' 'piii' 'ppp' 'pp' 'pl' 's'),
     'bignn_readout_fwd': ('i', 'pl' 'pii' 'i' 'p' 'pli' 's'),

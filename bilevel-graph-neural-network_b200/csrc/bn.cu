@@ -206,8 +206,8 @@ extern "C" int64_t bignn_bn_workspace_bytes(int32_t S, int32_t C, int32_t parts)
 extern "C" int bignn_bn_seg_fwd(const float* X, int64_t ldx, float* Y, int64_t ldy, const int32_t* seg_row_ptr,
                                 int32_t S, int32_t C, int32_t parts, const float* gamma, const float* beta,
                                 float eps, float momentum, float* running_mean, float* running_var,
-                                int64_t* num_batches_tracked, float* mean, float* rstd, void* workspace,
-                                int64_t workspace_bytes, void* stream) {
+                                int64_t* num_batches_tracked, float* mean, float* rstd, double* seg_stats_out,
+                                void* workspace, int64_t workspace_bytes, void* stream) {
   if (S < 0 || C < 0 || parts <= 0) return BIGNN_EINVAL;
   if (S == 0 || C == 0) return 0;
   if (!X || !Y || !seg_row_ptr || !mean || !rstd || ldx < C || ldy < C) return BIGNN_EINVAL;
@@ -216,7 +216,7 @@ extern "C" int bignn_bn_seg_fwd(const float* X, int64_t ldx, float* Y, int64_t l
   cudaStream_t st = (cudaStream_t)stream;
   double* ws_a = (double*)workspace;
   double* ws_b = ws_a + (int64_t)S * parts * C;
-  double* mean_d = ws_b + (int64_t)S * parts * C;
+  double* mean_d = seg_stats_out ? seg_stats_out : ws_b + (int64_t)S * parts * C;
   double* varu_d = mean_d + (int64_t)S * C;
   dim3 grid(S * parts, ceil_div(C, 32));
   k_bn_reduce_part<false><<<grid, 256, 0, st>>>(X, ldx, nullptr, 0, seg_row_ptr, C, parts, nullptr, nullptr, ws_a, ws_b);
@@ -227,6 +227,19 @@ extern "C" int bignn_bn_seg_fwd(const float* X, int64_t ldx, float* Y, int64_t l
     BIGNN_LAUNCH_COUNT(1);
   }
   k_bn_apply<<<grid, 256, 0, st>>>(X, ldx, Y, ldy, seg_row_ptr, C, parts, gamma, beta, mean, rstd);
+  BIGNN_LAUNCH_COUNT(1);
+  return last_launch_status();
+}
+
+extern "C" int bignn_bn_running_update(const double* seg_stats, const int32_t* seg_row_ptr, int32_t S, int32_t C,
+                                       float momentum, float* running_mean, float* running_var,
+                                       int64_t* num_batches_tracked, void* stream) {
+  if (S < 0 || C < 0) return BIGNN_EINVAL;
+  if (S == 0 || C == 0) return 0;
+  if (!seg_stats || !seg_row_ptr || !running_mean || !running_var) return BIGNN_EINVAL;
+  k_bn_running<<<ceil_div(C, 256), 256, 0, (cudaStream_t)stream>>>(seg_stats, seg_stats + (int64_t)S * C, seg_row_ptr, S,
+                                                                  C, (double)momentum, running_mean, running_var,
+                                                                  num_batches_tracked);
   BIGNN_LAUNCH_COUNT(1);
   return last_launch_status();
 }

@@ -14,7 +14,7 @@ src/train.py:75-108,177-182), re-organised for the GPU:
 import numpy as np
 import torch
 
-from . import ops
+from . import ops, dist as bdist
 from .batch import BatchData, unique_graphs_in_order
 from .config import get_flags
 from .graph import MergedGraph
@@ -54,14 +54,14 @@ class _StaticPairBatch(object):
 class _Staging(object):
     """Pinned host buffers for one step's inputs (+ the loss read-back)."""
 
-    def __init__(self, P, N):
-        pin = dict(pin_memory=True)
+    def __init__(self, P, N, cuda=True):
+        pin = dict(pin_memory=True) if cuda else {}
         self.ids = torch.zeros((P, 2), dtype=torch.int32, **pin)
         self.y = torch.zeros(P, dtype=torch.float32, **pin)
         self.e_ptr = torch.zeros(N + 1, dtype=torch.int32, **pin)
         self.e_idx = torch.zeros(2 * P, dtype=torch.int32, **pin)
         self.loss = torch.zeros((), dtype=torch.float32, **pin)
-        self.event = torch.cuda.Event()
+        self.event = torch.cuda.Event() if cuda else None
         self.busy = False
 
     def nbytes_in(self):
@@ -70,33 +70,47 @@ class _Staging(object):
 
 class BiGNNEngine(object):
     def __init__(self, data, model, optimizer=None, lr=None, use_cuda_graph=True, rebuild_each_step=True,
-                 n_staging=4):
+                 n_staging=4, rank=0, world=1, group=None):
         flags = get_flags()
         assert flags.lower_level_layers and flags.higher_level_layers, 'engine runs the Bi-GNN mode'
         self.data, self.model = data, model
         self.device = data.device
-        self.use_cuda_graph = use_cuda_graph
+        self.use_cuda_graph = use_cuda_graph and self.device.type == 'cuda'
         self.rebuild_each_step = rebuild_each_step
         self.optimizer = optimizer if optimizer is not None else torch.optim.Adam(
-            model.parameters(), lr=flags.lr if lr is None else lr, capturable=use_cuda_graph)
+            model.parameters(), lr=flags.lr if lr is None else lr, capturable=self.use_cuda_graph)
         # ---- static all-drug merged graph: chunk schedule of src/train.py:52-71
+        self.rank, self.world, self.group = int(rank), int(world), group
         gids = list(data.gs_map.keys())
-        rows, chunk_ptr = [], [0]
+        chunk_rows = []
         for pairs in all_drug_chunks(gids, flags.batch_size):
             order = unique_graphs_in_order(pairs)
-            rows.extend(data.gs_map[g] for g in order.keys())
-            chunk_ptr.append(len(rows))
-        rows = np.asarray(rows, np.int64)
+            chunk_rows.append(np.asarray([data.gs_map[g] for g in order.keys()], np.int64))
+        self.n_chunks_total = len(chunk_rows)
+        # shard whole chunks over the ranks, balanced by atoms (dist.shard_chunks)
+        weights = [int(data.packed.sizes(r)[0].sum()) for r in chunk_rows]
+        self.chunk_shards = bdist.shard_chunks(weights, self.world)
+        lo, hi = self.chunk_shards[self.rank]
+        self.my_chunks = (lo, hi)
+        all_rows_in_order = np.concatenate(chunk_rows)
+        mine = chunk_rows[lo:hi]
+        rows = np.concatenate(mine) if mine else np.zeros(0, np.int64)
+        chunk_ptr = np.concatenate([[0], np.cumsum([len(r) for r in mine])]).astype(np.int64)
         self.merged = MergedGraph(data.packed, rows, chunk_graph_ptr=chunk_ptr)
+        self._bn_sink = [] if self.world > 1 else None
+        self.merged.bn_stats_sink = self._bn_sink
         # a drug that appears in two chunks is overwritten by the later one in the reference
         # (layers_aggregation.py:72-74); earlier duplicates go to a trash row N
+        first_later = {}
+        for i in range(len(all_rows_in_order) - 1, -1, -1):
+            first_later.setdefault(int(all_rows_in_order[i]), i)      # last occurrence wins
+        offset = int(sum(len(r) for r in chunk_rows[:lo]))
         dst = rows.copy()
-        seen = set()
-        for i in range(len(rows) - 1, -1, -1):
-            if rows[i] in seen:
+        for i in range(len(rows)):
+            if first_later[int(rows[i])] != offset + i:
                 dst[i] = data.N
-            seen.add(rows[i])
         self.dst_row = torch.as_tensor(dst.astype(np.int32)).to(self.device)
+        self._all_chunk_ptr = torch.arange(self.n_chunks_total + 1, dtype=torch.int32, device=self.device)
         self._lower_bd = type('LowerBatch', (), {})()
         self._lower_bd.merge_data = {'merge': self.merged}
         self._lower_bd.merge_higher_level = {}
@@ -122,6 +136,8 @@ class BiGNNEngine(object):
             acts.append(h)
         pooled = ops.readout(acts if self._multi else [h], m.seg_ptr, m.G, self._agg_style,
                              self.dst_row, self.data.N + 1)
+        if self.world > 1:
+            pooled = bdist.sum_disjoint_rows(pooled, self.group)      # the exchange step (NCCL)
         return pooled, acts
 
     def forward(self, pair_batch):
@@ -135,10 +151,26 @@ class BiGNNEngine(object):
             model.acts.append(layer(model.acts[-1], pair_batch, model))
         return model.acts[-1]
 
+    def _sync_lower(self):
+        """after backward on a sharded lower level: sum the partial weight gradients and replay
+        the BatchNorm running-buffer updates in global chunk order."""
+        lower = [p for l in self.model.init_layers for p in l.parameters()]
+        bdist.all_reduce_grads(lower, self.group)
+        s_max = max(hi - lo for lo, hi in self.chunk_shards)
+        for bn, stats in self._bn_sink:
+            allst = bdist.gather_chunk_stats(stats, s_max, self.group)       # [world, 2, s_max, C]
+            parts = [allst[r][:, :hi - lo] for r, (lo, hi) in enumerate(self.chunk_shards)]
+            ordered = torch.cat(parts, dim=1).contiguous()                   # [2, S_total, C]
+            ops.bn_running_update(ordered, self._all_chunk_ptr, self.n_chunks_total, bn.running_mean,
+                                  bn.running_var, bn.num_batches_tracked, bn.momentum)
+        del self._bn_sink[:]
+
     def _device_step(self, pair_batch):
         self.optimizer.zero_grad(set_to_none=True)
         loss = self.forward(pair_batch)
         loss.backward()
+        if self.world > 1:
+            self._sync_lower()
         self.optimizer.step()
         ig = self.data.interaction_combo_nxgraph
         ig.init_x = ig.init_x.detach()
@@ -181,8 +213,11 @@ class BiGNNEngine(object):
         torch.cuda.current_stream().wait_stream(s)
         g = torch.cuda.CUDAGraph()
         self.optimizer.zero_grad(set_to_none=True)
+        from . import _lib
+        n0 = _lib.launch_count()
         with torch.cuda.graph(g):
             loss = self._device_step(sb)
+        self.launches_per_step = _lib.launch_count() - n0
         # undo the warm-up steps: parameters, BN buffers and Adam moments back to where they were
         self._restore(snap)
         if opt_snap is not None:
@@ -199,11 +234,12 @@ class BiGNNEngine(object):
     def _staging(self, P):
         key = P
         if key not in self._stagings:
-            self._stagings[key] = [_Staging(P, self.data.N) for _ in range(self._n_staging)]
+            self._stagings[key] = [_Staging(P, self.data.N, self.device.type == 'cuda')
+                                   for _ in range(self._n_staging)]
         st = self._stagings[key][self._step_idx % self._n_staging]
-        if st.busy:
+        if st.busy and st.event is not None:
             st.event.synchronize()
-            st.busy = False
+        st.busy = False
         return st
 
     def stage_pairs(self, batch_gids, labels):
@@ -241,7 +277,8 @@ class BiGNNEngine(object):
         else:
             loss = self._device_step(sb)
         st.loss.copy_(loss, non_blocking=True)
-        st.event.record()
+        if st.event is not None:
+            st.event.record()
         st.busy = True
         self._step_idx += 1
         self.h2d_bytes_per_step = st.nbytes_in()
@@ -250,7 +287,8 @@ class BiGNNEngine(object):
 
     @staticmethod
     def read_loss(st):
-        st.event.synchronize()
+        if st.event is not None:
+            st.event.synchronize()
         st.busy = False
         return float(st.loss)
 

@@ -76,7 +76,15 @@ class NodeEmbedding(nn.Module):
             t = ops.linear_act(z, lin1.weight, lin1.bias, a, 'oi')
             x = ops.linear_act(t, lin2.weight, lin2.bias, a, 'oi')
         if self.bn:
-            if self.training:
+            sink = getattr(graph, 'bn_stats_sink', None)
+            if self.training and sink is not None:
+                # chunks sharded over several GPUs: keep the per-chunk statistics; the engine replays
+                # the running-buffer updates in global chunk order after exchanging them
+                stats = torch.empty((2, S, x.shape[1]), dtype=torch.float64, device=x.device)
+                x = ops.seg_batch_norm(x, self.bn.weight, self.bn.bias, seg, S, None, None, None,
+                                       self.bn.eps, self.bn.momentum, stats)
+                sink.append((self.bn, stats))
+            elif self.training:
                 x = ops.seg_batch_norm(x, self.bn.weight, self.bn.bias, seg, S, self.bn.running_mean,
                                        self.bn.running_var, self.bn.num_batches_tracked,
                                        self.bn.eps, self.bn.momentum)

@@ -213,7 +213,7 @@ class _SegBatchNorm(torch.autograd.Function):
     """Train-mode BatchNorm1d with independent statistics per row segment."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, seg_row_ptr, S, running_mean, running_var, nbt, eps, momentum):
+    def forward(ctx, x, gamma, beta, seg_row_ptr, S, running_mean, running_var, nbt, eps, momentum, stats_out):
         x = _f32c(x)
         _lib.require_device(x)
         rows, C = x.shape
@@ -224,7 +224,7 @@ class _SegBatchNorm(torch.autograd.Function):
         wsb = _lib.call('bignn_bn_workspace_bytes', S, C, parts)
         ws = _ws(wsb, x.device)
         _lib.call('bignn_bn_seg_fwd', x, x.stride(0), y, y.stride(0), seg_row_ptr, S, C, parts, gamma, beta,
-                  float(eps), float(momentum), running_mean, running_var, nbt, mean, rstd, ws, int(wsb))
+                  float(eps), float(momentum), running_mean, running_var, nbt, mean, rstd, stats_out, ws, int(wsb))
         ctx.S, ctx.parts, ctx.seg = S, parts, seg_row_ptr
         ctx.save_for_backward(x, gamma, mean, rstd)
         return y
@@ -241,7 +241,7 @@ class _SegBatchNorm(torch.autograd.Function):
         ws = _ws(wsb, x.device)
         _lib.call('bignn_bn_seg_bwd', x, x.stride(0), dy, dy.stride(0), dx, dx.stride(0), ctx.seg, ctx.S, C,
                   ctx.parts, gamma, mean, rstd, dgamma, dbeta, ws, int(wsb))
-        return dx, dgamma, dbeta, None, None, None, None, None, None, None
+        return dx, dgamma, dbeta, None, None, None, None, None, None, None, None
 
 
 class _Readout(torch.autograd.Function):
@@ -337,8 +337,18 @@ def linear_act(x, weight, bias=None, act=0, layout='oi'):
     return _LinearAct.apply(x, weight, bias, act, layout)
 
 
-def seg_batch_norm(x, gamma, beta, seg_row_ptr, S, running_mean, running_var, nbt, eps=1e-5, momentum=0.1):
-    return _SegBatchNorm.apply(x, gamma, beta, seg_row_ptr, S, running_mean, running_var, nbt, eps, momentum)
+def seg_batch_norm(x, gamma, beta, seg_row_ptr, S, running_mean, running_var, nbt, eps=1e-5, momentum=0.1,
+                   stats_out=None):
+    """stats_out: optional fp64 [2,S,C] buffer receiving the per-segment mean / unbiased variance
+    (multi-GPU: running buffers are then advanced by `bn_running_update` after an exchange)."""
+    return _SegBatchNorm.apply(x, gamma, beta, seg_row_ptr, S, running_mean, running_var, nbt, eps, momentum,
+                               stats_out)
+
+
+def bn_running_update(seg_stats, seg_row_ptr, S, running_mean, running_var, nbt, momentum=0.1):
+    C = running_mean.numel()
+    _lib.call('bignn_bn_running_update', seg_stats, seg_row_ptr, int(S), int(C), float(momentum), running_mean,
+              running_var, nbt)
 
 
 def bn_eval(x, gamma, beta, running_mean, running_var, eps=1e-5):

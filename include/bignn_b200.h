@@ -152,8 +152,15 @@ int bignn_bn_seg_fwd(const float* X, int64_t ldx, float* Y, int64_t ldy,
                      const int32_t* seg_row_ptr, int32_t S, int32_t C, int32_t parts,
                      const float* gamma, const float* beta, float eps, float momentum,
                      float* running_mean, float* running_var, int64_t* num_batches_tracked,
-                     float* mean, float* rstd,
+                     float* mean, float* rstd, double* seg_stats_out,
                      void* workspace, int64_t workspace_bytes, void* stream);
+/* seg_stats_out (optional, [2, S, C] fp64): per-segment batch mean and UNBIASED variance.  When the
+ * chunks of one all-drug pass are sharded over several GPUs, each rank passes running_mean = NULL,
+ * the ranks exchange these statistics, and every rank replays the reference's sequential momentum
+ * updates (one per chunk, in chunk order) with bignn_bn_running_update. */
+int bignn_bn_running_update(const double* seg_stats, const int32_t* seg_row_ptr, int32_t S, int32_t C,
+                            float momentum, float* running_mean, float* running_var,
+                            int64_t* num_batches_tracked, void* stream);
 /* eval mode: normalise with the running buffers (one launch, no statistics) */
 int bignn_bn_eval_fwd(const float* X, int64_t ldx, float* Y, int64_t ldy, int32_t rows, int32_t C,
                       const float* gamma, const float* beta, float eps,

@@ -117,8 +117,19 @@ class Fake(object):
             dX.copy_(dY)
         return 0
 
+    def bignn_bn_running_update(self, stats, seg, S, C, mom, rm, rv, nbt):
+        st = stats.view(2, S, C)
+        for s in range(S):
+            if int(seg[s + 1]) - int(seg[s]) <= 0:
+                continue
+            rm.copy_((mom * st[0, s] + (1 - mom) * rm.double()).float())
+            rv.copy_((mom * st[1, s] + (1 - mom) * rv.double()).float())
+            if nbt is not None:
+                nbt += 1
+        return 0
+
     def bignn_bn_seg_fwd(self, X, ldx, Y, ldy, seg, S, C, parts, gamma, beta, eps, mom, rm, rv, nbt, mean, rstd,
-                         ws, wsb):
+                         stats_out, ws, wsb):
         for s in range(S):
             a, b = int(seg[s]), int(seg[s + 1])
             x = X[a:b].double()
@@ -127,6 +138,9 @@ class Fake(object):
             var = (x * x).mean(0) - mu * mu
             mean[s] = mu.float()
             rstd[s] = (1.0 / torch.sqrt(var + eps)).float()
+            if stats_out is not None:
+                stats_out.view(2, S, C)[0, s] = mu
+                stats_out.view(2, S, C)[1, s] = var * n / max(n - 1, 1)
             if rm is not None:
                 rm.copy_((mom * mu + (1 - mom) * rm.double()).float())
                 rv.copy_((mom * var * n / max(n - 1, 1) + (1 - mom) * rv.double()).float())
