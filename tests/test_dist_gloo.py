@@ -85,7 +85,7 @@ def test_shard_chunks_covers_and_balances():
 def test_two_rank_step_equals_single_rank_and_golden(tmp_path):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
-    _worker(0, 1, port, str(tmp_path))
+    mp.spawn(_worker, args=(1, port, str(tmp_path)), nprocs=1, join=True)   # own process: keeps this one's threads
     r0 = np.load(os.path.join(tmp_path, 'w2_r0.npz'))
     r1 = np.load(os.path.join(tmp_path, 'w2_r1.npz'))
     s = np.load(os.path.join(tmp_path, 'w1_r0.npz'))

@@ -49,6 +49,10 @@ def test_negative_sampler_sequence_bit_exact(drugbank, golden_dir):
 
 @pytest.fixture(scope='module')
 def oracle_step(drugbank, step_golden, gin_gcn_specs):
+    # the golden vectors were recorded with 8 intra-op threads; torch's CPU reductions change their
+    # association with the thread count, and the lower-level gradients are ill-conditioned enough
+    #  for that alone to move them by 4e-3
+    torch.set_num_threads(8)
     z = step_golden
     sd = O.state_from_npz(z, 'sd0/')
     for k in list(sd):                                   # BN buffers as they stood before the step
