@@ -53,6 +53,20 @@ SIGNATURES = {
     'bignn_bce_bwd': ('i', 'ppipps'),
     'bignn_bce_logits_fwd': ('i', 'ppips'),
     'bignn_bce_logits_bwd': ('i', 'ppipps'),
+    'bignn_gat_fwd': ('i', 'ppii' 'pl' 'pp' 'fi' 'pl' 'p' 's'),
+    'bignn_gat_bwd_workspace_bytes': ('l', 'ii'),
+    'bignn_gat_bwd': ('i', 'ppii' 'pl' 'pp' 'fi' 'pl' 'pl' 'p' 'pl' 'p' 'pl' 's'),
+    'bignn_act_fwd_f32': ('i', 'pplis'),
+    'bignn_prelu_fwd_f32': ('i', 'pplipis'),
+    'bignn_prelu_bwd_f32': ('i', 'pppplipis'),
+    'bignn_rownorm_fwd_f32': ('i', 'plpliips'),
+    'bignn_rownorm_bwd_f32': ('i', 'plplppliis'),
+    'bignn_gate_mul_fwd_f32': ('i', 'pppls'),
+    'bignn_gate_mul_bwd_f32': ('i', 'pppppls'),
+    'bignn_pair_dot_fwd_f32': ('i', 'pliipis'),
+    'bignn_pair_dot_bwd_f32': ('i', 'pliippipls'),
+    'bignn_ce_fwd': ('i', 'plpiips'),
+    'bignn_ce_bwd': ('i', 'plpiippls'),
 }
 
 _CT = {'p': ctypes.c_void_p, 'i': ctypes.c_int32, 'l': ctypes.c_int64, 'f': ctypes.c_float,

@@ -104,11 +104,12 @@ class BatchData(object):
         self._pair_rows = None
 
     # -- device views used by the layers ---------------------------------------------
-    def y_true_device(self):
+    def y_true_device(self, as_int=False):
         if self._y is None:
-            y = np.asarray([p.true_label for p in self.pair_list], np.float32)
-            self._y = torch.as_tensor(y).to(self.dataset.device, non_blocking=True)
-        return self._y
+            y = np.asarray([p.true_label for p in self.pair_list])
+            self._y = (torch.as_tensor(y.astype(np.float32)).to(self.dataset.device, non_blocking=True),
+                       torch.as_tensor(y.astype(np.int32)).to(self.dataset.device, non_blocking=True))
+        return self._y[1] if as_int else self._y[0]
 
     def pair_rows_device(self, n_rows, higher=True, unique=True):
         """[P,2] int32 rows of the scored embeddings (layers_link_pred.py:46-54) and the
@@ -134,7 +135,7 @@ class BatchData(object):
     def link_preds(self):
         p = self._preds.cpu().numpy()
         for rec, v in zip(self.pair_list, p):
-            rec.link_pred = float(v[0]) if v.shape[0] == 1 else v
+            rec.link_pred = float(v) if v.ndim == 0 else (float(v[0]) if v.shape[0] == 1 else v)
         return p
 
     def restore_interaction_nxgraph(self):

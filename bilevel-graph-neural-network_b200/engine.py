@@ -41,8 +41,8 @@ class _StaticPairBatch(object):
         self.batch_gids = np.zeros((P, 2), np.int64)
         self.preds = None
 
-    def y_true_device(self):
-        return self.y
+    def y_true_device(self, as_int=False):
+        return self.y.to(torch.int32) if as_int else self.y
 
     def pair_rows_device(self, n_rows, higher=True, unique=True):
         return self.ids, self.entry_csr

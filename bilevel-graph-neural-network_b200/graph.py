@@ -78,6 +78,7 @@ class MergedGraph(object):
         self.chunk_graph_ptr_host = np.asarray(chunk_graph_ptr, np.int64)
         self.S = len(self.chunk_graph_ptr_host) - 1
         self.chunk_row_ptr = _i32(self.seg_ptr_host[self.chunk_graph_ptr_host], dev)
+        self.chunk_graph_ptr = _i32(self.chunk_graph_ptr_host, dev)
         self._ws_bytes = int(_lib.call('bignn_merge_build_workspace_bytes', self.G))
         self._ws = torch.empty(max(self._ws_bytes, 16), dtype=torch.uint8, device=dev)
         self.build()

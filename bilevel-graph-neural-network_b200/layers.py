@@ -5,7 +5,12 @@ import torch.nn as nn
 
 from . import ops
 from .config import get_flags
-from .layers_util import create_act
+from .layers_util import create_act, apply_linear_act
+
+# softmax grouping index of GATConv: 'source' = torch-geometric 1.1.x (the reference's pin,
+# Dockerfile:32), 'target' = >= 1.2.  Unverifiable offline -> switchable.
+GAT_SOFTMAX_GROUP = 'source'
+
 
 
 class GINConv(nn.Module):
@@ -34,6 +39,19 @@ class GCNConv(nn.Module):
         _glorot(self.weight)
 
 
+class GATConv(nn.Module):
+    """PyG 1.1.2 GATConv parameters, heads=1: weight [in,out], att [1,1,2*out] glorot, bias zeros."""
+
+    def __init__(self, in_channels, out_channels, negative_slope=0.2):
+        super().__init__()
+        self.negative_slope = negative_slope
+        self.weight = nn.Parameter(torch.empty(in_channels, out_channels))
+        self.att = nn.Parameter(torch.empty(1, 1, 2 * out_channels))
+        self.bias = nn.Parameter(torch.zeros(out_channels))
+        _glorot(self.weight)
+        _glorot(self.att)
+
+
 class NodeEmbedding(nn.Module):
     def __init__(self, type, in_dim, out_dim, act, bn, normalize, higher_level=False, use_edge_attr=None):
         super().__init__()
@@ -49,14 +67,13 @@ class NodeEmbedding(nn.Module):
             self.act = create_act(act, out_dim)
             self.conv = GINConv(nn.Sequential(nn.Linear(in_dim, out_dim), self.act, nn.Linear(out_dim, out_dim)))
         elif type == 'gat':
-            raise NotImplementedError('gat is built in a later step of the path')
+            self.conv = GATConv(in_dim, out_dim)
+            self.act = create_act(act, out_dim)
         else:
             raise ValueError('Unknown node embedding layer type {}'.format(type))
         self.bn = bn
         if self.bn:
             self.bn = nn.BatchNorm1d(out_dim)
-        if normalize:
-            raise NotImplementedError('normalize=True is not on the Bi-GNN default path')
 
     def forward(self, ins, batch_data, model):
         if self.higher_level:
@@ -66,15 +83,21 @@ class NodeEmbedding(nn.Module):
             graph = batch_data.merge_data['merge']
             seg, S = graph.chunk_row_ptr, graph.S
         csr = graph.csr
-        a = self.act.code
+        a = self.act.code                   # None for PReLU (not fusable: it has a parameter)
         if self.type == 'gcn':
             h = ops.linear_act(ins, self.conv.weight, None, 0, 'io')
-            x = ops.gcn_propagate(h, self.conv.bias, csr, a)
+            x = ops.gcn_propagate(h, self.conv.bias, csr, a if a is not None else 0)
+            if a is None:
+                x = self.act(x)
+        elif self.type == 'gat':
+            h = ops.linear_act(ins, self.conv.weight, None, 0, 'io')
+            x = ops.gat_conv(h, self.conv.att, self.conv.bias, csr, self.conv.negative_slope, GAT_SOFTMAX_GROUP)
+            x = ops.activation(x, a) if a is not None else self.act(x)
         else:
             z = ops.gin_aggregate(ins, csr, self._eps_value())
             lin1, lin2 = self.conv.nn[0], self.conv.nn[2]
-            t = ops.linear_act(z, lin1.weight, lin1.bias, a, 'oi')
-            x = ops.linear_act(t, lin2.weight, lin2.bias, a, 'oi')
+            t = apply_linear_act(z, lin1, self.act)
+            x = apply_linear_act(t, lin2, self.act)
         if self.bn:
             sink = getattr(graph, 'bn_stats_sink', None)
             if self.training and sink is not None:
@@ -92,6 +115,8 @@ class NodeEmbedding(nn.Module):
                 x = ops.bn_eval(x, self.bn.weight, self.bn.bias, self.bn.running_mean, self.bn.running_var,
                                 self.bn.eps)
         model.store_layer_output(self, x)
+        if self.normalize:
+            x = ops.row_normalize(x)
         return x
 
     def _eps_value(self):
@@ -112,9 +137,9 @@ class Loss(nn.Module):
         self.type = type
         if type not in ('BCE', 'BCEWithLogits', 'CE'):
             raise ValueError('Unknown loss layer type {}'.format(type))
-        if type == 'CE':
-            raise NotImplementedError('CE (DrugCombo multi-class) is built in a later step of the path')
 
     def forward(self, ins, batch_data, _):
+        if self.type == 'CE':
+            return ops.cross_entropy(ins, batch_data.y_true_device(as_int=True))
         y_true = batch_data.y_true_device()
         return ops.bce(ins.view(-1), y_true, logits=(self.type == 'BCEWithLogits'))

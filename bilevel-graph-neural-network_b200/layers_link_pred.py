@@ -20,9 +20,14 @@ class LinkPred(nn.Module):
         self.multi_label_pred = multi_label_pred
         if self.type not in ['dot_product', 'mlp_concat']:
             raise NotImplementedError
-        if self.type == 'dot_product' or weight_dim:
-            raise NotImplementedError('only mlp_concat is on the Bi-GNN path')
-        if multi_label_pred:
+        if weight_dim:
+            self.weight_matrix = nn.Parameter(torch.zeros((weight_dim, weight_dim)))
+            nn.init.xavier_normal_(self.weight_matrix, gain=nn.init.calculate_gain('relu'))
+        if self.multi_label_pred:
+            assert self.type == 'ntn' or self.type == 'mlp_concat'
+        if self.type != 'mlp_concat':
+            pass
+        elif multi_label_pred:
             dims = self._calc_mlp_dims(mlp_dim * 2, num_labels, division=8)
             self.mlp_concat = MLP(mlp_dim * 2, num_labels, num_hidden_lyr=len(dims), hidden_channels=dims, bn=False)
         else:
@@ -43,7 +48,10 @@ class LinkPred(nn.Module):
                                                     higher=get_flags().higher_level_layers,
                                                     unique=self.batch_unique_graphs)
         z = ops.pair_gather_norm(ins, ids_dev, ecsr)
-        final = 0 if self.multi_label_pred else ops.ACT_CODES['sigmoid']
-        pair_preds = self.mlp_concat(z, final_act=final)
+        if self.type == 'dot_product':
+            pair_preds = ops.pair_dot(z, ops.ACT_CODES['sigmoid'])
+        else:
+            final = 0 if self.multi_label_pred else ops.ACT_CODES['sigmoid']
+            pair_preds = self.mlp_concat(z, final_act=final)
         batch_data.assign_link_preds(pair_preds)
         return pair_preds

@@ -21,12 +21,30 @@ class Act(nn.Module):
         return self.name
 
 
+class PReLUAct(nn.PReLU):
+    """nn.PReLU parameters (state_dict key `act.weight`); applied by the prelu kernels."""
+    name = 'prelu'
+    code = None
+
+    def forward(self, x):
+        return ops.prelu(x, self.weight)
+
+
 def create_act(act, num_parameters=None):
     if act in ('relu', 'sigmoid', 'tanh', 'identity'):
         return Act(act)
     if act == 'prelu':
-        raise NotImplementedError('prelu is not on the B200 path yet')
+        return PReLUAct(num_parameters if num_parameters is not None else 1)
     raise ValueError('Unknown activation function {}'.format(act))
+
+
+def apply_linear_act(x, lin, act_module, layout='oi'):
+    """act(linear(x)) with the activation fused into the GEMM epilogue when it can be."""
+    if act_module is None:
+        return ops.linear_act(x, lin.weight, lin.bias, 0, layout)
+    if act_module.code is not None:
+        return ops.linear_act(x, lin.weight, lin.bias, act_module.code, layout)
+    return act_module(ops.linear_act(x, lin.weight, lin.bias, 0, layout))
 
 
 class MLP(nn.Module):
@@ -42,8 +60,6 @@ class MLP(nn.Module):
             hidden_channels = [input_dim for _ in range(num_hidden_lyr)]
         elif len(hidden_channels) != num_hidden_lyr:
             raise ValueError('number of hidden layers should be the same as the lengh of hidden_channels')
-        if bn:
-            raise NotImplementedError('MLP with BatchNorm is not on the Bi-GNN path')
         self.layer_channels = [input_dim] + list(hidden_channels) + [output_dim]
         self.activation = create_act(activation_type)
         self.layers = nn.ModuleList()
@@ -52,10 +68,25 @@ class MLP(nn.Module):
             nn.init.xavier_uniform_(lin.weight, gain=nn.init.calculate_gain('relu'))
             self.layers.append(lin)
         self.bn = bn
+        if self.bn:
+            self.bn = nn.ModuleList([nn.BatchNorm1d(dim) for dim in self.layer_channels[1:-1]])
 
-    def forward(self, x, final_act=0):
+    def forward(self, x, final_act=0, seg=None):
+        """seg = (row_ptr int32 device tensor, S): independent BatchNorm batches (needed when bn)."""
         n = len(self.layers)
         for i, lin in enumerate(self.layers):
-            act = self.activation.code if i < n - 1 else final_act
-            x = ops.linear_act(x, lin.weight, lin.bias, act, 'oi')
+            if i == n - 1:
+                x = ops.linear_act(x, lin.weight, lin.bias, final_act, 'oi')
+            elif self.bn:
+                x = ops.linear_act(x, lin.weight, lin.bias, 0, 'oi')
+                b = self.bn[i]
+                if self.training:
+                    ptr, S = seg
+                    x = ops.seg_batch_norm(x, b.weight, b.bias, ptr, S, b.running_mean, b.running_var,
+                                           b.num_batches_tracked, b.eps, b.momentum)
+                else:
+                    x = ops.bn_eval(x, b.weight, b.bias, b.running_mean, b.running_var, b.eps)
+                x = ops.activation(x, self.activation.code) if self.activation.code is not None else self.activation(x)
+            else:
+                x = apply_linear_act(x, lin, self.activation)
         return x

@@ -325,6 +325,189 @@ class _BCE(torch.autograd.Function):
         return dp, None, None
 
 
+class _GatConv(torch.autograd.Function):
+    """PyG 1.1.2 GATConv propagate, 1 head: out = edge_softmax-weighted sum of h + bias."""
+
+    @staticmethod
+    def forward(ctx, h, att, bias, csr, slope, group_target):
+        h = _f32c(h)
+        _lib.require_device(h, att)
+        n, D = h.shape
+        out = torch.empty_like(h)
+        scratch = torch.empty(4 * max(n, 1), dtype=torch.float32, device=h.device)
+        a = att.reshape(-1)
+        _lib.call('bignn_gat_fwd', csr.row_ptr, csr.col_idx, n, D, h, h.stride(0), a, bias, float(slope),
+                  int(group_target), out, out.stride(0), scratch)
+        ctx.csr, ctx.slope, ctx.group = csr, float(slope), int(group_target)
+        ctx.att_shape = att.shape
+        ctx.save_for_backward(h, a, bias, out, scratch)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        h, a, bias, out, scratch = ctx.saved_tensors
+        dout = _f32c(dout)
+        n, D = h.shape
+        dh = torch.empty_like(h)
+        dpq = torch.empty(2 * max(n, 1), dtype=torch.float32, device=h.device)
+        wsb = _lib.call('bignn_gat_bwd_workspace_bytes', n, D)
+        ws = _ws(wsb, h.device)
+        _lib.call('bignn_gat_bwd', ctx.csr.row_ptr, ctx.csr.col_idx, n, D, h, h.stride(0), a, bias, ctx.slope,
+                  ctx.group, out, out.stride(0), dout, dout.stride(0), scratch, dh, dh.stride(0), dpq, ws, int(wsb))
+        datt = gemm(dpq[:2 * n].view(2, n), h).reshape(ctx.att_shape) if ctx.needs_input_grad[1] else None
+        dbias = colsum(dout) if bias is not None and ctx.needs_input_grad[2] else None
+        return dh, datt, dbias, None, None, None
+
+
+class _Act(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, act):
+        x = _f32c(x)
+        _lib.require_device(x)
+        y = torch.empty_like(x)
+        _lib.call('bignn_act_fwd_f32', x, y, x.numel(), int(act))
+        ctx.act = act
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        return act_bwd(y, dy, ctx.act), None
+
+
+class _PReLU(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight):
+        x = _f32c(x)
+        _lib.require_device(x, weight)
+        y = torch.empty_like(x)
+        _lib.call('bignn_prelu_fwd_f32', x, y, x.shape[0], x.shape[1], weight, weight.numel())
+        ctx.save_for_backward(x, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = _f32c(dy)
+        dx = torch.empty_like(x)
+        t = torch.empty_like(x)
+        _lib.call('bignn_prelu_bwd_f32', x, dy, dx, t, x.shape[0], x.shape[1], weight, weight.numel())
+        dw = colsum(t) if weight.numel() > 1 else colsum(t.view(-1, 1))
+        return dx, dw
+
+
+class _RowNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _f32c(x)
+        _lib.require_device(x)
+        y = torch.empty_like(x)
+        nrm = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+        _lib.call('bignn_rownorm_fwd_f32', x, x.stride(0), y, y.stride(0), x.shape[0], x.shape[1], nrm)
+        ctx.save_for_backward(y, nrm)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        y, nrm = ctx.saved_tensors
+        dy = _f32c(dy)
+        dx = torch.empty_like(y)
+        _lib.call('bignn_rownorm_bwd_f32', y, y.stride(0), dy, dy.stride(0), nrm, dx, dx.stride(0), y.shape[0],
+                  y.shape[1])
+        return dx
+
+
+class _GateMul(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gate, w):
+        gate, w = _f32c(gate), _f32c(w)
+        _lib.require_device(gate, w)
+        o = torch.empty_like(w)
+        _lib.call('bignn_gate_mul_fwd_f32', gate, w, o, w.numel())
+        ctx.save_for_backward(gate, w)
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        gate, w = ctx.saved_tensors
+        do = _f32c(do)
+        dg, dw = torch.empty_like(gate), torch.empty_like(w)
+        _lib.call('bignn_gate_mul_bwd_f32', gate, w, do, dg, dw, w.numel())
+        return dg, dw
+
+
+class _PairDot(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, act):
+        z = _f32c(z)
+        _lib.require_device(z)
+        P, D = z.shape[0], z.shape[1] // 2
+        out = torch.empty(P, dtype=torch.float32, device=z.device)
+        _lib.call('bignn_pair_dot_fwd_f32', z, z.stride(0), P, D, out, int(act))
+        ctx.act = act
+        ctx.save_for_backward(z, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        z, out = ctx.saved_tensors
+        dout = _f32c(dout)
+        dz = torch.empty_like(z)
+        _lib.call('bignn_pair_dot_bwd_f32', z, z.stride(0), z.shape[0], z.shape[1] // 2, out, dout, int(ctx.act), dz,
+                  dz.stride(0))
+        return dz, None
+
+
+class _CE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels):
+        logits = _f32c(logits)
+        _lib.require_device(logits, labels)
+        loss = torch.empty((), dtype=torch.float32, device=logits.device)
+        _lib.call('bignn_ce_fwd', logits, logits.stride(0), labels, logits.shape[0], logits.shape[1], loss)
+        ctx.save_for_backward(logits, labels)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        logits, labels = ctx.saved_tensors
+        d = torch.empty_like(logits)
+        _lib.call('bignn_ce_bwd', logits, logits.stride(0), labels, logits.shape[0], logits.shape[1], _f32c(dloss), d,
+                  d.stride(0))
+        return d, None
+
+
+def gat_conv(h, att, bias, csr, negative_slope=0.2, group='source'):
+    if group not in ('source', 'target'):
+        raise ValueError('GAT softmax group must be source or target')
+    return _GatConv.apply(h, att, bias, csr, negative_slope, 1 if group == 'target' else 0)
+
+
+def activation(x, act):
+    return x if act == 0 else _Act.apply(x, act)
+
+
+def prelu(x, weight):
+    return _PReLU.apply(x, weight)
+
+
+def row_normalize(x):
+    return _RowNorm.apply(x)
+
+
+def gate_mul(gate, w):
+    return _GateMul.apply(gate, w)
+
+
+def pair_dot(z, act=0):
+    return _PairDot.apply(z, act)
+
+
+def cross_entropy(logits, labels_i32):
+    return _CE.apply(logits, labels_i32)
+
+
 def gin_aggregate(x, csr, eps=0.0):
     return _GinAggregate.apply(x, csr, eps)
 

@@ -215,6 +215,59 @@ int bignn_bce_logits_fwd(const float* x, const float* y, int32_t P, float* loss,
 int bignn_bce_logits_bwd(const float* x, const float* y, int32_t P, const float* dloss, float* dx,
                          void* stream);
 
+/* ---------------------------------------------------------------------------
+ * One-head GAT edge-softmax message passing (PyG 1.1.2 GATConv reached from
+ * model/layers.py:32-34,54).  H = x W is computed by bignn_gemm_f32.
+ * att[2D] = [att_i ; att_j] (target part, source part).  group_target = 0 groups the
+ * softmax by the SOURCE node (torch-geometric 1.1.x), 1 by the TARGET (>= 1.2).
+ * scratch4n[4n] floats (p, q, max, sum) are produced by fwd and consumed by bwd.
+ * bwd returns dH and dpq[2n] = (d p, d q); d att = [dp^T H ; dq^T H] (a GEMM).
+ * D <= 128.
+ * ------------------------------------------------------------------------- */
+int bignn_gat_fwd(const int32_t* row_ptr, const int32_t* col_idx, int32_t n, int32_t D,
+                  const float* H, int64_t ldh, const float* att, const float* bias,
+                  float negative_slope, int32_t group_target, float* out, int64_t ldo,
+                  float* scratch4n, void* stream);
+int64_t bignn_gat_bwd_workspace_bytes(int32_t n, int32_t D);
+int bignn_gat_bwd(const int32_t* row_ptr, const int32_t* col_idx, int32_t n, int32_t D,
+                  const float* H, int64_t ldh, const float* att, const float* bias,
+                  float negative_slope, int32_t group_target, const float* out, int64_t ldo,
+                  const float* dOut, int64_t lddo, const float* scratch4n,
+                  float* dH, int64_t lddh, float* dpq,
+                  float* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Elementwise / row-wise operators.
+ *   act_fwd            standalone activation (MLP with BatchNorm: act(bn(linear(x))),
+ *                      model/layers_util.py:51-52)
+ *   prelu_fwd/bwd      nn.PReLU (create_act 'prelu', model/layers_util.py:63-64); bwd also
+ *                      writes T = dY * min(x,0)/x-part whose column sums are d slope
+ *   rownorm_fwd/bwd    F.normalize(p=2, dim=1) of NodeEmbedding normalize=True (model/layers.py:60-61)
+ *   gate_mul_fwd/bwd   sigmoid(gate) * weight of the gmn_aggr readout (model/layers_aggregation.py:90-93)
+ *   pair_dot_fwd/bwd   dot-product scorer sigmoid(<g1, g2>) (model/layers_link_pred.py:66-67)
+ *   ce_fwd/bwd         nn.CrossEntropyLoss, mean (model/layers.py:75,85-88); labels int32
+ * ------------------------------------------------------------------------- */
+int bignn_act_fwd_f32(const float* X, float* Y, int64_t n, int32_t act, void* stream);
+int bignn_prelu_fwd_f32(const float* X, float* Y, int64_t rows, int32_t C, const float* w, int32_t nw,
+                        void* stream);
+int bignn_prelu_bwd_f32(const float* X, const float* dY, float* dX, float* T, int64_t rows, int32_t C,
+                        const float* w, int32_t nw, void* stream);
+int bignn_rownorm_fwd_f32(const float* X, int64_t ldx, float* Y, int64_t ldy, int32_t rows, int32_t D,
+                          float* nrm, void* stream);
+int bignn_rownorm_bwd_f32(const float* Y, int64_t ldy, const float* dY, int64_t lddy, const float* nrm,
+                          float* dX, int64_t lddx, int32_t rows, int32_t D, void* stream);
+int bignn_gate_mul_fwd_f32(const float* G, const float* W, float* O, int64_t n, void* stream);
+int bignn_gate_mul_bwd_f32(const float* G, const float* W, const float* dO, float* dG, float* dW,
+                           int64_t n, void* stream);
+int bignn_pair_dot_fwd_f32(const float* Z, int64_t ldz, int32_t P, int32_t D, float* out, int32_t act,
+                           void* stream);
+int bignn_pair_dot_bwd_f32(const float* Z, int64_t ldz, int32_t P, int32_t D, const float* out,
+                           const float* dout, int32_t act, float* dZ, int64_t lddz, void* stream);
+int bignn_ce_fwd(const float* logits, int64_t ldx, const int32_t* labels, int32_t P, int32_t K,
+                 float* loss, void* stream);
+int bignn_ce_bwd(const float* logits, int64_t ldx, const int32_t* labels, int32_t P, int32_t K,
+                 const float* dloss, float* dlogits, int64_t lddx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

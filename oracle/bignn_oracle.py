@@ -604,3 +604,31 @@ class OracleTrainer(object):
         loss.backward()
         adam_step(self.model.P, self.adam)
         return float(loss.detach()), len(gids)
+
+
+# --------------------------------------------------------------------------
+# non-default readouts / heads (model/layers_aggregation.py:45-56,78-95;
+# model/layers_util.py:44-57 MLP; model/layers_link_pred.py:66-67)
+# --------------------------------------------------------------------------
+def mlp_forward(x, P, p, n_layers, bn=False, training=True):
+    """model/layers_util.py:44-57: act(bn(linear)) on all but the last layer (relu)."""
+    for i in range(n_layers):
+        x = F.linear(x, P[p + '.layers.%d.weight' % i], P[p + '.layers.%d.bias' % i])
+        if i < n_layers - 1:
+            if bn:
+                x = F.batch_norm(x, None, None, P[p + '.bn.%d.weight' % i], P[p + '.bn.%d.bias' % i], True, 0.1, 1e-5)
+            x = torch.relu(x)
+    return x
+
+
+def deepsets_readout(x, batch, G, P, p, n_layers):
+    h = mlp_forward(x, P, p + '.phi', n_layers)
+    h = readout([h], batch, G, 'avg_pool')
+    return mlp_forward(h, P, p + '.rho', n_layers)
+
+
+def gmn_aggr_readout(x, batch, G, P, p):
+    w = mlp_forward(x, P, p + '.weight_func', 2, bn=True)
+    g = torch.sigmoid(mlp_forward(x, P, p + '.gate_func', 2, bn=True))
+    emb = _scatter_rows(g * w, batch, G)
+    return mlp_forward(emb, P, p + '.mlp_graph', 2, bn=True)

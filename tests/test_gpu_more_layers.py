@@ -1,0 +1,219 @@
+"""Parity of the remaining SURVEY 8(a) rows on the GPU (`-m gpu`): GAT (a8), sum / deepsets /
+gated readouts (a10), dot-product and multi-class scorers (a13), CE / BCEWithLogits (a14),
+PReLU / sigmoid / tanh activations and normalize=True (a6/a7), each through the layer classes of
+the registry against the CPU oracle on seeded inputs (tolerances at the asserts)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import bignn_b200 as B
+from bignn_b200 import ops, layers as L
+from oracle import bignn_oracle as O
+
+DEV = 'cuda:0'
+
+
+def rel(a, b):
+    a = np.asarray(a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else a, np.float64)
+    b = np.asarray(b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.fixture(scope='module')
+def data(golden_dir):
+    B._lib.load()
+    B.set_flags(B.make_flags(device=DEV))
+    return B.BiGNNData.from_npz(os.path.join(golden_dir, 'drugbank_packed.npz'), device=DEV)
+
+
+class FakeModel(object):
+    def __init__(self):
+        self.acts = None
+
+    def store_layer_output(self, layer, x):
+        pass
+
+
+def params_of(module, prefix):
+    return {prefix + '.' + k: v.detach().cpu().clone().requires_grad_(v.requires_grad and v.is_floating_point())
+            for k, v in module.state_dict(keep_vars=True).items()}
+
+
+@pytest.mark.parametrize('group', ['source', 'target'])
+def test_gat_conv_fwd_bwd_vs_oracle(data, drugbank, group):
+    g = torch.Generator().manual_seed(3)
+    n, D = drugbank.N, 64
+    h = torch.randn(n, D, generator=g, requires_grad=True)
+    att = (torch.randn(1, 1, 2 * D, generator=g) * 0.3).requires_grad_(True)
+    bias = torch.randn(D, generator=g, requires_grad=True)
+    ei = torch.from_numpy(np.stack([drugbank.ddi_row, drugbank.ddi_col]))
+    P = {'l.conv.weight': torch.eye(D), 'l.conv.att': att, 'l.conv.bias': bias}
+    # oracle in fp64 for the gradient reference
+    P64 = {k: v.detach().double().requires_grad_(True) for k, v in P.items()}
+    h64 = h.detach().double().requires_grad_(True)
+    want = O.gat_conv(h64, ei, P64, 'l', softmax_group=group)
+    dout = torch.randn(n, D, generator=g)
+    want.backward(dout.double())
+    csr = data.interaction_combo_nxgraph.csr
+    hd, ad, bd = (t.detach().to(DEV).requires_grad_(True) for t in (h, att, bias))
+    got = ops.gat_conv(hd, ad, bd, csr, 0.2, group)
+    got.backward(dout.to(DEV))
+    assert rel(got, want) < 5e-6
+    assert rel(hd.grad, h64.grad) < 2e-5
+    assert rel(ad.grad, P64['l.conv.att'].grad) < 2e-5
+    assert rel(bd.grad, P64['l.conv.bias'].grad) < 5e-6
+
+
+@pytest.mark.parametrize('typ,act,normalize,higher', [('gat', 'relu', False, True), ('gcn', 'prelu', False, True),
+                                                      ('gin', 'prelu', False, False), ('gin', 'tanh', True, False),
+                                                      ('gcn', 'sigmoid', True, False), ('gat', 'identity', False, False)])
+def test_node_embedding_variants_vs_oracle(data, drugbank, typ, act, normalize, higher):
+    torch.manual_seed(5)
+    in_dim = 49 if not higher else 320
+    layer = L.NodeEmbedding(typ, in_dim, 64, act, True, normalize, higher_level=higher).to(DEV)
+    layer.train()
+    if higher:
+        graph = data.interaction_combo_nxgraph
+        n = data.N
+        ei = torch.from_numpy(np.stack([drugbank.ddi_row, drugbank.ddi_col]))
+        x = torch.randn(n, in_dim)
+        bd = type('B', (), {})()
+        bd.merge_higher_level = {'merge': graph}
+        bd.merge_data = {'merge': None}
+    else:
+        m = B.MergedGraph(data.packed, np.arange(100))
+        ei = m.edge_index.cpu()
+        x = m.x.cpu().clone()
+        bd = type('B', (), {})()
+        bd.merge_data = {'merge': m}
+        bd.merge_higher_level = {}
+    P = params_of(layer, 'l')
+    lf = dict(type=typ, act=act, bn='True', normalize=str(normalize))
+    xr = x.clone().requires_grad_(True)
+    want = O.node_embedding(xr, ei, P, 'l', lf, True, gat_group='source')
+    dy = torch.randn(want.shape, generator=torch.Generator().manual_seed(1))
+    want.backward(dy)
+    xd = x.to(DEV).requires_grad_(True)
+    got = layer(xd, bd, FakeModel())
+    got.backward(dy.to(DEV))
+    assert rel(got, want) < 2e-5
+    assert rel(xd.grad, xr.grad) < 2e-4
+    for k, p in layer.named_parameters():
+        ref = P['l.' + k].grad
+        scale = max(float(ref.abs().max()), 1e-3 * float(xr.grad.abs().max()))
+        assert float((p.grad.cpu() - ref).abs().max()) / scale < 3e-4, k
+
+
+def test_readout_styles_vs_oracle(data, drugbank):
+    torch.manual_seed(7)
+    from bignn_b200.layers_aggregation import NodeAggregationPairs
+    m = B.MergedGraph(data.packed, np.arange(300), chunk_graph_ptr=[0, 128, 256, 300])
+    bd = type('B', (), {})()
+    bd.merge_data = {'merge': m}
+    batch = m.batch.cpu()
+    x = torch.randn(m.A, 64)
+    fm = FakeModel()
+    # deepsets
+    agg = NodeAggregationPairs('deepsets', in_dim=64, out_dim=64, num_mlp_layers=2).to(DEV)
+    P = params_of(agg.agg_func, 'a')
+    xr = x.clone().requires_grad_(True)
+    want = O.deepsets_readout(xr, batch, 300, P, 'a', 2)
+    want.sum().backward()
+    xd = x.to(DEV).requires_grad_(True)
+    got = agg(xd, bd, fm)
+    got.sum().backward()
+    assert rel(got, want) < 1e-5 and rel(xd.grad, xr.grad) < 1e-5
+    # gated readout: BatchNorm batches are per chunk -> compare chunk by chunk
+    agg = NodeAggregationPairs('gmn_aggr', in_dim=64, out_dim=64).to(DEV)
+    agg.train()
+    P = params_of(agg.agg_func, 'a')
+    got = agg(x.to(DEV), bd, fm)
+    ptr = m.seg_ptr_host
+    for c, (g0, g1) in enumerate([(0, 128), (128, 256), (256, 300)]):
+        r0, r1 = int(ptr[g0]), int(ptr[g1])
+        want = O.gmn_aggr_readout(x[r0:r1], batch[r0:r1] - g0, g1 - g0, P, 'a')
+        assert rel(got[g0:g1], want) < 2e-5, c
+    # plain sum
+    agg = NodeAggregationPairs('sum').to(DEV)
+    assert rel(agg(x.to(DEV), bd, fm), O.readout([x], batch, 300, 'sum')) < 1e-6
+
+
+def test_scorers_and_losses_vs_oracle(data):
+    from bignn_b200.layers_link_pred import LinkPred
+    g = torch.Generator().manual_seed(9)
+    N, D, P_ = data.N, 64, 128
+    h = torch.randn(N, D, generator=g)
+    ids = torch.randint(0, N, (P_, 2), generator=g)
+
+    class BD(object):
+        dataset = data
+        pair_list = []
+
+        def pair_rows_device(self, n_rows, higher=True, unique=True):
+            return ids.to(torch.int32).to(DEV), B.graph.entry_csr(ids.numpy(), N, DEV)
+
+        def assign_link_preds(self, p):
+            self.p = p
+
+    # dot product
+    lp = LinkPred('dot_product', 64, 3).to(DEV)
+    hr = h.clone().requires_grad_(True)
+    want = O.link_pred(hr, ids, {}, 'l', dict(type='dot_product'))
+    want.sum().backward()
+    hd = h.to(DEV).requires_grad_(True)
+    got = lp(hd, BD(), None)
+    got.sum().backward()
+    assert rel(got, want) < 2e-6 and rel(hd.grad, hr.grad) < 1e-5
+    # multi-class logits + CE
+    torch.manual_seed(1)
+    lp = LinkPred('mlp_concat', 64, 3, multi_label_pred=True).to(DEV)
+    Pm = params_of(lp, 'l')
+    y = torch.randint(0, 3, (P_,), generator=g)
+    hr = h.clone().requires_grad_(True)
+    logits = O.link_pred(hr, ids, Pm, 'l', dict(type='mlp_concat', multi_label_pred='True'), 2)
+    loss = O.loss_fn(logits, y, 'CE')
+    loss.backward()
+    hd = h.to(DEV).requires_grad_(True)
+    got = lp(hd, BD(), None)
+    ld = ops.cross_entropy(got, y.to(torch.int32).to(DEV))
+    ld.backward()
+    assert tuple(got.shape) == (P_, 3)
+    assert rel(got, logits) < 5e-6 and abs(float(ld) - float(loss)) < 2e-6
+    assert rel(hd.grad, hr.grad) < 2e-5
+    for k, p in lp.named_parameters():
+        assert rel(p.grad, Pm['l.' + k].grad) < 2e-5, k
+
+
+def test_prelu_rownorm_gate_vs_torch():
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(3000, 64, generator=g, requires_grad=True)
+    for nw in (1, 64):
+        w = (torch.rand(nw, generator=g) * 0.5).requires_grad_(True)
+        y = torch.nn.functional.prelu(x, w)
+        dy = torch.randn(3000, 64, generator=g)
+        x.grad = None
+        y.backward(dy)
+        xd, wd = x.detach().to(DEV).requires_grad_(True), w.detach().to(DEV).requires_grad_(True)
+        yd = ops.prelu(xd, wd)
+        yd.backward(dy.to(DEV))
+        assert rel(yd, y) < 1e-6 and rel(xd.grad, x.grad) < 1e-6 and rel(wd.grad, w.grad) < 5e-6
+    x.grad = None
+    y = torch.nn.functional.normalize(x, p=2, dim=1)
+    dy = torch.randn(3000, 64, generator=g)
+    y.backward(dy)
+    xd = x.detach().to(DEV).requires_grad_(True)
+    yd = ops.row_normalize(xd)
+    yd.backward(dy.to(DEV))
+    assert rel(yd, y) < 1e-6 and rel(xd.grad, x.grad) < 5e-6
+    a = torch.randn(500, 64, generator=g, requires_grad=True)
+    b = torch.randn(500, 64, generator=g, requires_grad=True)
+    o = torch.sigmoid(a) * b
+    o.backward(dy[:500])
+    ad, bd = a.detach().to(DEV).requires_grad_(True), b.detach().to(DEV).requires_grad_(True)
+    od = ops.gate_mul(ad, bd)
+    od.backward(dy[:500].to(DEV))
+    assert rel(od, o) < 1e-6 and rel(ad.grad, a.grad) < 2e-6 and rel(bd.grad, b.grad) < 2e-6

@@ -118,3 +118,39 @@ def test_lower_chunk_activations(world, step_golden):
             assert rel(out, z['chunk10/act6']) < 1e-5
         else:
             assert rel(out, z['chunk0/pooled']) < 1e-5
+
+
+def test_gin_gat_step_vs_golden(golden_dir, drugbank):
+    """GIN lower + GAT upper (the reference's shipped upper-level type), same gates as above."""
+    z = np.load(os.path.join(golden_dir, 'bignn_gin_gat_step.npz'))
+    B.set_flags(B.make_flags(device=DEV, higher_level_gnn_type='gat'))
+    with open(os.path.join(golden_dir, 'bignn_gin_gat_layers.txt')) as f:
+        lines = f.read().split()
+    f_ = B.get_flags()
+    assert [getattr(f_, 'layer_%d' % i) for i in range(1, f_.layer_num + 1)] == lines
+    data = B.BiGNNData.from_npz(os.path.join(golden_dir, 'drugbank_packed.npz'), device=DEV)
+    model = B.Model(data).to(DEV)
+    sd = {k[4:]: torch.from_numpy(np.asarray(z[k])) for k in z.files if k.startswith('sd0/')}
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected
+    bd, loss = run_step(data, model, z)
+    assert rel(data.interaction_combo_nxgraph.init_x, z['init_x']) < 1e-5
+    for l in range(3):
+        assert rel(model.acts[l + 2], z['upper/act%d' % (l + 2)]) < 1e-5
+    assert abs(float(loss) - float(z['loss'])) < 1e-5
+    loss.backward()
+    specs = O.parse_specs(lines)
+    om = O.OracleModel(specs, O.state_from_npz(z, 'sd0/'), dtype=torch.float64)
+    _, _, _, l64 = O.train_step_forward(om, drugbank, z['batch_gids'], z['y_true'])
+    l64.backward()
+    g64 = {k: v.grad.numpy() for k, v in om.params().items()}
+    scale = {}
+    for k, g in g64.items():
+        scale[k.split('.')[1]] = max(scale.get(k.split('.')[1], 0.0), float(np.abs(g).max()))
+    for k, p in model.named_parameters():
+        if k.startswith('layers.'):
+            s = scale[k.split('.')[1]]
+            ours = float(np.abs(p.grad.double().cpu().numpy() - g64[k]).max()) / s
+            ref = float(np.abs(z['grad/' + k].astype(np.float64) - g64[k]).max()) / s
+            assert ours <= 3.0 * ref + 1e-5, (k, ours, ref)
+    B.set_flags(B.make_flags(device=DEV))

@@ -110,3 +110,21 @@ def test_adam_and_bn_buffers_match_reference(oracle_step, step_golden):
             assert int(got) == int(z[k])
         else:
             assert rel(got, z[k]) < 2e-6, name
+
+
+def test_gin_gat_step_matches_reference(drugbank, golden_dir):
+    """second pinned configuration: GIN lower + GAT upper (the reference's shipped upper type)."""
+    torch.set_num_threads(8)
+    z = np.load(os.path.join(golden_dir, 'bignn_gin_gat_step.npz'))
+    with open(os.path.join(golden_dir, 'bignn_gin_gat_layers.txt')) as f:
+        specs = O.parse_specs(f.read().splitlines())
+    sd = O.state_from_npz(z, 'sd0/')
+    model = O.OracleModel(specs, sd, gat_group='source')
+    init_x, acts, pred, loss = O.train_step_forward(model, drugbank, z['batch_gids'], z['y_true'], 64)
+    loss.backward()
+    assert rel(init_x.detach().numpy(), z['init_x']) < 1e-6
+    for l in range(3):
+        assert rel(acts[l].detach().numpy(), z['upper/act%d' % (l + 2)]) < 1e-6
+    assert abs(float(loss.detach()) - float(z['loss'])) < 1e-6
+    for k, v in model.params().items():
+        assert rel(v.grad.numpy(), z['grad/' + k]) < 2e-5, k
