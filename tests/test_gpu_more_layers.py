@@ -102,9 +102,10 @@ def test_node_embedding_variants_vs_oracle(data, drugbank, typ, act, normalize, 
     got.backward(dy.to(DEV))
     assert rel(got, want) < 2e-5
     assert rel(xd.grad, xr.grad) < 2e-4
+    # layer gradient scale: a conv bias that feeds BatchNorm has a true gradient of zero (noise only)
+    scale = max(float(P['l.' + k].grad.abs().max()) for k, _ in layer.named_parameters())
     for k, p in layer.named_parameters():
         ref = P['l.' + k].grad
-        scale = max(float(ref.abs().max()), 1e-3 * float(xr.grad.abs().max()))
         assert float((p.grad.cpu() - ref).abs().max()) / scale < 3e-4, k
 
 
