@@ -135,4 +135,4 @@ def test_gin_gat_step_matches_reference(drugbank, golden_dir):
     for k, v in model.params().items():
         lid = k.split('.')[1]
         err = float(np.abs(v.grad.numpy().astype(np.float64) - z['grad/' + k]).max()) / scale[lid]
-        assert err < (1e-4 if int(lid) < 5 else 2e-5), (k, err)
+        assert err < (1e-4 if int(lid) < 5 else 5e-5), (k, err)
