@@ -109,6 +109,29 @@ def gemm(a, b, ta=False, tb=False, bias=None, act=0, out=None):
     return c
 
 
+TC_MIN_ROWS = 512      # below this a 128-row tensor-core tile grid cannot fill the SMs; SIMT path
+
+
+def gemm_tc(a, b, b_is_nk, bias=None, act=0, act_y=None, act_in=0, out=None):
+    """C = act((a * act_in'(act_y)) @ op(b) + bias) on the tensor cores (tcgen05, 3xTF32)."""
+    a, b = _f32c(a), _f32c(b)
+    _lib.require_device(a, b)
+    M, K = a.shape
+    N = b.shape[0] if b_is_nk else b.shape[1]
+    if (b.shape[1] if b_is_nk else b.shape[0]) != K:
+        raise ValueError('gemm_tc: inner dimensions differ')
+    c = out if out is not None else torch.empty((M, N), dtype=torch.float32, device=a.device)
+    if act_y is not None:
+        act_y = _f32c(act_y)
+    _lib.call('bignn_gemm_tc_f32', M, N, K, a, a.stride(0), act_y, act_y.stride(0) if act_y is not None else 0,
+              int(act_in), b, b.stride(0), int(bool(b_is_nk)), c, c.stride(0), bias, int(act))
+    return c
+
+
+def use_tc(M, N):
+    return M >= TC_MIN_ROWS and N <= 128
+
+
 def colsum(x):
     x = _f32c(x)
     _lib.require_device(x)
@@ -190,7 +213,11 @@ class _LinearAct(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, act, layout):
-        y = gemm(x, weight, False, layout == 'oi', bias, act)
+        N = weight.shape[0] if layout == 'oi' else weight.shape[1]
+        if use_tc(x.shape[0], N):
+            y = gemm_tc(x, weight, layout == 'oi', bias, act)
+        else:
+            y = gemm(x, weight, False, layout == 'oi', bias, act)
         ctx.act, ctx.layout = act, layout
         ctx.save_for_backward(x, weight, y)
         return y
@@ -201,7 +228,11 @@ class _LinearAct(torch.autograd.Function):
         g = act_bwd(y, dy, ctx.act)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = gemm(g, weight, False, ctx.layout == 'io')
+            if use_tc(g.shape[0], x.shape[1]):
+                # dX = g W (oi: W is [N,K] = op(B)^T stored [K',N'] -> b_is_nk False) / g W^T (io)
+                dx = gemm_tc(g, weight, ctx.layout == 'io')
+            else:
+                dx = gemm(g, weight, False, ctx.layout == 'io')
         if ctx.needs_input_grad[1]:
             dw = gemm(g, x, True, False) if ctx.layout == 'oi' else gemm(x, g, True, False)
         if ctx.needs_input_grad[2]:

@@ -203,6 +203,28 @@ def test_gemm_vs_torch(ta, tb, M, N, K):
     assert rel(got2, torch.relu(want + bias.double())) < 2e-6 * max(1.0, np.sqrt(K) / 8)
 
 
+@pytest.mark.parametrize('M,N,K,nk', [(3712, 64, 64, True), (95038, 64, 40, True), (1309, 64, 320, False),
+                                      (1000, 64, 49, True), (130, 16, 128, True), (4097, 32, 64, False),
+                                      (700, 128, 96, True), (128, 64, 8, True), (129, 56, 33, False)])
+def test_gemm_tensor_core_3xtf32_vs_fp64(M, N, K, nk):
+    """tcgen05 / TMEM path: fp32-level accuracy from three TF32 products."""
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g)
+    b = torch.randn((N, K) if nk else (K, N), generator=g)
+    bias = torch.randn(N, generator=g)
+    want = a.double() @ (b.double().t() if nk else b.double())
+    got = ops.gemm_tc(a.to(DEV), b.to(DEV), nk)
+    assert rel(got, want) < 3e-6 * max(1.0, np.sqrt(K) / 8)
+    got2 = ops.gemm_tc(a.to(DEV), b.to(DEV), nk, bias.to(DEV), ops.ACT_CODES['relu'])
+    assert rel(got2, torch.relu(want + bias.double())) < 3e-6 * max(1.0, np.sqrt(K) / 8)
+    # fused activation backward on the A operand
+    y = torch.relu(torch.randn(M, K, generator=g))
+    got3 = ops.gemm_tc(a.to(DEV), b.to(DEV), nk, None, 0, y.to(DEV), ops.ACT_CODES['relu'])
+    want3 = (a.double() * (y > 0)) @ (b.double().t() if nk else b.double())
+    assert rel(got3, want3) < 3e-6 * max(1.0, np.sqrt(K) / 8)
+    assert torch.equal(got, ops.gemm_tc(a.to(DEV), b.to(DEV), nk))       # deterministic
+
+
 def test_gemm_is_deterministic_with_split_k():
     g = torch.Generator().manual_seed(0)
     a = torch.randn(36816, 64, generator=g).to(DEV)
