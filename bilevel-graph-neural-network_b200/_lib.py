@@ -37,6 +37,7 @@ SIGNATURES = {
     'bignn_spmm_planned_f32': ('i', 'pp' 'ppii' 'pi' 'pl' 'pl' 'iiif' 'ppi' 'pl' 's'),
     'bignn_gemm_workspace_bytes': ('l', 'iiii'),
     'bignn_gemm_f32': ('i', 'iiiii' 'pl' 'pl' 'pl' 'pi' 'pl' 's'),
+    'bignn_gemm_tc_supported': ('i', 'iii'),
     'bignn_gemm_tc_f32': ('i', 'iii' 'pl' 'pli' 'pli' 'pl' 'pi' 's'),
     'bignn_colsum_workspace_bytes': ('l', 'ii'),
     'bignn_colsum_f32': ('i', 'pliip' 'pl' 's'),
@@ -159,7 +160,7 @@ def call(name, *args):
     if codes.endswith('s'):
         cargs.append(torch.cuda.current_stream().cuda_stream)
     out = getattr(lib, name)(*cargs)
-    if res == 'i' and name != 'bignn_abi_version' and out != 0:
+    if res == 'i' and name not in ('bignn_abi_version', 'bignn_gemm_tc_supported') and out != 0:
         raise RuntimeError('{} failed with status {}: {}'.format(name, out, error_string(out)))
     return out
 

@@ -99,25 +99,51 @@ __device__ __forceinline__ void split_store(uint8_t* hi_base, uint8_t* lo_base, 
   *reinterpret_cast<uint4*>(lo_base + off) = l;
 }
 
-// NPAD = N rounded up to a multiple of 32 (TMEM columns / epilogue granularity), <= 256
-template <int NPAD>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// ---- TMEM accumulator -> 32 registers (this warp's 32 lanes x 32 consecutive columns)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Persistent kernel: NPAD = N rounded up to a multiple of 32 (<= 128); KCH = ceil(K/32) chunks (<= 4).
+// TMEM budget per CTA: NA "main" accumulators + 1 correction accumulator of NPAD columns each.
+// tcgen05.mma truncates (round-toward-zero) every time it writes the fp32 accumulator, so a long
+// accumulation chain drifts by ~0.7 ulp per step (measured: -2.1e-8 * K relative bias).  The hi*hi
+// products therefore rotate over NA accumulators (chain length K/8/NA) and the 2^-11-scaled
+// correction products go to their own accumulator; the epilogue adds them in fp32 round-to-nearest.
+template <int NPAD, int KCH>
+__global__ void __launch_bounds__(TC_THREADS, 2)
 k_gemm_tc(int M, int N, int K, const float* __restrict__ A, int64_t lda, const float* __restrict__ Yact, int64_t ldy,
           int act_in, const float* __restrict__ B, int64_t ldb, int b_is_nk, float* __restrict__ C, int64_t ldc,
           const float* __restrict__ bias, int act) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: 2 stages x { A_hi, A_lo : 128 x 128 B ; B_hi, B_lo : NPAD x 128 B }
-  constexpr int A_BYTES = TC_BM * 128;
+  constexpr int A_BYTES = TC_BM * 128;            // one K chunk of the A tile (hi or lo)
   constexpr int B_BYTES = NPAD * 128;
-  constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  constexpr int NA = (NPAD <= 64) ? 2 : 1;        // main accumulators
+  constexpr int ACC_COLS = (NA + 1) * NPAD;
+  constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : (ACC_COLS <= 64 ? 64 : (ACC_COLS <= 128 ? 128 : 256));
+  static_assert(ACC_COLS <= 256, "two CTAs per SM share the 512 TMEM columns");
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t mma_bar[2];
-  __shared__ uint64_t done_bar;
+  uint8_t* a_hi = smem;                            // [KCH][128 x 128 B]
+  uint8_t* a_lo = a_hi + KCH * A_BYTES;
+  constexpr int LDS = NPAD + 4;                    // padded row of the output staging tile
+  constexpr int A_REGION = (2 * KCH * A_BYTES > TC_BM * LDS * 4 ? 2 * KCH * A_BYTES : TC_BM * LDS * 4 + 1023) & ~1023;
+  uint8_t* b_hi = smem + A_REGION;                 // [KCH][NPAD x 128 B]
+  uint8_t* b_lo = b_hi + KCH * B_BYTES;
+  __shared__ uint64_t mma_bar;
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.x * TC_BM;
-  constexpr int TMEM_COLS = NPAD <= 32 ? 32 : (NPAD <= 64 ? 64 : (NPAD <= 128 ? 128 : 256));
+  const int n_tiles = (M + TC_BM - 1) / TC_BM;
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
@@ -126,126 +152,143 @@ k_gemm_tc(int M, int N, int K, const float* __restrict__ A, int64_t lda, const f
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 32) {
-    mbar_init(&mma_bar[0], 1);
-    mbar_init(&mma_bar[1], 1);
-    mbar_init(&done_bar, 1);
+    mbar_init(&mma_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // ---- weights: split once per CTA, resident in shared memory for every tile
+  for (int idx = tid; idx < KCH * NPAD * 8; idx += TC_THREADS) {
+    const int ch = idx / (NPAD * 8), rem = idx % (NPAD * 8);
+    const int n = rem >> 3, c = rem & 7;
+    const int gk = ch * TC_KC + c * 4;
+    float t[4] = {0.f, 0.f, 0.f, 0.f};
+    if (n < N) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (gk + j < K) t[j] = b_is_nk ? __ldg(B + (int64_t)n * ldb + gk + j) : __ldg(B + (int64_t)(gk + j) * ldb + n);
+    }
+    split_store(b_hi + ch * B_BYTES, b_lo + ch * B_BYTES, sw128_off(n, c), make_float4(t[0], t[1], t[2], t[3]));
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = tmem_base_s;
   const uint32_t idesc = umma_idesc_tf32(TC_BM, NPAD);
-
-  const int n_chunks = (K + TC_KC - 1) / TC_KC;
   const bool a_vec = ((lda & 3) == 0) && aligned16(A) && (Yact == nullptr || (((ldy & 3) == 0) && aligned16(Yact)));
-  uint32_t phase[2] = {0, 0};
+  const bool c_vec = ((ldc & 3) == 0) && aligned16(C) && ((N & 3) == 0);
 
-  for (int ch = 0; ch < n_chunks; ++ch) {
-    const int st = ch & 1;
-    uint8_t* a_hi = smem + st * STAGE_BYTES;
-    uint8_t* a_lo = a_hi + A_BYTES;
-    uint8_t* b_hi = a_lo + A_BYTES;
-    uint8_t* b_lo = b_hi + B_BYTES;
-    if (ch >= 2) {             // the MMAs that read this stage two chunks ago must have finished
-      mbar_wait(&mma_bar[st], phase[st]);
-      phase[st] ^= 1;
-    }
-    const int kbase = ch * TC_KC;
-    // ---- A chunk: 128 rows x 8 sixteen-byte chunks = 1024 float4, 4 per thread
+  // each thread stages 4 sixteen-byte chunks per K chunk: (row, chunk) = ((tid + i*256) >> 3, (tid + i*256) & 7)
+  float4 areg[KCH][4];
+  auto load_tile = [&](int tile) {
+    const int m0 = tile * TC_BM;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int idx = tid + i * TC_THREADS;
-      const int r = idx >> 3, c = idx & 7;
-      const int gm = m0 + r, gk = kbase + c * 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (gm < M && gk < K) {
-        const float* ap = A + (int64_t)gm * lda + gk;
-        if (a_vec && gk + 3 < K) {
-          v = ldg4(ap);
-          if (Yact) {
-            const float4 y = ldg4(Yact + (int64_t)gm * ldy + gk);
-            v.x *= act_grad_from_output(y.x, act_in); v.y *= act_grad_from_output(y.y, act_in);
-            v.z *= act_grad_from_output(y.z, act_in); v.w *= act_grad_from_output(y.w, act_in);
-          }
-        } else {
-          float t[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int ch = 0; ch < KCH; ++ch) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (gk + j < K) {
-              t[j] = __ldg(ap + j);
-              if (Yact) t[j] *= act_grad_from_output(__ldg(Yact + (int64_t)gm * ldy + gk + j), act_in);
+      for (int i = 0; i < 4; ++i) {
+        const int idx = tid + i * TC_THREADS;
+        const int r = idx >> 3, c = idx & 7;
+        const int gm = m0 + r, gk = ch * TC_KC + c * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gm < M && gk < K) {
+          const float* ap = A + (int64_t)gm * lda + gk;
+          if (a_vec && gk + 3 < K) {
+            v = ldg4(ap);
+            if (Yact) {
+              const float4 y = ldg4(Yact + (int64_t)gm * ldy + gk);
+              v.x *= act_grad_from_output(y.x, act_in); v.y *= act_grad_from_output(y.y, act_in);
+              v.z *= act_grad_from_output(y.z, act_in); v.w *= act_grad_from_output(y.w, act_in);
             }
-          v = make_float4(t[0], t[1], t[2], t[3]);
-        }
-      }
-      split_store(a_hi, a_lo, sw128_off(r, c), v);
-    }
-    // ---- B chunk: NPAD rows (output features) x 8 chunks; B stored [N,K] (b_is_nk) or [K,N]
-    for (int idx = tid; idx < NPAD * 8; idx += TC_THREADS) {
-      const int n = idx >> 3, c = idx & 7;
-      const int gk = kbase + c * 4;
-      float t[4] = {0.f, 0.f, 0.f, 0.f};
-      if (n < N) {
+          } else {
+            float t[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (gk + j < K) t[j] = b_is_nk ? __ldg(B + (int64_t)n * ldb + gk + j) : __ldg(B + (int64_t)(gk + j) * ldb + n);
+            for (int j = 0; j < 4; ++j)
+              if (gk + j < K) {
+                t[j] = __ldg(ap + j);
+                if (Yact) t[j] *= act_grad_from_output(__ldg(Yact + (int64_t)gm * ldy + gk + j), act_in);
+              }
+            v = make_float4(t[0], t[1], t[2], t[3]);
+          }
+        }
+        areg[ch][i] = v;
       }
-      split_store(b_hi, b_lo, sw128_off(n, c), make_float4(t[0], t[1], t[2], t[3]));
     }
-    // generic-proxy smem writes -> visible to the async (tensor core) proxy
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  };
+
+  uint32_t phase = 0;
+  int tile = blockIdx.x;
+  if (tile < n_tiles) load_tile(tile);
+  for (; tile < n_tiles; tile += gridDim.x) {
+    const int m0 = tile * TC_BM;
+    // ---- registers -> split -> swizzled shared memory
+#pragma unroll
+    for (int ch = 0; ch < KCH; ++ch)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int idx = tid + i * TC_THREADS;
+        split_store(a_hi + ch * A_BYTES, a_lo + ch * A_BYTES, sw128_off(idx >> 3, idx & 7), areg[ch][i]);
+      }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async (tensor core) proxy
     __syncthreads();
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint64_t da_hi = umma_desc_k_sw128(smem_u32(a_hi)), da_lo = umma_desc_k_sw128(smem_u32(a_lo));
-      const uint64_t db_hi = umma_desc_k_sw128(smem_u32(b_hi)), db_lo = umma_desc_k_sw128(smem_u32(b_lo));
+      int ks = 0;
 #pragma unroll
-      for (int k = 0; k < TC_KC / 8; ++k) {
-        const uint64_t adv = (uint64_t)((k * 32) >> 4);       // 8 TF32 = 32 bytes along K inside the swizzle span
-        umma_tf32(tmem_d, da_lo + adv, db_hi + adv, idesc, (ch | k) ? 1u : 0u);
-        umma_tf32(tmem_d, da_hi + adv, db_lo + adv, idesc, 1u);
-        umma_tf32(tmem_d, da_hi + adv, db_hi + adv, idesc, 1u);
-      }
-      umma_commit(&mma_bar[st]);
-      if (ch == n_chunks - 1) umma_commit(&done_bar);
-    }
-  }
-  // ---- epilogue: TMEM -> registers -> (bias, act) -> smem -> coalesced global stores
-  mbar_wait(&done_bar, 0);
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  float* stage_out = reinterpret_cast<float*>(smem);            // [128][NPAD + 4] floats; operand buffers are free now
-  constexpr int LDS = NPAD + 4;
-  {
-    const int q = warp & 3;                                     // TMEM lane quadrant this warp may read
-    const int row = q * 32 + lane;
-    for (int cb = (warp >> 2) * 32; cb < NPAD; cb += 64) {
-      uint32_t r[32];
-      const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)cb;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-            "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-            "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-          : "r"(taddr)
-          : "memory");
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      for (int ch = 0; ch < KCH; ++ch) {
+        if (ch * TC_KC >= K) break;
+        const uint64_t da_hi = umma_desc_k_sw128(smem_u32(a_hi + ch * A_BYTES));
+        const uint64_t da_lo = umma_desc_k_sw128(smem_u32(a_lo + ch * A_BYTES));
+        const uint64_t db_hi = umma_desc_k_sw128(smem_u32(b_hi + ch * B_BYTES));
+        const uint64_t db_lo = umma_desc_k_sw128(smem_u32(b_lo + ch * B_BYTES));
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int n = cb + j;
-        float v = __uint_as_float(r[j]);
-        if (bias && n < N) v += __ldg(bias + n);
-        stage_out[row * LDS + n] = apply_act(v, act);
+        for (int k = 0; k < TC_KC / 8; ++k, ++ks) {
+          if (ch * TC_KC + k * 8 >= K) break;
+          const uint64_t adv = (uint64_t)((k * 32) >> 4);     // 8 TF32 = 32 bytes along K inside the swizzle span
+          umma_tf32(tmem_d + (uint32_t)((ks % NA) * NPAD), da_hi + adv, db_hi + adv, idesc, ks >= NA ? 1u : 0u);
+          umma_tf32(tmem_d + (uint32_t)(NA * NPAD), da_lo + adv, db_hi + adv, idesc, ks > 0 ? 1u : 0u);
+          umma_tf32(tmem_d + (uint32_t)(NA * NPAD), da_hi + adv, db_lo + adv, idesc, 1u);
+        }
+      }
+      umma_commit(&mma_bar);
+    }
+    // ---- prefetch the next tile's rows while the tensor core and the epilogue run
+    if (tile + gridDim.x < n_tiles) load_tile(tile + gridDim.x);
+    mbar_wait(&mma_bar, phase);
+    phase ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // ---- epilogue: TMEM -> registers (sum of accumulators, RN) -> bias/act -> smem -> coalesced stores
+    float* stage_out = reinterpret_cast<float*>(smem);          // aliases the A buffers: the MMAs are done
+    const int n_main = (K + 7) / 8 < NA ? (K + 7) / 8 : NA;
+    {
+      const int q = warp & 3;                                   // TMEM lane quadrant this warp may read
+      const int row = q * 32 + lane;
+      for (int cb = (warp >> 2) * 32; cb < NPAD; cb += 64) {
+        uint32_t r[32];
+        float v[32];
+        const uint32_t tbase = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)cb;
+        tmem_ld32(tbase + (uint32_t)(NA * NPAD), r);            // corrections first (small)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (NA == 2 && n_main == 2) {
+          uint32_t r2[32];
+          tmem_ld32(tbase, r);
+          tmem_ld32(tbase + (uint32_t)NPAD, r2);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __fadd_rn(__fadd_rn(__uint_as_float(r[j]), __uint_as_float(r2[j])), v[j]);
+        } else {
+          tmem_ld32(tbase, r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __fadd_rn(__uint_as_float(r[j]), v[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int n = cb + j;
+          float o = v[j];
+          if (bias && n < N) o += __ldg(bias + n);
+          stage_out[row * LDS + n] = apply_act(o, act);
+        }
       }
     }
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  {
-    const bool c_vec = ((ldc & 3) == 0) && aligned16(C) && ((N & 3) == 0);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
     if (c_vec) {
       const int n4 = N >> 2;
       for (int idx = tid; idx < TC_BM * n4; idx += TC_THREADS) {
@@ -259,35 +302,56 @@ k_gemm_tc(int M, int N, int K, const float* __restrict__ A, int64_t lda, const f
         if (m0 + r < M) C[(int64_t)(m0 + r) * ldc + c] = stage_out[r * LDS + c];
       }
     }
+    __syncthreads();                                            // staging is overwritten by the next tile's operands
   }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TMEM_COLS) : "memory");
   }
 }
 
-template <int NPAD>
+template <int NPAD, int KCH>
 static int launch_tc(int M, int N, int K, const float* A, int64_t lda, const float* Yact, int64_t ldy, int act_in,
                      const float* B, int64_t ldb, int b_is_nk, float* C, int64_t ldc, const float* bias, int act,
                      cudaStream_t st) {
-  constexpr int stage = 2 * TC_BM * 128 + 2 * NPAD * 128;
-  constexpr int out_stage = TC_BM * (NPAD + 4) * 4;
-  constexpr int smem = (2 * stage > out_stage ? 2 * stage : out_stage) + 1024;
+  constexpr int a_region = (2 * KCH * TC_BM * 128 > TC_BM * (NPAD + 4) * 4 ? 2 * KCH * TC_BM * 128
+                                                                          : TC_BM * (NPAD + 4) * 4 + 1023) & ~1023;
+  constexpr int smem = a_region + 2 * KCH * NPAD * 128 + 1024;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<NPAD, KCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  k_gemm_tc<NPAD><<<ceil_div(M, TC_BM), TC_THREADS, smem, st>>>(M, N, K, A, lda, Yact, ldy, act_in, B, ldb, b_is_nk, C,
-                                                                ldc, bias, act);
+  const int n_tiles = ceil_div(M, TC_BM);
+  int grid = 2 * sm_count();
+  if (grid > n_tiles) grid = n_tiles;
+  k_gemm_tc<NPAD, KCH><<<grid, TC_THREADS, smem, st>>>(M, N, K, A, lda, Yact, ldy, act_in, B, ldb, b_is_nk, C, ldc, bias,
+                                                       act);
   BIGNN_LAUNCH_COUNT(1);
   return last_launch_status();
+}
+
+template <int NPAD>
+static int launch_tc_k(int M, int N, int K, const float* A, int64_t lda, const float* Yact, int64_t ldy, int act_in,
+                       const float* B, int64_t ldb, int b_is_nk, float* C, int64_t ldc, const float* bias, int act,
+                       cudaStream_t st) {
+  if (K <= 32) return launch_tc<NPAD, 1>(M, N, K, A, lda, Yact, ldy, act_in, B, ldb, b_is_nk, C, ldc, bias, act, st);
+  if (K <= 64) return launch_tc<NPAD, 2>(M, N, K, A, lda, Yact, ldy, act_in, B, ldb, b_is_nk, C, ldc, bias, act, st);
+  if (NPAD <= 64 && K <= 96)
+    return launch_tc<NPAD, 3>(M, N, K, A, lda, Yact, ldy, act_in, B, ldb, b_is_nk, C, ldc, bias, act, st);
+  return BIGNN_EINVAL;
 }
 
 }  // namespace bignn
 
 using namespace bignn;
+
+extern "C" int bignn_gemm_tc_supported(int32_t M, int32_t N, int32_t K) {
+  if (M <= 0 || N <= 0 || K <= 0 || N > 128) return 0;
+  return (K <= 64 || (N <= 64 && K <= 96)) ? 1 : 0;
+}
 
 extern "C" int bignn_gemm_tc_f32(int32_t M, int32_t N, int32_t K, const float* A, int64_t lda, const float* act_y,
                                  int64_t ldy, int32_t act_in, const float* B, int64_t ldb, int32_t b_is_nk, float* C,
@@ -295,12 +359,12 @@ extern "C" int bignn_gemm_tc_f32(int32_t M, int32_t N, int32_t K, const float* A
   if (M < 0 || N < 0 || K < 0) return BIGNN_EINVAL;
   if (M == 0 || N == 0) return 0;
   if (K == 0 || !A || !B || !C || ldc < N || lda < K) return BIGNN_EINVAL;
-  if (N > 128) return BIGNN_EINVAL;                          // the path's widths are <= 64; 128 keeps smem < 227 KB
+  if (!bignn_gemm_tc_supported(M, N, K)) return BIGNN_EINVAL;   // two CTAs/SM: operands must fit in ~110 KB
   if (act < 0 || act > BIGNN_ACT_TANH || act_in < 0 || act_in > BIGNN_ACT_TANH) return BIGNN_EINVAL;
   if (act_y && ldy < K) return BIGNN_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
-  if (N <= 32) return launch_tc<32>(M, N, K, A, lda, act_y, ldy, act_in, B, ldb, b_is_nk, C, ldc, bias, act, st);
-  if (N <= 64) return launch_tc<64>(M, N, K, A, lda, act_y, ldy, act_in, B, ldb, b_is_nk, C, ldc, bias, act, st);
-  if (N <= 96) return launch_tc<96>(M, N, K, A, lda, act_y, ldy, act_in, B, ldb, b_is_nk, C, ldc, bias, act, st);
-  return launch_tc<128>(M, N, K, A, lda, act_y, ldy, act_in, B, ldb, b_is_nk, C, ldc, bias, act, st);
+  if (N <= 32) return launch_tc_k<32>(M, N, K, A, lda, act_y, ldy, act_in, B, ldb, b_is_nk, C, ldc, bias, act, st);
+  if (N <= 64) return launch_tc_k<64>(M, N, K, A, lda, act_y, ldy, act_in, B, ldb, b_is_nk, C, ldc, bias, act, st);
+  if (N <= 96) return launch_tc_k<96>(M, N, K, A, lda, act_y, ldy, act_in, B, ldb, b_is_nk, C, ldc, bias, act, st);
+  return launch_tc_k<128>(M, N, K, A, lda, act_y, ldy, act_in, B, ldb, b_is_nk, C, ldc, bias, act, st);
 }

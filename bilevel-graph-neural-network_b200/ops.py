@@ -128,8 +128,8 @@ def gemm_tc(a, b, b_is_nk, bias=None, act=0, act_y=None, act_in=0, out=None):
     return c
 
 
-def use_tc(M, N):
-    return M >= TC_MIN_ROWS and N <= 128
+def use_tc(M, N, K):
+    return M >= TC_MIN_ROWS and N <= 128 and (K <= 64 or (N <= 64 and K <= 96))
 
 
 def colsum(x):
@@ -214,7 +214,7 @@ class _LinearAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, act, layout):
         N = weight.shape[0] if layout == 'oi' else weight.shape[1]
-        if use_tc(x.shape[0], N):
+        if use_tc(x.shape[0], N, x.shape[1]):
             y = gemm_tc(x, weight, layout == 'oi', bias, act)
         else:
             y = gemm(x, weight, False, layout == 'oi', bias, act)
@@ -228,7 +228,7 @@ class _LinearAct(torch.autograd.Function):
         g = act_bwd(y, dy, ctx.act)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            if use_tc(g.shape[0], x.shape[1]):
+            if use_tc(g.shape[0], x.shape[1], g.shape[1]):
                 # dX = g W (oi: W is [N,K] = op(B)^T stored [K',N'] -> b_is_nk False) / g W^T (io)
                 dx = gemm_tc(g, weight, ctx.layout == 'io')
             else:

@@ -136,6 +136,7 @@ int bignn_gemm_f32(int32_t ta, int32_t tb, int32_t M, int32_t N, int32_t K,
  * B stored [N,K] (b_is_nk = 1, nn.Linear layout) or [K,N] (b_is_nk = 0, PyG layout).  act_y (optional)
  * fuses the backward of an activation into the operand load: A is then dY and act_y the activation
  * OUTPUT it is masked/scaled with. */
+int bignn_gemm_tc_supported(int32_t M, int32_t N, int32_t K);   /* 1 if the shape has a tensor-core kernel (N<=128, K<=64; K<=96 for N<=64) */
 int bignn_gemm_tc_f32(int32_t M, int32_t N, int32_t K, const float* A, int64_t lda,
                       const float* act_y, int64_t ldy, int32_t act_in,
                       const float* B, int64_t ldb, int32_t b_is_nk,
