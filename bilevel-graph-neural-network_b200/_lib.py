@@ -38,7 +38,7 @@ SIGNATURES = {
     'bignn_gemm_workspace_bytes': ('l', 'iiii'),
     'bignn_gemm_f32': ('i', 'iiiii' 'pl' 'pl' 'pl' 'pi' 'pl' 's'),
     'bignn_gemm_tc_supported': ('i', 'iii'),
-    'bignn_gemm_tc_f32': ('i', 'iii' 'pl' 'pli' 'pli' 'pl' 'pi' 's'),
+    'bignn_gemm_tc_f32': ('i', 'iii' 'pl' 'pli' 'pl' 'pi' 's'),
     'bignn_colsum_workspace_bytes': ('l', 'ii'),
     'bignn_colsum_f32': ('i', 'pliip' 'pl' 's'),
     'bignn_act_bwd_f32': ('i', 'ppplis'),

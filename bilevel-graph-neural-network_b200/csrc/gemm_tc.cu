@@ -114,36 +114,49 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// Persistent kernel: NPAD = N rounded up to a multiple of 32 (<= 128); KCH = ceil(K/32) chunks (<= 4).
-// TMEM budget per CTA: NA "main" accumulators + 1 correction accumulator of NPAD columns each.
-// tcgen05.mma truncates (round-toward-zero) every time it writes the fp32 accumulator, so a long
-// accumulation chain drifts by ~0.7 ulp per step (measured: -2.1e-8 * K relative bias).  The hi*hi
-// products therefore rotate over NA accumulators (chain length K/8/NA) and the 2^-11-scaled
-// correction products go to their own accumulator; the epilogue adds them in fp32 round-to-nearest.
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* gptr, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(gptr), "r"(src_bytes) : "memory");
+}
+
+// Persistent kernel: NPAD = N rounded up to a multiple of 32 (<= 128); KCH = ceil(K/32) chunks (<= 3).
+// Requires K % 4 == 0, lda % 4 == 0 and a 16-byte aligned A (128-bit cp.async).
+//
+// Per 128-row tile:
+//   cp.async (LDGSTS, no registers) streams the raw fp32 rows straight into the swizzled A_hi operand
+//   buffer -- kind::tf32 reads only the upper 19 bits of each word, so the raw data IS the hi operand;
+//   one shared->shared pass derives A_lo = tf32(x - hi(x));  one elected thread issues the MMAs;
+//   the next tile's cp.async is issued as soon as the MMAs have drained the buffer, so it overlaps
+//   the epilogue (TMEM -> registers -> swizzled staging in the A_lo area -> coalesced 128-bit stores).
+// Two CTAs per SM (96 KB smem, <= 256 TMEM columns each) overlap each other's phases.
+//
+// TMEM: tcgen05.mma truncates (round-toward-zero) when it writes the fp32 accumulator, so a long
+// accumulation chain drifts (measured -2.1e-8 * K relative).  The hi*hi products rotate over NA
+// accumulators, the 2^-11-scaled correction products use their own, and the epilogue adds them in
+// fp32 round-to-nearest.
 template <int NPAD, int KCH>
 __global__ void __launch_bounds__(TC_THREADS, 2)
-k_gemm_tc(int M, int N, int K, const float* __restrict__ A, int64_t lda, const float* __restrict__ Yact, int64_t ldy,
-          int act_in, const float* __restrict__ B, int64_t ldb, int b_is_nk, float* __restrict__ C, int64_t ldc,
-          const float* __restrict__ bias, int act) {
+k_gemm_tc(int M, int N, int K, const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb,
+          int b_is_nk, float* __restrict__ C, int64_t ldc, const float* __restrict__ bias, int act) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  constexpr int A_BYTES = TC_BM * 128;            // one K chunk of the A tile (hi or lo)
+  constexpr int A_BYTES = TC_BM * 128;            // one K chunk of the A tile
   constexpr int B_BYTES = NPAD * 128;
+  constexpr int NBLK = NPAD / 32;                 // 32-column blocks of the output tile
+  constexpr int LO_CH = KCH > NBLK ? KCH : NBLK;  // the A_lo area doubles as the output staging tile
   constexpr int NA = (NPAD <= 64) ? 2 : 1;        // main accumulators
   constexpr int ACC_COLS = (NA + 1) * NPAD;
   constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : (ACC_COLS <= 64 ? 64 : (ACC_COLS <= 128 ? 128 : 256));
   static_assert(ACC_COLS <= 256, "two CTAs per SM share the 512 TMEM columns");
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* a_hi = smem;                            // [KCH][128 x 128 B]
-  uint8_t* a_lo = a_hi + KCH * A_BYTES;
-  constexpr int LDS = NPAD + 4;                    // padded row of the output staging tile
-  constexpr int A_REGION = (2 * KCH * A_BYTES > TC_BM * LDS * 4 ? 2 * KCH * A_BYTES : TC_BM * LDS * 4 + 1023) & ~1023;
-  uint8_t* b_hi = smem + A_REGION;                 // [KCH][NPAD x 128 B]
+  uint8_t* a_hi = smem;                            // [KCH][128 x 128 B]  raw fp32 rows
+  uint8_t* a_lo = a_hi + KCH * A_BYTES;            // [LO_CH][128 x 128 B]
+  uint8_t* b_hi = a_lo + LO_CH * A_BYTES;          // [KCH][NPAD x 128 B]
   uint8_t* b_lo = b_hi + KCH * B_BYTES;
   __shared__ uint64_t mma_bar;
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_tiles = (M + TC_BM - 1) / TC_BM;
+  const int kch_used = (K + TC_KC - 1) / TC_KC;
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
@@ -155,8 +168,25 @@ k_gemm_tc(int M, int N, int K, const float* __restrict__ A, int64_t lda, const f
     mbar_init(&mma_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  const uint32_t a_hi_s = smem_u32(a_hi);
+  auto prefetch_tile = [&](int tile) {
+    const int m0 = tile * TC_BM;
+#pragma unroll 1
+    for (int j = tid; j < kch_used * 1024; j += TC_THREADS) {
+      const int ch = j >> 10, idx = j & 1023;
+      const int r = idx >> 3, c = idx & 7;
+      const int gm = m0 + r, gk = ch * TC_KC + c * 4;
+      const bool ok = gm < M && gk < K;
+      const float* src = ok ? A + (int64_t)gm * lda + gk : A;
+      cp_async16(a_hi_s + ch * A_BYTES + sw128_off(r, c), src, ok ? 16u : 0u);     // src_bytes 0 -> zero fill
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int tile = blockIdx.x;
+  if (tile < n_tiles) prefetch_tile(tile);
   // ---- weights: split once per CTA, resident in shared memory for every tile
-  for (int idx = tid; idx < KCH * NPAD * 8; idx += TC_THREADS) {
+#pragma unroll 1
+  for (int idx = tid; idx < kch_used * NPAD * 8; idx += TC_THREADS) {
     const int ch = idx / (NPAD * 8), rem = idx % (NPAD * 8);
     const int n = rem >> 3, c = rem & 7;
     const int gk = ch * TC_KC + c * 4;
@@ -173,59 +203,26 @@ k_gemm_tc(int M, int N, int K, const float* __restrict__ A, int64_t lda, const f
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = tmem_base_s;
   const uint32_t idesc = umma_idesc_tf32(TC_BM, NPAD);
-  const bool a_vec = ((lda & 3) == 0) && aligned16(A) && (Yact == nullptr || (((ldy & 3) == 0) && aligned16(Yact)));
   const bool c_vec = ((ldc & 3) == 0) && aligned16(C) && ((N & 3) == 0);
-
-  // each thread stages 4 sixteen-byte chunks per K chunk: (row, chunk) = ((tid + i*256) >> 3, (tid + i*256) & 7)
-  float4 areg[KCH][4];
-  auto load_tile = [&](int tile) {
-    const int m0 = tile * TC_BM;
-#pragma unroll
-    for (int ch = 0; ch < KCH; ++ch) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int idx = tid + i * TC_THREADS;
-        const int r = idx >> 3, c = idx & 7;
-        const int gm = m0 + r, gk = ch * TC_KC + c * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gm < M && gk < K) {
-          const float* ap = A + (int64_t)gm * lda + gk;
-          if (a_vec && gk + 3 < K) {
-            v = ldg4(ap);
-            if (Yact) {
-              const float4 y = ldg4(Yact + (int64_t)gm * ldy + gk);
-              v.x *= act_grad_from_output(y.x, act_in); v.y *= act_grad_from_output(y.y, act_in);
-              v.z *= act_grad_from_output(y.z, act_in); v.w *= act_grad_from_output(y.w, act_in);
-            }
-          } else {
-            float t[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (gk + j < K) {
-                t[j] = __ldg(ap + j);
-                if (Yact) t[j] *= act_grad_from_output(__ldg(Yact + (int64_t)gm * ldy + gk + j), act_in);
-              }
-            v = make_float4(t[0], t[1], t[2], t[3]);
-          }
-        }
-        areg[ch][i] = v;
-      }
-    }
-  };
+  const int n_main = (K + 7) / 8 < NA ? (K + 7) / 8 : NA;
 
   uint32_t phase = 0;
-  int tile = blockIdx.x;
-  if (tile < n_tiles) load_tile(tile);
   for (; tile < n_tiles; tile += gridDim.x) {
     const int m0 = tile * TC_BM;
-    // ---- registers -> split -> swizzled shared memory
-#pragma unroll
-    for (int ch = 0; ch < KCH; ++ch)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int idx = tid + i * TC_THREADS;
-        split_store(a_hi + ch * A_BYTES, a_lo + ch * A_BYTES, sw128_off(idx >> 3, idx & 7), areg[ch][i]);
-      }
+    // ---- this thread's cp.async chunks have landed; derive the lo operand from them (same chunks)
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll 1
+    for (int j = tid; j < kch_used * 1024; j += TC_THREADS) {
+      const int ch = j >> 10, idx = j & 1023;
+      const uint32_t off = ch * A_BYTES + sw128_off(idx >> 3, idx & 7);
+      const float4 x = *reinterpret_cast<const float4*>(a_hi + off);
+      uint4 l;
+      l.x = __float_as_uint(x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u)) & 0xffffe000u;
+      l.y = __float_as_uint(x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u)) & 0xffffe000u;
+      l.z = __float_as_uint(x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u)) & 0xffffe000u;
+      l.w = __float_as_uint(x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u)) & 0xffffe000u;
+      *reinterpret_cast<uint4*>(a_lo + off) = l;
+    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async (tensor core) proxy
     __syncthreads();
     if (tid == 0) {
@@ -249,17 +246,16 @@ k_gemm_tc(int M, int N, int K, const float* __restrict__ A, int64_t lda, const f
       }
       umma_commit(&mma_bar);
     }
-    // ---- prefetch the next tile's rows while the tensor core and the epilogue run
-    if (tile + gridDim.x < n_tiles) load_tile(tile + gridDim.x);
     mbar_wait(&mma_bar, phase);
     phase ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // ---- epilogue: TMEM -> registers (sum of accumulators, RN) -> bias/act -> smem -> coalesced stores
-    float* stage_out = reinterpret_cast<float*>(smem);          // aliases the A buffers: the MMAs are done
-    const int n_main = (K + 7) / 8 < NA ? (K + 7) / 8 : NA;
+    // ---- the MMAs have drained A_hi: stream the next tile in while the epilogue runs
+    if (tile + gridDim.x < n_tiles) prefetch_tile(tile + gridDim.x);
+    // ---- epilogue: TMEM -> registers (sum of accumulators, RN) -> bias/act -> swizzled staging (A_lo area)
     {
       const int q = warp & 3;                                   // TMEM lane quadrant this warp may read
       const int row = q * 32 + lane;
+#pragma unroll 1
       for (int cb = (warp >> 2) * 32; cb < NPAD; cb += 64) {
         uint32_t r[32];
         float v[32];
@@ -267,43 +263,53 @@ k_gemm_tc(int M, int N, int K, const float* __restrict__ A, int64_t lda, const f
         tmem_ld32(tbase + (uint32_t)(NA * NPAD), r);            // corrections first (small)
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (NA == 2 && n_main == 2) {
-          uint32_t r2[32];
-          tmem_ld32(tbase, r);
-          tmem_ld32(tbase + (uint32_t)NPAD, r2);
+        tmem_ld32(tbase, r);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __fadd_rn(__fadd_rn(__uint_as_float(r[j]), __uint_as_float(r2[j])), v[j]);
-        } else {
-          tmem_ld32(tbase, r);
+        for (int j = 0; j < 32; ++j) v[j] = __fadd_rn(__uint_as_float(r[j]), v[j]);
+        if (NA == 2 && n_main == 2) {
+          tmem_ld32(tbase + (uint32_t)NPAD, r);
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __fadd_rn(__uint_as_float(r[j]), v[j]);
         }
+        uint8_t* blk = a_lo + (cb >> 5) * A_BYTES;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int n = cb + j;
-          float o = v[j];
-          if (bias && n < N) o += __ldg(bias + n);
-          stage_out[row * LDS + n] = apply_act(o, act);
-        }
+        for (int c = 0; c < 8; ++c)      // raw sums; bias + activation are applied in the (rolled) copy-out loop
+          *reinterpret_cast<float4*>(blk + sw128_off(row, c)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (c_vec) {
       const int n4 = N >> 2;
+#pragma unroll 1
       for (int idx = tid; idx < TC_BM * n4; idx += TC_THREADS) {
-        const int r = idx / n4, c = idx % n4;
-        if (m0 + r < M)
-          st4(C + (int64_t)(m0 + r) * ldc + 4 * c, *reinterpret_cast<const float4*>(&stage_out[r * LDS + 4 * c]));
+        const int r = idx / n4, c4 = idx % n4;
+        if (m0 + r < M) {
+          float4 o = *reinterpret_cast<const float4*>(a_lo + (c4 >> 3) * A_BYTES + sw128_off(r, c4 & 7));
+          if (bias) {
+            o.x += __ldg(bias + 4 * c4); o.y += __ldg(bias + 4 * c4 + 1);
+            o.z += __ldg(bias + 4 * c4 + 2); o.w += __ldg(bias + 4 * c4 + 3);
+          }
+          if (act != BIGNN_ACT_IDENTITY) {
+            o.x = apply_act(o.x, act); o.y = apply_act(o.y, act); o.z = apply_act(o.z, act); o.w = apply_act(o.w, act);
+          }
+          st4(C + (int64_t)(m0 + r) * ldc + 4 * c4, o);
+        }
       }
     } else {
+#pragma unroll 1
       for (int idx = tid; idx < TC_BM * N; idx += TC_THREADS) {
-        const int r = idx / N, c = idx % N;
-        if (m0 + r < M) C[(int64_t)(m0 + r) * ldc + c] = stage_out[r * LDS + c];
+        const int r = idx / N, n = idx % N;
+        if (m0 + r < M) {
+          float o = *reinterpret_cast<const float*>(a_lo + (n >> 5) * A_BYTES + sw128_off(r, (n & 31) >> 2) + (n & 3) * 4);
+          if (bias) o += __ldg(bias + n);
+          C[(int64_t)(m0 + r) * ldc + n] = apply_act(o, act);
+        }
       }
     }
-    __syncthreads();                                            // staging is overwritten by the next tile's operands
+    __syncthreads();                                            // staging (A_lo) is rewritten by the next tile's split
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) {
@@ -312,12 +318,10 @@ k_gemm_tc(int M, int N, int K, const float* __restrict__ A, int64_t lda, const f
 }
 
 template <int NPAD, int KCH>
-static int launch_tc(int M, int N, int K, const float* A, int64_t lda, const float* Yact, int64_t ldy, int act_in,
-                     const float* B, int64_t ldb, int b_is_nk, float* C, int64_t ldc, const float* bias, int act,
-                     cudaStream_t st) {
-  constexpr int a_region = (2 * KCH * TC_BM * 128 > TC_BM * (NPAD + 4) * 4 ? 2 * KCH * TC_BM * 128
-                                                                          : TC_BM * (NPAD + 4) * 4 + 1023) & ~1023;
-  constexpr int smem = a_region + 2 * KCH * NPAD * 128 + 1024;
+static int launch_tc(int M, int N, int K, const float* A, int64_t lda, const float* B, int64_t ldb, int b_is_nk,
+                     float* C, int64_t ldc, const float* bias, int act, cudaStream_t st) {
+  constexpr int lo_ch = KCH > NPAD / 32 ? KCH : NPAD / 32;
+  constexpr int smem = (KCH + lo_ch) * TC_BM * 128 + 2 * KCH * NPAD * 128 + 1024;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<NPAD, KCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -327,20 +331,17 @@ static int launch_tc(int M, int N, int K, const float* A, int64_t lda, const flo
   const int n_tiles = ceil_div(M, TC_BM);
   int grid = 2 * sm_count();
   if (grid > n_tiles) grid = n_tiles;
-  k_gemm_tc<NPAD, KCH><<<grid, TC_THREADS, smem, st>>>(M, N, K, A, lda, Yact, ldy, act_in, B, ldb, b_is_nk, C, ldc, bias,
-                                                       act);
+  k_gemm_tc<NPAD, KCH><<<grid, TC_THREADS, smem, st>>>(M, N, K, A, lda, B, ldb, b_is_nk, C, ldc, bias, act);
   BIGNN_LAUNCH_COUNT(1);
   return last_launch_status();
 }
 
 template <int NPAD>
-static int launch_tc_k(int M, int N, int K, const float* A, int64_t lda, const float* Yact, int64_t ldy, int act_in,
-                       const float* B, int64_t ldb, int b_is_nk, float* C, int64_t ldc, const float* bias, int act,
-                       cudaStream_t st) {
-  if (K <= 32) return launch_tc<NPAD, 1>(M, N, K, A, lda, Yact, ldy, act_in, B, ldb, b_is_nk, C, ldc, bias, act, st);
-  if (K <= 64) return launch_tc<NPAD, 2>(M, N, K, A, lda, Yact, ldy, act_in, B, ldb, b_is_nk, C, ldc, bias, act, st);
-  if (NPAD <= 64 && K <= 96)
-    return launch_tc<NPAD, 3>(M, N, K, A, lda, Yact, ldy, act_in, B, ldb, b_is_nk, C, ldc, bias, act, st);
+static int launch_tc_k(int M, int N, int K, const float* A, int64_t lda, const float* B, int64_t ldb, int b_is_nk,
+                       float* C, int64_t ldc, const float* bias, int act, cudaStream_t st) {
+  if (K <= 32) return launch_tc<NPAD, 1>(M, N, K, A, lda, B, ldb, b_is_nk, C, ldc, bias, act, st);
+  if (K <= 64) return launch_tc<NPAD, 2>(M, N, K, A, lda, B, ldb, b_is_nk, C, ldc, bias, act, st);
+  if (NPAD <= 64 && K <= 96) return launch_tc<NPAD, 3>(M, N, K, A, lda, B, ldb, b_is_nk, C, ldc, bias, act, st);
   return BIGNN_EINVAL;
 }
 
@@ -349,22 +350,22 @@ static int launch_tc_k(int M, int N, int K, const float* A, int64_t lda, const f
 using namespace bignn;
 
 extern "C" int bignn_gemm_tc_supported(int32_t M, int32_t N, int32_t K) {
-  if (M <= 0 || N <= 0 || K <= 0 || N > 128) return 0;
+  if (M <= 0 || N <= 0 || K <= 0 || N > 128 || (K & 3)) return 0;
   return (K <= 64 || (N <= 64 && K <= 96)) ? 1 : 0;
 }
 
-extern "C" int bignn_gemm_tc_f32(int32_t M, int32_t N, int32_t K, const float* A, int64_t lda, const float* act_y,
-                                 int64_t ldy, int32_t act_in, const float* B, int64_t ldb, int32_t b_is_nk, float* C,
-                                 int64_t ldc, const float* bias, int32_t act, void* stream) {
+extern "C" int bignn_gemm_tc_f32(int32_t M, int32_t N, int32_t K, const float* A, int64_t lda, const float* B,
+                                 int64_t ldb, int32_t b_is_nk, float* C, int64_t ldc, const float* bias, int32_t act,
+                                 void* stream) {
   if (M < 0 || N < 0 || K < 0) return BIGNN_EINVAL;
   if (M == 0 || N == 0) return 0;
   if (K == 0 || !A || !B || !C || ldc < N || lda < K) return BIGNN_EINVAL;
   if (!bignn_gemm_tc_supported(M, N, K)) return BIGNN_EINVAL;   // two CTAs/SM: operands must fit in ~110 KB
-  if (act < 0 || act > BIGNN_ACT_TANH || act_in < 0 || act_in > BIGNN_ACT_TANH) return BIGNN_EINVAL;
-  if (act_y && ldy < K) return BIGNN_EINVAL;
+  if ((lda & 3) || !aligned16(A)) return BIGNN_EALIGN;          // 128-bit cp.async of the A rows
+  if (act < 0 || act > BIGNN_ACT_TANH) return BIGNN_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
-  if (N <= 32) return launch_tc_k<32>(M, N, K, A, lda, act_y, ldy, act_in, B, ldb, b_is_nk, C, ldc, bias, act, st);
-  if (N <= 64) return launch_tc_k<64>(M, N, K, A, lda, act_y, ldy, act_in, B, ldb, b_is_nk, C, ldc, bias, act, st);
-  if (N <= 96) return launch_tc_k<96>(M, N, K, A, lda, act_y, ldy, act_in, B, ldb, b_is_nk, C, ldc, bias, act, st);
-  return launch_tc_k<128>(M, N, K, A, lda, act_y, ldy, act_in, B, ldb, b_is_nk, C, ldc, bias, act, st);
+  if (N <= 32) return launch_tc_k<32>(M, N, K, A, lda, B, ldb, b_is_nk, C, ldc, bias, act, st);
+  if (N <= 64) return launch_tc_k<64>(M, N, K, A, lda, B, ldb, b_is_nk, C, ldc, bias, act, st);
+  if (N <= 96) return launch_tc_k<96>(M, N, K, A, lda, B, ldb, b_is_nk, C, ldc, bias, act, st);
+  return launch_tc_k<128>(M, N, K, A, lda, B, ldb, b_is_nk, C, ldc, bias, act, st);
 }

@@ -112,8 +112,8 @@ def gemm(a, b, ta=False, tb=False, bias=None, act=0, out=None):
 TC_MIN_ROWS = 512      # below this a 128-row tensor-core tile grid cannot fill the SMs; SIMT path
 
 
-def gemm_tc(a, b, b_is_nk, bias=None, act=0, act_y=None, act_in=0, out=None):
-    """C = act((a * act_in'(act_y)) @ op(b) + bias) on the tensor cores (tcgen05, 3xTF32)."""
+def gemm_tc(a, b, b_is_nk, bias=None, act=0, out=None):
+    """C = act(a @ op(b) + bias) on the tensor cores (tcgen05, 3xTF32)."""
     a, b = _f32c(a), _f32c(b)
     _lib.require_device(a, b)
     M, K = a.shape
@@ -121,15 +121,13 @@ def gemm_tc(a, b, b_is_nk, bias=None, act=0, act_y=None, act_in=0, out=None):
     if (b.shape[1] if b_is_nk else b.shape[0]) != K:
         raise ValueError('gemm_tc: inner dimensions differ')
     c = out if out is not None else torch.empty((M, N), dtype=torch.float32, device=a.device)
-    if act_y is not None:
-        act_y = _f32c(act_y)
-    _lib.call('bignn_gemm_tc_f32', M, N, K, a, a.stride(0), act_y, act_y.stride(0) if act_y is not None else 0,
-              int(act_in), b, b.stride(0), int(bool(b_is_nk)), c, c.stride(0), bias, int(act))
+    _lib.call('bignn_gemm_tc_f32', M, N, K, a, a.stride(0), b, b.stride(0), int(bool(b_is_nk)), c, c.stride(0), bias,
+              int(act))
     return c
 
 
 def use_tc(M, N, K):
-    return M >= TC_MIN_ROWS and N <= 128 and (K <= 64 or (N <= 64 and K <= 96))
+    return M >= TC_MIN_ROWS and N <= 128 and K % 4 == 0 and (K <= 64 or (N <= 64 and K <= 96))
 
 
 def colsum(x):

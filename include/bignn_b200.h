@@ -131,14 +131,12 @@ int bignn_gemm_f32(int32_t ta, int32_t tb, int32_t M, int32_t N, int32_t K,
                    float* C, int64_t ldc, const float* bias, int32_t act,
                    void* workspace, int64_t workspace_bytes, void* stream);
 /* Tensor-core variant for the tall-skinny transforms of the path (tcgen05.mma kind::tf32 with TMEM
- * accumulators, fp32-accurate through a 3xTF32 hi/lo split; N <= 128, any K, any M):
- *   C[M,N] = act( (A * act_in'(act_y))[M,K] * op(B) + bias ),
- * B stored [N,K] (b_is_nk = 1, nn.Linear layout) or [K,N] (b_is_nk = 0, PyG layout).  act_y (optional)
- * fuses the backward of an activation into the operand load: A is then dY and act_y the activation
- * OUTPUT it is masked/scaled with. */
+ * accumulators, fp32-accurate through a 3xTF32 hi/lo split):  C[M,N] = act(A[M,K] * op(B) + bias),
+ * B stored [N,K] (b_is_nk = 1, nn.Linear layout) or [K,N] (b_is_nk = 0, PyG layout).
+ * Persistent kernel, two CTAs per SM, cp.async operand staging.  Requires N <= 128, K % 4 == 0,
+ * K <= 64 (K <= 96 for N <= 64), lda % 4 == 0 and a 16-byte aligned A. */
 int bignn_gemm_tc_supported(int32_t M, int32_t N, int32_t K);   /* 1 if the shape has a tensor-core kernel (N<=128, K<=64; K<=96 for N<=64) */
 int bignn_gemm_tc_f32(int32_t M, int32_t N, int32_t K, const float* A, int64_t lda,
-                      const float* act_y, int64_t ldy, int32_t act_in,
                       const float* B, int64_t ldb, int32_t b_is_nk,
                       float* C, int64_t ldc, const float* bias, int32_t act, void* stream);
 /* column sums out[c] = sum_r X[r,c]  (bias gradients), deterministic */

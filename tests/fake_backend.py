@@ -105,12 +105,8 @@ class Fake(object):
     def bignn_gemm_tc_supported(self, M, N, K):
         return 1
 
-    def bignn_gemm_tc_f32(self, M, N, K, A, lda, act_y, ldy, act_in, B, ldb, b_is_nk, C, ldc, bias, act):
-        a = A
-        if act_y is not None:
-            g = {0: torch.ones_like(act_y), 1: (act_y > 0).float(), 2: (1 - act_y) * act_y, 3: 1 - act_y * act_y}[act_in]
-            a = A * g
-        out = a @ (B.t() if b_is_nk else B)
+    def bignn_gemm_tc_f32(self, M, N, K, A, lda, B, ldb, b_is_nk, C, ldc, bias, act):
+        out = A @ (B.t() if b_is_nk else B)
         if bias is not None:
             out = out + bias
         C[:M, :N] = ACTS[act](out)
