@@ -39,6 +39,9 @@ SIGNATURES = {
     'bignn_gemm_f32': ('i', 'iiiii' 'pl' 'pl' 'pl' 'pi' 'pl' 's'),
     'bignn_gemm_tc_supported': ('i', 'iii'),
     'bignn_gemm_tc_f32': ('i', 'iii' 'pl' 'pli' 'pl' 'pi' 's'),
+    'bignn_dw_tc_supported': ('i', 'iii'),
+    'bignn_dw_tc_workspace_bytes': ('l', 'iii'),
+    'bignn_dw_tc_f32': ('i', 'iii' 'pl' 'pl' 'p' 'ip' 'pl' 's'),
     'bignn_colsum_workspace_bytes': ('l', 'ii'),
     'bignn_colsum_f32': ('i', 'pliip' 'pl' 's'),
     'bignn_act_bwd_f32': ('i', 'ppplis'),
@@ -160,7 +163,7 @@ def call(name, *args):
     if codes.endswith('s'):
         cargs.append(torch.cuda.current_stream().cuda_stream)
     out = getattr(lib, name)(*cargs)
-    if res == 'i' and name not in ('bignn_abi_version', 'bignn_gemm_tc_supported') and out != 0:
+    if res == 'i' and name not in ('bignn_abi_version', 'bignn_gemm_tc_supported', 'bignn_dw_tc_supported') and out != 0:
         raise RuntimeError('{} failed with status {}: {}'.format(name, out, error_string(out)))
     return out
 

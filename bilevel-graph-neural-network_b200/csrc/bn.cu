@@ -76,6 +76,7 @@ k_bn_finalize(const double* __restrict__ ws_a, const double* __restrict__ ws_b,
   const int s = (int)(i / C), c = (int)(i % C);
   const int n = seg_row_ptr[s + 1] - seg_row_ptr[s];
   double a = 0.0, b = 0.0;
+#pragma unroll 8
   for (int p = 0; p < parts; ++p) {
     a += ws_a[((int64_t)s * parts + p) * C + c];
     b += ws_b[((int64_t)s * parts + p) * C + c];
@@ -153,6 +154,7 @@ k_bn_bwd_finalize(const double* __restrict__ ws_a, const double* __restrict__ ws
   if (i >= (int64_t)S * C) return;
   const int s = (int)(i / C), c = (int)(i % C);
   double a = 0.0, b = 0.0;
+#pragma unroll 8
   for (int p = 0; p < parts; ++p) {
     a += ws_a[((int64_t)s * parts + p) * C + c];
     b += ws_b[((int64_t)s * parts + p) * C + c];
@@ -167,6 +169,7 @@ k_bn_bwd_params(const double* __restrict__ seg_a, const double* __restrict__ seg
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double a = 0.0, b = 0.0;
+#pragma unroll 8
   for (int s = 0; s < S; ++s) { a += seg_a[(int64_t)s * C + c]; b += seg_b[(int64_t)s * C + c]; }
   if (dbeta) dbeta[c] = (float)a;
   if (dgamma) dgamma[c] = (float)b;

@@ -102,16 +102,29 @@ k_gemm_f32(int M, int N, int K, const float* __restrict__ A, int64_t lda,
   }
 }
 
+// C[i] = act(sum_z ws[z][i] + bias): 32 consecutive outputs x 8 split groups per block -- every
+// warp reads 128 contiguous bytes per split, the 8 groups are combined in fixed order (deterministic).
 __global__ void __launch_bounds__(256)
 k_splitk_reduce(const float* __restrict__ ws, int splits, int M, int N, float* __restrict__ C, int64_t ldc,
                 const float* __restrict__ bias, int act) {
+  __shared__ float red[8][33];
   const int64_t total = (int64_t)M * N;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    float s = 0.f;
-    for (int z = 0; z < splits; ++z) s += ws[(int64_t)z * total + i];   // fixed order
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+  const int64_t i = (int64_t)blockIdx.x * 32 + tx;
+  float s = 0.f;
+  if (i < total) {
+#pragma unroll 4
+    for (int z = ty; z < splits; z += 8) s += __ldg(ws + (int64_t)z * total + i);
+  }
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && i < total) {
+    float t = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) t += red[g][tx];
     const int m = (int)(i / N), n = (int)(i % N);
-    if (bias) s += __ldg(bias + n);
-    C[(int64_t)m * ldc + n] = apply_act(s, act);
+    if (bias) t += __ldg(bias + n);
+    C[(int64_t)m * ldc + n] = apply_act(t, act);
   }
 }
 
@@ -157,11 +170,22 @@ k_colsum_part(const float* __restrict__ X, int64_t ldx, int rows, int cols, int 
 
 __global__ void __launch_bounds__(256)
 k_colsum_final(const double* __restrict__ ws, int parts, int cols, float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
+  __shared__ double red[8][33];
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+  const int c = blockIdx.x * 32 + tx;
   double s = 0.0;
-  for (int p = 0; p < parts; ++p) s += ws[(int64_t)p * cols + c];
-  out[c] = (float)s;
+  if (c < cols) {
+#pragma unroll 4
+    for (int p = ty; p < parts; p += 8) s += ws[(int64_t)p * cols + c];
+  }
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < cols) {
+    double t = 0.0;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) t += red[g][tx];
+    out[c] = (float)t;
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -213,10 +237,7 @@ extern "C" int bignn_gemm_f32(int32_t ta, int32_t tb, int32_t M, int32_t N, int3
   else k_gemm_f32<true, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, act, k_chunk, ws);
   BIGNN_LAUNCH_COUNT(1);
   if (splits > 1) {
-    int g = ceil_div(M * N, 256);
-    const int cap = sm_count() * 8;
-    if (g > cap) g = cap;
-    k_splitk_reduce<<<g, 256, 0, st>>>(ws, splits, M, N, C, ldc, bias, act);
+    k_splitk_reduce<<<ceil_div(M * N, 32), 256, 0, st>>>(ws, splits, M, N, C, ldc, bias, act);
     BIGNN_LAUNCH_COUNT(1);
   }
   return last_launch_status();
@@ -239,7 +260,7 @@ extern "C" int bignn_colsum_f32(const float* X, int64_t ldx, int32_t rows, int32
   if (!workspace || workspace_bytes < (int64_t)parts * cols * (int64_t)sizeof(double)) return BIGNN_EWORKSPACE;
   dim3 grid(ceil_div(cols, 32), parts);
   k_colsum_part<<<grid, 256, 0, st>>>(X, ldx, rows, cols, parts, (double*)workspace);
-  k_colsum_final<<<ceil_div(cols, 256), 256, 0, st>>>((const double*)workspace, parts, cols, out);
+  k_colsum_final<<<ceil_div(cols, 32), 256, 0, st>>>((const double*)workspace, parts, cols, out);
   BIGNN_LAUNCH_COUNT(2);
   return last_launch_status();
 }

@@ -1,0 +1,274 @@
+// Weight gradients on the tensor cores:  D[Np, Nq] = P^T Q  (+ column sums of P or Q), reduction over
+// the M rows (atoms / drugs), fp32-accurate through 3xTF32 (see include/bignn_b200.h: bignn_dw_tc_f32).
+// Replaces autograd's dW = dY^T X / X^T dY and db = sum dY of nn.Linear / `x @ weight`
+// (model/layers.py:26-30, PyG GCNConv/GATConv).
+//
+// A row tile [128 rows x 64 floats] staged as two [rows x 128 B] SWIZZLE_128B blocks is exactly the
+// canonical MN-major UMMA operand (MN = feature, K = row): 8-row groups are the K steps (SBO = 1024 B),
+// the two 32-feature blocks are LBO = 16 KB apart.  Per 128-row tile 16 K-steps x 3 products
+// (hi*hi + lo*hi + hi*lo) accumulate into TMEM; accumulators persist across all tiles of the CTA and
+// the per-CTA partial [64 x 64] goes to a workspace that a fixed-order reduction sums (deterministic).
+// The MMA runs with M = 128: rows 64..127 of D come from the Q blocks that follow P in shared memory
+// and are ignored (a 64-row MMA costs the same tensor time and has a scattered TMEM layout).
+#include "tc_common.cuh"
+
+namespace bignn {
+
+constexpr int DW_F = 64;                       // padded feature width of both operands
+constexpr int DW_BLK = TC_BM * 128;            // one [128 rows x 128 B] block
+constexpr int DW_TILE = 2 * DW_BLK;            // one operand tile (64 features)
+constexpr int DW_NA = 4;                       // rotating main accumulators
+
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
+  // MN-major, SWIZZLE_128B: LBO = distance between 32-feature blocks, SBO = distance between 8-row groups
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(DW_BLK >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+
+__device__ __forceinline__ uint32_t umma_idesc_tf32_mn(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+
+// smem: [P_hi][Q_hi][P_lo][Q_lo], each DW_TILE bytes
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_dw_tc(int M, int Np, int Nq, const float* __restrict__ P, int64_t ldp, const float* __restrict__ Q, int64_t ldq,
+        int colsum_of, float* __restrict__ ws_dw, double* __restrict__ ws_cs) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* p_hi = smem;
+  uint8_t* q_hi = p_hi + DW_TILE;
+  uint8_t* p_lo = q_hi + DW_TILE;
+  __shared__ uint64_t mma_bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ double cs_red[4][DW_F];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_tiles = (M + TC_BM - 1) / TC_BM;
+  constexpr int TMEM_COLS = 512;               // (DW_NA + 1) * 64 = 320 columns -> next power of two
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 32) {
+    mbar_init(&mma_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  const uint32_t hi_s = smem_u32(p_hi);
+  // both operand tiles: 2 x 2048 sixteen-byte chunks; zero fill beyond M rows / N features
+  auto prefetch_tile = [&](int tile) {
+    const int m0 = tile * TC_BM;
+#pragma unroll 1
+    for (int j = tid; j < 4096; j += TC_THREADS) {
+      const int op = j >> 11, idx = j & 2047;           // op 0 = P, 1 = Q
+      const int blk = idx >> 10, r = (idx & 1023) >> 3, c = idx & 7;
+      const int gm = m0 + r, gf = blk * 32 + c * 4;
+      const int nf = op ? Nq : Np;
+      const bool ok = gm < M && gf < nf;
+      const float* base = op ? Q + (int64_t)gm * ldq : P + (int64_t)gm * ldp;
+      cp_async16(hi_s + op * DW_TILE + blk * DW_BLK + sw128_off(r, c), ok ? base + gf : (op ? Q : P), ok ? 16u : 0u);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int tile = blockIdx.x;
+  if (tile < n_tiles) prefetch_tile(tile);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = tmem_base_s;
+  const uint32_t idesc = umma_idesc_tf32_mn(TC_BM, DW_F);
+
+  double cs = 0.0;                                     // this thread's column-sum share
+  const int cs_col = tid & 63, cs_rg = tid >> 6;
+  uint32_t phase = 0;
+  int ks = 0;                                          // K steps issued so far (across tiles)
+  for (; tile < n_tiles; tile += gridDim.x) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    // ---- lo = tf32(x - hi(x)) for the chunks this thread copied
+#pragma unroll 1
+    for (int j = tid; j < 4096; j += TC_THREADS) {
+      const int op = j >> 11, idx = j & 2047;
+      const uint32_t off = op * DW_TILE + (idx >> 10) * DW_BLK + sw128_off((idx & 1023) >> 3, idx & 7);
+      const float4 x = *reinterpret_cast<const float4*>(p_hi + off);
+      uint4 l;
+      l.x = __float_as_uint(x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u)) & 0xffffe000u;
+      l.y = __float_as_uint(x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u)) & 0xffffe000u;
+      l.z = __float_as_uint(x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u)) & 0xffffe000u;
+      l.w = __float_as_uint(x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u)) & 0xffffe000u;
+      *reinterpret_cast<uint4*>(p_lo + off) = l;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint64_t dp_hi = umma_desc_mn_sw128(smem_u32(p_hi)), dp_lo = umma_desc_mn_sw128(smem_u32(p_lo));
+      const uint64_t dq_hi = umma_desc_mn_sw128(smem_u32(q_hi)), dq_lo = umma_desc_mn_sw128(smem_u32(p_lo + DW_TILE));
+#pragma unroll 1
+      for (int k = 0; k < TC_BM / 8; ++k, ++ks) {
+        const uint64_t adv = (uint64_t)((k * 1024) >> 4);       // next 8-row group
+        umma_tf32(tmem_d + (uint32_t)((ks % DW_NA) * DW_F), dp_hi + adv, dq_hi + adv, idesc, ks >= DW_NA ? 1u : 0u);
+        umma_tf32(tmem_d + (uint32_t)(DW_NA * DW_F), dp_lo + adv, dq_hi + adv, idesc, ks > 0 ? 1u : 0u);
+        umma_tf32(tmem_d + (uint32_t)(DW_NA * DW_F), dp_hi + adv, dq_lo + adv, idesc, 1u);
+      }
+      umma_commit(&mma_bar);
+    } else if (tid >= 32) {
+      ks += TC_BM / 8;
+    }
+    // ---- column sums of the chosen operand from the raw tile (while the tensor core runs)
+    if (colsum_of >= 0) {
+      const uint8_t* t0 = p_hi + (colsum_of ? DW_TILE : 0) + (cs_col >> 5) * DW_BLK;
+      const int c = (cs_col & 31) >> 2, e = cs_col & 3;
+      float s = 0.f;
+#pragma unroll 4
+      for (int r = cs_rg; r < TC_BM; r += 4) s += *reinterpret_cast<const float*>(t0 + sw128_off(r, c) + e * 4);
+      cs += (double)s;
+    }
+    mbar_wait(&mma_bar, phase);
+    phase ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    __syncthreads();                                     // every thread is done reading the raw tile
+    if (tile + gridDim.x < n_tiles) prefetch_tile(tile + gridDim.x);
+  }
+  ks = __shfl_sync(0xffffffffu, ks, 0);                  // warp 0: lane 0 counted while issuing
+  // ---- per-CTA partials: D rows 0..63 live in TMEM lanes 0..63 (warps with quadrant 0 and 1)
+  const int n_steps = ((n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * (TC_BM / 8);
+  {
+    const int q = warp & 3;
+    if (q < 2) {
+      const int row = q * 32 + lane;                     // output feature of P
+#pragma unroll 1
+      for (int cb = (warp >> 2) * 32; cb < DW_F; cb += 64) {
+        uint32_t r[32];
+        float v[32];
+        const uint32_t tbase = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)cb;
+        if (n_steps > 0) {
+          tmem_ld32(tbase + (uint32_t)(DW_NA * DW_F), r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+#pragma unroll 1
+        for (int a = 0; a < DW_NA; ++a) {
+          if (a >= n_steps) break;
+          tmem_ld32(tbase + (uint32_t)(a * DW_F), r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __fadd_rn(__uint_as_float(r[j]), v[j]);
+        }
+        if (row < Np) {
+          float* dst = ws_dw + ((int64_t)blockIdx.x * Np + row) * Nq;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (cb + j < Nq) dst[cb + j] = v[j];
+        }
+      }
+    }
+  }
+  if (colsum_of >= 0) {
+    cs_red[cs_rg][cs_col] = cs;
+    __syncthreads();
+    const int ncs = colsum_of ? Nq : Np;
+    if (tid < ncs) ws_cs[(int64_t)blockIdx.x * ncs + tid] = ((cs_red[0][tid] + cs_red[1][tid]) + cs_red[2][tid]) + cs_red[3][tid];
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// fixed-order sums over the per-CTA partials
+__global__ void __launch_bounds__(256)
+k_dw_reduce(const float* __restrict__ ws_dw, int parts, int total, float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+  const int i = blockIdx.x * 32 + tx;
+  float s = 0.f;
+  if (i < total) {
+#pragma unroll 4
+    for (int z = ty; z < parts; z += 8) s += __ldg(ws_dw + (int64_t)z * total + i);
+  }
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && i < total) {
+    float t = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) t += red[g][tx];
+    out[i] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_dw_cs_reduce(const double* __restrict__ ws, int parts, int cols, float* __restrict__ out) {
+  __shared__ double red[8][33];
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+  const int c = blockIdx.x * 32 + tx;
+  double s = 0.0;
+  if (c < cols) {
+#pragma unroll 4
+    for (int p = ty; p < parts; p += 8) s += ws[(int64_t)p * cols + c];
+  }
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < cols) {
+    double t = 0.0;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) t += red[g][tx];
+    out[c] = (float)t;
+  }
+}
+
+static int dw_grid(int M) {
+  const int n_tiles = ceil_div(M, TC_BM);
+  int g = sm_count();
+  return g > n_tiles ? n_tiles : g;
+}
+
+}  // namespace bignn
+
+using namespace bignn;
+
+extern "C" int bignn_dw_tc_supported(int32_t M, int32_t Np, int32_t Nq) {
+  return (M > 0 && Np > 0 && Nq > 0 && Np <= DW_F && Nq <= DW_F && (Np % 4) == 0 && (Nq % 4) == 0) ? 1 : 0;
+}
+
+extern "C" int64_t bignn_dw_tc_workspace_bytes(int32_t M, int32_t Np, int32_t Nq) {
+  if (!bignn_dw_tc_supported(M, Np, Nq)) return 0;
+  const int64_t g = dw_grid(M);
+  return g * Np * Nq * (int64_t)sizeof(float) + g * DW_F * (int64_t)sizeof(double) + 64;
+}
+
+extern "C" int bignn_dw_tc_f32(int32_t M, int32_t Np, int32_t Nq, const float* P, int64_t ldp, const float* Q,
+                               int64_t ldq, float* D, int32_t colsum_of, float* colsum, void* workspace,
+                               int64_t workspace_bytes, void* stream) {
+  if (!bignn_dw_tc_supported(M, Np, Nq)) return BIGNN_EINVAL;
+  if (!P || !Q || !D || ldp < Np || ldq < Nq) return BIGNN_EINVAL;
+  if (colsum_of > 1 || (colsum_of >= 0 && !colsum)) return BIGNN_EINVAL;
+  if ((ldp & 3) || (ldq & 3) || !aligned16(P) || !aligned16(Q)) return BIGNN_EALIGN;
+  if (!workspace || workspace_bytes < bignn_dw_tc_workspace_bytes(M, Np, Nq)) return BIGNN_EWORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = dw_grid(M);
+  float* ws_dw = (float*)workspace;
+  double* ws_cs = (double*)((uint8_t*)workspace + (((int64_t)grid * Np * Nq * sizeof(float) + 15) & ~(int64_t)15));
+  constexpr int smem = 4 * DW_TILE + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_dw_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  k_dw_tc<<<grid, TC_THREADS, smem, st>>>(M, Np, Nq, P, ldp, Q, ldq, colsum_of < 0 ? -1 : colsum_of, ws_dw, ws_cs);
+  k_dw_reduce<<<ceil_div(Np * Nq, 32), 256, 0, st>>>(ws_dw, grid, Np * Nq, D);
+  BIGNN_LAUNCH_COUNT(2);
+  if (colsum_of >= 0) {
+    const int ncs = colsum_of ? Nq : Np;
+    k_dw_cs_reduce<<<ceil_div(ncs, 32), 256, 0, st>>>(ws_cs, grid, ncs, colsum);
+    BIGNN_LAUNCH_COUNT(1);
+  }
+  return last_launch_status();
+}

@@ -70,7 +70,7 @@ class _Staging(object):
 
 class BiGNNEngine(object):
     def __init__(self, data, model, optimizer=None, lr=None, use_cuda_graph=True, rebuild_each_step=True,
-                 n_staging=4, rank=0, world=1, group=None):
+                 n_staging=4, rank=0, world=1, group=None, adam_capturable=None):
         flags = get_flags()
         assert flags.lower_level_layers and flags.higher_level_layers, 'engine runs the Bi-GNN mode'
         self.data, self.model = data, model
@@ -78,7 +78,8 @@ class BiGNNEngine(object):
         self.use_cuda_graph = use_cuda_graph and self.device.type == 'cuda'
         self.rebuild_each_step = rebuild_each_step
         self.optimizer = optimizer if optimizer is not None else torch.optim.Adam(
-            model.parameters(), lr=flags.lr if lr is None else lr, capturable=self.use_cuda_graph)
+            model.parameters(), lr=flags.lr if lr is None else lr,
+            capturable=self.use_cuda_graph if adam_capturable is None else adam_capturable)
         # ---- static all-drug merged graph: chunk schedule of src/train.py:52-71
         self.rank, self.world, self.group = int(rank), int(world), group
         gids = list(data.gs_map.keys())

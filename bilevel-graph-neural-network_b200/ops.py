@@ -130,6 +130,23 @@ def use_tc(M, N, K):
     return M >= TC_MIN_ROWS and N <= 128 and K % 4 == 0 and (K <= 64 or (N <= 64 and K <= 96))
 
 
+def dw_tc(p, q, colsum_of=-1):
+    """(p^T q, column sums of p or q) on the tensor cores; p [M,Np], q [M,Nq]."""
+    p, q = _f32c(p), _f32c(q)
+    _lib.require_device(p, q)
+    M, Np, Nq = p.shape[0], p.shape[1], q.shape[1]
+    d = torch.empty((Np, Nq), dtype=torch.float32, device=p.device)
+    cs = torch.empty(Nq if colsum_of == 1 else Np, dtype=torch.float32, device=p.device) if colsum_of >= 0 else None
+    wsb = _lib.call('bignn_dw_tc_workspace_bytes', M, Np, Nq)
+    ws = _ws(wsb, p.device)
+    _lib.call('bignn_dw_tc_f32', M, Np, Nq, p, p.stride(0), q, q.stride(0), d, int(colsum_of), cs, ws, int(wsb))
+    return d, cs
+
+
+def use_dw_tc(M, Np, Nq):
+    return M >= TC_MIN_ROWS and Np <= 64 and Nq <= 64 and Np % 4 == 0 and Nq % 4 == 0
+
+
 def colsum(x):
     x = _f32c(x)
     _lib.require_device(x)
@@ -231,10 +248,17 @@ class _LinearAct(torch.autograd.Function):
                 dx = gemm_tc(g, weight, ctx.layout == 'io')
             else:
                 dx = gemm(g, weight, False, ctx.layout == 'io')
-        if ctx.needs_input_grad[1]:
-            dw = gemm(g, x, True, False) if ctx.layout == 'oi' else gemm(x, g, True, False)
-        if ctx.needs_input_grad[2]:
-            db = colsum(g)
+        want_b = ctx.needs_input_grad[2]
+        if ctx.needs_input_grad[1] and use_dw_tc(g.shape[0], g.shape[1], x.shape[1]):
+            if ctx.layout == 'oi':
+                dw, db = dw_tc(g, x, 0 if want_b else -1)
+            else:
+                dw, db = dw_tc(x, g, 1 if want_b else -1)
+        else:
+            if ctx.needs_input_grad[1]:
+                dw = gemm(g, x, True, False) if ctx.layout == 'oi' else gemm(x, g, True, False)
+            if want_b:
+                db = colsum(g)
         return dx, dw, db, None, None
 
 

@@ -139,6 +139,16 @@ int bignn_gemm_tc_supported(int32_t M, int32_t N, int32_t K);   /* 1 if the shap
 int bignn_gemm_tc_f32(int32_t M, int32_t N, int32_t K, const float* A, int64_t lda,
                       const float* B, int64_t ldb, int32_t b_is_nk,
                       float* C, int64_t ldc, const float* bias, int32_t act, void* stream);
+/* Weight gradients on the tensor cores:  D[Np,Nq] = P[M,Np]^T * Q[M,Nq]  (row-major, ld = Nq) and,
+ * optionally, the column sums of P (colsum_of = 0) or Q (colsum_of = 1) -> colsum[] (bias gradient);
+ * colsum_of = -1 skips them.  3xTF32 on tcgen05 with MN-major operands, per-CTA partials summed in a
+ * fixed order (deterministic).  Requires Np, Nq <= 64 and multiples of 4, ld % 4 == 0, 16-byte
+ * aligned operands. */
+int bignn_dw_tc_supported(int32_t M, int32_t Np, int32_t Nq);
+int64_t bignn_dw_tc_workspace_bytes(int32_t M, int32_t Np, int32_t Nq);
+int bignn_dw_tc_f32(int32_t M, int32_t Np, int32_t Nq, const float* P, int64_t ldp,
+                    const float* Q, int64_t ldq, float* D, int32_t colsum_of, float* colsum,
+                    void* workspace, int64_t workspace_bytes, void* stream);
 /* column sums out[c] = sum_r X[r,c]  (bias gradients), deterministic */
 int64_t bignn_colsum_workspace_bytes(int32_t rows, int32_t cols);
 int bignn_colsum_f32(const float* X, int64_t ldx, int32_t rows, int32_t cols, float* out,

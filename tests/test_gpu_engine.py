@@ -66,7 +66,9 @@ def test_graph_replay_equals_eager_over_several_steps(golden_dir, step_golden):
     losses = {}
     for graph in (False, True):
         data, model = fresh(golden_dir, z)
-        eng = BiGNNEngine(data, model, use_cuda_graph=graph)
+        # same Adam code path in both (capturable=True keeps `step` on the device and orders a few
+        # scalar operations differently from the host-scalar path)
+        eng = BiGNNEngine(data, model, use_cuda_graph=graph, adam_capturable=True)
         out = []
         for i in range(4):
             gids = np.concatenate([s['pos'][i], s['neg'][i]])

@@ -221,6 +221,24 @@ def test_gemm_tensor_core_3xtf32_vs_fp64(M, N, K, nk):
     assert torch.equal(got, ops.gemm_tc(a.to(DEV), b.to(DEV), nk))       # deterministic
 
 
+@pytest.mark.parametrize('M,Np,Nq,cs', [(95038, 64, 64, 0), (95038, 64, 40, 0), (3242, 64, 64, 1), (3712, 40, 64, 1),
+                                        (513, 64, 64, -1), (128, 16, 8, 0), (40000, 64, 64, 0)])
+def test_weight_gradient_tensor_core_vs_fp64(M, Np, Nq, cs):
+    g = torch.Generator().manual_seed(M + Np + Nq)
+    p = torch.randn(M, Np, generator=g)
+    q = torch.randn(M, Nq, generator=g) + 0.5
+    want = p.double().t() @ q.double()
+    d, c = ops.dw_tc(p.to(DEV), q.to(DEV), cs)
+    scale = float(np.sqrt(M))                       # |sum of M unit-variance products|
+    assert float((d.double().cpu() - want).abs().max()) / (scale * max(1.0, float(want.abs().max()) / scale)) < 2e-5
+    assert rel(d, want) < 5e-5
+    if cs >= 0:
+        ref = (p if cs == 0 else q).double().sum(0)
+        assert rel(c, ref) < 1e-6
+    d2, _ = ops.dw_tc(p.to(DEV), q.to(DEV), cs)
+    assert torch.equal(d, d2)                       # deterministic
+
+
 def test_gemm_is_deterministic_with_split_k():
     g = torch.Generator().manual_seed(0)
     a = torch.randn(36816, 64, generator=g).to(DEV)
