@@ -3,9 +3,10 @@
 // Replaces autograd's dW = dY^T X / X^T dY and db = sum dY of nn.Linear / `x @ weight`
 // (model/layers.py:26-30, PyG GCNConv/GATConv).
 //
-// A row tile [128 rows x 64 floats] staged as two [rows x 128 B] SWIZZLE_128B blocks is exactly the
-// canonical MN-major UMMA operand (MN = feature, K = row): 8-row groups are the K steps (SBO = 1024 B),
-// the two 32-feature blocks are LBO = 16 KB apart.  Per 128-row tile 16 K-steps x 3 products
+// A row tile [128 rows x 64 floats] staged as two [rows x 128 B] blocks is the canonical MN-major UMMA
+// operand (MN = feature, K = row).  For 32-bit MN-major operands the only legal shared-memory layout is
+// SWIZZLE_128B_BASE32B: 4-row groups (SBO = 512 B) whose four 32-byte chunks are XOR-permuted with
+// the row index; the two 32-feature blocks are LBO = 16 KB apart; one K step (8 TF32) = two groups.  Per 128-row tile 16 K-steps x 3 products
 // (hi*hi + lo*hi + hi*lo) accumulate into TMEM; accumulators persist across all tiles of the CTA and
 // the per-CTA partial [64 x 64] goes to a workspace that a fixed-order reduction sums (deterministic).
 // The MMA runs with M = 128: rows 64..127 of D come from the Q blocks that follow P in shared memory
@@ -20,9 +21,16 @@ constexpr int DW_TILE = 2 * DW_BLK;            // one operand tile (64 features)
 constexpr int DW_NA = 4;                       // rotating main accumulators
 
 __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
-  // MN-major, SWIZZLE_128B: LBO = distance between 32-feature blocks, SBO = distance between 8-row groups
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(DW_BLK >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
-         (1ull << 46) | (2ull << 61);
+  // MN-major, SWIZZLE_128B_BASE32B (layout type 1): LBO = distance between 32-feature blocks,
+  // SBO = distance between 4-row groups
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(DW_BLK >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
+         (1ull << 46) | (1ull << 61);
+}
+
+// byte offset of 16-byte chunk c (0..7) of row r inside a [rows x 128 B] block, Swizzle<2,5,2>:
+// the 32-byte chunk index (c >> 1) is XORed with the row's position in its 4-row group
+__device__ __forceinline__ uint32_t sw32b_off(int r, int c) {
+  return (uint32_t)((r >> 2) * 512 + (r & 3) * 128 + ((((c >> 1) ^ (r & 3)) << 5) | ((c & 1) << 4)));
 }
 
 __device__ __forceinline__ uint32_t umma_idesc_tf32_mn(int M, int N) {
@@ -30,15 +38,14 @@ __device__ __forceinline__ uint32_t umma_idesc_tf32_mn(int M, int N) {
          ((uint32_t)(M >> 4) << 24);
 }
 
-// smem: [P_hi][Q_hi][P_lo][Q_lo], each DW_TILE bytes
+// smem: 2 x [P_hi][Q_hi] (double buffered: the next tile streams in while this one is multiplied)
+//       + [P_lo][Q_lo], each DW_TILE bytes
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_dw_tc(int M, int Np, int Nq, const float* __restrict__ P, int64_t ldp, const float* __restrict__ Q, int64_t ldq,
         int colsum_of, float* __restrict__ ws_dw, double* __restrict__ ws_cs) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* p_hi = smem;
-  uint8_t* q_hi = p_hi + DW_TILE;
-  uint8_t* p_lo = q_hi + DW_TILE;
+  uint8_t* p_lo = smem + 4 * DW_TILE;
   __shared__ uint64_t mma_bar;
   __shared__ uint32_t tmem_base_s;
   __shared__ double cs_red[4][DW_F];
@@ -57,10 +64,11 @@ k_dw_tc(int M, int Np, int Nq, const float* __restrict__ P, int64_t ldp, const f
     mbar_init(&mma_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  const uint32_t hi_s = smem_u32(p_hi);
+  const uint32_t smem_s = smem_u32(smem);
   // both operand tiles: 2 x 2048 sixteen-byte chunks; zero fill beyond M rows / N features
-  auto prefetch_tile = [&](int tile) {
+  auto prefetch_tile = [&](int tile, int buf) {
     const int m0 = tile * TC_BM;
+    const uint32_t hi_s = smem_s + buf * 2 * DW_TILE;
 #pragma unroll 1
     for (int j = tid; j < 4096; j += TC_THREADS) {
       const int op = j >> 11, idx = j & 2047;           // op 0 = P, 1 = Q
@@ -69,12 +77,13 @@ k_dw_tc(int M, int Np, int Nq, const float* __restrict__ P, int64_t ldp, const f
       const int nf = op ? Nq : Np;
       const bool ok = gm < M && gf < nf;
       const float* base = op ? Q + (int64_t)gm * ldq : P + (int64_t)gm * ldp;
-      cp_async16(hi_s + op * DW_TILE + blk * DW_BLK + sw128_off(r, c), ok ? base + gf : (op ? Q : P), ok ? 16u : 0u);
+      cp_async16(hi_s + op * DW_TILE + blk * DW_BLK + sw32b_off(r, c), ok ? base + gf : (op ? Q : P), ok ? 16u : 0u);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   int tile = blockIdx.x;
-  if (tile < n_tiles) prefetch_tile(tile);
+  int buf = 0;
+  if (tile < n_tiles) prefetch_tile(tile, 0);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -85,13 +94,17 @@ k_dw_tc(int M, int Np, int Nq, const float* __restrict__ P, int64_t ldp, const f
   const int cs_col = tid & 63, cs_rg = tid >> 6;
   uint32_t phase = 0;
   int ks = 0;                                          // K steps issued so far (across tiles)
-  for (; tile < n_tiles; tile += gridDim.x) {
+  for (; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
+    uint8_t* p_hi = smem + buf * 2 * DW_TILE;
+    uint8_t* q_hi = p_hi + DW_TILE;
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+    // the other hi buffer was last read by the previous tile's MMAs, which have completed: refill it now
+    if (tile + gridDim.x < n_tiles) prefetch_tile(tile + gridDim.x, buf ^ 1);
     // ---- lo = tf32(x - hi(x)) for the chunks this thread copied
 #pragma unroll 1
     for (int j = tid; j < 4096; j += TC_THREADS) {
       const int op = j >> 11, idx = j & 2047;
-      const uint32_t off = op * DW_TILE + (idx >> 10) * DW_BLK + sw128_off((idx & 1023) >> 3, idx & 7);
+      const uint32_t off = op * DW_TILE + (idx >> 10) * DW_BLK + sw32b_off((idx & 1023) >> 3, idx & 7);
       const float4 x = *reinterpret_cast<const float4*>(p_hi + off);
       uint4 l;
       l.x = __float_as_uint(x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u)) & 0xffffe000u;
@@ -123,14 +136,13 @@ k_dw_tc(int M, int Np, int Nq, const float* __restrict__ P, int64_t ldp, const f
       const int c = (cs_col & 31) >> 2, e = cs_col & 3;
       float s = 0.f;
 #pragma unroll 4
-      for (int r = cs_rg; r < TC_BM; r += 4) s += *reinterpret_cast<const float*>(t0 + sw128_off(r, c) + e * 4);
+      for (int r = cs_rg; r < TC_BM; r += 4) s += *reinterpret_cast<const float*>(t0 + sw32b_off(r, c) + e * 4);
       cs += (double)s;
     }
     mbar_wait(&mma_bar, phase);
     phase ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     __syncthreads();                                     // every thread is done reading the raw tile
-    if (tile + gridDim.x < n_tiles) prefetch_tile(tile + gridDim.x);
   }
   ks = __shfl_sync(0xffffffffu, ks, 0);                  // warp 0: lane 0 counted while issuing
   // ---- per-CTA partials: D rows 0..63 live in TMEM lanes 0..63 (warps with quadrant 0 and 1)
@@ -255,7 +267,7 @@ extern "C" int bignn_dw_tc_f32(int32_t M, int32_t Np, int32_t Nq, const float* P
   const int grid = dw_grid(M);
   float* ws_dw = (float*)workspace;
   double* ws_cs = (double*)((uint8_t*)workspace + (((int64_t)grid * Np * Nq * sizeof(float) + 15) & ~(int64_t)15));
-  constexpr int smem = 4 * DW_TILE + 1024;
+  constexpr int smem = 6 * DW_TILE + 1024;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(k_dw_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
