@@ -112,204 +112,6 @@ k_spmm_v4(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col_i
   }
 }
 
-// ---- software-pipelined variant for short rows (NV = 1) -----------------------------------------
-// The plain loop serialises three dependent global-load latencies per row (row_ptr -> col_idx ->
-// neighbour rows).  Here the row pointers are fetched two rows ahead and the first four neighbour ids
-// one row ahead, so that per iteration only the neighbour-row gathers are on the critical path and
-// the index loads of the following rows are in flight underneath them.
-template <int L, int MODE>
-__global__ void __launch_bounds__(256)
-k_spmm_pipe_v4(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx,
-               const float* __restrict__ X, int64_t ldx, float* __restrict__ Y, int64_t ldy,
-               int n_rows, int D4, float self_coef, const float* __restrict__ dinv,
-               const float* __restrict__ bias, int act) {
-  constexpr int U = 4;
-  const int rpb = blockDim.x / L;
-  const int sub = threadIdx.x / L;
-  const int lane = threadIdx.x % L;
-  const int stride = gridDim.x * rpb;
-  int row = blockIdx.x * rpb + sub;
-  if (row >= n_rows) return;
-  const bool active = lane < D4;
-  // stage 0: pointers of `row`; stage 1: pointers of row + stride
-  int k0 = __ldg(row_ptr + row), k1 = __ldg(row_ptr + row + 1);
-  int nrow = row + stride;
-  int nk0 = 0, nk1 = 0;
-  if (nrow < n_rows) { nk0 = __ldg(row_ptr + nrow); nk1 = __ldg(row_ptr + nrow + 1); }
-  int c[U];
-#pragma unroll
-  for (int u = 0; u < U; ++u) c[u] = (k0 + u < k1) ? __ldg(col_idx + k0 + u) : -1;
-  while (true) {
-    // ---- issue this row's gathers (first U neighbours + self)
-    float di = 0.f;
-    if (MODE == BIGNN_SPMM_GCN) di = __ldg(dinv + row);
-    float4 val[U];
-    float w[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      int cu = c[u];
-      if (MODE != BIGNN_SPMM_SUM && cu == row) cu = -1;
-      c[u] = cu;
-      if (MODE == BIGNN_SPMM_GCN) w[u] = cu >= 0 ? __fmul_rn(__ldg(dinv + cu), di) : 0.f;
-      val[u] = (cu >= 0 && active) ? ldg4(X + (int64_t)cu * ldx + 4 * lane) : f4zero();
-    }
-    float4 self = f4zero();
-    if (MODE != BIGNN_SPMM_SUM && active) self = ldg4(X + (int64_t)row * ldx + 4 * lane);
-    // ---- prefetch: pointers two rows ahead, neighbour ids one row ahead
-    const int nnrow = nrow + stride;
-    int nnk0 = 0, nnk1 = 0;
-    if (nnrow < n_rows) { nnk0 = __ldg(row_ptr + nnrow); nnk1 = __ldg(row_ptr + nnrow + 1); }
-    int nc[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) nc[u] = (nrow < n_rows && nk0 + u < nk1) ? __ldg(col_idx + nk0 + u) : -1;
-    // ---- accumulate in ascending neighbour order
-    float4 acc[1];
-    acc[0] = f4zero();
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (c[u] >= 0) {
-        if (MODE == BIGNN_SPMM_GCN) acc_add_scaled(acc[0], w[u], val[u]);
-        else acc_add(acc[0], val[u]);
-      }
-    }
-    if (k0 + U < k1)       // rows with more than U neighbours: the rest through the generic loop
-      accumulate_range<L, 1, MODE>(acc, k0 + U, k1, row, lane, D4, di, col_idx, X, ldx, dinv);
-    if (active) {
-      float4 a = acc[0];
-      if (MODE == BIGNN_SPMM_GIN) {
-        a.x = __fadd_rn(__fmul_rn(self_coef, self.x), a.x); a.y = __fadd_rn(__fmul_rn(self_coef, self.y), a.y);
-        a.z = __fadd_rn(__fmul_rn(self_coef, self.z), a.z); a.w = __fadd_rn(__fmul_rn(self_coef, self.w), a.w);
-      } else if (MODE == BIGNN_SPMM_GCN) {
-        acc_add_scaled(a, __fmul_rn(di, di), self);
-      }
-      if (bias) {
-        const float4 b = ldg4(bias + 4 * lane);
-        a.x = __fadd_rn(a.x, b.x); a.y = __fadd_rn(a.y, b.y); a.z = __fadd_rn(a.z, b.z); a.w = __fadd_rn(a.w, b.w);
-      }
-      if (act != BIGNN_ACT_IDENTITY) {
-        a.x = apply_act(a.x, act); a.y = apply_act(a.y, act); a.z = apply_act(a.z, act); a.w = apply_act(a.w, act);
-      }
-      st4(Y + (int64_t)row * ldy + 4 * lane, a);
-    }
-    if (nrow >= n_rows) break;
-    row = nrow; k0 = nk0; k1 = nk1;
-    nrow = nnrow; nk0 = nnk0; nk1 = nnk1;
-#pragma unroll
-    for (int u = 0; u < U; ++u) c[u] = nc[u];
-  }
-}
-
-// ---- block-tiled variant for D = 64 on block-diagonal (molecule) graphs ------------------------------
-// Merged molecule graphs are block diagonal with ~30-atom blocks, so almost every neighbour of a row
-// lies within +-30 rows.  A CTA stages 128 consecutive feature rows (32 KB, cp.async, double
-// buffered) and the block's slice of row_ptr / col_idx in shared memory, and gathers from there;
-// only neighbours outside the staged window go to L2.  Every feature row then crosses the
-// L2->SM link once instead of ~3 times, which is what bounded the plain kernel (L2 at ~70 % of its
-// throughput cap with DRAM at 53 %).
-constexpr int TILE_R = 128;          // rows staged per block
-constexpr int TILE_ECAP = 1024;      // staged col_idx entries per block (rows beyond fall back to global)
-
-__device__ __forceinline__ void cp_async16_sp(void* sdst, const void* gsrc, unsigned src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)),
-               "l"(gsrc), "r"(src_bytes)
-               : "memory");
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(256)
-k_spmm_tile64(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx,
-              const float* __restrict__ X, int64_t ldx, float* __restrict__ Y, int64_t ldy,
-              int n_rows, float self_coef, const float* __restrict__ dinv,
-              const float* __restrict__ bias, int act) {
-  constexpr int L = 16, U = 4;
-  extern __shared__ __align__(16) unsigned char tile_smem[];
-  float4* xs = reinterpret_cast<float4*>(tile_smem);                       // [2][TILE_R * 16]
-  int* rp_s = reinterpret_cast<int*>(tile_smem + 2 * TILE_R * 16 * sizeof(float4));   // [TILE_R + 1]
-  int* ci_s = rp_s + TILE_R + 8;                                           // [TILE_ECAP]
-  const int tid = threadIdx.x;
-  const int sub = tid / L, lane = tid % L;
-  const int nblk = (n_rows + TILE_R - 1) / TILE_R;
-  auto stage_rows = [&](int blk, int buf) {
-    const int base = blk * TILE_R;
-#pragma unroll
-    for (int i = 0; i < TILE_R * 16 / 256; ++i) {
-      const int j = tid + i * 256;
-      const int row = base + (j >> 4);
-      const bool ok = row < n_rows;
-      cp_async16_sp(xs + buf * TILE_R * 16 + j, ok ? X + (int64_t)row * ldx + 4 * (j & 15) : X, ok ? 16u : 0u);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-  int blk = blockIdx.x, buf = 0;
-  if (blk < nblk) stage_rows(blk, 0);
-  for (; blk < nblk; blk += gridDim.x, buf ^= 1) {
-    const int base = blk * TILE_R;
-    const int rows_here = min(TILE_R, n_rows - base);
-    const int nb = blk + gridDim.x;
-    if (nb < nblk) stage_rows(nb, buf ^ 1);
-    // ---- this block's CSR slice -> shared memory
-    if (tid <= rows_here) rp_s[tid] = __ldg(row_ptr + base + tid);
-    __syncthreads();
-    const int kb = rp_s[0], ke = rp_s[rows_here];
-    const int staged = min(ke - kb, TILE_ECAP);
-    for (int j = tid; j < staged; j += 256) ci_s[j] = __ldg(col_idx + kb + j);
-    if (nb < nblk) asm volatile("cp.async.wait_group 1;" ::: "memory");
-    else asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-    const float4* xb = xs + buf * TILE_R * 16;
-    for (int rr = sub; rr < rows_here; rr += 256 / L) {
-      const int row = base + rr;
-      const int k0 = rp_s[rr], k1 = rp_s[rr + 1];
-      float4 acc = f4zero();
-      float di = 0.f;
-      if (MODE == BIGNN_SPMM_GCN) di = __ldg(dinv + row);
-      for (int k = k0; k < k1; k += U) {
-        int c[U];
-        float w[U];
-        float4 val[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int kk = k + u;
-          int cu = -1;
-          if (kk < k1) cu = (kk - kb < staged) ? ci_s[kk - kb] : __ldg(col_idx + kk);
-          if (MODE != BIGNN_SPMM_SUM && cu == row) cu = -1;
-          c[u] = cu;
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (MODE == BIGNN_SPMM_GCN) w[u] = c[u] >= 0 ? __fmul_rn(__ldg(dinv + c[u]), di) : 0.f;
-          const unsigned loc = (unsigned)(c[u] - base);
-          val[u] = c[u] < 0 ? f4zero() : (loc < (unsigned)TILE_R ? xb[loc * 16 + lane] : ldg4(X + (int64_t)c[u] * ldx + 4 * lane));
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (c[u] >= 0) {
-            if (MODE == BIGNN_SPMM_GCN) acc_add_scaled(acc, w[u], val[u]);
-            else acc_add(acc, val[u]);
-          }
-        }
-      }
-      float4 a = acc;
-      if (MODE == BIGNN_SPMM_GIN) {
-        const float4 s = xb[rr * 16 + lane];
-        a.x = __fadd_rn(__fmul_rn(self_coef, s.x), a.x); a.y = __fadd_rn(__fmul_rn(self_coef, s.y), a.y);
-        a.z = __fadd_rn(__fmul_rn(self_coef, s.z), a.z); a.w = __fadd_rn(__fmul_rn(self_coef, s.w), a.w);
-      } else if (MODE == BIGNN_SPMM_GCN) {
-        acc_add_scaled(a, __fmul_rn(di, di), xb[rr * 16 + lane]);
-      }
-      if (bias) {
-        const float4 b = ldg4(bias + 4 * lane);
-        a.x = __fadd_rn(a.x, b.x); a.y = __fadd_rn(a.y, b.y); a.z = __fadd_rn(a.z, b.z); a.w = __fadd_rn(a.w, b.w);
-      }
-      if (act != BIGNN_ACT_IDENTITY) {
-        a.x = apply_act(a.x, act); a.y = apply_act(a.y, act); a.z = apply_act(a.z, act); a.w = apply_act(a.w, act);
-      }
-      st4(Y + (int64_t)row * ldy + 4 * lane, a);
-    }
-    __syncthreads();      // the staged window and CSR slice are overwritten next iteration
-  }
-}
-
 // ---- long-row variant: work items of at most `seg` neighbours --------------------------------
 // item i covers neighbours [row_ptr[r] + c*seg, ...) of row r = item_row[i], c = i - item_ptr[r].
 // Rows with one item are finished in place; rows with several items leave per-item partial sums in
@@ -475,34 +277,13 @@ static int launch_mode(const int32_t* row_ptr, const int32_t* col_idx, const flo
     k_spmm_v4<L, NV, MODE><<<grid, 256, 0, st>>>(row_ptr, col_idx, Xb, ldx, Yb, ldy, n_rows, d4, \
                                                  self_coef, dinv, bb, act);                   \
   }
-#define BIGNN_SPMM_PIPE(L)                                                                    \
-  {                                                                                           \
-    int rpb = 256 / L;                                                                        \
-    int grid = ceil_div(n_rows, rpb);                                                         \
-    if (grid > cap) grid = cap;                                                               \
-    k_spmm_pipe_v4<L, MODE><<<grid, 256, 0, st>>>(row_ptr, col_idx, Xb, ldx, Yb, ldy, n_rows, d4, \
-                                                  self_coef, dinv, bb, act);                  \
-  }
-      if (d4 == 16 && n_rows >= 4 * TILE_R && (ldx & 3) == 0) {
-        constexpr int smem = 2 * TILE_R * 16 * 16 + (TILE_R + 8 + TILE_ECAP) * 4;
-        static bool configured = false;
-        if (!configured) {
-          cudaFuncSetAttribute(k_spmm_tile64<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-          configured = true;
-        }
-        int grid = ceil_div(n_rows, TILE_R);
-        const int cap3 = sm_count() * 3;
-        if (grid > cap3) grid = cap3;
-        k_spmm_tile64<MODE><<<grid, 256, smem, st>>>(row_ptr, col_idx, Xb, ldx, Yb, ldy, n_rows, self_coef, dinv, bb, act);
-      }
-      else if (d4 <= 8) BIGNN_SPMM_PIPE(8)
-      else if (d4 <= 16) BIGNN_SPMM_PIPE(16)
-      else if (d4 <= 32) BIGNN_SPMM_PIPE(32)
+      if (d4 <= 8) BIGNN_SPMM_LAUNCH(8, 1)
+      else if (d4 <= 16) BIGNN_SPMM_LAUNCH(16, 1)
+      else if (d4 <= 32) BIGNN_SPMM_LAUNCH(32, 1)
       else if (d4 <= 64) BIGNN_SPMM_LAUNCH(32, 2)
       else if (d4 <= 96) BIGNN_SPMM_LAUNCH(32, 3)
       else BIGNN_SPMM_LAUNCH(32, 4)
 #undef BIGNN_SPMM_LAUNCH
-#undef BIGNN_SPMM_PIPE
       BIGNN_LAUNCH_COUNT(1);
     }
   } else {
