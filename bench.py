@@ -42,8 +42,10 @@ def parse():
 def workload_config(name):
     from bignn_b200 import synthetic as S
     w = S.WORKLOADS[name]
-    return dict(workload='Bi-GNN (GIN x5 lower, multi-scale mean readout, GCN x3 upper, MLP scorer, BCE, Adam) '
-                         'on a synthetic dataset of {} shape'.format(name),
+    arch = ('GIN x5 lower, multi-scale mean readout, MetaLayer x3 upper (one GAT per interaction edge type, summed), '
+            'MLP scorer 128-16-3, CE, Adam') if 'drugcombo' in name else \
+        'GIN x5 lower, multi-scale mean readout, GCN x3 upper, MLP scorer, BCE, Adam'
+    return dict(workload='Bi-GNN ({}) on a synthetic dataset of {} shape'.format(arch, name),
                 name=name, drugs=w['N'], ddi_edges=w['M'], mean_atoms=w['mean_atoms'],
                 node_feat=int(sum(w['groups'])), pos_pairs_per_step=64, neg_pairs_per_step=64,
                 lower_chunk_graphs=128)
@@ -54,9 +56,17 @@ def make_workload(name, seed):
     return S.bignn_workload(seed=seed, **S.WORKLOADS[name])
 
 
-def layer_specs():
+def workload_flags(name, device='cuda:0'):
+    """drugcombo_shape runs the DrugCombo architecture the reference ships for that dataset
+    (src/config.py:74-88,120-123,224): one GAT per interaction edge type through MetaLayer, 3-class CE."""
     import bignn_b200 as B
-    f = B.make_flags()
+    if 'drugcombo' in name:
+        return B.make_flags(dataset='drugcombo', higher_level_gnn_type='gat', device=device)
+    return B.make_flags(device=device)
+
+
+def layer_specs(name):
+    f = workload_flags(name)
     return [getattr(f, 'layer_%d' % i) for i in range(1, f.layer_num + 1)]
 
 
@@ -70,8 +80,9 @@ def run_reference(args, sample_steps=None, quiet=False):
     torch.set_num_threads(cores)
     w = make_workload(args.workload, args.seed)
     ds = O.PackedDataset(w)
-    specs = O.parse_specs(layer_specs())
-    state = O.init_params(specs, ds.num_node_feat, seed=8)
+    specs = O.parse_specs(layer_specs(args.workload))
+    state = O.init_params(specs, ds.num_node_feat, num_labels=int(w['num_labels']), seed=8,
+                          num_edge_types=len(ds.etypes) + 1)
     tr = O.OracleTrainer(ds, specs, state, 64)
     np.random.seed(8)
     torch.manual_seed(8)
@@ -182,10 +193,9 @@ def run_ours(args):
     if os.path.exists(pk):
         peaks = json.load(open(pk))
 
-    B.set_flags(B.make_flags(device=dev))
+    B.set_flags(workload_flags(args.workload, dev))
     w = make_workload(args.workload, args.seed)
-    data = B.BiGNNData(w['gids'], w['atom_ptr'], w['nbr_ptr'], w['nbr_idx'], w['x_u8'].astype(np.float32),
-                       w['ddi_row'], w['ddi_col'], w['train_pairs'], w['pair_keys'], w['pair_labels'], 2, dev)
+    data = B.BiGNNData.from_npz(w, device=dev)
     torch.manual_seed(8)
     np.random.seed(8)            # every rank stages the same pair batches (the upper level is replicated)
     model = B.Model(data).to(dev)

@@ -62,6 +62,7 @@ SIGNATURES = {
     'bignn_gat_bwd_workspace_bytes': ('l', 'ii'),
     'bignn_gat_bwd': ('i', 'ppii' 'pl' 'pp' 'fi' 'pl' 'pl' 'p' 'pl' 'p' 'pl' 's'),
     'bignn_act_fwd_f32': ('i', 'pplis'),
+    'bignn_add_f32': ('i', 'pppls'),
     'bignn_prelu_fwd_f32': ('i', 'pplipis'),
     'bignn_prelu_bwd_f32': ('i', 'pppplipis'),
     'bignn_rownorm_fwd_f32': ('i', 'plpliips'),

@@ -17,7 +17,13 @@ _FLAGS = None
 def make_flags(model='lower_level_gnn_higher_level', lower_level_gnn_type='gin', higher_level_gnn_type='gcn',
                lower_level_num_layers=5, higher_level_num_layers=3, D_lower=64, D_higher=64,
                node_aggr='multi_scale', style='avg_pool', bn=True, gnn_normalize=False,
-               multi_class_pred=False, batch_size=64, device='cuda:0', dataset='drugbank', **extra):
+               multi_class_pred=None, batch_size=64, device='cuda:0', dataset='drugbank', **extra):
+    # DrugCombo defaults (src/config.py:74-88,120-123,224): one GNN per interaction edge type through
+    # MetaLayer, 3-class prediction with cross entropy
+    combo = 'drugcombo' in dataset
+    if multi_class_pred is None:
+        multi_class_pred = combo
+    node_model = extra.pop('node_model', '{}_multi_edge_aggr'.format(higher_level_gnn_type) if combo else None)
     lower = 'lower_level' in model
     higher = 'higher_level' in model
     specs = []
@@ -46,13 +52,24 @@ def make_flags(model='lower_level_gnn_higher_level', lower_level_gnn_type='gin',
         specs.append('LoadInteractionLayer')
         g = higher_level_gnn_type
         n_h = higher_level_num_layers
-        if lower:
+        if combo:
+            if lower:
+                specs.append('MetaLayer:input_dim={},output_dim={},act=relu,higher_level={},edge_model={},'
+                             'node_model={}'.format(d_lower, D_higher, True, 'none', node_model))
+            else:
+                specs.append('MetaLayer:output_dim={},act=relu,higher_level={},edge_model={},node_model={}'.format(
+                    D_higher, True, 'none', node_model))
+            for i in range(n_h - 1):
+                act = 'identity' if i == n_h - 2 else 'relu'
+                specs.append('MetaLayer:input_dim={},output_dim={},act={},higher_level={},edge_model={},'
+                             'node_model={}'.format(D_higher, D_higher, act, True, 'none', node_model))
+        elif lower:
             specs.append('NodeEmbedding:type={},input_dim={},output_dim={},act=relu,bn={},higher_level={},'
                          'normalize={}'.format(g, d_lower, D_higher, bn, True, gnn_normalize))
         else:
             specs.append('NodeEmbedding:type={},output_dim={},act=relu,bn={},higher_level={},normalize={}'.format(
                 g, D_higher, bn, True, gnn_normalize))
-        for i in range(n_h - 1):
+        for i in range(n_h - 1 if not combo else 0):
             act = 'identity' if i == n_h - 2 else 'relu'
             specs.append('NodeEmbedding:type={},input_dim={},output_dim={},act={},bn={},higher_level={},'
                          'normalize={}'.format(g, D_higher, D_higher, act, bn, True, gnn_normalize))
@@ -80,7 +97,7 @@ def make_flags(model='lower_level_gnn_higher_level', lower_level_gnn_type='gin',
     f.enforce_negative_sampling = True
     f.enforce_sampling_amongst_same_graphs = True
     f.sample_induced = False
-    f.different_edge_type_aggr = False
+    f.different_edge_type_aggr = combo
     f.use_hyper_edge_attrs = False
     f.multi_class_pred = multi_class_pred
     f.d_init = 64

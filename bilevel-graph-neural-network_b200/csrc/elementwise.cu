@@ -13,6 +13,12 @@ k_act_fwd(const float* __restrict__ X, float* __restrict__ Y, int64_t n, int act
     Y[i] = apply_act(X[i], act);
 }
 
+__global__ void __launch_bounds__(256)
+k_add(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ O, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    O[i] = A[i] + B[i];
+}
+
 // PReLU: y = x > 0 ? x : w[c] * x   (nw == 1: one shared slope, else one per column)
 __global__ void __launch_bounds__(256)
 k_prelu_fwd(const float* __restrict__ X, float* __restrict__ Y, int64_t n, int C, const float* __restrict__ w, int nw) {
@@ -169,6 +175,15 @@ extern "C" int bignn_act_fwd_f32(const float* X, float* Y, int64_t n, int32_t ac
   if (n == 0) return 0;
   if (!X || !Y) return BIGNN_EINVAL;
   k_act_fwd<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(X, Y, n, act);
+  BIGNN_LAUNCH_COUNT(1);
+  return last_launch_status();
+}
+
+extern "C" int bignn_add_f32(const float* A, const float* B, float* O, int64_t n, void* stream) {
+  if (n < 0) return BIGNN_EINVAL;
+  if (n == 0) return 0;
+  if (!A || !B || !O) return BIGNN_EINVAL;
+  k_add<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(A, B, O, n);
   BIGNN_LAUNCH_COUNT(1);
   return last_launch_status();
 }

@@ -9,7 +9,7 @@ from .graph import PackedGraphs, InteractionGraph
 
 class BiGNNData(object):
     def __init__(self, gids, atom_ptr, nbr_ptr, nbr_idx, x, ddi_row, ddi_col, train_pairs,
-                 pair_keys=None, pair_labels=None, num_labels=2, device='cuda:0'):
+                 pair_keys=None, pair_labels=None, num_labels=2, device='cuda:0', edge_types=None):
         self.device = torch.device(device)
         self.packed = PackedGraphs(gids, atom_ptr, nbr_ptr, nbr_idx, x, self.device)
         self.gs_map = self.packed.gs_map
@@ -20,6 +20,13 @@ class BiGNNData(object):
         self.interaction_num_node_feat = None
         self.num_hyper_edge_feat = 0
         self.interaction_combo_nxgraph = InteractionGraph(self.N, ddi_row, ddi_col, self.device)
+        # per-edge-type interaction graphs (utils/data/dataset.py:105-115), DrugCombo: synergy / antagonism
+        self.interaction_nxgraphs = {}
+        if edge_types:
+            for name in sorted(edge_types):
+                r, c = edge_types[name]
+                self.interaction_nxgraphs[name] = InteractionGraph(self.N, r, c, self.device)
+            self.num_hyper_edge_feat = len(edge_types) + 1        # + the 'none' type of the added self loops
         # sorted (N*row+col) keys of the train graph for O(log E) membership tests
         self._edge_keys = np.sort(np.asarray(self.interaction_combo_nxgraph.row_host, np.int64) * self.N +
                                   np.asarray(self.interaction_combo_nxgraph.col_host, np.int64))
@@ -38,12 +45,17 @@ class BiGNNData(object):
     @classmethod
     def from_npz(cls, path_or_npz, device='cuda:0'):
         z = np.load(path_or_npz) if isinstance(path_or_npz, str) else path_or_npz
-        x = z['x_u8'] if 'x_u8' in z else z['x']
+        files = z.files if hasattr(z, 'files') else list(z.keys())
+        x = z['x_u8'] if 'x_u8' in files else z['x']
+        et = None
+        names = [k[len('etype_row/'):] for k in files if k.startswith('etype_row/')]
+        if names:
+            et = {n: (z['etype_row/' + n], z['etype_col/' + n]) for n in names}
         return cls(z['gids'], z['atom_ptr'], z['nbr_ptr'], z['nbr_idx'], np.asarray(x, np.float32),
                    z['ddi_row'], z['ddi_col'], z['train_pairs'],
-                   z['pair_keys'] if 'pair_keys' in z else None,
-                   z['pair_labels'] if 'pair_labels' in z else None,
-                   int(z['num_labels']) if 'num_labels' in z else 2, device)
+                   z['pair_keys'] if 'pair_keys' in files else None,
+                   z['pair_labels'] if 'pair_labels' in files else None,
+                   int(z['num_labels']) if 'num_labels' in files else 2, device, et)
 
     def __len__(self):
         return self.train_pairs.shape[0]

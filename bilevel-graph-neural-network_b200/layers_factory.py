@@ -7,6 +7,7 @@ from .layers import NodeEmbedding, Loss
 from .layers_aggregation import NodeAggregation, NodeAggregationPairs
 from .layers_link_pred import LinkPred
 from .layers_load_interaction_graph import LoadInteractionGraph
+from .layers_meta import MetaLayerWrapper
 
 
 def create_layers(model, pattern, num_layers):
@@ -59,6 +60,14 @@ def create_node_embedding_layer(lf, model, layer_id, layers, *unused):
     return NodeEmbedding(type=lf['type'], in_dim=input_dim, out_dim=int(lf['output_dim']), act=lf['act'],
                          bn=_parse_as_bool(lf['bn']), normalize=_parse_as_bool(lf['normalize']),
                          higher_level=higher_level)
+
+
+def create_meta_wrapper_layer(lf, model, layer_id, layers, *unused):
+    _check_spec([5, 6], lf, 'MetaLayerWrapper')
+    input_dim, higher_level = get_input_dim_higher_level(lf, MetaLayerWrapper, layers, layer_id, model)
+    return MetaLayerWrapper(input_dim=input_dim, edge_dim=model.num_hyper_edge_feat, output_dim=int(lf['output_dim']),
+                            edge_model=lf['edge_model'], node_model=lf['node_model'], higher_level=higher_level,
+                            num_edge_types=model.num_hyper_edge_feat, act=lf['act'])
 
 
 def create_load_interaction_graph_layer(lf, *unused):
@@ -117,6 +126,6 @@ layer_ctors = {
     'GMNPropagator': _later('GMNPropagator'),
     'GMNAggregatorPairs': _later('GMNAggregatorPairs'),
     'LinkPredictor': create_link_pred_layer,
-    'MetaLayer': _later('MetaLayer'),
+    'MetaLayer': create_meta_wrapper_layer,
     'LoadInteractionLayer': create_load_interaction_graph_layer,
 }

@@ -531,6 +531,24 @@ class _CE(torch.autograd.Function):
         return d, None
 
 
+class _Add(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = _f32c(a), _f32c(b)
+        _lib.require_device(a, b)
+        o = torch.empty_like(a)
+        _lib.call('bignn_add_f32', a, b, o, a.numel())
+        return o
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
+
+
+def add(a, b):
+    return _Add.apply(a, b)
+
+
 def gat_conv(h, att, bias, csr, negative_slope=0.2, group='source'):
     if group not in ('source', 'target'):
         raise ValueError('GAT softmax group must be source or target')

@@ -76,16 +76,32 @@ def interaction_graph(N, M, seed=0, skew=0.8):
     return pairs, key // N, key % N
 
 
-def bignn_workload(N, M, mean_atoms=28.0, seed=0, groups=FEATURE_GROUPS, max_atoms=457):
-    """A full Bi-GNN dataset dict (keys as tests/golden/drugbank_packed.npz)."""
+def bignn_workload(N, M, mean_atoms=28.0, seed=0, groups=FEATURE_GROUPS, max_atoms=457, edge_type_fracs=None):
+    """A full Bi-GNN dataset dict (keys as tests/golden/drugbank_packed.npz).  With
+    `edge_type_fracs` (e.g. {'synergy': 0.68, 'antagonism': 0.32}) every interaction gets one
+    edge type: pair labels become 1..T (0 = sampled negative) and per-type directed COOs are added
+    as `etype_row/<name>`, `etype_col/<name>` (the DrugCombo layout, utils/data/dataset.py:82-115)."""
     atom_ptr, nbr_ptr, nbr_idx, x = molecule_graphs(N, mean_atoms, seed, groups=groups, max_atoms=max_atoms)
     pairs, row, col = interaction_graph(N, M, seed)
     gids = np.arange(N, dtype=np.int64) + 1000          # gids are labels, not row numbers
     train_pairs = gids[pairs]
-    return dict(gids=gids, atom_ptr=atom_ptr, nbr_ptr=nbr_ptr, nbr_idx=nbr_idx, x_u8=x,
-                ddi_row=row.astype(np.int32), ddi_col=col.astype(np.int32), train_pairs=train_pairs,
-                pair_keys=train_pairs, pair_labels=np.ones(train_pairs.shape[0], np.int8),
-                num_labels=np.int64(2))
+    out = dict(gids=gids, atom_ptr=atom_ptr, nbr_ptr=nbr_ptr, nbr_idx=nbr_idx, x_u8=x,
+               ddi_row=row.astype(np.int32), ddi_col=col.astype(np.int32), train_pairs=train_pairs,
+               pair_keys=train_pairs, pair_labels=np.ones(train_pairs.shape[0], np.int8),
+               num_labels=np.int64(2))
+    if edge_type_fracs:
+        rng = np.random.default_rng(seed + 77)
+        names = sorted(edge_type_fracs)
+        p = np.asarray([edge_type_fracs[n] for n in names], np.float64)
+        t = rng.choice(len(names), size=pairs.shape[0], p=p / p.sum())
+        out['pair_labels'] = (t + 1).astype(np.int8)
+        out['num_labels'] = np.int64(len(names))
+        for i, n in enumerate(names):
+            pr = pairs[t == i]
+            key = np.unique(np.concatenate([pr[:, 0] * N + pr[:, 1], pr[:, 1] * N + pr[:, 0]]))
+            out['etype_row/' + n] = (key // N).astype(np.int32)
+            out['etype_col/' + n] = (key % N).astype(np.int32)
+    return out
 
 
 WORKLOADS = {
@@ -93,5 +109,6 @@ WORKLOADS = {
     'drugbank_shape': dict(N=1309, M=28751, mean_atoms=28.1, groups=FEATURE_GROUPS),
     # DrugCombo (App. D): 3 242 drugs in the interaction graphs, 29.3 atoms, synergy 34 355 +
     # antagonism 15 908 undirected edges, one-hot width <= 40
-    'drugcombo_shape': dict(N=3242, M=50263, mean_atoms=29.3, groups=(22, 2, 2, 2, 6, 6)),
+    'drugcombo_shape': dict(N=3242, M=50263, mean_atoms=29.3, groups=(22, 2, 2, 2, 6, 6),
+                            edge_type_fracs={'synergy': 34355.0, 'antagonism': 15908.0}),
 }

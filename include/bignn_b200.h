@@ -267,6 +267,8 @@ int bignn_gat_bwd(const int32_t* row_ptr, const int32_t* col_idx, int32_t n, int
  *   ce_fwd/bwd         nn.CrossEntropyLoss, mean (model/layers.py:75,85-88); labels int32
  * ------------------------------------------------------------------------- */
 int bignn_act_fwd_f32(const float* X, float* Y, int64_t n, int32_t act, void* stream);
+/* O = A + B: the sum over edge types of NodeModelAggrByEdge (model/layers_meta.py:74-79) */
+int bignn_add_f32(const float* A, const float* B, float* O, int64_t n, void* stream);
 int bignn_prelu_fwd_f32(const float* X, float* Y, int64_t rows, int32_t C, const float* w, int32_t nw,
                         void* stream);
 int bignn_prelu_bwd_f32(const float* X, const float* dY, float* dX, float* T, int64_t rows, int32_t C,

@@ -67,6 +67,9 @@ class PackedDataset(object):
                 self.pairs[(a, b)] = int(l)
         self.num_node_feat = self.x.shape[1]
         self.N = len(self.gids)
+        keys = d.files if hasattr(d, 'files') else d.keys()
+        self.etypes = {k[len('etype_row/'):]: (np.asarray(d[k], np.int64), np.asarray(d['etype_col/' + k[len('etype_row/'):]], np.int64))
+                       for k in sorted(keys) if k.startswith('etype_row/')}
 
     @classmethod
     def load(cls, path):
@@ -238,7 +241,7 @@ def calc_mlp_dims(dim, out_dim=1, division=2):
 
 
 def init_params(specs, num_node_feat, num_labels=2, interaction_num_node_feat=None,
-                seed=0, dtype=torch.float32):
+                seed=0, dtype=torch.float32, num_edge_types=3):
     """Default-initialised parameters/buffers with the reference's state_dict
     names and shapes; init distributions as in App. A."""
     g = torch.Generator().manual_seed(seed)
@@ -288,6 +291,21 @@ def init_params(specs, num_node_feat, num_labels=2, interaction_num_node_feat=No
                 sd[p + '.bn.running_mean'] = torch.zeros(fout, dtype=dtype)
                 sd[p + '.bn.running_var'] = torch.ones(fout, dtype=dtype)
                 sd[p + '.bn.num_batches_tracked'] = torch.zeros((), dtype=torch.int64)
+        elif name == 'MetaLayer':
+            # model/layers_meta.py:61-79: one GCNConv / GATConv per edge type except 'none'
+            higher = True
+            if 'input_dim' in lf:
+                fin = int(lf['input_dim'])
+            else:
+                fin = interaction_num_node_feat
+            fout = int(lf['output_dim'])
+            kind = lf['node_model'].split('_')[0]
+            for e in range(num_edge_types - 1):
+                q = p + '.node_model.GNNS.%d' % e
+                sd[q + '.weight'] = uni((fin, fout), math.sqrt(6.0 / (fin + fout)))
+                if kind == 'gat':
+                    sd[q + '.att'] = uni((1, 1, 2 * fout), math.sqrt(6.0 / (1 + 2 * fout)))
+                sd[q + '.bias'] = torch.zeros(fout, dtype=dtype)
         elif name == 'LinkPredictor' and lf['type'] == 'mlp_concat':
             d = int(lf['mlp_dim']) * 2
             multi = _b(lf['multi_label_pred']) if lf.get('multi_label_pred') else False
@@ -505,7 +523,17 @@ class OracleModel(object):
         pooled = readout(acts if multi else [h], batch, G, lf['style'])
         return acts, pooled
 
-    def upper(self, init_x, ddi_ei, pair_rows, y, num_labels=2):
+    def meta_layer(self, h, etype_eis, p, lf):
+        """MetaLayerWrapper + NodeModelAggrByEdge (model/layers_meta.py:39-47,74-79)."""
+        kind = lf['node_model'].split('_')[0]
+        outs = torch.zeros(h.shape[0], int(lf['output_dim']), dtype=h.dtype)
+        for e, ei in enumerate(etype_eis):
+            q = p + '.node_model.GNNS.%d' % e
+            view = {q + '.conv.' + k: self.P[q + '.' + k] for k in ('weight', 'bias', 'att') if (q + '.' + k) in self.P}
+            outs = outs + (gcn_conv(h, ei, view, q) if kind == 'gcn' else gat_conv(h, ei, view, q, self.gat_group))
+        return _act(lf['act'], outs)
+
+    def upper(self, init_x, ddi_ei, pair_rows, y, num_labels=2, etype_eis=None):
         h = init_x
         acts = []
         start = self.i_load + 1 if self.i_load is not None else 0
@@ -515,6 +543,8 @@ class OracleModel(object):
             p = 'layers.%d' % i
             if name == 'NodeEmbedding':
                 h = node_embedding(h, ddi_ei, self.P, p, lf, self.training, self.gat_group)
+            elif name == 'MetaLayer':
+                h = self.meta_layer(h, etype_eis, p, lf)
             elif name == 'LinkPredictor':
                 h = pred = link_pred(h, pair_rows, self.P, p, lf, num_labels)
             elif name == 'Loss':
@@ -549,7 +579,8 @@ def train_step_forward(model, ds, batch_gids, y, batch_size=64, record=None):
     init_x = all_drug_pass(model, ds, batch_size, record)
     ddi = torch.from_numpy(np.stack([ds.ddi_row, ds.ddi_col]))
     rows = torch.from_numpy(np.vectorize(ds.gs_map.get)(np.asarray(batch_gids)).astype(np.int64))
-    acts, pred, loss = model.upper(init_x, ddi, rows, torch.from_numpy(np.asarray(y)))
+    et = [torch.from_numpy(np.stack([r, c])) for r, c in ds.etypes.values()] if ds.etypes else None
+    acts, pred, loss = model.upper(init_x, ddi, rows, torch.from_numpy(np.asarray(y)), etype_eis=et)
     return init_x, acts, pred, loss
 
 

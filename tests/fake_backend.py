@@ -233,6 +233,27 @@ class Fake(object):
         dRows.copy_((dz - zh * (dz * zh).sum(1, keepdim=True)) / n)
         return 0
 
+    def bignn_add_f32(self, A, B, O, n):
+        O.copy_(A + B)
+        return 0
+
+    def bignn_act_fwd_f32(self, X, Y, n, act):
+        Y.copy_(ACTS[act](X))
+        return 0
+
+    def bignn_gat_fwd(self, *a):
+        raise NotImplementedError('GAT is exercised by the gpu tests')
+
+    def bignn_ce_fwd(self, logits, ldx, labels, P, K, loss):
+        loss.copy_(torch.nn.functional.cross_entropy(logits, labels.long()))
+        return 0
+
+    def bignn_ce_bwd(self, logits, ldx, labels, P, K, dloss, dlogits, lddx):
+        sm = torch.softmax(logits, 1)
+        sm[torch.arange(P), labels.long()] -= 1
+        dlogits.copy_(sm * dloss / P)
+        return 0
+
     def bignn_bce_fwd(self, pred, y, P, loss):
         loss.copy_(torch.nn.functional.binary_cross_entropy(pred, y))
         return 0

@@ -218,3 +218,61 @@ def test_prelu_rownorm_gate_vs_torch():
     od = ops.gate_mul(ad, bd)
     od.backward(dy[:500].to(DEV))
     assert rel(od, o) < 1e-6 and rel(ad.grad, a.grad) < 2e-6 and rel(bd.grad, b.grad) < 2e-6
+
+
+def test_drugcombo_architecture_step_vs_oracle():
+    """Bi-GNN with the DrugCombo upper level (MetaLayer: one GAT per interaction edge type, summed;
+    3-class scorer; cross entropy) on a small synthetic dataset: engine step vs the CPU oracle.
+    (No reference-generated golden exists for this layer: the DrugCombo csv blob is missing from the
+    reference tree, so this configuration is pinned to the oracle only.)"""
+    from bignn_b200 import synthetic as S
+    from bignn_b200.engine import BiGNNEngine
+    w = S.bignn_workload(N=420, M=3000, mean_atoms=20.0, seed=5, groups=(22, 2, 2, 2, 6, 6),
+                         edge_type_fracs={'synergy': 0.68, 'antagonism': 0.32})
+    flags = B.make_flags(dataset='drugcombo', higher_level_gnn_type='gat', device=DEV)
+    B.set_flags(flags)
+    try:
+        data = B.BiGNNData.from_npz(w, device=DEV)
+        assert data.num_hyper_edge_feat == 3 and len(data.interaction_nxgraphs) == 2
+        specs = O.parse_specs([getattr(flags, 'layer_%d' % i) for i in range(1, flags.layer_num + 1)])
+        ds = O.PackedDataset(w)
+        state = O.init_params(specs, ds.num_node_feat, num_labels=2, seed=3, num_edge_types=3)
+        model = B.Model(data).to(DEV)
+        missing, unexpected = model.load_state_dict(state, strict=False)
+        assert not unexpected, unexpected
+        assert all(not m.startswith('layers.') or '.meta_layer.' in m for m in missing), missing
+        model.train()
+        rng = np.random.default_rng(0)
+        pos = w['train_pairs'][rng.choice(len(w['train_pairs']), 64, replace=False)]
+        neg = np.stack([w['gids'][rng.integers(0, 420, 64)], w['gids'][rng.integers(0, 420, 64)]], 1)
+        gids = np.concatenate([pos, neg])
+        y = O.pair_labels(ds, gids)
+        assert set(np.unique(y)) <= {0, 1, 2} and (y > 0).sum() >= 64
+        eng = BiGNNEngine(data, model, use_cuda_graph=False)
+        st, P = eng.stage_pairs(gids, y.astype(np.float32))
+        from bignn_b200.engine import _StaticPairBatch
+        sb = _StaticPairBatch(data, P, data.device)
+        sb.ids.copy_(st.ids); sb.y.copy_(st.y); sb.e_ptr.copy_(st.e_ptr); sb.e_idx.copy_(st.e_idx)
+        loss = eng.forward(sb)
+        loss.backward()
+        res = {}
+        for dt in (torch.float32, torch.float64):
+            om = O.OracleModel(specs, state, dtype=dt)
+            init_x, acts, pred, l = O.train_step_forward(om, ds, gids, y)
+            l.backward()
+            res[dt] = (float(l.detach()), init_x.detach(), pred.detach(), {k: v.grad for k, v in om.params().items()})
+        assert abs(float(loss) - res[torch.float32][0]) < 2e-5
+        assert rel(data.interaction_combo_nxgraph.init_x, res[torch.float32][1]) < 1e-5
+        assert rel(sb.preds, res[torch.float32][2]) < 5e-5
+        g64, g32 = res[torch.float64][3], res[torch.float32][3]
+        scale = {}
+        for k, g in g64.items():
+            scale[k.split('.')[1]] = max(scale.get(k.split('.')[1], 0.0), float(g.abs().max()))
+        named = dict(model.named_parameters())
+        for k in g64:
+            s = scale[k.split('.')[1]]
+            ours = float((named[k].grad.double().cpu() - g64[k]).abs().max()) / s
+            ref = float((g32[k].double() - g64[k]).abs().max()) / s
+            assert ours <= 6.0 * ref + 2e-5, (k, ours, ref)
+    finally:
+        B.set_flags(B.make_flags(device=DEV))
