@@ -12,7 +12,6 @@
 
 namespace bignn {
 
-constexpr int GAT_MAXS = 4;   // columns per lane -> D <= 128
 
 __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
 __device__ __forceinline__ float lrelu_grad(float v, float slope) { return v > 0.f ? 1.f : slope; }
@@ -57,68 +56,164 @@ __device__ __forceinline__ int edge_group(int r, int nb, int group_target) {
   return ROLE == 0 ? (group_target ? r : nb) : (group_target ? nb : r);
 }
 
-// m[g], z[g]: max and sum of exp(s - m) over the edges grouped at g (ROLE = group_target ? 0 : 1)
+// ---- work items -----------------------------------------------------------------------------------
+// Interaction graphs have hub drugs (DrugCombo synergy graph: max degree 1 401, p99 226), so every
+// neighbour pass runs over WORK ITEMS of at most `seg` neighbours (the same plan as
+// bignn_spmm_planned_f32): a 16-lane sub-warp owns one item, 128-bit loads for the 64-float rows.
+// Rows made of one item are finished in place (including their self-loop edge); rows made of several
+// items leave per-item partials that a second kernel combines in item order (deterministic).
+struct ItemPlan {
+  const int32_t* item_ptr;
+  const int32_t* item_row;
+  const int32_t* multi_rows;
+  int n_items, n_multi, seg;
+};
+
+__device__ __forceinline__ unsigned half_mask() { return (threadIdx.x & 16) ? 0xffff0000u : 0x0000ffffu; }
+__device__ __forceinline__ float half_sum(float v, unsigned mask) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+  return v;
+}
+__device__ __forceinline__ void softmax_merge(float& m, float& s, float om, float os) {
+  const float nm = fmaxf(m, om);
+  const float a = m == -INFINITY ? 0.f : s * expf(m - nm);
+  const float b = om == -INFINITY ? 0.f : os * expf(om - nm);
+  m = nm;
+  s = a + b;
+}
+
+// (max, sum exp) per grouping node.  ROLE = group_target ? 0 : 1
 template <int ROLE>
 __global__ void __launch_bounds__(256)
-k_gat_group_stats(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx, int n,
+k_gat_stats_items(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx, ItemPlan pl,
                   const float* __restrict__ p, const float* __restrict__ q, float slope,
-                  float* __restrict__ m, float* __restrict__ z) {
-  const int lane = threadIdx.x % 32, wpb = blockDim.x / 32;
-  for (int r = blockIdx.x * wpb + threadIdx.x / 32; r < n; r += gridDim.x * wpb) {
-    const int k0 = row_ptr[r], k1 = row_ptr[r + 1];
+                  float* __restrict__ m, float* __restrict__ z, float* __restrict__ part) {
+  const int lane = threadIdx.x & 15;
+  const unsigned mask = half_mask();
+  for (int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 4; item < pl.n_items; item += (gridDim.x * blockDim.x) >> 4) {
+    const int r = __ldg(pl.item_row + item);
+    const int i0 = __ldg(pl.item_ptr + r), i1 = __ldg(pl.item_ptr + r + 1);
+    const int k0 = __ldg(row_ptr + r) + (item - i0) * pl.seg;
+    const int k1 = min(k0 + pl.seg, __ldg(row_ptr + r + 1));
     float mx = -INFINITY, sm = 0.f;
-    for (int k = k0 + lane; k <= k1; k += 32) {           // k == k1 is the added self loop
-      const int nb = k < k1 ? __ldg(col_idx + k) : r;
-      if (k < k1 && nb == r) continue;                    // remove_self_loops
+    for (int k = k0 + lane; k < k1; k += 16) {
+      const int nb = __ldg(col_idx + k);
+      if (nb == r) continue;
       const float s = edge_score<ROLE>(p, q, r, nb, slope);
-      if (s > mx) { sm = sm * expf(mx - s) + 1.f; mx = s; }
-      else sm += expf(s - mx);
+      softmax_merge(mx, sm, s, 1.f);
     }
+    const bool single = (i1 - i0) == 1;
+    if (single && lane == 0) softmax_merge(mx, sm, edge_score<ROLE>(p, q, r, r, slope), 1.f);   // self loop
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float om = __shfl_xor_sync(0xffffffffu, mx, o);
-      const float os = __shfl_xor_sync(0xffffffffu, sm, o);
-      const float nm = fmaxf(mx, om);
-      const float a = mx == -INFINITY ? 0.f : sm * expf(mx - nm);
-      const float b = om == -INFINITY ? 0.f : os * expf(om - nm);
-      mx = nm;
-      sm = a + b;
+    for (int o = 8; o > 0; o >>= 1) {
+      const float om = __shfl_xor_sync(mask, mx, o), os = __shfl_xor_sync(mask, sm, o);
+      softmax_merge(mx, sm, om, os);
     }
-    if (lane == 0) { m[r] = mx; z[r] = sm; }
+    if (lane == 0) {
+      if (single) { m[r] = mx; z[r] = sm; }
+      else { part[2 * item] = mx; part[2 * item + 1] = sm; }
+    }
   }
 }
 
-// out[r] = sum_nb alpha(r,nb) V[nb] (+ bias).  ROLE 0 = forward aggregation at targets (V = h);
-// ROLE 1 = backward of it at sources (V = d out).
 template <int ROLE>
 __global__ void __launch_bounds__(256)
-k_gat_gather(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx, int n, int D,
-             const float* __restrict__ V, int64_t ldv, const float* __restrict__ p, const float* __restrict__ q,
-             const float* __restrict__ m, const float* __restrict__ z, float slope, int group_target,
-             const float* __restrict__ bias, float* __restrict__ out, int64_t ldo) {
-  const int lane = threadIdx.x % 32, wpb = blockDim.x / 32;
-  for (int r = blockIdx.x * wpb + threadIdx.x / 32; r < n; r += gridDim.x * wpb) {
-    const int k0 = row_ptr[r], k1 = row_ptr[r + 1];
-    float acc[GAT_MAXS];
+k_gat_stats_multi(ItemPlan pl, const float* __restrict__ p, const float* __restrict__ q, float slope,
+                  float* __restrict__ m, float* __restrict__ z, const float* __restrict__ part) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pl.n_multi) return;
+  const int r = pl.multi_rows[i];
+  float mx = -INFINITY, sm = 0.f;
+  for (int it = pl.item_ptr[r]; it < pl.item_ptr[r + 1]; ++it) softmax_merge(mx, sm, part[2 * it], part[2 * it + 1]);
+  softmax_merge(mx, sm, edge_score<ROLE>(p, q, r, r, slope), 1.f);
+  m[r] = mx;
+  z[r] = sm;
+}
+
+template <int ROLE>
+__device__ __forceinline__ float edge_alpha(const float* __restrict__ p, const float* __restrict__ q,
+                                            const float* __restrict__ m, const float* __restrict__ z, int r, int nb,
+                                            float slope, int group_target) {
+  const int g = edge_group<ROLE>(r, nb, group_target);
+  return expf(edge_score<ROLE>(p, q, r, nb, slope) - __ldg(m + g)) / (__ldg(z + g) + 1e-16f);
+}
+
+// out[r] = sum_nb alpha(r,nb) V[nb] (+ alpha(r,r) V[r] + bias).  ROLE 0 = forward aggregation at the
+// targets (V = h); ROLE 1 = its backward at the sources (V = d out).
+template <int ROLE>
+__global__ void __launch_bounds__(256)
+k_gat_gather_items(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx, ItemPlan pl, int D4,
+                   const float* __restrict__ V, int64_t ldv, const float* __restrict__ p, const float* __restrict__ q,
+                   const float* __restrict__ m, const float* __restrict__ z, float slope, int group_target,
+                   const float* __restrict__ bias, float* __restrict__ out, int64_t ldo, float* __restrict__ part) {
+  constexpr int U = 4;
+  const int lane = threadIdx.x & 15;
+  const bool active = lane < D4;
+  for (int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 4; item < pl.n_items; item += (gridDim.x * blockDim.x) >> 4) {
+    const int r = __ldg(pl.item_row + item);
+    const int i0 = __ldg(pl.item_ptr + r), i1 = __ldg(pl.item_ptr + r + 1);
+    const int k0 = __ldg(row_ptr + r) + (item - i0) * pl.seg;
+    const int k1 = min(k0 + pl.seg, __ldg(row_ptr + r + 1));
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = k0; k < k1; k += U) {
+      int c[U];
+      float w[U];
+      float4 val[U];
 #pragma unroll
-    for (int s = 0; s < GAT_MAXS; ++s) acc[s] = 0.f;
-    for (int k = k0; k <= k1; ++k) {
-      const int nb = k < k1 ? __ldg(col_idx + k) : r;
-      if (k < k1 && nb == r) continue;
-      const int g = edge_group<ROLE>(r, nb, group_target);
-      const float sc = edge_score<ROLE>(p, q, r, nb, slope);
-      const float alpha = expf(sc - __ldg(m + g)) / (__ldg(z + g) + 1e-16f);
-#pragma unroll
-      for (int s = 0; s < GAT_MAXS; ++s) {
-        const int c = lane + 32 * s;
-        if (c < D) acc[s] = __fadd_rn(acc[s], __fmul_rn(alpha, __ldg(V + (int64_t)nb * ldv + c)));
+      for (int u = 0; u < U; ++u) {
+        c[u] = (k + u < k1) ? __ldg(col_idx + k + u) : -1;
+        if (c[u] == r) c[u] = -1;
       }
-    }
 #pragma unroll
-    for (int s = 0; s < GAT_MAXS; ++s) {
-      const int c = lane + 32 * s;
-      if (c < D) out[(int64_t)r * ldo + c] = acc[s] + (bias ? __ldg(bias + c) : 0.f);
+      for (int u = 0; u < U; ++u) {
+        w[u] = c[u] >= 0 ? edge_alpha<ROLE>(p, q, m, z, r, c[u], slope, group_target) : 0.f;
+        val[u] = (c[u] >= 0 && active) ? ldg4(V + (int64_t)c[u] * ldv + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (c[u] >= 0) {
+          acc.x = __fadd_rn(acc.x, __fmul_rn(w[u], val[u].x)); acc.y = __fadd_rn(acc.y, __fmul_rn(w[u], val[u].y));
+          acc.z = __fadd_rn(acc.z, __fmul_rn(w[u], val[u].z)); acc.w = __fadd_rn(acc.w, __fmul_rn(w[u], val[u].w));
+        }
     }
+    if (!active) continue;
+    if (i1 - i0 == 1) {
+      const float ws = edge_alpha<ROLE>(p, q, m, z, r, r, slope, group_target);
+      const float4 sv = ldg4(V + (int64_t)r * ldv + 4 * lane);
+      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (bias) b = ldg4(bias + 4 * lane);
+      acc.x = __fadd_rn(acc.x, __fmul_rn(ws, sv.x)) + b.x; acc.y = __fadd_rn(acc.y, __fmul_rn(ws, sv.y)) + b.y;
+      acc.z = __fadd_rn(acc.z, __fmul_rn(ws, sv.z)) + b.z; acc.w = __fadd_rn(acc.w, __fmul_rn(ws, sv.w)) + b.w;
+      st4(out + (int64_t)r * ldo + 4 * lane, acc);
+    } else {
+      st4(part + ((int64_t)item * D4 + lane) * 4, acc);
+    }
+  }
+}
+
+template <int ROLE>
+__global__ void __launch_bounds__(256)
+k_gat_gather_multi(ItemPlan pl, int D4, const float* __restrict__ V, int64_t ldv, const float* __restrict__ p,
+                   const float* __restrict__ q, const float* __restrict__ m, const float* __restrict__ z, float slope,
+                   int group_target, const float* __restrict__ bias, float* __restrict__ out, int64_t ldo,
+                   const float* __restrict__ part) {
+  const int lane = threadIdx.x & 15;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 4; i < pl.n_multi; i += (gridDim.x * blockDim.x) >> 4) {
+    if (lane >= D4) continue;
+    const int r = pl.multi_rows[i];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int it = pl.item_ptr[r]; it < pl.item_ptr[r + 1]; ++it) {
+      const float4 v = ldg4(part + ((int64_t)it * D4 + lane) * 4);
+      acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y); acc.z = __fadd_rn(acc.z, v.z); acc.w = __fadd_rn(acc.w, v.w);
+    }
+    const float ws = edge_alpha<ROLE>(p, q, m, z, r, r, slope, group_target);
+    const float4 sv = ldg4(V + (int64_t)r * ldv + 4 * lane);
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias) b = ldg4(bias + 4 * lane);
+    acc.x = __fadd_rn(acc.x, __fmul_rn(ws, sv.x)) + b.x; acc.y = __fadd_rn(acc.y, __fmul_rn(ws, sv.y)) + b.y;
+    acc.z = __fadd_rn(acc.z, __fmul_rn(ws, sv.z)) + b.z; acc.w = __fadd_rn(acc.w, __fmul_rn(ws, sv.w)) + b.w;
+    st4(out + (int64_t)r * ldo + 4 * lane, acc);
   }
 }
 
@@ -140,38 +235,84 @@ k_rowdot(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, 
 //                ROLE 1: dq[r] = sum over out-edges (r -> nb) of u_e, own = h, gathered = d out.
 // u_e = alpha_e (d alpha_e - t[group]) * leaky_relu'(pre_e),  d alpha_e = <d out_target, h_source>
 template <int ROLE>
+__device__ __forceinline__ float edge_u(const float* __restrict__ p, const float* __restrict__ q,
+                                        const float* __restrict__ m, const float* __restrict__ z,
+                                        const float* __restrict__ t, int r, int nb, float d, float slope,
+                                        int group_target) {
+  const int g = edge_group<ROLE>(r, nb, group_target);
+  const float pre = edge_pre<ROLE>(p, q, r, nb);
+  const float alpha = expf(lrelu(pre, slope) - __ldg(m + g)) / (__ldg(z + g) + 1e-16f);
+  return alpha * (d - __ldg(t + g)) * lrelu_grad(pre, slope);
+}
+
+template <int ROLE>
 __global__ void __launch_bounds__(256)
-k_gat_edge_grad(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx, int n, int D,
-                const float* __restrict__ Own, int64_t ldown, const float* __restrict__ Oth, int64_t ldoth,
-                const float* __restrict__ p, const float* __restrict__ q, const float* __restrict__ m,
-                const float* __restrict__ z, const float* __restrict__ t, float slope, int group_target,
-                float* __restrict__ out) {
-  const int lane = threadIdx.x % 32, wpb = blockDim.x / 32;
-  for (int r = blockIdx.x * wpb + threadIdx.x / 32; r < n; r += gridDim.x * wpb) {
-    const int k0 = row_ptr[r], k1 = row_ptr[r + 1];
-    float own[GAT_MAXS];
-#pragma unroll
-    for (int s = 0; s < GAT_MAXS; ++s) {
-      const int c = lane + 32 * s;
-      own[s] = c < D ? __ldg(Own + (int64_t)r * ldown + c) : 0.f;
-    }
+k_gat_edge_grad_items(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx, ItemPlan pl, int D4,
+                      const float* __restrict__ Own, int64_t ldown, const float* __restrict__ Oth, int64_t ldoth,
+                      const float* __restrict__ p, const float* __restrict__ q, const float* __restrict__ m,
+                      const float* __restrict__ z, const float* __restrict__ t, float slope, int group_target,
+                      float* __restrict__ out, float* __restrict__ part) {
+  constexpr int U = 4;
+  const int lane = threadIdx.x & 15;
+  const unsigned mask = half_mask();
+  const bool active = lane < D4;
+  for (int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 4; item < pl.n_items; item += (gridDim.x * blockDim.x) >> 4) {
+    const int r = __ldg(pl.item_row + item);
+    const int i0 = __ldg(pl.item_ptr + r), i1 = __ldg(pl.item_ptr + r + 1);
+    const int k0 = __ldg(row_ptr + r) + (item - i0) * pl.seg;
+    const int k1 = min(k0 + pl.seg, __ldg(row_ptr + r + 1));
+    const float4 own = active ? ldg4(Own + (int64_t)r * ldown + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
     float acc = 0.f;
-    for (int k = k0; k <= k1; ++k) {
-      const int nb = k < k1 ? __ldg(col_idx + k) : r;
-      if (k < k1 && nb == r) continue;
-      float d = 0.f;
+    for (int k = k0; k < k1; k += U) {
+      int c[U];
+      float d[U];
 #pragma unroll
-      for (int s = 0; s < GAT_MAXS; ++s) {
-        const int c = lane + 32 * s;
-        if (c < D) d = fmaf(own[s], __ldg(Oth + (int64_t)nb * ldoth + c), d);
+      for (int u = 0; u < U; ++u) {
+        c[u] = (k + u < k1) ? __ldg(col_idx + k + u) : -1;
+        if (c[u] == r) c[u] = -1;
       }
-      d = warp_sum(d);
-      const int g = edge_group<ROLE>(r, nb, group_target);
-      const float pre = edge_pre<ROLE>(p, q, r, nb);
-      const float alpha = expf(lrelu(pre, slope) - __ldg(m + g)) / (__ldg(z + g) + 1e-16f);
-      acc += alpha * (d - __ldg(t + g)) * lrelu_grad(pre, slope);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c[u] >= 0 && active) v = ldg4(Oth + (int64_t)c[u] * ldoth + 4 * lane);
+        d[u] = fmaf(own.x, v.x, fmaf(own.y, v.y, fmaf(own.z, v.z, own.w * v.w)));
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) d[u] = half_sum(d[u], mask);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (c[u] >= 0) acc += edge_u<ROLE>(p, q, m, z, t, r, c[u], d[u], slope, group_target);
     }
-    if (lane == 0) out[r] = acc;
+    if (i1 - i0 == 1) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (active) v = ldg4(Oth + (int64_t)r * ldoth + 4 * lane);
+      const float ds = half_sum(fmaf(own.x, v.x, fmaf(own.y, v.y, fmaf(own.z, v.z, own.w * v.w))), mask);
+      if (lane == 0) out[r] = acc + edge_u<ROLE>(p, q, m, z, t, r, r, ds, slope, group_target);
+    } else if (lane == 0) {
+      part[item] = acc;
+    }
+  }
+}
+
+template <int ROLE>
+__global__ void __launch_bounds__(256)
+k_gat_edge_grad_multi(ItemPlan pl, int D4, const float* __restrict__ Own, int64_t ldown,
+                      const float* __restrict__ Oth, int64_t ldoth, const float* __restrict__ p,
+                      const float* __restrict__ q, const float* __restrict__ m, const float* __restrict__ z,
+                      const float* __restrict__ t, float slope, int group_target, float* __restrict__ out,
+                      const float* __restrict__ part) {
+  const int lane = threadIdx.x & 15;
+  const unsigned mask = half_mask();
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+  const bool valid = i < pl.n_multi;
+  const int r = valid ? pl.multi_rows[i] : 0;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+  if (valid && lane < D4) { a = ldg4(Own + (int64_t)r * ldown + 4 * lane); b = ldg4(Oth + (int64_t)r * ldoth + 4 * lane); }
+  const float ds = half_sum(fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w))), mask);
+  if (valid && lane == 0) {
+    float acc = 0.f;
+    for (int it = pl.item_ptr[r]; it < pl.item_ptr[r + 1]; ++it) acc += part[it];
+    out[r] = acc + edge_u<ROLE>(p, q, m, z, t, r, r, ds, slope, group_target);
   }
 }
 
@@ -192,60 +333,113 @@ static inline int warp_grid(int n) {
   return g > cap ? cap : (g < 1 ? 1 : g);
 }
 
+static inline int item_grid(int n_items) {
+  int g = ceil_div(n_items, 16);
+  const int cap = sm_count() * 8;
+  return g > cap ? cap : (g < 1 ? 1 : g);
+}
+
+static int gat_check(int n, int D, const int32_t* row_ptr, const int32_t* item_ptr, const int32_t* item_row, int n_items,
+                     int seg, const int32_t* multi_rows, int n_multi) {
+  if (n < 0 || D < 0 || n_items < 0 || n_multi < 0 || seg <= 0) return BIGNN_EINVAL;
+  if (D > 64 || (D & 3)) return BIGNN_EINVAL;
+  if (!row_ptr || !item_ptr || !item_row || (n_multi > 0 && !multi_rows)) return BIGNN_EINVAL;
+  return 0;
+}
+
 }  // namespace bignn
 
 using namespace bignn;
 
+extern "C" int64_t bignn_gat_fwd_workspace_bytes(int32_t n_items, int32_t D) {
+  if (n_items <= 0 || D <= 0) return 0;
+  return (int64_t)n_items * (D + 2) * (int64_t)sizeof(float) + 64;
+}
+
 // scratch layout (floats): p[n] q[n] m[n] z[n]  -- kept by the caller for the backward
-extern "C" int bignn_gat_fwd(const int32_t* row_ptr, const int32_t* col_idx, int32_t n, int32_t D, const float* H,
-                             int64_t ldh, const float* att, const float* bias, float negative_slope,
-                             int32_t group_target, float* out, int64_t ldo, float* scratch4n, void* stream) {
-  if (n < 0 || D < 0) return BIGNN_EINVAL;
+extern "C" int bignn_gat_fwd(const int32_t* row_ptr, const int32_t* col_idx, const int32_t* item_ptr,
+                             const int32_t* item_row, int32_t n_items, int32_t seg, const int32_t* multi_rows,
+                             int32_t n_multi, int32_t n, int32_t D, const float* H, int64_t ldh, const float* att,
+                             const float* bias, float negative_slope, int32_t group_target, float* out, int64_t ldo,
+                             float* scratch4n, void* workspace, int64_t workspace_bytes, void* stream) {
+  int rc = gat_check(n, D, row_ptr, item_ptr, item_row, n_items, seg, multi_rows, n_multi);
+  if (rc) return rc;
   if (n == 0 || D == 0) return 0;
-  if (D > 32 * GAT_MAXS || !row_ptr || !H || !att || !out || !scratch4n || ldh < D || ldo < D) return BIGNN_EINVAL;
+  if (!H || !att || !out || !scratch4n || ldh < D || ldo < D) return BIGNN_EINVAL;
+  if ((ldh & 3) || (ldo & 3) || !aligned16(H) || !aligned16(out) || (bias && !aligned16(bias))) return BIGNN_EALIGN;
+  if (n_multi > 0 && (!workspace || workspace_bytes < bignn_gat_fwd_workspace_bytes(n_items, D))) return BIGNN_EWORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   float *p = scratch4n, *q = p + n, *m = q + n, *z = m + n;
-  const int g = warp_grid(n);
-  k_gat_scores<<<g, 256, 0, st>>>(H, ldh, n, D, att, p, q);
-  if (group_target) k_gat_group_stats<0><<<g, 256, 0, st>>>(row_ptr, col_idx, n, p, q, negative_slope, m, z);
-  else k_gat_group_stats<1><<<g, 256, 0, st>>>(row_ptr, col_idx, n, p, q, negative_slope, m, z);
-  k_gat_gather<0><<<g, 256, 0, st>>>(row_ptr, col_idx, n, D, H, ldh, p, q, m, z, negative_slope, group_target, bias, out, ldo);
-  BIGNN_LAUNCH_COUNT(3);
+  float* part_s = (float*)workspace;                       // [n_items][2]
+  float* part_v = part_s ? part_s + (((int64_t)2 * n_items + 3) & ~(int64_t)3) : nullptr;   // [n_items][D], 16-byte aligned
+  ItemPlan pl{item_ptr, item_row, multi_rows, n_items, n_multi, seg};
+  const int g = item_grid(n_items), gm = item_grid(n_multi > 0 ? n_multi : 1);
+  k_gat_scores<<<warp_grid(n), 256, 0, st>>>(H, ldh, n, D, att, p, q);
+  if (group_target) {
+    k_gat_stats_items<0><<<g, 256, 0, st>>>(row_ptr, col_idx, pl, p, q, negative_slope, m, z, part_s);
+    if (n_multi) k_gat_stats_multi<0><<<ceil_div(n_multi, 256), 256, 0, st>>>(pl, p, q, negative_slope, m, z, part_s);
+  } else {
+    k_gat_stats_items<1><<<g, 256, 0, st>>>(row_ptr, col_idx, pl, p, q, negative_slope, m, z, part_s);
+    if (n_multi) k_gat_stats_multi<1><<<ceil_div(n_multi, 256), 256, 0, st>>>(pl, p, q, negative_slope, m, z, part_s);
+  }
+  k_gat_gather_items<0><<<g, 256, 0, st>>>(row_ptr, col_idx, pl, D / 4, H, ldh, p, q, m, z, negative_slope, group_target,
+                                            bias, out, ldo, part_v);
+  if (n_multi)
+    k_gat_gather_multi<0><<<gm, 256, 0, st>>>(pl, D / 4, H, ldh, p, q, m, z, negative_slope, group_target, bias, out, ldo,
+                                              part_v);
+  BIGNN_LAUNCH_COUNT(3 + (n_multi ? 2 : 0));
   return last_launch_status();
 }
 
+extern "C" int64_t bignn_gat_bwd_workspace_bytes(int32_t n, int32_t D, int32_t n_items) {
+  if (n <= 0 || D <= 0) return 0;
+  return ((int64_t)n * D + n + (int64_t)n_items * (D + 1) + 16) * (int64_t)sizeof(float);
+}
+
 // dH[n,D] and the two score-gradient vectors dpq[2n] (d att = [dp^T H ; dq^T H] is a GEMM for the caller)
-extern "C" int bignn_gat_bwd(const int32_t* row_ptr, const int32_t* col_idx, int32_t n, int32_t D, const float* H,
-                             int64_t ldh, const float* att, const float* bias, float negative_slope,
-                             int32_t group_target, const float* out, int64_t ldo, const float* dOut, int64_t lddo,
-                             const float* scratch4n, float* dH, int64_t lddh, float* dpq, float* workspace,
-                             int64_t workspace_bytes, void* stream) {
-  if (n < 0 || D < 0) return BIGNN_EINVAL;
+extern "C" int bignn_gat_bwd(const int32_t* row_ptr, const int32_t* col_idx, const int32_t* item_ptr,
+                             const int32_t* item_row, int32_t n_items, int32_t seg, const int32_t* multi_rows,
+                             int32_t n_multi, int32_t n, int32_t D, const float* H, int64_t ldh, const float* att,
+                             const float* bias, float negative_slope, int32_t group_target, const float* out,
+                             int64_t ldo, const float* dOut, int64_t lddo, const float* scratch4n, float* dH,
+                             int64_t lddh, float* dpq, void* workspace, int64_t workspace_bytes, void* stream) {
+  int rc = gat_check(n, D, row_ptr, item_ptr, item_row, n_items, seg, multi_rows, n_multi);
+  if (rc) return rc;
   if (n == 0 || D == 0) return 0;
-  if (D > 32 * GAT_MAXS || !row_ptr || !H || !att || !out || !dOut || !scratch4n || !dH || !dpq) return BIGNN_EINVAL;
+  if (!H || !att || !out || !dOut || !scratch4n || !dH || !dpq) return BIGNN_EINVAL;
   if (ldh < D || ldo < D || lddo < D || lddh < D) return BIGNN_EINVAL;
-  const int64_t need = ((int64_t)n * D + n) * (int64_t)sizeof(float);
-  if (!workspace || workspace_bytes < need) return BIGNN_EWORKSPACE;
+  if ((ldh & 3) || (lddo & 3) || !aligned16(H) || !aligned16(dOut)) return BIGNN_EALIGN;
+  if (!workspace || workspace_bytes < bignn_gat_bwd_workspace_bytes(n, D, n_items)) return BIGNN_EWORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   const float *p = scratch4n, *q = p + n, *m = q + n, *z = m + n;
-  float* G = workspace;
-  float* t = G + (int64_t)n * D;
+  float* G = (float*)workspace;                                   // [n][D]
+  float* part_v = G + (int64_t)n * D;                             // [n_items][D]
+  float* t = part_v + (int64_t)n_items * D;                       // [n]
+  float* part_s = t + n;                                          // [n_items]
   float *dp = dpq, *dq = dpq + n;
-  const int g = warp_grid(n);
-  k_gat_gather<1><<<g, 256, 0, st>>>(row_ptr, col_idx, n, D, dOut, lddo, p, q, m, z, negative_slope, group_target, nullptr, G, D);
-  if (group_target) k_rowdot<<<g, 256, 0, st>>>(dOut, lddo, out, ldo, bias, n, D, t);
-  else k_rowdot<<<g, 256, 0, st>>>(H, ldh, G, D, nullptr, n, D, t);
-  k_gat_edge_grad<0><<<g, 256, 0, st>>>(row_ptr, col_idx, n, D, dOut, lddo, H, ldh, p, q, m, z, t, negative_slope, group_target, dp);
-  k_gat_edge_grad<1><<<g, 256, 0, st>>>(row_ptr, col_idx, n, D, H, ldh, dOut, lddo, p, q, m, z, t, negative_slope, group_target, dq);
+  ItemPlan pl{item_ptr, item_row, multi_rows, n_items, n_multi, seg};
+  const int g = item_grid(n_items), gm = item_grid(n_multi > 0 ? n_multi : 1), wg = warp_grid(n);
+  k_gat_gather_items<1><<<g, 256, 0, st>>>(row_ptr, col_idx, pl, D / 4, dOut, lddo, p, q, m, z, negative_slope,
+                                            group_target, nullptr, G, D, part_v);
+  if (n_multi)
+    k_gat_gather_multi<1><<<gm, 256, 0, st>>>(pl, D / 4, dOut, lddo, p, q, m, z, negative_slope, group_target, nullptr, G, D,
+                                              part_v);
+  if (group_target) k_rowdot<<<wg, 256, 0, st>>>(dOut, lddo, out, ldo, bias, n, D, t);
+  else k_rowdot<<<wg, 256, 0, st>>>(H, ldh, G, D, nullptr, n, D, t);
+  k_gat_edge_grad_items<0><<<g, 256, 0, st>>>(row_ptr, col_idx, pl, D / 4, dOut, lddo, H, ldh, p, q, m, z, t,
+                                               negative_slope, group_target, dp, part_s);
+  if (n_multi)
+    k_gat_edge_grad_multi<0><<<gm, 256, 0, st>>>(pl, D / 4, dOut, lddo, H, ldh, p, q, m, z, t, negative_slope,
+                                                 group_target, dp, part_s);
+  k_gat_edge_grad_items<1><<<g, 256, 0, st>>>(row_ptr, col_idx, pl, D / 4, H, ldh, dOut, lddo, p, q, m, z, t,
+                                               negative_slope, group_target, dq, part_s);
+  if (n_multi)
+    k_gat_edge_grad_multi<1><<<gm, 256, 0, st>>>(pl, D / 4, H, ldh, dOut, lddo, p, q, m, z, t, negative_slope,
+                                                 group_target, dq, part_s);
   int eg = (int)ceil_div<int64_t>((int64_t)n * D, 256);
   const int cap = sm_count() * 8;
   if (eg > cap) eg = cap;
   k_gat_combine<<<eg, 256, 0, st>>>(G, D, dp, dq, att, n, D, dH, lddh);
-  BIGNN_LAUNCH_COUNT(5);
+  BIGNN_LAUNCH_COUNT(5 + (n_multi ? 3 : 0));
   return last_launch_status();
-}
-
-extern "C" int64_t bignn_gat_bwd_workspace_bytes(int32_t n, int32_t D) {
-  if (n <= 0 || D <= 0) return 0;
-  return ((int64_t)n * D + n) * (int64_t)sizeof(float);
 }

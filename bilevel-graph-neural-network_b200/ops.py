@@ -57,6 +57,7 @@ class CSR(object):
         self.row_ptr, self.col_idx, self.n_rows = row_ptr, col_idx, int(n_rows)
         self._dinv = None
         self.plan = None
+        self._row_ptr_host = row_ptr_host
         if row_ptr_host is not None and len(row_ptr_host) > 1:
             import numpy as np
             if int(np.diff(np.asarray(row_ptr_host, np.int64)).max()) > LONG_ROW_SEG:
@@ -65,6 +66,14 @@ class CSR(object):
     @property
     def nnz(self):
         return int(self.col_idx.numel())
+
+    def ensure_plan(self):
+        """a work-item plan for kernels that always run over items (GAT): one item per row when the
+        graph has no long rows."""
+        if self.plan is None:
+            rp = self.row_ptr.cpu().numpy() if self._row_ptr_host is None else self._row_ptr_host
+            self.plan = RowPlan(rp, self.row_ptr.device)
+        return self.plan
 
     def dinv(self):
         if self._dinv is None:
@@ -389,8 +398,12 @@ class _GatConv(torch.autograd.Function):
         out = torch.empty_like(h)
         scratch = torch.empty(4 * max(n, 1), dtype=torch.float32, device=h.device)
         a = att.reshape(-1)
-        _lib.call('bignn_gat_fwd', csr.row_ptr, csr.col_idx, n, D, h, h.stride(0), a, bias, float(slope),
-                  int(group_target), out, out.stride(0), scratch)
+        pl = csr.ensure_plan()
+        wsb = _lib.call('bignn_gat_fwd_workspace_bytes', pl.n_items, D)
+        ws = _ws(wsb, h.device)
+        _lib.call('bignn_gat_fwd', csr.row_ptr, csr.col_idx, pl.item_ptr, pl.item_row, pl.n_items, pl.seg,
+                  pl.multi_rows, pl.n_multi, n, D, h, h.stride(0), a, bias, float(slope),
+                  int(group_target), out, out.stride(0), scratch, ws, int(wsb))
         ctx.csr, ctx.slope, ctx.group = csr, float(slope), int(group_target)
         ctx.att_shape = att.shape
         ctx.save_for_backward(h, a, bias, out, scratch)
@@ -403,9 +416,11 @@ class _GatConv(torch.autograd.Function):
         n, D = h.shape
         dh = torch.empty_like(h)
         dpq = torch.empty(2 * max(n, 1), dtype=torch.float32, device=h.device)
-        wsb = _lib.call('bignn_gat_bwd_workspace_bytes', n, D)
+        pl = ctx.csr.ensure_plan()
+        wsb = _lib.call('bignn_gat_bwd_workspace_bytes', n, D, pl.n_items)
         ws = _ws(wsb, h.device)
-        _lib.call('bignn_gat_bwd', ctx.csr.row_ptr, ctx.csr.col_idx, n, D, h, h.stride(0), a, bias, ctx.slope,
+        _lib.call('bignn_gat_bwd', ctx.csr.row_ptr, ctx.csr.col_idx, pl.item_ptr, pl.item_row, pl.n_items, pl.seg,
+                  pl.multi_rows, pl.n_multi, n, D, h, h.stride(0), a, bias, ctx.slope,
                   ctx.group, out, out.stride(0), dout, dout.stride(0), scratch, dh, dh.stride(0), dpq, ws, int(wsb))
         datt = gemm(dpq[:2 * n].view(2, n), h).reshape(ctx.att_shape) if ctx.needs_input_grad[1] else None
         dbias = colsum(dout) if bias is not None and ctx.needs_input_grad[2] else None

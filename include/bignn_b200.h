@@ -241,19 +241,26 @@ int bignn_bce_logits_bwd(const float* x, const float* y, int32_t P, const float*
  * softmax by the SOURCE node (torch-geometric 1.1.x), 1 by the TARGET (>= 1.2).
  * scratch4n[4n] floats (p, q, max, sum) are produced by fwd and consumed by bwd.
  * bwd returns dH and dpq[2n] = (d p, d q); d att = [dp^T H ; dq^T H] (a GEMM).
- * D <= 128.
  * ------------------------------------------------------------------------- */
-int bignn_gat_fwd(const int32_t* row_ptr, const int32_t* col_idx, int32_t n, int32_t D,
+/* Every neighbour pass runs over the work items of a row plan (see bignn_spmm_planned_f32: item_ptr,
+ * item_row, multi_rows; rows of one item are finished in place, hub rows through per-item partials
+ * combined in item order).  D <= 64, D % 4 == 0, 16-byte aligned rows. */
+int64_t bignn_gat_fwd_workspace_bytes(int32_t n_items, int32_t D);
+int bignn_gat_fwd(const int32_t* row_ptr, const int32_t* col_idx,
+                  const int32_t* item_ptr, const int32_t* item_row, int32_t n_items, int32_t seg,
+                  const int32_t* multi_rows, int32_t n_multi, int32_t n, int32_t D,
                   const float* H, int64_t ldh, const float* att, const float* bias,
                   float negative_slope, int32_t group_target, float* out, int64_t ldo,
-                  float* scratch4n, void* stream);
-int64_t bignn_gat_bwd_workspace_bytes(int32_t n, int32_t D);
-int bignn_gat_bwd(const int32_t* row_ptr, const int32_t* col_idx, int32_t n, int32_t D,
+                  float* scratch4n, void* workspace, int64_t workspace_bytes, void* stream);
+int64_t bignn_gat_bwd_workspace_bytes(int32_t n, int32_t D, int32_t n_items);
+int bignn_gat_bwd(const int32_t* row_ptr, const int32_t* col_idx,
+                  const int32_t* item_ptr, const int32_t* item_row, int32_t n_items, int32_t seg,
+                  const int32_t* multi_rows, int32_t n_multi, int32_t n, int32_t D,
                   const float* H, int64_t ldh, const float* att, const float* bias,
                   float negative_slope, int32_t group_target, const float* out, int64_t ldo,
                   const float* dOut, int64_t lddo, const float* scratch4n,
                   float* dH, int64_t lddh, float* dpq,
-                  float* workspace, int64_t workspace_bytes, void* stream);
+                  void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------
  * Elementwise / row-wise operators.
