@@ -169,9 +169,45 @@ def spmm_roofline(torch, B, rows, peaks, device):
     alg = 4.0 * D * A * 2 + 4.0 * nnz + 4.0 * (A + 1)
     ach = alg / (ms * 1e-3) / 1e9
     peak = peaks.get('hbm_gbs', 6650.0)
+    # DRAM bytes per launch of this exact case from the committed `ncu --set full` capture
+    # (profiles/r1_summary.md: dram__bytes_read.sum + dram__bytes_write.sum = 2.148 + 2.007 GB)
+    traffic = 4.155e9 if abs(A - 8000311) < 1000 else None
     return dict(kernel='k_spmm_v4<16,1,GIN> (bignn_spmm_f32)', bound='hbm', achieved=ach, peak=peak, unit='GB/s',
-                frac=ach / peak, traffic=None, rows=A, nnz=nnz, D=D, ms_per_launch=ms,
+                frac=ach / peak, traffic=traffic, rows=A, nnz=nnz, D=D, ms_per_launch=ms,
                 algorithmic_bytes=alg, peak_source='MEASURED_PEAKS.json' if 'hbm_gbs' in peaks else 'fallback 6650')
+
+
+def dense_roofline(torch, B, rows, peaks, device):
+    """The step's dominant kernel by device time (profiles/r1_final_summary.md): the tcgen05 3xTF32 node
+    transform k_gemm_tc<64,2>, at the in-step shape (rows = atoms of the workload) and at a > L2 shape.
+    It is HBM-bound (64 FLOP per byte at three TF32 products), so it is reported against the copy peak."""
+    from bignn_b200 import ops
+    out = {}
+    peak = peaks.get('hbm_gbs', 6650.0)
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=device)
+    for tag, M in (('in_step_shape', rows), ('gt_l2_shape', 2_000_000)):
+        a = torch.randn(M, 64, device=device)
+        w = torch.randn(64, 64, device=device)
+        b = torch.randn(64, device=device)
+        c = torch.empty(M, 64, device=device)
+        for _ in range(3):
+            ops.gemm_tc(a, w, True, b, 1, out=c)
+        ts = []
+        for _ in range(10):
+            flush.fill_(0.0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ops.gemm_tc(a, w, True, b, 1, out=c)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = float(np.mean(ts))
+        alg = 2.0 * M * 64 * 4 + 64 * 64 * 4
+        ach = alg / (ms * 1e-3) / 1e9
+        out[tag] = dict(rows=M, ms_per_launch=ms, algorithmic_bytes=alg, achieved=ach, frac=ach / peak,
+                        tflops_3xtf32=3 * 2.0 * M * 64 * 64 / (ms * 1e-3) / 1e12)
+    return dict(kernel='k_gemm_tc<64,2> (bignn_gemm_tc_f32, tcgen05 kind::tf32 x3)', bound='hbm', peak=peak, unit='GB/s',
+                traffic_gt_l2_shape=0.977e9, **out)
 
 
 def run_ours(args):
@@ -365,6 +401,7 @@ def main():
     out['kernel_profile'] = prof
     if args.gpus == 1:
         out['roofline'] = spmm_roofline(torch, B, args.spmm_rows, peaks, dev)
+        out['roofline_step_dominant'] = dense_roofline(torch, B, int(data.packed.atom_ptr_host[-1]), peaks, dev)
         cpu_args = argparse.Namespace(**vars(args))
         r = run_reference(cpu_args, sample_steps=args.cpu_sample_steps)
         out['cpu_baseline'] = dict(value=r['value'], unit=UNIT, cores=r['cores'], kind='port', sample=r['sample'],
