@@ -307,8 +307,6 @@ def run_ours(args):
     launches_per_step = getattr(eng, 'launches_per_step', None)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
         return None
     out = dict(metric=METRIC, value=pairs_dev / (dev_ms * 1e-3), unit=UNIT, n_gpus=world, steps=args.steps,
                warmup=max(args.warmup, 3), ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling='strong',
@@ -390,9 +388,8 @@ def main():
         return
     out, (torch, B, peaks, dev, eng, data, model) = res
     if args.gpus > 1:
-        import torch.distributed as dist
-        if dist.is_initialized():
-            dist.destroy_process_group()
+        # no destroy_process_group() here: tearing the NCCL communicator down while captured CUDA graphs
+        # still hold its kernels blocks forever (measured: a 900 s hang); the process simply exits
         out['gpu_launches'] = None if not hasattr(eng, 'launches_per_step') else eng.launches_per_step * args.steps
         print(json.dumps(out))
         return

@@ -118,7 +118,10 @@ def gemm(a, b, ta=False, tb=False, bias=None, act=0, out=None):
     return c
 
 
+import os as _os
+
 TC_MIN_ROWS = 512      # below this a 128-row tensor-core tile grid cannot fill the SMs; SIMT path
+_NO_TC = bool(_os.environ.get('BIGNN_NO_TC'))      # debugging switch: route the transforms to the SIMT kernels
 
 
 def gemm_tc(a, b, b_is_nk, bias=None, act=0, out=None):
@@ -136,7 +139,7 @@ def gemm_tc(a, b, b_is_nk, bias=None, act=0, out=None):
 
 
 def use_tc(M, N, K):
-    return M >= TC_MIN_ROWS and N <= 128 and K % 4 == 0 and (K <= 64 or (N <= 64 and K <= 96))
+    return (not _NO_TC) and M >= TC_MIN_ROWS and N <= 128 and K % 4 == 0 and (K <= 64 or (N <= 64 and K <= 96))
 
 
 def dw_tc(p, q, colsum_of=-1):
@@ -153,7 +156,7 @@ def dw_tc(p, q, colsum_of=-1):
 
 
 def use_dw_tc(M, Np, Nq):
-    return M >= TC_MIN_ROWS and Np <= 64 and Nq <= 64 and Np % 4 == 0 and Nq % 4 == 0
+    return (not _NO_TC) and M >= TC_MIN_ROWS and Np <= 64 and Nq <= 64 and Np % 4 == 0 and Nq % 4 == 0
 
 
 def colsum(x):
