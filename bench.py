@@ -222,6 +222,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = 'cuda:%d' % local
     if world > 1:
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+            os.environ['NCCL_DEBUG'] = 'WARN'          # keep stdout to the one JSON line
         dist.init_process_group('nccl', device_id=torch.device(dev))
     B._lib.load()
     peaks = {}

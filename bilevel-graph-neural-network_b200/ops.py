@@ -28,7 +28,8 @@ def _ws(nbytes, device):
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
 
-LONG_ROW_SEG = 128     # neighbours per work item of the long-row SpMM variant
+LONG_ROW_SEG = 32      # neighbours per work item: a sub-warp walks its item 4 neighbours at a time, so the
+                       # item length bounds the dependent-latency chain (8 steps); hub rows become many items
 
 
 class RowPlan(object):
