@@ -59,9 +59,9 @@ SIGNATURES = {
     'bignn_bce_logits_fwd': ('i', 'ppips'),
     'bignn_bce_logits_bwd': ('i', 'ppipps'),
     'bignn_gat_fwd_workspace_bytes': ('l', 'ii'),
-    'bignn_gat_fwd': ('i', 'pp' 'ppii' 'pi' 'ii' 'pl' 'pp' 'fi' 'pl' 'p' 'pl' 's'),
+    'bignn_gat_fwd': ('i', 'pp' 'ppii' 'pi' 'iii' 'pl' 'pp' 'fi' 'pl' 'p' 'pl' 's'),
     'bignn_gat_bwd_workspace_bytes': ('l', 'iii'),
-    'bignn_gat_bwd': ('i', 'pp' 'ppii' 'pi' 'ii' 'pl' 'pp' 'fi' 'pl' 'pl' 'p' 'pl' 'p' 'pl' 's'),
+    'bignn_gat_bwd': ('i', 'pp' 'ppii' 'pi' 'iii' 'pl' 'pp' 'fi' 'pl' 'pl' 'p' 'pl' 'p' 'pl' 's'),
     'bignn_act_fwd_f32': ('i', 'pplis'),
     'bignn_add_f32': ('i', 'pppls'),
     'bignn_prelu_fwd_f32': ('i', 'pplipis'),

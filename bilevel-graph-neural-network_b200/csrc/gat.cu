@@ -22,11 +22,14 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // p[n] = att_i . h[n],  q[n] = att_j . h[n]
+// (several edge types are batched as one block-diagonal graph of n / n_block blocks; block b uses
+//  att[b] and bias[b])
 __global__ void __launch_bounds__(256)
-k_gat_scores(const float* __restrict__ H, int64_t ldh, int n, int D, const float* __restrict__ att,
+k_gat_scores(const float* __restrict__ H, int64_t ldh, int n, int D, const float* __restrict__ att_all, int n_block,
              float* __restrict__ p, float* __restrict__ q) {
   const int lane = threadIdx.x % 32, wpb = blockDim.x / 32;
   for (int r = blockIdx.x * wpb + threadIdx.x / 32; r < n; r += gridDim.x * wpb) {
+    const float* att = att_all + (int64_t)(r / n_block) * 2 * D;
     float a = 0.f, b = 0.f;
     for (int c = lane; c < D; c += 32) {
       const float v = __ldg(H + (int64_t)r * ldh + c);
@@ -146,7 +149,8 @@ __global__ void __launch_bounds__(256)
 k_gat_gather_items(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx, ItemPlan pl, int D4,
                    const float* __restrict__ V, int64_t ldv, const float* __restrict__ p, const float* __restrict__ q,
                    const float* __restrict__ m, const float* __restrict__ z, float slope, int group_target,
-                   const float* __restrict__ bias, float* __restrict__ out, int64_t ldo, float* __restrict__ part) {
+                   const float* __restrict__ bias_all, int n_block, float* __restrict__ out, int64_t ldo,
+                   float* __restrict__ part) {
   constexpr int U = 4;
   const int lane = threadIdx.x & 15;
   const bool active = lane < D4;
@@ -182,7 +186,7 @@ k_gat_gather_items(const int32_t* __restrict__ row_ptr, const int32_t* __restric
       const float ws = edge_alpha<ROLE>(p, q, m, z, r, r, slope, group_target);
       const float4 sv = ldg4(V + (int64_t)r * ldv + 4 * lane);
       float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (bias) b = ldg4(bias + 4 * lane);
+      if (bias_all) b = ldg4(bias_all + (int64_t)(r / n_block) * 4 * D4 + 4 * lane);
       acc.x = __fadd_rn(acc.x, __fmul_rn(ws, sv.x)) + b.x; acc.y = __fadd_rn(acc.y, __fmul_rn(ws, sv.y)) + b.y;
       acc.z = __fadd_rn(acc.z, __fmul_rn(ws, sv.z)) + b.z; acc.w = __fadd_rn(acc.w, __fmul_rn(ws, sv.w)) + b.w;
       st4(out + (int64_t)r * ldo + 4 * lane, acc);
@@ -196,8 +200,8 @@ template <int ROLE>
 __global__ void __launch_bounds__(256)
 k_gat_gather_multi(ItemPlan pl, int D4, const float* __restrict__ V, int64_t ldv, const float* __restrict__ p,
                    const float* __restrict__ q, const float* __restrict__ m, const float* __restrict__ z, float slope,
-                   int group_target, const float* __restrict__ bias, float* __restrict__ out, int64_t ldo,
-                   const float* __restrict__ part) {
+                   int group_target, const float* __restrict__ bias_all, int n_block, float* __restrict__ out,
+                   int64_t ldo, const float* __restrict__ part) {
   const int lane = threadIdx.x & 15;
   for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 4; i < pl.n_multi; i += (gridDim.x * blockDim.x) >> 4) {
     if (lane >= D4) continue;
@@ -210,7 +214,7 @@ k_gat_gather_multi(ItemPlan pl, int D4, const float* __restrict__ V, int64_t ldv
     const float ws = edge_alpha<ROLE>(p, q, m, z, r, r, slope, group_target);
     const float4 sv = ldg4(V + (int64_t)r * ldv + 4 * lane);
     float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (bias) b = ldg4(bias + 4 * lane);
+    if (bias_all) b = ldg4(bias_all + (int64_t)(r / n_block) * 4 * D4 + 4 * lane);
     acc.x = __fadd_rn(acc.x, __fmul_rn(ws, sv.x)) + b.x; acc.y = __fadd_rn(acc.y, __fmul_rn(ws, sv.y)) + b.y;
     acc.z = __fadd_rn(acc.z, __fmul_rn(ws, sv.z)) + b.z; acc.w = __fadd_rn(acc.w, __fmul_rn(ws, sv.w)) + b.w;
     st4(out + (int64_t)r * ldo + 4 * lane, acc);
@@ -220,9 +224,10 @@ k_gat_gather_multi(ItemPlan pl, int D4, const float* __restrict__ V, int64_t ldv
 // t[r] = <A[r], B[r] - sub>     (softmax-backward group term)
 __global__ void __launch_bounds__(256)
 k_rowdot(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb,
-         const float* __restrict__ sub, int n, int D, float* __restrict__ t) {
+         const float* __restrict__ sub_all, int n_block, int n, int D, float* __restrict__ t) {
   const int lane = threadIdx.x % 32, wpb = blockDim.x / 32;
   for (int r = blockIdx.x * wpb + threadIdx.x / 32; r < n; r += gridDim.x * wpb) {
+    const float* sub = sub_all ? sub_all + (int64_t)(r / n_block) * D : nullptr;
     float a = 0.f;
     for (int c = lane; c < D; c += 32)
       a = fmaf(__ldg(A + (int64_t)r * lda + c), __ldg(B + (int64_t)r * ldb + c) - (sub ? __ldg(sub + c) : 0.f), a);
@@ -319,10 +324,11 @@ k_gat_edge_grad_multi(ItemPlan pl, int D4, const float* __restrict__ Own, int64_
 // dH[r,:] = G[r,:] + dp[r] att_i + dq[r] att_j
 __global__ void __launch_bounds__(256)
 k_gat_combine(const float* __restrict__ G, int64_t ldg, const float* __restrict__ dp, const float* __restrict__ dq,
-              const float* __restrict__ att, int n, int D, float* __restrict__ dH, int64_t ldd) {
+              const float* __restrict__ att_all, int n_block, int n, int D, float* __restrict__ dH, int64_t ldd) {
   const int64_t total = (int64_t)n * D;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int r = (int)(i / D), c = (int)(i % D);
+    const float* att = att_all + (int64_t)(r / n_block) * 2 * D;
     dH[(int64_t)r * ldd + c] = G[(int64_t)r * ldg + c] + dp[r] * __ldg(att + c) + dq[r] * __ldg(att + D + c);
   }
 }
@@ -359,9 +365,11 @@ extern "C" int64_t bignn_gat_fwd_workspace_bytes(int32_t n_items, int32_t D) {
 // scratch layout (floats): p[n] q[n] m[n] z[n]  -- kept by the caller for the backward
 extern "C" int bignn_gat_fwd(const int32_t* row_ptr, const int32_t* col_idx, const int32_t* item_ptr,
                              const int32_t* item_row, int32_t n_items, int32_t seg, const int32_t* multi_rows,
-                             int32_t n_multi, int32_t n, int32_t D, const float* H, int64_t ldh, const float* att,
-                             const float* bias, float negative_slope, int32_t group_target, float* out, int64_t ldo,
-                             float* scratch4n, void* workspace, int64_t workspace_bytes, void* stream) {
+                             int32_t n_multi, int32_t n, int32_t n_block, int32_t D, const float* H, int64_t ldh,
+                             const float* att, const float* bias, float negative_slope, int32_t group_target,
+                             float* out, int64_t ldo, float* scratch4n, void* workspace, int64_t workspace_bytes,
+                             void* stream) {
+  if (n_block <= 0 || (n > 0 && n % n_block)) return BIGNN_EINVAL;
   int rc = gat_check(n, D, row_ptr, item_ptr, item_row, n_items, seg, multi_rows, n_multi);
   if (rc) return rc;
   if (n == 0 || D == 0) return 0;
@@ -374,7 +382,7 @@ extern "C" int bignn_gat_fwd(const int32_t* row_ptr, const int32_t* col_idx, con
   float* part_v = part_s ? part_s + (((int64_t)2 * n_items + 3) & ~(int64_t)3) : nullptr;   // [n_items][D], 16-byte aligned
   ItemPlan pl{item_ptr, item_row, multi_rows, n_items, n_multi, seg};
   const int g = item_grid(n_items), gm = item_grid(n_multi > 0 ? n_multi : 1);
-  k_gat_scores<<<warp_grid(n), 256, 0, st>>>(H, ldh, n, D, att, p, q);
+  k_gat_scores<<<warp_grid(n), 256, 0, st>>>(H, ldh, n, D, att, n_block, p, q);
   if (group_target) {
     k_gat_stats_items<0><<<g, 256, 0, st>>>(row_ptr, col_idx, pl, p, q, negative_slope, m, z, part_s);
     if (n_multi) k_gat_stats_multi<0><<<ceil_div(n_multi, 256), 256, 0, st>>>(pl, p, q, negative_slope, m, z, part_s);
@@ -383,10 +391,10 @@ extern "C" int bignn_gat_fwd(const int32_t* row_ptr, const int32_t* col_idx, con
     if (n_multi) k_gat_stats_multi<1><<<ceil_div(n_multi, 256), 256, 0, st>>>(pl, p, q, negative_slope, m, z, part_s);
   }
   k_gat_gather_items<0><<<g, 256, 0, st>>>(row_ptr, col_idx, pl, D / 4, H, ldh, p, q, m, z, negative_slope, group_target,
-                                            bias, out, ldo, part_v);
+                                            bias, n_block, out, ldo, part_v);
   if (n_multi)
-    k_gat_gather_multi<0><<<gm, 256, 0, st>>>(pl, D / 4, H, ldh, p, q, m, z, negative_slope, group_target, bias, out, ldo,
-                                              part_v);
+    k_gat_gather_multi<0><<<gm, 256, 0, st>>>(pl, D / 4, H, ldh, p, q, m, z, negative_slope, group_target, bias, n_block,
+                                              out, ldo, part_v);
   BIGNN_LAUNCH_COUNT(3 + (n_multi ? 2 : 0));
   return last_launch_status();
 }
@@ -399,10 +407,12 @@ extern "C" int64_t bignn_gat_bwd_workspace_bytes(int32_t n, int32_t D, int32_t n
 // dH[n,D] and the two score-gradient vectors dpq[2n] (d att = [dp^T H ; dq^T H] is a GEMM for the caller)
 extern "C" int bignn_gat_bwd(const int32_t* row_ptr, const int32_t* col_idx, const int32_t* item_ptr,
                              const int32_t* item_row, int32_t n_items, int32_t seg, const int32_t* multi_rows,
-                             int32_t n_multi, int32_t n, int32_t D, const float* H, int64_t ldh, const float* att,
-                             const float* bias, float negative_slope, int32_t group_target, const float* out,
-                             int64_t ldo, const float* dOut, int64_t lddo, const float* scratch4n, float* dH,
-                             int64_t lddh, float* dpq, void* workspace, int64_t workspace_bytes, void* stream) {
+                             int32_t n_multi, int32_t n, int32_t n_block, int32_t D, const float* H, int64_t ldh,
+                             const float* att, const float* bias, float negative_slope, int32_t group_target,
+                             const float* out, int64_t ldo, const float* dOut, int64_t lddo, const float* scratch4n,
+                             float* dH, int64_t lddh, float* dpq, void* workspace, int64_t workspace_bytes,
+                             void* stream) {
+  if (n_block <= 0 || (n > 0 && n % n_block)) return BIGNN_EINVAL;
   int rc = gat_check(n, D, row_ptr, item_ptr, item_row, n_items, seg, multi_rows, n_multi);
   if (rc) return rc;
   if (n == 0 || D == 0) return 0;
@@ -420,12 +430,12 @@ extern "C" int bignn_gat_bwd(const int32_t* row_ptr, const int32_t* col_idx, con
   ItemPlan pl{item_ptr, item_row, multi_rows, n_items, n_multi, seg};
   const int g = item_grid(n_items), gm = item_grid(n_multi > 0 ? n_multi : 1), wg = warp_grid(n);
   k_gat_gather_items<1><<<g, 256, 0, st>>>(row_ptr, col_idx, pl, D / 4, dOut, lddo, p, q, m, z, negative_slope,
-                                            group_target, nullptr, G, D, part_v);
+                                            group_target, nullptr, n_block, G, D, part_v);
   if (n_multi)
-    k_gat_gather_multi<1><<<gm, 256, 0, st>>>(pl, D / 4, dOut, lddo, p, q, m, z, negative_slope, group_target, nullptr, G, D,
-                                              part_v);
-  if (group_target) k_rowdot<<<wg, 256, 0, st>>>(dOut, lddo, out, ldo, bias, n, D, t);
-  else k_rowdot<<<wg, 256, 0, st>>>(H, ldh, G, D, nullptr, n, D, t);
+    k_gat_gather_multi<1><<<gm, 256, 0, st>>>(pl, D / 4, dOut, lddo, p, q, m, z, negative_slope, group_target, nullptr,
+                                              n_block, G, D, part_v);
+  if (group_target) k_rowdot<<<wg, 256, 0, st>>>(dOut, lddo, out, ldo, bias, n_block, n, D, t);
+  else k_rowdot<<<wg, 256, 0, st>>>(H, ldh, G, D, nullptr, n_block, n, D, t);
   k_gat_edge_grad_items<0><<<g, 256, 0, st>>>(row_ptr, col_idx, pl, D / 4, dOut, lddo, H, ldh, p, q, m, z, t,
                                                negative_slope, group_target, dp, part_s);
   if (n_multi)
@@ -439,7 +449,7 @@ extern "C" int bignn_gat_bwd(const int32_t* row_ptr, const int32_t* col_idx, con
   int eg = (int)ceil_div<int64_t>((int64_t)n * D, 256);
   const int cap = sm_count() * 8;
   if (eg > cap) eg = cap;
-  k_gat_combine<<<eg, 256, 0, st>>>(G, D, dp, dq, att, n, D, dH, lddh);
+  k_gat_combine<<<eg, 256, 0, st>>>(G, D, dp, dq, att, n_block, n, D, dH, lddh);
   BIGNN_LAUNCH_COUNT(5 + (n_multi ? 3 : 0));
   return last_launch_status();
 }

@@ -27,6 +27,13 @@ class BiGNNData(object):
                 r, c = edge_types[name]
                 self.interaction_nxgraphs[name] = InteractionGraph(self.N, r, c, self.device)
             self.num_hyper_edge_feat = len(edge_types) + 1        # + the 'none' type of the added self loops
+            # all edge types as ONE block-diagonal graph (type t occupies rows/cols [t*N, (t+1)*N)): the
+            # per-type message passing of NodeModelAggrByEdge then runs as a single batched launch
+            rows = np.concatenate([np.asarray(edge_types[n][0], np.int64) + t * self.N
+                                   for t, n in enumerate(sorted(edge_types))])
+            cols = np.concatenate([np.asarray(edge_types[n][1], np.int64) + t * self.N
+                                   for t, n in enumerate(sorted(edge_types))])
+            self.interaction_stack = InteractionGraph(len(edge_types) * self.N, rows, cols, self.device)
         # sorted (N*row+col) keys of the train graph for O(log E) membership tests
         self._edge_keys = np.sort(np.asarray(self.interaction_combo_nxgraph.row_host, np.int64) * self.N +
                                   np.asarray(self.interaction_combo_nxgraph.col_host, np.int64))

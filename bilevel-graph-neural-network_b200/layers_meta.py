@@ -31,6 +31,19 @@ class NodeModelAggrByEdge(nn.Module):
             raise ValueError
 
     def forward(self, x, batch_data):
+        stack = getattr(batch_data.dataset, 'interaction_stack', None)
+        T = len(self.GNNS)
+        if self.type == 'gat' and stack is not None and T > 1 and stack.n == T * x.shape[0]:
+            # batched over edge types: one stacked transform buffer, one block-diagonal GAT launch
+            N = x.shape[0]
+            h = ops.stacked_linear(x, [c.weight for c in self.GNNS])
+            att = torch.cat([c.att.reshape(1, -1) for c in self.GNNS], 0)
+            bias = torch.stack([c.bias for c in self.GNNS], 0)
+            o = ops.gat_conv(h, att, bias, stack.csr, self.GNNS[0].negative_slope, L.GAT_SOFTMAX_GROUP, n_block=N)
+            outs = o[:N]
+            for t in range(1, T):
+                outs = ops.add(outs, o[t * N:(t + 1) * N])
+            return outs
         outs = None
         for i, g in enumerate(batch_data.merge_higher_level['edges'].values()):
             conv = self.GNNS[i]

@@ -28,7 +28,7 @@ def _ws(nbytes, device):
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
 
-LONG_ROW_SEG = 32      # neighbours per work item: a sub-warp walks its item 4 neighbours at a time, so the
+LONG_ROW_SEG = int(__import__('os').environ.get('BIGNN_SEG', 32))      # neighbours per work item: a sub-warp walks its item 4 neighbours at a time, so the
                        # item length bounds the dependent-latency chain (8 steps); hub rows become many items
 
 
@@ -395,10 +395,13 @@ class _GatConv(torch.autograd.Function):
     """PyG 1.1.2 GATConv propagate, 1 head: out = edge_softmax-weighted sum of h + bias."""
 
     @staticmethod
-    def forward(ctx, h, att, bias, csr, slope, group_target):
+    def forward(ctx, h, att, bias, csr, slope, group_target, n_block=None):
         h = _f32c(h)
         _lib.require_device(h, att)
         n, D = h.shape
+        n_block = n if n_block is None else int(n_block)
+        att = att.contiguous()
+        bias = bias.contiguous() if bias is not None else None
         out = torch.empty_like(h)
         scratch = torch.empty(4 * max(n, 1), dtype=torch.float32, device=h.device)
         a = att.reshape(-1)
@@ -406,9 +409,10 @@ class _GatConv(torch.autograd.Function):
         wsb = _lib.call('bignn_gat_fwd_workspace_bytes', pl.n_items, D)
         ws = _ws(wsb, h.device)
         _lib.call('bignn_gat_fwd', csr.row_ptr, csr.col_idx, pl.item_ptr, pl.item_row, pl.n_items, pl.seg,
-                  pl.multi_rows, pl.n_multi, n, D, h, h.stride(0), a, bias, float(slope),
+                  pl.multi_rows, pl.n_multi, n, n_block, D, h, h.stride(0), a, bias, float(slope),
                   int(group_target), out, out.stride(0), scratch, ws, int(wsb))
-        ctx.csr, ctx.slope, ctx.group = csr, float(slope), int(group_target)
+        ctx.csr, ctx.slope, ctx.group, ctx.n_block = csr, float(slope), int(group_target), n_block
+        ctx.bias_shape = bias.shape if bias is not None else None
         ctx.att_shape = att.shape
         ctx.save_for_backward(h, a, bias, out, scratch)
         return out
@@ -424,11 +428,18 @@ class _GatConv(torch.autograd.Function):
         wsb = _lib.call('bignn_gat_bwd_workspace_bytes', n, D, pl.n_items)
         ws = _ws(wsb, h.device)
         _lib.call('bignn_gat_bwd', ctx.csr.row_ptr, ctx.csr.col_idx, pl.item_ptr, pl.item_row, pl.n_items, pl.seg,
-                  pl.multi_rows, pl.n_multi, n, D, h, h.stride(0), a, bias, ctx.slope,
+                  pl.multi_rows, pl.n_multi, n, ctx.n_block, D, h, h.stride(0), a, bias, ctx.slope,
                   ctx.group, out, out.stride(0), dout, dout.stride(0), scratch, dh, dh.stride(0), dpq, ws, int(wsb))
-        datt = gemm(dpq[:2 * n].view(2, n), h).reshape(ctx.att_shape) if ctx.needs_input_grad[1] else None
-        dbias = colsum(dout) if bias is not None and ctx.needs_input_grad[2] else None
-        return dh, datt, dbias, None, None, None
+        nb, T = ctx.n_block, n // ctx.n_block
+        datt = dbias = None
+        if ctx.needs_input_grad[1]:
+            v = dpq[:2 * n].view(2, n)
+            parts = [gemm(v[:, t * nb:(t + 1) * nb], h[t * nb:(t + 1) * nb]).reshape(1, 2 * D) for t in range(T)]
+            datt = (parts[0] if T == 1 else torch.cat(parts, 0)).reshape(ctx.att_shape)
+        if bias is not None and ctx.needs_input_grad[2]:
+            parts = [colsum(dout[t * nb:(t + 1) * nb]) for t in range(T)]
+            dbias = (parts[0] if T == 1 else torch.stack(parts, 0)).reshape(ctx.bias_shape)
+        return dh, datt, dbias, None, None, None, None
 
 
 class _Act(torch.autograd.Function):
@@ -568,10 +579,53 @@ def add(a, b):
     return _Add.apply(a, b)
 
 
-def gat_conv(h, att, bias, csr, negative_slope=0.2, group='source'):
+def gat_conv(h, att, bias, csr, negative_slope=0.2, group='source', n_block=None):
+    """n_block: several edge types batched as a block-diagonal graph (h [T*n_block, D], att [T, 2D],
+    bias [T, D]); None = one graph."""
     if group not in ('source', 'target'):
         raise ValueError('GAT softmax group must be source or target')
-    return _GatConv.apply(h, att, bias, csr, negative_slope, 1 if group == 'target' else 0)
+    return _GatConv.apply(h, att, bias, csr, negative_slope, 1 if group == 'target' else 0, n_block)
+
+
+class _StackedLinear(torch.autograd.Function):
+    """H[t*N:(t+1)*N] = x @ W_t for every edge type t (PyG weight layout [in, out]): the node
+    transforms of NodeModelAggrByEdge written into one stacked buffer for the batched GAT."""
+
+    @staticmethod
+    def forward(ctx, x, *weights):
+        x = _f32c(x)
+        N, T, D = x.shape[0], len(weights), weights[0].shape[1]
+        h = torch.empty((T * N, D), dtype=torch.float32, device=x.device)
+        for t, w in enumerate(weights):
+            dst = h[t * N:(t + 1) * N]
+            if use_tc(N, D, x.shape[1]):
+                gemm_tc(x, w, False, out=dst)
+            else:
+                gemm(x, w, False, False, out=dst)
+        ctx.save_for_backward(x, *weights)
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        x, *weights = ctx.saved_tensors
+        dh = _f32c(dh)
+        N = x.shape[0]
+        dx = None
+        dws = []
+        for t, w in enumerate(weights):
+            g = dh[t * N:(t + 1) * N]
+            if ctx.needs_input_grad[0]:
+                part = gemm_tc(g, w, True) if use_tc(N, x.shape[1], g.shape[1]) else gemm(g, w, False, True)
+                dx = part if dx is None else add(dx, part)
+            if ctx.needs_input_grad[1 + t]:
+                dws.append(dw_tc(x, g, -1)[0] if use_dw_tc(N, x.shape[1], g.shape[1]) else gemm(x, g, True, False))
+            else:
+                dws.append(None)
+        return (dx,) + tuple(dws)
+
+
+def stacked_linear(x, weights):
+    return _StackedLinear.apply(x, *weights)
 
 
 def activation(x, act):

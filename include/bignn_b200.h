@@ -244,18 +244,21 @@ int bignn_bce_logits_bwd(const float* x, const float* y, int32_t P, const float*
  * ------------------------------------------------------------------------- */
 /* Every neighbour pass runs over the work items of a row plan (see bignn_spmm_planned_f32: item_ptr,
  * item_row, multi_rows; rows of one item are finished in place, hub rows through per-item partials
- * combined in item order).  D <= 64, D % 4 == 0, 16-byte aligned rows. */
+ * combined in item order).  D <= 64, D % 4 == 0, 16-byte aligned rows.
+ * Several edge types (model/layers_meta.py:61-79) are batched as ONE block-diagonal graph of
+ * n / n_block blocks of n_block nodes: block b uses att[b, 2D] and bias[b, D] (n_block = n for a
+ * single graph). */
 int64_t bignn_gat_fwd_workspace_bytes(int32_t n_items, int32_t D);
 int bignn_gat_fwd(const int32_t* row_ptr, const int32_t* col_idx,
                   const int32_t* item_ptr, const int32_t* item_row, int32_t n_items, int32_t seg,
-                  const int32_t* multi_rows, int32_t n_multi, int32_t n, int32_t D,
+                  const int32_t* multi_rows, int32_t n_multi, int32_t n, int32_t n_block, int32_t D,
                   const float* H, int64_t ldh, const float* att, const float* bias,
                   float negative_slope, int32_t group_target, float* out, int64_t ldo,
                   float* scratch4n, void* workspace, int64_t workspace_bytes, void* stream);
 int64_t bignn_gat_bwd_workspace_bytes(int32_t n, int32_t D, int32_t n_items);
 int bignn_gat_bwd(const int32_t* row_ptr, const int32_t* col_idx,
                   const int32_t* item_ptr, const int32_t* item_row, int32_t n_items, int32_t seg,
-                  const int32_t* multi_rows, int32_t n_multi, int32_t n, int32_t D,
+                  const int32_t* multi_rows, int32_t n_multi, int32_t n, int32_t n_block, int32_t D,
                   const float* H, int64_t ldh, const float* att, const float* bias,
                   float negative_slope, int32_t group_target, const float* out, int64_t ldo,
                   const float* dOut, int64_t lddo, const float* scratch4n,
