@@ -89,3 +89,43 @@ def test_public_train_step_runs_and_learns(golden_dir, step_golden):
     ls = [eng.read_loss(eng.train_step(sampler)) for _ in range(30)]
     assert all(np.isfinite(ls))
     assert np.mean(ls[-5:]) < np.mean(ls[:5])
+
+
+def test_lower_pass_at_scale_matches_oracle_on_sampled_chunks():
+    """100 k molecule graphs (2.8 M atoms, 782 chunks of 128) through the batched lower pass in one
+    launch sequence; chunks are independent BatchNorm batches, so the pooled rows of a few sampled
+    chunks are compared with the CPU oracle run on those chunks alone (size-independent parity)."""
+    from bignn_b200 import synthetic as S
+    from oracle import bignn_oracle as O
+    G = 100_000
+    atom_ptr, nbr_ptr, nbr_idx, x = S.molecule_graphs(G, 28.0, seed=11)
+    w = dict(gids=np.arange(G, dtype=np.int64), atom_ptr=atom_ptr, nbr_ptr=nbr_ptr, nbr_idx=nbr_idx, x_u8=x,
+             ddi_row=np.asarray([0, 1], np.int32), ddi_col=np.asarray([1, 0], np.int32),
+             train_pairs=np.asarray([[0, 1]], np.int64), pair_keys=np.asarray([[0, 1]], np.int64),
+             pair_labels=np.ones(1, np.int8), num_labels=np.int64(2))
+    flags = B.make_flags(device=DEV)
+    B.set_flags(flags)
+    data = B.BiGNNData.from_npz(w, device=DEV)
+    torch.manual_seed(3)
+    model = B.Model(data).to(DEV)
+    model.train()
+    eng = BiGNNEngine(data, model, use_cuda_graph=False)
+    assert eng.merged.S == 782 and eng.merged.A == int(atom_ptr[-1])
+    with torch.no_grad():
+        pooled, acts = eng.lower_pass()
+    assert pooled.shape == (G + 1, 320) and bool(torch.isfinite(pooled).all())
+    # oracle on three chunks (first, middle, last) with the same weights
+    specs = O.parse_specs([getattr(flags, 'layer_%d' % i) for i in range(1, flags.layer_num + 1)])
+    state = {k: v.detach().cpu() for k, v in model.state_dict().items() if k.startswith('layers.')}
+    om = O.OracleModel(specs, state)
+    ds = O.PackedDataset(w)
+    chunks = O.all_drug_chunks(ds.gids.tolist(), 64)
+    assert len(chunks) == 782
+    for c in (0, 391, 781):
+        gids = O.unique_graphs_in_order(chunks[c])
+        m = O.merge_graphs(ds, gids)
+        with torch.no_grad():
+            _, want = om.lower(torch.from_numpy(m['x']), torch.from_numpy(m['edge_index']),
+                               torch.from_numpy(m['batch']), len(gids))
+        got = pooled[torch.as_tensor(np.asarray(gids)).to(DEV)]
+        assert rel(got, want) < 1e-5, c
