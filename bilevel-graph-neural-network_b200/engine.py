@@ -293,6 +293,32 @@ class BiGNNEngine(object):
         st.busy = False
         return float(st.loss)
 
+    @torch.no_grad()
+    def score_pairs(self, gid_pairs, recompute_init_x=True):
+        """Evaluation path (src/train.py:185-220): model.eval() statistics, one all-drug lower pass
+        (or the last training init_x, as the reference's validation does), one upper pass over the whole
+        interaction graph and ONE decoder launch over all given pairs -- instead of a full upper pass and
+        128 `.item()` syncs per 64-pair batch.  Returns the LinkPred outputs [P, 1] (or [P, K] logits)."""
+        model = self.model
+        was_training = model.training
+        model.eval()
+        try:
+            ig = self.data.interaction_combo_nxgraph
+            if recompute_init_x or ig.init_x is None:
+                pooled, _ = self.lower_pass()
+                ig.init_x = pooled[:self.data.N]
+            gs_map = self.data.gs_map
+            flat = np.fromiter((gs_map[g] for g in np.asarray(gid_pairs).reshape(-1).tolist()), np.int64)
+            P = flat.shape[0] // 2
+            sb = _StaticPairBatch(self.data, P, self.device)
+            sb.ids.copy_(torch.as_tensor(flat.reshape(P, 2).astype(np.int32)))
+            model.acts = [None]
+            for layer in model.higher_level_layers[:-1]:           # everything but the loss
+                model.acts.append(layer(model.acts[-1], sb, model))
+            return model.acts[-1]
+        finally:
+            model.train(was_training)
+
     def train_step(self, sampler):
         """Public API: sample (host, bit-exact with the reference), stage, run, return the
         staging slot (loss is read back asynchronously)."""

@@ -129,3 +129,24 @@ def test_lower_pass_at_scale_matches_oracle_on_sampled_chunks():
                                torch.from_numpy(m['batch']), len(gids))
         got = pooled[torch.as_tensor(np.asarray(gids)).to(DEV)]
         assert rel(got, want) < 1e-5, c
+
+
+def test_score_pairs_eval_mode_matches_oracle(golden_dir, step_golden, drugbank, gin_gcn_specs):
+    """evaluation path: running-statistics BatchNorm, all pairs scored in one decoder launch."""
+    from oracle import bignn_oracle as O
+    z = step_golden
+    data, model = fresh(golden_dir, z)
+    eng = BiGNNEngine(data, model, use_cuda_graph=False)
+    pairs = z['batch_gids']
+    got = eng.score_pairs(pairs)
+    assert got.shape == (128, 1)
+    sd = O.state_from_npz(z, 'sd0/')
+    for k in z.files:
+        if k.startswith('sd_init/'):
+            sd[k[len('sd_init/'):]] = torch.from_numpy(np.asarray(z[k]))
+    om = O.OracleModel(gin_gcn_specs, sd)
+    om.training = False
+    with torch.no_grad():
+        _, _, pred, _ = O.train_step_forward(om, drugbank, pairs, z['y_true'])
+    assert rel(got.view(-1), pred.view(-1)) < 1e-5
+    assert model.training
