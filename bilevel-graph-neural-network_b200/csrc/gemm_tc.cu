@@ -115,7 +115,7 @@ k_gemm_tc(int M, int N, int K, const float* __restrict__ A, int64_t lda, const f
     const int m0 = tile * TC_BM;
     // ---- this thread's cp.async chunks have landed; derive the lo operand from them (same chunks)
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-#pragma unroll 1
+#pragma unroll 4
     for (int j = tid; j < kch_used * 1024; j += TC_THREADS) {
       const int ch = j >> 10, idx = j & 1023;
       const uint32_t off = ch * A_BYTES + sw128_off(idx >> 3, idx & 7);

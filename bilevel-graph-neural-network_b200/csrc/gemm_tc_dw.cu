@@ -101,7 +101,7 @@ k_dw_tc(int M, int Np, int Nq, const float* __restrict__ P, int64_t ldp, const f
     // the other hi buffer was last read by the previous tile's MMAs, which have completed: refill it now
     if (tile + gridDim.x < n_tiles) prefetch_tile(tile + gridDim.x, buf ^ 1);
     // ---- lo = tf32(x - hi(x)) for the chunks this thread copied
-#pragma unroll 1
+#pragma unroll 4
     for (int j = tid; j < 4096; j += TC_THREADS) {
       const int op = j >> 11, idx = j & 2047;
       const uint32_t off = op * DW_TILE + (idx >> 10) * DW_BLK + sw32b_off((idx & 1023) >> 3, idx & 7);
