@@ -183,7 +183,39 @@ k_gemm_tc(int M, int N, int K, const float* __restrict__ A, int64_t lda, const f
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (c_vec) {
+    if (c_vec && N == NPAD && (NPAD == 32 || NPAD == 64 || NPAD == 128)) {
+      // fast path (the path's widths): 256 % (N/4) == 0, so a thread keeps one 16-byte column chunk for
+      // all its rows -- no integer division, bias loaded once, activation branch hoisted out of the loop
+      constexpr int N4 = NPAD / 4, RSTEP = TC_THREADS / N4;
+      const int c4 = tid % N4;
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (bias) b4 = ldg4(bias + 4 * c4);
+      const uint8_t* src = a_lo + (c4 >> 3) * A_BYTES;
+      const int rows_here = min(TC_BM, M - m0);
+      if (act == BIGNN_ACT_RELU) {
+#pragma unroll 4
+        for (int r = tid / N4; r < rows_here; r += RSTEP) {
+          float4 o = *reinterpret_cast<const float4*>(src + sw128_off(r, c4 & 7));
+          o.x = fmaxf(o.x + b4.x, 0.f); o.y = fmaxf(o.y + b4.y, 0.f); o.z = fmaxf(o.z + b4.z, 0.f); o.w = fmaxf(o.w + b4.w, 0.f);
+          st4(C + (int64_t)(m0 + r) * ldc + 4 * c4, o);
+        }
+      } else if (act == BIGNN_ACT_IDENTITY) {
+#pragma unroll 4
+        for (int r = tid / N4; r < rows_here; r += RSTEP) {
+          float4 o = *reinterpret_cast<const float4*>(src + sw128_off(r, c4 & 7));
+          o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+          st4(C + (int64_t)(m0 + r) * ldc + 4 * c4, o);
+        }
+      } else {
+#pragma unroll 1
+        for (int r = tid / N4; r < rows_here; r += RSTEP) {
+          float4 o = *reinterpret_cast<const float4*>(src + sw128_off(r, c4 & 7));
+          o.x = apply_act(o.x + b4.x, act); o.y = apply_act(o.y + b4.y, act);
+          o.z = apply_act(o.z + b4.z, act); o.w = apply_act(o.w + b4.w, act);
+          st4(C + (int64_t)(m0 + r) * ldc + 4 * c4, o);
+        }
+      }
+    } else if (c_vec) {
       const int n4 = N >> 2;
 #pragma unroll 1
       for (int idx = tid; idx < TC_BM * n4; idx += TC_THREADS) {
