@@ -207,7 +207,7 @@ def dense_roofline(torch, B, rows, peaks, device):
         out[tag] = dict(rows=M, ms_per_launch=ms, algorithmic_bytes=alg, achieved=ach, frac=ach / peak,
                         tflops_3xtf32=3 * 2.0 * M * 64 * 64 / (ms * 1e-3) / 1e12)
     return dict(kernel='k_gemm_tc<64,2> (bignn_gemm_tc_f32, tcgen05 kind::tf32 x3)', bound='hbm', peak=peak, unit='GB/s',
-                traffic_gt_l2_shape=0.977e9, **out)
+                traffic_gt_l2_shape=0.98e9, **out)
 
 
 def run_ours(args):
