@@ -137,7 +137,13 @@ k_merge_fill(const int32_t* __restrict__ atom_ptr, const int32_t* __restrict__ n
     if (x) {
       const int64_t src = (int64_t)a0 * F, dst = (int64_t)s0 * F;
       const int cnt = n * F;
-      for (int t = lane; t < cnt; t += 32) x[dst + t] = x_all[src + t];
+      if ((F & 3) == 0 && aligned16(x_all) && aligned16(x)) {       // whole graph block as 128-bit words
+        const float4* s4 = reinterpret_cast<const float4*>(x_all + src);
+        float4* d4 = reinterpret_cast<float4*>(x + dst);
+        for (int t = lane; t < (cnt >> 2); t += 32) d4[t] = __ldg(s4 + t);
+      } else {
+        for (int t = lane; t < cnt; t += 32) x[dst + t] = x_all[src + t];
+      }
     }
     if (g == G - 1 && lane == 0) row_ptr[s0 + n] = E0 + (nbr_ptr[a0 + n] - e0);
   }
