@@ -13,8 +13,9 @@ fold 1 with set_seed(3+5) (reference src/main.py:42):
                         state_dict after the Adam step.
   sampler_seq.npz       24 consecutive steps of positive batches, negative
                         samples (order included) and labels.
-  micro_*.npz           known-answer micro cases (P3 path, star, two components,
-                        isolated node, duplicate/self-loop coalesce input).
+(Known-answer micro cases -- P3 path, star, two components, isolated node,
+duplicate / self-loop coalesce input -- are written out by hand in
+tests/test_known_answers_cpu.py and tests/test_gpu_kernels.py.)
 
 Usage:  python oracle/make_golden.py [--out tests/golden] [--config gin_gcn|gat_gat|...]
 The reference cannot travel to the GPU box, hence the committed fixtures.

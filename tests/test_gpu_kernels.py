@@ -166,6 +166,29 @@ def test_spmm_long_rows_planned(mode):
                                      bias.to(DEV) if mode == 'gcn' else None, 1 if mode == 'gcn' else 0))  # deterministic
 
 
+def test_spmm_known_answers_small_graphs():
+    """P3 path, star + second component + isolated node, self-loop input: results written by hand."""
+    # P3: 0 - 1 - 2, x = [1, 10, 100] in every column
+    csr = csr_from_coo(np.asarray([0, 1, 1, 2]), np.asarray([1, 0, 2, 1]), 3)
+    x = torch.tensor([[1.0], [10.0], [100.0]]).repeat(1, 64).to(DEV)
+    assert ops.spmm(csr, x, ops.SPMM_GIN, 1.0)[:, 0].tolist() == [11.0, 111.0, 110.0]
+    assert ops.spmm(csr, x, ops.SPMM_SUM)[:, 7].tolist() == [10.0, 101.0, 10.0]
+    d = torch.tensor([2.0, 3.0, 2.0]).pow(-0.5)
+    want = torch.stack([d[0] * d[0] * 1 + d[0] * d[1] * 10, d[1] * d[0] * 1 + d[1] * d[1] * 10 + d[1] * d[2] * 100,
+                        d[2] * d[1] * 10 + d[2] * d[2] * 100])
+    got = ops.spmm(csr, x, ops.SPMM_GCN, 0.0, csr.dinv())[:, 63].cpu()
+    assert torch.allclose(got, want, rtol=1e-6)
+    # star (0; 1,2,3) + edge 4-5 + isolated 6, and an explicit self loop on node 4 that GIN/GCN must drop
+    row = np.asarray([0, 0, 0, 1, 2, 3, 4, 4, 5]); col = np.asarray([1, 2, 3, 0, 0, 0, 4, 5, 4])
+    csr = csr_from_coo(row, col, 7)
+    x = torch.arange(1.0, 8.0).view(7, 1).repeat(1, 16).to(DEV)
+    assert ops.spmm(csr, x, ops.SPMM_GIN, 1.0)[:, 3].tolist() == [10.0, 3.0, 4.0, 5.0, 11.0, 11.0, 7.0]
+    assert ops.spmm(csr, x, ops.SPMM_SUM)[:, 3].tolist() == [9.0, 1.0, 1.0, 1.0, 11.0, 5.0, 0.0]   # SUM keeps the loop
+    got = ops.spmm(csr, x, ops.SPMM_GCN, 0.0, csr.dinv())[:, 0].cpu()
+    assert abs(float(got[6]) - 7.0) < 1e-6 and abs(float(got[4]) - (0.5 * 5 + 0.5 * 6)) < 1e-6
+    assert csr.dinv().cpu().tolist() == [0.5, 2 ** -0.5, 2 ** -0.5, 2 ** -0.5, 2 ** -0.5, 2 ** -0.5, 1.0]
+
+
 def test_spmm_is_its_own_transpose_at_scale():
     """size-independent property on a >L2 operand: <y, A x> == <A y, x> for a symmetric graph,
     and A*ones == degree (+ self coefficient) exactly."""
