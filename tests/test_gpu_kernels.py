@@ -186,7 +186,7 @@ def test_spmm_known_answers_small_graphs():
     assert ops.spmm(csr, x, ops.SPMM_SUM)[:, 3].tolist() == [9.0, 1.0, 1.0, 1.0, 11.0, 5.0, 0.0]   # SUM keeps the loop
     got = ops.spmm(csr, x, ops.SPMM_GCN, 0.0, csr.dinv())[:, 0].cpu()
     assert abs(float(got[6]) - 7.0) < 1e-6 and abs(float(got[4]) - (0.5 * 5 + 0.5 * 6)) < 1e-6
-    assert csr.dinv().cpu().tolist() == [0.5, 2 ** -0.5, 2 ** -0.5, 2 ** -0.5, 2 ** -0.5, 2 ** -0.5, 1.0]
+    assert torch.equal(csr.dinv().cpu(), torch.tensor([4.0, 2.0, 2.0, 2.0, 2.0, 2.0, 1.0]).pow(-0.5))
 
 
 def test_spmm_is_its_own_transpose_at_scale():
