@@ -33,6 +33,8 @@ SIGNATURES = {
     'bignn_merge_build': ('i', 'pppp' 'i' 'p' 'i' 'pp' 'ppp' 'ppp' 'ii' 'pl' 's'),
     'bignn_gcn_dinv': ('i', 'ppips'),
     'bignn_spmm_f32': ('i', 'pp' 'pl' 'pl' 'iiif' 'ppi' 's'),
+    'bignn_spmm_rows_f32': ('i', 'pp' 'pl' 'pl' 'iiiif' 'ppi' 's'),
+    'bignn_spmm_planned_rows_f32': ('i', 'pp' 'ppii' 'pi' 'pl' 'pl' 'iiiif' 'ppi' 'pl' 's'),
     'bignn_spmm_planned_workspace_bytes': ('l', 'ii'),
     'bignn_spmm_planned_f32': ('i', 'pp' 'ppii' 'pi' 'pl' 'pl' 'iiif' 'ppi' 'pl' 's'),
     'bignn_gemm_workspace_bytes': ('l', 'iiii'),
@@ -50,6 +52,10 @@ SIGNATURES = {
     'bignn_bn_running_update': ('i', 'ppiifppp' 's'),
     'bignn_bn_eval_fwd': ('i', 'plpl' 'ii' 'pp' 'f' 'pp' 's'),
     'bignn_bn_seg_bwd': ('i', 'plplpl' 'piii' 'ppp' 'pp' 'pl' 's'),
+    'bignn_bn_rows_workspace_bytes': ('l', 'ii'),
+    'bignn_bn_rows_sums': ('i', 'plpl' 'iii' 'ppp' 'pl' 's'),
+    'bignn_bn_rows_fwd_apply': ('i', 'plpl' 'iii' 'pl' 'pp' 'ff' 'ppp' 'pp' 's'),
+    'bignn_bn_rows_bwd_apply': ('i', 'plplpl' 'iii' 'ppp' 'pl' 's'),
     'bignn_readout_fwd': ('i', 'pl' 'pii' 'i' 'p' 'pli' 's'),
     'bignn_readout_bwd': ('i', 'pli' 'p' 'pii' 'i' 'pl' 'i' 's'),
     'bignn_pair_gather_norm_fwd': ('i', 'pl' 'pii' 'pl' 'p' 's'),

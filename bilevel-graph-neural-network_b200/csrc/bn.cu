@@ -15,9 +15,10 @@ namespace bignn {
 
 constexpr int BN_ROWS = 8;
 
-__device__ __forceinline__ void part_range(const int32_t* __restrict__ seg_row_ptr, int s, int p, int parts,
+// seg_row_ptr == nullptr: one segment made of rows [0, rows) (the row-partitioned upper level)
+__device__ __forceinline__ void part_range(const int32_t* __restrict__ seg_row_ptr, int rows, int s, int p, int parts,
                                            int& r0, int& r1, int& n) {
-  const int a = seg_row_ptr[s], b = seg_row_ptr[s + 1];
+  const int a = seg_row_ptr ? seg_row_ptr[s] : 0, b = seg_row_ptr ? seg_row_ptr[s + 1] : rows;
   n = b - a;
   r0 = a + (int)(((int64_t)n * p) / parts);
   r1 = a + (int)(((int64_t)n * (p + 1)) / parts);
@@ -30,14 +31,14 @@ __global__ void __launch_bounds__(256)
 k_bn_reduce_part(const float* __restrict__ X, int64_t ldx, const float* __restrict__ dY, int64_t lddy,
                  const int32_t* __restrict__ seg_row_ptr, int C, int parts,
                  const float* __restrict__ mean, const float* __restrict__ rstd,
-                 double* __restrict__ ws_a, double* __restrict__ ws_b) {
+                 double* __restrict__ ws_a, double* __restrict__ ws_b, int rows) {
   __shared__ double ra[BN_ROWS][33];
   __shared__ double rb[BN_ROWS][33];
   const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
   const int c = blockIdx.y * 32 + tx;
   const int s = blockIdx.x / parts, p = blockIdx.x % parts;
   int r0, r1, n;
-  part_range(seg_row_ptr, s, p, parts, r0, r1, n);
+  part_range(seg_row_ptr, rows, s, p, parts, r0, r1, n);
   double a = 0.0, b = 0.0;
   if (c < C) {
     float mu = 0.f, rs = 0.f;
@@ -120,12 +121,12 @@ __global__ void __launch_bounds__(256)
 k_bn_apply(const float* __restrict__ X, int64_t ldx, float* __restrict__ Y, int64_t ldy,
            const int32_t* __restrict__ seg_row_ptr, int C, int parts,
            const float* __restrict__ gamma, const float* __restrict__ beta,
-           const float* __restrict__ mean, const float* __restrict__ rstd) {
+           const float* __restrict__ mean, const float* __restrict__ rstd, int rows) {
   const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
   const int c = blockIdx.y * 32 + tx;
   const int s = blockIdx.x / parts, p = blockIdx.x % parts;
   int r0, r1, n;
-  part_range(seg_row_ptr, s, p, parts, r0, r1, n);
+  part_range(seg_row_ptr, rows, s, p, parts, r0, r1, n);
   if (c >= C) return;
   const float alpha = rstd[(int64_t)s * C + c] * (gamma ? gamma[c] : 1.f);
   const float bt = (beta ? beta[c] : 0.f) - mean[(int64_t)s * C + c] * alpha;
@@ -179,22 +180,61 @@ __global__ void __launch_bounds__(256)
 k_bn_bwd_apply(const float* __restrict__ X, int64_t ldx, const float* __restrict__ dY, int64_t lddy,
                float* __restrict__ dX, int64_t lddx, const int32_t* __restrict__ seg_row_ptr, int C, int parts,
                const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
-               const double* __restrict__ seg_a, const double* __restrict__ seg_b) {
+               const double* __restrict__ seg_a, const double* __restrict__ seg_b, int rows, int64_t n_total) {
   const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
   const int c = blockIdx.y * 32 + tx;
   const int s = blockIdx.x / parts, p = blockIdx.x % parts;
   int r0, r1, n;
-  part_range(seg_row_ptr, s, p, parts, r0, r1, n);
+  part_range(seg_row_ptr, rows, s, p, parts, r0, r1, n);
   if (c >= C || n <= 0) return;
   const float mu = mean[(int64_t)s * C + c], rs = rstd[(int64_t)s * C + c];
-  const float gmean = (float)(seg_a[(int64_t)s * C + c] / n);
-  const float dgn = (float)(seg_b[(int64_t)s * C + c] / n);
+  const double cnt = n_total > 0 ? (double)n_total : (double)n;    // n_total: the batch spans several ranks
+  const float gmean = (float)(seg_a[(int64_t)s * C + c] / cnt);
+  const float dgn = (float)(seg_b[(int64_t)s * C + c] / cnt);
   const float scale = rs * (gamma ? gamma[c] : 1.f);
   for (int r = r0 + ty; r < r1; r += BN_ROWS) {
     const float xhat = (__ldg(X + (int64_t)r * ldx + c) - mu) * rs;
     const float g = __ldg(dY + (int64_t)r * lddy + c);
     dX[(int64_t)r * lddx + c] = (g - gmean - xhat * dgn) * scale;
   }
+}
+
+// ---- row-partitioned batch (upper level sharded by source drug): one batch spans the rows of all ranks.
+// sums[0..C) = sum of parts of ws_a, sums[C..2C) = of ws_b, parts added in part order
+__global__ void __launch_bounds__(256)
+k_bn_rows_sum_parts(const double* __restrict__ ws_a, const double* __restrict__ ws_b, int C, int parts,
+                    double* __restrict__ sums) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double a = 0.0, b = 0.0;
+#pragma unroll 8
+  for (int p = 0; p < parts; ++p) { a += ws_a[(int64_t)p * C + c]; b += ws_b[(int64_t)p * C + c]; }
+  sums[c] = a;
+  sums[C + c] = b;
+}
+
+// statistics of the whole batch from the rank-summed (sum x, sum x^2); one momentum update
+__global__ void __launch_bounds__(256)
+k_bn_rows_finalize(const double* __restrict__ sums, int64_t n_total, int C, float eps, double momentum,
+                   float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ running_mean,
+                   float* __restrict__ running_var, int64_t* __restrict__ nbt) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    double mu = 0.0, var = 0.0;
+    if (n_total > 0) {
+      mu = sums[c] / (double)n_total;
+      var = sums[C + c] / (double)n_total - mu * mu;
+      if (var < 0.0) var = 0.0;
+    }
+    mean[c] = (float)mu;
+    rstd[c] = n_total > 0 ? (float)(1.0 / sqrt(var + (double)eps)) : 0.f;
+    if (running_mean && running_var && n_total > 0) {
+      const double varu = n_total > 1 ? var * ((double)n_total / (double)(n_total - 1)) : var;
+      running_mean[c] = (float)(momentum * mu + (1.0 - momentum) * (double)running_mean[c]);
+      running_var[c] = (float)(momentum * varu + (1.0 - momentum) * (double)running_var[c]);
+    }
+  }
+  if (c == 0 && nbt && running_mean && n_total > 0) *nbt += 1;
 }
 
 }  // namespace bignn
@@ -222,14 +262,14 @@ extern "C" int bignn_bn_seg_fwd(const float* X, int64_t ldx, float* Y, int64_t l
   double* mean_d = seg_stats_out ? seg_stats_out : ws_b + (int64_t)S * parts * C;
   double* varu_d = mean_d + (int64_t)S * C;
   dim3 grid(S * parts, ceil_div(C, 32));
-  k_bn_reduce_part<false><<<grid, 256, 0, st>>>(X, ldx, nullptr, 0, seg_row_ptr, C, parts, nullptr, nullptr, ws_a, ws_b);
+  k_bn_reduce_part<false><<<grid, 256, 0, st>>>(X, ldx, nullptr, 0, seg_row_ptr, C, parts, nullptr, nullptr, ws_a, ws_b, 0);
   k_bn_finalize<<<(int)ceil_div<int64_t>((int64_t)S * C, 256), 256, 0, st>>>(ws_a, ws_b, seg_row_ptr, S, C, parts, eps, mean, rstd, mean_d, varu_d);
   BIGNN_LAUNCH_COUNT(2);
   if (running_mean && running_var) {
     k_bn_running<<<ceil_div(C, 256), 256, 0, st>>>(mean_d, varu_d, seg_row_ptr, S, C, (double)momentum, running_mean, running_var, num_batches_tracked);
     BIGNN_LAUNCH_COUNT(1);
   }
-  k_bn_apply<<<grid, 256, 0, st>>>(X, ldx, Y, ldy, seg_row_ptr, C, parts, gamma, beta, mean, rstd);
+  k_bn_apply<<<grid, 256, 0, st>>>(X, ldx, Y, ldy, seg_row_ptr, C, parts, gamma, beta, mean, rstd, 0);
   BIGNN_LAUNCH_COUNT(1);
   return last_launch_status();
 }
@@ -277,10 +317,70 @@ extern "C" int bignn_bn_seg_bwd(const float* X, int64_t ldx, const float* dY, in
   double* seg_a = ws_b + (int64_t)S * parts * C;
   double* seg_b = seg_a + (int64_t)S * C;
   dim3 grid(S * parts, ceil_div(C, 32));
-  k_bn_reduce_part<true><<<grid, 256, 0, st>>>(X, ldx, dY, lddy, seg_row_ptr, C, parts, mean, rstd, ws_a, ws_b);
+  k_bn_reduce_part<true><<<grid, 256, 0, st>>>(X, ldx, dY, lddy, seg_row_ptr, C, parts, mean, rstd, ws_a, ws_b, 0);
   k_bn_bwd_finalize<<<(int)ceil_div<int64_t>((int64_t)S * C, 256), 256, 0, st>>>(ws_a, ws_b, S, C, parts, seg_a, seg_b);
   k_bn_bwd_params<<<ceil_div(C, 256), 256, 0, st>>>(seg_a, seg_b, S, C, dgamma, dbeta);
-  k_bn_bwd_apply<<<grid, 256, 0, st>>>(X, ldx, dY, lddy, dX, lddx, seg_row_ptr, C, parts, gamma, mean, rstd, seg_a, seg_b);
+  k_bn_bwd_apply<<<grid, 256, 0, st>>>(X, ldx, dY, lddy, dX, lddx, seg_row_ptr, C, parts, gamma, mean, rstd, seg_a, seg_b, 0, 0);
   BIGNN_LAUNCH_COUNT(4);
+  return last_launch_status();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Row-partitioned BatchNorm (multi-GPU upper level): local sums -> (caller: all-reduce) -> apply.
+extern "C" int64_t bignn_bn_rows_workspace_bytes(int32_t C, int32_t parts) {
+  if (C <= 0 || parts <= 0) return 0;
+  return (int64_t)sizeof(double) * 2 * (int64_t)parts * C;
+}
+
+extern "C" int bignn_bn_rows_sums(const float* X, int64_t ldx, const float* dY, int64_t lddy, int32_t rows,
+                                  int32_t C, int32_t parts, const float* mean, const float* rstd, double* sums,
+                                  void* workspace, int64_t workspace_bytes, void* stream) {
+  if (rows < 0 || C < 0 || parts <= 0) return BIGNN_EINVAL;
+  if (C == 0) return 0;
+  if (!sums || (rows > 0 && (!X || ldx < C))) return BIGNN_EINVAL;
+  if (dY && (!mean || !rstd || lddy < C)) return BIGNN_EINVAL;
+  if (!workspace || workspace_bytes < bignn_bn_rows_workspace_bytes(C, parts)) return BIGNN_EWORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  double* ws_a = (double*)workspace;
+  double* ws_b = ws_a + (int64_t)parts * C;
+  dim3 grid(parts, ceil_div(C, 32));
+  if (dY) k_bn_reduce_part<true><<<grid, 256, 0, st>>>(X, ldx, dY, lddy, nullptr, C, parts, mean, rstd, ws_a, ws_b, rows);
+  else k_bn_reduce_part<false><<<grid, 256, 0, st>>>(X, ldx, nullptr, 0, nullptr, C, parts, nullptr, nullptr, ws_a, ws_b, rows);
+  k_bn_rows_sum_parts<<<ceil_div(C, 256), 256, 0, st>>>(ws_a, ws_b, C, parts, sums);
+  BIGNN_LAUNCH_COUNT(2);
+  return last_launch_status();
+}
+
+extern "C" int bignn_bn_rows_fwd_apply(const float* X, int64_t ldx, float* Y, int64_t ldy, int32_t rows, int32_t C,
+                                       int32_t parts, const double* sums, int64_t n_total, const float* gamma,
+                                       const float* beta, float eps, float momentum, float* running_mean,
+                                       float* running_var, int64_t* num_batches_tracked, float* mean, float* rstd,
+                                       void* stream) {
+  if (rows < 0 || C < 0 || parts <= 0 || n_total < rows) return BIGNN_EINVAL;
+  if (C == 0) return 0;
+  if (!sums || !mean || !rstd || (rows > 0 && (!X || !Y || ldx < C || ldy < C))) return BIGNN_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  k_bn_rows_finalize<<<ceil_div(C, 256), 256, 0, st>>>(sums, n_total, C, eps, (double)momentum, mean, rstd,
+                                                        running_mean, running_var, num_batches_tracked);
+  BIGNN_LAUNCH_COUNT(1);
+  if (rows > 0) {
+    dim3 grid(parts, ceil_div(C, 32));
+    k_bn_apply<<<grid, 256, 0, st>>>(X, ldx, Y, ldy, nullptr, C, parts, gamma, beta, mean, rstd, rows);
+    BIGNN_LAUNCH_COUNT(1);
+  }
+  return last_launch_status();
+}
+
+extern "C" int bignn_bn_rows_bwd_apply(const float* X, int64_t ldx, const float* dY, int64_t lddy, float* dX,
+                                       int64_t lddx, int32_t rows, int32_t C, int32_t parts, const float* gamma,
+                                       const float* mean, const float* rstd, const double* sums, int64_t n_total,
+                                       void* stream) {
+  if (rows < 0 || C < 0 || parts <= 0 || n_total < rows) return BIGNN_EINVAL;
+  if (rows == 0 || C == 0) return 0;
+  if (!X || !dY || !dX || !mean || !rstd || !sums || ldx < C || lddy < C || lddx < C) return BIGNN_EINVAL;
+  dim3 grid(parts, ceil_div(C, 32));
+  k_bn_bwd_apply<<<grid, 256, 0, (cudaStream_t)stream>>>(X, ldx, dY, lddy, dX, lddx, nullptr, C, parts, gamma, mean,
+                                                          rstd, sums, sums + C, rows, n_total);
+  BIGNN_LAUNCH_COUNT(1);
   return last_launch_status();
 }

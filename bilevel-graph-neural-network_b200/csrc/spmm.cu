@@ -64,7 +64,7 @@ __device__ __forceinline__ void accumulate_range(float4 (&acc)[NV], int k0, int 
 
 // self term, bias, activation, store
 template <int L, int NV, int MODE>
-__device__ __forceinline__ void finish_row(float4 (&acc)[NV], int row, int lane, int D4, float self_coef, float di,
+__device__ __forceinline__ void finish_row(float4 (&acc)[NV], int row, int grow, int lane, int D4, float self_coef, float di,
                                            const float* __restrict__ X, int64_t ldx, float* __restrict__ Y,
                                            int64_t ldy, const float* __restrict__ bias, int act) {
 #pragma unroll
@@ -73,11 +73,11 @@ __device__ __forceinline__ void finish_row(float4 (&acc)[NV], int row, int lane,
     if (q >= D4) continue;
     float4 a = acc[v];
     if (MODE == BIGNN_SPMM_GIN) {
-      const float4 s = ldg4(X + (int64_t)row * ldx + 4 * q);
+      const float4 s = ldg4(X + (int64_t)grow * ldx + 4 * q);
       a.x = __fadd_rn(__fmul_rn(self_coef, s.x), a.x); a.y = __fadd_rn(__fmul_rn(self_coef, s.y), a.y);
       a.z = __fadd_rn(__fmul_rn(self_coef, s.z), a.z); a.w = __fadd_rn(__fmul_rn(self_coef, s.w), a.w);
     } else if (MODE == BIGNN_SPMM_GCN) {
-      const float4 s = ldg4(X + (int64_t)row * ldx + 4 * q);
+      const float4 s = ldg4(X + (int64_t)grow * ldx + 4 * q);
       acc_add_scaled(a, __fmul_rn(di, di), s);       // self loop is the last COO entry
     }
     if (bias) {
@@ -96,19 +96,20 @@ __global__ void __launch_bounds__(256)
 k_spmm_v4(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx,
           const float* __restrict__ X, int64_t ldx, float* __restrict__ Y, int64_t ldy,
           int n_rows, int D4, float self_coef, const float* __restrict__ dinv,
-          const float* __restrict__ bias, int act) {
+          const float* __restrict__ bias, int act, int roff) {
   const int rpb = blockDim.x / L;
   const int sub = threadIdx.x / L;
   const int lane = threadIdx.x % L;
   for (int row = blockIdx.x * rpb + sub; row < n_rows; row += gridDim.x * rpb) {
+    const int grow = row + roff;          // row id in the column (node) index space
     const int k0 = __ldg(row_ptr + row), k1 = __ldg(row_ptr + row + 1);
     float4 acc[NV];
 #pragma unroll
     for (int v = 0; v < NV; ++v) acc[v] = f4zero();
     float di = 0.f;
-    if (MODE == BIGNN_SPMM_GCN) di = __ldg(dinv + row);
-    accumulate_range<L, NV, MODE>(acc, k0, k1, row, lane, D4, di, col_idx, X, ldx, dinv);
-    finish_row<L, NV, MODE>(acc, row, lane, D4, self_coef, di, X, ldx, Y, ldy, bias, act);
+    if (MODE == BIGNN_SPMM_GCN) di = __ldg(dinv + grow);
+    accumulate_range<L, NV, MODE>(acc, k0, k1, grow, lane, D4, di, col_idx, X, ldx, dinv);
+    finish_row<L, NV, MODE>(acc, row, grow, lane, D4, self_coef, di, X, ldx, Y, ldy, bias, act);
   }
 }
 
@@ -123,7 +124,7 @@ k_spmm_items_v4(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__
                 const int32_t* __restrict__ item_ptr, const int32_t* __restrict__ item_row, int n_items, int seg,
                 const float* __restrict__ X, int64_t ldx, float* __restrict__ Y, int64_t ldy,
                 int D4, float self_coef, const float* __restrict__ dinv, const float* __restrict__ bias, int act,
-                float* __restrict__ partial) {
+                float* __restrict__ partial, int roff) {
   const int ipb = blockDim.x / L;
   const int sub = threadIdx.x / L;
   const int lane = threadIdx.x % L;
@@ -136,11 +137,12 @@ k_spmm_items_v4(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__
     float4 acc[NV];
 #pragma unroll
     for (int v = 0; v < NV; ++v) acc[v] = f4zero();
+    const int grow = row + roff;
     float di = 0.f;
-    if (MODE == BIGNN_SPMM_GCN) di = __ldg(dinv + row);
-    accumulate_range<L, NV, MODE>(acc, k0, k1, row, lane, D4, di, col_idx, X, ldx, dinv);
+    if (MODE == BIGNN_SPMM_GCN) di = __ldg(dinv + grow);
+    accumulate_range<L, NV, MODE>(acc, k0, k1, grow, lane, D4, di, col_idx, X, ldx, dinv);
     if (i1 - i0 == 1) {
-      finish_row<L, NV, MODE>(acc, row, lane, D4, self_coef, di, X, ldx, Y, ldy, bias, act);
+      finish_row<L, NV, MODE>(acc, row, grow, lane, D4, self_coef, di, X, ldx, Y, ldy, bias, act);
     } else {
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
@@ -156,7 +158,7 @@ __global__ void __launch_bounds__(256)
 k_spmm_multi_v4(const int32_t* __restrict__ item_ptr, const int32_t* __restrict__ multi_rows, int n_multi,
                 const float* __restrict__ X, int64_t ldx, float* __restrict__ Y, int64_t ldy,
                 int D4, float self_coef, const float* __restrict__ dinv, const float* __restrict__ bias, int act,
-                const float* __restrict__ partial) {
+                const float* __restrict__ partial, int roff) {
   const int rpb = blockDim.x / L;
   const int sub = threadIdx.x / L;
   const int lane = threadIdx.x % L;
@@ -174,8 +176,8 @@ k_spmm_multi_v4(const int32_t* __restrict__ item_ptr, const int32_t* __restrict_
       }
     }
     float di = 0.f;
-    if (MODE == BIGNN_SPMM_GCN) di = __ldg(dinv + row);
-    finish_row<L, NV, MODE>(acc, row, lane, D4, self_coef, di, X, ldx, Y, ldy, bias, act);
+    if (MODE == BIGNN_SPMM_GCN) di = __ldg(dinv + row + roff);
+    finish_row<L, NV, MODE>(acc, row, row + roff, lane, D4, self_coef, di, X, ldx, Y, ldy, bias, act);
   }
 }
 
@@ -185,7 +187,7 @@ __global__ void __launch_bounds__(256)
 k_spmm_scalar(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx,
               const float* __restrict__ X, int64_t ldx, float* __restrict__ Y, int64_t ldy,
               int n_rows, int D, float self_coef, const float* __restrict__ dinv,
-              const float* __restrict__ bias, int act) {
+              const float* __restrict__ bias, int act, int roff) {
   constexpr int U = 4;
   const int rpb = blockDim.x / 32;
   const int sub = threadIdx.x / 32;
@@ -195,8 +197,9 @@ k_spmm_scalar(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ c
     float acc[NS];
 #pragma unroll
     for (int s = 0; s < NS; ++s) acc[s] = 0.f;
+    const int grow = row + roff;
     float di = 0.f;
-    if (MODE == BIGNN_SPMM_GCN) di = __ldg(dinv + row);
+    if (MODE == BIGNN_SPMM_GCN) di = __ldg(dinv + grow);
     for (int k = k0; k < k1; k += U) {
       int c[U];
       float w[U];
@@ -204,7 +207,7 @@ k_spmm_scalar(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ c
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         c[u] = (k + u < k1) ? __ldg(col_idx + k + u) : -1;
-        if (MODE != BIGNN_SPMM_SUM && c[u] == row) c[u] = -1;
+        if (MODE != BIGNN_SPMM_SUM && c[u] == grow) c[u] = -1;
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -232,9 +235,9 @@ k_spmm_scalar(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ c
       if (q >= D) continue;
       float a = acc[s];
       if (MODE == BIGNN_SPMM_GIN) {
-        a = __fadd_rn(__fmul_rn(self_coef, __ldg(X + (int64_t)row * ldx + q)), a);
+        a = __fadd_rn(__fmul_rn(self_coef, __ldg(X + (int64_t)grow * ldx + q)), a);
       } else if (MODE == BIGNN_SPMM_GCN) {
-        a = __fadd_rn(a, __fmul_rn(__fmul_rn(di, di), __ldg(X + (int64_t)row * ldx + q)));
+        a = __fadd_rn(a, __fmul_rn(__fmul_rn(di, di), __ldg(X + (int64_t)grow * ldx + q)));
       }
       if (bias) a = __fadd_rn(a, __ldg(bias + q));
       a = apply_act(a, act);
@@ -258,7 +261,7 @@ k_gcn_dinv(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col_
 template <int MODE>
 static int launch_mode(const int32_t* row_ptr, const int32_t* col_idx, const float* X, int64_t ldx,
                        float* Y, int64_t ldy, int n_rows, int D, float self_coef, const float* dinv,
-                       const float* bias, int act, cudaStream_t st) {
+                       const float* bias, int act, int roff, cudaStream_t st) {
   const bool vec = (D % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && aligned16(X) && aligned16(Y) &&
                    (bias == nullptr || aligned16(bias));
   const int cap = sm_count() * 8;
@@ -275,7 +278,7 @@ static int launch_mode(const int32_t* row_ptr, const int32_t* col_idx, const flo
     int grid = ceil_div(n_rows, rpb);                                                         \
     if (grid > cap) grid = cap;                                                               \
     k_spmm_v4<L, NV, MODE><<<grid, 256, 0, st>>>(row_ptr, col_idx, Xb, ldx, Yb, ldy, n_rows, d4, \
-                                                 self_coef, dinv, bb, act);                   \
+                                                 self_coef, dinv, bb, act, roff);             \
   }
       if (d4 <= 8) BIGNN_SPMM_LAUNCH(8, 1)
       else if (d4 <= 16) BIGNN_SPMM_LAUNCH(16, 1)
@@ -292,9 +295,9 @@ static int launch_mode(const int32_t* row_ptr, const int32_t* col_idx, const flo
       int grid = ceil_div(n_rows, 8);
       if (grid > cap) grid = cap;
       const float* bb = bias ? bias + c0 : nullptr;
-      if (d <= 32) k_spmm_scalar<1, MODE><<<grid, 256, 0, st>>>(row_ptr, col_idx, X + c0, ldx, Y + c0, ldy, n_rows, d, self_coef, dinv, bb, act);
-      else if (d <= 64) k_spmm_scalar<2, MODE><<<grid, 256, 0, st>>>(row_ptr, col_idx, X + c0, ldx, Y + c0, ldy, n_rows, d, self_coef, dinv, bb, act);
-      else k_spmm_scalar<4, MODE><<<grid, 256, 0, st>>>(row_ptr, col_idx, X + c0, ldx, Y + c0, ldy, n_rows, d, self_coef, dinv, bb, act);
+      if (d <= 32) k_spmm_scalar<1, MODE><<<grid, 256, 0, st>>>(row_ptr, col_idx, X + c0, ldx, Y + c0, ldy, n_rows, d, self_coef, dinv, bb, act, roff);
+      else if (d <= 64) k_spmm_scalar<2, MODE><<<grid, 256, 0, st>>>(row_ptr, col_idx, X + c0, ldx, Y + c0, ldy, n_rows, d, self_coef, dinv, bb, act, roff);
+      else k_spmm_scalar<4, MODE><<<grid, 256, 0, st>>>(row_ptr, col_idx, X + c0, ldx, Y + c0, ldy, n_rows, d, self_coef, dinv, bb, act, roff);
       BIGNN_LAUNCH_COUNT(1);
     }
   }
@@ -306,7 +309,7 @@ template <int MODE>
 static int launch_planned(const int32_t* row_ptr, const int32_t* col_idx, const int32_t* item_ptr,
                           const int32_t* item_row, int n_items, int seg, const int32_t* multi_rows, int n_multi,
                           const float* X, int64_t ldx, float* Y, int64_t ldy, int D, float self_coef,
-                          const float* dinv, const float* bias, int act, float* partial, cudaStream_t st) {
+                          const float* dinv, const float* bias, int act, float* partial, int roff, cudaStream_t st) {
   const int cap = sm_count() * 8;
   const int d4 = D / 4;
 #define BIGNN_PLANNED(L, NV)                                                                          \
@@ -315,13 +318,13 @@ static int launch_planned(const int32_t* row_ptr, const int32_t* col_idx, const 
     int grid = ceil_div(n_items, per);                                                                \
     if (grid > cap) grid = cap;                                                                       \
     k_spmm_items_v4<L, NV, MODE><<<grid, 256, 0, st>>>(row_ptr, col_idx, item_ptr, item_row, n_items, seg, X, \
-                                                       ldx, Y, ldy, d4, self_coef, dinv, bias, act, partial); \
+                                                       ldx, Y, ldy, d4, self_coef, dinv, bias, act, partial, roff); \
     BIGNN_LAUNCH_COUNT(1);                                                                            \
     if (n_multi > 0) {                                                                                \
       int g2 = ceil_div(n_multi, per);                                                                \
       if (g2 > cap) g2 = cap;                                                                         \
       k_spmm_multi_v4<L, NV, MODE><<<g2, 256, 0, st>>>(item_ptr, multi_rows, n_multi, X, ldx, Y, ldy, d4,     \
-                                                       self_coef, dinv, bias, act, partial);          \
+                                                       self_coef, dinv, bias, act, partial, roff);    \
       BIGNN_LAUNCH_COUNT(1);                                                                          \
     }                                                                                                 \
   }
@@ -355,6 +358,14 @@ extern "C" int bignn_spmm_f32(const int32_t* row_ptr, const int32_t* col_idx, co
                               float* Y, int64_t ldy, int32_t n_rows, int32_t D, int32_t mode,
                               float self_coef, const float* dinv, const float* bias, int32_t act,
                               void* stream) {
+  return bignn_spmm_rows_f32(row_ptr, col_idx, X, ldx, Y, ldy, n_rows, 0, D, mode, self_coef, dinv, bias, act, stream);
+}
+
+extern "C" int bignn_spmm_rows_f32(const int32_t* row_ptr, const int32_t* col_idx, const float* X, int64_t ldx,
+                                   float* Y, int64_t ldy, int32_t n_rows, int32_t row_offset, int32_t D,
+                                   int32_t mode, float self_coef, const float* dinv, const float* bias,
+                                   int32_t act, void* stream) {
+  const int roff = row_offset;
   if (n_rows < 0 || D < 0 || !row_ptr) return BIGNN_EINVAL;
   if (n_rows == 0 || D == 0) return 0;
   if (!X || !Y || ldx < D || ldy < D) return BIGNN_EINVAL;
@@ -362,9 +373,9 @@ extern "C" int bignn_spmm_f32(const int32_t* row_ptr, const int32_t* col_idx, co
   if (act < 0 || act > BIGNN_ACT_TANH) return BIGNN_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   switch (mode) {
-    case BIGNN_SPMM_SUM: return launch_mode<BIGNN_SPMM_SUM>(row_ptr, col_idx, X, ldx, Y, ldy, n_rows, D, self_coef, dinv, bias, act, st);
-    case BIGNN_SPMM_GIN: return launch_mode<BIGNN_SPMM_GIN>(row_ptr, col_idx, X, ldx, Y, ldy, n_rows, D, self_coef, dinv, bias, act, st);
-    case BIGNN_SPMM_GCN: return launch_mode<BIGNN_SPMM_GCN>(row_ptr, col_idx, X, ldx, Y, ldy, n_rows, D, self_coef, dinv, bias, act, st);
+    case BIGNN_SPMM_SUM: return launch_mode<BIGNN_SPMM_SUM>(row_ptr, col_idx, X, ldx, Y, ldy, n_rows, D, self_coef, dinv, bias, act, roff, st);
+    case BIGNN_SPMM_GIN: return launch_mode<BIGNN_SPMM_GIN>(row_ptr, col_idx, X, ldx, Y, ldy, n_rows, D, self_coef, dinv, bias, act, roff, st);
+    case BIGNN_SPMM_GCN: return launch_mode<BIGNN_SPMM_GCN>(row_ptr, col_idx, X, ldx, Y, ldy, n_rows, D, self_coef, dinv, bias, act, roff, st);
     default: return BIGNN_EINVAL;
   }
 }
@@ -380,6 +391,18 @@ extern "C" int bignn_spmm_planned_f32(const int32_t* row_ptr, const int32_t* col
                                       float* Y, int64_t ldy, int32_t n_rows, int32_t D, int32_t mode,
                                       float self_coef, const float* dinv, const float* bias, int32_t act,
                                       void* workspace, int64_t workspace_bytes, void* stream) {
+  return bignn_spmm_planned_rows_f32(row_ptr, col_idx, item_ptr, item_row, n_items, seg, multi_rows, n_multi, X, ldx, Y,
+                                     ldy, n_rows, 0, D, mode, self_coef, dinv, bias, act, workspace, workspace_bytes,
+                                     stream);
+}
+
+extern "C" int bignn_spmm_planned_rows_f32(const int32_t* row_ptr, const int32_t* col_idx, const int32_t* item_ptr,
+                                           const int32_t* item_row, int32_t n_items, int32_t seg,
+                                           const int32_t* multi_rows, int32_t n_multi, const float* X, int64_t ldx,
+                                           float* Y, int64_t ldy, int32_t n_rows, int32_t row_offset, int32_t D,
+                                           int32_t mode, float self_coef, const float* dinv, const float* bias,
+                                           int32_t act, void* workspace, int64_t workspace_bytes, void* stream) {
+  const int roff = row_offset;
   if (n_rows < 0 || D < 0 || n_items < 0 || n_multi < 0 || seg <= 0 || !row_ptr) return BIGNN_EINVAL;
   if (n_rows == 0 || D == 0) return 0;
   if (!X || !Y || !item_ptr || !item_row || ldx < D || ldy < D || D > 512) return BIGNN_EINVAL;
@@ -394,9 +417,9 @@ extern "C" int bignn_spmm_planned_f32(const int32_t* row_ptr, const int32_t* col
   cudaStream_t st = (cudaStream_t)stream;
   float* partial = (float*)workspace;
   switch (mode) {
-    case BIGNN_SPMM_SUM: return launch_planned<BIGNN_SPMM_SUM>(row_ptr, col_idx, item_ptr, item_row, n_items, seg, multi_rows, n_multi, X, ldx, Y, ldy, D, self_coef, dinv, bias, act, partial, st);
-    case BIGNN_SPMM_GIN: return launch_planned<BIGNN_SPMM_GIN>(row_ptr, col_idx, item_ptr, item_row, n_items, seg, multi_rows, n_multi, X, ldx, Y, ldy, D, self_coef, dinv, bias, act, partial, st);
-    case BIGNN_SPMM_GCN: return launch_planned<BIGNN_SPMM_GCN>(row_ptr, col_idx, item_ptr, item_row, n_items, seg, multi_rows, n_multi, X, ldx, Y, ldy, D, self_coef, dinv, bias, act, partial, st);
+    case BIGNN_SPMM_SUM: return launch_planned<BIGNN_SPMM_SUM>(row_ptr, col_idx, item_ptr, item_row, n_items, seg, multi_rows, n_multi, X, ldx, Y, ldy, D, self_coef, dinv, bias, act, partial, roff, st);
+    case BIGNN_SPMM_GIN: return launch_planned<BIGNN_SPMM_GIN>(row_ptr, col_idx, item_ptr, item_row, n_items, seg, multi_rows, n_multi, X, ldx, Y, ldy, D, self_coef, dinv, bias, act, partial, roff, st);
+    case BIGNN_SPMM_GCN: return launch_planned<BIGNN_SPMM_GCN>(row_ptr, col_idx, item_ptr, item_row, n_items, seg, multi_rows, n_multi, X, ldx, Y, ldy, D, self_coef, dinv, bias, act, partial, roff, st);
     default: return BIGNN_EINVAL;
   }
 }

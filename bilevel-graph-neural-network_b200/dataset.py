@@ -6,6 +6,56 @@ import torch
 
 from .graph import PackedGraphs, InteractionGraph
 
+# above this many pairs / edges the Python dict / set of the reference (utils/data/dataset.py:394-403,
+# src/batch.py:73) is replaced by binary search over sorted int64 keys: same answers, O(log E) per query,
+# no per-call O(E) host work ("fine at 28 k, catastrophic at 20 M")
+BIG_TABLE = 2_000_000
+
+
+class _SortedKeySet(object):
+    """`(a, b) in s` over sorted keys a*n + b."""
+
+    def __init__(self, keys_sorted, n):
+        self.keys, self.n = keys_sorted, int(n)
+
+    def __contains__(self, ab):
+        k = int(ab[0]) * self.n + int(ab[1])
+        i = int(np.searchsorted(self.keys, k))
+        return i < self.keys.shape[0] and int(self.keys[i]) == k
+
+    def __len__(self):
+        return int(self.keys.shape[0])
+
+
+class _PairTable(object):
+    """gid pair -> label for datasets too large for a dict of tuples."""
+
+    def __init__(self, gs_map, n, pair_keys, pair_labels):
+        gids = np.asarray(pair_keys, np.int64)
+        lut_keys = np.fromiter(gs_map.keys(), np.int64, len(gs_map))
+        lut_vals = np.fromiter(gs_map.values(), np.int64, len(gs_map))
+        order = np.argsort(lut_keys)
+        lut_keys, lut_vals = lut_keys[order], lut_vals[order]
+        rows = lut_vals[np.searchsorted(lut_keys, gids)]
+        key = rows[:, 0] * n + rows[:, 1]
+        order = np.argsort(key, kind='stable')
+        self.keys = key[order]
+        self.labels = np.asarray(pair_labels)[order]
+        self.gs_map, self.n = gs_map, int(n)
+
+    def get(self, ab, default=None):
+        a, b = self.gs_map.get(int(ab[0])), self.gs_map.get(int(ab[1]))
+        if a is None or b is None:
+            return default
+        k = a * self.n + b
+        i = int(np.searchsorted(self.keys, k))
+        if i < self.keys.shape[0] and int(self.keys[i]) == k:
+            return int(self.labels[i])
+        return default
+
+    def __len__(self):
+        return int(self.keys.shape[0])
+
 
 class BiGNNData(object):
     def __init__(self, gids, atom_ptr, nbr_ptr, nbr_idx, x, ddi_row, ddi_col, train_pairs,
@@ -41,7 +91,9 @@ class BiGNNData(object):
         self.train_pairs = np.asarray(train_pairs, np.int64)
         self.data_items = torch.as_tensor(self.train_pairs)        # sorted pair tensor (dataset.py:34)
         self.pairs = {}
-        if pair_keys is not None:
+        if pair_keys is not None and len(pair_keys) > BIG_TABLE:
+            self.pairs = _PairTable(self.gs_map, self.N, pair_keys, pair_labels)
+        elif pair_keys is not None:
             for (a, b), l in zip(np.asarray(pair_keys).tolist(), np.asarray(pair_labels).tolist()):
                 self.pairs[(a, b)] = int(l)
         else:
@@ -82,5 +134,8 @@ class BiGNNData(object):
         orientations (src/batch.py:73 builds it per call; it never changes)."""
         if self._edge_set is None:
             g = self.interaction_combo_nxgraph
-            self._edge_set = set(zip(g.row_host.tolist(), g.col_host.tolist()))
+            if self._edge_keys.shape[0] > BIG_TABLE:
+                self._edge_set = _SortedKeySet(self._edge_keys, self.N)
+            else:
+                self._edge_set = set(zip(g.row_host.tolist(), g.col_host.tolist()))
         return self._edge_set

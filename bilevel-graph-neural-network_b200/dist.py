@@ -89,3 +89,155 @@ def gather_chunk_stats(stats_local, s_max, group=None):
     out = torch.empty((world, 2, s_max, C), dtype=stats_local.dtype, device=stats_local.device)
     dist.all_gather_into_tensor(out.view(-1), pad.view(-1), group=group)
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Row-partitioned upper level (SURVEY 8e): interaction-graph rows (= edges by source drug) are split
+# over the ranks (graph.RowPartition); per layer: local GEMM on own rows -> ALL-GATHER of the
+# transformed rows -> local SpMM on own rows -> BatchNorm over all N rows through an all-reduce of
+# (sum x, sum x^2).  The graph is symmetric, so each backward is the same exchange on the gradient.
+def _group_size(group):
+    return dist.get_world_size(group) if is_dist() else 1
+
+
+def gather_rows(x_loc, pg):
+    """[n_loc, D] rows of this rank -> [world*n_max, D] rows of all ranks in the position space of
+    graph.RowPartition (equal-count all-gather, in place in the output buffer: NCCL's in-place form,
+    sendbuff = recvbuff + rank*count)."""
+    D = x_loc.shape[1]
+    out = torch.empty((pg.n_pad, D), dtype=x_loc.dtype, device=x_loc.device)
+    mine = out[pg.row_offset:pg.row_offset + pg.n_max]
+    mine[:pg.n_loc].copy_(x_loc)
+    if pg.n_loc < pg.n_max:
+        mine[pg.n_loc:].zero_()
+    if pg.world > 1:
+        src = mine if x_loc.is_cuda else mine.clone()          # gloo (CPU tests): no aliasing of in/out
+        dist.all_gather_into_tensor(out.view(-1), src.reshape(-1), group=pg.group)
+    return out
+
+
+class _ExchangePooledRows(torch.autograd.Function):
+    """init_x = sum over ranks of zero-padded row blocks (forward: the all-gather of pooled drug
+    embeddings, each row written by exactly one rank).  With a row-partitioned upper level a rank holds
+    d loss / d init_x only for its own interaction-graph rows, so the backward is the same rank sum."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        ctx.group = group
+        x = x.contiguous()
+        dist.all_reduce(x, op=dist.ReduceOp.SUM, group=group)
+        return x
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous().clone()
+        dist.all_reduce(g, op=dist.ReduceOp.SUM, group=ctx.group)
+        return g, None
+
+
+def exchange_pooled_rows(x, group=None):
+    if not is_dist():
+        return x
+    return _ExchangePooledRows.apply(x, group)
+
+
+class _GcnPropagateRows(torch.autograd.Function):
+    """u_loc = act(rows_loc(D^-1/2 (A+I) D^-1/2) all_gather(h_loc) + bias); backward: the same
+    all-gather + local SpMM on act'(u) * du (A symmetric); dbias is this rank's partial column sum."""
+
+    @staticmethod
+    def forward(ctx, h_loc, bias, pg, act):
+        from . import ops
+        H = gather_rows(h_loc, pg)
+        u = ops.spmm(pg.csr, H, ops.SPMM_GCN, 0.0, pg.csr.dinv(), bias, act)
+        ctx.pg, ctx.act, ctx.has_bias = pg, act, bias is not None
+        ctx.save_for_backward(u)
+        return u
+
+    @staticmethod
+    def backward(ctx, du):
+        from . import ops
+        (u,) = ctx.saved_tensors
+        pg = ctx.pg
+        g = ops.act_bwd(u, du, ctx.act)
+        dbias = ops.colsum(g) if ctx.has_bias and ctx.needs_input_grad[1] else None
+        dh = None
+        if ctx.needs_input_grad[0]:
+            G = gather_rows(g, pg)
+            dh = ops.spmm(pg.csr, G, ops.SPMM_GCN, 0.0, pg.csr.dinv(), None, 0)
+        return dh, dbias, None, None
+
+
+def gcn_propagate_rows(h_loc, bias, pg, act=0):
+    return _GcnPropagateRows.apply(h_loc, bias, pg, act)
+
+
+class _RowsBatchNorm(torch.autograd.Function):
+    """Train-mode BatchNorm1d whose batch is the rows of all ranks: local fp64 sums, one [2, C] fp64
+    all-reduce, local apply (bignn_bn_rows_*).  dgamma / dbeta come out rank-summed (global)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, pg, running_mean, running_var, nbt, eps, momentum):
+        from . import ops, _lib
+        x = ops._f32c(x)
+        _lib.require_device(x)
+        rows, C = x.shape
+        parts = ops.bn_parts(1, max(rows, 1))
+        wsb = _lib.call('bignn_bn_rows_workspace_bytes', C, parts)
+        ws = ops._ws(wsb, x.device)
+        sums = torch.empty((2, C), dtype=torch.float64, device=x.device)
+        _lib.call('bignn_bn_rows_sums', x, x.stride(0), None, 0, rows, C, parts, None, None, sums, ws, int(wsb))
+        if pg.world > 1:
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=pg.group)
+        y = torch.empty_like(x)
+        mean = torch.empty(C, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(C, dtype=torch.float32, device=x.device)
+        _lib.call('bignn_bn_rows_fwd_apply', x, x.stride(0), y, y.stride(0), rows, C, parts, sums, int(pg.n),
+                  gamma, beta, float(eps), float(momentum), running_mean, running_var, nbt, mean, rstd)
+        ctx.pg, ctx.parts = pg, parts
+        ctx.save_for_backward(x, gamma, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import ops, _lib
+        x, gamma, mean, rstd = ctx.saved_tensors
+        pg, parts = ctx.pg, ctx.parts
+        dy = ops._f32c(dy)
+        rows, C = x.shape
+        wsb = _lib.call('bignn_bn_rows_workspace_bytes', C, parts)
+        ws = ops._ws(wsb, x.device)
+        sums = torch.empty((2, C), dtype=torch.float64, device=x.device)
+        _lib.call('bignn_bn_rows_sums', x, x.stride(0), dy, dy.stride(0), rows, C, parts, mean, rstd, sums, ws,
+                  int(wsb))
+        if pg.world > 1:
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=pg.group)
+        dx = torch.empty_like(x)
+        _lib.call('bignn_bn_rows_bwd_apply', x, x.stride(0), dy, dy.stride(0), dx, dx.stride(0), rows, C, parts,
+                  gamma, mean, rstd, sums, int(pg.n))
+        dbeta, dgamma = sums[0].to(torch.float32), sums[1].to(torch.float32)
+        return dx, dgamma, dbeta, None, None, None, None, None, None
+
+
+def rows_batch_norm(x, gamma, beta, pg, running_mean, running_var, nbt, eps=1e-5, momentum=0.1):
+    return _RowsBatchNorm.apply(x, gamma, beta, pg, running_mean, running_var, nbt, eps, momentum)
+
+
+class _GatherRowsReplicatedConsumer(torch.autograd.Function):
+    """All-gather of the final upper-level embeddings for a consumer that every rank evaluates
+    identically (the pair scorer over the whole pair batch): every rank then holds the same gradient of
+    the gathered matrix, so the backward of the gather is this rank's own row block of it."""
+
+    @staticmethod
+    def forward(ctx, x_loc, pg):
+        ctx.pg = pg
+        return gather_rows(x_loc, pg)
+
+    @staticmethod
+    def backward(ctx, g):
+        pg = ctx.pg
+        return g[pg.row_offset:pg.row_offset + pg.n_loc].contiguous(), None
+
+
+def gather_rows_for_replicated_consumer(x_loc, pg):
+    return _GatherRowsReplicatedConsumer.apply(x_loc, pg)

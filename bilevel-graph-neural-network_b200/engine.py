@@ -17,7 +17,8 @@ import torch
 from . import ops, dist as bdist
 from .batch import BatchData, unique_graphs_in_order
 from .config import get_flags
-from .graph import MergedGraph
+from .graph import MergedGraph, PartitionedInteractionGraph
+from .layers_load_interaction_graph import LoadInteractionGraph
 from .ops import CSR
 from .train import all_drug_chunks
 
@@ -26,11 +27,13 @@ class _StaticPairBatch(object):
     """The pair batch as the upper-level layers see it (LinkPred / Loss), backed by static
     device buffers so that a captured graph can be replayed on new pairs."""
 
-    def __init__(self, data, P, device):
+    def __init__(self, data, P, device, graph=None):
         self.dataset = data
         self.P = P
-        N = data.N
-        self.interaction_combo_nxgraph = data.interaction_combo_nxgraph
+        # pair rows index the matrix the scorer gathers from: the N drug rows, or -- with a row-partitioned
+        # upper level -- the world*n_max positions of the all-gathered embeddings
+        N = data.N if graph is None else graph.n_pad
+        self.interaction_combo_nxgraph = data.interaction_combo_nxgraph if graph is None else graph
         self.merge_data = {}
         self.merge_higher_level = {}
         self.ids = torch.zeros((P, 2), dtype=torch.int32, device=device)
@@ -70,7 +73,7 @@ class _Staging(object):
 
 class BiGNNEngine(object):
     def __init__(self, data, model, optimizer=None, lr=None, use_cuda_graph=True, rebuild_each_step=True,
-                 n_staging=4, rank=0, world=1, group=None, adam_capturable=None):
+                 n_staging=4, rank=0, world=1, group=None, adam_capturable=None, partition_upper=None):
         flags = get_flags()
         assert flags.lower_level_layers and flags.higher_level_layers, 'engine runs the Bi-GNN mode'
         self.data, self.model = data, model
@@ -100,6 +103,19 @@ class BiGNNEngine(object):
         self.merged = MergedGraph(data.packed, rows, chunk_graph_ptr=chunk_ptr)
         self._bn_sink = [] if self.world > 1 else None
         self.merged.bn_stats_sink = self._bn_sink
+        # ---- upper level: replicated, or rows (= edges by source drug) partitioned over the ranks with a
+        # per-layer all-gather.  Partitioned by default when every upper layer is a GCN.
+        from .layers import NodeEmbedding
+        convs = [l for l in model.higher_level_layers if not isinstance(l, (LoadInteractionGraph,))][:-2]
+        can_part = all(isinstance(l, NodeEmbedding) and l.type == 'gcn' for l in convs)
+        if partition_upper is None:
+            partition_upper = self.world > 1 and can_part
+        if partition_upper and not can_part:
+            raise NotImplementedError('partition_upper: only GCN upper levels are row-partitioned')
+        self.upper = PartitionedInteractionGraph(data.interaction_combo_nxgraph, self.rank, self.world,
+                                                 group) if partition_upper else None
+        self._upper_partial = [p for l in convs for p in l.conv.parameters()] if partition_upper else []
+        self._n_pair_rows = self.upper.n_pad if self.upper is not None else data.N
         # a drug that appears in two chunks is overwritten by the later one in the reference
         # (layers_aggregation.py:72-74); earlier duplicates go to a trash row N
         first_later = {}
@@ -137,15 +153,18 @@ class BiGNNEngine(object):
             acts.append(h)
         pooled = ops.readout(acts if self._multi else [h], m.seg_ptr, m.G, self._agg_style,
                              self.dst_row, self.data.N + 1)
-        if self.world > 1:
-            pooled = bdist.sum_disjoint_rows(pooled, self.group)      # the exchange step (NCCL)
+        if self.world > 1:                                            # the exchange step (NCCL)
+            pooled = (bdist.exchange_pooled_rows if self.upper is not None else bdist.sum_disjoint_rows)(
+                pooled, self.group)
         return pooled, acts
+
+    def _ig(self):
+        return self.upper if self.upper is not None else self.data.interaction_combo_nxgraph
 
     def forward(self, pair_batch):
         model = self.model
         pooled, _ = self.lower_pass()
-        ig = self.data.interaction_combo_nxgraph
-        ig.init_x = pooled[:self.data.N]
+        self._ig().init_x = pooled[:self.data.N]
         model.use_layers = 'higher_layers'
         model.acts = [None]
         for layer in model.higher_level_layers:
@@ -156,7 +175,8 @@ class BiGNNEngine(object):
         """after backward on a sharded lower level: sum the partial weight gradients and replay
         the BatchNorm running-buffer updates in global chunk order."""
         lower = [p for l in self.model.init_layers for p in l.parameters()]
-        bdist.all_reduce_grads(lower, self.group)
+        # + the conv weights / biases of a row-partitioned upper level (partial sums over a rank's rows)
+        bdist.all_reduce_grads(lower + self._upper_partial, self.group)
         s_max = max(hi - lo for lo, hi in self.chunk_shards)
         for bn, stats in self._bn_sink:
             allst = bdist.gather_chunk_stats(stats, s_max, self.group)       # [world, 2, s_max, C]
@@ -173,9 +193,15 @@ class BiGNNEngine(object):
         if self.world > 1:
             self._sync_lower()
         self.optimizer.step()
-        ig = self.data.interaction_combo_nxgraph
-        ig.init_x = ig.init_x.detach()
+        self._detach_init_x()
         return loss.detach()
+
+    def _detach_init_x(self):
+        ig = self._ig()
+        if self.upper is not None:
+            ig.init_x_full = ig.init_x_full.detach()
+        else:
+            ig.init_x = ig.init_x.detach()
 
     # ------------------------------------------------------------------ capture
     def _snapshot(self):
@@ -192,10 +218,10 @@ class BiGNNEngine(object):
                         v.zero_()
 
     def _capture(self, P):
-        sb = _StaticPairBatch(self.data, P, self.device)
+        sb = _StaticPairBatch(self.data, P, self.device, self.upper)
         # a valid dummy batch for warm-up: pairs (0,1) with label 0
         sb.ids[:, 1] = 1
-        e_ptr = np.zeros(self.data.N + 1, np.int64)
+        e_ptr = np.zeros(self._n_pair_rows + 1, np.int64)
         e_ptr[1:] = P
         e_ptr[2:] = 2 * P
         sb.e_ptr.copy_(torch.as_tensor(e_ptr.astype(np.int32)))
@@ -235,7 +261,7 @@ class BiGNNEngine(object):
     def _staging(self, P):
         key = P
         if key not in self._stagings:
-            self._stagings[key] = [_Staging(P, self.data.N, self.device.type == 'cuda')
+            self._stagings[key] = [_Staging(P, self._n_pair_rows, self.device.type == 'cuda')
                                    for _ in range(self._n_staging)]
         st = self._stagings[key][self._step_idx % self._n_staging]
         if st.busy and st.event is not None:
@@ -243,16 +269,23 @@ class BiGNNEngine(object):
         st.busy = False
         return st
 
+    def _pair_rows(self, batch_gids):
+        """gid pairs -> flat rows of the matrix the scorer gathers from (drug rows; positions of the
+        all-gathered embeddings when the upper level is row-partitioned)."""
+        gs_map = self.data.gs_map
+        flat = np.fromiter((gs_map[g] for g in np.asarray(batch_gids).reshape(-1).tolist()), np.int64)
+        return flat if self.upper is None else self.upper.part.pos(flat)
+
     def stage_pairs(self, batch_gids, labels):
         """Host -> pinned staging: pair rows (gs_map), labels and the decoder's entry CSR."""
         gs_map = self.data.gs_map
-        flat = np.fromiter((gs_map[g] for g in np.asarray(batch_gids).reshape(-1).tolist()), np.int64)
+        flat = self._pair_rows(batch_gids)
         P = flat.shape[0] // 2
         st = self._staging(P)
         st.ids.numpy()[:] = flat.reshape(P, 2)
         st.y.numpy()[:] = labels
         order = np.argsort(flat, kind='stable')
-        cnt = np.bincount(flat, minlength=self.data.N)
+        cnt = np.bincount(flat, minlength=self._n_pair_rows)
         ep = st.e_ptr.numpy()
         ep[0] = 0
         np.cumsum(cnt, out=ep[1:])
@@ -268,7 +301,7 @@ class BiGNNEngine(object):
         else:
             sb = self._graphs.get(('eager', P))
             if sb is None:
-                sb = self._graphs[('eager', P)] = _StaticPairBatch(self.data, P, self.device)
+                sb = self._graphs[('eager', P)] = _StaticPairBatch(self.data, P, self.device, self.upper)
         sb.ids.copy_(st.ids, non_blocking=True)
         sb.y.copy_(st.y, non_blocking=True)
         sb.e_ptr.copy_(st.e_ptr, non_blocking=True)
@@ -303,14 +336,13 @@ class BiGNNEngine(object):
         was_training = model.training
         model.eval()
         try:
-            ig = self.data.interaction_combo_nxgraph
+            ig = self._ig()
             if recompute_init_x or ig.init_x is None:
                 pooled, _ = self.lower_pass()
                 ig.init_x = pooled[:self.data.N]
-            gs_map = self.data.gs_map
-            flat = np.fromiter((gs_map[g] for g in np.asarray(gid_pairs).reshape(-1).tolist()), np.int64)
+            flat = self._pair_rows(gid_pairs)
             P = flat.shape[0] // 2
-            sb = _StaticPairBatch(self.data, P, self.device)
+            sb = _StaticPairBatch(self.data, P, self.device, self.upper)
             sb.ids.copy_(torch.as_tensor(flat.reshape(P, 2).astype(np.int32)))
             model.acts = [None]
             for layer in model.higher_level_layers[:-1]:           # everything but the loss

@@ -130,9 +130,7 @@ class InteractionGraph(object):
             row, col = row[keep], col[keep]
         self.n = int(n_nodes)
         self.row_host, self.col_host = row, col
-        ptr = np.zeros(self.n + 1, np.int64)
-        np.add.at(ptr, row + 1, 1)
-        ptr = np.cumsum(ptr)
+        ptr = np.concatenate([[0], np.cumsum(np.bincount(row, minlength=self.n))]).astype(np.int64)
         dev = torch.device(device)
         self.csr = CSR(_i32(ptr, dev), _i32(col, dev), self.n, row_ptr_host=ptr)
         self.bn_row_ptr = _i32([0, self.n], dev)     # the whole graph is one BatchNorm batch
@@ -163,3 +161,83 @@ def entry_csr(ids_host, n_rows, device):
     ptr = np.zeros(n_rows + 1, np.int64)
     np.add.at(ptr, flat + 1, 1)
     return CSR(_i32(np.cumsum(ptr), device), _i32(order, device), n_rows)
+
+
+class RowPartition(object):
+    """Contiguous row ranges of the interaction graph, one per rank, balanced by work (nnz + rows) --
+    'edges partitioned by source drug' (SURVEY 8e).  Every rank's block is padded to `n_max` rows so that
+    the per-layer exchange is one equal-count all-gather: drug row g of rank r lives at position
+    r*n_max + (g - lo_r) of the gathered [world*n_max, D] matrix, and the local CSRs store their column
+    ids in that position space (the map is monotone, so neighbour order -- and with it the summation
+    order of every SpMM row -- is the one of the unpartitioned graph)."""
+
+    def __init__(self, row_ptr_host, world):
+        ptr = np.asarray(row_ptr_host, np.int64)
+        n = ptr.shape[0] - 1
+        work = ptr + np.arange(n + 1, dtype=np.int64)            # prefix of (nnz + 1) per row
+        bounds = [0]
+        for r in range(1, world):
+            i = int(np.searchsorted(work, work[-1] * r / world))
+            bounds.append(min(max(i, bounds[-1]), n))
+        bounds.append(n)
+        self.world = int(world)
+        self.bounds = np.asarray(bounds, np.int64)
+        self.n = n
+        self.n_max = max(int(np.diff(self.bounds).max()), 1)
+        self.n_pad = self.world * self.n_max
+
+    def rows_of(self, rank):
+        return int(self.bounds[rank]), int(self.bounds[rank + 1])
+
+    def pos(self, rows):
+        """drug rows -> positions in the gathered matrix."""
+        rows = np.asarray(rows, np.int64)
+        r = np.searchsorted(self.bounds[1:], rows, side='right')
+        r = np.minimum(r, self.world - 1)
+        return r * self.n_max + rows - self.bounds[r]
+
+
+class PartitionedInteractionGraph(object):
+    """This rank's rows of the upper-level graph (see RowPartition): local int32 CSR with columns in the
+    gathered position space, the cached deg^-1/2 of ALL nodes in that space, and the pooled drug
+    embeddings `init_x` of the local rows.  Stands in for InteractionGraph on `batch.merge_higher_level`;
+    the layers recognise it by `partitioned`."""
+    partitioned = True
+
+    def __init__(self, full, rank, world, group=None):
+        ptr = np.asarray(full.csr._row_ptr_host, np.int64)
+        self.part = RowPartition(ptr, world)
+        self.rank, self.world, self.group = int(rank), int(world), group
+        self.full = full
+        self.n = full.n                                          # rows of the whole batch (BatchNorm count)
+        lo, hi = self.part.rows_of(rank)
+        self.lo, self.hi, self.n_loc = lo, hi, hi - lo
+        self.n_max, self.n_pad = self.part.n_max, self.part.n_pad
+        self.row_offset = self.rank * self.n_max
+        dev = full.csr.row_ptr.device
+        lptr = ptr[lo:hi + 1] - ptr[lo]
+        lcol = self.part.pos(full.col_host[ptr[lo]:ptr[hi]])
+        self.csr = CSR(_i32(lptr, dev), _i32(lcol, dev), self.n_loc, row_ptr_host=lptr)
+        self.csr.row_offset = self.row_offset
+        # deg^-1/2 of every node, scattered to the position space (pad positions are never referenced)
+        dinv = torch.zeros(self.n_pad, dtype=torch.float32, device=dev)
+        dinv[torch.as_tensor(self.part.pos(np.arange(full.n))).to(dev)] = full.csr.dinv()
+        self.csr._dinv = dinv
+        self.init_x_full = None
+        self.edge_attr = None
+        self.bn_row_ptr = None                 # BatchNorm goes through bignn_bn_rows_* (batch = rows of all ranks)
+
+    @property
+    def init_x(self):
+        return None if self.init_x_full is None else self.init_x_full[self.lo:self.hi]
+
+    @init_x.setter
+    def init_x(self, value):
+        self.init_x_full = value
+
+    @property
+    def x(self):
+        return self.init_x
+
+    def number_of_nodes(self):
+        return self.n

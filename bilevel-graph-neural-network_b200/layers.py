@@ -3,7 +3,7 @@ state_dict layout (model/layers.py:9-89), computed by the sm_100a kernels."""
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import ops, dist as bdist
 from .config import get_flags
 from .layers_util import create_act, apply_linear_act
 
@@ -84,7 +84,16 @@ class NodeEmbedding(nn.Module):
             seg, S = graph.chunk_row_ptr, graph.S
         csr = graph.csr
         a = self.act.code                   # None for PReLU (not fusable: it has a parameter)
-        if self.type == 'gcn':
+        parted = getattr(graph, 'partitioned', False)     # this rank's rows of a row-partitioned upper level
+        if parted and self.type != 'gcn':
+            raise NotImplementedError('row-partitioned upper level: only GCN layers are partitioned; run the '
+                                      '{} upper level replicated (BiGNNEngine(partition_upper=False))'.format(self.type))
+        if parted:
+            h = ops.linear_act(ins, self.conv.weight, None, 0, 'io')           # own rows only
+            x = bdist.gcn_propagate_rows(h, self.conv.bias, graph, a if a is not None else 0)
+            if a is None:
+                x = self.act(x)
+        elif self.type == 'gcn':
             h = ops.linear_act(ins, self.conv.weight, None, 0, 'io')
             x = ops.gcn_propagate(h, self.conv.bias, csr, a if a is not None else 0)
             if a is None:
@@ -98,7 +107,11 @@ class NodeEmbedding(nn.Module):
             lin1, lin2 = self.conv.nn[0], self.conv.nn[2]
             t = apply_linear_act(z, lin1, self.act)
             x = apply_linear_act(t, lin2, self.act)
-        if self.bn:
+        if self.bn and parted and self.training:
+            x = bdist.rows_batch_norm(x, self.bn.weight, self.bn.bias, graph, self.bn.running_mean,
+                                      self.bn.running_var, self.bn.num_batches_tracked, self.bn.eps,
+                                      self.bn.momentum)
+        elif self.bn:
             sink = getattr(graph, 'bn_stats_sink', None)
             if self.training and sink is not None:
                 # chunks sharded over several GPUs: keep the per-chunk statistics; the engine replays

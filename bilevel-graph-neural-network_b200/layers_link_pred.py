@@ -5,7 +5,7 @@ a dot product; multi-class mode returns the logits."""
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import ops, dist as bdist
 from .config import get_flags
 from .layers_util import MLP
 
@@ -44,6 +44,11 @@ class LinkPred(nn.Module):
     _calc_mlp_dims = staticmethod(hidden_widths)
 
     def forward(self, ins, batch_data, model):
+        graph = getattr(batch_data, 'merge_higher_level', {}).get('merge')
+        if getattr(graph, 'partitioned', False):
+            # row-partitioned upper level: all-gather the final embeddings; the pair batch is scored by every
+            # rank (P pairs << nnz), pair rows are positions of the gathered matrix (engine.stage_pairs)
+            ins = bdist.gather_rows_for_replicated_consumer(ins, graph)
         rows, entry_csr = batch_data.pair_rows_device(ins.shape[0], higher=get_flags().higher_level_layers,
                                                       unique=self.batch_unique_graphs)
         z = ops.pair_gather_norm(ins, rows, entry_csr)                 # [P, 2D] = [norm(h_a) || norm(h_b)]

@@ -58,6 +58,7 @@ class CSR(object):
         self.row_ptr, self.col_idx, self.n_rows = row_ptr, col_idx, int(n_rows)
         self._dinv = None
         self.plan = None
+        self.row_offset = None      # set for one rank's rows of a row-partitioned graph (graph.PartitionedInteractionGraph)
         self._row_ptr_host = row_ptr_host
         if row_ptr_host is not None and len(row_ptr_host) > 1:
             import numpy as np
@@ -86,20 +87,32 @@ class CSR(object):
 
 # ----------------------------------------------------------------------------- raw ops
 def spmm(csr, x, mode, self_coef=0.0, dinv=None, bias=None, act=0, out=None):
+    """y = A x over the rows of `csr`.  For a row-partitioned graph (`csr.row_offset` set) x covers ALL
+    nodes in the gathered position space and y only this rank's rows."""
     x = _f32c(x)
     _lib.require_device(x, csr.row_ptr)
     n, d = csr.n_rows, x.shape[1]
     y = out if out is not None else torch.empty((n, d), dtype=torch.float32, device=x.device)
     pl = csr.plan
+    roff = csr.row_offset
     if pl is not None and d % 4 == 0 and d <= 512:
         wsb = _lib.call('bignn_spmm_planned_workspace_bytes', pl.n_items, d) if pl.n_multi else 0
         ws = _ws(wsb, x.device) if wsb else None
-        _lib.call('bignn_spmm_planned_f32', csr.row_ptr, csr.col_idx, pl.item_ptr, pl.item_row, pl.n_items, pl.seg,
-                  pl.multi_rows, pl.n_multi, x, x.stride(0), y, y.stride(0), n, d, int(mode), float(self_coef),
-                  dinv, bias, int(act), ws, int(wsb))
+        if roff is None:
+            _lib.call('bignn_spmm_planned_f32', csr.row_ptr, csr.col_idx, pl.item_ptr, pl.item_row, pl.n_items, pl.seg,
+                      pl.multi_rows, pl.n_multi, x, x.stride(0), y, y.stride(0), n, d, int(mode), float(self_coef),
+                      dinv, bias, int(act), ws, int(wsb))
+        else:
+            _lib.call('bignn_spmm_planned_rows_f32', csr.row_ptr, csr.col_idx, pl.item_ptr, pl.item_row, pl.n_items,
+                      pl.seg, pl.multi_rows, pl.n_multi, x, x.stride(0), y, y.stride(0), n, int(roff), d, int(mode),
+                      float(self_coef), dinv, bias, int(act), ws, int(wsb))
         return y
-    _lib.call('bignn_spmm_f32', csr.row_ptr, csr.col_idx, x, x.stride(0), y, y.stride(0), n, d,
-              int(mode), float(self_coef), dinv, bias, int(act))
+    if roff is None:
+        _lib.call('bignn_spmm_f32', csr.row_ptr, csr.col_idx, x, x.stride(0), y, y.stride(0), n, d,
+                  int(mode), float(self_coef), dinv, bias, int(act))
+    else:
+        _lib.call('bignn_spmm_rows_f32', csr.row_ptr, csr.col_idx, x, x.stride(0), y, y.stride(0), n, int(roff), d,
+                  int(mode), float(self_coef), dinv, bias, int(act))
     return y
 
 

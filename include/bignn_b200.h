@@ -101,6 +101,21 @@ int bignn_spmm_f32(const int32_t* row_ptr, const int32_t* col_idx,
                    int32_t n_rows, int32_t D, int32_t mode, float self_coef,
                    const float* dinv, const float* bias, int32_t act, void* stream);
 
+/* Row-partitioned form (multi-GPU upper level, edges partitioned by source drug): the CSR holds only this
+ * rank's n_rows rows, whose node ids are row_offset .. row_offset + n_rows - 1 in the column / feature
+ * index space; X and dinv cover ALL nodes, Y only the local rows. */
+int bignn_spmm_rows_f32(const int32_t* row_ptr, const int32_t* col_idx,
+                        const float* X, int64_t ldx, float* Y, int64_t ldy,
+                        int32_t n_rows, int32_t row_offset, int32_t D, int32_t mode, float self_coef,
+                        const float* dinv, const float* bias, int32_t act, void* stream);
+int bignn_spmm_planned_rows_f32(const int32_t* row_ptr, const int32_t* col_idx,
+                                const int32_t* item_ptr, const int32_t* item_row, int32_t n_items, int32_t seg,
+                                const int32_t* multi_rows, int32_t n_multi,
+                                const float* X, int64_t ldx, float* Y, int64_t ldy,
+                                int32_t n_rows, int32_t row_offset, int32_t D, int32_t mode, float self_coef,
+                                const float* dinv, const float* bias, int32_t act,
+                                void* workspace, int64_t workspace_bytes, void* stream);
+
 /* Long-row variant for skewed graphs (interaction graphs with hub drugs): the caller splits every
  * row into work items of at most `seg` neighbours -- item_ptr[n_rows+1] (items per row, prefix sum,
  * every row has >= 1 item), item_row[n_items], multi_rows[n_multi] = rows with more than one item.
@@ -191,6 +206,30 @@ int bignn_bn_seg_bwd(const float* X, int64_t ldx, const float* dY, int64_t lddy,
                      const float* gamma, const float* mean, const float* rstd,
                      float* dgamma, float* dbeta,
                      void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Row-partitioned BatchNorm (multi-GPU upper level, SURVEY 8e: interaction-graph rows partitioned by
+ * source drug, one BatchNorm batch = the rows of ALL ranks).  Three steps around one all-reduce that the
+ * caller issues (NCCL, [2, C] fp64):
+ *   bignn_bn_rows_sums       local (sum x, sum x^2) -- or, with dY != NULL, (sum dy, sum dy*xhat) -- over this
+ *                            rank's `rows` rows, fp64, fixed part order;
+ *   bignn_bn_rows_fwd_apply  mean / rstd of the whole batch from the rank-summed sums and n_total rows, one
+ *                            momentum update of the (replicated) running buffers, y = bn(x) on the local rows;
+ *   bignn_bn_rows_bwd_apply  dX on the local rows from the rank-summed backward sums.
+ * The local backward sums ARE this rank's partial dbeta / dgamma.  With one rank the results equal
+ * bignn_bn_seg_fwd / bwd with S = 1. */
+int64_t bignn_bn_rows_workspace_bytes(int32_t C, int32_t parts);
+int bignn_bn_rows_sums(const float* X, int64_t ldx, const float* dY, int64_t lddy, int32_t rows, int32_t C,
+                       int32_t parts, const float* mean, const float* rstd, double* sums,
+                       void* workspace, int64_t workspace_bytes, void* stream);
+int bignn_bn_rows_fwd_apply(const float* X, int64_t ldx, float* Y, int64_t ldy, int32_t rows, int32_t C,
+                            int32_t parts, const double* sums, int64_t n_total,
+                            const float* gamma, const float* beta, float eps, float momentum,
+                            float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                            float* mean, float* rstd, void* stream);
+int bignn_bn_rows_bwd_apply(const float* X, int64_t ldx, const float* dY, int64_t lddy, float* dX, int64_t lddx,
+                            int32_t rows, int32_t C, int32_t parts, const float* gamma,
+                            const float* mean, const float* rstd, const double* sums, int64_t n_total,
+                            void* stream);
 
 /* ---------------------------------------------------------------------------
  * Segment readout (atoms -> one row per drug), rows summed in ascending order.

@@ -69,21 +69,61 @@ class Fake(object):
         return 0
 
     def bignn_spmm_f32(self, row_ptr, col_idx, X, ldx, Y, ldy, n, D, mode, self_coef, dinv, bias, act):
+        return self.bignn_spmm_rows_f32(row_ptr, col_idx, X, ldx, Y, ldy, n, 0, D, mode, self_coef, dinv, bias, act)
+
+    def bignn_spmm_rows_f32(self, row_ptr, col_idx, X, ldx, Y, ldy, n, roff, D, mode, self_coef, dinv, bias, act):
+        """rows are local (0..n), columns and X / dinv live in the global index space; local row i is node i+roff"""
         r, c = self._coo(row_ptr, col_idx, n)
         if mode != 0:
-            keep = r != c
+            keep = (r + roff) != c
             r, c = r[keep], c[keep]
         src = X[c][:, :D]
         if mode == 2:
-            src = (dinv[c] * dinv[r]).view(-1, 1) * src
+            src = (dinv[c] * dinv[r + roff]).view(-1, 1) * src
         out = torch.zeros(n, D).index_add_(0, r, src)
         if mode == 1:
-            out = self_coef * X[:n, :D] + out
+            out = self_coef * X[roff:roff + n, :D] + out
         elif mode == 2:
-            out = out + (dinv[:n] * dinv[:n]).view(-1, 1) * X[:n, :D]
+            out = out + (dinv[roff:roff + n] * dinv[roff:roff + n]).view(-1, 1) * X[roff:roff + n, :D]
         if bias is not None:
             out = out + bias
         Y[:n, :D] = ACTS[act](out)
+        return 0
+
+    def bignn_spmm_planned_rows_f32(self, row_ptr, col_idx, item_ptr, item_row, n_items, seg, multi_rows, n_multi,
+                                    X, ldx, Y, ldy, n, roff, D, mode, self_coef, dinv, bias, act, ws, wsb):
+        return self.bignn_spmm_rows_f32(row_ptr, col_idx, X, ldx, Y, ldy, n, roff, D, mode, self_coef, dinv, bias, act)
+
+    def bignn_bn_rows_workspace_bytes(self, C, parts):
+        return 16
+
+    def bignn_bn_rows_sums(self, X, ldx, dY, lddy, rows, C, parts, mean, rstd, sums, ws, wsb):
+        x = X[:rows].double()
+        if dY is None:
+            sums[0], sums[1] = x.sum(0), (x * x).sum(0)
+        else:
+            xhat = ((X[:rows] - mean) * rstd).double()
+            sums[0], sums[1] = dY[:rows].double().sum(0), (dY[:rows].double() * xhat).sum(0)
+        return 0
+
+    def bignn_bn_rows_fwd_apply(self, X, ldx, Y, ldy, rows, C, parts, sums, n_total, gamma, beta, eps, mom, rm, rv,
+                                nbt, mean, rstd):
+        mu = sums[0] / n_total
+        var = (sums[1] / n_total - mu * mu).clamp(min=0)
+        mean.copy_(mu.float())
+        rstd.copy_((1.0 / torch.sqrt(var + eps)).float())
+        if rm is not None:
+            rm.copy_((mom * mu + (1 - mom) * rm.double()).float())
+            rv.copy_((mom * var * n_total / max(n_total - 1, 1) + (1 - mom) * rv.double()).float())
+            if nbt is not None:
+                nbt += 1
+        alpha = rstd * gamma
+        Y[:rows] = X[:rows] * alpha + (beta - mean * alpha)
+        return 0
+
+    def bignn_bn_rows_bwd_apply(self, X, ldx, dY, lddy, dX, lddx, rows, C, parts, gamma, mean, rstd, sums, n_total):
+        xhat = (X[:rows] - mean) * rstd
+        dX[:rows] = (dY[:rows] - (sums[0] / n_total).float() - xhat * (sums[1] / n_total).float()) * (rstd * gamma)
         return 0
 
     def bignn_spmm_planned_workspace_bytes(self, n_items, D):

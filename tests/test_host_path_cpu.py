@@ -124,3 +124,21 @@ def test_negative_sampler_bit_exact(cpu_world, golden_dir):
         assert np.array_equal(bd.negative_pair_gids, neg)
         assert np.array_equal(bd.batch_gids, np.concatenate([pos, neg]))
         assert np.array_equal([p.true_label for p in bd.pair_list], y)
+
+
+def test_negative_sampler_bit_exact_with_sorted_key_tables(cpu_world, golden_dir, monkeypatch):
+    """the at-scale membership structures (binary search over sorted keys instead of the reference's Python
+    set of all train edges / dict of all pairs) give the same accept/reject stream"""
+    from bignn_b200 import dataset as D
+    monkeypatch.setattr(D, 'BIG_TABLE', 10)
+    data = B.BiGNNData.from_npz(os.path.join(golden_dir, 'drugbank_packed.npz'), device='cpu')
+    assert isinstance(data.pairs, D._PairTable) and isinstance(data.edge_set(), D._SortedKeySet)
+    s = np.load(os.path.join(golden_dir, 'bignn_gin_gcn_sampler_seq.npz'))
+    np.random.set_state(('MT19937', s['np_state_keys'], int(s['np_state_pos']), 0, 0.0))
+    pos_all = [s['first_pos']] + list(s['pos'])
+    neg_all = [s['first_neg']] + list(s['neg'])
+    y_all = [s['first_y']] + list(s['y'])
+    for pos, neg, y in zip(pos_all, neg_all, y_all):
+        bd = B.BatchData(pos, data, sampled_gids=np.unique(pos), is_train=True, merge_graphs=False)
+        assert np.array_equal(bd.negative_pair_gids, neg)
+        assert np.array_equal([p.true_label for p in bd.pair_list], y)
