@@ -111,4 +111,30 @@ WORKLOADS = {
     # antagonism 15 908 undirected edges, one-hot width <= 40
     'drugcombo_shape': dict(N=3242, M=50263, mean_atoms=29.3, groups=(22, 2, 2, 2, 6, 6),
                             edge_type_fracs={'synergy': 34355.0, 'antagonism': 15908.0}),
+    # BASELINE config 4 / SURVEY C4: 200 k drugs, 20 M undirected DDI edges (40 M nnz), 64-dim upper level
+    'ddi_scaled': dict(N=200_000, M=20_000_000, mean_atoms=30.0, groups=FEATURE_GROUPS),
+    # the same shape at 1/10 (CPU baseline of the scaled configuration; quick multi-GPU checks)
+    'ddi_scaled_small': dict(N=20_000, M=2_000_000, mean_atoms=30.0, groups=FEATURE_GROUPS),
 }
+
+
+def cached_workload(name, seed=0, cache_dir=None):
+    """bignn_workload(**WORKLOADS[name]) through an .npz cache in the temp directory (the 20 M-edge graph
+    takes about a minute to draw; every rank of a multi-GPU job and the CPU baseline need the same arrays)."""
+    import os
+    import tempfile
+    w = WORKLOADS[name]
+    if w['N'] < 10_000:
+        return bignn_workload(seed=seed, **w)
+    path = os.path.join(cache_dir or tempfile.gettempdir(), 'bignn_synth_{}_{}.npz'.format(name, seed))
+    if os.path.exists(path):
+        try:
+            z = np.load(path)
+            return {k: z[k] for k in z.files}
+        except Exception:
+            pass
+    out = bignn_workload(seed=seed, **w)
+    tmp = '{}.{}.tmp.npz'.format(path, os.getpid())
+    np.savez(tmp, **out)
+    os.replace(tmp, path)
+    return out

@@ -1,0 +1,82 @@
+#!/usr/bin/env python
+"""Multi-GPU parity check on real NCCL (run under torchrun on a 2+ GPU box):
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+      tools/nccl_partition_check.py
+
+Every rank runs the reference's golden DrugBank step (tests/golden/bignn_gin_gcn_step.npz) with the lower level
+sharded by drug and the upper level (a) replicated, (b) row-partitioned by source drug, eagerly and as a captured
+CUDA graph, and compares loss, pair predictions, init_x and the post-step BatchNorm buffers with the golden
+vectors (the same assertions as tests/test_gpu_engine.py makes on one GPU).  Prints one line per rank."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def rel(a, b):
+    a = np.asarray(a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else a, np.float64)
+    b = np.asarray(b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def main():
+    rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
+    torch.cuda.set_device(local)
+    dev = 'cuda:%d' % local
+    os.environ.setdefault('NCCL_DEBUG', 'WARN')
+    dist.init_process_group('nccl', device_id=torch.device(dev))
+    import bignn_b200 as B
+    from bignn_b200.engine import BiGNNEngine
+    B._lib.load()
+    gold = os.path.join(ROOT, 'tests', 'golden')
+    z = np.load(os.path.join(gold, 'bignn_gin_gcn_step.npz'))
+    ok = True
+    for part in (False, True):
+        for graph in (False, True):
+            B.set_flags(B.make_flags(device=dev))
+            data = B.BiGNNData.from_npz(os.path.join(gold, 'drugbank_packed.npz'), device=dev)
+            model = B.Model(data).to(dev)
+            sd = {k[4:]: torch.from_numpy(np.asarray(z[k])) for k in z.files if k.startswith('sd0/')}
+            for k in z.files:
+                if k.startswith('sd_init/'):
+                    sd[k[len('sd_init/'):]] = torch.from_numpy(np.asarray(z[k]))
+            model.load_state_dict(sd, strict=False)
+            model.train()
+            eng = BiGNNEngine(data, model, use_cuda_graph=graph, rank=rank, world=world, partition_upper=part)
+            st, P = eng.stage_pairs(z['batch_gids'], z['y_true'].astype(np.float32))
+            slot = eng.step_staged(st, P)
+            loss = eng.read_loss(slot)
+            ig = eng._ig()
+            init_x = ig.init_x_full if eng.upper is not None else ig.init_x
+            e = dict(loss=abs(loss - float(z['loss'])), init_x=rel(init_x, z['init_x']),
+                     preds=rel(eng.last_static_batch.preds.view(-1), z['pair_preds']))
+            msd = model.state_dict()
+            e['bn_running'] = max(rel(msd[k[4:]], z[k]) for k in z.files if k.startswith('sd1/') and 'running' in k)
+            nb = all(int(msd[k[4:]]) == int(z[k]) for k in z.files if k.startswith('sd1/') and 'num_batches' in k)
+            # parameters that moved by Adam's first update (well-conditioned upper level and scorer)
+            for k in ('layers.10.mlp_concat.layers.0.weight', 'layers.7.conv.weight', 'layers.9.bn.weight'):
+                g = z['grad/' + k]
+                mask = np.abs(g) > 1e-3 * np.abs(g).max()
+                e['adam/' + k] = float(np.abs(msd[k].cpu().numpy() - z['sd1/' + k])[mask].max())
+            good = (e['loss'] < 1e-5 and e['init_x'] < 1e-5 and e['preds'] < 1e-5 and e['bn_running'] < 1e-5 and nb
+                    and all(v < 2e-6 for k, v in e.items() if k.startswith('adam/')))
+            ok = ok and good
+            print('rank {}/{} partition_upper={} cuda_graph={} {} {}'.format(
+                rank, world, part, graph, 'OK' if good else 'FAIL',
+                {k: float('%.3g' % v) for k, v in e.items()}), flush=True)
+            del eng
+            torch.cuda.synchronize()
+            dist.barrier()
+    print('rank {} RESULT {}'.format(rank, 'PASS' if ok else 'FAIL'), flush=True)
+    # no destroy_process_group(): captured graphs still hold NCCL kernels (see bench.py)
+    os._exit(0 if ok else 1)
+
+
+if __name__ == '__main__':
+    main()
