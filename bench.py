@@ -35,6 +35,9 @@ def parse():
     ap.add_argument('--no-graph', action='store_true', help='eager launches instead of CUDA-graph replay')
     ap.add_argument('--no-l2-flush', action='store_true')
     ap.add_argument('--cpu-sample-steps', type=int, default=6)
+    ap.add_argument('--dist-profile', action='store_true',
+                    help='N > 1: after the timed region, two eager steps with CUDA events around every C-ABI call and '
+                         'every collective (rank 0 reports; collective times include waiting for the slowest rank)')
     ap.add_argument('--skip-cpu', action='store_true', help='no cpu_baseline leg (non-default workloads)')
     ap.add_argument('--skip-rooflines', action='store_true', help='no kernel roofline legs (non-default workloads)')
     ap.add_argument('--replicated-upper', action='store_true',
@@ -333,6 +336,16 @@ def run_ours(args):
         dev_ms, e2e_ms = float(t[0]), float(t[1])
     launches_per_step = getattr(eng, 'launches_per_step', None)
 
+    dist_prof = None
+    if world > 1 and args.dist_profile:
+        from bignn_b200 import dist as bdist
+        eng.last_static_batch = sb
+        bdist.TIMING = {}
+        prof = kernel_profile(torch, B, eng, steps=2, on_start=lambda: bdist.TIMING.clear())
+        coll = bdist.timing_summary(2)
+        bdist.TIMING = None
+        dist_prof = dict(kernels=prof, collectives={k: dict(ms_per_step=round(v[0], 4), calls_per_step=v[1])
+                                                    for k, v in sorted(coll.items(), key=lambda kv: -kv[1][0])})
     if rank != 0:
         return None
     out = dict(metric=METRIC, value=pairs_dev / (dev_ms * 1e-3), unit=UNIT, n_gpus=world, steps=args.steps,
@@ -346,10 +359,12 @@ def run_ours(args):
                         d2h_bytes_per_step=eng.d2h_bytes_per_step, ms_per_step=e2e_ms / args.steps,
                         wall_ms_per_step=wall_ms / args.steps),
                clocks=clk, last_loss=losses[-1] if losses else None)
+    if dist_prof is not None:
+        out['dist_profile'] = dist_prof
     return out, (torch, B, peaks, dev, eng, data, model)
 
 
-def kernel_profile(torch, B, eng, steps=3):
+def kernel_profile(torch, B, eng, steps=3, on_start=None):
     """Per-entry-point device time of one eager step (CUDA events around every C-ABI call on the
     launching stream) -- finds the dominant kernel and its average launch duration."""
     lib = B._lib
@@ -374,6 +389,8 @@ def kernel_profile(torch, B, eng, steps=3):
     n0 = lib.launch_count()
     eng._device_step(sb)           # eager warm-up of this path
     launches_per_step = lib.launch_count() - n0
+    if on_start is not None:
+        on_start()
     lib.call = timed
     ops_mod = B.ops
     try:

@@ -41,6 +41,7 @@ SIGNATURES = {
     'bignn_gemm_f32': ('i', 'iiiii' 'pl' 'pl' 'pl' 'pi' 'pl' 's'),
     'bignn_gemm_tc_supported': ('i', 'iii'),
     'bignn_gemm_tc_f32': ('i', 'iii' 'pl' 'pli' 'pl' 'pi' 's'),
+    'bignn_gemm_tc_masked_f32': ('i', 'iii' 'pl' 'pli' 'pl' 'pi' 'pli' 's'),
     'bignn_dw_tc_supported': ('i', 'iii'),
     'bignn_dw_tc_workspace_bytes': ('l', 'iii'),
     'bignn_dw_tc_f32': ('i', 'iii' 'pl' 'pl' 'p' 'ip' 'pl' 's'),
@@ -51,11 +52,11 @@ SIGNATURES = {
     'bignn_bn_seg_fwd': ('i', 'plpl' 'piii' 'pp' 'ff' 'ppp' 'pp' 'p' 'pl' 's'),
     'bignn_bn_running_update': ('i', 'ppiifppp' 's'),
     'bignn_bn_eval_fwd': ('i', 'plpl' 'ii' 'pp' 'f' 'pp' 's'),
-    'bignn_bn_seg_bwd': ('i', 'plplpl' 'piii' 'ppp' 'pp' 'pl' 's'),
+    'bignn_bn_seg_bwd': ('i', 'plplpl' 'piii' 'ppp' 'pp' 'i' 'pl' 's'),
     'bignn_bn_rows_workspace_bytes': ('l', 'ii'),
     'bignn_bn_rows_sums': ('i', 'plpl' 'iii' 'ppp' 'pl' 's'),
     'bignn_bn_rows_fwd_apply': ('i', 'plpl' 'iii' 'pl' 'pp' 'ff' 'ppp' 'pp' 's'),
-    'bignn_bn_rows_bwd_apply': ('i', 'plplpl' 'iii' 'ppp' 'pl' 's'),
+    'bignn_bn_rows_bwd_apply': ('i', 'plplpl' 'iii' 'ppp' 'pl' 'i' 's'),
     'bignn_readout_fwd': ('i', 'pl' 'pii' 'i' 'p' 'pli' 's'),
     'bignn_readout_bwd': ('i', 'pli' 'p' 'pii' 'i' 'pl' 'i' 's'),
     'bignn_pair_gather_norm_fwd': ('i', 'pl' 'pii' 'pl' 'p' 's'),

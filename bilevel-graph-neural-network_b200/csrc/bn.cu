@@ -94,24 +94,43 @@ k_bn_finalize(const double* __restrict__ ws_a, const double* __restrict__ ws_b,
   varu_d[i] = n > 1 ? var * ((double)n / (double)(n - 1)) : var;
 }
 
-__global__ void __launch_bounds__(256)
+// The S momentum updates of one channel are a sequential, float-rounded recurrence (the reference runs one
+// BatchNorm call per chunk, src/train.py:62-71) -- kept as such, but the operands of RB segments are fetched
+// together so that the dependent chain waits on arithmetic latency, not on one L2 round trip per segment.
+__global__ void __launch_bounds__(64)
 k_bn_running(const double* __restrict__ mean_d, const double* __restrict__ varu_d,
              const int32_t* __restrict__ seg_row_ptr, int S, int C, double momentum,
              float* __restrict__ running_mean, float* __restrict__ running_var,
              int64_t* __restrict__ nbt) {
+  constexpr int RB = 16;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) {
     float rm = running_mean[c], rv = running_var[c];
-    for (int s = 0; s < S; ++s) {
-      if (seg_row_ptr[s + 1] - seg_row_ptr[s] <= 0) continue;
-      rm = (float)(momentum * mean_d[(int64_t)s * C + c] + (1.0 - momentum) * (double)rm);
-      rv = (float)(momentum * varu_d[(int64_t)s * C + c] + (1.0 - momentum) * (double)rv);
+    const double keep = 1.0 - momentum;
+    for (int s0 = 0; s0 < S; s0 += RB) {
+      double mu[RB], vu[RB];
+      bool live[RB];
+#pragma unroll
+      for (int j = 0; j < RB; ++j) {
+        const int s = s0 + j;
+        live[j] = s < S && (seg_row_ptr[s + 1] - seg_row_ptr[s] > 0);
+        mu[j] = s < S ? mean_d[(int64_t)s * C + c] : 0.0;
+        vu[j] = s < S ? varu_d[(int64_t)s * C + c] : 0.0;
+      }
+#pragma unroll
+      for (int j = 0; j < RB; ++j) {
+        if (live[j]) {
+          rm = (float)(momentum * mu[j] + keep * (double)rm);
+          rv = (float)(momentum * vu[j] + keep * (double)rv);
+        }
+      }
     }
     running_mean[c] = rm;
     running_var[c] = rv;
   }
-  if (c == 0 && nbt) {
+  if (blockIdx.x == 0 && threadIdx.x == blockDim.x - 1 && nbt) {   // (a lane without a recurrence when C < 64)
     int64_t k = 0;
+#pragma unroll 8
     for (int s = 0; s < S; ++s) k += (seg_row_ptr[s + 1] - seg_row_ptr[s] > 0);
     *nbt += k;
   }
@@ -180,7 +199,8 @@ __global__ void __launch_bounds__(256)
 k_bn_bwd_apply(const float* __restrict__ X, int64_t ldx, const float* __restrict__ dY, int64_t lddy,
                float* __restrict__ dX, int64_t lddx, const int32_t* __restrict__ seg_row_ptr, int C, int parts,
                const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
-               const double* __restrict__ seg_a, const double* __restrict__ seg_b, int rows, int64_t n_total) {
+               const double* __restrict__ seg_a, const double* __restrict__ seg_b, int rows, int64_t n_total,
+               int in_act) {
   const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
   const int c = blockIdx.y * 32 + tx;
   const int s = blockIdx.x / parts, p = blockIdx.x % parts;
@@ -193,9 +213,19 @@ k_bn_bwd_apply(const float* __restrict__ X, int64_t ldx, const float* __restrict
   const float dgn = (float)(seg_b[(int64_t)s * C + c] / cnt);
   const float scale = rs * (gamma ? gamma[c] : 1.f);
   for (int r = r0 + ty; r < r1; r += BN_ROWS) {
-    const float xhat = (__ldg(X + (int64_t)r * ldx + c) - mu) * rs;
+    const float x = __ldg(X + (int64_t)r * ldx + c);
+    const float xhat = (x - mu) * rs;
     const float g = __ldg(dY + (int64_t)r * lddy + c);
-    dX[(int64_t)r * lddx + c] = (g - gmean - xhat * dgn) * scale;
+    float d = (g - gmean - xhat * dgn) * scale;
+    // X is the OUTPUT of the activation in front of this BatchNorm (model/layers.py:55-57): its derivative is
+    // applied here, on the value already in a register, instead of in a separate pass (same formulas as k_act_bwd)
+    switch (in_act) {
+      case BIGNN_ACT_RELU: d = x > 0.f ? d : 0.f; break;
+      case BIGNN_ACT_SIGMOID: d = d * ((1.0f - x) * x); break;
+      case BIGNN_ACT_TANH: d = d * (1.0f - x * x); break;
+      default: break;
+    }
+    dX[(int64_t)r * lddx + c] = d;
   }
 }
 
@@ -266,7 +296,7 @@ extern "C" int bignn_bn_seg_fwd(const float* X, int64_t ldx, float* Y, int64_t l
   k_bn_finalize<<<(int)ceil_div<int64_t>((int64_t)S * C, 256), 256, 0, st>>>(ws_a, ws_b, seg_row_ptr, S, C, parts, eps, mean, rstd, mean_d, varu_d);
   BIGNN_LAUNCH_COUNT(2);
   if (running_mean && running_var) {
-    k_bn_running<<<ceil_div(C, 256), 256, 0, st>>>(mean_d, varu_d, seg_row_ptr, S, C, (double)momentum, running_mean, running_var, num_batches_tracked);
+    k_bn_running<<<ceil_div(C, 64), 64, 0, st>>>(mean_d, varu_d, seg_row_ptr, S, C, (double)momentum, running_mean, running_var, num_batches_tracked);
     BIGNN_LAUNCH_COUNT(1);
   }
   k_bn_apply<<<grid, 256, 0, st>>>(X, ldx, Y, ldy, seg_row_ptr, C, parts, gamma, beta, mean, rstd, 0);
@@ -280,7 +310,7 @@ extern "C" int bignn_bn_running_update(const double* seg_stats, const int32_t* s
   if (S < 0 || C < 0) return BIGNN_EINVAL;
   if (S == 0 || C == 0) return 0;
   if (!seg_stats || !seg_row_ptr || !running_mean || !running_var) return BIGNN_EINVAL;
-  k_bn_running<<<ceil_div(C, 256), 256, 0, (cudaStream_t)stream>>>(seg_stats, seg_stats + (int64_t)S * C, seg_row_ptr, S,
+  k_bn_running<<<ceil_div(C, 64), 64, 0, (cudaStream_t)stream>>>(seg_stats, seg_stats + (int64_t)S * C, seg_row_ptr, S,
                                                                   C, (double)momentum, running_mean, running_var,
                                                                   num_batches_tracked);
   BIGNN_LAUNCH_COUNT(1);
@@ -305,8 +335,9 @@ extern "C" int bignn_bn_eval_fwd(const float* X, int64_t ldx, float* Y, int64_t 
 extern "C" int bignn_bn_seg_bwd(const float* X, int64_t ldx, const float* dY, int64_t lddy, float* dX,
                                 int64_t lddx, const int32_t* seg_row_ptr, int32_t S, int32_t C, int32_t parts,
                                 const float* gamma, const float* mean, const float* rstd, float* dgamma,
-                                float* dbeta, void* workspace, int64_t workspace_bytes, void* stream) {
-  if (S < 0 || C < 0 || parts <= 0) return BIGNN_EINVAL;
+                                float* dbeta, int32_t input_act, void* workspace, int64_t workspace_bytes,
+                                void* stream) {
+  if (S < 0 || C < 0 || parts <= 0 || input_act < 0 || input_act > BIGNN_ACT_TANH) return BIGNN_EINVAL;
   if (S == 0 || C == 0) return 0;
   if (!X || !dY || !dX || !seg_row_ptr || !mean || !rstd || ldx < C || lddy < C || lddx < C) return BIGNN_EINVAL;
   if ((int64_t)S * parts > 2147483647LL) return BIGNN_EINVAL;
@@ -320,7 +351,7 @@ extern "C" int bignn_bn_seg_bwd(const float* X, int64_t ldx, const float* dY, in
   k_bn_reduce_part<true><<<grid, 256, 0, st>>>(X, ldx, dY, lddy, seg_row_ptr, C, parts, mean, rstd, ws_a, ws_b, 0);
   k_bn_bwd_finalize<<<(int)ceil_div<int64_t>((int64_t)S * C, 256), 256, 0, st>>>(ws_a, ws_b, S, C, parts, seg_a, seg_b);
   k_bn_bwd_params<<<ceil_div(C, 256), 256, 0, st>>>(seg_a, seg_b, S, C, dgamma, dbeta);
-  k_bn_bwd_apply<<<grid, 256, 0, st>>>(X, ldx, dY, lddy, dX, lddx, seg_row_ptr, C, parts, gamma, mean, rstd, seg_a, seg_b, 0, 0);
+  k_bn_bwd_apply<<<grid, 256, 0, st>>>(X, ldx, dY, lddy, dX, lddx, seg_row_ptr, C, parts, gamma, mean, rstd, seg_a, seg_b, 0, 0, input_act);
   BIGNN_LAUNCH_COUNT(4);
   return last_launch_status();
 }
@@ -374,13 +405,13 @@ extern "C" int bignn_bn_rows_fwd_apply(const float* X, int64_t ldx, float* Y, in
 extern "C" int bignn_bn_rows_bwd_apply(const float* X, int64_t ldx, const float* dY, int64_t lddy, float* dX,
                                        int64_t lddx, int32_t rows, int32_t C, int32_t parts, const float* gamma,
                                        const float* mean, const float* rstd, const double* sums, int64_t n_total,
-                                       void* stream) {
-  if (rows < 0 || C < 0 || parts <= 0 || n_total < rows) return BIGNN_EINVAL;
+                                       int32_t input_act, void* stream) {
+  if (rows < 0 || C < 0 || parts <= 0 || n_total < rows || input_act < 0 || input_act > BIGNN_ACT_TANH) return BIGNN_EINVAL;
   if (rows == 0 || C == 0) return 0;
   if (!X || !dY || !dX || !mean || !rstd || !sums || ldx < C || lddy < C || lddx < C) return BIGNN_EINVAL;
   dim3 grid(parts, ceil_div(C, 32));
   k_bn_bwd_apply<<<grid, 256, 0, (cudaStream_t)stream>>>(X, ldx, dY, lddy, dX, lddx, nullptr, C, parts, gamma, mean,
-                                                          rstd, sums, sums + C, rows, n_total);
+                                                          rstd, sums, sums + C, rows, n_total, input_act);
   BIGNN_LAUNCH_COUNT(1);
   return last_launch_status();
 }

@@ -37,10 +37,22 @@ namespace bignn {
 // accumulation chain drifts (measured -2.1e-8 * K relative).  The hi*hi products rotate over NA
 // accumulators, the 2^-11-scaled correction products use their own, and the epilogue adds them in
 // fp32 round-to-nearest.
+// out * act'(y) from the activation OUTPUT y (the formulas of k_act_bwd): the fused activation backward of the
+// backward-input GEMM  dT = (g W) * act'(t)
+__device__ __forceinline__ float mask1(float o, float y, int mask_act) {
+  switch (mask_act) {
+    case BIGNN_ACT_RELU: return y > 0.f ? o : 0.f;
+    case BIGNN_ACT_SIGMOID: return o * ((1.0f - y) * y);
+    case BIGNN_ACT_TANH: return o * (1.0f - y * y);
+    default: return o;
+  }
+}
+
 template <int NPAD, int KCH>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 k_gemm_tc(int M, int N, int K, const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb,
-          int b_is_nk, float* __restrict__ C, int64_t ldc, const float* __restrict__ bias, int act) {
+          int b_is_nk, float* __restrict__ C, int64_t ldc, const float* __restrict__ bias, int act,
+          const float* __restrict__ mask_y, int64_t ldmy, int mask_act) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int A_BYTES = TC_BM * 128;            // one K chunk of the A tile
   constexpr int B_BYTES = NPAD * 128;
@@ -107,7 +119,8 @@ k_gemm_tc(int M, int N, int K, const float* __restrict__ A, int64_t lda, const f
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = tmem_base_s;
   const uint32_t idesc = umma_idesc_tf32(TC_BM, NPAD);
-  const bool c_vec = ((ldc & 3) == 0) && aligned16(C) && ((N & 3) == 0);
+  const bool c_vec = ((ldc & 3) == 0) && aligned16(C) && ((N & 3) == 0) &&
+                     (mask_y == nullptr || (((ldmy & 3) == 0) && aligned16(mask_y)));
   const int n_main = (K + 7) / 8 < NA ? (K + 7) / 8 : NA;
 
   uint32_t phase = 0;
@@ -199,7 +212,16 @@ k_gemm_tc(int M, int N, int K, const float* __restrict__ A, int64_t lda, const f
           o.x = fmaxf(o.x + b4.x, 0.f); o.y = fmaxf(o.y + b4.y, 0.f); o.z = fmaxf(o.z + b4.z, 0.f); o.w = fmaxf(o.w + b4.w, 0.f);
           st4(C + (int64_t)(m0 + r) * ldc + 4 * c4, o);
         }
-      } else if (act == BIGNN_ACT_IDENTITY) {
+      } else if (act == BIGNN_ACT_IDENTITY && mask_y != nullptr && mask_act == BIGNN_ACT_RELU) {
+#pragma unroll 4
+        for (int r = tid / N4; r < rows_here; r += RSTEP) {       // backward-input GEMM with the ReLU mask of t
+          float4 o = *reinterpret_cast<const float4*>(src + sw128_off(r, c4 & 7));
+          const float4 y = ldg4(mask_y + (int64_t)(m0 + r) * ldmy + 4 * c4);
+          o.x = y.x > 0.f ? o.x + b4.x : 0.f; o.y = y.y > 0.f ? o.y + b4.y : 0.f;
+          o.z = y.z > 0.f ? o.z + b4.z : 0.f; o.w = y.w > 0.f ? o.w + b4.w : 0.f;
+          st4(C + (int64_t)(m0 + r) * ldc + 4 * c4, o);
+        }
+      } else if (act == BIGNN_ACT_IDENTITY && mask_y == nullptr) {
 #pragma unroll 4
         for (int r = tid / N4; r < rows_here; r += RSTEP) {
           float4 o = *reinterpret_cast<const float4*>(src + sw128_off(r, c4 & 7));
@@ -212,6 +234,11 @@ k_gemm_tc(int M, int N, int K, const float* __restrict__ A, int64_t lda, const f
           float4 o = *reinterpret_cast<const float4*>(src + sw128_off(r, c4 & 7));
           o.x = apply_act(o.x + b4.x, act); o.y = apply_act(o.y + b4.y, act);
           o.z = apply_act(o.z + b4.z, act); o.w = apply_act(o.w + b4.w, act);
+          if (mask_y) {
+            const float4 y = ldg4(mask_y + (int64_t)(m0 + r) * ldmy + 4 * c4);
+            o.x = mask1(o.x, y.x, mask_act); o.y = mask1(o.y, y.y, mask_act);
+            o.z = mask1(o.z, y.z, mask_act); o.w = mask1(o.w, y.w, mask_act);
+          }
           st4(C + (int64_t)(m0 + r) * ldc + 4 * c4, o);
         }
       }
@@ -229,6 +256,11 @@ k_gemm_tc(int M, int N, int K, const float* __restrict__ A, int64_t lda, const f
           if (act != BIGNN_ACT_IDENTITY) {
             o.x = apply_act(o.x, act); o.y = apply_act(o.y, act); o.z = apply_act(o.z, act); o.w = apply_act(o.w, act);
           }
+          if (mask_y) {
+            const float4 y = ldg4(mask_y + (int64_t)(m0 + r) * ldmy + 4 * c4);
+            o.x = mask1(o.x, y.x, mask_act); o.y = mask1(o.y, y.y, mask_act);
+            o.z = mask1(o.z, y.z, mask_act); o.w = mask1(o.w, y.w, mask_act);
+          }
           st4(C + (int64_t)(m0 + r) * ldc + 4 * c4, o);
         }
       }
@@ -239,7 +271,9 @@ k_gemm_tc(int M, int N, int K, const float* __restrict__ A, int64_t lda, const f
         if (m0 + r < M) {
           float o = *reinterpret_cast<const float*>(a_lo + (n >> 5) * A_BYTES + sw128_off(r, (n & 31) >> 2) + (n & 3) * 4);
           if (bias) o += __ldg(bias + n);
-          C[(int64_t)(m0 + r) * ldc + n] = apply_act(o, act);
+          o = apply_act(o, act);
+          if (mask_y) o = mask1(o, __ldg(mask_y + (int64_t)(m0 + r) * ldmy + n), mask_act);
+          C[(int64_t)(m0 + r) * ldc + n] = o;
         }
       }
     }
@@ -255,7 +289,8 @@ k_gemm_tc(int M, int N, int K, const float* __restrict__ A, int64_t lda, const f
 
 template <int NPAD, int KCH>
 static int launch_tc(int M, int N, int K, const float* A, int64_t lda, const float* B, int64_t ldb, int b_is_nk,
-                     float* C, int64_t ldc, const float* bias, int act, cudaStream_t st) {
+                     float* C, int64_t ldc, const float* bias, int act, const float* mask_y, int64_t ldmy,
+                     int mask_act, cudaStream_t st) {
   constexpr int lo_ch = KCH > NPAD / 32 ? KCH : NPAD / 32;
   constexpr int smem = (KCH + lo_ch) * TC_BM * 128 + 2 * KCH * NPAD * 128 + 1024;
   static bool configured = false;
@@ -267,17 +302,20 @@ static int launch_tc(int M, int N, int K, const float* A, int64_t lda, const flo
   const int n_tiles = ceil_div(M, TC_BM);
   int grid = 2 * sm_count();
   if (grid > n_tiles) grid = n_tiles;
-  k_gemm_tc<NPAD, KCH><<<grid, TC_THREADS, smem, st>>>(M, N, K, A, lda, B, ldb, b_is_nk, C, ldc, bias, act);
+  k_gemm_tc<NPAD, KCH><<<grid, TC_THREADS, smem, st>>>(M, N, K, A, lda, B, ldb, b_is_nk, C, ldc, bias, act, mask_y,
+                                                       ldmy, mask_act);
   BIGNN_LAUNCH_COUNT(1);
   return last_launch_status();
 }
 
 template <int NPAD>
 static int launch_tc_k(int M, int N, int K, const float* A, int64_t lda, const float* B, int64_t ldb, int b_is_nk,
-                       float* C, int64_t ldc, const float* bias, int act, cudaStream_t st) {
-  if (K <= 32) return launch_tc<NPAD, 1>(M, N, K, A, lda, B, ldb, b_is_nk, C, ldc, bias, act, st);
-  if (K <= 64) return launch_tc<NPAD, 2>(M, N, K, A, lda, B, ldb, b_is_nk, C, ldc, bias, act, st);
-  if (NPAD <= 64 && K <= 96) return launch_tc<NPAD, 3>(M, N, K, A, lda, B, ldb, b_is_nk, C, ldc, bias, act, st);
+                       float* C, int64_t ldc, const float* bias, int act, const float* mask_y, int64_t ldmy,
+                       int mask_act, cudaStream_t st) {
+  if (K <= 32) return launch_tc<NPAD, 1>(M, N, K, A, lda, B, ldb, b_is_nk, C, ldc, bias, act, mask_y, ldmy, mask_act, st);
+  if (K <= 64) return launch_tc<NPAD, 2>(M, N, K, A, lda, B, ldb, b_is_nk, C, ldc, bias, act, mask_y, ldmy, mask_act, st);
+  if (NPAD <= 64 && K <= 96)
+    return launch_tc<NPAD, 3>(M, N, K, A, lda, B, ldb, b_is_nk, C, ldc, bias, act, mask_y, ldmy, mask_act, st);
   return BIGNN_EINVAL;
 }
 
@@ -290,18 +328,27 @@ extern "C" int bignn_gemm_tc_supported(int32_t M, int32_t N, int32_t K) {
   return (K <= 64 || (N <= 64 && K <= 96)) ? 1 : 0;
 }
 
-extern "C" int bignn_gemm_tc_f32(int32_t M, int32_t N, int32_t K, const float* A, int64_t lda, const float* B,
-                                 int64_t ldb, int32_t b_is_nk, float* C, int64_t ldc, const float* bias, int32_t act,
-                                 void* stream) {
+extern "C" int bignn_gemm_tc_masked_f32(int32_t M, int32_t N, int32_t K, const float* A, int64_t lda, const float* B,
+                                        int64_t ldb, int32_t b_is_nk, float* C, int64_t ldc, const float* bias,
+                                        int32_t act, const float* mask_y, int64_t ldmy, int32_t mask_act,
+                                        void* stream) {
   if (M < 0 || N < 0 || K < 0) return BIGNN_EINVAL;
   if (M == 0 || N == 0) return 0;
   if (K == 0 || !A || !B || !C || ldc < N || lda < K) return BIGNN_EINVAL;
   if (!bignn_gemm_tc_supported(M, N, K)) return BIGNN_EINVAL;   // two CTAs/SM: operands must fit in ~110 KB
   if ((lda & 3) || !aligned16(A)) return BIGNN_EALIGN;          // 128-bit cp.async of the A rows
   if (act < 0 || act > BIGNN_ACT_TANH) return BIGNN_EINVAL;
+  if (mask_y && (ldmy < N || mask_act < 0 || mask_act > BIGNN_ACT_TANH)) return BIGNN_EINVAL;
+  if (!mask_y || mask_act == BIGNN_ACT_IDENTITY) { mask_y = nullptr; mask_act = 0; }
   cudaStream_t st = (cudaStream_t)stream;
-  if (N <= 32) return launch_tc_k<32>(M, N, K, A, lda, B, ldb, b_is_nk, C, ldc, bias, act, st);
-  if (N <= 64) return launch_tc_k<64>(M, N, K, A, lda, B, ldb, b_is_nk, C, ldc, bias, act, st);
-  if (N <= 96) return launch_tc_k<96>(M, N, K, A, lda, B, ldb, b_is_nk, C, ldc, bias, act, st);
-  return launch_tc_k<128>(M, N, K, A, lda, B, ldb, b_is_nk, C, ldc, bias, act, st);
+  if (N <= 32) return launch_tc_k<32>(M, N, K, A, lda, B, ldb, b_is_nk, C, ldc, bias, act, mask_y, ldmy, mask_act, st);
+  if (N <= 64) return launch_tc_k<64>(M, N, K, A, lda, B, ldb, b_is_nk, C, ldc, bias, act, mask_y, ldmy, mask_act, st);
+  if (N <= 96) return launch_tc_k<96>(M, N, K, A, lda, B, ldb, b_is_nk, C, ldc, bias, act, mask_y, ldmy, mask_act, st);
+  return launch_tc_k<128>(M, N, K, A, lda, B, ldb, b_is_nk, C, ldc, bias, act, mask_y, ldmy, mask_act, st);
+}
+
+extern "C" int bignn_gemm_tc_f32(int32_t M, int32_t N, int32_t K, const float* A, int64_t lda, const float* B,
+                                 int64_t ldb, int32_t b_is_nk, float* C, int64_t ldc, const float* bias, int32_t act,
+                                 void* stream) {
+  return bignn_gemm_tc_masked_f32(M, N, K, A, lda, B, ldb, b_is_nk, C, ldc, bias, act, nullptr, 0, 0, stream);
 }

@@ -20,6 +20,33 @@ def is_dist():
     return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
 
+# ---- optional per-collective device timing (bench.py --dist-profile; eager steps only, never under capture)
+TIMING = None          # None = off; else {tag: [(start event, end event), ...]}
+
+
+class _timed(object):
+    def __init__(self, tag):
+        self.tag = tag
+
+    def __enter__(self):
+        if TIMING is not None and torch.cuda.is_available():
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *a):
+        if TIMING is not None and torch.cuda.is_available():
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            TIMING.setdefault(self.tag, []).append((self.e0, e1))
+
+
+def timing_summary(steps=1):
+    """{tag: (ms per step, calls per step)} of the collectives recorded since TIMING was set (includes the
+    wait for the slowest rank)."""
+    torch.cuda.synchronize()
+    return {k: (sum(a.elapsed_time(b) for a, b in v) / steps, len(v) // steps) for k, v in (TIMING or {}).items()}
+
+
 def shard_chunks(chunk_weights, world):
     """Contiguous blocks of chunks per rank, balanced by weight (atoms).  Returns [(lo, hi)]."""
     w = np.asarray(chunk_weights, np.float64)
@@ -48,7 +75,8 @@ class _SumDisjointRows(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, group):
         x = x.contiguous()
-        dist.all_reduce(x, op=dist.ReduceOp.SUM, group=group)
+        with _timed('pooled_rows_all_reduce'):
+            dist.all_reduce(x, op=dist.ReduceOp.SUM, group=group)
         return x
 
     @staticmethod
@@ -71,7 +99,8 @@ def all_reduce_grads(params, group=None):
     if not grads:
         return
     flat = torch.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    with _timed('grad_all_reduce'):
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     off = 0
     for g in grads:
         n = g.numel()
@@ -87,7 +116,8 @@ def gather_chunk_stats(stats_local, s_max, group=None):
     pad = torch.zeros((2, s_max, C), dtype=stats_local.dtype, device=stats_local.device)
     pad[:, :s_loc] = stats_local
     out = torch.empty((world, 2, s_max, C), dtype=stats_local.dtype, device=stats_local.device)
-    dist.all_gather_into_tensor(out.view(-1), pad.view(-1), group=group)
+    with _timed('bn_chunk_stats_all_gather'):
+        dist.all_gather_into_tensor(out.view(-1), pad.view(-1), group=group)
     return out
 
 
@@ -112,7 +142,8 @@ def gather_rows(x_loc, pg):
         mine[pg.n_loc:].zero_()
     if pg.world > 1:
         src = mine if x_loc.is_cuda else mine.clone()          # gloo (CPU tests): no aliasing of in/out
-        dist.all_gather_into_tensor(out.view(-1), src.reshape(-1), group=pg.group)
+        with _timed('upper_rows_all_gather'):
+            dist.all_gather_into_tensor(out.view(-1), src.reshape(-1), group=pg.group)
     return out
 
 
@@ -125,13 +156,15 @@ class _ExchangePooledRows(torch.autograd.Function):
     def forward(ctx, x, group):
         ctx.group = group
         x = x.contiguous()
-        dist.all_reduce(x, op=dist.ReduceOp.SUM, group=group)
+        with _timed('pooled_rows_exchange_fwd'):
+            dist.all_reduce(x, op=dist.ReduceOp.SUM, group=group)
         return x
 
     @staticmethod
     def backward(ctx, g):
         g = g.contiguous().clone()
-        dist.all_reduce(g, op=dist.ReduceOp.SUM, group=ctx.group)
+        with _timed('pooled_rows_exchange_bwd'):
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=ctx.group)
         return g, None
 
 
@@ -146,11 +179,11 @@ class _GcnPropagateRows(torch.autograd.Function):
     all-gather + local SpMM on act'(u) * du (A symmetric); dbias is this rank's partial column sum."""
 
     @staticmethod
-    def forward(ctx, h_loc, bias, pg, act):
+    def forward(ctx, h_loc, bias, pg, act, act_bwd_by_consumer=False):
         from . import ops
         H = gather_rows(h_loc, pg)
         u = ops.spmm(pg.csr, H, ops.SPMM_GCN, 0.0, pg.csr.dinv(), bias, act)
-        ctx.pg, ctx.act, ctx.has_bias = pg, act, bias is not None
+        ctx.pg, ctx.act, ctx.has_bias = pg, (0 if act_bwd_by_consumer else act), bias is not None
         ctx.save_for_backward(u)
         return u
 
@@ -165,11 +198,11 @@ class _GcnPropagateRows(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             G = gather_rows(g, pg)
             dh = ops.spmm(pg.csr, G, ops.SPMM_GCN, 0.0, pg.csr.dinv(), None, 0)
-        return dh, dbias, None, None
+        return dh, dbias, None, None, None
 
 
-def gcn_propagate_rows(h_loc, bias, pg, act=0):
-    return _GcnPropagateRows.apply(h_loc, bias, pg, act)
+def gcn_propagate_rows(h_loc, bias, pg, act=0, act_bwd_by_consumer=False):
+    return _GcnPropagateRows.apply(h_loc, bias, pg, act, act_bwd_by_consumer)
 
 
 class _RowsBatchNorm(torch.autograd.Function):
@@ -177,7 +210,7 @@ class _RowsBatchNorm(torch.autograd.Function):
     all-reduce, local apply (bignn_bn_rows_*).  dgamma / dbeta come out rank-summed (global)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, pg, running_mean, running_var, nbt, eps, momentum):
+    def forward(ctx, x, gamma, beta, pg, running_mean, running_var, nbt, eps, momentum, input_act=0):
         from . import ops, _lib
         x = ops._f32c(x)
         _lib.require_device(x)
@@ -188,13 +221,14 @@ class _RowsBatchNorm(torch.autograd.Function):
         sums = torch.empty((2, C), dtype=torch.float64, device=x.device)
         _lib.call('bignn_bn_rows_sums', x, x.stride(0), None, 0, rows, C, parts, None, None, sums, ws, int(wsb))
         if pg.world > 1:
-            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=pg.group)
+            with _timed('upper_bn_stats_all_reduce'):
+                dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=pg.group)
         y = torch.empty_like(x)
         mean = torch.empty(C, dtype=torch.float32, device=x.device)
         rstd = torch.empty(C, dtype=torch.float32, device=x.device)
         _lib.call('bignn_bn_rows_fwd_apply', x, x.stride(0), y, y.stride(0), rows, C, parts, sums, int(pg.n),
                   gamma, beta, float(eps), float(momentum), running_mean, running_var, nbt, mean, rstd)
-        ctx.pg, ctx.parts = pg, parts
+        ctx.pg, ctx.parts, ctx.input_act = pg, parts, int(input_act)
         ctx.save_for_backward(x, gamma, mean, rstd)
         return y
 
@@ -211,16 +245,17 @@ class _RowsBatchNorm(torch.autograd.Function):
         _lib.call('bignn_bn_rows_sums', x, x.stride(0), dy, dy.stride(0), rows, C, parts, mean, rstd, sums, ws,
                   int(wsb))
         if pg.world > 1:
-            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=pg.group)
+            with _timed('upper_bn_stats_all_reduce'):
+                dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=pg.group)
         dx = torch.empty_like(x)
         _lib.call('bignn_bn_rows_bwd_apply', x, x.stride(0), dy, dy.stride(0), dx, dx.stride(0), rows, C, parts,
-                  gamma, mean, rstd, sums, int(pg.n))
+                  gamma, mean, rstd, sums, int(pg.n), ctx.input_act)
         dbeta, dgamma = sums[0].to(torch.float32), sums[1].to(torch.float32)
-        return dx, dgamma, dbeta, None, None, None, None, None, None
+        return dx, dgamma, dbeta, None, None, None, None, None, None, None
 
 
-def rows_batch_norm(x, gamma, beta, pg, running_mean, running_var, nbt, eps=1e-5, momentum=0.1):
-    return _RowsBatchNorm.apply(x, gamma, beta, pg, running_mean, running_var, nbt, eps, momentum)
+def rows_batch_norm(x, gamma, beta, pg, running_mean, running_var, nbt, eps=1e-5, momentum=0.1, input_act=0):
+    return _RowsBatchNorm.apply(x, gamma, beta, pg, running_mean, running_var, nbt, eps, momentum, input_act)
 
 
 class _GatherRowsReplicatedConsumer(torch.autograd.Function):

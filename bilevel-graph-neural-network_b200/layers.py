@@ -88,14 +88,18 @@ class NodeEmbedding(nn.Module):
         if parted and self.type != 'gcn':
             raise NotImplementedError('row-partitioned upper level: only GCN layers are partitioned; run the '
                                       '{} upper level replicated (BiGNNEngine(partition_upper=False))'.format(self.type))
+        # the activation's derivative is folded into the backward of the BatchNorm that follows it (one pass less
+        # over [rows, C]); only when the activation output feeds nothing but that BatchNorm
+        fuse = bool(self.bn) and self.training and a is not None and a != 0 and self.type in ('gcn', 'gin')
+        in_act = a if fuse else 0
         if parted:
             h = ops.linear_act(ins, self.conv.weight, None, 0, 'io')           # own rows only
-            x = bdist.gcn_propagate_rows(h, self.conv.bias, graph, a if a is not None else 0)
+            x = bdist.gcn_propagate_rows(h, self.conv.bias, graph, a if a is not None else 0, fuse)
             if a is None:
                 x = self.act(x)
         elif self.type == 'gcn':
             h = ops.linear_act(ins, self.conv.weight, None, 0, 'io')
-            x = ops.gcn_propagate(h, self.conv.bias, csr, a if a is not None else 0)
+            x = ops.gcn_propagate(h, self.conv.bias, csr, a if a is not None else 0, fuse)
             if a is None:
                 x = self.act(x)
         elif self.type == 'gat':
@@ -105,12 +109,15 @@ class NodeEmbedding(nn.Module):
         else:
             z = ops.gin_aggregate(ins, csr, self._eps_value())
             lin1, lin2 = self.conv.nn[0], self.conv.nn[2]
-            t = apply_linear_act(z, lin1, self.act)
-            x = apply_linear_act(t, lin2, self.act)
+            # Linear -> act -> Linear (model/layers.py:27-29): the inner activation's derivative is applied in the
+            # epilogue of the second Linear's backward-input GEMM (t is its saved input)
+            inner = a if (a is not None and a != 0) else 0
+            t = apply_linear_act(z, lin1, self.act, act_bwd_by_consumer=bool(inner))
+            x = apply_linear_act(t, lin2, self.act, act_bwd_by_consumer=fuse, input_act=inner)
         if self.bn and parted and self.training:
             x = bdist.rows_batch_norm(x, self.bn.weight, self.bn.bias, graph, self.bn.running_mean,
                                       self.bn.running_var, self.bn.num_batches_tracked, self.bn.eps,
-                                      self.bn.momentum)
+                                      self.bn.momentum, in_act)
         elif self.bn:
             sink = getattr(graph, 'bn_stats_sink', None)
             if self.training and sink is not None:
@@ -118,12 +125,12 @@ class NodeEmbedding(nn.Module):
                 # the running-buffer updates in global chunk order after exchanging them
                 stats = torch.empty((2, S, x.shape[1]), dtype=torch.float64, device=x.device)
                 x = ops.seg_batch_norm(x, self.bn.weight, self.bn.bias, seg, S, None, None, None,
-                                       self.bn.eps, self.bn.momentum, stats)
+                                       self.bn.eps, self.bn.momentum, stats, in_act)
                 sink.append((self.bn, stats))
             elif self.training:
                 x = ops.seg_batch_norm(x, self.bn.weight, self.bn.bias, seg, S, self.bn.running_mean,
                                        self.bn.running_var, self.bn.num_batches_tracked,
-                                       self.bn.eps, self.bn.momentum)
+                                       self.bn.eps, self.bn.momentum, None, in_act)
             else:
                 x = ops.bn_eval(x, self.bn.weight, self.bn.bias, self.bn.running_mean, self.bn.running_var,
                                 self.bn.eps)

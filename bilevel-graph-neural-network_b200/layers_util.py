@@ -38,13 +38,14 @@ def create_act(act, num_parameters=None):
     raise ValueError('Unknown activation function {}'.format(act))
 
 
-def apply_linear_act(x, lin, act_module, layout='oi'):
-    """act(linear(x)) with the activation fused into the GEMM epilogue when it can be."""
+def apply_linear_act(x, lin, act_module, layout='oi', act_bwd_by_consumer=False, input_act=0):
+    """act(linear(x)) with the activation fused into the GEMM epilogue when it can be.
+    act_bwd_by_consumer: the (BatchNorm) consumer folds act' into its backward (ops.seg_batch_norm input_act)."""
     if act_module is None:
-        return ops.linear_act(x, lin.weight, lin.bias, 0, layout)
+        return ops.linear_act(x, lin.weight, lin.bias, 0, layout, False, input_act)
     if act_module.code is not None:
-        return ops.linear_act(x, lin.weight, lin.bias, act_module.code, layout)
-    return act_module(ops.linear_act(x, lin.weight, lin.bias, 0, layout))
+        return ops.linear_act(x, lin.weight, lin.bias, act_module.code, layout, act_bwd_by_consumer, input_act)
+    return act_module(ops.linear_act(x, lin.weight, lin.bias, 0, layout, False, input_act))
 
 
 class MLP(nn.Module):

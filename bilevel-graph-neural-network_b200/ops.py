@@ -138,8 +138,8 @@ TC_MIN_ROWS = 512      # below this a 128-row tensor-core tile grid cannot fill 
 _NO_TC = bool(_os.environ.get('BIGNN_NO_TC'))      # debugging switch: route the transforms to the SIMT kernels
 
 
-def gemm_tc(a, b, b_is_nk, bias=None, act=0, out=None):
-    """C = act(a @ op(b) + bias) on the tensor cores (tcgen05, 3xTF32)."""
+def gemm_tc(a, b, b_is_nk, bias=None, act=0, out=None, mask_y=None, mask_act=0):
+    """C = act(a @ op(b) + bias) [* mask_act'(mask_y)] on the tensor cores (tcgen05, 3xTF32)."""
     a, b = _f32c(a), _f32c(b)
     _lib.require_device(a, b)
     M, K = a.shape
@@ -147,6 +147,13 @@ def gemm_tc(a, b, b_is_nk, bias=None, act=0, out=None):
     if (b.shape[1] if b_is_nk else b.shape[0]) != K:
         raise ValueError('gemm_tc: inner dimensions differ')
     c = out if out is not None else torch.empty((M, N), dtype=torch.float32, device=a.device)
+    if mask_y is not None and mask_act:
+        mask_y = _f32c(mask_y)
+        if tuple(mask_y.shape) != (M, N):
+            raise ValueError('gemm_tc: mask shape {} != output shape {}'.format(tuple(mask_y.shape), (M, N)))
+        _lib.call('bignn_gemm_tc_masked_f32', M, N, K, a, a.stride(0), b, b.stride(0), int(bool(b_is_nk)), c,
+                  c.stride(0), bias, int(act), mask_y, mask_y.stride(0), int(mask_act))
+        return c
     _lib.call('bignn_gemm_tc_f32', M, N, K, a, a.stride(0), b, b.stride(0), int(bool(b_is_nk)), c, c.stride(0), bias,
               int(act))
     return c
@@ -221,9 +228,9 @@ class _GcnPropagate(torch.autograd.Function):
     """u = act(D^-1/2 (A+I) D^-1/2 h + bias)  (PyG GCNConv propagate + model/layers.py:55)."""
 
     @staticmethod
-    def forward(ctx, h, bias, csr, act):
+    def forward(ctx, h, bias, csr, act, act_bwd_by_consumer=False):
         u = spmm(csr, h, SPMM_GCN, 0.0, csr.dinv(), bias, act)
-        ctx.csr, ctx.act, ctx.has_bias = csr, act, bias is not None
+        ctx.csr, ctx.act, ctx.has_bias = csr, (0 if act_bwd_by_consumer else act), bias is not None
         ctx.save_for_backward(u)
         return u
 
@@ -233,7 +240,7 @@ class _GcnPropagate(torch.autograd.Function):
         g = act_bwd(u, du, ctx.act)
         dbias = colsum(g) if ctx.has_bias and ctx.needs_input_grad[1] else None
         dh = spmm(ctx.csr, g, SPMM_GCN, 0.0, ctx.csr.dinv(), None, 0) if ctx.needs_input_grad[0] else None
-        return dh, dbias, None, None
+        return dh, dbias, None, None, None
 
 
 class _SumRows(torch.autograd.Function):
@@ -253,13 +260,17 @@ class _LinearAct(torch.autograd.Function):
     """y = act(x W^T + b) (layout 'oi', nn.Linear) or act(x W + b) (layout 'io', PyG)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, act, layout):
+    def forward(ctx, x, weight, bias, act, layout, act_bwd_by_consumer=False, input_act=0):
         N = weight.shape[0] if layout == 'oi' else weight.shape[1]
         if use_tc(x.shape[0], N, x.shape[1]):
             y = gemm_tc(x, weight, layout == 'oi', bias, act)
         else:
             y = gemm(x, weight, False, layout == 'oi', bias, act)
-        ctx.act, ctx.layout = act, layout
+        # act_bwd_by_consumer: the BatchNorm that consumes y folds act'(y) into its own backward
+        # (bignn_bn_seg_bwd input_act), so the incoming gradient is already w.r.t. the pre-activation
+        # input_act: x is the output of that activation and ITS producer was told act_bwd_by_consumer: dX is
+        # returned w.r.t. the activation's input (mask fused into the backward-input GEMM's epilogue)
+        ctx.act, ctx.layout, ctx.input_act = (0 if act_bwd_by_consumer else act), layout, int(input_act)
         ctx.save_for_backward(x, weight, y)
         return y
 
@@ -271,9 +282,12 @@ class _LinearAct(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             if use_tc(g.shape[0], x.shape[1], g.shape[1]):
                 # dX = g W (oi: W is [N,K] = op(B)^T stored [K',N'] -> b_is_nk False) / g W^T (io)
-                dx = gemm_tc(g, weight, ctx.layout == 'io')
+                dx = gemm_tc(g, weight, ctx.layout == 'io', mask_y=x if ctx.input_act else None,
+                             mask_act=ctx.input_act)
             else:
                 dx = gemm(g, weight, False, ctx.layout == 'io')
+                if ctx.input_act:
+                    dx = act_bwd(x, dx, ctx.input_act)
         want_b = ctx.needs_input_grad[2]
         if ctx.needs_input_grad[1] and use_dw_tc(g.shape[0], g.shape[1], x.shape[1]):
             if ctx.layout == 'oi':
@@ -285,14 +299,15 @@ class _LinearAct(torch.autograd.Function):
                 dw = gemm(g, x, True, False) if ctx.layout == 'oi' else gemm(x, g, True, False)
             if want_b:
                 db = colsum(g)
-        return dx, dw, db, None, None
+        return dx, dw, db, None, None, None, None
 
 
 class _SegBatchNorm(torch.autograd.Function):
     """Train-mode BatchNorm1d with independent statistics per row segment."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, seg_row_ptr, S, running_mean, running_var, nbt, eps, momentum, stats_out):
+    def forward(ctx, x, gamma, beta, seg_row_ptr, S, running_mean, running_var, nbt, eps, momentum, stats_out,
+                input_act=0):
         x = _f32c(x)
         _lib.require_device(x)
         rows, C = x.shape
@@ -304,7 +319,7 @@ class _SegBatchNorm(torch.autograd.Function):
         ws = _ws(wsb, x.device)
         _lib.call('bignn_bn_seg_fwd', x, x.stride(0), y, y.stride(0), seg_row_ptr, S, C, parts, gamma, beta,
                   float(eps), float(momentum), running_mean, running_var, nbt, mean, rstd, stats_out, ws, int(wsb))
-        ctx.S, ctx.parts, ctx.seg = S, parts, seg_row_ptr
+        ctx.S, ctx.parts, ctx.seg, ctx.input_act = S, parts, seg_row_ptr, int(input_act)
         ctx.save_for_backward(x, gamma, mean, rstd)
         return y
 
@@ -319,8 +334,8 @@ class _SegBatchNorm(torch.autograd.Function):
         wsb = _lib.call('bignn_bn_workspace_bytes', ctx.S, C, ctx.parts)
         ws = _ws(wsb, x.device)
         _lib.call('bignn_bn_seg_bwd', x, x.stride(0), dy, dy.stride(0), dx, dx.stride(0), ctx.seg, ctx.S, C,
-                  ctx.parts, gamma, mean, rstd, dgamma, dbeta, ws, int(wsb))
-        return dx, dgamma, dbeta, None, None, None, None, None, None, None, None
+                  ctx.parts, gamma, mean, rstd, dgamma, dbeta, ctx.input_act, ws, int(wsb))
+        return dx, dgamma, dbeta, None, None, None, None, None, None, None, None, None
 
 
 class _Readout(torch.autograd.Function):
@@ -669,20 +684,22 @@ def gin_aggregate(x, csr, eps=0.0):
     return _GinAggregate.apply(x, csr, eps)
 
 
-def gcn_propagate(h, bias, csr, act=0):
-    return _GcnPropagate.apply(h, bias, csr, act)
+def gcn_propagate(h, bias, csr, act=0, act_bwd_by_consumer=False):
+    return _GcnPropagate.apply(h, bias, csr, act, act_bwd_by_consumer)
 
 
-def linear_act(x, weight, bias=None, act=0, layout='oi'):
-    return _LinearAct.apply(x, weight, bias, act, layout)
+def linear_act(x, weight, bias=None, act=0, layout='oi', act_bwd_by_consumer=False, input_act=0):
+    return _LinearAct.apply(x, weight, bias, act, layout, act_bwd_by_consumer, input_act)
 
 
 def seg_batch_norm(x, gamma, beta, seg_row_ptr, S, running_mean, running_var, nbt, eps=1e-5, momentum=0.1,
-                   stats_out=None):
+                   stats_out=None, input_act=0):
     """stats_out: optional fp64 [2,S,C] buffer receiving the per-segment mean / unbiased variance
-    (multi-GPU: running buffers are then advanced by `bn_running_update` after an exchange)."""
+    (multi-GPU: running buffers are then advanced by `bn_running_update` after an exchange).
+    input_act: x is the output of this activation and its producer was told `act_bwd_by_consumer`: the
+    backward returns the gradient w.r.t. the activation's input (one pass less over [rows, C])."""
     return _SegBatchNorm.apply(x, gamma, beta, seg_row_ptr, S, running_mean, running_var, nbt, eps, momentum,
-                               stats_out)
+                               stats_out, input_act)
 
 
 def bn_running_update(seg_stats, seg_row_ptr, S, running_mean, running_var, nbt, momentum=0.1):

@@ -154,6 +154,14 @@ int bignn_gemm_tc_supported(int32_t M, int32_t N, int32_t K);   /* 1 if the shap
 int bignn_gemm_tc_f32(int32_t M, int32_t N, int32_t K, const float* A, int64_t lda,
                       const float* B, int64_t ldb, int32_t b_is_nk,
                       float* C, int64_t ldc, const float* bias, int32_t act, void* stream);
+/* The same GEMM with a fused activation backward in the epilogue:  C = act(A * op(B) + bias) * mask_act'(mask_y),
+ * mask_y [M,N] being the OUTPUT of activation mask_act (relu: mask_y > 0).  Used for the backward-input transform
+ * dT = (g W2) * relu'(t) of the GIN MLP (model/layers.py:27-29: Linear, act, Linear), which saves the separate
+ * elementwise pass of autograd's ReluBackward.  mask_y = NULL: identical to bignn_gemm_tc_f32. */
+int bignn_gemm_tc_masked_f32(int32_t M, int32_t N, int32_t K, const float* A, int64_t lda,
+                             const float* B, int64_t ldb, int32_t b_is_nk,
+                             float* C, int64_t ldc, const float* bias, int32_t act,
+                             const float* mask_y, int64_t ldmy, int32_t mask_act, void* stream);
 /* Weight gradients on the tensor cores:  D[Np,Nq] = P[M,Np]^T * Q[M,Nq]  (row-major, ld = Nq) and,
  * optionally, the column sums of P (colsum_of = 0) or Q (colsum_of = 1) -> colsum[] (bias gradient);
  * colsum_of = -1 skips them.  3xTF32 on tcgen05 with MN-major operands, per-CTA partials summed in a
@@ -199,12 +207,15 @@ int bignn_bn_running_update(const double* seg_stats, const int32_t* seg_row_ptr,
 int bignn_bn_eval_fwd(const float* X, int64_t ldx, float* Y, int64_t ldy, int32_t rows, int32_t C,
                       const float* gamma, const float* beta, float eps,
                       const float* running_mean, const float* running_var, void* stream);
-/* dX, and dgamma/dbeta ACCUMULATED over segments in segment order (written, not added) */
+/* dX, and dgamma/dbeta ACCUMULATED over segments in segment order (written, not added).
+ * input_act (BIGNN_ACT_*): X is the output of that activation (model/layers.py:55-57 applies act, then bn); its
+ * derivative is folded into dX, so dX is the gradient w.r.t. the activation's INPUT (BIGNN_ACT_IDENTITY = plain
+ * BatchNorm backward).  Saves the separate elementwise pass over [rows, C]. */
 int bignn_bn_seg_bwd(const float* X, int64_t ldx, const float* dY, int64_t lddy,
                      float* dX, int64_t lddx,
                      const int32_t* seg_row_ptr, int32_t S, int32_t C, int32_t parts,
                      const float* gamma, const float* mean, const float* rstd,
-                     float* dgamma, float* dbeta,
+                     float* dgamma, float* dbeta, int32_t input_act,
                      void* workspace, int64_t workspace_bytes, void* stream);
 
 /* Row-partitioned BatchNorm (multi-GPU upper level, SURVEY 8e: interaction-graph rows partitioned by
@@ -229,7 +240,7 @@ int bignn_bn_rows_fwd_apply(const float* X, int64_t ldx, float* Y, int64_t ldy, 
 int bignn_bn_rows_bwd_apply(const float* X, int64_t ldx, const float* dY, int64_t lddy, float* dX, int64_t lddx,
                             int32_t rows, int32_t C, int32_t parts, const float* gamma,
                             const float* mean, const float* rstd, const double* sums, int64_t n_total,
-                            void* stream);
+                            int32_t input_act, void* stream);
 
 /* ---------------------------------------------------------------------------
  * Segment readout (atoms -> one row per drug), rows summed in ascending order.

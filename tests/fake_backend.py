@@ -121,9 +121,11 @@ class Fake(object):
         Y[:rows] = X[:rows] * alpha + (beta - mean * alpha)
         return 0
 
-    def bignn_bn_rows_bwd_apply(self, X, ldx, dY, lddy, dX, lddx, rows, C, parts, gamma, mean, rstd, sums, n_total):
+    def bignn_bn_rows_bwd_apply(self, X, ldx, dY, lddy, dX, lddx, rows, C, parts, gamma, mean, rstd, sums, n_total,
+                                in_act):
         xhat = (X[:rows] - mean) * rstd
-        dX[:rows] = (dY[:rows] - (sums[0] / n_total).float() - xhat * (sums[1] / n_total).float()) * (rstd * gamma)
+        dX[:rows] = self._act_prime((dY[:rows] - (sums[0] / n_total).float() - xhat * (sums[1] / n_total).float())
+                                    * (rstd * gamma), X[:rows], in_act)
         return 0
 
     def bignn_spmm_planned_workspace_bytes(self, n_items, D):
@@ -164,6 +166,12 @@ class Fake(object):
         if bias is not None:
             out = out + bias
         C[:M, :N] = ACTS[act](out)
+        return 0
+
+    def bignn_gemm_tc_masked_f32(self, M, N, K, A, lda, B, ldb, b_is_nk, C, ldc, bias, act, mask_y, ldmy, mask_act):
+        self.bignn_gemm_tc_f32(M, N, K, A, lda, B, ldb, b_is_nk, C, ldc, bias, act)
+        if mask_y is not None:
+            C[:M, :N] = self._act_prime(C[:M, :N], mask_y[:M, :N], mask_act)
         return 0
 
     def bignn_colsum_f32(self, X, ldx, rows, cols, out, ws, wsb):
@@ -219,8 +227,18 @@ class Fake(object):
         Y.copy_(X * alpha + (beta - rm * alpha))
         return 0
 
+    @staticmethod
+    def _act_prime(d, x, act):
+        if act == 1:
+            return d * (x > 0)
+        if act == 2:
+            return d * ((1 - x) * x)
+        if act == 3:
+            return d * (1 - x * x)
+        return d
+
     def bignn_bn_seg_bwd(self, X, ldx, dY, lddy, dX, lddx, seg, S, C, parts, gamma, mean, rstd, dgamma, dbeta,
-                         ws, wsb):
+                         in_act, ws, wsb):
         dg = torch.zeros(C, dtype=torch.float64)
         db = torch.zeros(C, dtype=torch.float64)
         for s in range(S):
@@ -232,7 +250,7 @@ class Fake(object):
             sb = (g.double() * xhat.double()).sum(0)
             db += sa
             dg += sb
-            dX[a:b] = (g - (sa / n).float() - xhat * (sb / n).float()) * (rstd[s] * gamma)
+            dX[a:b] = self._act_prime((g - (sa / n).float() - xhat * (sb / n).float()) * (rstd[s] * gamma), X[a:b], in_act)
         dgamma.copy_(dg.float())
         dbeta.copy_(db.float())
         return 0

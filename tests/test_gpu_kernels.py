@@ -123,7 +123,18 @@ def test_spmm_gcn_vs_oracle(data, drugbank, D, act):
     want = O._act(act, O.gcn_conv(h, ei, P, 'l'))
     csr = data.interaction_combo_nxgraph.csr
     got = ops.spmm(csr, h.to(DEV), ops.SPMM_GCN, 0.0, csr.dinv(), bias.to(DEV), ops.act_code(act))
-    assert rel(got, want) < 2e-6
+    err = rel(got, want)
+    if err >= 2e-6:
+        # DESIGN.md "known open item": seen twice in ~20 fresh-box runs ([49-tanh], 5e-5, first run of a new
+        # build).  Still a failure -- but say which side is not reproducible.
+        got2 = ops.spmm(csr, h.to(DEV), ops.SPMM_GCN, 0.0, csr.dinv(), bias.to(DEV), ops.act_code(act))
+        want2 = O._act(act, O.gcn_conv(h, ei, P, 'l'))
+        d = (got.cpu() - want).abs()
+        pytest.fail('GCN SpMM vs oracle: err {:.3g}; kernel reproducible: {}, oracle reproducible: {}, second '
+                    'kernel run vs oracle {:.3g}, kernel vs second oracle run {:.3g}; worst element {} of row degree {}'
+                    .format(err, torch.equal(got, got2), torch.equal(want, want2), rel(got2, want), rel(got, want2),
+                            np.unravel_index(int(d.argmax()), d.shape),
+                            int(np.bincount(drugbank.ddi_row, minlength=n)[int(d.argmax()) // D])))
     # deg^-1/2 itself is bit-exact
     row, col = ei
     deg = torch.zeros(n).index_add_(0, row, torch.ones(row.shape[0])) + 1

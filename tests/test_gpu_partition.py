@@ -135,7 +135,7 @@ def test_bn_rows_equals_segmented_bn_and_oracle(world):
         sl = slice(bounds[r], bounds[r + 1])
         xs, ds, dxs = xd[sl], dy[sl], dx[sl]
         _lib.call('bignn_bn_rows_bwd_apply', xs, xs.stride(0), ds, ds.stride(0), dxs, dxs.stride(0), xs.shape[0], C,
-                  parts, gamma, means[r], rstds[r], totb, n)
+                  parts, gamma, means[r], rstds[r], totb, n, 0)
     assert rel(dx, x.grad) < 2e-6
     assert rel(totb[0].float(), b1.grad) < 1e-6 and rel(totb[1].float(), g1.grad) < 1e-6
     # ---- and against torch's own BatchNorm1d on the CPU (the reference's operator, model/layers.py:57)
