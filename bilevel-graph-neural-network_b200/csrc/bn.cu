@@ -195,12 +195,12 @@ k_bn_bwd_params(const double* __restrict__ seg_a, const double* __restrict__ seg
   if (dgamma) dgamma[c] = (float)b;
 }
 
+template <int IN_ACT>
 __global__ void __launch_bounds__(256)
 k_bn_bwd_apply(const float* __restrict__ X, int64_t ldx, const float* __restrict__ dY, int64_t lddy,
                float* __restrict__ dX, int64_t lddx, const int32_t* __restrict__ seg_row_ptr, int C, int parts,
                const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
-               const double* __restrict__ seg_a, const double* __restrict__ seg_b, int rows, int64_t n_total,
-               int in_act) {
+               const double* __restrict__ seg_a, const double* __restrict__ seg_b, int rows, int64_t n_total) {
   const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
   const int c = blockIdx.y * 32 + tx;
   const int s = blockIdx.x / parts, p = blockIdx.x % parts;
@@ -219,12 +219,9 @@ k_bn_bwd_apply(const float* __restrict__ X, int64_t ldx, const float* __restrict
     float d = (g - gmean - xhat * dgn) * scale;
     // X is the OUTPUT of the activation in front of this BatchNorm (model/layers.py:55-57): its derivative is
     // applied here, on the value already in a register, instead of in a separate pass (same formulas as k_act_bwd)
-    switch (in_act) {
-      case BIGNN_ACT_RELU: d = x > 0.f ? d : 0.f; break;
-      case BIGNN_ACT_SIGMOID: d = d * ((1.0f - x) * x); break;
-      case BIGNN_ACT_TANH: d = d * (1.0f - x * x); break;
-      default: break;
-    }
+    if (IN_ACT == BIGNN_ACT_RELU) d = x > 0.f ? d : 0.f;
+    else if (IN_ACT == BIGNN_ACT_SIGMOID) d = d * ((1.0f - x) * x);
+    else if (IN_ACT == BIGNN_ACT_TANH) d = d * (1.0f - x * x);
     dX[(int64_t)r * lddx + c] = d;
   }
 }
@@ -267,6 +264,186 @@ k_bn_rows_finalize(const double* __restrict__ sums, int64_t n_total, int C, floa
   if (c == 0 && nbt && running_mean && n_total > 0) *nbt += 1;
 }
 
+// ---- 128-bit variants of the three streaming passes (C % 4 == 0, 16-byte aligned rows): `tpr` threads own one
+// row (a float4 of channels each), 256/tpr rows per pass, four rows in flight per thread.  Same reduction tree as the
+// scalar kernels: per-thread fp64 partials over the thread's rows (ascending), then the rows of the block in order.
+template <bool BWD>
+__global__ void __launch_bounds__(256)
+k_bn_reduce_part_v4(const float* __restrict__ X, int64_t ldx, const float* __restrict__ dY, int64_t lddy,
+                    const int32_t* __restrict__ seg_row_ptr, int C, int tpr, int parts,
+                    const float* __restrict__ mean, const float* __restrict__ rstd,
+                    double* __restrict__ ws_a, double* __restrict__ ws_b, int rows) {
+  extern __shared__ double bn_sm[];                 // [2][rpb][C]
+  const int lane = threadIdx.x % tpr, ty = threadIdx.x / tpr, rpb = blockDim.x / tpr;
+  const int s = blockIdx.x / parts, p = blockIdx.x % parts;
+  int r0, r1, n;
+  part_range(seg_row_ptr, rows, s, p, parts, r0, r1, n);
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+  const int c = 4 * lane;
+  if (c < C) {
+    float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), rs = mu;
+    if (BWD) { mu = ldg4(mean + (int64_t)s * C + c); rs = ldg4(rstd + (int64_t)s * C + c); }
+#pragma unroll 4
+    for (int r = r0 + ty; r < r1; r += rpb) {
+      const float4 x = ldg4(X + (int64_t)r * ldx + c);
+      if (BWD) {
+        const float4 g = ldg4(dY + (int64_t)r * lddy + c);
+        a0 += (double)g.x; a1 += (double)g.y; a2 += (double)g.z; a3 += (double)g.w;
+        b0 += (double)g.x * (double)((x.x - mu.x) * rs.x); b1 += (double)g.y * (double)((x.y - mu.y) * rs.y);
+        b2 += (double)g.z * (double)((x.z - mu.z) * rs.z); b3 += (double)g.w * (double)((x.w - mu.w) * rs.w);
+      } else {
+        a0 += (double)x.x; a1 += (double)x.y; a2 += (double)x.z; a3 += (double)x.w;
+        b0 += (double)x.x * (double)x.x; b1 += (double)x.y * (double)x.y;
+        b2 += (double)x.z * (double)x.z; b3 += (double)x.w * (double)x.w;
+      }
+    }
+    double* sa = bn_sm + (int64_t)ty * C + c;
+    double* sb = bn_sm + (int64_t)(rpb + ty) * C + c;
+    sa[0] = a0; sa[1] = a1; sa[2] = a2; sa[3] = a3;
+    sb[0] = b0; sb[1] = b1; sb[2] = b2; sb[3] = b3;
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+    double ta = 0.0, tb = 0.0;
+    for (int i = 0; i < rpb; ++i) { ta += bn_sm[(int64_t)i * C + ch]; tb += bn_sm[(int64_t)(rpb + i) * C + ch]; }
+    ws_a[(int64_t)blockIdx.x * C + ch] = ta;
+    ws_b[(int64_t)blockIdx.x * C + ch] = tb;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_bn_apply_v4(const float* __restrict__ X, int64_t ldx, float* __restrict__ Y, int64_t ldy,
+              const int32_t* __restrict__ seg_row_ptr, int C, int tpr, int parts,
+              const float* __restrict__ gamma, const float* __restrict__ beta,
+              const float* __restrict__ mean, const float* __restrict__ rstd, int rows) {
+  const int lane = threadIdx.x % tpr, ty = threadIdx.x / tpr, rpb = blockDim.x / tpr;
+  const int s = blockIdx.x / parts, p = blockIdx.x % parts;
+  int r0, r1, n;
+  part_range(seg_row_ptr, rows, s, p, parts, r0, r1, n);
+  const int c = 4 * lane;
+  if (c >= C) return;
+  const float4 rs = ldg4(rstd + (int64_t)s * C + c), mu = ldg4(mean + (int64_t)s * C + c);
+  const float4 ga = gamma ? ldg4(gamma + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+  const float4 be = beta ? ldg4(beta + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 al = make_float4(rs.x * ga.x, rs.y * ga.y, rs.z * ga.z, rs.w * ga.w);
+  const float4 bt = make_float4(be.x - mu.x * al.x, be.y - mu.y * al.y, be.z - mu.z * al.z, be.w - mu.w * al.w);
+#pragma unroll 4
+  for (int r = r0 + ty; r < r1; r += rpb) {
+    const float4 x = ldg4(X + (int64_t)r * ldx + c);
+    st4(Y + (int64_t)r * ldy + c, make_float4(fmaf(x.x, al.x, bt.x), fmaf(x.y, al.y, bt.y), fmaf(x.z, al.z, bt.z),
+                                              fmaf(x.w, al.w, bt.w)));
+  }
+}
+
+template <int IN_ACT>
+__device__ __forceinline__ float bn_bwd_one(float x, float g, float mu, float rs, float gmean, float dgn, float scale) {
+  const float xhat = (x - mu) * rs;
+  float d = (g - gmean - xhat * dgn) * scale;
+  if (IN_ACT == BIGNN_ACT_RELU) d = x > 0.f ? d : 0.f;
+  else if (IN_ACT == BIGNN_ACT_SIGMOID) d = d * ((1.0f - x) * x);
+  else if (IN_ACT == BIGNN_ACT_TANH) d = d * (1.0f - x * x);
+  return d;
+}
+
+template <int IN_ACT>
+__global__ void __launch_bounds__(256)
+k_bn_bwd_apply_v4(const float* __restrict__ X, int64_t ldx, const float* __restrict__ dY, int64_t lddy,
+                  float* __restrict__ dX, int64_t lddx, const int32_t* __restrict__ seg_row_ptr, int C, int tpr,
+                  int parts, const float* __restrict__ gamma, const float* __restrict__ mean,
+                  const float* __restrict__ rstd, const double* __restrict__ seg_a,
+                  const double* __restrict__ seg_b, int rows, int64_t n_total) {
+  const int lane = threadIdx.x % tpr, ty = threadIdx.x / tpr, rpb = blockDim.x / tpr;
+  const int s = blockIdx.x / parts, p = blockIdx.x % parts;
+  int r0, r1, n;
+  part_range(seg_row_ptr, rows, s, p, parts, r0, r1, n);
+  const int c = 4 * lane;
+  if (c >= C || n <= 0) return;
+  const double cnt = n_total > 0 ? (double)n_total : (double)n;
+  const float4 mu = ldg4(mean + (int64_t)s * C + c), rs = ldg4(rstd + (int64_t)s * C + c);
+  const float4 ga = gamma ? ldg4(gamma + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+  const double* pa = seg_a + (int64_t)s * C + c;
+  const double* pb = seg_b + (int64_t)s * C + c;
+  const float4 gm = make_float4((float)(pa[0] / cnt), (float)(pa[1] / cnt), (float)(pa[2] / cnt), (float)(pa[3] / cnt));
+  const float4 dg = make_float4((float)(pb[0] / cnt), (float)(pb[1] / cnt), (float)(pb[2] / cnt), (float)(pb[3] / cnt));
+  const float4 sc = make_float4(rs.x * ga.x, rs.y * ga.y, rs.z * ga.z, rs.w * ga.w);
+#pragma unroll 4
+  for (int r = r0 + ty; r < r1; r += rpb) {
+    const float4 x = ldg4(X + (int64_t)r * ldx + c);
+    const float4 g = ldg4(dY + (int64_t)r * lddy + c);
+    st4(dX + (int64_t)r * lddx + c,
+        make_float4(bn_bwd_one<IN_ACT>(x.x, g.x, mu.x, rs.x, gm.x, dg.x, sc.x),
+                    bn_bwd_one<IN_ACT>(x.y, g.y, mu.y, rs.y, gm.y, dg.y, sc.y),
+                    bn_bwd_one<IN_ACT>(x.z, g.z, mu.z, rs.z, gm.z, dg.z, sc.z),
+                    bn_bwd_one<IN_ACT>(x.w, g.w, mu.w, rs.w, gm.w, dg.w, sc.w)));
+  }
+}
+
+// threads per row of the 128-bit kernels (power of two >= C/4), 0 = take the scalar kernels
+static int bn_tpr(int C, const void* a, int64_t lda, const void* b, int64_t ldb, const void* c, int64_t ldc) {
+  if ((C & 3) || C > 1024) return 0;
+  if (a && (!aligned16(a) || (lda & 3))) return 0;
+  if (b && (!aligned16(b) || (ldb & 3))) return 0;
+  if (c && (!aligned16(c) || (ldc & 3))) return 0;
+  int t = 1;
+  while (t < C / 4) t <<= 1;
+  return t;
+}
+
+static void launch_bn_reduce(bool bwd, int nblk, cudaStream_t st, const float* X, int64_t ldx, const float* dY,
+                             int64_t lddy, const int32_t* seg_row_ptr, int C, int parts, const float* mean,
+                             const float* rstd, double* ws_a, double* ws_b, int rows) {
+  const int tpr = bn_tpr(C, X, ldx, dY, lddy, (bwd ? (const void*)mean : nullptr), 4);
+  if (tpr > 0 && (!bwd || aligned16(rstd))) {
+    const size_t sm = sizeof(double) * 2 * (256 / tpr) * C;
+    if (bwd) k_bn_reduce_part_v4<true><<<nblk, 256, sm, st>>>(X, ldx, dY, lddy, seg_row_ptr, C, tpr, parts, mean, rstd, ws_a, ws_b, rows);
+    else k_bn_reduce_part_v4<false><<<nblk, 256, sm, st>>>(X, ldx, nullptr, 0, seg_row_ptr, C, tpr, parts, nullptr, nullptr, ws_a, ws_b, rows);
+    return;
+  }
+  dim3 grid(nblk, ceil_div(C, 32));
+  if (bwd) k_bn_reduce_part<true><<<grid, 256, 0, st>>>(X, ldx, dY, lddy, seg_row_ptr, C, parts, mean, rstd, ws_a, ws_b, rows);
+  else k_bn_reduce_part<false><<<grid, 256, 0, st>>>(X, ldx, nullptr, 0, seg_row_ptr, C, parts, nullptr, nullptr, ws_a, ws_b, rows);
+}
+
+static void launch_bn_apply(int nblk, cudaStream_t st, const float* X, int64_t ldx, float* Y, int64_t ldy,
+                            const int32_t* seg_row_ptr, int C, int parts, const float* gamma, const float* beta,
+                            const float* mean, const float* rstd, int rows) {
+  const int tpr = bn_tpr(C, X, ldx, Y, ldy, mean, 4);
+  if (tpr > 0 && aligned16(rstd) && (!gamma || aligned16(gamma)) && (!beta || aligned16(beta))) {
+    k_bn_apply_v4<<<nblk, 256, 0, st>>>(X, ldx, Y, ldy, seg_row_ptr, C, tpr, parts, gamma, beta, mean, rstd, rows);
+    return;
+  }
+  dim3 grid(nblk, ceil_div(C, 32));
+  k_bn_apply<<<grid, 256, 0, st>>>(X, ldx, Y, ldy, seg_row_ptr, C, parts, gamma, beta, mean, rstd, rows);
+}
+
+static void launch_bn_bwd_apply(dim3 grid, cudaStream_t st, int in_act, const float* X, int64_t ldx, const float* dY,
+                                int64_t lddy, float* dX, int64_t lddx, const int32_t* seg_row_ptr, int C, int parts,
+                                const float* gamma, const float* mean, const float* rstd, const double* seg_a,
+                                const double* seg_b, int rows, int64_t n_total) {
+  const int tpr = bn_tpr(C, X, ldx, dY, lddy, dX, lddx);
+  if (tpr > 0 && aligned16(mean) && aligned16(rstd) && (!gamma || aligned16(gamma))) {
+#define BIGNN_BN_BWD4(A) k_bn_bwd_apply_v4<A><<<grid.x, 256, 0, st>>>(X, ldx, dY, lddy, dX, lddx, seg_row_ptr, C, tpr, \
+                                                                      parts, gamma, mean, rstd, seg_a, seg_b, rows, n_total)
+    switch (in_act) {
+      case BIGNN_ACT_RELU: BIGNN_BN_BWD4(BIGNN_ACT_RELU); break;
+      case BIGNN_ACT_SIGMOID: BIGNN_BN_BWD4(BIGNN_ACT_SIGMOID); break;
+      case BIGNN_ACT_TANH: BIGNN_BN_BWD4(BIGNN_ACT_TANH); break;
+      default: BIGNN_BN_BWD4(BIGNN_ACT_IDENTITY);
+    }
+#undef BIGNN_BN_BWD4
+    return;
+  }
+#define BIGNN_BN_BWD(A) k_bn_bwd_apply<A><<<grid, 256, 0, st>>>(X, ldx, dY, lddy, dX, lddx, seg_row_ptr, C, parts, \
+                                                                 gamma, mean, rstd, seg_a, seg_b, rows, n_total)
+  switch (in_act) {
+    case BIGNN_ACT_RELU: BIGNN_BN_BWD(BIGNN_ACT_RELU); break;
+    case BIGNN_ACT_SIGMOID: BIGNN_BN_BWD(BIGNN_ACT_SIGMOID); break;
+    case BIGNN_ACT_TANH: BIGNN_BN_BWD(BIGNN_ACT_TANH); break;
+    default: BIGNN_BN_BWD(BIGNN_ACT_IDENTITY);
+  }
+#undef BIGNN_BN_BWD
+}
+
 }  // namespace bignn
 
 using namespace bignn;
@@ -292,14 +469,14 @@ extern "C" int bignn_bn_seg_fwd(const float* X, int64_t ldx, float* Y, int64_t l
   double* mean_d = seg_stats_out ? seg_stats_out : ws_b + (int64_t)S * parts * C;
   double* varu_d = mean_d + (int64_t)S * C;
   dim3 grid(S * parts, ceil_div(C, 32));
-  k_bn_reduce_part<false><<<grid, 256, 0, st>>>(X, ldx, nullptr, 0, seg_row_ptr, C, parts, nullptr, nullptr, ws_a, ws_b, 0);
+  launch_bn_reduce(false, S * parts, st, X, ldx, nullptr, 0, seg_row_ptr, C, parts, nullptr, nullptr, ws_a, ws_b, 0);
   k_bn_finalize<<<(int)ceil_div<int64_t>((int64_t)S * C, 256), 256, 0, st>>>(ws_a, ws_b, seg_row_ptr, S, C, parts, eps, mean, rstd, mean_d, varu_d);
   BIGNN_LAUNCH_COUNT(2);
   if (running_mean && running_var) {
     k_bn_running<<<ceil_div(C, 64), 64, 0, st>>>(mean_d, varu_d, seg_row_ptr, S, C, (double)momentum, running_mean, running_var, num_batches_tracked);
     BIGNN_LAUNCH_COUNT(1);
   }
-  k_bn_apply<<<grid, 256, 0, st>>>(X, ldx, Y, ldy, seg_row_ptr, C, parts, gamma, beta, mean, rstd, 0);
+  launch_bn_apply(S * parts, st, X, ldx, Y, ldy, seg_row_ptr, C, parts, gamma, beta, mean, rstd, 0);
   BIGNN_LAUNCH_COUNT(1);
   return last_launch_status();
 }
@@ -348,10 +525,11 @@ extern "C" int bignn_bn_seg_bwd(const float* X, int64_t ldx, const float* dY, in
   double* seg_a = ws_b + (int64_t)S * parts * C;
   double* seg_b = seg_a + (int64_t)S * C;
   dim3 grid(S * parts, ceil_div(C, 32));
-  k_bn_reduce_part<true><<<grid, 256, 0, st>>>(X, ldx, dY, lddy, seg_row_ptr, C, parts, mean, rstd, ws_a, ws_b, 0);
+  launch_bn_reduce(true, S * parts, st, X, ldx, dY, lddy, seg_row_ptr, C, parts, mean, rstd, ws_a, ws_b, 0);
   k_bn_bwd_finalize<<<(int)ceil_div<int64_t>((int64_t)S * C, 256), 256, 0, st>>>(ws_a, ws_b, S, C, parts, seg_a, seg_b);
   k_bn_bwd_params<<<ceil_div(C, 256), 256, 0, st>>>(seg_a, seg_b, S, C, dgamma, dbeta);
-  k_bn_bwd_apply<<<grid, 256, 0, st>>>(X, ldx, dY, lddy, dX, lddx, seg_row_ptr, C, parts, gamma, mean, rstd, seg_a, seg_b, 0, 0, input_act);
+  launch_bn_bwd_apply(grid, st, input_act, X, ldx, dY, lddy, dX, lddx, seg_row_ptr, C, parts, gamma, mean, rstd, seg_a,
+                      seg_b, 0, 0);
   BIGNN_LAUNCH_COUNT(4);
   return last_launch_status();
 }
@@ -375,8 +553,7 @@ extern "C" int bignn_bn_rows_sums(const float* X, int64_t ldx, const float* dY, 
   double* ws_a = (double*)workspace;
   double* ws_b = ws_a + (int64_t)parts * C;
   dim3 grid(parts, ceil_div(C, 32));
-  if (dY) k_bn_reduce_part<true><<<grid, 256, 0, st>>>(X, ldx, dY, lddy, nullptr, C, parts, mean, rstd, ws_a, ws_b, rows);
-  else k_bn_reduce_part<false><<<grid, 256, 0, st>>>(X, ldx, nullptr, 0, nullptr, C, parts, nullptr, nullptr, ws_a, ws_b, rows);
+  launch_bn_reduce(dY != nullptr, parts, st, X, ldx, dY, lddy, nullptr, C, parts, mean, rstd, ws_a, ws_b, rows);
   k_bn_rows_sum_parts<<<ceil_div(C, 256), 256, 0, st>>>(ws_a, ws_b, C, parts, sums);
   BIGNN_LAUNCH_COUNT(2);
   return last_launch_status();
@@ -396,7 +573,7 @@ extern "C" int bignn_bn_rows_fwd_apply(const float* X, int64_t ldx, float* Y, in
   BIGNN_LAUNCH_COUNT(1);
   if (rows > 0) {
     dim3 grid(parts, ceil_div(C, 32));
-    k_bn_apply<<<grid, 256, 0, st>>>(X, ldx, Y, ldy, nullptr, C, parts, gamma, beta, mean, rstd, rows);
+    launch_bn_apply(parts, st, X, ldx, Y, ldy, nullptr, C, parts, gamma, beta, mean, rstd, rows);
     BIGNN_LAUNCH_COUNT(1);
   }
   return last_launch_status();
@@ -410,8 +587,8 @@ extern "C" int bignn_bn_rows_bwd_apply(const float* X, int64_t ldx, const float*
   if (rows == 0 || C == 0) return 0;
   if (!X || !dY || !dX || !mean || !rstd || !sums || ldx < C || lddy < C || lddx < C) return BIGNN_EINVAL;
   dim3 grid(parts, ceil_div(C, 32));
-  k_bn_bwd_apply<<<grid, 256, 0, (cudaStream_t)stream>>>(X, ldx, dY, lddy, dX, lddx, nullptr, C, parts, gamma, mean,
-                                                          rstd, sums, sums + C, rows, n_total, input_act);
+  launch_bn_bwd_apply(grid, (cudaStream_t)stream, input_act, X, ldx, dY, lddy, dX, lddx, nullptr, C, parts, gamma, mean,
+                      rstd, sums, sums + C, rows, n_total);
   BIGNN_LAUNCH_COUNT(1);
   return last_launch_status();
 }

@@ -163,6 +163,27 @@ k_gemm_tc(int M, int N, int K, const float* __restrict__ A, int64_t lda, const f
       }
       umma_commit(&mma_bar);
     }
+    // ---- fused ReLU backward: fetch this thread's part of the mask tile now (its copy-out elements), as one bit
+    // per element, so that the loads fly while the tensor core works instead of stalling the copy-out loop
+    uint64_t mbits = 0;
+    const bool mask_bits = mask_y != nullptr && mask_act == BIGNN_ACT_RELU && c_vec && N == NPAD &&
+                           (NPAD == 32 || NPAD == 64 || NPAD == 128);
+    if (mask_bits) {
+      constexpr int N4 = NPAD / 4, RSTEP = TC_THREADS / N4, NR = TC_BM / RSTEP;
+      const int c4 = tid % N4, rows_here = min(TC_BM, M - m0);
+      float4 y[NR];
+#pragma unroll
+      for (int i = 0; i < NR; ++i) {
+        const int r = tid / N4 + i * RSTEP;
+        y[i] = r < rows_here ? ldg4(mask_y + (int64_t)(m0 + r) * ldmy + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < NR; ++i) {
+        const uint32_t b = (y[i].x > 0.f ? 1u : 0u) | (y[i].y > 0.f ? 2u : 0u) | (y[i].z > 0.f ? 4u : 0u) |
+                           (y[i].w > 0.f ? 8u : 0u);
+        mbits |= (uint64_t)b << (4 * i);
+      }
+    }
     mbar_wait(&mma_bar, phase);
     phase ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -212,14 +233,18 @@ k_gemm_tc(int M, int N, int K, const float* __restrict__ A, int64_t lda, const f
           o.x = fmaxf(o.x + b4.x, 0.f); o.y = fmaxf(o.y + b4.y, 0.f); o.z = fmaxf(o.z + b4.z, 0.f); o.w = fmaxf(o.w + b4.w, 0.f);
           st4(C + (int64_t)(m0 + r) * ldc + 4 * c4, o);
         }
-      } else if (act == BIGNN_ACT_IDENTITY && mask_y != nullptr && mask_act == BIGNN_ACT_RELU) {
-#pragma unroll 4
-        for (int r = tid / N4; r < rows_here; r += RSTEP) {       // backward-input GEMM with the ReLU mask of t
-          float4 o = *reinterpret_cast<const float4*>(src + sw128_off(r, c4 & 7));
-          const float4 y = ldg4(mask_y + (int64_t)(m0 + r) * ldmy + 4 * c4);
-          o.x = y.x > 0.f ? o.x + b4.x : 0.f; o.y = y.y > 0.f ? o.y + b4.y : 0.f;
-          o.z = y.z > 0.f ? o.z + b4.z : 0.f; o.w = y.w > 0.f ? o.w + b4.w : 0.f;
-          st4(C + (int64_t)(m0 + r) * ldc + 4 * c4, o);
+      } else if (act == BIGNN_ACT_IDENTITY && mask_bits) {
+        constexpr int NR = TC_BM / RSTEP;
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {                           // backward-input GEMM with the ReLU mask of t
+          const int r = tid / N4 + i * RSTEP;
+          if (r < rows_here) {
+            float4 o = *reinterpret_cast<const float4*>(src + sw128_off(r, c4 & 7));
+            const uint32_t b = (uint32_t)(mbits >> (4 * i));
+            o.x = (b & 1u) ? o.x + b4.x : 0.f; o.y = (b & 2u) ? o.y + b4.y : 0.f;
+            o.z = (b & 4u) ? o.z + b4.z : 0.f; o.w = (b & 8u) ? o.w + b4.w : 0.f;
+            st4(C + (int64_t)(m0 + r) * ldc + 4 * c4, o);
+          }
         }
       } else if (act == BIGNN_ACT_IDENTITY && mask_y == nullptr) {
 #pragma unroll 4

@@ -11,19 +11,22 @@
 // the per-CTA partial [64 x 64] goes to a workspace that a fixed-order reduction sums (deterministic).
 // The MMA runs with M = 128: rows 64..127 of D come from the Q blocks that follow P in shared memory
 // and are ignored (a 64-row MMA costs the same tensor time and has a scattered TMEM layout).
+#include <cstdlib>
 #include "tc_common.cuh"
 
 namespace bignn {
 
 constexpr int DW_F = 64;                       // padded feature width of both operands
-constexpr int DW_BLK = TC_BM * 128;            // one [128 rows x 128 B] block
-constexpr int DW_TILE = 2 * DW_BLK;            // one operand tile (64 features)
-constexpr int DW_NA = 4;                       // rotating main accumulators
+constexpr int DW_MMA_M = 128;                  // MMA M (features of P in rows 0..63; rows 64..127 ignored)
 
-__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
+// Two configurations of the row tile (= K extent per tile) BM and the number NA of rotating accumulators:
+//   <64, 3>   96 KB of shared memory and (3+1)*64 = 256 TMEM columns per CTA -> TWO CTAs per SM, whose phases
+//             (cp.async fill, hi/lo split on the SIMT pipes, MMAs on the tensor pipe) overlap each other;
+//   <128, 4>  192 KB, 512 TMEM columns, one CTA per SM (the first version; BIGNN_DW_BM=128 selects it).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr, int blk_bytes) {
   // MN-major, SWIZZLE_128B_BASE32B (layout type 1): LBO = distance between 32-feature blocks,
   // SBO = distance between 4-row groups
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(DW_BLK >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(blk_bytes >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
          (1ull << 46) | (1ull << 61);
 }
 
@@ -40,9 +43,15 @@ __device__ __forceinline__ uint32_t umma_idesc_tf32_mn(int M, int N) {
 
 // smem: 2 x [P_hi][Q_hi] (double buffered: the next tile streams in while this one is multiplied)
 //       + [P_lo][Q_lo], each DW_TILE bytes
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int BM, int DW_NA>
+__global__ void __launch_bounds__(TC_THREADS, (BM == 64 ? 2 : 1))
 k_dw_tc(int M, int Np, int Nq, const float* __restrict__ P, int64_t ldp, const float* __restrict__ Q, int64_t ldq,
         int colsum_of, float* __restrict__ ws_dw, double* __restrict__ ws_cs) {
+  constexpr int DW_BLK = BM * 128;               // one [BM rows x 128 B] block (32 features)
+  constexpr int DW_TILE = 2 * DW_BLK;            // one operand tile (64 features)
+  constexpr int NCHUNK = 4 * BM * 8;             // 16-byte chunks of both operand tiles
+  constexpr int LOG_OP = (BM == 64 ? 10 : 11);   // chunks per operand = 2 * BM * 8
+  static_assert((DW_NA + 1) * DW_F <= (BM == 64 ? 256 : 512), "TMEM columns");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* p_lo = smem + 4 * DW_TILE;
@@ -51,8 +60,8 @@ k_dw_tc(int M, int Np, int Nq, const float* __restrict__ P, int64_t ldp, const f
   __shared__ double cs_red[4][DW_F];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n_tiles = (M + TC_BM - 1) / TC_BM;
-  constexpr int TMEM_COLS = 512;               // (DW_NA + 1) * 64 = 320 columns -> next power of two
+  const int n_tiles = (M + BM - 1) / BM;
+  constexpr int TMEM_COLS = (DW_NA + 1) * DW_F <= 256 ? 256 : 512;   // power of two >= (DW_NA + 1) * 64
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
@@ -67,12 +76,12 @@ k_dw_tc(int M, int Np, int Nq, const float* __restrict__ P, int64_t ldp, const f
   const uint32_t smem_s = smem_u32(smem);
   // both operand tiles: 2 x 2048 sixteen-byte chunks; zero fill beyond M rows / N features
   auto prefetch_tile = [&](int tile, int buf) {
-    const int m0 = tile * TC_BM;
+    const int m0 = tile * BM;
     const uint32_t hi_s = smem_s + buf * 2 * DW_TILE;
 #pragma unroll 1
-    for (int j = tid; j < 4096; j += TC_THREADS) {
-      const int op = j >> 11, idx = j & 2047;           // op 0 = P, 1 = Q
-      const int blk = idx >> 10, r = (idx & 1023) >> 3, c = idx & 7;
+    for (int j = tid; j < NCHUNK; j += TC_THREADS) {
+      const int op = j >> LOG_OP, idx = j & ((1 << LOG_OP) - 1);           // op 0 = P, 1 = Q
+      const int blk = idx >> (LOG_OP - 1), r = (idx & ((1 << (LOG_OP - 1)) - 1)) >> 3, c = idx & 7;
       const int gm = m0 + r, gf = blk * 32 + c * 4;
       const int nf = op ? Nq : Np;
       const bool ok = gm < M && gf < nf;
@@ -88,7 +97,7 @@ k_dw_tc(int M, int Np, int Nq, const float* __restrict__ P, int64_t ldp, const f
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = tmem_base_s;
-  const uint32_t idesc = umma_idesc_tf32_mn(TC_BM, DW_F);
+  const uint32_t idesc = umma_idesc_tf32_mn(DW_MMA_M, DW_F);
 
   double cs = 0.0;                                     // this thread's column-sum share
   const int cs_col = tid & 63, cs_rg = tid >> 6;
@@ -102,9 +111,10 @@ k_dw_tc(int M, int Np, int Nq, const float* __restrict__ P, int64_t ldp, const f
     if (tile + gridDim.x < n_tiles) prefetch_tile(tile + gridDim.x, buf ^ 1);
     // ---- lo = tf32(x - hi(x)) for the chunks this thread copied
 #pragma unroll 4
-    for (int j = tid; j < 4096; j += TC_THREADS) {
-      const int op = j >> 11, idx = j & 2047;
-      const uint32_t off = op * DW_TILE + (idx >> 10) * DW_BLK + sw32b_off((idx & 1023) >> 3, idx & 7);
+    for (int j = tid; j < NCHUNK; j += TC_THREADS) {
+      const int op = j >> LOG_OP, idx = j & ((1 << LOG_OP) - 1);
+      const uint32_t off = op * DW_TILE + (idx >> (LOG_OP - 1)) * DW_BLK +
+                           sw32b_off((idx & ((1 << (LOG_OP - 1)) - 1)) >> 3, idx & 7);
       const float4 x = *reinterpret_cast<const float4*>(p_hi + off);
       uint4 l;
       l.x = __float_as_uint(x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u)) & 0xffffe000u;
@@ -117,10 +127,11 @@ k_dw_tc(int M, int Np, int Nq, const float* __restrict__ P, int64_t ldp, const f
     __syncthreads();
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint64_t dp_hi = umma_desc_mn_sw128(smem_u32(p_hi)), dp_lo = umma_desc_mn_sw128(smem_u32(p_lo));
-      const uint64_t dq_hi = umma_desc_mn_sw128(smem_u32(q_hi)), dq_lo = umma_desc_mn_sw128(smem_u32(p_lo + DW_TILE));
+      const uint64_t dp_hi = umma_desc_mn_sw128(smem_u32(p_hi), DW_BLK), dp_lo = umma_desc_mn_sw128(smem_u32(p_lo), DW_BLK);
+      const uint64_t dq_hi = umma_desc_mn_sw128(smem_u32(q_hi), DW_BLK),
+                     dq_lo = umma_desc_mn_sw128(smem_u32(p_lo + DW_TILE), DW_BLK);
 #pragma unroll 1
-      for (int k = 0; k < TC_BM / 8; ++k, ++ks) {
+      for (int k = 0; k < BM / 8; ++k, ++ks) {
         const uint64_t adv = (uint64_t)((k * 1024) >> 4);       // next 8-row group
         umma_tf32(tmem_d + (uint32_t)((ks % DW_NA) * DW_F), dp_hi + adv, dq_hi + adv, idesc, ks >= DW_NA ? 1u : 0u);
         umma_tf32(tmem_d + (uint32_t)(DW_NA * DW_F), dp_lo + adv, dq_hi + adv, idesc, ks > 0 ? 1u : 0u);
@@ -128,7 +139,7 @@ k_dw_tc(int M, int Np, int Nq, const float* __restrict__ P, int64_t ldp, const f
       }
       umma_commit(&mma_bar);
     } else if (tid >= 32) {
-      ks += TC_BM / 8;
+      ks += BM / 8;
     }
     // ---- column sums of the chosen operand from the raw tile (while the tensor core runs)
     if (colsum_of >= 0) {
@@ -136,7 +147,7 @@ k_dw_tc(int M, int Np, int Nq, const float* __restrict__ P, int64_t ldp, const f
       const int c = (cs_col & 31) >> 2, e = cs_col & 3;
       float s = 0.f;
 #pragma unroll 4
-      for (int r = cs_rg; r < TC_BM; r += 4) s += *reinterpret_cast<const float*>(t0 + sw32b_off(r, c) + e * 4);
+      for (int r = cs_rg; r < BM; r += 4) s += *reinterpret_cast<const float*>(t0 + sw32b_off(r, c) + e * 4);
       cs += (double)s;
     }
     mbar_wait(&mma_bar, phase);
@@ -146,7 +157,7 @@ k_dw_tc(int M, int Np, int Nq, const float* __restrict__ P, int64_t ldp, const f
   }
   ks = __shfl_sync(0xffffffffu, ks, 0);                  // warp 0: lane 0 counted while issuing
   // ---- per-CTA partials: D rows 0..63 live in TMEM lanes 0..63 (warps with quadrant 0 and 1)
-  const int n_steps = ((n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * (TC_BM / 8);
+  const int n_steps = ((n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * (BM / 8);
   {
     const int q = warp & 3;
     if (q < 2) {
@@ -235,9 +246,19 @@ k_dw_cs_reduce(const double* __restrict__ ws, int parts, int cols, float* __rest
   }
 }
 
+static int dw_bm() {                 // rows per tile: 64 (two CTAs per SM, default) or 128 (BIGNN_DW_BM=128)
+  static int bm = 0;
+  if (bm == 0) {
+    const char* e = getenv("BIGNN_DW_BM");
+    bm = (e && atoi(e) == 128) ? 128 : 64;
+  }
+  return bm;
+}
+
 static int dw_grid(int M) {
-  const int n_tiles = ceil_div(M, TC_BM);
-  int g = sm_count();
+  const int bm = dw_bm();
+  const int n_tiles = ceil_div(M, bm);
+  int g = sm_count() * (bm == 64 ? 2 : 1);
   return g > n_tiles ? n_tiles : g;
 }
 
@@ -267,14 +288,18 @@ extern "C" int bignn_dw_tc_f32(int32_t M, int32_t Np, int32_t Nq, const float* P
   const int grid = dw_grid(M);
   float* ws_dw = (float*)workspace;
   double* ws_cs = (double*)((uint8_t*)workspace + (((int64_t)grid * Np * Nq * sizeof(float) + 15) & ~(int64_t)15));
-  constexpr int smem = 6 * DW_TILE + 1024;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_dw_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(k_dw_tc<64, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * 2 * 64 * 128 + 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(k_dw_tc<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * 2 * 128 * 128 + 1024);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  k_dw_tc<<<grid, TC_THREADS, smem, st>>>(M, Np, Nq, P, ldp, Q, ldq, colsum_of < 0 ? -1 : colsum_of, ws_dw, ws_cs);
+  if (dw_bm() == 64)
+    k_dw_tc<64, 3><<<grid, TC_THREADS, 6 * 2 * 64 * 128 + 1024, st>>>(M, Np, Nq, P, ldp, Q, ldq, colsum_of < 0 ? -1 : colsum_of, ws_dw, ws_cs);
+  else
+    k_dw_tc<128, 4><<<grid, TC_THREADS, 6 * 2 * 128 * 128 + 1024, st>>>(M, Np, Nq, P, ldp, Q, ldq, colsum_of < 0 ? -1 : colsum_of, ws_dw, ws_cs);
   k_dw_reduce<<<ceil_div(Np * Nq, 32), 256, 0, st>>>(ws_dw, grid, Np * Nq, D);
   BIGNN_LAUNCH_COUNT(2);
   if (colsum_of >= 0) {

@@ -79,8 +79,16 @@ def test_gin_mlp_bn_block_fused_backward_vs_torch_fp64(act, rows, F):
         yy.backward(dy.to(DEV))
         res[fused] = (yy.detach(), [q.grad for q in Q])
         assert rel(yy, want) < 5e-6
+        scale = {}
         for name, q, p in zip(('dz', 'dw1', 'db1', 'dw2', 'db2', 'dgamma', 'dbeta'), Q, P):
-            assert rel(q.grad, p.grad) < 5e-5, (name, fused)
+            # a bias that reaches the BatchNorm through identity activations has a true gradient of exactly 0
+            # (what is stored is rounding noise): measure biases on the scale of their layer's weight gradient
+            sc = float(p.grad.abs().max())
+            scale[name] = sc
+            if name in ('db1', 'db2'):
+                sc = max(sc, scale['dw' + name[-1]])
+            err = float((q.grad.double().cpu() - p.grad).abs().max()) / max(sc, 1e-30)
+            assert err < 5e-5, (name, fused, err)
     assert torch.equal(res[True][0], res[False][0])
     for a, b in zip(res[True][1], res[False][1]):
         assert torch.equal(a, b)                 # same formulas on the same values: identical bits
