@@ -250,8 +250,21 @@ def run_ours(args):
     dev = 'cuda:%d' % local
     if world > 1:
         if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
-            os.environ['NCCL_DEBUG'] = 'WARN'          # keep stdout to the one JSON line
-        dist.init_process_group('nccl', device_id=torch.device(dev))
+            os.environ['NCCL_DEBUG'] = 'WARN'
+        # NCCL prints its version banner on stdout when the first communicator comes up (at WARN level too):
+        # point fd 1 at stderr until then, so that stdout carries nothing but the one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=torch.device(dev))
+            t = torch.zeros(1, device=dev)
+            dist.all_reduce(t)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     B._lib.load()
     peaks = {}
     pk = os.path.join(ROOT, 'MEASURED_PEAKS.json')
