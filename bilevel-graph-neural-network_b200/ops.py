@@ -204,7 +204,10 @@ def bn_parts(S, rows):
     """Row parts per segment so that S*parts CTAs cover the SMs a few times."""
     if S <= 0:
         return 1
-    want = max(1, (148 * 4) // S)
+    # streaming-sized inputs (> 64 MB at 64 channels): fill all 8 resident CTAs per SM; small inputs keep fewer,
+    # larger parts (their finalize kernels walk the parts and are latency-bound)
+    per_sm = 8 if rows >= 262144 else 4
+    want = max(1, (148 * per_sm) // S)
     by_rows = max(1, (rows // max(S, 1)) // 64)
     return int(max(1, min(want, by_rows, 256)))
 
