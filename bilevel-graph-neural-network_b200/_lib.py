@@ -34,7 +34,7 @@ SIGNATURES = {
     'bignn_gcn_dinv': ('i', 'ppips'),
     'bignn_spmm_f32': ('i', 'pp' 'pl' 'pl' 'iiif' 'ppi' 's'),
     'bignn_spmm_rows_f32': ('i', 'pp' 'pl' 'pl' 'iiiif' 'ppi' 's'),
-    'bignn_spmm_planned_rows_f32': ('i', 'pp' 'ppii' 'pi' 'pl' 'pl' 'iiiif' 'ppi' 'pl' 's'),
+    'bignn_spmm_planned_rows_f32': ('i', 'pp' 'ppii' 'pii' 'pl' 'pl' 'iiiif' 'ppi' 'pl' 's'),
     'bignn_spmm_planned_workspace_bytes': ('l', 'ii'),
     'bignn_spmm_planned_f32': ('i', 'pp' 'ppii' 'pi' 'pl' 'pl' 'iiif' 'ppi' 'pl' 's'),
     'bignn_gemm_workspace_bytes': ('l', 'iiii'),

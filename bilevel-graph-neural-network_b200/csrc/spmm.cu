@@ -153,6 +153,37 @@ k_spmm_items_v4(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__
   }
 }
 
+// partial sums of items [a, b) added to acc in item order, four 128-bit loads in flight per lane
+template <int L, int NV>
+__device__ __forceinline__ void sum_items(float4 (&acc)[NV], int a, int b, int lane, int D4,
+                                          const float* __restrict__ partial) {
+  constexpr int U = 4;
+  int it = a;
+  for (; it + U <= b; it += U) {
+    float4 val[U][NV];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int q = lane + v * L;
+        val[u][v] = q < D4 ? ldg4(partial + ((int64_t)(it + u) * D4 + q) * 4) : f4zero();
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) acc_add(acc[v], val[u][v]);
+    }
+  }
+  for (; it < b; ++it) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int q = lane + v * L;
+      if (q < D4) acc_add(acc[v], ldg4(partial + ((int64_t)it * D4 + q) * 4));
+    }
+  }
+}
+
 template <int L, int NV, int MODE>
 __global__ void __launch_bounds__(256)
 k_spmm_multi_v4(const int32_t* __restrict__ item_ptr, const int32_t* __restrict__ multi_rows, int n_multi,
@@ -168,16 +199,57 @@ k_spmm_multi_v4(const int32_t* __restrict__ item_ptr, const int32_t* __restrict_
     float4 acc[NV];
 #pragma unroll
     for (int v = 0; v < NV; ++v) acc[v] = f4zero();
-    for (int it = i0; it < i1; ++it) {
-#pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        const int q = lane + v * L;
-        if (q < D4) acc_add(acc[v], ldg4(partial + ((int64_t)it * D4 + q) * 4));
-      }
-    }
+    sum_items<L, NV>(acc, i0, i1, lane, D4, partial);
     float di = 0.f;
     if (MODE == BIGNN_SPMM_GCN) di = __ldg(dinv + row + roff);
     finish_row<L, NV, MODE>(acc, row, row + roff, lane, D4, self_coef, di, X, ldx, Y, ldy, bias, act);
+  }
+}
+
+// Hub rows (more than BIGNN_SPMM_BIG_ITEMS work items, e.g. a drug that interacts with most of a 200 k-drug graph):
+// one CTA per row; every sub-warp sums a contiguous chunk of the row's partials in item order, the chunk sums are
+// added in chunk order by sub-warp 0.  A fixed tree per (number of items, kernel configuration) -- deterministic --
+// that shortens the dependent chain of the row from n_items to n_items / (256/L) + 256/L additions.
+template <int L, int NV, int MODE>
+__global__ void __launch_bounds__(256)
+k_spmm_multi_big_v4(const int32_t* __restrict__ item_ptr, const int32_t* __restrict__ big_rows, int n_big,
+                    const float* __restrict__ X, int64_t ldx, float* __restrict__ Y, int64_t ldy,
+                    int D4, float self_coef, const float* __restrict__ dinv, const float* __restrict__ bias, int act,
+                    const float* __restrict__ partial, int roff) {
+  extern __shared__ float4 big_red[];                 // [256/L][D4]
+  const int rpb = blockDim.x / L;
+  const int sub = threadIdx.x / L;
+  const int lane = threadIdx.x % L;
+  for (int m = blockIdx.x; m < n_big; m += gridDim.x) {
+    const int row = __ldg(big_rows + m);
+    const int i0 = __ldg(item_ptr + row), i1 = __ldg(item_ptr + row + 1);
+    const int chunk = (i1 - i0 + rpb - 1) / rpb;
+    const int a = min(i0 + sub * chunk, i1), b = min(a + chunk, i1);
+    float4 acc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) acc[v] = f4zero();
+    sum_items<L, NV>(acc, a, b, lane, D4, partial);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int q = lane + v * L;
+      if (q < D4) big_red[sub * D4 + q] = acc[v];
+    }
+    __syncthreads();
+    if (sub == 0) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) acc[v] = f4zero();
+      for (int s = 0; s < rpb; ++s) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const int q = lane + v * L;
+          if (q < D4) acc_add(acc[v], big_red[s * D4 + q]);
+        }
+      }
+      float di = 0.f;
+      if (MODE == BIGNN_SPMM_GCN) di = __ldg(dinv + row + roff);
+      finish_row<L, NV, MODE>(acc, row, row + roff, lane, D4, self_coef, di, X, ldx, Y, ldy, bias, act);
+    }
+    __syncthreads();                                   // big_red is rewritten for the CTA's next row
   }
 }
 
@@ -309,7 +381,8 @@ template <int MODE>
 static int launch_planned(const int32_t* row_ptr, const int32_t* col_idx, const int32_t* item_ptr,
                           const int32_t* item_row, int n_items, int seg, const int32_t* multi_rows, int n_multi,
                           const float* X, int64_t ldx, float* Y, int64_t ldy, int D, float self_coef,
-                          const float* dinv, const float* bias, int act, float* partial, int roff, cudaStream_t st) {
+                          const float* dinv, const float* bias, int act, float* partial, int roff, int n_big,
+                          cudaStream_t st) {
   const int cap = sm_count() * 8;
   const int d4 = D / 4;
 #define BIGNN_PLANNED(L, NV)                                                                          \
@@ -320,11 +393,18 @@ static int launch_planned(const int32_t* row_ptr, const int32_t* col_idx, const 
     k_spmm_items_v4<L, NV, MODE><<<grid, 256, 0, st>>>(row_ptr, col_idx, item_ptr, item_row, n_items, seg, X, \
                                                        ldx, Y, ldy, d4, self_coef, dinv, bias, act, partial, roff); \
     BIGNN_LAUNCH_COUNT(1);                                                                            \
-    if (n_multi > 0) {                                                                                \
-      int g2 = ceil_div(n_multi, per);                                                                \
+    const int n_small = n_multi - n_big;               /* the hub rows are the LAST n_big of multi_rows */ \
+    if (n_small > 0) {                                                                                \
+      int g2 = ceil_div(n_small, per);                                                                \
       if (g2 > cap) g2 = cap;                                                                         \
-      k_spmm_multi_v4<L, NV, MODE><<<g2, 256, 0, st>>>(item_ptr, multi_rows, n_multi, X, ldx, Y, ldy, d4,     \
+      k_spmm_multi_v4<L, NV, MODE><<<g2, 256, 0, st>>>(item_ptr, multi_rows, n_small, X, ldx, Y, ldy, d4,     \
                                                        self_coef, dinv, bias, act, partial, roff);    \
+      BIGNN_LAUNCH_COUNT(1);                                                                          \
+    }                                                                                                 \
+    if (n_big > 0) {                                                                                  \
+      const int g3 = n_big > cap ? cap : n_big;                                                       \
+      k_spmm_multi_big_v4<L, NV, MODE><<<g3, 256, (256 / L) * d4 * sizeof(float4), st>>>(             \
+          item_ptr, multi_rows + n_small, n_big, X, ldx, Y, ldy, d4, self_coef, dinv, bias, act, partial, roff); \
       BIGNN_LAUNCH_COUNT(1);                                                                          \
     }                                                                                                 \
   }
@@ -391,19 +471,21 @@ extern "C" int bignn_spmm_planned_f32(const int32_t* row_ptr, const int32_t* col
                                       float* Y, int64_t ldy, int32_t n_rows, int32_t D, int32_t mode,
                                       float self_coef, const float* dinv, const float* bias, int32_t act,
                                       void* workspace, int64_t workspace_bytes, void* stream) {
-  return bignn_spmm_planned_rows_f32(row_ptr, col_idx, item_ptr, item_row, n_items, seg, multi_rows, n_multi, X, ldx, Y,
-                                     ldy, n_rows, 0, D, mode, self_coef, dinv, bias, act, workspace, workspace_bytes,
-                                     stream);
+  return bignn_spmm_planned_rows_f32(row_ptr, col_idx, item_ptr, item_row, n_items, seg, multi_rows, n_multi, 0, X, ldx,
+                                     Y, ldy, n_rows, 0, D, mode, self_coef, dinv, bias, act, workspace,
+                                     workspace_bytes, stream);
 }
 
 extern "C" int bignn_spmm_planned_rows_f32(const int32_t* row_ptr, const int32_t* col_idx, const int32_t* item_ptr,
                                            const int32_t* item_row, int32_t n_items, int32_t seg,
-                                           const int32_t* multi_rows, int32_t n_multi, const float* X, int64_t ldx,
+                                           const int32_t* multi_rows, int32_t n_multi, int32_t n_big,
+                                           const float* X, int64_t ldx,
                                            float* Y, int64_t ldy, int32_t n_rows, int32_t row_offset, int32_t D,
                                            int32_t mode, float self_coef, const float* dinv, const float* bias,
                                            int32_t act, void* workspace, int64_t workspace_bytes, void* stream) {
   const int roff = row_offset;
   if (n_rows < 0 || D < 0 || n_items < 0 || n_multi < 0 || seg <= 0 || !row_ptr) return BIGNN_EINVAL;
+  if (n_big < 0 || n_big > n_multi) return BIGNN_EINVAL;
   if (n_rows == 0 || D == 0) return 0;
   if (!X || !Y || !item_ptr || !item_row || ldx < D || ldy < D || D > 512) return BIGNN_EINVAL;
   if (n_multi > 0 && !multi_rows) return BIGNN_EINVAL;
@@ -417,9 +499,9 @@ extern "C" int bignn_spmm_planned_rows_f32(const int32_t* row_ptr, const int32_t
   cudaStream_t st = (cudaStream_t)stream;
   float* partial = (float*)workspace;
   switch (mode) {
-    case BIGNN_SPMM_SUM: return launch_planned<BIGNN_SPMM_SUM>(row_ptr, col_idx, item_ptr, item_row, n_items, seg, multi_rows, n_multi, X, ldx, Y, ldy, D, self_coef, dinv, bias, act, partial, roff, st);
-    case BIGNN_SPMM_GIN: return launch_planned<BIGNN_SPMM_GIN>(row_ptr, col_idx, item_ptr, item_row, n_items, seg, multi_rows, n_multi, X, ldx, Y, ldy, D, self_coef, dinv, bias, act, partial, roff, st);
-    case BIGNN_SPMM_GCN: return launch_planned<BIGNN_SPMM_GCN>(row_ptr, col_idx, item_ptr, item_row, n_items, seg, multi_rows, n_multi, X, ldx, Y, ldy, D, self_coef, dinv, bias, act, partial, roff, st);
+    case BIGNN_SPMM_SUM: return launch_planned<BIGNN_SPMM_SUM>(row_ptr, col_idx, item_ptr, item_row, n_items, seg, multi_rows, n_multi, X, ldx, Y, ldy, D, self_coef, dinv, bias, act, partial, roff, n_big, st);
+    case BIGNN_SPMM_GIN: return launch_planned<BIGNN_SPMM_GIN>(row_ptr, col_idx, item_ptr, item_row, n_items, seg, multi_rows, n_multi, X, ldx, Y, ldy, D, self_coef, dinv, bias, act, partial, roff, n_big, st);
+    case BIGNN_SPMM_GCN: return launch_planned<BIGNN_SPMM_GCN>(row_ptr, col_idx, item_ptr, item_row, n_items, seg, multi_rows, n_multi, X, ldx, Y, ldy, D, self_coef, dinv, bias, act, partial, roff, n_big, st);
     default: return BIGNN_EINVAL;
   }
 }

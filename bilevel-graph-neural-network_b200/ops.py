@@ -32,6 +32,9 @@ LONG_ROW_SEG = int(__import__('os').environ.get('BIGNN_SEG', 32))      # neighbo
                        # item length bounds the dependent-latency chain (8 steps); hub rows become many items
 
 
+BIG_ITEMS = 64         # = BIGNN_SPMM_BIG_ITEMS (include/bignn_b200.h)
+
+
 class RowPlan(object):
     """Work-item split of a skewed CSR (host-built once for a static graph)."""
 
@@ -43,6 +46,10 @@ class RowPlan(object):
         self.seg = int(seg)
         self.n_items = int(ptr[-1])
         multi = np.nonzero(items > 1)[0]
+        # hub rows (more than BIG_ITEMS items) go last: bignn_spmm_planned_rows_f32 sums them with a whole CTA
+        big = items[multi] > BIG_ITEMS
+        multi = np.concatenate([multi[~big], multi[big]])
+        self.n_big = int(big.sum())
         self.n_multi = int(multi.shape[0])
         as_dev = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32)).to(device)
         self.item_ptr = as_dev(ptr)
@@ -98,14 +105,10 @@ def spmm(csr, x, mode, self_coef=0.0, dinv=None, bias=None, act=0, out=None):
     if pl is not None and d % 4 == 0 and d <= 512:
         wsb = _lib.call('bignn_spmm_planned_workspace_bytes', pl.n_items, d) if pl.n_multi else 0
         ws = _ws(wsb, x.device) if wsb else None
-        if roff is None:
-            _lib.call('bignn_spmm_planned_f32', csr.row_ptr, csr.col_idx, pl.item_ptr, pl.item_row, pl.n_items, pl.seg,
-                      pl.multi_rows, pl.n_multi, x, x.stride(0), y, y.stride(0), n, d, int(mode), float(self_coef),
-                      dinv, bias, int(act), ws, int(wsb))
-        else:
-            _lib.call('bignn_spmm_planned_rows_f32', csr.row_ptr, csr.col_idx, pl.item_ptr, pl.item_row, pl.n_items,
-                      pl.seg, pl.multi_rows, pl.n_multi, x, x.stride(0), y, y.stride(0), n, int(roff), d, int(mode),
-                      float(self_coef), dinv, bias, int(act), ws, int(wsb))
+        _lib.call('bignn_spmm_planned_rows_f32', csr.row_ptr, csr.col_idx, pl.item_ptr, pl.item_row, pl.n_items,
+                  pl.seg, pl.multi_rows, pl.n_multi, pl.n_big, x, x.stride(0), y, y.stride(0), n,
+                  int(roff) if roff is not None else 0, d, int(mode), float(self_coef), dinv, bias, int(act), ws,
+                  int(wsb))
         return y
     if roff is None:
         _lib.call('bignn_spmm_f32', csr.row_ptr, csr.col_idx, x, x.stride(0), y, y.stride(0), n, d,

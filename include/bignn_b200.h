@@ -108,9 +108,13 @@ int bignn_spmm_rows_f32(const int32_t* row_ptr, const int32_t* col_idx,
                         const float* X, int64_t ldx, float* Y, int64_t ldy,
                         int32_t n_rows, int32_t row_offset, int32_t D, int32_t mode, float self_coef,
                         const float* dinv, const float* bias, int32_t act, void* stream);
+/* n_big: the LAST n_big entries of multi_rows are hub rows (more than BIGNN_SPMM_BIG_ITEMS work items); their
+ * partial sums are added by a whole CTA in a fixed two-level order instead of one sub-warp walking all of them
+ * (a drug with 150 k interactions has ~4 900 items).  n_big = 0: every multi-item row is summed in item order. */
+#define BIGNN_SPMM_BIG_ITEMS 64
 int bignn_spmm_planned_rows_f32(const int32_t* row_ptr, const int32_t* col_idx,
                                 const int32_t* item_ptr, const int32_t* item_row, int32_t n_items, int32_t seg,
-                                const int32_t* multi_rows, int32_t n_multi,
+                                const int32_t* multi_rows, int32_t n_multi, int32_t n_big,
                                 const float* X, int64_t ldx, float* Y, int64_t ldy,
                                 int32_t n_rows, int32_t row_offset, int32_t D, int32_t mode, float self_coef,
                                 const float* dinv, const float* bias, int32_t act,

@@ -91,7 +91,7 @@ class Fake(object):
         return 0
 
     def bignn_spmm_planned_rows_f32(self, row_ptr, col_idx, item_ptr, item_row, n_items, seg, multi_rows, n_multi,
-                                    X, ldx, Y, ldy, n, roff, D, mode, self_coef, dinv, bias, act, ws, wsb):
+                                    n_big, X, ldx, Y, ldy, n, roff, D, mode, self_coef, dinv, bias, act, ws, wsb):
         return self.bignn_spmm_rows_f32(row_ptr, col_idx, X, ldx, Y, ldy, n, roff, D, mode, self_coef, dinv, bias, act)
 
     def bignn_bn_rows_workspace_bytes(self, C, parts):
