@@ -75,6 +75,14 @@ def pack_dataset(train_data, val_pairs, test_pairs):
         test_pairs=test_pairs.numpy().astype(np.int64),
         num_labels=np.int64(ds.num_labels),
     )
+    # per-edge-type interaction graphs (DrugCombo; utils/data/dataset.py:105-115), in the order
+    # LoadInteractionGraph hands them to NodeModelAggrByEdge.GNNS[i] (model/layers_load_interaction_graph.py:16-19):
+    # the index prefix keeps that order under sorting
+    if getattr(ds, 'interaction_nxgraphs', None) and len(ds.interaction_nxgraphs) > 1:
+        for i, (k, g) in enumerate(ds.interaction_nxgraphs.items()):
+            ei = create_edge_index(g)[0].numpy()
+            out['etype_row/%d_%s' % (i, k)] = ei[0].astype(np.int32)
+            out['etype_col/%d_%s' % (i, k)] = ei[1].astype(np.int32)
     return out
 
 
@@ -84,7 +92,7 @@ def sd_to_np(sd):
     return {k: v.detach().cpu().numpy().copy() for k, v in sd.items() if k.startswith('layers.')}
 
 
-def run_step_golden(train_data, FLAGS, out_path, n_seq=24):
+def run_step_golden(train_data, FLAGS, out_path, n_seq=24, light=False):
     """One recorded train step (reference src/train.py:136-141) + sampler sequence."""
     import torch
     import train as T
@@ -162,11 +170,16 @@ def run_step_golden(train_data, FLAGS, out_path, n_seq=24):
         if 'running' in k or 'num_batches' in k:
             rec['sd_init/' + k] = v
     for k, v in sd1.items():
+        if light and not ('running' in k or 'num_batches' in k or k.startswith('layers.%d.' % (FLAGS.layer_num - 2))):
+            continue          # light fixture: post-step BatchNorm buffers and the scorer only
         rec['sd1/' + k] = v
     for k, v in grads.items():
         rec['grad/' + k] = v
     # per-chunk indexing (bit-exact targets) -- all chunks; activations: first & last chunk
     for c, b in enumerate(chunks):
+        if light:             # indexing is pinned by the DrugBank fixture; keep the chunk schedule only
+            rec['chunk%d/gids' % c] = np.asarray(list(b.merge_data['gids_to_batch_ind'].keys()), np.int64)
+            continue
         md = b.merge_data
         m = md['merge']
         rec['chunk%d/gids' % c] = np.asarray(list(md['gids_to_batch_ind'].keys()), np.int64)
@@ -183,12 +196,16 @@ def run_step_golden(train_data, FLAGS, out_path, n_seq=24):
                 rec['chunk%d/act%d' % (c, li + 1)] = a
         if c == 0:
             rec['chunk0/pooled'] = acts_per_chunk[0][-1]
+    rec['upper_acts_n'] = list(range(len(rec['upper_acts'])))
     for li, a in enumerate(rec.pop('upper_acts')):
         if li == 0:
             continue          # acts[0] is the pair batch's merged x (unused upstairs)
         if a.ndim == 0:
             continue
+        if light and li not in (2, len(rec['upper_acts_n']) - 3, len(rec['upper_acts_n']) - 2):
+            continue          # light fixture: first and last upper-level activations + scorer output (act1 = init_x)
         rec['upper/act%d' % li] = a
+    rec.pop('upper_acts_n', None)
     np.savez_compressed(out_path, **rec)
     print('wrote', out_path, 'loss', loss.item(), 'chunks', len(chunks), 'init chunks', n_init_chunks)
 
@@ -196,6 +213,10 @@ def run_step_golden(train_data, FLAGS, out_path, n_seq=24):
     seq = dict(np_state_keys=np.asarray(rng_state_np[1], np.uint32),
                np_state_pos=np.int64(rng_state_np[2]))
     pos, neg, ys, losses = [], [], [], []
+    if n_seq == 0:
+        BatchData.__init__ = orig_init
+        Model.forward = orig_fwd
+        return seq
     for it in range(n_seq):
         model.train()
         model.zero_grad()
@@ -222,15 +243,20 @@ def main():
     ap.add_argument('--model', default='lower_level_gnn_higher_level')
     ap.add_argument('--tag', default='bignn_gin_gcn')
     ap.add_argument('--skip_pack', action='store_true')
+    ap.add_argument('--dataset', default='drugbank', choices=['drugbank', 'drugcombo'])
+    ap.add_argument('--n_seq', type=int, default=24)
+    ap.add_argument('--light', action='store_true', help='smaller step fixture (no per-chunk indexing arrays)')
     args = ap.parse_args()
     os.makedirs(args.out, exist_ok=True)
-    ref_loader.load_reference(model=args.model, lower=args.lower, higher=args.higher)
+    ref_loader.load_reference(model=args.model, lower=args.lower, higher=args.higher, dataset=args.dataset)
+    if args.dataset == 'drugcombo':
+        ref_loader.patch_for_drugcombo()
     train_data, val_pairs, test_pairs, FLAGS = ref_loader.load_drugbank_fold(1)
     if not args.skip_pack:
         packed = pack_dataset(train_data, val_pairs, test_pairs)
-        np.savez_compressed(os.path.join(args.out, 'drugbank_packed.npz'), **packed)
+        np.savez_compressed(os.path.join(args.out, args.dataset + '_packed.npz'), **packed)
         print('packed', {k: getattr(v, 'shape', v) for k, v in packed.items()})
-    seq = run_step_golden(train_data, FLAGS, os.path.join(args.out, args.tag + '_step.npz'))
+    seq = run_step_golden(train_data, FLAGS, os.path.join(args.out, args.tag + '_step.npz'), n_seq=args.n_seq, light=args.light)
     np.savez_compressed(os.path.join(args.out, args.tag + '_sampler_seq.npz'), **seq)
     layer_specs = [getattr(FLAGS, 'layer_%d' % i) for i in range(1, FLAGS.layer_num + 1)]
     with open(os.path.join(args.out, args.tag + '_layers.txt'), 'w') as f:

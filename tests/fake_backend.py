@@ -299,8 +299,54 @@ class Fake(object):
         Y.copy_(ACTS[act](X))
         return 0
 
-    def bignn_gat_fwd(self, *a):
-        raise NotImplementedError('GAT is exercised by the gpu tests')
+    # ---- one-head GAT edge softmax (include/bignn_b200.h); CSR row r aggregates over its neighbours c, i.e.
+    # PyG's edge (source = c, target = r); self loops removed, then one added per node (GATConv 1.1.2)
+    def _gat_out(self, row_ptr, col_idx, n, n_block, D, H, p, q, bias, slope, group_target):
+        r, c = self._coo(row_ptr, col_idx, n)
+        keep = r != c
+        loops = torch.arange(n)
+        tgt, src = torch.cat([r[keep], loops]), torch.cat([c[keep], loops])
+        a = torch.nn.functional.leaky_relu(p[tgt] + q[src], slope)
+        grp = tgt if group_target else src
+        amax = torch.full((n,), -float('inf'), dtype=a.dtype).scatter_reduce(0, grp, a.detach(), 'amax')
+        e = (a - amax[grp]).exp()
+        ssum = torch.zeros(n, dtype=a.dtype).index_add(0, grp, e)
+        alpha = e / (ssum[grp] + 1e-16)
+        out = torch.zeros(n, D, dtype=H.dtype).index_add(0, tgt, alpha.view(-1, 1) * H[src, :D])
+        if bias is not None:
+            out = out + bias.view(-1, D).repeat_interleave(n_block, 0)[:n]
+        return out
+
+    @staticmethod
+    def _gat_pq(H, att, n, n_block, D):
+        a = att.view(-1, 2 * D).repeat_interleave(n_block, 0)[:n]
+        return (H[:, :D] * a[:, :D]).sum(-1), (H[:, :D] * a[:, D:]).sum(-1), a
+
+    def bignn_gat_fwd_workspace_bytes(self, n_items, D):
+        return 16
+
+    def bignn_gat_bwd_workspace_bytes(self, n, D, n_items):
+        return 16
+
+    def bignn_gat_fwd(self, row_ptr, col_idx, item_ptr, item_row, n_items, seg, multi_rows, n_multi, n, n_block, D,
+                      H, ldh, att, bias, slope, group_target, out, ldo, scratch, ws, wsb):
+        with torch.no_grad():
+            p, q, _ = self._gat_pq(H, att, n, n_block, D)
+            out[:n, :D] = self._gat_out(row_ptr, col_idx, n, n_block, D, H, p, q, bias, slope, group_target)
+        return 0
+
+    def bignn_gat_bwd(self, row_ptr, col_idx, item_ptr, item_row, n_items, seg, multi_rows, n_multi, n, n_block, D,
+                      H, ldh, att, bias, slope, group_target, out, ldo, dOut, lddo, scratch, dH, lddh, dpq, ws, wsb):
+        with torch.enable_grad():
+            Hg = H.detach().clone().requires_grad_(True)
+            p0, q0, a = self._gat_pq(H.detach(), att.detach(), n, n_block, D)
+            p, q = p0.clone().requires_grad_(True), q0.clone().requires_grad_(True)
+            o = self._gat_out(row_ptr, col_idx, n, n_block, D, Hg, p, q, None, slope, group_target)
+            G, dp, dq = torch.autograd.grad(o, (Hg, p, q), dOut[:n, :D])
+        dH[:n, :D] = G + dp.view(-1, 1) * a[:, :D] + dq.view(-1, 1) * a[:, D:]      # dH includes the p / q paths
+        dpq[:n] = dp
+        dpq[n:2 * n] = dq
+        return 0
 
     def bignn_ce_fwd(self, logits, ldx, labels, P, K, loss):
         loss.copy_(torch.nn.functional.cross_entropy(logits, labels.long()))

@@ -142,3 +142,61 @@ def test_negative_sampler_bit_exact_with_sorted_key_tables(cpu_world, golden_dir
         bd = B.BatchData(pos, data, sampled_gids=np.unique(pos), is_train=True, merge_graphs=False)
         assert np.array_equal(bd.negative_pair_gids, neg)
         assert np.array_equal([p.true_label for p in bd.pair_list], y)
+
+
+def test_drugcombo_architecture_host_path_matches_reference_golden(golden_dir):
+    """Host wiring of the DrugCombo architecture (layer specs, state_dict layout incl. the MetaLayer aliases, the
+    per-edge-type upper level batched as one block-diagonal GAT, 3-class scorer, cross entropy) against vectors
+    recorded from the reference's own code (tests/golden/bignn_drugcombo_step.npz); arithmetic = the torch-CPU
+    stand-in of the C-ABI."""
+    fake_backend.install()
+    try:
+        z = np.load(os.path.join(golden_dir, 'bignn_drugcombo_step.npz'))
+        with open(os.path.join(golden_dir, 'bignn_drugcombo_layers.txt')) as f:
+            lines = f.read().split()
+        flags = B.make_flags(dataset='drugcombo', higher_level_gnn_type='gat', device='cpu')
+        B.set_flags(flags)
+        assert [getattr(flags, 'layer_%d' % i) for i in range(1, flags.layer_num + 1)] == lines
+        data = B.BiGNNData.from_npz(os.path.join(golden_dir, 'drugcombo_packed.npz'), device='cpu')
+        model = B.Model(data)
+        assert {k for k in model.state_dict() if k.startswith('layers.')} == {k[4:] for k in z.files if k.startswith('sd0/')}
+        load_state(model, z)
+        for k in z.files:
+            if k.startswith('sd_init/'):
+                model.state_dict()[k[len('sd_init/'):]].copy_(torch.from_numpy(np.asarray(z[k])))
+        model.train()
+        model.zero_grad()
+        B.train._get_initial_embd(data, model)
+        assert rel(data.interaction_combo_nxgraph.init_x.detach().numpy(), z['init_x']) < 1e-5
+        bd = B.BatchData(z['positive_gids'], data, sampled_gids=z['sampled_gids'], is_train=False, merge_graphs=False)
+        bd.batch_gids = z['batch_gids']
+        bd.pair_list = [B.batch.PairRecord(int(l), tuple(g)) for l, g in zip(z['y_true'], z['batch_gids'].tolist())]
+        bd.batch_interaction_inds = [data.gs_map[g] for g in bd.batch_gids.flatten().tolist()]
+        model.use_layers = 'higher_layers'
+        loss = model(bd)
+        assert abs(float(loss.detach()) - float(z['loss'])) < 1e-5
+        assert rel(model.acts[2].detach().numpy(), z['upper/act2']) < 1e-5
+        assert rel(model.acts[4].detach().numpy(), z['upper/act4']) < 1e-5
+        assert rel(model.acts[-2].detach().numpy(), z['upper/act5']) < 1e-5
+        loss.backward()
+        scale = {}
+        for k in z.files:
+            if k.startswith('grad/'):
+                lid = k.split('.')[1]
+                scale[lid] = max(scale.get(lid, 0.0), float(np.abs(z[k]).max()))
+        n = 0
+        for k, p in model.named_parameters():
+            if k.startswith('layers.'):
+                err = float(np.abs(p.grad.numpy().astype(np.float64) - z['grad/' + k]).max()) / scale[k.split('.')[1]]
+                assert err < (1e-3 if int(k.split('.')[1]) < 5 else 5e-5), (k, err)      # wiring check (see above)
+                n += 1
+        assert n == len([k for k in z.files if k.startswith('grad/')])
+        sd = model.state_dict()
+        for k in z.files:
+            if k.startswith('sd1/') and 'running' in k:
+                assert rel(sd[k[4:]].numpy(), z[k]) < 1e-5, k
+            if k.startswith('sd1/') and 'num_batches' in k:
+                assert int(sd[k[4:]]) == int(z[k])
+    finally:
+        fake_backend.uninstall()
+        B.set_flags(None)

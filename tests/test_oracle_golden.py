@@ -136,3 +136,73 @@ def test_gin_gat_step_matches_reference(drugbank, golden_dir):
         lid = k.split('.')[1]
         err = float(np.abs(v.grad.numpy().astype(np.float64) - z['grad/' + k]).max()) / scale[lid]
         assert err < (1e-4 if int(lid) < 5 else 5e-5), (k, err)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Third pinned configuration: the architecture the reference ships for DrugCombo (src/config.py:74-88,
+# 120-123): GIN x5 lower + 3 x MetaLayer (one GAT per interaction edge type, summed:
+# model/layers_meta.py:61-79) + 3-class MLP scorer + cross entropy, recorded from the reference's own code on
+# the DrugCombo subset the reference tree still holds (oracle/ref_loader.py:prepare_drugcombo_subset:
+# 1 621 drugs, synergy / antagonism interaction graphs).
+@pytest.fixture(scope='module')
+def drugcombo(golden_dir):
+    return O.PackedDataset.load(os.path.join(golden_dir, 'drugcombo_packed.npz'))
+
+
+def test_drugcombo_fixture_shape(drugcombo, golden_dir):
+    ds = drugcombo
+    assert ds.N == 1621 and list(ds.etypes) == ['0_synergy', '1_antagonism']       # GNNS[0] = synergy
+    z = np.load(os.path.join(golden_dir, 'bignn_drugcombo_step.npz'))
+    chunks = O.all_drug_chunks(ds.gids.tolist(), 64)
+    assert len(chunks) == int(z['n_chunks']) == 13
+    for c, pairs in enumerate(chunks):
+        assert np.array_equal(O.unique_graphs_in_order(pairs), z['chunk%d/gids' % c])
+    # labels: 1 = synergy, 2 = antagonism, 0 = sampled negative (utils/data/load_raw_data.py:66-70)
+    assert np.array_equal(O.pair_labels(ds, z['batch_gids']), z['y_true'])
+
+
+def test_drugcombo_negative_sampler_sequence_bit_exact(drugcombo, golden_dir):
+    s = np.load(os.path.join(golden_dir, 'bignn_drugcombo_sampler_seq.npz'))
+    np.random.set_state(('MT19937', s['np_state_keys'], int(s['np_state_pos']), 0, 0.0))
+    ds = drugcombo
+    edge_set = set(zip(ds.ddi_row.tolist(), ds.ddi_col.tolist()))
+    for pos, neg, y in zip([s['first_pos']] + list(s['pos']), [s['first_neg']] + list(s['neg']),
+                           [s['first_y']] + list(s['y'])):
+        got = O.sample_negative_pairs(ds, pos, np.unique(pos), edge_set)
+        assert np.array_equal(got, neg)
+        assert np.array_equal(O.pair_labels(ds, np.concatenate([pos, got])), y)
+
+
+def test_drugcombo_metalayer_step_matches_reference(drugcombo, golden_dir):
+    torch.set_num_threads(8)
+    z = np.load(os.path.join(golden_dir, 'bignn_drugcombo_step.npz'))
+    with open(os.path.join(golden_dir, 'bignn_drugcombo_layers.txt')) as f:
+        specs = O.parse_specs(f.read().splitlines())
+    sd = O.state_from_npz(z, 'sd0/')
+    for k in list(sd):
+        if ('sd_init/' + k) in z.files:
+            sd[k] = torch.from_numpy(np.asarray(z['sd_init/' + k])).clone()
+    model = O.OracleModel(specs, sd, gat_group='source')
+    init_x, acts, pred, loss = O.train_step_forward(model, drugcombo, z['batch_gids'], z['y_true'], 64)
+    loss.backward()
+    assert rel(init_x.detach().numpy(), z['init_x']) < 1e-6
+    assert rel(acts[0].detach().numpy(), z['upper/act2']) < 1e-6          # first MetaLayer
+    assert rel(acts[2].detach().numpy(), z['upper/act4']) < 2e-6          # third MetaLayer
+    assert rel(pred.detach().numpy(), z['upper/act5']) < 2e-6             # [128, 3] logits
+    assert abs(float(loss.detach()) - float(z['loss'])) < 1e-6
+    scale = {}
+    for k in z.files:
+        if k.startswith('grad/'):
+            scale[k.split('.')[1]] = max(scale.get(k.split('.')[1], 0.0), float(np.abs(z[k]).max()))
+    n = 0
+    for k, v in model.params().items():
+        if '.meta_layer.' in k:
+            # MetaLayerWrapper registers its node model twice (self.node_model and inside self.meta_layer,
+            # model/layers_meta.py:31-35): the state_dict carries both names, named_parameters() the first only
+            assert v.grad is None and np.array_equal(z['sd0/' + k], z['sd0/' + k.replace('.meta_layer.', '.')])
+            continue
+        lid = k.split('.')[1]
+        err = float(np.abs(v.grad.numpy().astype(np.float64) - z['grad/' + k]).max()) / scale[lid]
+        assert err < (1e-4 if int(lid) < 5 else 5e-5), (k, err)
+        n += 1
+    assert n == len([k for k in z.files if k.startswith('grad/')])
