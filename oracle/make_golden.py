@@ -92,7 +92,7 @@ def sd_to_np(sd):
     return {k: v.detach().cpu().numpy().copy() for k, v in sd.items() if k.startswith('layers.')}
 
 
-def run_step_golden(train_data, FLAGS, out_path, n_seq=24, light=False):
+def run_step_golden(train_data, FLAGS, out_path, n_seq=24, light=False, eval_pairs=None, eval_out=None):
     """One recorded train step (reference src/train.py:136-141) + sampler sequence."""
     import torch
     import train as T
@@ -206,6 +206,30 @@ def run_step_golden(train_data, FLAGS, out_path, n_seq=24, light=False):
             continue          # light fixture: first and last upper-level activations + scorer output (act1 = init_x)
         rec['upper/act%d' % li] = a
     rec.pop('upper_acts_n', None)
+    if eval_out is not None:
+        # --- evaluation path (reference src/train.py:185-220) right after the recorded step: model.eval(), the
+        # init_x of that step, one upper pass + scorer per 64-pair batch.  Written to its own file; the step and
+        # sampler fixtures are NOT rewritten in this mode (evaluate() consumes torch RNG for its shuffle).
+        eval_batches = []
+
+        def rec_eval_init(self, *a, **k):
+            orig_init(self, *a, **k)
+            if not self.ignore_pairs and not self.is_train:
+                eval_batches.append(self)
+        BatchData.__init__ = rec_eval_init
+        pl, eloss = T.evaluate(model, train_data, eval_pairs, None)
+        BatchData.__init__ = orig_init
+        Model.forward = orig_fwd
+        gids = np.concatenate([np.asarray(b.batch_gids, np.int64) for b in eval_batches])
+        preds = np.asarray([np.asarray(p.link_pred, np.float32).reshape(-1) for b in eval_batches for p in b.pair_list])
+        ys = np.asarray([p.true_label for b in eval_batches for p in b.pair_list], np.int64)
+        ev = dict(gids=gids, preds=preds, y_true=ys, mean_loss=np.float32(eloss),
+                  batch_sizes=np.asarray([len(b.pair_list) for b in eval_batches], np.int64), init_x=init_x)
+        for k, v in sd1.items():
+            ev['sd1/' + k] = v
+        np.savez_compressed(eval_out, **ev)
+        print('wrote', eval_out, 'pairs', gids.shape, 'mean loss', eloss)
+        return None
     np.savez_compressed(out_path, **rec)
     print('wrote', out_path, 'loss', loss.item(), 'chunks', len(chunks), 'init chunks', n_init_chunks)
 
@@ -246,12 +270,19 @@ def main():
     ap.add_argument('--dataset', default='drugbank', choices=['drugbank', 'drugcombo'])
     ap.add_argument('--n_seq', type=int, default=24)
     ap.add_argument('--light', action='store_true', help='smaller step fixture (no per-chunk indexing arrays)')
+    ap.add_argument('--eval_only', type=int, default=0,
+                    help='record the evaluation path on the first N validation pairs after the step -> <tag>_eval.npz '
+                         '(writes nothing else)')
     args = ap.parse_args()
     os.makedirs(args.out, exist_ok=True)
     ref_loader.load_reference(model=args.model, lower=args.lower, higher=args.higher, dataset=args.dataset)
     if args.dataset == 'drugcombo':
         ref_loader.patch_for_drugcombo()
     train_data, val_pairs, test_pairs, FLAGS = ref_loader.load_drugbank_fold(1)
+    if args.eval_only:
+        run_step_golden(train_data, FLAGS, None, eval_pairs=val_pairs[:args.eval_only],
+                        eval_out=os.path.join(args.out, args.tag + '_eval.npz'))
+        return
     if not args.skip_pack:
         packed = pack_dataset(train_data, val_pairs, test_pairs)
         np.savez_compressed(os.path.join(args.out, args.dataset + '_packed.npz'), **packed)

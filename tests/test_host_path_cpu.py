@@ -144,12 +144,11 @@ def test_negative_sampler_bit_exact_with_sorted_key_tables(cpu_world, golden_dir
         assert np.array_equal([p.true_label for p in bd.pair_list], y)
 
 
-def test_drugcombo_architecture_host_path_matches_reference_golden(golden_dir):
+def test_drugcombo_architecture_host_path_matches_reference_golden(cpu_world, golden_dir):
     """Host wiring of the DrugCombo architecture (layer specs, state_dict layout incl. the MetaLayer aliases, the
     per-edge-type upper level batched as one block-diagonal GAT, 3-class scorer, cross entropy) against vectors
     recorded from the reference's own code (tests/golden/bignn_drugcombo_step.npz); arithmetic = the torch-CPU
     stand-in of the C-ABI."""
-    fake_backend.install()
     try:
         z = np.load(os.path.join(golden_dir, 'bignn_drugcombo_step.npz'))
         with open(os.path.join(golden_dir, 'bignn_drugcombo_layers.txt')) as f:
@@ -198,5 +197,20 @@ def test_drugcombo_architecture_host_path_matches_reference_golden(golden_dir):
             if k.startswith('sd1/') and 'num_batches' in k:
                 assert int(sd[k[4:]]) == int(z[k])
     finally:
-        fake_backend.uninstall()
-        B.set_flags(None)
+        B.set_flags(B.make_flags(device='cpu'))
+
+
+def test_engine_score_pairs_matches_reference_evaluation(cpu_world, step_golden, golden_dir):
+    """BiGNNEngine.score_pairs (one upper pass + ONE scorer launch over all pairs) against the reference's own
+    `evaluate` output for 512 validation pairs (tests/golden/bignn_gin_gcn_eval.npz)."""
+    from bignn_b200.engine import BiGNNEngine
+    z, e = step_golden, np.load(os.path.join(golden_dir, 'bignn_gin_gcn_eval.npz'))
+    data = cpu_world
+    model = B.Model(data)
+    load_state(model, z, 'sd1/')
+    model.train()
+    eng = BiGNNEngine(data, model, use_cuda_graph=False)
+    data.interaction_combo_nxgraph.init_x = torch.from_numpy(z['init_x'])
+    got = eng.score_pairs(e['gids'], recompute_init_x=False)
+    assert got.shape == (512, 1) and model.training
+    assert rel(got.detach().numpy().reshape(-1), e['preds'].reshape(-1)) < 1e-5

@@ -206,3 +206,26 @@ def test_drugcombo_metalayer_step_matches_reference(drugcombo, golden_dir):
         assert err < (1e-4 if int(lid) < 5 else 5e-5), (k, err)
         n += 1
     assert n == len([k for k in z.files if k.startswith('grad/')])
+
+
+def test_evaluation_path_matches_reference(drugbank, step_golden, gin_gcn_specs, golden_dir):
+    """src/train.py:185-220 `evaluate` right after the recorded step (oracle/make_golden.py --eval_only): model.eval()
+    (running-statistics BatchNorm upstairs), the step's init_x, 64-pair batches of validation pairs."""
+    torch.set_num_threads(8)
+    z, e = step_golden, np.load(os.path.join(golden_dir, 'bignn_gin_gcn_eval.npz'))
+    model = O.OracleModel(gin_gcn_specs, O.state_from_npz(z, 'sd1/'))
+    model.training = False
+    ddi = torch.from_numpy(np.stack([drugbank.ddi_row, drugbank.ddi_col]))
+    init_x = torch.from_numpy(z['init_x'])
+    rows = torch.from_numpy(np.vectorize(drugbank.gs_map.get)(e['gids']).astype(np.int64))
+    y = torch.from_numpy(e['y_true'])
+    losses, off = [], 0
+    with torch.no_grad():
+        for n in e['batch_sizes'].tolist():
+            _, pred, loss = model.upper(init_x, ddi, rows[off:off + n], y[off:off + n])
+            assert rel(pred.numpy().reshape(-1), e['preds'][off:off + n].reshape(-1)) < 1e-6
+            losses.append(float(loss))
+            off += n
+    assert abs(np.mean(losses) - float(e['mean_loss'])) < 1e-6
+    # labels of the validation pairs: positives and the pre-drawn validation negatives (label 0)
+    assert np.array_equal(O.pair_labels(drugbank, e['gids']), e['y_true'])
