@@ -10,11 +10,11 @@ from .config import make_flags, set_flags, get_flags
 from .dataset import BiGNNData
 from .graph import PackedGraphs, MergedGraph, InteractionGraph
 from .batch import BatchData, sample_negative_pairs
-from .sampler import RandomSampler
+from .sampler import RandomSampler, EverythingSampler, NeighborSampler
 from .layers_factory import create_layers, layer_ctors
 from .model import Model
 from . import ops, train
 
 __all__ = ['make_flags', 'set_flags', 'get_flags', 'BiGNNData', 'PackedGraphs', 'MergedGraph',
-           'InteractionGraph', 'BatchData', 'sample_negative_pairs', 'RandomSampler', 'create_layers',
+           'InteractionGraph', 'BatchData', 'sample_negative_pairs', 'RandomSampler', 'EverythingSampler', 'NeighborSampler', 'create_layers',
            'layer_ctors', 'Model', 'ops', 'train']

@@ -214,3 +214,34 @@ def test_engine_score_pairs_matches_reference_evaluation(cpu_world, step_golden,
     got = eng.score_pairs(e['gids'], recompute_init_x=False)
     assert got.shape == (512, 1) and model.training
     assert rel(got.detach().numpy().reshape(-1), e['preds'].reshape(-1)) < 1e-5
+
+
+def test_neighbor_and_everything_samplers_bit_exact(cpu_world, golden_dir):
+    """src/sampler.py:51-107 against the reference's own run (oracle/make_golden_samplers.py): sampled drugs and
+    induced pairs, order included, for six consecutive batches; the visit counter; EverythingSampler's batch."""
+    import random
+    z = np.load(os.path.join(golden_dir, 'bignn_samplers.npz'))
+    random.seed(8); np.random.seed(8); torch.manual_seed(8)                 # utils/util.py:384-392 set_seed(8)
+    s = B.NeighborSampler(cpu_world, 5, 64)
+    for i in range(6):
+        bg, sg, sub = s.sample_next_training_batch()
+        assert len(sg) == 64
+        assert np.array_equal(np.asarray(sg), z['sampled_gids/%d' % i])
+        assert np.array_equal(bg, z['batch_gids/%d' % i])
+        assert np.array_equal(sub.nodes, z['sub_nodes/%d' % i])
+        # every sampled pair is a train edge between two sampled drugs, and no such edge is missing
+        rows = set(cpu_world.gs_map[g] for g in sg)
+        es = cpu_world.edge_set()
+        assert all((cpu_world.gs_map[a], cpu_world.gs_map[b]) in es for a, b in bg.tolist())
+        assert len(bg) == sum(1 for (a, b) in es if a < b and a in rows and b in rows)
+    assert np.array_equal(s.nodes_visited_counter, z['visited_counter'])
+    random.seed(8); np.random.seed(8); torch.manual_seed(8)
+    e = B.EverythingSampler(cpu_world)
+    bg, sg, none = e.sample_next_training_batch()
+    assert none is None and len(bg) == int(z['everything/n']) == len(cpu_world.train_pairs)
+    assert len(sg) == int(z['everything/sampled_n'])
+    assert np.array_equal(bg[:256], z['everything/batch_gids_head'])
+    # a fractional neighbour budget (src/sampler.py:83-84)
+    s2 = B.NeighborSampler(cpu_world, 0.5, 32)
+    bg, sg, _ = s2.sample_next_training_batch()
+    assert len(sg) == 32 and bg.shape[1] == 2
