@@ -135,6 +135,7 @@ class BiGNNEngine(object):
         agg = model.lower_layers[-1]
         self._agg_style, self._multi = agg.style, agg.concat_multi_scale
         self._graphs = {}          # P -> (graph, static batch, loss tensor)
+        self.max_graphs = 8
         self._stagings = {}
         self._n_staging = n_staging
         self._step_idx = 0
@@ -261,6 +262,11 @@ class BiGNNEngine(object):
     def _staging(self, P):
         key = P
         if key not in self._stagings:
+            if len(self._stagings) >= 16:                  # varying batch sizes: keep the pinned pool bounded
+                old = next(iter(self._stagings))
+                for s_ in self._stagings.pop(old):
+                    if s_.busy and s_.event is not None:
+                        s_.event.synchronize()
             self._stagings[key] = [_Staging(P, self._n_pair_rows, self.device.type == 'cuda')
                                    for _ in range(self._n_staging)]
         st = self._stagings[key][self._step_idx % self._n_staging]
@@ -295,18 +301,24 @@ class BiGNNEngine(object):
     def step_staged(self, st, P):
         """Runs one train step on staged inputs; returns the staging slot whose `.loss`
         holds the loss once `.event` has completed (read it with `read_loss`)."""
-        if self.use_cuda_graph:
+        # one captured graph per pair-batch size; samplers with a varying batch (NeighborSampler, the short last
+        # batch of an epoch) get at most `max_graphs` of them, further sizes run as eager launches
+        use_graph = self.use_cuda_graph and (
+            P in self._graphs or sum(1 for k in self._graphs if isinstance(k, int)) < self.max_graphs)
+        if use_graph:
             entry = self._graphs.get(P) or self._capture(P)
             g, sb, loss = entry
         else:
             sb = self._graphs.get(('eager', P))
             if sb is None:
+                for k in [k for k in self._graphs if isinstance(k, tuple)]:
+                    del self._graphs[k]                    # keep one eager batch
                 sb = self._graphs[('eager', P)] = _StaticPairBatch(self.data, P, self.device, self.upper)
         sb.ids.copy_(st.ids, non_blocking=True)
         sb.y.copy_(st.y, non_blocking=True)
         sb.e_ptr.copy_(st.e_ptr, non_blocking=True)
         sb.e_idx.copy_(st.e_idx, non_blocking=True)
-        if self.use_cuda_graph:
+        if use_graph:
             g.replay()
         else:
             loss = self._device_step(sb)
