@@ -294,8 +294,6 @@ def run_ours(args):
         st = eng.train_step(sampler)
     eng.read_loss(st)
     l0 = B._lib.launch_count()
-    eager_probe = BiGNNEngine(data, model, optimizer=eng.optimizer, use_cuda_graph=False) if False else None
-    del eager_probe
 
     clocks = ClockSampler(local)
     clocks.start()
