@@ -101,21 +101,22 @@ def all_reduce_grads(params, group=None):
     flat = torch.cat([g.reshape(-1) for g in grads])
     with _timed('grad_all_reduce'):
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    off = 0
+    views, off = [], 0
     for g in grads:
         n = g.numel()
-        g.copy_(flat[off:off + n].view_as(g))
+        views.append(flat[off:off + n].view_as(g))
         off += n
+    torch._foreach_copy_(grads, views)               # one multi-tensor launch instead of one copy per gradient
 
 
 def gather_chunk_stats(stats_local, s_max, group=None):
-    """all-gather of per-chunk BatchNorm statistics [2, S_local, C] (padded to s_max chunks)
-    -> [world, 2, s_max, C]."""
+    """all-gather of per-chunk BatchNorm statistics [K, S_local, C] (K = 2 per layer; padded to s_max chunks)
+    -> [world, K, s_max, C]."""
     world = dist.get_world_size(group)
-    two, s_loc, C = stats_local.shape
-    pad = torch.zeros((2, s_max, C), dtype=stats_local.dtype, device=stats_local.device)
+    K, s_loc, C = stats_local.shape
+    pad = torch.zeros((K, s_max, C), dtype=stats_local.dtype, device=stats_local.device)
     pad[:, :s_loc] = stats_local
-    out = torch.empty((world, 2, s_max, C), dtype=stats_local.dtype, device=stats_local.device)
+    out = torch.empty((world, K, s_max, C), dtype=stats_local.dtype, device=stats_local.device)
     with _timed('bn_chunk_stats_all_gather'):
         dist.all_gather_into_tensor(out.view(-1), pad.view(-1), group=group)
     return out

@@ -179,12 +179,20 @@ class BiGNNEngine(object):
         # + the conv weights / biases of a row-partitioned upper level (partial sums over a rank's rows)
         bdist.all_reduce_grads(lower + self._upper_partial, self.group)
         s_max = max(hi - lo for lo, hi in self.chunk_shards)
-        for bn, stats in self._bn_sink:
-            allst = bdist.gather_chunk_stats(stats, s_max, self.group)       # [world, 2, s_max, C]
-            parts = [allst[r][:, :hi - lo] for r, (lo, hi) in enumerate(self.chunk_shards)]
-            ordered = torch.cat(parts, dim=1).contiguous()                   # [2, S_total, C]
-            ops.bn_running_update(ordered, self._all_chunk_ptr, self.n_chunks_total, bn.running_mean,
-                                  bn.running_var, bn.num_batches_tracked, bn.momentum)
+        if self._bn_sink:
+            # the per-chunk statistics of ALL BatchNorm layers travel in one all-gather
+            widths = [st.shape[2] for _, st in self._bn_sink]
+            if len(set(widths)) == 1:
+                stacked = torch.cat([st for _, st in self._bn_sink], dim=0)              # [2L, S_local, C]
+                allst = bdist.gather_chunk_stats(stacked, s_max, self.group)             # [world, 2L, s_max, C]
+                per_layer = [allst[:, 2 * l:2 * l + 2] for l in range(len(self._bn_sink))]
+            else:
+                per_layer = [bdist.gather_chunk_stats(st, s_max, self.group) for _, st in self._bn_sink]
+            for (bn, _), allst in zip(self._bn_sink, per_layer):
+                parts = [allst[r][:, :hi - lo] for r, (lo, hi) in enumerate(self.chunk_shards)]
+                ordered = torch.cat(parts, dim=1).contiguous()                           # [2, S_total, C]
+                ops.bn_running_update(ordered, self._all_chunk_ptr, self.n_chunks_total, bn.running_mean,
+                                      bn.running_var, bn.num_batches_tracked, bn.momentum)
         del self._bn_sink[:]
 
     def _device_step(self, pair_batch):
