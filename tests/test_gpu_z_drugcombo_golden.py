@@ -2,10 +2,10 @@
 GAT per interaction edge type, summed: model/layers_meta.py:61-79), 3-class MLP scorer, cross entropy -- on the GPU
 against vectors recorded from the REFERENCE'S OWN CODE on the DrugCombo subset its tree still holds
 (tests/golden/bignn_drugcombo_step.npz, oracle/make_golden.py --dataset drugcombo; 1 621 drugs, synergy and
-antagonism interaction graphs).  Same gates as tests/test_gpu_step.py: forward 1e-5 (2e-5 behind three GAT layers),
-gradients no further from the fp64 oracle than 6x the reference's own fp32 gradients are (+2e-5).
-(The file sorts last on purpose: it was added after the round's GPU budget was spent and runs for the first time in
-the round-end suite; nothing that follows it can be masked by `-x`.)"""
+antagonism interaction graphs).  Same gates as tests/test_gpu_step.py: forward 1e-5, gradients no further from the
+fp64 oracle than 6x the reference's own fp32 gradients are (+2e-5).
+Measured on B200 (profiles/r1b_golden_gpu.log): init_x 6.9e-6, MetaLayer activations 3.0e-6, logits 4.6e-6, loss
+equal to 7 digits."""
 import os
 
 import numpy as np
@@ -68,17 +68,11 @@ def test_drugcombo_step_vs_reference_golden(golden_dir, golden):
         acts = model.acts                   # [None, LoadInteraction, MetaLayer x3, LinkPred, Loss]
         errs = dict(init_x=rel(data.interaction_combo_nxgraph.init_x, z['init_x']), act2=rel(acts[2], z['upper/act2']),
                     act4=rel(acts[4], z['upper/act4']), logits=rel(sb.preds, z['upper/act5']),
-                    loss=abs(float(loss) - float(z['loss'])))
+                    loss=abs(float(loss.detach()) - float(z['loss'])))
         print('drugcombo golden, forward errors:', {k: float('%.3g' % v) for k, v in errs.items()})
-        # the path's forward bar is 1e-5 (met with 1.8e-6 on the DrugBank golden); this fixture is compared on the
-        # GPU for the first time at round end, so the hard gate is 2e-5 and anything above 1e-5 is reported
-        if max(errs['init_x'], errs['loss']) > 1e-5:
-            import warnings
-            warnings.warn('drugcombo golden: forward error above 1e-5: {}'.format(errs))
-        assert errs['init_x'] < 2e-5
-        assert errs['act2'] < 2e-5 and errs['act4'] < 2e-5
-        assert errs['logits'] < 5e-5          # [128, 3] logits
-        assert errs['loss'] < 2e-5
+        assert errs['init_x'] < 1e-5 and errs['act2'] < 1e-5 and errs['act4'] < 1e-5
+        assert errs['logits'] < 1e-5          # [128, 3] logits
+        assert errs['loss'] < 1e-5
         # gradients: fp64 ground truth from the oracle (itself pinned to this golden, tests/test_oracle_golden.py)
         ds = O.PackedDataset.load(os.path.join(golden_dir, 'drugcombo_packed.npz'))
         om = O.OracleModel(O.parse_specs(lines), O.state_from_npz(z, 'sd0/'), dtype=torch.float64, gat_group='source')
@@ -115,8 +109,8 @@ def test_drugcombo_reference_sequenced_path_and_bn_buffers(golden_dir, golden):
         bd.batch_interaction_inds = [data.gs_map[g] for g in bd.batch_gids.flatten().tolist()]
         model.use_layers = 'higher_layers'
         loss = model(bd)
-        assert abs(float(loss) - float(z['loss'])) < 2e-5
-        assert rel(data.interaction_combo_nxgraph.init_x, z['init_x']) < 2e-5
+        assert abs(float(loss.detach()) - float(z['loss'])) < 1e-5
+        assert rel(data.interaction_combo_nxgraph.init_x, z['init_x']) < 1e-5
         sdm = model.state_dict()
         for k in z.files:
             if k.startswith('sd1/') and 'running' in k:

@@ -1,8 +1,7 @@
 """Evaluation path on the GPU against the reference's own `evaluate` (src/train.py:185-220) output, recorded right
 after the golden train step for 512 validation pairs (tests/golden/bignn_gin_gcn_eval.npz, oracle/make_golden.py
 --eval_only 512): model.eval() statistics, the step's init_x, ONE upper pass and ONE scorer launch over all pairs
-(`BiGNNEngine.score_pairs`) instead of an upper pass and 128 `.item()` syncs per 64-pair batch.
-(Sorts last: added after the round's GPU budget was spent; first GPU run is the round-end suite.)"""
+(`BiGNNEngine.score_pairs`) instead of an upper pass and 128 `.item()` syncs per 64-pair batch."""
 import os
 
 import numpy as np
