@@ -61,3 +61,40 @@ def test_chunk_schedule_small_cases():
     assert O.unique_graphs_in_order(ch[1]) == [4, 5, 6]              # 5 appears twice, merged once
     ch = O.all_drug_chunks(list(range(6)), 64)         # 2*bs >= #pairs: chunk = #pairs // 2 = 1 pair
     assert [len(c) for c in ch] == [1, 1, 1]
+
+
+def test_smallest_and_largest_molecule_of_drugbank(drugbank):
+    """the smallest usable molecule (2 atoms, 1 bond) and the 457-atom maximum, through the oracle's
+    merge and the host-side MergedGraph (CPU stand-in backend): indexing by hand for the former, consistency
+    properties for the latter."""
+    import bignn_b200 as B
+    from tests import fake_backend
+    ds = drugbank
+    sizes = np.diff(ds.atom_ptr)
+    small, big = int(np.argmin(sizes)), int(np.argmax(sizes))
+    assert sizes[small] == 2 and sizes[big] == 457
+    m = O.merge_graphs(ds, [int(ds.gids[small]), int(ds.gids[big])])
+    # graph 0: atoms 0,1 joined by one bond -> directed entries (0,1),(1,0); graph 1 starts at node 2
+    assert m['edge_index'][:, :2].tolist() == [[0, 1], [1, 0]]
+    assert m['ind_list'].tolist() == [[0, 2], [2, 459]] and m['edge_ind_list'][0].tolist() == [0, 2]
+    assert m['batch'].tolist() == [0, 0] + [1] * 457
+    ei = m['edge_index'][:, 2:]
+    assert ei.min() == 2 and ei.max() == 458                                   # offset by the first graph's atoms
+    key = ei[0].astype(np.int64) * 459 + ei[1]
+    assert np.all(np.diff(key) > 0)                                            # sorted, no duplicates
+    assert set(map(tuple, ei.T.tolist())) == set(map(tuple, ei[::-1].T.tolist()))   # symmetric
+    assert np.all(m['x'].sum(1) == 6) and set(np.unique(m['x'])) <= {0.0, 1.0}       # six one-hot groups per atom
+    fake_backend.install()
+    try:
+        B.set_flags(B.make_flags(device='cpu'))
+        import os
+        from tests.conftest import GOLDEN
+        data = B.BiGNNData.from_npz(os.path.join(GOLDEN, 'drugbank_packed.npz'), device='cpu')
+        g = B.MergedGraph(data.packed, [small, big])
+        assert np.array_equal(g.edge_index.numpy(), m['edge_index'].astype(np.int64))
+        assert np.array_equal(g.batch.numpy(), m['batch'].astype(np.int64))
+        assert np.array_equal(g.x.numpy(), m['x'])
+        assert g.seg_ptr.tolist() == [0, 2, 459] and g.row_ptr[:3].tolist() == [0, 1, 2]
+    finally:
+        fake_backend.uninstall()
+        B.set_flags(None)
