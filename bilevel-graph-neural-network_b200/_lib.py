@@ -20,6 +20,8 @@ LIB_DIR = os.path.join(HERE, '_C')
 LIB_PATH = os.path.join(LIB_DIR, 'libbignn_b200.so')
 HEADER = os.path.join(ROOT, 'include', 'bignn_b200.h')
 
+ABI_VERSION = 2          # include/bignn_b200.h BIGNN_ABI_VERSION (2: bn_seg_bwd input_act, spmm_planned_rows n_big)
+
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC']
 
@@ -138,8 +140,9 @@ def load():
             fn = getattr(lib, name)        # AttributeError if the symbol is not exported
             fn.restype = _CT[res]
             fn.argtypes = [_CT[c] for c in args]
-        if lib.bignn_abi_version() != 1:
-            raise ImportError('bignn_b200: ABI version mismatch')
+        if lib.bignn_abi_version() != ABI_VERSION:
+            raise ImportError('bignn_b200: ABI version mismatch (library {}, binding {}): rebuild with '
+                              '__graft_entry__.build()'.format(lib.bignn_abi_version(), ABI_VERSION))
         _lib = lib
     return _lib
 

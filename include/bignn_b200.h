@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define BIGNN_ABI_VERSION 1
+#define BIGNN_ABI_VERSION 2
 
 /* argument errors */
 #define BIGNN_EINVAL   (-1)   /* bad size / null pointer / unsupported flag */
