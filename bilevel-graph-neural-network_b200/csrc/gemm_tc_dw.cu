@@ -205,6 +205,185 @@ k_dw_tc(int M, int Np, int Nq, const float* __restrict__ P, int64_t ldp, const f
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Ring variant (BIGNN_DW_BM=32 selects it; NOT the default -- written after the round's GPU budget was spent, to be
+// measured first): ncu on k_dw_tc<64,3> shows no dominant stall, 23 % tensor-pipe activity and one 32 KB tile in flight
+// per CTA, i.e. the kernel waits for data.  Here the operand tiles are 32-row stages in an NST-deep cp.async ring
+// (NST-2 tiles in flight beyond the one being split) and the lo operand is double buffered, so the hi/lo split of
+// tile i+1 overlaps the MMAs of tile i (one mbarrier per lo buffer; a stage is refilled only after the MMAs that
+// read it have committed).  96 KB of shared memory and 256 TMEM columns per CTA -> two CTAs per SM.
+template <int BM, int NST, int DW_NA>
+__global__ void __launch_bounds__(TC_THREADS, 2)
+k_dw_tc_ring(int M, int Np, int Nq, const float* __restrict__ P, int64_t ldp, const float* __restrict__ Q, int64_t ldq,
+             int colsum_of, float* __restrict__ ws_dw, double* __restrict__ ws_cs) {
+  constexpr int DW_BLK = BM * 128;
+  constexpr int DW_TILE = 2 * DW_BLK;
+  constexpr int STAGE = 2 * DW_TILE;               // [P][Q]
+  constexpr int NCHUNK = 4 * BM * 8;
+  constexpr int LOG_OP = (BM == 32 ? 9 : (BM == 64 ? 10 : 11));
+  static_assert((DW_NA + 1) * DW_F <= 256 && NST >= 3, "two CTAs per SM");
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* lo_base = smem + NST * STAGE;           // two lo buffers of STAGE bytes
+  __shared__ uint64_t mma_bar[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ double cs_red[4][DW_F];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_tiles = (M + BM - 1) / BM;
+  const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  constexpr int TMEM_COLS = 256;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 32) {
+    mbar_init(&mma_bar[0], 1);
+    mbar_init(&mma_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  const uint32_t smem_s = smem_u32(smem);
+  auto prefetch_tile = [&](int i, int stage) {       // i = this CTA's tile index
+    const int m0 = ((int)blockIdx.x + i * (int)gridDim.x) * BM;
+    const uint32_t hi_s = smem_s + stage * STAGE;
+#pragma unroll 1
+    for (int j = tid; j < NCHUNK; j += TC_THREADS) {
+      const int op = j >> LOG_OP, idx = j & ((1 << LOG_OP) - 1);
+      const int blk = idx >> (LOG_OP - 1), r = (idx & ((1 << (LOG_OP - 1)) - 1)) >> 3, c = idx & 7;
+      const int gm = m0 + r, gf = blk * 32 + c * 4;
+      const int nf = op ? Nq : Np;
+      const bool ok = gm < M && gf < nf;
+      const float* base = op ? Q + (int64_t)gm * ldq : P + (int64_t)gm * ldp;
+      cp_async16(hi_s + op * DW_TILE + blk * DW_BLK + sw32b_off(r, c), ok ? base + gf : (op ? Q : P), ok ? 16u : 0u);
+    }
+  };
+  // prologue: tiles 0 .. NST-3 in flight, one commit group per tile (empty groups keep the count uniform)
+#pragma unroll
+  for (int j = 0; j < NST - 2; ++j) {
+    if (j < my_tiles) prefetch_tile(j, j);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = tmem_base_s;
+  const uint32_t idesc = umma_idesc_tf32_mn(DW_MMA_M, DW_F);
+
+  double cs = 0.0;
+  const int cs_col = tid & 63, cs_rg = tid >> 6;
+  uint32_t ph0 = 0, ph1 = 0;
+  int ks = 0;
+  for (int i = 0; i < my_tiles; ++i) {
+    const int stage = i % NST, lb = i & 1;
+    uint8_t* p_hi = smem + stage * STAGE;
+    uint8_t* p_lo = lo_base + lb * STAGE;
+    // groups committed so far: (NST-2) + i; tile i is group i -> at most NST-3 newer groups may be pending
+    asm volatile("cp.async.wait_group %0;" ::"n"(NST - 3) : "memory");
+    if (i >= 2) {                                      // MMAs of tile i-2: they read lo[lb] and stage (i-2) % NST
+      if (lb == 0) { mbar_wait(&mma_bar[0], ph0); ph0 ^= 1; } else { mbar_wait(&mma_bar[1], ph1); ph1 ^= 1; }
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    if (i + NST - 2 < my_tiles) prefetch_tile(i + NST - 2, (i + NST - 2) % NST);     // = the stage of tile i-2
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    // ---- lo = tf32(x - hi(x)) for the chunks this thread copied
+#pragma unroll 4
+    for (int j = tid; j < NCHUNK; j += TC_THREADS) {
+      const int op = j >> LOG_OP, idx = j & ((1 << LOG_OP) - 1);
+      const uint32_t off = op * DW_TILE + (idx >> (LOG_OP - 1)) * DW_BLK +
+                           sw32b_off((idx & ((1 << (LOG_OP - 1)) - 1)) >> 3, idx & 7);
+      const float4 x = *reinterpret_cast<const float4*>(p_hi + off);
+      uint4 l;
+      l.x = __float_as_uint(x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u)) & 0xffffe000u;
+      l.y = __float_as_uint(x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u)) & 0xffffe000u;
+      l.z = __float_as_uint(x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u)) & 0xffffe000u;
+      l.w = __float_as_uint(x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u)) & 0xffffe000u;
+      *reinterpret_cast<uint4*>(p_lo + off) = l;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint64_t dp_hi = umma_desc_mn_sw128(smem_u32(p_hi), DW_BLK), dp_lo = umma_desc_mn_sw128(smem_u32(p_lo), DW_BLK);
+      const uint64_t dq_hi = umma_desc_mn_sw128(smem_u32(p_hi + DW_TILE), DW_BLK),
+                     dq_lo = umma_desc_mn_sw128(smem_u32(p_lo + DW_TILE), DW_BLK);
+#pragma unroll 1
+      for (int k = 0; k < BM / 8; ++k, ++ks) {
+        const uint64_t adv = (uint64_t)((k * 1024) >> 4);
+        umma_tf32(tmem_d + (uint32_t)((ks % DW_NA) * DW_F), dp_hi + adv, dq_hi + adv, idesc, ks >= DW_NA ? 1u : 0u);
+        umma_tf32(tmem_d + (uint32_t)(DW_NA * DW_F), dp_lo + adv, dq_hi + adv, idesc, ks > 0 ? 1u : 0u);
+        umma_tf32(tmem_d + (uint32_t)(DW_NA * DW_F), dp_hi + adv, dq_lo + adv, idesc, 1u);
+      }
+      umma_commit(lb == 0 ? &mma_bar[0] : &mma_bar[1]);
+    } else if (tid >= 32) {
+      ks += BM / 8;
+    }
+    if (colsum_of >= 0) {                              // from the raw tile, while the tensor core runs
+      const uint8_t* t0 = p_hi + (colsum_of ? DW_TILE : 0) + (cs_col >> 5) * DW_BLK;
+      const int c = (cs_col & 31) >> 2, e = cs_col & 3;
+      float s = 0.f;
+#pragma unroll 4
+      for (int r = cs_rg; r < BM; r += 4) s += *reinterpret_cast<const float*>(t0 + sw32b_off(r, c) + e * 4);
+      cs += (double)s;
+    }
+  }
+  // drain: the MMAs of the last two tiles
+  for (int i = (my_tiles >= 2 ? my_tiles - 2 : 0); i < my_tiles; ++i) {
+    if ((i & 1) == 0) { mbar_wait(&mma_bar[0], ph0); ph0 ^= 1; } else { mbar_wait(&mma_bar[1], ph1); ph1 ^= 1; }
+  }
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  __syncthreads();
+  ks = __shfl_sync(0xffffffffu, ks, 0);
+  const int n_steps = my_tiles * (BM / 8);
+  {
+    const int q = warp & 3;
+    if (q < 2) {
+      const int row = q * 32 + lane;
+#pragma unroll 1
+      for (int cb = (warp >> 2) * 32; cb < DW_F; cb += 64) {
+        uint32_t r[32];
+        float v[32];
+        const uint32_t tbase = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)cb;
+        if (n_steps > 0) {
+          tmem_ld32(tbase + (uint32_t)(DW_NA * DW_F), r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+#pragma unroll 1
+        for (int a = 0; a < DW_NA; ++a) {
+          if (a >= n_steps) break;
+          tmem_ld32(tbase + (uint32_t)(a * DW_F), r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __fadd_rn(__uint_as_float(r[j]), v[j]);
+        }
+        if (row < Np) {
+          float* dst = ws_dw + ((int64_t)blockIdx.x * Np + row) * Nq;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (cb + j < Nq) dst[cb + j] = v[j];
+        }
+      }
+    }
+  }
+  if (colsum_of >= 0) {
+    cs_red[cs_rg][cs_col] = cs;
+    __syncthreads();
+    const int ncs = colsum_of ? Nq : Np;
+    if (tid < ncs) ws_cs[(int64_t)blockIdx.x * ncs + tid] = ((cs_red[0][tid] + cs_red[1][tid]) + cs_red[2][tid]) + cs_red[3][tid];
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 // fixed-order sums over the per-CTA partials
 __global__ void __launch_bounds__(256)
 k_dw_reduce(const float* __restrict__ ws_dw, int parts, int total, float* __restrict__ out) {
@@ -246,11 +425,12 @@ k_dw_cs_reduce(const double* __restrict__ ws, int parts, int cols, float* __rest
   }
 }
 
-static int dw_bm() {                 // rows per tile: 64 (two CTAs per SM, default) or 128 (BIGNN_DW_BM=128)
+static int dw_bm() {   // rows per tile: 64 (two CTAs per SM, default), 128 (BIGNN_DW_BM=128) or the 32-row ring (=32)
   static int bm = 0;
   if (bm == 0) {
     const char* e = getenv("BIGNN_DW_BM");
-    bm = (e && atoi(e) == 128) ? 128 : 64;
+    const int v = e ? atoi(e) : 64;
+    bm = (v == 128 || v == 32) ? v : 64;
   }
   return bm;
 }
@@ -258,7 +438,7 @@ static int dw_bm() {                 // rows per tile: 64 (two CTAs per SM, defa
 static int dw_grid(int M) {
   const int bm = dw_bm();
   const int n_tiles = ceil_div(M, bm);
-  int g = sm_count() * (bm == 64 ? 2 : 1);
+  int g = sm_count() * (bm == 128 ? 1 : 2);
   return g > n_tiles ? n_tiles : g;
 }
 
@@ -293,10 +473,14 @@ extern "C" int bignn_dw_tc_f32(int32_t M, int32_t Np, int32_t Nq, const float* P
     cudaError_t e = cudaFuncSetAttribute(k_dw_tc<64, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * 2 * 64 * 128 + 1024);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(k_dw_tc<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * 2 * 128 * 128 + 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(k_dw_tc_ring<32, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * 4 * 32 * 128 + 1024);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  if (dw_bm() == 64)
+  if (dw_bm() == 32)
+    k_dw_tc_ring<32, 4, 3><<<grid, TC_THREADS, 6 * 4 * 32 * 128 + 1024, st>>>(M, Np, Nq, P, ldp, Q, ldq, colsum_of < 0 ? -1 : colsum_of, ws_dw, ws_cs);
+  else if (dw_bm() == 64)
     k_dw_tc<64, 3><<<grid, TC_THREADS, 6 * 2 * 64 * 128 + 1024, st>>>(M, Np, Nq, P, ldp, Q, ldq, colsum_of < 0 ? -1 : colsum_of, ws_dw, ws_cs);
   else
     k_dw_tc<128, 4><<<grid, TC_THREADS, 6 * 2 * 128 * 128 + 1024, st>>>(M, Np, Nq, P, ldp, Q, ldq, colsum_of < 0 ? -1 : colsum_of, ws_dw, ws_cs);

@@ -16,3 +16,8 @@ timeout 240 python bench.py --workload ddi_scaled --steps 5 --warmup 3 --skip-cp
 echo "c4 exit $?"; cut -c1-220 gpurun_out/bench_c4_n1_$tag.json
 timeout 60 python profiles/r1b_probe.py > gpurun_out/probe_$tag.log 2>&1; head -6 gpurun_out/probe_$tag.log
 timeout 90 python profiles/spmm_hub_probe.py 200000 8000000 > gpurun_out/hub_probe_$tag.log 2>&1; tail -2 gpurun_out/hub_probe_$tag.log
+# candidate kernels that are NOT the default yet (written without GPU access at the end of round 1):
+#   BIGNN_DW_BM=32  -> k_dw_tc_ring<32,4,3> (4-stage cp.async ring, double-buffered lo operand)
+BIGNN_DW_BM=32 timeout 120 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_fused_bwd.py -k "weight_gradient or linear_act or gin_mlp" -x -q \
+    > gpurun_out/pytest_dwring_$tag.log 2>&1; echo "dw ring pytest exit $?"; tail -2 gpurun_out/pytest_dwring_$tag.log
+BIGNN_DW_BM=32 timeout 60 python profiles/r1b_probe.py 2>&1 | head -1 | sed 's/^/ring: /'
