@@ -98,3 +98,19 @@ def test_smallest_and_largest_molecule_of_drugbank(drugbank):
     finally:
         fake_backend.uninstall()
         B.set_flags(None)
+
+
+def test_row_plan_items_and_hub_rows():
+    """work-item plan of a skewed CSR (ops.RowPlan): ceil(deg/seg) items per row (>= 1), multi-item rows listed with
+    the hub rows (> BIG_ITEMS items) LAST, as bignn_spmm_planned_rows_f32 expects."""
+    from bignn_b200 import ops
+    deg = np.asarray([0, 1, 32, 33, 64, 65, 5000, 31, 2049, 2048])
+    ptr = np.concatenate([[0], np.cumsum(deg)])
+    pl = ops.RowPlan(ptr, 'cpu', seg=32)
+    items = np.maximum(1, -(-deg // 32))
+    assert pl.n_items == int(items.sum()) and pl.item_ptr.tolist() == np.concatenate([[0], np.cumsum(items)]).tolist()
+    assert pl.item_row.tolist() == np.repeat(np.arange(10), items).tolist()
+    multi = pl.multi_rows.tolist()
+    assert sorted(multi) == [3, 4, 5, 6, 8, 9] and pl.n_multi == 6
+    assert pl.n_big == 2 and multi[-2:] == [6, 8]            # 157 and 65 items; row 9 has exactly 64 = not a hub
+    assert multi[:4] == [3, 4, 5, 9]                          # the others in ascending order
