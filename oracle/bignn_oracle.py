@@ -536,7 +536,8 @@ class OracleModel(object):
     def upper(self, init_x, ddi_ei, pair_rows, y, num_labels=2, etype_eis=None):
         h = init_x
         acts = []
-        start = self.i_load + 1 if self.i_load is not None else 0
+        # after LoadInteractionLayer (bi-level), else after the readout (lower-level-only model), else everything
+        start = self.i_load + 1 if self.i_load is not None else (self.i_agg + 1 if self.i_agg is not None else 0)
         pred = None
         for i in range(start, len(self.specs)):
             name, lf = self.specs[i]
@@ -582,6 +583,21 @@ def train_step_forward(model, ds, batch_gids, y, batch_size=64, record=None):
     et = [torch.from_numpy(np.stack([r, c])) for r, c in ds.etypes.values()] if ds.etypes else None
     acts, pred, loss = model.upper(init_x, ddi, rows, torch.from_numpy(np.asarray(y)), etype_eis=et)
     return init_x, acts, pred, loss
+
+
+def lower_only_step_forward(model, ds, batch_gids, y):
+    """The lower-level-only model (model='lower_level_gnn', LL-GNN baseline): src/train.py:99-107 merges
+    the pair batch's unique molecule graphs into ONE graph (first-appearance order, src/batch.py:131-136), Model.forward
+    runs the NodeEmbedding stack, the readout ([G, L*D], no init_x write: model/layers_aggregation.py:68-69), LinkPred
+    over gids_to_batch_ind rows (model/layers_link_pred.py:52) and the loss."""
+    gids = unique_graphs_in_order(np.asarray(batch_gids))
+    m = merge_graphs(ds, gids)
+    x = torch.from_numpy(m['x']).to(model.dtype)
+    acts, pooled = model.lower(x, torch.from_numpy(m['edge_index']), torch.from_numpy(m['batch']), len(gids))
+    to_row = m['gids_to_batch_ind']
+    rows = torch.from_numpy(np.vectorize(to_row.get)(np.asarray(batch_gids)).astype(np.int64))
+    _, pred, loss = model.upper(pooled, None, rows, torch.from_numpy(np.asarray(y)))
+    return m, acts, pooled, pred, loss
 
 
 def adam_step(P, state, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):

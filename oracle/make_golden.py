@@ -259,6 +259,56 @@ def run_step_golden(train_data, FLAGS, out_path, n_seq=24, light=False, eval_pai
     return seq
 
 
+def run_lower_only_golden(train_data, FLAGS, out_path):
+    """One recorded train step of the lower-level-only model (model='lower_level_gnn', the LL-GNN baseline; SURVEY 3.5
+    / BASELINE config 3): src/train.py:99-107 builds ONE BatchData of the pair batch's unique molecule graphs,
+    Model.forward runs 5 x GIN -> multi-scale readout [G, 320] -> LinkPred over gids_to_batch_ind rows
+    (MLP 640-80-10-1, model/layers_link_pred.py:52) -> BCE."""
+    import torch
+    import train as T
+    from model.model import Model
+    from sampler import RandomSampler
+    from utils.util import set_seed
+    set_seed(FLAGS.random_seed + 5)
+    model = Model(train_data)
+    sd0 = sd_to_np(model.state_dict())
+    opt = torch.optim.Adam(model.parameters(), lr=FLAGS.lr)
+    sampler = RandomSampler(train_data, FLAGS.batch_size, FLAGS.sample_induced)
+    model.train()
+    model.zero_grad()
+    bd = T.model_forward(model, train_data, sampler=sampler)
+    loss = model(bd)
+    acts = [a.detach().numpy().copy() for a in model.acts]
+    loss.backward()
+    grads = {k: p.grad.detach().numpy().copy() for k, p in model.named_parameters()
+             if k.startswith('layers.') and p.grad is not None}
+    opt.step()
+    sd1 = sd_to_np(model.state_dict())
+    md = bd.merge_data
+    rec = dict(loss=np.float32(loss.item()),
+               batch_gids=np.asarray(bd.batch_gids, np.int64),
+               positive_gids=np.asarray(bd.positive_pair_gids, np.int64),
+               negative_gids=np.asarray(bd.negative_pair_gids, np.int64),
+               sampled_gids=np.asarray(bd.sampled_gids, np.int64),
+               y_true=np.asarray([p.true_label for p in bd.pair_list], np.int64),
+               merge_gids=np.asarray(list(md['gids_to_batch_ind'].keys()), np.int64),
+               ind_list=np.asarray(md['ind_list'], np.int64),
+               edge_index=md['merge'].edge_index.numpy().astype(np.int32),
+               batch=md['merge'].batch.numpy().astype(np.int32))
+    # acts: [x, 5 x NodeEmbedding, NodeAggregation [G, 320], LinkPred [P, 1], loss]
+    for li in (1, 5, 6, 7):
+        rec['act%d' % li] = acts[li]
+    for k, v in sd0.items():
+        rec['sd0/' + k] = v
+    for k, v in sd1.items():
+        if 'running' in k or 'num_batches' in k:
+            rec['sd1/' + k] = v
+    for k, v in grads.items():
+        rec['grad/' + k] = v
+    np.savez_compressed(out_path, **rec)
+    print('wrote', out_path, 'loss', loss.item(), 'unique graphs', len(rec['merge_gids']), 'atoms', acts[1].shape[0])
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--out', default=os.path.join(os.path.dirname(HERE), 'tests', 'golden'))
@@ -279,6 +329,11 @@ def main():
     if args.dataset == 'drugcombo':
         ref_loader.patch_for_drugcombo()
     train_data, val_pairs, test_pairs, FLAGS = ref_loader.load_drugbank_fold(1)
+    if 'higher_level' not in args.model:
+        run_lower_only_golden(train_data, FLAGS, os.path.join(args.out, args.tag + '_step.npz'))
+        with open(os.path.join(args.out, args.tag + '_layers.txt'), 'w') as f:
+            f.write('\n'.join(getattr(FLAGS, 'layer_%d' % i) for i in range(1, FLAGS.layer_num + 1)) + '\n')
+        return
     if args.eval_only:
         run_step_golden(train_data, FLAGS, None, eval_pairs=val_pairs[:args.eval_only],
                         eval_out=os.path.join(args.out, args.tag + '_eval.npz'))

@@ -1,0 +1,73 @@
+"""Lower-level-only model (model='lower_level_gnn', the LL-GNN baseline = the model of BASELINE config 3) on the GPU
+against the reference's own recorded step (tests/golden/bignn_ll_gnn_step.npz).  The same fixture is green for the
+oracle and for the host path on the CPU stand-in backend; THIS file was written after the round's GPU budget was
+spent and has never run on a GPU, so it only runs when BIGNN_RUN_UNVALIDATED=1 (tools/gpu_validate.sh sets it) --
+remove the gate once it has been seen green."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get('BIGNN_RUN_UNVALIDATED') != '1',
+                                 reason='never run on a GPU yet: set BIGNN_RUN_UNVALIDATED=1')]
+
+import bignn_b200 as B
+from oracle import bignn_oracle as O
+
+DEV = 'cuda:0'
+
+
+def rel(a, b):
+    a = np.asarray(a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else a, np.float64)
+    b = np.asarray(b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def test_ll_gnn_step_vs_reference_golden(golden_dir, drugbank):
+    B._lib.load()
+    z = np.load(os.path.join(golden_dir, 'bignn_ll_gnn_step.npz'))
+    with open(os.path.join(golden_dir, 'bignn_ll_gnn_layers.txt')) as f:
+        lines = f.read().split()
+    try:
+        flags = B.make_flags(model='lower_level_gnn', device=DEV)
+        B.set_flags(flags)
+        assert [getattr(flags, 'layer_%d' % i) for i in range(1, flags.layer_num + 1)] == lines
+        data = B.BiGNNData.from_npz(os.path.join(golden_dir, 'drugbank_packed.npz'), device=DEV)
+        model = B.Model(data).to(DEV)
+        sd = {k[4:]: torch.from_numpy(np.asarray(z[k])) for k in z.files if k.startswith('sd0/')}
+        missing, unexpected = model.load_state_dict(sd, strict=False)
+        assert not unexpected
+        model.train()
+        model.zero_grad()
+        bd = B.BatchData(z['batch_gids'], data, is_train=False)
+        m = bd.merge_data['merge']
+        assert np.array_equal(m.edge_index.cpu().numpy(), z['edge_index'].astype(np.int64))       # bit-exact
+        assert np.array_equal(m.batch.cpu().numpy(), z['batch'].astype(np.int64))
+        loss = model(bd)
+        errs = dict(act1=rel(model.acts[1], z['act1']), act5=rel(model.acts[5], z['act5']),
+                    pooled=rel(model.acts[6], z['act6']), preds=rel(model.acts[7].view(-1), z['act7'].reshape(-1)),
+                    loss=abs(float(loss.detach()) - float(z['loss'])))
+        print('ll-gnn golden, forward errors:', {k: float('%.3g' % v) for k, v in errs.items()})
+        assert max(errs.values()) < 1e-5, errs
+        loss.backward()
+        om = O.OracleModel(O.parse_specs(lines), O.state_from_npz(z, 'sd0/'), dtype=torch.float64)
+        _, _, _, _, l64 = O.lower_only_step_forward(om, drugbank, z['batch_gids'], z['y_true'])
+        l64.backward()
+        g64 = {k: v.grad.numpy() for k, v in om.params().items()}
+        scale = {}
+        for k, g in g64.items():
+            scale[k.split('.')[1]] = max(scale.get(k.split('.')[1], 0.0), float(np.abs(g).max()))
+        named = dict(model.named_parameters())
+        for k, g in g64.items():
+            s = scale[k.split('.')[1]]
+            ours = float(np.abs(named[k].grad.double().cpu().numpy() - g).max()) / s
+            ref = float(np.abs(z['grad/' + k].astype(np.float64) - g).max()) / s
+            assert ours <= 6.0 * ref + 2e-5, (k, ours, ref)
+        sdm = model.state_dict()
+        for k in z.files:
+            if k.startswith('sd1/') and 'running' in k:
+                assert rel(sdm[k[4:]], z[k]) < 1e-5, k
+    finally:
+        B.set_flags(B.make_flags(device=DEV))

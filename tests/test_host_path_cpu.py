@@ -245,3 +245,49 @@ def test_neighbor_and_everything_samplers_bit_exact(cpu_world, golden_dir):
     s2 = B.NeighborSampler(cpu_world, 0.5, 32)
     bg, sg, _ = s2.sample_next_training_batch()
     assert len(sg) == 32 and bg.shape[1] == 2
+
+
+def test_lower_level_only_model_host_path_matches_reference_golden(cpu_world, golden_dir):
+    """model='lower_level_gnn' (LL-GNN baseline): BatchData merges the pair batch's unique molecule graphs
+    on the device path, NodeAggregation returns [G, 320] without writing init_x, LinkPred gathers through
+    gids_to_batch_ind -- against the reference's own recorded step (tests/golden/bignn_ll_gnn_step.npz)."""
+    try:
+        z = np.load(os.path.join(golden_dir, 'bignn_ll_gnn_step.npz'))
+        with open(os.path.join(golden_dir, 'bignn_ll_gnn_layers.txt')) as f:
+            lines = f.read().split()
+        flags = B.make_flags(model='lower_level_gnn', device='cpu')
+        B.set_flags(flags)
+        assert [getattr(flags, 'layer_%d' % i) for i in range(1, flags.layer_num + 1)] == lines
+        data = cpu_world
+        model = B.Model(data)
+        assert {k for k in model.state_dict() if k.startswith('layers.')} == {k[4:] for k in z.files if k.startswith('sd0/')}
+        load_state(model, z)
+        model.train()
+        model.zero_grad()
+        bd = B.BatchData(z['batch_gids'], data, is_train=False)           # recorded positives + negatives
+        assert np.array_equal([p.true_label for p in bd.pair_list], z['y_true'])
+        m = bd.merge_data['merge']
+        assert np.array_equal(list(bd.merge_data['gids_to_batch_ind'].keys()), z['merge_gids'])
+        assert np.array_equal(m.edge_index.numpy(), z['edge_index'].astype(np.int64))
+        assert np.array_equal(m.batch.numpy(), z['batch'].astype(np.int64))
+        loss = model(bd)
+        assert rel(model.acts[1].detach().numpy(), z['act1']) < 1e-5
+        assert rel(model.acts[5].detach().numpy(), z['act5']) < 1e-5
+        assert rel(model.acts[6].detach().numpy(), z['act6']) < 1e-5          # pooled [G, 320]
+        assert rel(model.acts[7].detach().numpy().reshape(-1), z['act7'].reshape(-1)) < 1e-5
+        assert abs(float(loss.detach()) - float(z['loss'])) < 1e-5
+        loss.backward()
+        scale = {}
+        for k in z.files:
+            if k.startswith('grad/'):
+                scale[k.split('.')[1]] = max(scale.get(k.split('.')[1], 0.0), float(np.abs(z[k]).max()))
+        for k, p in model.named_parameters():
+            if k.startswith('layers.'):
+                err = float(np.abs(p.grad.numpy().astype(np.float64) - z['grad/' + k]).max()) / scale[k.split('.')[1]]
+                assert err < 1e-3, (k, err)                                     # wiring check (see the Bi-GNN test)
+        sd = model.state_dict()
+        for k in z.files:
+            if k.startswith('sd1/') and 'running' in k:
+                assert rel(sd[k[4:]].numpy(), z[k]) < 1e-5, k
+    finally:
+        B.set_flags(B.make_flags(device='cpu'))

@@ -229,3 +229,35 @@ def test_evaluation_path_matches_reference(drugbank, step_golden, gin_gcn_specs,
     assert abs(np.mean(losses) - float(e['mean_loss'])) < 1e-6
     # labels of the validation pairs: positives and the pre-drawn validation negatives (label 0)
     assert np.array_equal(O.pair_labels(drugbank, e['gids']), e['y_true'])
+
+
+def test_lower_level_only_model_matches_reference(drugbank, golden_dir):
+    """fourth pinned configuration: model='lower_level_gnn' (the LL-GNN baseline, BASELINE config 3's model): one
+    merged graph of the pair batch's unique molecules, multi-scale readout [G, 320], MLP 640-80-10-1 scorer."""
+    torch.set_num_threads(8)
+    z = np.load(os.path.join(golden_dir, 'bignn_ll_gnn_step.npz'))
+    with open(os.path.join(golden_dir, 'bignn_ll_gnn_layers.txt')) as f:
+        specs = O.parse_specs(f.read().splitlines())
+    model = O.OracleModel(specs, O.state_from_npz(z, 'sd0/'))
+    m, acts, pooled, pred, loss = O.lower_only_step_forward(model, drugbank, z['batch_gids'], z['y_true'])
+    loss.backward()
+    assert np.array_equal(np.asarray(list(m['gids_to_batch_ind'].keys())), z['merge_gids'])
+    assert np.array_equal(m['edge_index'], z['edge_index']) and np.array_equal(m['batch'], z['batch'])
+    assert np.array_equal(m['ind_list'], z['ind_list'])
+    assert rel(acts[0].detach().numpy(), z['act1']) < 1e-6 and rel(acts[4].detach().numpy(), z['act5']) < 1e-6
+    assert rel(pooled.detach().numpy(), z['act6']) < 1e-6
+    assert rel(pred.detach().numpy().reshape(-1), z['act7'].reshape(-1)) < 1e-6
+    assert abs(float(loss.detach()) - float(z['loss'])) < 1e-6
+    scale = {}
+    for k in z.files:
+        if k.startswith('grad/'):
+            scale[k.split('.')[1]] = max(scale.get(k.split('.')[1], 0.0), float(np.abs(z[k]).max()))
+    n = 0
+    for k, v in model.params().items():
+        err = float(np.abs(v.grad.numpy().astype(np.float64) - z['grad/' + k]).max()) / scale[k.split('.')[1]]
+        assert err < 5e-5, (k, err)
+        n += 1
+    assert n == len([k for k in z.files if k.startswith('grad/')])
+    for k in z.files:
+        if k.startswith('sd1/') and 'running' in k:
+            assert rel(model.P[k[4:]].numpy(), z[k]) < 1e-6, k
