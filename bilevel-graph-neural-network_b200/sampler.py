@@ -16,22 +16,73 @@ import numpy as np
 from torch.utils.data import DataLoader
 
 
+def _host_adjacency(graph):
+    """neighbour lists of the interaction graph in the reference graph's order: ascending (nx.from_scipy_sparse_matrix
+    adds the edges of a sorted symmetric matrix row by row)."""
+    ptr = np.asarray(graph.csr._row_ptr_host, np.int64)
+    col = np.asarray(graph.col_host, np.int64)
+    return [col[ptr[i]:ptr[i + 1]].tolist() for i in range(graph.number_of_nodes())]
+
+
+def _induced_edges(adj, n_nodes, nodes, copied):
+    """Edges of the sub-graph induced by `nodes`, in the order networkx 3.x reports them: the node view walks the
+    filter set when it is less than half the size of the graph, else the graph's node order; each node's neighbours
+    come in adjacency order; an undirected edge is reported from its first endpoint.  `copied`: the order of
+    `G.subgraph(nodes).copy().edges` (the copy keeps first-insertion order of each adjacency), else of the view's
+    own `.edges`."""
+    keep = set(n for n in nodes)                     # nbunch_iter -> a fresh set with its own iteration order
+    order = [n for n in keep] if 2 * len(keep) < n_nodes else [n for n in range(n_nodes) if n in keep]
+    if copied:
+        sub = {n: {} for n in order}
+        for u in order:
+            for v in adj[u]:
+                if v in keep:
+                    sub[u][v] = None
+                    sub[v][u] = None
+    else:
+        sub = {u: [v for v in adj[u] if v in keep] for u in order}
+    edges, seen = [], set()
+    for n, nbrs in sub.items():
+        for v in nbrs:
+            if v not in seen:
+                edges.append((n, v))
+        seen.add(n)
+    return order, edges
+
+
 class RandomSampler(object):
+    """Shuffled mini-batches of positive train pairs (src/sampler.py:110-131); with `sample_induced` every train pair
+    between the drugs of the drawn batch (:133-142)."""
+
     def __init__(self, data, batch_size, sample_induced=False):
-        if sample_induced:
-            raise NotImplementedError('sample_induced is off by default (src/config.py) and not on the path')
         self.batch_size = batch_size
+        self.sample_induced = sample_induced
         self.data_loader = DataLoader(data, batch_size=batch_size, shuffle=True)
         self.data_iterable = iter(self.data_loader)
+        if sample_induced:
+            ds = data.dataset
+            self.id_map, self.gs_map = ds.id_map, ds.gs_map
+            self.num_nodes = ds.interaction_combo_nxgraph.number_of_nodes()
+            self.nodes_visited_counter = np.zeros(self.num_nodes)
+            self._adj = _host_adjacency(ds.interaction_combo_nxgraph)
+
+    def _next_pairs(self):
+        pairs = next(self.data_iterable, None)
+        if pairs is None:                                   # epoch over: a fresh shuffle
+            self.data_iterable = iter(self.data_loader)
+            pairs = next(self.data_iterable)
+        return pairs.cpu().detach().numpy()
 
     def sample_next_training_batch(self):
-        try:
-            sampled_pairs = next(self.data_iterable)
-        except StopIteration:
-            self.data_iterable = iter(self.data_loader)
-            sampled_pairs = next(self.data_iterable)
-        batch_gids = sampled_pairs.cpu().detach().numpy()
-        return batch_gids, np.unique(batch_gids), None
+        batch_gids = self._next_pairs()
+        if not self.sample_induced:
+            return batch_gids, np.unique(batch_gids), None
+        rows = [self.gs_map[int(g)] for g in np.unique(batch_gids)]
+        _, edges = _induced_edges(self._adj, self.num_nodes, rows, copied=False)
+        induced = np.asarray([(self.id_map[u], self.id_map[v]) for u, v in edges])
+        for r in np.unique(np.asarray(edges)):
+            self.nodes_visited_counter[r] += 1
+        return induced, np.unique(induced), None
 
 
 class EverythingSampler(RandomSampler):
@@ -60,11 +111,7 @@ class NeighborSampler(object):
         self.neighbor_size = neighbor_size              # int, or a fraction of the neighbours
         self.num_nodes = g.number_of_nodes()
         self.nodes_visited_counter = np.zeros(self.num_nodes)
-        ptr = np.asarray(g.csr._row_ptr_host, np.int64)
-        col = np.asarray(g.col_host, np.int64)
-        # adjacency in the reference graph's order: neighbours ascending (from_scipy_sparse_matrix adds the edges
-        # of a sorted symmetric matrix row by row)
-        self._adj = [col[ptr[i]:ptr[i + 1]].tolist() for i in range(self.num_nodes)]
+        self._adj = _host_adjacency(g)
 
     # -- src/sampler.py:80-86
     def _sampled_neighbours(self, node):
@@ -104,31 +151,8 @@ class NeighborSampler(object):
             nodes = nodes.union(self._bfs(cand, room))
         return nodes
 
-    def _induced_pairs(self, nodes):
-        """Edges of the induced sub-graph in the order `G.subgraph(nodes).copy().edges` yields them (networkx 3.x:
-        the node view walks the filter set when it is less than half the size of the graph, else the graph's node
-        order; each node's neighbours come in adjacency order; the copy keeps first-insertion order; an undirected
-        edge is reported from its first endpoint in node order)."""
-        keep = set(n for n in nodes)                     # nbunch_iter -> a fresh set: its own iteration order
-        order = [n for n in keep]                        # 2*len(keep) < num_nodes on this path
-        if 2 * len(keep) >= self.num_nodes:
-            order = [n for n in range(self.num_nodes) if n in keep]
-        adj = {n: {} for n in order}
-        for u in order:
-            for v in self._adj[u]:                       # a node's own neighbours: always in adjacency order
-                if v in keep:
-                    adj[u][v] = None
-                    adj[v][u] = None
-        edges, seen = [], set()
-        for n, nbrs in adj.items():
-            for v in nbrs:
-                if v not in seen:
-                    edges.append((n, v))
-            seen.add(n)
-        return order, edges
-
     def sample_next_training_batch(self):
         nodes = self._sample_nodes()
-        order, edges = self._induced_pairs(nodes)
+        order, edges = _induced_edges(self._adj, self.num_nodes, nodes, copied=True)
         batch_gids = np.asarray([(self.id_map[u], self.id_map[v]) for u, v in edges])
         return batch_gids, [self.id_map[n] for n in nodes], SampledSubgraph(order, edges)

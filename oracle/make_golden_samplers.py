@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY -- records the reference's NeighborSampler / EverythingSampler (src/sampler.py:51-107)
 on DrugBank fold 1 after set_seed(8): six consecutive NeighborSampler(neighbor_size=5, batch_size=64) batches
-(sampled drugs in order, induced pairs in order, sub-graph node order, the visit counter) and the head of one
-EverythingSampler batch -> tests/golden/bignn_samplers.npz.  Runs only where /root/reference exists.
+(sampled drugs in order, induced pairs in order, sub-graph node order, the visit counter) the head of one
+EverythingSampler batch, and four RandomSampler(sample_induced=True) batches -> tests/golden/bignn_samplers.npz.  Runs only where /root/reference exists.
 Note: recorded under the networkx installed in this container (3.x, version string patched to the 2.2 the reference
 demands, oracle/ref_loader.py); 2.2's sub-graph views order hub nodes' neighbours differently, which can only change
 the ORDER of the induced pairs, not the sampled drugs or the pair set.
@@ -25,7 +25,7 @@ def main():
     args = ap.parse_args()
     ref_loader.load_reference()
     train_data, _, _, FLAGS = ref_loader.load_drugbank_fold(1)
-    from sampler import NeighborSampler, EverythingSampler
+    from sampler import NeighborSampler, EverythingSampler, RandomSampler
     from utils.util import set_seed
     G = train_data.dataset.interaction_combo_nxgraph
     assert all(list(G.neighbors(u)) == sorted(G.neighbors(u)) for u in G.nodes)      # adjacency order = ascending
@@ -44,6 +44,13 @@ def main():
     out['everything/batch_gids_head'] = np.asarray(bg[:256], np.int64)
     out['everything/n'] = np.int64(len(bg))
     out['everything/sampled_n'] = np.int64(len(sg))
+    set_seed(8)
+    r = RandomSampler(train_data, 64, sample_induced=True)          # src/sampler.py:133-142
+    for i in range(4):
+        bg, sg, _ = r.sample_next_training_batch()
+        out['induced/batch_gids/%d' % i] = np.asarray(bg, np.int64)
+        out['induced/sampled_gids/%d' % i] = np.asarray(sg, np.int64)
+    out['induced/visited_counter'] = r.nodes_visited_counter.copy()
     np.savez_compressed(os.path.join(args.out, 'bignn_samplers.npz'), **out)
     print('wrote', os.path.join(args.out, 'bignn_samplers.npz'))
 

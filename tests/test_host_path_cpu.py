@@ -241,6 +241,15 @@ def test_neighbor_and_everything_samplers_bit_exact(cpu_world, golden_dir):
     assert none is None and len(bg) == int(z['everything/n']) == len(cpu_world.train_pairs)
     assert len(sg) == int(z['everything/sampled_n'])
     assert np.array_equal(bg[:256], z['everything/batch_gids_head'])
+    # RandomSampler(sample_induced=True): every train pair among the drugs of the drawn batch (src/sampler.py:133-142)
+    random.seed(8); np.random.seed(8); torch.manual_seed(8)
+    r = B.RandomSampler(cpu_world, 64, sample_induced=True)
+    for i in range(4):
+        bg, sg, none = r.sample_next_training_batch()
+        assert none is None
+        assert np.array_equal(bg, z['induced/batch_gids/%d' % i])
+        assert np.array_equal(sg, z['induced/sampled_gids/%d' % i])
+    assert np.array_equal(r.nodes_visited_counter, z['induced/visited_counter'])
     # a fractional neighbour budget (src/sampler.py:83-84)
     s2 = B.NeighborSampler(cpu_world, 0.5, 32)
     bg, sg, _ = s2.sample_next_training_batch()
