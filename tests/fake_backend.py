@@ -291,6 +291,36 @@ class Fake(object):
         dRows.copy_((dz - zh * (dz * zh).sum(1, keepdim=True)) / n)
         return 0
 
+    def bignn_prelu_fwd_f32(self, X, Y, rows, C, w, nw):
+        Y.copy_(torch.where(X >= 0, X, X * (w if nw > 1 else w.view(()))))
+        return 0
+
+    def bignn_prelu_bwd_f32(self, X, dY, dX, T, rows, C, w, nw):
+        dX.copy_(torch.where(X >= 0, dY, dY * (w if nw > 1 else w.view(()))))
+        T.copy_(torch.where(X >= 0, torch.zeros_like(X), dY * X))         # column sums of T = d slope
+        return 0
+
+    def bignn_rownorm_fwd_f32(self, X, ldx, Y, ldy, rows, D, nrm):
+        n = X[:rows, :D].norm(dim=1).clamp(min=1e-12)
+        nrm.copy_(n)
+        Y[:rows, :D] = X[:rows, :D] / n.view(-1, 1)
+        return 0
+
+    def bignn_rownorm_bwd_f32(self, Y, ldy, dY, lddy, nrm, dX, lddx, rows, D):
+        y, dy = Y[:rows, :D], dY[:rows, :D]
+        dX[:rows, :D] = (dy - y * (dy * y).sum(1, keepdim=True)) / nrm.view(-1, 1)
+        return 0
+
+    def bignn_gate_mul_fwd_f32(self, G, W, O, n):
+        O.copy_(torch.sigmoid(G) * W)
+        return 0
+
+    def bignn_gate_mul_bwd_f32(self, G, W, dO, dG, dW, n):
+        s = torch.sigmoid(G)
+        dG.copy_(dO * W * s * (1 - s))
+        dW.copy_(dO * s)
+        return 0
+
     def bignn_add_f32(self, A, B, O, n):
         O.copy_(A + B)
         return 0

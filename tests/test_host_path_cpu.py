@@ -300,3 +300,67 @@ def test_lower_level_only_model_host_path_matches_reference_golden(cpu_world, go
                 assert rel(sd[k[4:]].numpy(), z[k]) < 1e-5, k
     finally:
         B.set_flags(B.make_flags(device='cpu'))
+
+
+def test_layer_variants_host_classes_match_reference(cpu_world, golden_dir):
+    """bignn_b200's NodeEmbedding / NodeAggregation classes (constructor arguments, state_dict names, autograd
+    wiring of the prelu / normalize / deepsets / gated-readout variants) against the reference's own layer classes
+    (tests/golden/bignn_layer_variants.npz); arithmetic = the torch-CPU stand-in of the C-ABI."""
+    import types
+    from bignn_b200.layers import NodeEmbedding
+    from bignn_b200.layers_aggregation import NodeAggregation
+    z = np.load(os.path.join(golden_dir, 'bignn_layer_variants.npz'))
+    data = cpu_world
+    try:
+        B.set_flags(B.make_flags(model='lower_level_gnn', device='cpu'))
+        rows = [data.gs_map[int(g)] for g in z['gids']]
+        merged = B.MergedGraph(data.packed, rows)
+        assert np.array_equal(merged.edge_index.numpy(), z['edge_index'].astype(np.int64))
+        bd = types.SimpleNamespace(merge_data={'merge': merged, 'gids_to_batch_ind': {int(g): i for i, g in enumerate(z['gids'])}},
+                                   merge_higher_level={}, dataset=data)
+        model = types.SimpleNamespace(acts=None, store_layer_output=lambda layer, x: None)
+        R = torch.from_numpy(z['R_nodes'])
+
+        def run(tag, module, x_in, fn, Rm, tol_out=1e-5, tol_g=2e-4):
+            sd = {k[len(tag) + 4:]: torch.from_numpy(np.asarray(z[k])) for k in z.files if k.startswith(tag + '/sd/')}
+            missing, unexpected = module.load_state_dict(sd, strict=False)
+            assert not unexpected and not missing, (tag, missing, unexpected)
+            module.train()
+            x = x_in.clone().requires_grad_(True)
+            y = fn(module, x)
+            (y * Rm).sum().backward()
+            assert rel(y.detach().numpy(), z[tag + '/out']) < tol_out, tag
+            assert float(np.abs(x.grad.numpy() - z[tag + '/dx']).max()) <= tol_g * max(float(np.abs(z[tag + '/dx']).max()), 1e-9), tag
+            scale = max([float(np.abs(z[k]).max()) for k in z.files if k.startswith(tag + '/grad/')] or [0.0])
+            for k, p in module.named_parameters():
+                g = np.zeros_like(z[tag + '/grad/' + k]) if p.grad is None else p.grad.numpy()
+                assert float(np.abs(g - z[tag + '/grad/' + k]).max()) <= tol_g * scale, (tag, k)
+
+        n = 0
+        for tag in z['cases'].tolist():
+            parts = tag.split('/')
+            if parts[0] == 'ne' and parts[2] != 'first_layer':
+                if parts[1] == 'gat':
+                    continue                              # (covered by the DrugCombo / GIN+GAT golden steps)
+                m = NodeEmbedding(parts[1], 64, 64, parts[2], parts[3] == 'bn1', parts[4] == 'norm1')
+                run(tag, m, torch.from_numpy(z['h64']), lambda mod, x: mod(x, bd, model), R)
+                n += 1
+        m = NodeEmbedding('gin', int(z['x_u8'].shape[1]), 64, 'relu', True, False)
+        run('ne/gin/first_layer', m, torch.from_numpy(z['x_u8'].astype(np.float32)), lambda mod, x: mod(x, bd, model), R)
+        acts5 = [torch.from_numpy(z['acts5/%d' % i]) for i in range(5)]
+        Rg = torch.from_numpy(z['R_graphs'])
+        for style in ('avg_pool', 'sum'):
+            def multi(mod, x):
+                model.acts = [None] + [x] + acts5[1:]
+                return mod(x, bd, model)
+            run('agg/%s/multi' % style, NodeAggregation(style, True, concat_multi_scale=True, in_dim=64, out_dim=64),
+                acts5[0], multi, Rg)
+            run('agg/%s/single' % style, NodeAggregation(style, True, concat_multi_scale=False, in_dim=64, out_dim=64),
+                acts5[0], lambda mod, x: mod(x, bd, model), Rg[:, :64])
+        run('agg/deepsets', NodeAggregation('deepsets', True, concat_multi_scale=False, in_dim=64, out_dim=64,
+                                            num_mlp_layers=2), acts5[0], lambda mod, x: mod(x, bd, model), Rg[:, :64])
+        run('agg/gmn_aggr', NodeAggregation('gmn_aggr', True, concat_multi_scale=False, in_dim=64, out_dim=64),
+            acts5[0], lambda mod, x: mod(x, bd, model), Rg[:, :64])
+        assert n >= 20
+    finally:
+        B.set_flags(B.make_flags(device='cpu'))
