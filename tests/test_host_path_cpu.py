@@ -340,8 +340,6 @@ def test_layer_variants_host_classes_match_reference(cpu_world, golden_dir):
         for tag in z['cases'].tolist():
             parts = tag.split('/')
             if parts[0] == 'ne' and parts[2] != 'first_layer':
-                if parts[1] == 'gat':
-                    continue                              # (covered by the DrugCombo / GIN+GAT golden steps)
                 m = NodeEmbedding(parts[1], 64, 64, parts[2], parts[3] == 'bn1', parts[4] == 'norm1')
                 run(tag, m, torch.from_numpy(z['h64']), lambda mod, x: mod(x, bd, model), R)
                 n += 1
