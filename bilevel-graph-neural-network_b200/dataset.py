@@ -116,6 +116,25 @@ class BiGNNData(object):
                    z['pair_labels'] if 'pair_labels' in files else None,
                    int(z['num_labels']) if 'num_labels' in files else 2, device, et)
 
+    def init_interaction_graph_feats(self, init_method, d_init=64, feats=None, feat_size=None):
+        """Fixed drug features for models WITHOUT a lower level (utils/data/dataset.py:176-198; src/load_data.py:
+        150-153): 'rand_init' = xavier-normal [N, d_init] (gain of relu) drawn from torch's global RNG as the reference
+        does, 'ones_init', or given `feats` ('graph_feats': the ECFP fingerprints the reference keeps in a klepto
+        blob).  They become the interaction graph's node features (`init_x`), as `init_interaction_graph_embds` does
+        (utils/data/dataset.py:166-175)."""
+        if feats is not None:
+            x = torch.as_tensor(np.asarray(feats, np.float32))
+        elif 'rand_init' in init_method:
+            x = torch.nn.init.xavier_normal_(torch.empty(self.N, d_init), gain=torch.nn.init.calculate_gain('relu'))
+        elif 'ones_init' in init_method:
+            x = torch.ones(self.N, d_init)
+        else:
+            raise NotImplementedError('init_embds={!r} needs the drug features passed in as `feats`'.format(init_method))
+        self.graph_feats = x.to(self.device)
+        self.interaction_num_node_feat = int(x.shape[1])
+        self.interaction_combo_nxgraph.init_x = self.graph_feats
+        return self.graph_feats
+
     def __len__(self):
         return self.train_pairs.shape[0]
 

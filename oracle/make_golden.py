@@ -309,6 +309,53 @@ def run_lower_only_golden(train_data, FLAGS, out_path):
     print('wrote', out_path, 'loss', loss.item(), 'unique graphs', len(rec['merge_gids']), 'atoms', acts[1].shape[0])
 
 
+def run_upper_only_golden(train_data, FLAGS, out_path):
+    """One recorded train step of the upper-level-only model (model='higher_level_gnn', DECAGON -- the model the
+    reference's config.py selects as shipped): fixed random drug features (init_embds='rand_init',
+    utils/data/dataset.py:181-188) -> LoadInteractionLayer -> 3 x NodeEmbedding over the interaction graph ->
+    LinkPred -> BCE."""
+    import torch
+    import train as T
+    from model.model import Model
+    from sampler import RandomSampler
+    from utils.util import set_seed
+    ds = train_data.dataset
+    set_seed(FLAGS.random_seed + 5)
+    model = Model(train_data)
+    sd0 = sd_to_np(model.state_dict())
+    opt = torch.optim.Adam(model.parameters(), lr=FLAGS.lr)
+    sampler = RandomSampler(train_data, FLAGS.batch_size, FLAGS.sample_induced)
+    ds.init_interaction_graph_embds(device=FLAGS.device)          # src/train.py:22-28 (no lower level: graph_feats)
+    feats = ds.interaction_combo_nxgraph.init_x.detach().numpy().copy()
+    model.train()
+    model.zero_grad()
+    bd = T.model_forward(model, train_data, sampler=sampler)
+    loss = model(bd)
+    acts = [a.detach().numpy().copy() if a is not None else None for a in model.acts]
+    loss.backward()
+    grads = {k: p.grad.detach().numpy().copy() for k, p in model.named_parameters()
+             if k.startswith('layers.') and p.grad is not None}
+    opt.step()
+    sd1 = sd_to_np(model.state_dict())
+    rec = dict(loss=np.float32(loss.item()), graph_feats=feats,
+               batch_gids=np.asarray(bd.batch_gids, np.int64),
+               positive_gids=np.asarray(bd.positive_pair_gids, np.int64),
+               sampled_gids=np.asarray(bd.sampled_gids, np.int64),
+               y_true=np.asarray([p.true_label for p in bd.pair_list], np.int64))
+    for li in range(1, len(acts)):
+        if acts[li] is not None and acts[li].ndim > 0:
+            rec['act%d' % li] = acts[li]
+    for k, v in sd0.items():
+        rec['sd0/' + k] = v
+    for k, v in sd1.items():
+        if 'running' in k or 'num_batches' in k:
+            rec['sd1/' + k] = v
+    for k, v in grads.items():
+        rec['grad/' + k] = v
+    np.savez_compressed(out_path, **rec)
+    print('wrote', out_path, 'loss', loss.item(), 'acts', [None if a is None else a.shape for a in acts])
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--out', default=os.path.join(os.path.dirname(HERE), 'tests', 'golden'))
@@ -329,6 +376,11 @@ def main():
     if args.dataset == 'drugcombo':
         ref_loader.patch_for_drugcombo()
     train_data, val_pairs, test_pairs, FLAGS = ref_loader.load_drugbank_fold(1)
+    if 'lower_level' not in args.model:
+        run_upper_only_golden(train_data, FLAGS, os.path.join(args.out, args.tag + '_step.npz'))
+        with open(os.path.join(args.out, args.tag + '_layers.txt'), 'w') as f:
+            f.write('\n'.join(getattr(FLAGS, 'layer_%d' % i) for i in range(1, FLAGS.layer_num + 1)) + '\n')
+        return
     if 'higher_level' not in args.model:
         run_lower_only_golden(train_data, FLAGS, os.path.join(args.out, args.tag + '_step.npz'))
         with open(os.path.join(args.out, args.tag + '_layers.txt'), 'w') as f:

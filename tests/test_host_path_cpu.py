@@ -362,3 +362,49 @@ def test_layer_variants_host_classes_match_reference(cpu_world, golden_dir):
         assert n >= 20
     finally:
         B.set_flags(B.make_flags(device='cpu'))
+
+
+def test_upper_level_only_model_host_path_matches_reference_golden(golden_dir):
+    """model='higher_level_gnn' (DECAGON; the reference's shipped default model) through the drop-in layer registry:
+    fixed drug features as the interaction graph's node features, `Model.forward` over all layers."""
+    fake_backend.install()
+    try:
+        z = np.load(os.path.join(golden_dir, 'bignn_decagon_step.npz'))
+        with open(os.path.join(golden_dir, 'bignn_decagon_layers.txt')) as f:
+            lines = f.read().split()
+        flags = B.make_flags(model='higher_level_gnn', higher_level_gnn_type='gat', device='cpu')
+        B.set_flags(flags)
+        assert [getattr(flags, 'layer_%d' % i) for i in range(1, flags.layer_num + 1)] == lines
+        data = B.BiGNNData.from_npz(os.path.join(golden_dir, 'drugbank_packed.npz'), device='cpu')
+        with pytest.raises((RuntimeError, TypeError)):
+            B.Model(data)                                   # no drug features yet: the first layer has no input width
+        torch.manual_seed(3)
+        f1 = data.init_interaction_graph_feats('rand_init', 64)
+        torch.manual_seed(3)
+        f2 = torch.nn.init.xavier_normal_(torch.empty(data.N, 64), gain=torch.nn.init.calculate_gain('relu'))
+        assert torch.equal(f1, f2) and data.interaction_num_node_feat == 64       # the reference's draw
+        data.init_interaction_graph_feats('rand_init', 64, feats=z['graph_feats'])
+        model = B.Model(data)
+        assert {k for k in model.state_dict() if k.startswith('layers.')} == {k[4:] for k in z.files if k.startswith('sd0/')}
+        load_state(model, z)
+        model.train()
+        model.zero_grad()
+        bd = B.BatchData(z['batch_gids'], data, is_train=False)
+        assert np.array_equal([p.true_label for p in bd.pair_list], z['y_true'])
+        loss = model(bd)
+        for i in (2, 3, 4):
+            assert rel(model.acts[i].detach().numpy(), z['act%d' % i]) < 1e-5
+        assert rel(model.acts[5].detach().numpy().reshape(-1), z['act5'].reshape(-1)) < 1e-5
+        assert abs(float(loss.detach()) - float(z['loss'])) < 1e-6
+        loss.backward()
+        scale = {}
+        for k in z.files:
+            if k.startswith('grad/'):
+                scale[k.split('.')[1]] = max(scale.get(k.split('.')[1], 0.0), float(np.abs(z[k]).max()))
+        for k, p in model.named_parameters():
+            if k.startswith('layers.'):
+                err = float(np.abs(p.grad.numpy().astype(np.float64) - z['grad/' + k]).max()) / scale[k.split('.')[1]]
+                assert err < 5e-5, (k, err)
+    finally:
+        fake_backend.uninstall()
+        B.set_flags(None)

@@ -261,3 +261,31 @@ def test_lower_level_only_model_matches_reference(drugbank, golden_dir):
     for k in z.files:
         if k.startswith('sd1/') and 'running' in k:
             assert rel(model.P[k[4:]].numpy(), z[k]) < 1e-6, k
+
+
+def test_upper_level_only_model_matches_reference(drugbank, golden_dir):
+    """fifth pinned configuration: model='higher_level_gnn' (DECAGON, the model src/config.py selects as shipped):
+    fixed random drug features -> 3 x GAT NodeEmbedding over the interaction graph -> MLP scorer -> BCE."""
+    torch.set_num_threads(8)
+    z = np.load(os.path.join(golden_dir, 'bignn_decagon_step.npz'))
+    with open(os.path.join(golden_dir, 'bignn_decagon_layers.txt')) as f:
+        specs = O.parse_specs(f.read().splitlines())
+    model = O.OracleModel(specs, O.state_from_npz(z, 'sd0/'), gat_group='source')
+    ddi = torch.from_numpy(np.stack([drugbank.ddi_row, drugbank.ddi_col]))
+    rows = torch.from_numpy(np.vectorize(drugbank.gs_map.get)(z['batch_gids']).astype(np.int64))
+    acts, pred, loss = model.upper(torch.from_numpy(z['graph_feats']), ddi, rows, torch.from_numpy(z['y_true']))
+    loss.backward()
+    for l in range(3):
+        assert rel(acts[l].detach().numpy(), z['act%d' % (l + 2)]) < 1e-6
+    assert rel(pred.detach().numpy().reshape(-1), z['act5'].reshape(-1)) < 1e-6
+    assert abs(float(loss.detach()) - float(z['loss'])) < 1e-6
+    scale = {}
+    for k in z.files:
+        if k.startswith('grad/'):
+            scale[k.split('.')[1]] = max(scale.get(k.split('.')[1], 0.0), float(np.abs(z[k]).max()))
+    n = 0
+    for k, v in model.params().items():
+        err = float(np.abs(v.grad.numpy().astype(np.float64) - z['grad/' + k]).max()) / scale[k.split('.')[1]]
+        assert err < 2e-5, (k, err)
+        n += 1
+    assert n == len([k for k in z.files if k.startswith('grad/')])
