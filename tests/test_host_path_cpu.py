@@ -364,10 +364,9 @@ def test_layer_variants_host_classes_match_reference(cpu_world, golden_dir):
         B.set_flags(B.make_flags(device='cpu'))
 
 
-def test_upper_level_only_model_host_path_matches_reference_golden(golden_dir):
+def test_upper_level_only_model_host_path_matches_reference_golden(cpu_world, golden_dir):
     """model='higher_level_gnn' (DECAGON; the reference's shipped default model) through the drop-in layer registry:
     fixed drug features as the interaction graph's node features, `Model.forward` over all layers."""
-    fake_backend.install()
     try:
         z = np.load(os.path.join(golden_dir, 'bignn_decagon_step.npz'))
         with open(os.path.join(golden_dir, 'bignn_decagon_layers.txt')) as f:
@@ -406,5 +405,4 @@ def test_upper_level_only_model_host_path_matches_reference_golden(golden_dir):
                 err = float(np.abs(p.grad.numpy().astype(np.float64) - z['grad/' + k]).max()) / scale[k.split('.')[1]]
                 assert err < 5e-5, (k, err)
     finally:
-        fake_backend.uninstall()
-        B.set_flags(None)
+        B.set_flags(B.make_flags(device='cpu'))
