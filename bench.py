@@ -27,10 +27,12 @@ UNIT = 'pairs/s'
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='drugcombo_shape')
+    ap.add_argument('--workload', default='ddi_scaled',
+                    help='ddi_scaled = BASELINE config 4 (the configuration the 1/2/4/8-GPU metric is quoted on); '
+                         'drugcombo_shape = config 2; drugbank_shape = config 1')
     ap.add_argument('--seed', type=int, default=0)
     ap.add_argument('--no-graph', action='store_true', help='eager launches instead of CUDA-graph replay')
     ap.add_argument('--no-l2-flush', action='store_true')
@@ -39,6 +41,8 @@ def parse():
                     help='N > 1: after the timed region, two eager steps with CUDA events around every C-ABI call and '
                          'every collective (rank 0 reports; collective times include waiting for the slowest rank)')
     ap.add_argument('--skip-cpu', action='store_true', help='no cpu_baseline leg (non-default workloads)')
+    ap.add_argument('--skip-gpu-eager', action='store_true', help='no gpu_eager_baseline leg')
+    ap.add_argument('--ref-device', default='cpu', help='--impl reference: cpu (the reference arm) or cuda (eager baseline)')
     ap.add_argument('--skip-rooflines', action='store_true', help='no kernel roofline legs (non-default workloads)')
     ap.add_argument('--replicated-upper', action='store_true',
                     help='N > 1: evaluate the upper level on every rank instead of row-partitioning it (GCN only)')
@@ -61,7 +65,8 @@ def workload_config(name):
 
 def make_workload(name, seed):
     from bignn_b200 import synthetic as S
-    return S.cached_workload(name, seed)
+    # one process per node draws the 20 M-edge graph; the other ranks wait for its cache file
+    return S.cached_workload(name, seed, writer=int(os.environ.get('LOCAL_RANK', 0)) == 0)
 
 
 def workload_flags(name, device='cuda:0'):
@@ -81,39 +86,56 @@ def layer_specs(name):
 
 
 # --------------------------------------------------------------------------- reference arm
-def run_reference(args, sample_steps=None, quiet=False):
+# the reference's per-graph host conversion and Python edge set make the 200 k-drug / 20 M-edge configuration
+# infeasible as a bounded sample on the CPU (~30 s and tens of GB of autograd state per
+# step): each reference-arm step is ONE FULL TRAIN STEP OF THE SAME WORKLOAD AT 1/10 SIZE, and the reported value is
+# the linear extrapolation to full size (the step cost scales with drugs and edges, not with the 128 scored pairs).
+REFERENCE_SAMPLE = {'ddi_scaled': ('ddi_scaled_small', 10.0)}
+
+
+def run_reference(args, sample_steps=None, device='cpu'):
     """The reference path on the host cores: oracle/bignn_oracle.py (CPU port; the reference is
-    pure Python over un-vendored wheels and cannot travel to the GPU box)."""
+    pure Python over un-vendored wheels and cannot travel to the GPU box).  device='cuda' runs the same eager
+    code on the GPU (what the reference would do on a B200 today)."""
     import torch
     from oracle import bignn_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    # the reference's per-graph host conversion and Python edge set make the 200 k-drug / 20 M-edge configuration
-    # infeasible on the CPU (SURVEY 8d): it is timed at 1/10 of the shape and labelled as such
-    name = 'ddi_scaled_small' if args.workload == 'ddi_scaled' else args.workload
+    name, scale = REFERENCE_SAMPLE.get(args.workload, (args.workload, 1.0))
     w = make_workload(name, args.seed)
     ds = O.PackedDataset(w)
     specs = O.parse_specs(layer_specs(args.workload))
     state = O.init_params(specs, ds.num_node_feat, num_labels=int(w['num_labels']), seed=8,
                           num_edge_types=len(ds.etypes) + 1)
-    tr = O.OracleTrainer(ds, specs, state, 64)
+    tr = O.OracleTrainer(ds, specs, state, 64, device=device)
     np.random.seed(8)
     torch.manual_seed(8)
     steps = args.steps if sample_steps is None else sample_steps
     warm = min(args.warmup, 2) if sample_steps is not None else args.warmup
+    sync = torch.cuda.synchronize if device != 'cpu' else (lambda: None)
     for _ in range(warm):
         tr.step()
+    sync()
     t0 = time.perf_counter()
     pairs = 0
     for _ in range(steps):
         _, p = tr.step()
         pairs += p
+    sync()
     dt = time.perf_counter() - t0
-    return dict(value=pairs / dt, ms_per_step=1e3 * dt / steps, cores=cores, steps=steps,
-                sample='{} full train steps of {} ({} pairs/step), torch CPU fp32, {} threads'.format(
-                    steps, 'the same workload' if name == args.workload else
-                    'the workload at 1/10 size ({}: the step cost scales with drugs and edges, not pairs)'.format(name),
-                    pairs // max(steps, 1), cores))
+    measured = pairs / dt
+    what = 'torch {} eager fp32'.format('CUDA' if device != 'cpu' else 'CPU')
+    if scale == 1.0:
+        sample = '{} full train steps of the same workload ({} pairs/step), {}, {} host threads'.format(
+            steps, pairs // max(steps, 1), what, cores)
+    else:
+        sample = ('{} full train steps of the workload at 1/{:g} size ({}: {} drugs, {} DDI edges; {} pairs/step), {}, '
+                  '{} host threads: measured {:.1f} pairs/s = {:.1f} ms/step; value = linear extrapolation to full size '
+                  '(measured / {:g}: the step cost scales with drugs and edges, not with the pairs scored)').format(
+            steps, scale, name, ds.N, len(ds.ddi_row) // 2, pairs // max(steps, 1), what, cores, measured,
+            1e3 * dt / steps, scale)
+    return dict(value=measured / scale, ms_per_step=1e3 * dt / steps * scale, cores=cores, steps=steps, sample=sample,
+                measured_sample_value=measured, extrapolation_factor=scale)
 
 
 # --------------------------------------------------------------------------- clocks
@@ -190,39 +212,6 @@ def spmm_roofline(torch, B, rows, peaks, device):
     return dict(kernel='k_spmm_v4<16,1,GIN> (bignn_spmm_f32)', bound='hbm', achieved=ach, peak=peak, unit='GB/s',
                 frac=ach / peak, traffic=traffic, rows=A, nnz=nnz, D=D, ms_per_launch=ms,
                 algorithmic_bytes=alg, peak_source='MEASURED_PEAKS.json' if 'hbm_gbs' in peaks else 'fallback 6650')
-
-
-def dense_roofline(torch, B, rows, peaks, device):
-    """The step's dominant kernel by device time (profiles/r1_final_summary.md): the tcgen05 3xTF32 node
-    transform k_gemm_tc<64,2>, at the in-step shape (rows = atoms of the workload) and at a > L2 shape.
-    It is HBM-bound (64 FLOP per byte at three TF32 products), so it is reported against the copy peak."""
-    from bignn_b200 import ops
-    out = {}
-    peak = peaks.get('hbm_gbs', 6650.0)
-    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=device)
-    for tag, M in (('in_step_shape', rows), ('gt_l2_shape', 2_000_000)):
-        a = torch.randn(M, 64, device=device)
-        w = torch.randn(64, 64, device=device)
-        b = torch.randn(64, device=device)
-        c = torch.empty(M, 64, device=device)
-        for _ in range(3):
-            ops.gemm_tc(a, w, True, b, 1, out=c)
-        ts = []
-        for _ in range(10):
-            flush.fill_(0.0)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            ops.gemm_tc(a, w, True, b, 1, out=c)
-            e1.record()
-            torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1))
-        ms = float(np.mean(ts))
-        alg = 2.0 * M * 64 * 4 + 64 * 64 * 4
-        ach = alg / (ms * 1e-3) / 1e9
-        out[tag] = dict(rows=M, ms_per_launch=ms, algorithmic_bytes=alg, achieved=ach, frac=ach / peak,
-                        tflops_3xtf32=3 * 2.0 * M * 64 * 64 / (ms * 1e-3) / 1e12)
-    return dict(kernel='k_gemm_tc<64,2> (bignn_gemm_tc_f32, tcgen05 kind::tf32 x3)', bound='hbm', peak=peak, unit='GB/s',
-                traffic_gt_l2_shape=0.98e9, **out)
 
 
 def parallelism(eng, world):
@@ -362,10 +351,10 @@ def run_ours(args):
     out = dict(metric=METRIC, value=pairs_dev / (dev_ms * 1e-3), unit=UNIT, n_gpus=world, steps=args.steps,
                warmup=max(args.warmup, 3), ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling='strong',
                vs_baseline=None, dtype='f32', data='synthetic', impl='ours',
-               config=dict(workload_config(args.workload), l2='flushed between timed steps (256 MiB write)'
-                           if flush is not None else 'not flushed (working set < L2)',
-                           cuda_graph=bool(eng.use_cuda_graph),
-                           parallelism=parallelism(eng, world)),
+               config=workload_config(args.workload),
+               run=dict(l2='flushed between timed steps (256 MiB write)' if flush is not None
+                        else 'not flushed (working set < L2)', cuda_graph=bool(eng.use_cuda_graph),
+                        parallelism=parallelism(eng, world), lower_path=getattr(eng, 'lower_path', 'layers')),
                e2e=dict(value=pairs_e2e / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=eng.h2d_bytes_per_step,
                         d2h_bytes_per_step=eng.d2h_bytes_per_step, ms_per_step=e2e_ms / args.steps,
                         wall_ms_per_step=wall_ms / args.steps),
@@ -375,9 +364,56 @@ def run_ours(args):
     return out, (torch, B, peaks, dev, eng, data, model)
 
 
+def _numel(t):
+    return int(t.numel()) if t is not None and hasattr(t, 'numel') else 0
+
+
+def algorithmic_bytes(name, a):
+    """SURVEY 8(d) compulsory traffic of one C-ABI call (every input read once, every output written once; fp32
+    features, int32 indices), from the call's own arguments.  None = no convention stated for this entry."""
+    try:
+        if name == 'bignn_spmm_f32':
+            n, d, mode = a[6], a[7], a[8]
+            return 8.0 * d * n + 4.0 * _numel(a[1]) + 4.0 * (n + 1) + (4.0 * n if mode == 2 else 0.0)
+        if name == 'bignn_spmm_rows_f32':
+            n, d = a[6], a[8]
+            return 4.0 * d * (n + a[2].shape[0]) + 4.0 * _numel(a[1]) + 4.0 * (n + 1) + 4.0 * a[2].shape[0]
+        if name == 'bignn_spmm_planned_rows_f32':
+            n, d = a[13], a[15]
+            return 4.0 * d * (n + a[9].shape[0]) + 4.0 * _numel(a[1]) + 4.0 * (n + 1) + 4.0 * a[9].shape[0]
+        if name == 'bignn_gemm_tc_f32':
+            return 4.0 * (a[0] * a[2] + a[0] * a[1] + a[1] * a[2])
+        if name == 'bignn_gemm_tc_masked_f32':
+            return 4.0 * (a[0] * a[2] + 2.0 * a[0] * a[1] + a[1] * a[2])
+        if name == 'bignn_gemm_f32':
+            M, N, K = a[2], a[3], a[4]
+            return 4.0 * (M * K + M * N + K * N)
+        if name == 'bignn_dw_tc_f32':
+            return 4.0 * a[0] * (a[1] + a[2])
+        if name == 'bignn_bn_seg_fwd':
+            return 12.0 * a[6] * a[0].shape[0]
+        if name == 'bignn_bn_seg_bwd':
+            return 20.0 * a[8] * a[0].shape[0]
+        if name == 'bignn_readout_fwd':
+            return 4.0 * a[4] * (a[0].shape[0] + a[3])
+        if name == 'bignn_gin_layer_fwd':
+            # read X (gather; neighbours are re-read from L1/L2), write Y (+ Z and T when they are kept for the
+            # backward), indices, row pointers
+            rows, din, dout = a[0], a[1], a[2]
+            kept = (1 if a[-4] is not None else 0) + (1 if a[-3] is not None else 0)
+            return 4.0 * rows * (din + dout) + 4.0 * _numel(a[4]) + 4.0 * (rows + 1) + 4.0 * rows * (din * (a[-4] is not None) + dout * (a[-3] is not None))
+        if name == 'bignn_merge_build':
+            F, G, A, E = a[4], a[6], a[15], a[16]
+            return 4.0 * (A + 1) + 8.0 * E + 4.0 * A + 4.0 * (G + 1) + 8.0 * F * A
+    except Exception:
+        return None
+    return None
+
+
 def kernel_profile(torch, B, eng, steps=3, on_start=None):
-    """Per-entry-point device time of one eager step (CUDA events around every C-ABI call on the
-    launching stream) -- finds the dominant kernel and its average launch duration."""
+    """Per-entry-point device time of one EAGER step (CUDA events around every C-ABI call on the launching stream;
+    a pass of its own after the timed region, not the CUDA-graph replay that `value` times) -- finds the dominant
+    kernel of the step, its average launch duration and its algorithmic bytes."""
     lib = B._lib
     rec = []
     orig = lib.call
@@ -394,7 +430,13 @@ def kernel_profile(torch, B, eng, steps=3, on_start=None):
             key = 'bignn_spmm_f32[mode={},D={},rows={}]'.format(a[8], a[7], a[6])
         elif name == 'bignn_gemm_f32':
             key = 'bignn_gemm_f32[ta={},tb={},M={},N={},K={}]'.format(*a[:5])
-        rec.append((key, e0, e1))
+        elif name in ('bignn_gemm_tc_f32', 'bignn_gemm_tc_masked_f32'):
+            key = '{}[M={},N={},K={}]'.format(name, *a[:3])
+        elif name == 'bignn_dw_tc_f32':
+            key = 'bignn_dw_tc_f32[M={},Np={},Nq={}]'.format(*a[:3])
+        elif name == 'bignn_gin_layer_fwd':
+            key = 'bignn_gin_layer_fwd[rows={},Din={},Dout={}]'.format(*a[:3])
+        rec.append((key, e0, e1, algorithmic_bytes(name, a)))
         return r
     sb = eng.last_static_batch
     n0 = lib.launch_count()
@@ -403,7 +445,6 @@ def kernel_profile(torch, B, eng, steps=3, on_start=None):
     if on_start is not None:
         on_start()
     lib.call = timed
-    ops_mod = B.ops
     try:
         for _ in range(steps):
             eng._device_step(sb)
@@ -411,15 +452,42 @@ def kernel_profile(torch, B, eng, steps=3, on_start=None):
     finally:
         lib.call = orig
     agg = {}
-    for key, e0, e1 in rec:
-        d = agg.setdefault(key, [0.0, 0])
+    for key, e0, e1, nb in rec:
+        d = agg.setdefault(key, [0.0, 0, 0.0, True])
         d[0] += e0.elapsed_time(e1)
         d[1] += 1
+        if nb is None:
+            d[3] = False
+        else:
+            d[2] += nb
     total = sum(v[0] for v in agg.values())
-    rows = sorted(((k, v[0] / steps, v[1] // steps, v[0] / v[1]) for k, v in agg.items()), key=lambda r: -r[1])
-    return dict(total_ms_per_step=total / steps, launches_per_step=launches_per_step,
-                top=[dict(entry=k, ms_per_step=round(ms, 5), calls_per_step=c, ms_per_call=round(avg, 5),
-                          share=round(ms / (total / steps), 4)) for k, ms, c, avg in rows[:12]])
+    rows = sorted(agg.items(), key=lambda kv: -kv[1][0])
+    top = []
+    for k, (ms, calls, nbytes, known) in rows[:14]:
+        e = dict(entry=k, ms_per_step=round(ms / steps, 5), calls_per_step=calls // steps,
+                 ms_per_call=round(ms / calls, 5), share=round(ms / total, 4))
+        if known and nbytes > 0:
+            e['algorithmic_bytes_per_call'] = nbytes / calls
+            e['achieved_gbs'] = round(nbytes / (ms * 1e-3) / 1e9, 1)
+        top.append(e)
+    return dict(total_ms_per_step=total / steps, launches_per_step=launches_per_step, top=top,
+                note='eager pass with CUDA events around every C-ABI call (not the CUDA-graph replay that `value` times)')
+
+
+def step_roofline(prof, peaks):
+    """`roofline` of the dominant kernel of the TIMED step: the C-ABI entry with the largest share of the step's device
+    time; achieved = its algorithmic bytes per call / its average call duration (CUDA events in the eager pass)."""
+    peak = peaks.get('hbm_gbs', 6650.0)
+    for e in prof.get('top', []):
+        if 'achieved_gbs' in e:
+            return dict(kernel=e['entry'], bound='hbm', achieved=e['achieved_gbs'], peak=peak, unit='GB/s',
+                        frac=round(e['achieved_gbs'] / peak, 4), traffic=None, share_of_step=e['share'],
+                        ms_per_launch=e['ms_per_call'], algorithmic_bytes=e['algorithmic_bytes_per_call'],
+                        peak_source='MEASURED_PEAKS.json hbm_gbs (measured copy peak)' if 'hbm_gbs' in peaks
+                        else 'fallback 6650 GB/s',
+                        traffic_note='dram bytes of this kernel: see the ncu --set full summary under profiles/ '
+                                     '(not measurable inside an un-profiled run)')
+    return None
 
 
 def main():
@@ -428,12 +496,14 @@ def main():
     if args.impl == 'reference':
         if rank != 0:
             return
-        r = run_reference(args)
+        r = run_reference(args, device=args.ref_device)
         cfg = workload_config(args.workload)
         out = dict(metric=METRIC, value=r['value'], unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                    ms_per_step=r['ms_per_step'], higher_is_better=True, scaling='strong', vs_baseline=None, dtype='f32',
                    data='synthetic', impl='reference', config=cfg,
-                   cpu_baseline=dict(value=r['value'], unit=UNIT, cores=r['cores'], kind='port', sample=r['sample']),
+                   cpu_baseline=dict(value=r['value'], unit=UNIT, cores=r['cores'], kind='port', sample=r['sample'],
+                                     measured_sample_value=r['measured_sample_value'],
+                                     extrapolation_factor=r['extrapolation_factor'], device=args.ref_device),
                    e2e=dict(value=r['value'], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         print(json.dumps(out))
         return
@@ -448,20 +518,31 @@ def main():
         print(json.dumps(out))
         return
     out['gpu_launches'] = int(getattr(eng, 'launches_per_step', 0) * args.steps)
+    prof = None
     try:
         prof = kernel_profile(torch, B, eng)
-        out['gpu_launches'] = int(prof['launches_per_step'] * args.steps)
+        if not eng.use_cuda_graph:
+            out['gpu_launches'] = int(prof['launches_per_step'] * args.steps)
         out['kernel_profile'] = prof
     except Exception as e:          # the headline numbers above are already measured: report, do not lose them
         out['kernel_profile'] = dict(error=repr(e)[:300])
-    if args.gpus == 1 and not args.skip_rooflines:
-        out['roofline'] = spmm_roofline(torch, B, args.spmm_rows, peaks, dev)
-        out['roofline_step_dominant'] = dense_roofline(torch, B, int(data.packed.atom_ptr_host[-1]), peaks, dev)
-    if args.gpus == 1 and not args.skip_cpu:
-        cpu_args = argparse.Namespace(**vars(args))
-        r = run_reference(cpu_args, sample_steps=args.cpu_sample_steps)
+    if not args.skip_rooflines:
+        if prof is not None:
+            out['roofline'] = step_roofline(prof, peaks)
+        # the kernel BASELINE's metric names (segment SpMM) on a > L2 molecule-like graph, stand-alone
+        out['roofline_segment_spmm'] = spmm_roofline(torch, B, args.spmm_rows, peaks, dev)
+    if not args.skip_gpu_eager:
+        try:
+            r = run_reference(argparse.Namespace(**vars(args)), sample_steps=3, device=dev)
+            out['gpu_eager_baseline'] = dict(value=r['value'], unit=UNIT, kind='port on cuda (torch eager + index_add)',
+                                             sample=r['sample'], ms_per_step=r['ms_per_step'])
+        except Exception as e:
+            out['gpu_eager_baseline'] = dict(error=repr(e)[:300])
+    if not args.skip_cpu:
+        r = run_reference(argparse.Namespace(**vars(args)), sample_steps=args.cpu_sample_steps)
         out['cpu_baseline'] = dict(value=r['value'], unit=UNIT, cores=r['cores'], kind='port', sample=r['sample'],
-                                   ms_per_step=r['ms_per_step'])
+                                   ms_per_step=r['ms_per_step'], measured_sample_value=r['measured_sample_value'],
+                                   extrapolation_factor=r['extrapolation_factor'])
     print(json.dumps(out))
 
 

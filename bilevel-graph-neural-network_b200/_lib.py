@@ -97,12 +97,27 @@ def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith('.cu'))
 
 
+STAMP_PATH = LIB_PATH + '.srchash'
+
+
+def source_hash():
+    """Content hash of everything the library is built from (kernels, shared headers, the C-ABI header, the flags):
+    file times mean nothing after a snapshot copy to another box."""
+    import hashlib
+    h = hashlib.sha256(' '.join(NVCC_FLAGS).encode())
+    deps = sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith('.cuh')) + [HEADER]
+    for d in deps:
+        h.update(os.path.basename(d).encode())
+        with open(d, 'rb') as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def needs_build():
-    if not os.path.exists(LIB_PATH):
+    if not os.path.exists(LIB_PATH) or not os.path.exists(STAMP_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = sources() + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith('.cuh')] + [HEADER]
-    return any(os.path.getmtime(d) > t for d in deps)
+    with open(STAMP_PATH) as f:
+        return f.read().strip() != source_hash()
 
 
 def build(force=False, verbose=False):
@@ -121,6 +136,8 @@ def build(force=False, verbose=False):
     if r.returncode != 0:
         raise RuntimeError('nvcc failed:\n' + r.stdout)
     os.replace(tmp, LIB_PATH)
+    with open(STAMP_PATH, 'w') as f:
+        f.write(source_hash())
     return LIB_PATH
 
 

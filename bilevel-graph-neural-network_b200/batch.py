@@ -19,16 +19,20 @@ def unique_graphs_in_order(batch_gids):
     return seen
 
 
-def sample_negative_pairs(dataset, positive_gids, sampled_gids, num_negative_samples=1, rng=np.random):
+def sample_negative_pairs(dataset, positive_gids, sampled_gids, num_negative_samples=1, rng=np.random,
+                          enforce_negative=True, amongst_same_graphs=True):
     """src/batch.py:61-103, verbatim in its decisions: target count, cyclic `orig` walk, one
-    `np.random.choice(sampled_gids, size=1)` per attempt, the five rejection tests, and the
+    `np.random.choice(negative_gids, size=1)` per attempt, the five rejection tests, and the
     CPython set -> dict -> list result order.  Only the membership structure is hoisted:
-    the train-edge set is built once per dataset, not once per call."""
+    the train-edge set is built once per dataset, not once per call.
+    enforce_negative=False skips the rejection loop (src/batch.py:88); amongst_same_graphs=False
+    (FLAGS.enforce_sampling_amongst_same_graphs, :69-79) draws candidates from every drug and lifts the pair cap."""
     neg = set()
     gid_ind = 0
     n = len(sampled_gids)
     gs_map = dataset.gs_map
-    max_pairs = ((n * (n - 1)) / 2) - len(positive_gids)
+    max_pairs = ((n * (n - 1)) / 2) - len(positive_gids) if amongst_same_graphs else float('inf')
+    negative_gids = sampled_gids if amongst_same_graphs else list(gs_map.keys())
     edges = dataset.edge_set()
     batch_pos = set((gs_map[int(a)], gs_map[int(b)]) for a, b in positive_gids)
     target = min(max_pairs, len(positive_gids) * num_negative_samples)
@@ -41,13 +45,13 @@ def sample_negative_pairs(dataset, positive_gids, sampled_gids, num_negative_sam
         if len(neg) == target:
             break
         orig = sampled_gids[gid_ind % n]
-        cand = rng.choice(sampled_gids, size=1)[0]
+        cand = rng.choice(negative_gids, size=1)[0]
         gid_ind += 1
-        while ((orig, cand) in neg or (cand, orig) in neg or orig == cand
-               or is_pos(orig, cand) or is_pos(cand, orig)):
+        while enforce_negative and ((orig, cand) in neg or (cand, orig) in neg or orig == cand
+                                    or is_pos(orig, cand) or is_pos(cand, orig)):
             orig = sampled_gids[gid_ind % n]
             gid_ind += 1
-            cand = rng.choice(sampled_gids, size=1)[0]
+            cand = rng.choice(negative_gids, size=1)[0]
         neg.add((orig, cand))
     ordered = {k: 0 for k in neg}
     return np.asarray(list(ordered.keys()), np.int64).reshape(-1, 2)
@@ -79,7 +83,9 @@ class BatchData(object):
             assert sampled_gids is not None
             self.sampled_gids = sampled_gids
             neg = sample_negative_pairs(dataset, self.positive_pair_gids, sampled_gids,
-                                        flags.num_negative_samples)
+                                        flags.num_negative_samples, enforce_negative=enforce_negative_sampling,
+                                        amongst_same_graphs=getattr(flags, 'enforce_sampling_amongst_same_graphs',
+                                                                    True))
             if len(neg) > 0:
                 self.negative_pair_gids = neg
                 self.batch_gids = np.concatenate((self.batch_gids, neg))

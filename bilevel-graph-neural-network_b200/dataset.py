@@ -36,7 +36,11 @@ class _PairTable(object):
         lut_vals = np.fromiter(gs_map.values(), np.int64, len(gs_map))
         order = np.argsort(lut_keys)
         lut_keys, lut_vals = lut_keys[order], lut_vals[order]
-        rows = lut_vals[np.searchsorted(lut_keys, gids)]
+        idx = np.minimum(np.searchsorted(lut_keys, gids), max(len(lut_keys) - 1, 0))
+        if gids.size and not np.array_equal(lut_keys[idx], gids):
+            raise KeyError('pair table: {} pair entries name a gid that is not in the dataset'.format(
+                int((lut_keys[idx] != gids).sum())))
+        rows = lut_vals[idx]
         key = rows[:, 0] * n + rows[:, 1]
         order = np.argsort(key, kind='stable')
         self.keys = key[order]

@@ -90,15 +90,16 @@ def sum_disjoint_rows(x, group=None):
     return _SumDisjointRows.apply(x, group)
 
 
-def all_reduce_grads(params, group=None):
+def all_reduce_grads(params, group=None, extra=None):
     """One flat SUM all-reduce over the gradients of `params` (lower-level weights: each rank
-    holds the partial sum over its own chunks)."""
+    holds the partial sum over its own chunks).  `extra`: a small fp32 vector that rides along (the pair-batch
+    checksum); its rank sum is returned."""
     if not is_dist():
-        return
+        return None
     grads = [p.grad for p in params if p.grad is not None]
-    if not grads:
-        return
-    flat = torch.cat([g.reshape(-1) for g in grads])
+    if not grads and extra is None:
+        return None
+    flat = torch.cat([g.reshape(-1) for g in grads] + ([extra.reshape(-1)] if extra is not None else []))
     with _timed('grad_all_reduce'):
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     views, off = [], 0
@@ -106,7 +107,9 @@ def all_reduce_grads(params, group=None):
         n = g.numel()
         views.append(flat[off:off + n].view_as(g))
         off += n
-    torch._foreach_copy_(grads, views)               # one multi-tensor launch instead of one copy per gradient
+    if grads:
+        torch._foreach_copy_(grads, views)           # one multi-tensor launch instead of one copy per gradient
+    return flat[off:] if extra is not None else None
 
 
 def gather_chunk_stats(stats_local, s_max, group=None):

@@ -38,11 +38,20 @@ class _StaticPairBatch(object):
         self.merge_higher_level = {}
         self.ids = torch.zeros((P, 2), dtype=torch.int32, device=device)
         self.y = torch.zeros(P, dtype=torch.float32, device=device)
+        # decoder entry CSR (drug row -> the pair entries that gather it): the 2P sorted rows come from the host,
+        # the N+1 pointer array is derived from them ON THE DEVICE each step (`refresh`), not copied
+        self.e_rows = torch.zeros(2 * P, dtype=torch.int32, device=device)
         self.e_ptr = torch.zeros(N + 1, dtype=torch.int32, device=device)
         self.e_idx = torch.zeros(2 * P, dtype=torch.int32, device=device)
+        self._bounds = torch.arange(N + 1, dtype=torch.int32, device=device)
         self.entry_csr = CSR(self.e_ptr, self.e_idx, N)
+        self.chk = torch.zeros(2, dtype=torch.float32, device=device)      # pair-batch checksum (multi-GPU agreement)
         self.batch_gids = np.zeros((P, 2), np.int64)
         self.preds = None
+
+    def refresh(self):
+        """e_ptr[r] = number of entries whose row is < r (capturable; runs at the head of every step)."""
+        torch.searchsorted(self.e_rows, self._bounds, out_int32=True, out=self.e_ptr)
 
     def y_true_device(self, as_int=False):
         return self.y.to(torch.int32) if as_int else self.y
@@ -61,14 +70,16 @@ class _Staging(object):
         pin = dict(pin_memory=True) if cuda else {}
         self.ids = torch.zeros((P, 2), dtype=torch.int32, **pin)
         self.y = torch.zeros(P, dtype=torch.float32, **pin)
-        self.e_ptr = torch.zeros(N + 1, dtype=torch.int32, **pin)
+        self.e_rows = torch.zeros(2 * P, dtype=torch.int32, **pin)
         self.e_idx = torch.zeros(2 * P, dtype=torch.int32, **pin)
+        self.chk = torch.zeros(2, dtype=torch.float32, **pin)
         self.loss = torch.zeros((), dtype=torch.float32, **pin)
+        self.chk_sum = torch.zeros(2, dtype=torch.float32, **pin)
         self.event = torch.cuda.Event() if cuda else None
         self.busy = False
 
     def nbytes_in(self):
-        return sum(t.numel() * t.element_size() for t in (self.ids, self.y, self.e_ptr, self.e_idx))
+        return sum(t.numel() * t.element_size() for t in (self.ids, self.y, self.e_rows, self.e_idx, self.chk))
 
 
 class BiGNNEngine(object):
@@ -114,7 +125,10 @@ class BiGNNEngine(object):
             raise NotImplementedError('partition_upper: only GCN upper levels are row-partitioned')
         self.upper = PartitionedInteractionGraph(data.interaction_combo_nxgraph, self.rank, self.world,
                                                  group) if partition_upper else None
-        self._upper_partial = [p for l in convs for p in l.conv.parameters()] if partition_upper else []
+        # parameters evaluated on this rank's rows only hold partial gradient sums: the conv weights / biases and a
+        # parametric activation (PReLU) join the flat all-reduce; BatchNorm's come out rank-summed already
+        self._upper_partial = [p for l in convs for m in (l.conv, l.act) for p in m.parameters()] \
+            if partition_upper else []
         self._n_pair_rows = self.upper.n_pad if self.upper is not None else data.N
         # a drug that appears in two chunks is overwritten by the later one in the reference
         # (layers_aggregation.py:72-74); earlier duplicates go to a trash row N
@@ -139,6 +153,8 @@ class BiGNNEngine(object):
         self._stagings = {}
         self._n_staging = n_staging
         self._step_idx = 0
+        self._chk_sum = torch.zeros(2, dtype=torch.float32, device=self.device)
+        self.init_x_static = None      # the last step's init_x (detached copy; what validation scores, src/train.py:185-220)
         self.h2d_bytes_per_step = 0
         self.d2h_bytes_per_step = 4
 
@@ -166,18 +182,27 @@ class BiGNNEngine(object):
         model = self.model
         pooled, _ = self.lower_pass()
         self._ig().init_x = pooled[:self.data.N]
+        with torch.no_grad():                                # engine-owned copy: survives CUDA-graph pool reuse
+            if self.init_x_static is None:
+                self.init_x_static = torch.empty_like(pooled[:self.data.N])
+            self.init_x_static.copy_(pooled[:self.data.N])
         model.use_layers = 'higher_layers'
         model.acts = [None]
         for layer in model.higher_level_layers:
             model.acts.append(layer(model.acts[-1], pair_batch, model))
         return model.acts[-1]
 
-    def _sync_lower(self):
+    def _sync_lower(self, pair_batch=None):
         """after backward on a sharded lower level: sum the partial weight gradients and replay
         the BatchNorm running-buffer updates in global chunk order."""
         lower = [p for l in self.model.init_layers for p in l.parameters()]
         # + the conv weights / biases of a row-partitioned upper level (partial sums over a rank's rows)
-        bdist.all_reduce_grads(lower + self._upper_partial, self.group)
+        # + the pair-batch checksum [c, c^2]: every rank must have staged the SAME pairs (the scorer and the upper
+        #   level treat their gradients as replicated); world * sum(c^2) == (sum c)^2 iff all ranks agree
+        extra = pair_batch.chk if pair_batch is not None and hasattr(pair_batch, 'chk') else None
+        red = bdist.all_reduce_grads(lower + self._upper_partial, self.group, extra=extra)
+        if red is not None:
+            self._chk_sum.copy_(red)
         s_max = max(hi - lo for lo, hi in self.chunk_shards)
         if self._bn_sink:
             # the per-chunk statistics of ALL BatchNorm layers travel in one all-gather
@@ -197,10 +222,11 @@ class BiGNNEngine(object):
 
     def _device_step(self, pair_batch):
         self.optimizer.zero_grad(set_to_none=True)
+        pair_batch.refresh()
         loss = self.forward(pair_batch)
         loss.backward()
         if self.world > 1:
-            self._sync_lower()
+            self._sync_lower(pair_batch)
         self.optimizer.step()
         self._detach_init_x()
         return loss.detach()
@@ -230,10 +256,7 @@ class BiGNNEngine(object):
         sb = _StaticPairBatch(self.data, P, self.device, self.upper)
         # a valid dummy batch for warm-up: pairs (0,1) with label 0
         sb.ids[:, 1] = 1
-        e_ptr = np.zeros(self._n_pair_rows + 1, np.int64)
-        e_ptr[1:] = P
-        e_ptr[2:] = 2 * P
-        sb.e_ptr.copy_(torch.as_tensor(e_ptr.astype(np.int32)))
+        sb.e_rows[P:] = 1
         sb.e_idx.copy_(torch.as_tensor(np.concatenate([np.arange(0, 2 * P, 2), np.arange(1, 2 * P, 2)]).astype(np.int32)))
         had_state = len(self.optimizer.state) > 0
         snap = self._snapshot()
@@ -299,11 +322,11 @@ class BiGNNEngine(object):
         st.ids.numpy()[:] = flat.reshape(P, 2)
         st.y.numpy()[:] = labels
         order = np.argsort(flat, kind='stable')
-        cnt = np.bincount(flat, minlength=self._n_pair_rows)
-        ep = st.e_ptr.numpy()
-        ep[0] = 0
-        np.cumsum(cnt, out=ep[1:])
+        st.e_rows.numpy()[:] = flat[order]
         st.e_idx.numpy()[:] = order
+        c = float((int(np.dot(flat % 1021, np.arange(1, flat.shape[0] + 1) % 1019)) +
+                   int(np.asarray(labels, np.int64).sum())) % 1009)
+        st.chk.numpy()[:] = (c, c * c)
         return st, P
 
     def step_staged(self, st, P):
@@ -324,13 +347,17 @@ class BiGNNEngine(object):
                 sb = self._graphs[('eager', P)] = _StaticPairBatch(self.data, P, self.device, self.upper)
         sb.ids.copy_(st.ids, non_blocking=True)
         sb.y.copy_(st.y, non_blocking=True)
-        sb.e_ptr.copy_(st.e_ptr, non_blocking=True)
+        sb.e_rows.copy_(st.e_rows, non_blocking=True)
         sb.e_idx.copy_(st.e_idx, non_blocking=True)
+        sb.chk.copy_(st.chk, non_blocking=True)
         if use_graph:
             g.replay()
         else:
             loss = self._device_step(sb)
         st.loss.copy_(loss, non_blocking=True)
+        if self.world > 1:
+            st.chk_sum.copy_(self._chk_sum, non_blocking=True)
+        st.world = self.world
         if st.event is not None:
             st.event.record()
         st.busy = True
@@ -344,6 +371,13 @@ class BiGNNEngine(object):
         if st.event is not None:
             st.event.synchronize()
         st.busy = False
+        w = getattr(st, 'world', 1)
+        if w > 1:
+            a, b = float(st.chk_sum[0]), float(st.chk_sum[1])
+            if abs(w * b - a * a) > 0.5:
+                raise RuntimeError('BiGNNEngine: the ranks staged different pair batches in this step (every rank must '
+                                   'sample the same pairs: seed numpy and torch identically on all ranks, see '
+                                   'INTEGRATION.md)')
         return float(st.loss)
 
     @torch.no_grad()
@@ -357,13 +391,20 @@ class BiGNNEngine(object):
         model.eval()
         try:
             ig = self._ig()
-            if recompute_init_x or ig.init_x is None:
-                pooled, _ = self.lower_pass()
+            if recompute_init_x or (self.init_x_static is None and ig.init_x is None):
+                pooled, _ = self.lower_pass()                         # eval-mode BatchNorm (running statistics)
                 ig.init_x = pooled[:self.data.N]
+            elif self.init_x_static is not None:
+                ig.init_x = self.init_x_static                        # the last TRAIN step's init_x, as the
+                                                                      # reference's validation uses (train.py:185-220)
             flat = self._pair_rows(gid_pairs)
             P = flat.shape[0] // 2
             sb = _StaticPairBatch(self.data, P, self.device, self.upper)
             sb.ids.copy_(torch.as_tensor(flat.reshape(P, 2).astype(np.int32)))
+            order = np.argsort(flat, kind='stable')
+            sb.e_rows.copy_(torch.as_tensor(flat[order].astype(np.int32)))
+            sb.e_idx.copy_(torch.as_tensor(order.astype(np.int32)))
+            sb.refresh()
             model.acts = [None]
             for layer in model.higher_level_layers[:-1]:           # everything but the loss
                 model.acts.append(layer(model.acts[-1], sb, model))

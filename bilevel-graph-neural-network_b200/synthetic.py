@@ -118,21 +118,32 @@ WORKLOADS = {
 }
 
 
-def cached_workload(name, seed=0, cache_dir=None):
+def cached_workload(name, seed=0, cache_dir=None, writer=True, wait_s=600.0):
     """bignn_workload(**WORKLOADS[name]) through an .npz cache in the temp directory (the 20 M-edge graph
-    takes about a minute to draw; every rank of a multi-GPU job and the CPU baseline need the same arrays)."""
+    takes about a minute to draw; every rank of a multi-GPU job and the CPU baseline need the same arrays).
+    writer=False (ranks other than local rank 0): wait for the writer's file instead of drawing the same graph
+    N times at once; falls back to drawing it after `wait_s`."""
     import os
     import tempfile
+    import time
     w = WORKLOADS[name]
     if w['N'] < 10_000:
         return bignn_workload(seed=seed, **w)
     path = os.path.join(cache_dir or tempfile.gettempdir(), 'bignn_synth_{}_{}.npz'.format(name, seed))
-    if os.path.exists(path):
-        try:
-            z = np.load(path)
-            return {k: z[k] for k in z.files}
-        except Exception:
-            pass
+
+    def load():
+        z = np.load(path)
+        return {k: z[k] for k in z.files}
+    t0 = time.time()
+    while True:
+        if os.path.exists(path):
+            try:
+                return load()
+            except Exception:
+                pass
+        if writer or time.time() - t0 > wait_s:
+            break
+        time.sleep(0.5)
     out = bignn_workload(seed=seed, **w)
     tmp = '{}.{}.tmp.npz'.format(path, os.getpid())
     np.savez(tmp, **out)

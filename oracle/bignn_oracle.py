@@ -364,7 +364,7 @@ def gin_conv(x, ei, P, p, act, prelu_w=None):
 def _with_self_loops(ei, n):
     row, col = ei
     keep = row != col
-    loop = torch.arange(n, dtype=torch.long)
+    loop = torch.arange(n, dtype=torch.long, device=row.device)
     return torch.cat([row[keep], loop]), torch.cat([col[keep], loop])
 
 
@@ -373,7 +373,7 @@ def gcn_conv(x, ei, P, p):
     n = x.shape[0]
     h = x @ P[p + '.conv.weight']
     row, col = _with_self_loops(ei, n)
-    w = torch.ones(row.shape[0], dtype=h.dtype)
+    w = torch.ones(row.shape[0], dtype=h.dtype, device=h.device)
     deg = _scatter_rows(w, row, n)
     dinv = deg.pow(-0.5)
     dinv[dinv == float('inf')] = 0
@@ -394,7 +394,7 @@ def gat_conv(x, ei, P, p, softmax_group='source', negative_slope=0.2):
     a = (h.index_select(0, col) * att[:d]).sum(-1) + (h.index_select(0, row) * att[d:]).sum(-1)
     a = F.leaky_relu(a, negative_slope)
     grp = row if softmax_group == 'source' else col
-    amax = torch.full((n,), -float('inf'), dtype=a.dtype).scatter_reduce(0, grp, a, 'amax')
+    amax = torch.full((n,), -float('inf'), dtype=a.dtype, device=a.device).scatter_reduce(0, grp, a, 'amax')
     e = (a - amax[grp]).exp()
     s = _scatter_rows(e, grp, n)
     alpha = e / (s[grp] + 1e-16)
@@ -485,13 +485,14 @@ class OracleModel(object):
     """Sequential layer list driven by the reference's spec strings
     (model/model.py:34-62), over a dict of leaf tensors named like the state_dict."""
 
-    def __init__(self, specs, state, dtype=torch.float32, gat_group='source'):
+    def __init__(self, specs, state, dtype=torch.float32, gat_group='source', device='cpu'):
         self.specs = specs
         self.dtype = dtype
+        self.device = torch.device(device)      # 'cuda': the same eager code on the GPU (bench.py gpu_eager_baseline)
         self.gat_group = gat_group
         self.P = {}
         for k, v in state.items():
-            v = v.clone()
+            v = v.clone().to(self.device)
             if v.is_floating_point():
                 v = v.to(dtype)
                 if not ('running_' in k or k.endswith('.eps')):
@@ -526,7 +527,7 @@ class OracleModel(object):
     def meta_layer(self, h, etype_eis, p, lf):
         """MetaLayerWrapper + NodeModelAggrByEdge (model/layers_meta.py:39-47,74-79)."""
         kind = lf['node_model'].split('_')[0]
-        outs = torch.zeros(h.shape[0], int(lf['output_dim']), dtype=h.dtype)
+        outs = torch.zeros(h.shape[0], int(lf['output_dim']), dtype=h.dtype, device=h.device)
         for e, ei in enumerate(etype_eis):
             q = p + '.node_model.GNNS.%d' % e
             view = {q + '.conv.' + k: self.P[q + '.' + k] for k in ('weight', 'bias', 'att') if (q + '.' + k) in self.P}
@@ -564,9 +565,10 @@ def all_drug_pass(model, ds, batch_size=64, record=None):
     for c, pairs in enumerate(chunks):
         gids = unique_graphs_in_order(pairs)
         m = merge_graphs(ds, gids)
-        x = torch.from_numpy(m['x']).to(model.dtype)
-        ei = torch.from_numpy(m['edge_index'])
-        batch = torch.from_numpy(m['batch'])
+        dev = getattr(model, 'device', 'cpu')
+        x = torch.from_numpy(m['x']).to(model.dtype).to(dev)
+        ei = torch.from_numpy(m['edge_index']).to(dev)
+        batch = torch.from_numpy(m['batch']).to(dev)
         acts, pooled = model.lower(x, ei, batch, len(gids))
         for g, i in m['gids_to_batch_ind'].items():
             rows_out[ds.gs_map[g]] = pooled[i]
@@ -578,10 +580,11 @@ def all_drug_pass(model, ds, batch_size=64, record=None):
 def train_step_forward(model, ds, batch_gids, y, batch_size=64, record=None):
     """model_forward + Model.forward of one Bi-GNN step (src/train.py:75-108,178)."""
     init_x = all_drug_pass(model, ds, batch_size, record)
-    ddi = torch.from_numpy(np.stack([ds.ddi_row, ds.ddi_col]))
-    rows = torch.from_numpy(np.vectorize(ds.gs_map.get)(np.asarray(batch_gids)).astype(np.int64))
-    et = [torch.from_numpy(np.stack([r, c])) for r, c in ds.etypes.values()] if ds.etypes else None
-    acts, pred, loss = model.upper(init_x, ddi, rows, torch.from_numpy(np.asarray(y)), etype_eis=et)
+    dev = getattr(model, 'device', 'cpu')
+    ddi = torch.from_numpy(np.stack([ds.ddi_row, ds.ddi_col])).to(dev)
+    rows = torch.from_numpy(np.vectorize(ds.gs_map.get)(np.asarray(batch_gids)).astype(np.int64)).to(dev)
+    et = [torch.from_numpy(np.stack([r, c])).to(dev) for r, c in ds.etypes.values()] if ds.etypes else None
+    acts, pred, loss = model.upper(init_x, ddi, rows, torch.from_numpy(np.asarray(y)).to(dev), etype_eis=et)
     return init_x, acts, pred, loss
 
 
@@ -623,10 +626,10 @@ class OracleTrainer(object):
     baseline: per step the all-drug lower pass (per-graph conversion + merge + 5 layers per
     chunk), positive/negative sampling, the upper pass, backward and Adam."""
 
-    def __init__(self, ds, specs, state, batch_size=64, dtype=torch.float32):
+    def __init__(self, ds, specs, state, batch_size=64, dtype=torch.float32, device='cpu'):
         from torch.utils.data import DataLoader
         self.ds, self.bs = ds, batch_size
-        self.model = OracleModel(specs, state, dtype)
+        self.model = OracleModel(specs, state, dtype, device=device)
         self.adam = {}
         self.items = torch.as_tensor(np.asarray(sorted(map(tuple, ds.train_pairs.tolist())), np.int64))
         self.loader = DataLoader(self.items, batch_size=batch_size, shuffle=True)

@@ -51,11 +51,14 @@ def _worker(rank, world, port, out_dir, partition_upper=False):
     st, P = eng.stage_pairs(z['batch_gids'], z['y_true'].astype(np.float32))
     from bignn_b200.engine import _StaticPairBatch
     sb = _StaticPairBatch(data, P, data.device, eng.upper)
-    sb.ids.copy_(st.ids); sb.y.copy_(st.y); sb.e_ptr.copy_(st.e_ptr); sb.e_idx.copy_(st.e_idx)
+    sb.ids.copy_(st.ids); sb.y.copy_(st.y); sb.e_rows.copy_(st.e_rows); sb.e_idx.copy_(st.e_idx); sb.chk.copy_(st.chk)
+    sb.refresh()
     loss = eng.forward(sb)
     loss.backward()
     if world > 1:
-        eng._sync_lower()
+        eng._sync_lower(sb)
+        w, (a, b) = world, eng._chk_sum.tolist()
+        assert abs(w * b - a * a) < 0.5, 'ranks disagree on the pair batch'
     ig = eng._ig()
     res = {'loss': float(loss.detach()), 'chunks': np.asarray(eng.my_chunks),
            'init_x': (ig.init_x_full if eng.upper is not None else ig.init_x).detach().numpy()}

@@ -1,17 +1,14 @@
 """Lower-level-only model (model='lower_level_gnn', the LL-GNN baseline = the model of BASELINE config 3) on the GPU
 against the reference's own recorded step (tests/golden/bignn_ll_gnn_step.npz).  The same fixture is green for the
-oracle and for the host path on the CPU stand-in backend; THIS file was written after the round's GPU budget was
-spent and has never run on a GPU, so it only runs when BIGNN_RUN_UNVALIDATED=1 (tools/gpu_validate.sh sets it) --
-remove the gate once it has been seen green."""
+oracle and for the host path on the CPU stand-in backend.  First seen green on a B200 in round 2
+(gpurun_out/pytest_r2a.log: 146 passed)."""
 import os
 
 import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get('BIGNN_RUN_UNVALIDATED') != '1',
-                                 reason='never run on a GPU yet: set BIGNN_RUN_UNVALIDATED=1')]
+pytestmark = [pytest.mark.gpu]
 
 import bignn_b200 as B
 from oracle import bignn_oracle as O
