@@ -20,7 +20,7 @@ LIB_DIR = os.path.join(HERE, '_C')
 LIB_PATH = os.path.join(LIB_DIR, 'libbignn_b200.so')
 HEADER = os.path.join(ROOT, 'include', 'bignn_b200.h')
 
-ABI_VERSION = 2          # include/bignn_b200.h BIGNN_ABI_VERSION (2: bn_seg_bwd input_act, spmm_planned_rows n_big)
+ABI_VERSION = 3          # include/bignn_b200.h BIGNN_ABI_VERSION (3: fused GIN layer, readout with folded BatchNorm)
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC']
@@ -61,6 +61,11 @@ SIGNATURES = {
     'bignn_bn_rows_bwd_apply': ('i', 'plplpl' 'iii' 'ppp' 'pl' 'i' 's'),
     'bignn_readout_fwd': ('i', 'pl' 'pii' 'i' 'p' 'pli' 's'),
     'bignn_readout_bwd': ('i', 'pli' 'p' 'pii' 'i' 'pl' 'i' 's'),
+    'bignn_readout_fold_fwd': ('i', 'pl' 'pii' 'i' 'p' 'ppp' 'pli' 's'),
+    'bignn_gin_layer_supported': ('i', 'ii'),
+    'bignn_gin_layer_stat_records': ('l', 'ii'),
+    'bignn_gin_layer_fwd': ('i', 'iii' 'pp' 'pl' 'pp' 'pip' 'f' 'pppp' 'ii' 'pl' 'pl' 'pl' 'p' 's'),
+    'bignn_gin_bn_finalize': ('i', 'ppii' 'f' 'pp' 'pp' 'p' 'pp' 's'),
     'bignn_pair_gather_norm_fwd': ('i', 'pl' 'pii' 'pl' 'p' 's'),
     'bignn_pair_gather_norm_bwd': ('i', 'pl' 'pii' 'pl' 'p' 'pl' 's'),
     'bignn_bce_fwd': ('i', 'ppips'),
@@ -192,7 +197,7 @@ def call(name, *args):
     if codes.endswith('s'):
         cargs.append(torch.cuda.current_stream().cuda_stream)
     out = getattr(lib, name)(*cargs)
-    if res == 'i' and name not in ('bignn_abi_version', 'bignn_gemm_tc_supported', 'bignn_dw_tc_supported') and out != 0:
+    if res == 'i' and name not in ('bignn_abi_version', 'bignn_gemm_tc_supported', 'bignn_dw_tc_supported', 'bignn_gin_layer_supported') and out != 0:
         raise RuntimeError('{} failed with status {}: {}'.format(name, out, error_string(out)))
     return out
 

@@ -1,0 +1,509 @@
+// One lower-level GIN layer as ONE kernel (see include/bignn_b200.h: bignn_gin_layer_fwd).
+//
+//   z_i = (1+eps) x_i + sum_{j in N(i)} x_j        x = BatchNorm-affine of the producer layer's output, folded
+//   t   = act(z W1^T + b1)                         into the aggregation (a*S + b*(1+eps+deg), never materialised)
+//   y   = act(t W2^T + b2)                         + per-chunk BatchNorm partial sums (fp64) of y from the epilogue
+//
+// Replaces model/layers.py:42-57 (GINConv -> act -> BatchNorm1d): PyG's index_select + scatter_add, two
+// nn.Linear launches, two activation launches and the BatchNorm statistics pass.  Traffic per layer: the
+// rows of X once (neighbour rows of a molecule are re-read from L1/L2), the rows of Y once, the CSR.
+//
+// Persistent, warp-specialised, one CTA per SM, 128-row tiles, two operand slots in shared memory:
+//   * producer warps  aggregate the tile's rows straight from global memory (8 lanes per row, two 128-bit
+//                     column slots per lane, 4 neighbour rows in flight, ascending neighbour order, unfused
+//                     mul/add: the arithmetic of bignn_spmm_f32's GIN mode) and write z into the slot as the
+//                     K-major SWIZZLE_128B A operand, raw fp32 (= the TF32 hi part) plus the lo part;
+//   * one MMA warp    issues tcgen05.mma kind::tf32 (3xTF32: hi*hi over two rotating TMEM accumulators,
+//                     lo*hi + hi*lo into a third) for z W1^T, then -- once the epilogue warps have turned the
+//                     first accumulator into t inside the same slot -- for t W2^T;
+//   * epilogue warps  (one per TMEM lane quadrant) read the accumulators with tcgen05.ld, add bias, apply the
+//                     activation, write t back as an operand, and finally stage y in the slot for coalesced
+//                     128-bit stores, summing the BatchNorm statistics of the rows they store.
+// mbarriers: z_full/z_empty per slot (producers <-> MMA / epilogue), t_full (epilogue -> MMA), m1/m2 (tcgen05.commit).
+// Weights (hi and lo parts of W1, W2) stay resident in shared memory for every tile of the CTA.
+#include "tc_common.cuh"
+
+namespace bignn {
+
+constexpr int GL_D = 64;                       // output width (and padded input width)
+constexpr int GL_SLOT = 4 * TC_BM * 128;       // [hi ch0][hi ch1][lo ch0][lo ch1], 16 KB each
+constexpr int GL_W = 2 * GL_D * 128;           // one weight part: two K chunks of [64 x 128 B]
+constexpr int GL_SMEM = 2 * GL_SLOT + 4 * GL_W + 1024;
+constexpr int GL_EPI_WARPS = 4;
+constexpr int GL_NA = 2;                       // rotating main accumulators (as k_gemm_tc<64, .>)
+constexpr int GL_ACC_COLS = (GL_NA + 1) * GL_D;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float4 f4z() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void add4(float4& a, const float4& v) {
+  a.x = __fadd_rn(a.x, v.x); a.y = __fadd_rn(a.y, v.y); a.z = __fadd_rn(a.z, v.z); a.w = __fadd_rn(a.w, v.w);
+}
+__device__ __forceinline__ uint4 lo_part(const float4& x) {
+  uint4 l;
+  l.x = __float_as_uint(x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u)) & 0xffffe000u;
+  l.y = __float_as_uint(x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u)) & 0xffffe000u;
+  l.z = __float_as_uint(x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u)) & 0xffffe000u;
+  l.w = __float_as_uint(x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u)) & 0xffffe000u;
+  return l;
+}
+
+struct GinLayerArgs {
+  int rows, din, n_tiles;
+  const int32_t* row_ptr; const int32_t* col_idx;
+  const float* X; int64_t ldx;
+  const float* fold_a; const float* fold_b;          // [S, din] or null
+  const int32_t* chunk_row_ptr; const int32_t* tile_chunk0;
+  float self_coef;
+  const float* W1; const float* b1; const float* W2; const float* b2;
+  int act_inner, act_outer;
+  float* Z; int64_t ldz; float* T; int64_t ldt; float* Y; int64_t ldy;
+  double* stat_parts;                                 // [(n_tiles + S)][2][64] or null
+};
+
+// issue the 3xTF32 MMAs of one [128 x K] x [K x 64] product (A in `slot`, B = resident weight parts)
+__device__ __forceinline__ void issue_gemm(uint32_t tmem_acc, const uint8_t* a_hi, const uint8_t* a_lo,
+                                           const uint8_t* b_hi, const uint8_t* b_lo, int K, uint32_t idesc) {
+  int ks = 0;
+#pragma unroll
+  for (int ch = 0; ch < 2; ++ch) {
+    if (ch * TC_KC >= K) break;
+    const uint64_t da_hi = umma_desc_k_sw128(smem_u32(a_hi + ch * (TC_BM * 128)));
+    const uint64_t da_lo = umma_desc_k_sw128(smem_u32(a_lo + ch * (TC_BM * 128)));
+    const uint64_t db_hi = umma_desc_k_sw128(smem_u32(b_hi + ch * (GL_D * 128)));
+    const uint64_t db_lo = umma_desc_k_sw128(smem_u32(b_lo + ch * (GL_D * 128)));
+#pragma unroll
+    for (int k = 0; k < TC_KC / 8; ++k, ++ks) {
+      if (ch * TC_KC + k * 8 >= K) break;
+      const uint64_t adv = (uint64_t)((k * 32) >> 4);
+      umma_tf32(tmem_acc + (uint32_t)((ks % GL_NA) * GL_D), da_hi + adv, db_hi + adv, idesc, ks >= GL_NA ? 1u : 0u);
+      umma_tf32(tmem_acc + (uint32_t)(GL_NA * GL_D), da_lo + adv, db_hi + adv, idesc, ks > 0 ? 1u : 0u);
+      umma_tf32(tmem_acc + (uint32_t)(GL_NA * GL_D), da_hi + adv, db_lo + adv, idesc, 1u);
+    }
+  }
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+k_gin_layer_fwd(const GinLayerArgs p) {
+  constexpr int N_WARPS = THREADS / 32;
+  constexpr int N_PROD_WARPS = N_WARPS - GL_EPI_WARPS - 1;
+  constexpr int N_GROUPS = N_PROD_WARPS * 4;           // 8-lane groups
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* w1_hi = smem + 2 * GL_SLOT;
+  uint8_t* w1_lo = w1_hi + GL_W;
+  uint8_t* w2_hi = w1_lo + GL_W;
+  uint8_t* w2_lo = w2_hi + GL_W;
+  __shared__ uint64_t z_full[2], z_empty[2], t_full, m1_done, m2_done;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float b1_s[GL_D], b2_s[GL_D];
+  __shared__ double red_s[2][8][GL_D];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int K1 = p.din, K2 = GL_D;               // din = in_features of W1 ([64, din] contiguous); X rows are zero-padded to a multiple of 4
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 32) {
+    mbar_init(&z_full[0], N_PROD_WARPS); mbar_init(&z_full[1], N_PROD_WARPS);
+    mbar_init(&z_empty[0], GL_EPI_WARPS); mbar_init(&z_empty[1], GL_EPI_WARPS);
+    mbar_init(&t_full, GL_EPI_WARPS);
+    mbar_init(&m1_done, 1); mbar_init(&m2_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < GL_D) {
+    b1_s[tid] = p.b1 ? __ldg(p.b1 + tid) : 0.f;
+    b2_s[tid] = p.b2 ? __ldg(p.b2 + tid) : 0.f;
+  }
+  // ---- weights: W[n][k] (nn.Linear layout) split once per CTA into the K-major SWIZZLE_128B B operands
+#pragma unroll 1
+  for (int idx = tid; idx < 2 * 2 * GL_D * 8; idx += THREADS) {
+    const int which = idx / (2 * GL_D * 8), rem = idx % (2 * GL_D * 8);
+    const int ch = rem / (GL_D * 8), n = (rem >> 3) % GL_D, c = rem & 7;
+    const int gk = ch * TC_KC + c * 4;
+    const int K = which ? K2 : K1;
+    const float* W = which ? p.W2 : p.W1;
+    float t[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (gk + j < K) t[j] = __ldg(W + (int64_t)n * K + gk + j);
+    split_store((which ? w2_hi : w1_hi) + ch * (GL_D * 128), (which ? w2_lo : w1_lo) + ch * (GL_D * 128),
+                sw128_off(n, c), make_float4(t[0], t[1], t[2], t[3]));
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = tmem_base_s;
+  const uint32_t acc1 = tmem_d, acc2 = tmem_d + (uint32_t)GL_ACC_COLS;
+
+  if (warp >= GL_EPI_WARPS + 1) {
+    // =============================================================== producers: z tiles
+    const int grp = (warp - GL_EPI_WARPS - 1) * 4 + (lane >> 3);
+    const int l8 = lane & 7;
+    const int din4 = (p.din + 3) >> 2;
+    const bool ok0 = l8 < din4, ok1 = l8 + 8 < din4;
+    const float* __restrict__ X = p.X;
+    const int64_t ldx = p.ldx;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const int b = it & 1;
+      mbar_wait(&z_empty[b], ((it >> 1) & 1) ^ 1);
+      uint8_t* a_hi = smem + b * GL_SLOT;
+      uint8_t* a_lo = a_hi + 2 * TC_BM * 128;
+      const int m0 = tile * TC_BM;
+      int chunk = p.fold_a ? __ldg(p.tile_chunk0 + tile) : 0;
+#pragma unroll 1
+      for (int r = grp; r < TC_BM; r += N_GROUPS) {
+        const int grow = m0 + r;
+        float4 z0 = f4z(), z1 = f4z();
+        if (grow < p.rows) {
+          const int k0 = __ldg(p.row_ptr + grow), k1 = __ldg(p.row_ptr + grow + 1);
+          const float* xr = X + (int64_t)grow * ldx;
+          const float4 s0 = ok0 ? ldg4(xr + 4 * l8) : f4z();
+          const float4 s1 = ok1 ? ldg4(xr + 4 * (l8 + 8)) : f4z();
+          float4 a0 = f4z(), a1 = f4z();
+          int cnt = 0;
+          for (int k = k0; k < k1; k += 4) {
+            int c[4];
+            float4 v0[4], v1[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              c[u] = (k + u < k1) ? __ldg(p.col_idx + k + u) : -1;
+              if (c[u] == grow) c[u] = -1;                       // remove_self_loops (PyG GINConv)
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float* nr = X + (int64_t)(c[u] >= 0 ? c[u] : 0) * ldx;
+              v0[u] = (c[u] >= 0 && ok0) ? ldg4(nr + 4 * l8) : f4z();
+              v1[u] = (c[u] >= 0 && ok1) ? ldg4(nr + 4 * (l8 + 8)) : f4z();
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (c[u] >= 0) { add4(a0, v0[u]); add4(a1, v1[u]); ++cnt; }
+            }
+          }
+          const float sc = p.self_coef;
+          z0.x = __fadd_rn(__fmul_rn(sc, s0.x), a0.x); z0.y = __fadd_rn(__fmul_rn(sc, s0.y), a0.y);
+          z0.z = __fadd_rn(__fmul_rn(sc, s0.z), a0.z); z0.w = __fadd_rn(__fmul_rn(sc, s0.w), a0.w);
+          z1.x = __fadd_rn(__fmul_rn(sc, s1.x), a1.x); z1.y = __fadd_rn(__fmul_rn(sc, s1.y), a1.y);
+          z1.z = __fadd_rn(__fmul_rn(sc, s1.z), a1.z); z1.w = __fadd_rn(__fmul_rn(sc, s1.w), a1.w);
+          if (p.fold_a) {
+            // BatchNorm of the producer layer folded in: sum_j (a*y_j + b) = a * sum_j y_j + b * (weights)
+            while (grow >= __ldg(p.chunk_row_ptr + chunk + 1)) ++chunk;
+            const float wsum = sc + (float)cnt;
+            const float* fa = p.fold_a + (int64_t)chunk * p.din;
+            const float* fb = p.fold_b + (int64_t)chunk * p.din;
+            if (ok0) {
+              const float4 A = ldg4(fa + 4 * l8), B = ldg4(fb + 4 * l8);
+              z0.x = fmaf(A.x, z0.x, B.x * wsum); z0.y = fmaf(A.y, z0.y, B.y * wsum);
+              z0.z = fmaf(A.z, z0.z, B.z * wsum); z0.w = fmaf(A.w, z0.w, B.w * wsum);
+            }
+            if (ok1) {
+              const float4 A = ldg4(fa + 4 * (l8 + 8)), B = ldg4(fb + 4 * (l8 + 8));
+              z1.x = fmaf(A.x, z1.x, B.x * wsum); z1.y = fmaf(A.y, z1.y, B.y * wsum);
+              z1.z = fmaf(A.z, z1.z, B.z * wsum); z1.w = fmaf(A.w, z1.w, B.w * wsum);
+            }
+          }
+        }
+        const uint32_t off = sw128_off(r, l8);
+        *reinterpret_cast<float4*>(a_hi + off) = z0;                          // raw fp32 = the TF32 hi operand
+        *reinterpret_cast<float4*>(a_hi + TC_BM * 128 + off) = z1;
+        *reinterpret_cast<uint4*>(a_lo + off) = lo_part(z0);
+        *reinterpret_cast<uint4*>(a_lo + TC_BM * 128 + off) = lo_part(z1);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core proxy
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&z_full[b]);
+    }
+  } else if (warp == GL_EPI_WARPS) {
+    // =============================================================== MMA issuer
+    const uint32_t idesc = umma_idesc_tf32(TC_BM, GL_D);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const int b = it & 1;
+      const uint8_t* a_hi = smem + b * GL_SLOT;
+      const uint8_t* a_lo = a_hi + 2 * TC_BM * 128;
+      mbar_wait(&z_full[b], (it >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lane == 0) {
+        issue_gemm(acc1, a_hi, a_lo, w1_hi, w1_lo, K1, idesc);
+        umma_commit(&m1_done);
+      }
+      __syncwarp();
+      mbar_wait(&t_full, it & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lane == 0) {
+        issue_gemm(acc2, a_hi, a_lo, w2_hi, w2_lo, K2, idesc);
+        umma_commit(&m2_done);
+      }
+      __syncwarp();
+    }
+  } else {
+    // =============================================================== epilogue warps (TMEM lane quadrant = warp)
+    const int row = warp * 32 + lane;                       // tile row this thread reads from TMEM
+    const int et = tid;                                     // 0..127
+    const int c4 = et & 15, rg = et >> 4;                   // copy-out: 16-byte column chunk, row group (8 groups)
+    const int n_main1 = (K1 + 7) / 8 < GL_NA ? (K1 + 7) / 8 : GL_NA;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const int b = it & 1;
+      uint8_t* a_hi = smem + b * GL_SLOT;
+      uint8_t* a_lo = a_hi + 2 * TC_BM * 128;
+      const int m0 = tile * TC_BM;
+      const int rows_here = min(TC_BM, p.rows - m0);
+      const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+      // ---------------- first transform done: z may leave (kept for the backward), t goes back in
+      mbar_wait(&m1_done, it & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (p.Z) {
+#pragma unroll 4
+        for (int i = 0; i < 16; ++i) {
+          const int r = rg + 8 * i;
+          if (r < rows_here && c4 < ((p.din + 3) >> 2))
+            st4(p.Z + (int64_t)(m0 + r) * p.ldz + 4 * c4,
+                *reinterpret_cast<const float4*>(a_hi + (c4 >> 3) * (TC_BM * 128) + sw128_off(r, c4 & 7)));
+        }
+        named_bar_sync(1, GL_EPI_WARPS * 32);               // every z row is out before any t row comes in
+      }
+#pragma unroll 1
+      for (int cb = 0; cb < GL_D; cb += 16) {
+        uint32_t r[16];
+        float v[16];
+        const uint32_t tb = acc1 + lane_off + (uint32_t)cb;
+        tmem_ld16(tb + (uint32_t)(GL_NA * GL_D), r);        // corrections first (small)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+        tmem_ld16(tb, r);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __fadd_rn(__uint_as_float(r[j]), v[j]);
+        if (n_main1 == 2) {
+          tmem_ld16(tb + (uint32_t)GL_D, r);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __fadd_rn(__uint_as_float(r[j]), v[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j] + b1_s[cb + j], p.act_inner);
+        uint8_t* hi = a_hi + (cb >> 5) * (TC_BM * 128);
+        uint8_t* lo = a_lo + (cb >> 5) * (TC_BM * 128);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float4 tv = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+          const uint32_t off = sw128_off(row, ((cb & 31) >> 2) + c);
+          *reinterpret_cast<float4*>(hi + off) = tv;
+          *reinterpret_cast<uint4*>(lo + off) = lo_part(tv);
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_full);
+      if (p.T) {
+        named_bar_sync(1, GL_EPI_WARPS * 32);               // all of t is in the slot; copy it out while the MMA runs
+#pragma unroll 4
+        for (int i = 0; i < 16; ++i) {
+          const int r = rg + 8 * i;
+          if (r < rows_here)
+            st4(p.T + (int64_t)(m0 + r) * p.ldt + 4 * c4,
+                *reinterpret_cast<const float4*>(a_hi + (c4 >> 3) * (TC_BM * 128) + sw128_off(r, c4 & 7)));
+        }
+      }
+      // ---------------- second transform done: y = act(acc + b2) staged in the slot (t has been consumed)
+      mbar_wait(&m2_done, it & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (p.T) named_bar_sync(1, GL_EPI_WARPS * 32);        // the T copy-out above has read the whole slot
+#pragma unroll 1
+      for (int cb = 0; cb < GL_D; cb += 16) {
+        uint32_t r[16];
+        float v[16];
+        const uint32_t tb = acc2 + lane_off + (uint32_t)cb;
+        tmem_ld16(tb + (uint32_t)(GL_NA * GL_D), r);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+        tmem_ld16(tb, r);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __fadd_rn(__uint_as_float(r[j]), v[j]);
+        tmem_ld16(tb + (uint32_t)GL_D, r);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __fadd_rn(__uint_as_float(r[j]), v[j]);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j] + b2_s[cb + j], p.act_outer);
+        uint8_t* hi = a_hi + (cb >> 5) * (TC_BM * 128);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          *reinterpret_cast<float4*>(hi + sw128_off(row, ((cb & 31) >> 2) + c)) =
+              make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      named_bar_sync(1, GL_EPI_WARPS * 32);
+      // ---------------- coalesced copy-out
+      const uint8_t* src = a_hi + (c4 >> 3) * (TC_BM * 128);
+#pragma unroll 4
+      for (int i = 0; i < 16; ++i) {
+        const int r = rg + 8 * i;
+        if (r < rows_here)
+          st4(p.Y + (int64_t)(m0 + r) * p.ldy + 4 * c4, *reinterpret_cast<const float4*>(src + sw128_off(r, c4 & 7)));
+      }
+      // ---------------- BatchNorm partial sums of the stored rows, per (tile, chunk) record
+      if (p.stat_parts) {
+        int chunk = __ldg(p.tile_chunk0 + tile);
+        int lo_r = 0;
+        while (lo_r < rows_here) {
+          const int hi_r = min(rows_here, __ldg(p.chunk_row_ptr + chunk + 1) - m0);
+          double s[4] = {0.0, 0.0, 0.0, 0.0}, ss[4] = {0.0, 0.0, 0.0, 0.0};
+          for (int r = lo_r + ((rg - lo_r) & 7); r < hi_r; r += 8) {
+            const float4 o = *reinterpret_cast<const float4*>(src + sw128_off(r, c4 & 7));
+            s[0] += (double)o.x; ss[0] += (double)o.x * (double)o.x;
+            s[1] += (double)o.y; ss[1] += (double)o.y * (double)o.y;
+            s[2] += (double)o.z; ss[2] += (double)o.z * (double)o.z;
+            s[3] += (double)o.w; ss[3] += (double)o.w * (double)o.w;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { red_s[0][rg][4 * c4 + j] = s[j]; red_s[1][rg][4 * c4 + j] = ss[j]; }
+          named_bar_sync(1, GL_EPI_WARPS * 32);
+          {
+            const int which = et >> 6, col = et & 63;
+            double a = 0.0;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) a += red_s[which][g][col];
+            p.stat_parts[((int64_t)(tile + chunk) * 2 + which) * GL_D + col] = a;
+          }
+          named_bar_sync(1, GL_EPI_WARPS * 32);
+          lo_r = hi_r;
+          ++chunk;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&z_empty[b]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(512) : "memory");
+  }
+}
+
+// ---- per-chunk statistics from the (tile, chunk) records, in tile order (deterministic); also the affine
+// (fold_a, fold_b) = (gamma*rstd, beta - mean*gamma*rstd) that the consumer layer folds into its aggregation.
+__global__ void __launch_bounds__(GL_D)
+k_gin_bn_finalize(const double* __restrict__ stat_parts, const int32_t* __restrict__ chunk_row_ptr, int S, float eps,
+                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                  float* __restrict__ mean, float* __restrict__ rstd, double* __restrict__ mean_d,
+                  double* __restrict__ varu_d, float* __restrict__ fold_a, float* __restrict__ fold_b) {
+  const int c = threadIdx.x;
+  for (int s = blockIdx.x; s < S; s += gridDim.x) {
+    const int lo = chunk_row_ptr[s], hi = chunk_row_ptr[s + 1];
+    const int n = hi - lo;
+    double a = 0.0, b = 0.0;
+    if (n > 0) {
+      const int t0 = lo / TC_BM, t1 = (hi - 1) / TC_BM;
+      for (int t = t0; t <= t1; ++t) {
+        a += stat_parts[((int64_t)(t + s) * 2 + 0) * GL_D + c];
+        b += stat_parts[((int64_t)(t + s) * 2 + 1) * GL_D + c];
+      }
+    }
+    double mu = 0.0, var = 0.0;
+    if (n > 0) {
+      mu = a / n;
+      var = b / n - mu * mu;
+      if (var < 0.0) var = 0.0;
+    }
+    const int64_t i = (int64_t)s * GL_D + c;
+    const float m_f = (float)mu;
+    const float r_f = n > 0 ? (float)(1.0 / sqrt(var + (double)eps)) : 0.f;
+    mean[i] = m_f;
+    rstd[i] = r_f;
+    mean_d[i] = mu;
+    varu_d[i] = n > 1 ? var * ((double)n / (double)(n - 1)) : var;
+    const float g = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+    const float fa = g * r_f;
+    fold_a[i] = fa;
+    fold_b[i] = be - m_f * fa;
+  }
+}
+
+}  // namespace bignn
+
+using namespace bignn;
+
+extern "C" int64_t bignn_gin_layer_stat_records(int32_t rows, int32_t S) {
+  return (int64_t)ceil_div(rows > 0 ? rows : 1, TC_BM) + (S > 0 ? S : 0);
+}
+
+extern "C" int bignn_gin_layer_supported(int32_t din, int32_t dout) {
+  return (dout == GL_D && din > 0 && din <= GL_D) ? 1 : 0;
+}
+
+extern "C" int bignn_gin_layer_fwd(int32_t rows, int32_t din, int32_t dout, const int32_t* row_ptr,
+                                   const int32_t* col_idx, const float* X, int64_t ldx, const float* fold_a,
+                                   const float* fold_b, const int32_t* chunk_row_ptr, int32_t S,
+                                   const int32_t* tile_chunk0, float self_coef, const float* W1, const float* b1,
+                                   const float* W2, const float* b2, int32_t act_inner, int32_t act_outer, float* Z,
+                                   int64_t ldz, float* T, int64_t ldt, float* Y, int64_t ldy, double* stat_parts,
+                                   void* stream) {
+  if (rows < 0) return BIGNN_EINVAL;
+  if (rows == 0) return 0;
+  if (!bignn_gin_layer_supported(din, dout)) return BIGNN_EINVAL;
+  const int din_pad = (din + 3) & ~3;
+  if (!row_ptr || !col_idx || !X || !W1 || !W2 || !Y || ldx < din_pad || ldy < dout) return BIGNN_EINVAL;
+  if (fold_a && (din & 3)) return BIGNN_EINVAL;
+  if ((fold_a != nullptr) != (fold_b != nullptr)) return BIGNN_EINVAL;
+  if ((fold_a || stat_parts) && (!chunk_row_ptr || !tile_chunk0 || S <= 0)) return BIGNN_EINVAL;
+  if ((Z && ldz < din_pad) || (T && ldt < dout)) return BIGNN_EINVAL;
+  if (act_inner < 0 || act_inner > BIGNN_ACT_TANH || act_outer < 0 || act_outer > BIGNN_ACT_TANH) return BIGNN_EINVAL;
+  if ((ldx & 3) || (ldy & 3) || !aligned16(X) || !aligned16(Y) || (Z && ((ldz & 3) || !aligned16(Z))) ||
+      (T && ((ldt & 3) || !aligned16(T))) || (fold_a && (!aligned16(fold_a) || !aligned16(fold_b))))
+    return BIGNN_EALIGN;
+  constexpr int THREADS = 768;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_gin_layer_fwd<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, GL_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  GinLayerArgs a;
+  a.rows = rows; a.din = din; a.n_tiles = ceil_div(rows, TC_BM);
+  a.row_ptr = row_ptr; a.col_idx = col_idx; a.X = X; a.ldx = ldx; a.fold_a = fold_a; a.fold_b = fold_b;
+  a.chunk_row_ptr = chunk_row_ptr; a.tile_chunk0 = tile_chunk0; a.self_coef = self_coef;
+  a.W1 = W1; a.b1 = b1; a.W2 = W2; a.b2 = b2; a.act_inner = act_inner; a.act_outer = act_outer;
+  a.Z = Z; a.ldz = ldz; a.T = T; a.ldt = ldt; a.Y = Y; a.ldy = ldy; a.stat_parts = stat_parts;
+  int grid = sm_count();
+  if (grid > a.n_tiles) grid = a.n_tiles;
+  k_gin_layer_fwd<THREADS><<<grid, THREADS, GL_SMEM, (cudaStream_t)stream>>>(a);
+  BIGNN_LAUNCH_COUNT(1);
+  return last_launch_status();
+}
+
+extern "C" int bignn_gin_bn_finalize(const double* stat_parts, const int32_t* chunk_row_ptr, int32_t S, int32_t C,
+                                     float eps, const float* gamma, const float* beta, float* mean, float* rstd,
+                                     double* seg_stats_out, float* fold_a, float* fold_b, void* stream) {
+  if (S < 0 || C != GL_D) return BIGNN_EINVAL;
+  if (S == 0) return 0;
+  if (!stat_parts || !chunk_row_ptr || !mean || !rstd || !seg_stats_out || !fold_a || !fold_b) return BIGNN_EINVAL;
+  int grid = S < 4 * sm_count() ? S : 4 * sm_count();
+  k_gin_bn_finalize<<<grid, GL_D, 0, (cudaStream_t)stream>>>(stat_parts, chunk_row_ptr, S, eps, gamma, beta, mean, rstd,
+                                                            seg_stats_out, seg_stats_out + (int64_t)S * C, fold_a,
+                                                            fold_b);
+  BIGNN_LAUNCH_COUNT(1);
+  return last_launch_status();
+}

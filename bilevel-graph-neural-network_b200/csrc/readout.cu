@@ -11,7 +11,9 @@ namespace bignn {
 template <int L>
 __global__ void __launch_bounds__(256)
 k_readout_fwd_v4(const float* __restrict__ X, int64_t ldx, const int32_t* __restrict__ seg_ptr, int G, int D4,
-                 int style, const int32_t* __restrict__ dst_row, float* __restrict__ out, int64_t ldo) {
+                 int style, const int32_t* __restrict__ dst_row, float* __restrict__ out, int64_t ldo,
+                 const float* __restrict__ fold_a, const float* __restrict__ fold_b,
+                 const int32_t* __restrict__ graph_chunk) {
   const int gpb = blockDim.x / L;
   const int sub = threadIdx.x / L, lane = threadIdx.x % L;
   for (int g = blockIdx.x * gpb + sub; g < G; g += gridDim.x * gpb) {
@@ -39,6 +41,13 @@ k_readout_fwd_v4(const float* __restrict__ X, int64_t ldx, const int32_t* __rest
         const float cnt = (float)(n > 1 ? n : 1);      // count.clamp(min=1)
         acc.x = __fdiv_rn(acc.x, cnt); acc.y = __fdiv_rn(acc.y, cnt);
         acc.z = __fdiv_rn(acc.z, cnt); acc.w = __fdiv_rn(acc.w, cnt);
+      }
+      if (fold_a) {                                    // BatchNorm affine of the pooled rows, folded in
+        const int64_t c = graph_chunk ? graph_chunk[g] : 0;
+        const float4 a = ldg4(fold_a + (c * D4 + q) * 4), b = ldg4(fold_b + (c * D4 + q) * 4);
+        const float w = style == BIGNN_READOUT_MEAN ? (n > 0 ? 1.f : 0.f) : (float)n;
+        acc.x = fmaf(a.x, acc.x, b.x * w); acc.y = fmaf(a.y, acc.y, b.y * w);
+        acc.z = fmaf(a.z, acc.z, b.z * w); acc.w = fmaf(a.w, acc.w, b.w * w);
       }
       st4(out + orow * ldo + 4 * q, acc);
     }
@@ -90,13 +99,18 @@ k_readout_bwd(const float* __restrict__ dOut, int64_t ldo, const int32_t* __rest
 
 using namespace bignn;
 
-extern "C" int bignn_readout_fwd(const float* X, int64_t ldx, const int32_t* seg_ptr, int32_t G, int32_t D,
-                                 int32_t style, const int32_t* dst_row, float* out, int64_t ldo,
-                                 int32_t col_off, void* stream) {
+extern "C" int bignn_readout_fold_fwd(const float* X, int64_t ldx, const int32_t* seg_ptr, int32_t G, int32_t D,
+                                      int32_t style, const int32_t* dst_row, const float* fold_a,
+                                      const float* fold_b, const int32_t* graph_chunk, float* out, int64_t ldo,
+                                      int32_t col_off, void* stream) {
   if (G < 0 || D < 0 || col_off < 0) return BIGNN_EINVAL;
   if (G == 0 || D == 0) return 0;
   if (!X || !seg_ptr || !out || ldx < D || ldo < col_off + D) return BIGNN_EINVAL;
   if (style != BIGNN_READOUT_SUM && style != BIGNN_READOUT_MEAN) return BIGNN_EINVAL;
+  if ((fold_a != nullptr) != (fold_b != nullptr)) return BIGNN_EINVAL;
+  if (fold_a && ((D % 4) || (ldx % 4) || (ldo % 4) || (col_off % 4) || !aligned16(X) || !aligned16(out) ||
+                 !aligned16(fold_a) || !aligned16(fold_b)))
+    return BIGNN_EALIGN;
   cudaStream_t st = (cudaStream_t)stream;
   float* o = out + col_off;
   const int cap = sm_count() * 8;
@@ -106,11 +120,11 @@ extern "C" int bignn_readout_fwd(const float* X, int64_t ldx, const int32_t* seg
     if (d4 <= 16) {
       int grid = ceil_div(G, 16);
       if (grid > cap) grid = cap;
-      k_readout_fwd_v4<16><<<grid, 256, 0, st>>>(X, ldx, seg_ptr, G, d4, style, dst_row, o, ldo);
+      k_readout_fwd_v4<16><<<grid, 256, 0, st>>>(X, ldx, seg_ptr, G, d4, style, dst_row, o, ldo, fold_a, fold_b, graph_chunk);
     } else {
       int grid = ceil_div(G, 8);
       if (grid > cap) grid = cap;
-      k_readout_fwd_v4<32><<<grid, 256, 0, st>>>(X, ldx, seg_ptr, G, d4, style, dst_row, o, ldo);
+      k_readout_fwd_v4<32><<<grid, 256, 0, st>>>(X, ldx, seg_ptr, G, d4, style, dst_row, o, ldo, fold_a, fold_b, graph_chunk);
     }
   } else {
     int grid = ceil_div(G, 8);
@@ -119,6 +133,13 @@ extern "C" int bignn_readout_fwd(const float* X, int64_t ldx, const int32_t* seg
   }
   BIGNN_LAUNCH_COUNT(1);
   return last_launch_status();
+}
+
+extern "C" int bignn_readout_fwd(const float* X, int64_t ldx, const int32_t* seg_ptr, int32_t G, int32_t D,
+                                 int32_t style, const int32_t* dst_row, float* out, int64_t ldo,
+                                 int32_t col_off, void* stream) {
+  return bignn_readout_fold_fwd(X, ldx, seg_ptr, G, D, style, dst_row, nullptr, nullptr, nullptr, out, ldo, col_off,
+                                stream);
 }
 
 extern "C" int bignn_readout_bwd(const float* dOut, int64_t ldo, int32_t col_off, const int32_t* dst_row,

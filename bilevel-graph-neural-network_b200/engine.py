@@ -14,7 +14,9 @@ src/train.py:75-108,177-182), re-organised for the GPU:
 import numpy as np
 import torch
 
-from . import ops, dist as bdist
+import os
+
+from . import ops, dist as bdist, fused
 from .batch import BatchData, unique_graphs_in_order
 from .config import get_flags
 from .graph import MergedGraph, PartitionedInteractionGraph
@@ -48,6 +50,16 @@ class _StaticPairBatch(object):
         self.chk = torch.zeros(2, dtype=torch.float32, device=device)      # pair-batch checksum (multi-GPU agreement)
         self.batch_gids = np.zeros((P, 2), np.int64)
         self.preds = None
+
+    def load(self, st, refresh=True):
+        """staged inputs (pinned host) -> the static device buffers."""
+        self.ids.copy_(st.ids, non_blocking=True)
+        self.y.copy_(st.y, non_blocking=True)
+        self.e_rows.copy_(st.e_rows, non_blocking=True)
+        self.e_idx.copy_(st.e_idx, non_blocking=True)
+        self.chk.copy_(st.chk, non_blocking=True)
+        if refresh:
+            self.refresh()
 
     def refresh(self):
         """e_ptr[r] = number of entries whose row is < r (capturable; runs at the head of every step)."""
@@ -84,7 +96,8 @@ class _Staging(object):
 
 class BiGNNEngine(object):
     def __init__(self, data, model, optimizer=None, lr=None, use_cuda_graph=True, rebuild_each_step=True,
-                 n_staging=4, rank=0, world=1, group=None, adam_capturable=None, partition_upper=None):
+                 n_staging=4, rank=0, world=1, group=None, adam_capturable=None, partition_upper=None,
+                 fused_lower=None):
         flags = get_flags()
         assert flags.lower_level_layers and flags.higher_level_layers, 'engine runs the Bi-GNN mode'
         self.data, self.model = data, model
@@ -111,7 +124,14 @@ class BiGNNEngine(object):
         mine = chunk_rows[lo:hi]
         rows = np.concatenate(mine) if mine else np.zeros(0, np.int64)
         chunk_ptr = np.concatenate([[0], np.cumsum([len(r) for r in mine])]).astype(np.int64)
-        self.merged = MergedGraph(data.packed, rows, chunk_graph_ptr=chunk_ptr)
+        # the lower level runs as fused layer kernels (fused.py) whenever they cover it exactly; otherwise -- and with
+        # BIGNN_NO_FUSED=1 -- layer by layer through the registry's layer classes
+        agg = model.lower_layers[-1]
+        self.fused_lower = (self.device.type == 'cuda' and not os.environ.get('BIGNN_NO_FUSED')
+                            and fused.stack_supported(model.init_layers, agg, data.num_node_feat)) \
+            if fused_lower is None else bool(fused_lower)
+        self.lower_path = 'fused' if self.fused_lower else 'layers'
+        self.merged = MergedGraph(data.packed, rows, chunk_graph_ptr=chunk_ptr, pad_features=self.fused_lower)
         self._bn_sink = [] if self.world > 1 else None
         self.merged.bn_stats_sink = self._bn_sink
         # ---- upper level: replicated, or rows (= edges by source drug) partitioned over the ranks with a
@@ -146,8 +166,9 @@ class BiGNNEngine(object):
         self._lower_bd.merge_data = {'merge': self.merged}
         self._lower_bd.merge_higher_level = {}
         self._lower_bd.dataset = data
-        agg = model.lower_layers[-1]
         self._agg_style, self._multi = agg.style, agg.concat_multi_scale
+        self._stack = fused.StackSpec(list(model.init_layers), agg, self.merged, self.dst_row, data.N + 1,
+                                      self._bn_sink) if self.fused_lower else None
         self._graphs = {}          # P -> (graph, static batch, loss tensor)
         self.max_graphs = 8
         self._stagings = {}
@@ -164,12 +185,16 @@ class BiGNNEngine(object):
         m, model = self.merged, self.model
         if self.rebuild_each_step:
             m.build()
-        acts, h = [], m.x
-        for layer in model.init_layers:
-            h = layer(h, self._lower_bd, model)
-            acts.append(h)
-        pooled = ops.readout(acts if self._multi else [h], m.seg_ptr, m.G, self._agg_style,
-                             self.dst_row, self.data.N + 1)
+        acts = []
+        if self._stack is not None:
+            pooled = fused.gin_stack(self._stack, m.x, model.training)
+        else:
+            h = m.x
+            for layer in model.init_layers:
+                h = layer(h, self._lower_bd, model)
+                acts.append(h)
+            pooled = ops.readout(acts if self._multi else [h], m.seg_ptr, m.G, self._agg_style,
+                                 self.dst_row, self.data.N + 1)
         if self.world > 1:                                            # the exchange step (NCCL)
             pooled = (bdist.exchange_pooled_rows if self.upper is not None else bdist.sum_disjoint_rows)(
                 pooled, self.group)
@@ -345,11 +370,7 @@ class BiGNNEngine(object):
                 for k in [k for k in self._graphs if isinstance(k, tuple)]:
                     del self._graphs[k]                    # keep one eager batch
                 sb = self._graphs[('eager', P)] = _StaticPairBatch(self.data, P, self.device, self.upper)
-        sb.ids.copy_(st.ids, non_blocking=True)
-        sb.y.copy_(st.y, non_blocking=True)
-        sb.e_rows.copy_(st.e_rows, non_blocking=True)
-        sb.e_idx.copy_(st.e_idx, non_blocking=True)
-        sb.chk.copy_(st.chk, non_blocking=True)
+        sb.load(st, refresh=False)               # (the pointer array is derived inside the step)
         if use_graph:
             g.replay()
         else:

@@ -44,6 +44,20 @@ class PackedGraphs(object):
         x = z['x_u8'] if 'x_u8' in z else z['x']
         return cls(z['gids'], z['atom_ptr'], z['nbr_ptr'], z['nbr_idx'], np.asarray(x, np.float32), device)
 
+    def x_padded(self):
+        """(x with the feature columns zero-padded to a multiple of 4, padded width): 16-byte aligned rows for the
+        fused layer kernel's 128-bit gathers (one-time copy; 49 -> 52 columns on DrugBank)."""
+        if getattr(self, '_x_pad', None) is None:
+            F = self.num_node_feat
+            Fp = (F + 3) // 4 * 4
+            if Fp == F:
+                self._x_pad = (self.x, F)
+            else:
+                xp = torch.zeros((self.x.shape[0], Fp), dtype=torch.float32, device=self.device)
+                xp[:, :F] = self.x
+                self._x_pad = (xp, Fp)
+        return self._x_pad
+
     def sizes(self, rows):
         rows = np.asarray(rows, np.int64)
         n = self.atom_ptr_host[rows + 1] - self.atom_ptr_host[rows]
@@ -55,8 +69,9 @@ class MergedGraph(object):
     """Merged batch on the device.  `chunk_row_ptr` (optional) marks groups of graphs that
     form independent BatchNorm batches (the 128-graph chunks of src/train.py:62-71)."""
 
-    def __init__(self, packed, rows, chunk_graph_ptr=None, with_x=True):
+    def __init__(self, packed, rows, chunk_graph_ptr=None, with_x=True, pad_features=False):
         rows = np.asarray(rows, np.int64)
+        self._src_x, self.feat_width = packed.x_padded() if pad_features else (packed.x, packed.num_node_feat)
         self.packed = packed
         self.G = int(rows.shape[0])
         n, e = packed.sizes(rows) if self.G else (np.zeros(0, np.int64), np.zeros(0, np.int64))
@@ -69,7 +84,7 @@ class MergedGraph(object):
         self.row_ptr = torch.empty(self.A + 1, dtype=torch.int32, device=dev)
         self.col_idx = torch.empty(max(self.E, 1), dtype=torch.int32, device=dev)[:self.E]
         self.batch_i32 = torch.empty(max(self.A, 1), dtype=torch.int32, device=dev)[:self.A]
-        self.x = torch.empty((self.A, packed.num_node_feat), dtype=torch.float32, device=dev) if with_x else None
+        self.x = torch.empty((self.A, self.feat_width), dtype=torch.float32, device=dev) if with_x else None
         self.edge_attr = None                 # molecule graphs carry no edge features (layers.py:48-50)
         self._edge_index = None
         self._batch = None
@@ -88,9 +103,23 @@ class MergedGraph(object):
         """(Re)runs the device-side construction; capturable in a CUDA graph."""
         p = self.packed
         _lib.require_device(p.atom_ptr)
-        _lib.call('bignn_merge_build', p.atom_ptr, p.nbr_ptr, p.nbr_idx, p.x, p.num_node_feat,
+        _lib.call('bignn_merge_build', p.atom_ptr, p.nbr_ptr, p.nbr_idx, self._src_x, self.feat_width,
                   self.rows, self.G, self.seg_ptr, self.edge_ptr, self.row_ptr, self.col_idx, self.batch_i32,
                   self.x, edge_index, batch64, self.A, self.E, self._ws, self._ws_bytes)
+
+    def fused_plan(self):
+        """Static index helpers of the fused layer kernel: the chunk of every 128-row tile's first row, the chunk of
+        every graph, and the number of (tile, chunk) statistics records."""
+        if getattr(self, '_fused_plan', None) is None:
+            dev = self.packed.device
+            crp = self.seg_ptr_host[self.chunk_graph_ptr_host]
+            n_tiles = max((self.A + 127) // 128, 1)
+            tile0 = np.searchsorted(crp, np.arange(n_tiles, dtype=np.int64) * 128, side='right') - 1
+            tile0 = np.clip(tile0, 0, max(self.S - 1, 0))
+            gchunk = np.searchsorted(self.chunk_graph_ptr_host, np.arange(self.G, dtype=np.int64), side='right') - 1
+            self._fused_plan = dict(tile_chunk0=_i32(tile0, dev), graph_chunk=_i32(np.clip(gchunk, 0, max(self.S - 1, 0)), dev),
+                                    n_tiles=int(n_tiles), records=int(n_tiles + self.S))
+        return self._fused_plan
 
     @property
     def edge_index(self):

@@ -286,26 +286,39 @@ class _LinearAct(torch.autograd.Function):
         g = act_bwd(y, dy, ctx.act)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            if use_tc(g.shape[0], x.shape[1], g.shape[1]):
-                # dX = g W (oi: W is [N,K] = op(B)^T stored [K',N'] -> b_is_nk False) / g W^T (io)
-                dx = gemm_tc(g, weight, ctx.layout == 'io', mask_y=x if ctx.input_act else None,
-                             mask_act=ctx.input_act)
-            else:
-                dx = gemm(g, weight, False, ctx.layout == 'io')
-                if ctx.input_act:
-                    dx = act_bwd(x, dx, ctx.input_act)
-        want_b = ctx.needs_input_grad[2]
-        if ctx.needs_input_grad[1] and use_dw_tc(g.shape[0], g.shape[1], x.shape[1]):
-            if ctx.layout == 'oi':
-                dw, db = dw_tc(g, x, 0 if want_b else -1)
-            else:
-                dw, db = dw_tc(x, g, 1 if want_b else -1)
-        else:
-            if ctx.needs_input_grad[1]:
-                dw = gemm(g, x, True, False) if ctx.layout == 'oi' else gemm(x, g, True, False)
-            if want_b:
-                db = colsum(g)
+            dx = linear_bwd_input(g, weight, ctx.layout, x if ctx.input_act else None, ctx.input_act)
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            dw, db = linear_bwd_params(g, x, ctx.layout, ctx.needs_input_grad[2], ctx.needs_input_grad[1])
         return dx, dw, db, None, None, None, None
+
+
+def linear_bwd_input(g, weight, layout, x_mask=None, input_act=0):
+    """dX = g W ('oi') / g W^T ('io'), times act'(x_mask) when the producer of x left its activation's derivative to
+    this consumer (mask fused into the tensor-core kernel's epilogue)."""
+    K = weight.shape[1] if layout == 'oi' else weight.shape[0]
+    if use_tc(g.shape[0], K, g.shape[1]):
+        # oi: W is [N,K] = op(B)^T stored [K',N'] -> b_is_nk False; io: W is [K,N] -> b_is_nk True
+        return gemm_tc(g, weight, layout == 'io', mask_y=x_mask if input_act else None, mask_act=input_act)
+    dx = gemm(g, weight, False, layout == 'io')
+    if input_act:
+        dx = act_bwd(x_mask, dx, input_act)
+    return dx
+
+
+def linear_bwd_params(g, x, layout, want_b=True, want_w=True):
+    """(dW, db) of y = x W^T + b ('oi': dW = g^T x) / y = x W + b ('io': dW = x^T g)."""
+    dw = db = None
+    if want_w and use_dw_tc(g.shape[0], g.shape[1], x.shape[1]):
+        if layout == 'oi':
+            dw, db = dw_tc(g, x, 0 if want_b else -1)
+        else:
+            dw, db = dw_tc(x, g, 1 if want_b else -1)
+    else:
+        if want_w:
+            dw = gemm(g, x, True, False) if layout == 'oi' else gemm(x, g, True, False)
+        if want_b:
+            db = colsum(g)
+    return dw, db
 
 
 class _SegBatchNorm(torch.autograd.Function):

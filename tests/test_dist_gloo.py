@@ -51,8 +51,7 @@ def _worker(rank, world, port, out_dir, partition_upper=False):
     st, P = eng.stage_pairs(z['batch_gids'], z['y_true'].astype(np.float32))
     from bignn_b200.engine import _StaticPairBatch
     sb = _StaticPairBatch(data, P, data.device, eng.upper)
-    sb.ids.copy_(st.ids); sb.y.copy_(st.y); sb.e_rows.copy_(st.e_rows); sb.e_idx.copy_(st.e_idx); sb.chk.copy_(st.chk)
-    sb.refresh()
+    sb.load(st)
     loss = eng.forward(sb)
     loss.backward()
     if world > 1:

@@ -1,0 +1,221 @@
+"""The fused lower-level layer kernel (`bignn_gin_layer_fwd` + `bignn_gin_bn_finalize` + `bignn_readout_fold_fwd`,
+fused.py) against the layer-by-layer kernels it replaces and against the golden step (`-m gpu`)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import bignn_b200 as B
+from bignn_b200 import _lib, ops, fused
+from bignn_b200.engine import BiGNNEngine
+
+DEV = 'cuda:0'
+
+
+def rel(a, b):
+    a = np.asarray(a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else a, np.float64)
+    b = np.asarray(b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def random_block_graph(rows, seed, mean_deg=2.2):
+    """symmetric, block-local random graph over `rows` nodes (blocks of ~30 like molecules), CSR on the device."""
+    rng = np.random.default_rng(seed)
+    m = int(rows * mean_deg / 2)
+    a = rng.integers(0, rows, m)
+    b = np.clip(a + rng.integers(-20, 21, m), 0, rows - 1)
+    keep = a != b
+    a, b = a[keep], b[keep]
+    key = np.unique(np.concatenate([a * rows + b, b * rows + a]))
+    r, c = key // rows, key % rows
+    ptr = np.concatenate([[0], np.cumsum(np.bincount(r, minlength=rows))])
+    return ops.CSR(torch.as_tensor(ptr.astype(np.int32)).to(DEV), torch.as_tensor(c.astype(np.int32)).to(DEV), rows)
+
+
+def run_layer(csr, X, din, W1, b1, W2, b2, a_in, a_out, crp, fold=None, keep=True, stats=True, self_coef=1.0):
+    rows = csr.n_rows
+    S = crp.numel() - 1
+    n_tiles = (rows + 127) // 128
+    crp_h = crp.cpu().numpy()
+    tile0 = np.clip(np.searchsorted(crp_h, np.arange(n_tiles) * 128, side='right') - 1, 0, S - 1)
+    tile0 = torch.as_tensor(tile0.astype(np.int32)).to(DEV)
+    din_pad = (din + 3) // 4 * 4
+    Y = torch.full((rows, 64), float('nan'), device=DEV)
+    Z = torch.full((rows, din_pad), float('nan'), device=DEV) if keep else None
+    T = torch.full((rows, 64), float('nan'), device=DEV) if keep else None
+    recs = _lib.call('bignn_gin_layer_stat_records', rows, S)
+    parts = torch.full((recs, 2, 64), float('nan'), dtype=torch.float64, device=DEV) if stats else None
+    fa, fb = fold if fold is not None else (None, None)
+    _lib.call('bignn_gin_layer_fwd', rows, din, 64, csr.row_ptr, csr.col_idx, X, X.stride(0), fa, fb, crp, S, tile0,
+              float(self_coef), W1, b1, W2, b2, a_in, a_out, Z, Z.stride(0) if keep else 0, T,
+              T.stride(0) if keep else 0, Y, Y.stride(0), parts)
+    return Y, Z, T, parts
+
+
+@pytest.mark.parametrize('rows,din,acts', [(128, 64, (1, 1)), (1000, 64, (1, 0)), (4133, 52, (1, 1)), (70001, 64, (3, 3)),
+                                           (257, 49, (2, 2)), (300000, 64, (1, 1))])
+def test_fused_layer_matches_unfused_kernels(rows, din, acts):
+    """no fold: aggregation, both transforms and the activations must reproduce the separate kernels
+    (same summation order, same 3xTF32 accumulator rotation) -- bit for bit for z, <= 1e-6 for t and y."""
+    torch.manual_seed(rows + din)
+    csr = random_block_graph(rows, rows)
+    din_pad = (din + 3) // 4 * 4
+    X = torch.zeros(rows, din_pad, device=DEV)
+    X[:, :din] = torch.randn(rows, din, device=DEV)
+    W1 = torch.randn(64, din, device=DEV) / din ** 0.5
+    W2 = torch.randn(64, 64, device=DEV) / 8
+    b1, b2 = torch.randn(64, device=DEV) * 0.1, torch.randn(64, device=DEV) * 0.1
+    crp = torch.as_tensor(np.asarray([0, rows], np.int32)).to(DEV)
+    Y, Z, T, _ = run_layer(csr, X, din, W1, b1, W2, b2, acts[0], acts[1], crp, stats=False, self_coef=1.25)
+    z_ref = ops.spmm(csr, X, ops.SPMM_GIN, 1.25)
+    assert torch.equal(Z, z_ref)
+    if ops.use_tc(rows, 64, din):
+        t_ref = ops.gemm_tc(z_ref[:, :din].contiguous() if din_pad != din else z_ref, W1, True, b1, acts[0])
+    else:
+        t_ref = ops.gemm(z_ref[:, :din].contiguous(), W1, False, True, b1, acts[0])
+    assert rel(T, t_ref) < 2e-6
+    y_ref = ops.gemm_tc(t_ref, W2, True, b2, acts[1]) if ops.use_tc(rows, 64, 64) else ops.gemm(t_ref, W2, False, True, b2, acts[1])
+    assert rel(Y, y_ref) < 2e-6
+    # fp64 ground truth of the whole layer
+    z64 = z_ref[:, :din].double()
+    f = {0: lambda v: v, 1: torch.relu, 2: torch.sigmoid, 3: torch.tanh}
+    t64 = f[acts[0]](z64 @ W1.double().t() + b1.double())
+    y64 = f[acts[1]](t64 @ W2.double().t() + b2.double())
+    assert rel(Y, y64) < 3e-6
+    # the outputs that are not asked for are not needed either
+    Y2, _, _, _ = run_layer(csr, X, din, W1, b1, W2, b2, acts[0], acts[1], crp, keep=False, stats=False, self_coef=1.25)
+    assert torch.equal(Y, Y2)
+
+
+@pytest.mark.parametrize('rows,bounds', [(1000, [0, 1000]), (1000, [0, 100, 130, 131, 500, 1000]),
+                                          (50000, None), (129, [0, 1, 128, 129])])
+def test_fused_layer_fold_and_statistics(rows, bounds):
+    """BatchNorm of the producer folded into the aggregation + per-chunk statistics from the epilogue, with chunk
+    boundaries inside tiles (and several inside one tile)."""
+    torch.manual_seed(rows)
+    rng = np.random.default_rng(rows)
+    if bounds is None:
+        cuts = np.sort(rng.choice(np.arange(1, rows), 40, replace=False))
+        bounds = [0] + cuts.tolist() + [rows]
+    crp_h = np.asarray(bounds, np.int32)
+    S = len(bounds) - 1
+    crp = torch.as_tensor(crp_h).to(DEV)
+    csr = random_block_graph(rows, rows + 1)
+    X = torch.randn(rows, 64, device=DEV)
+    W1 = torch.randn(64, 64, device=DEV) / 8
+    W2 = torch.randn(64, 64, device=DEV) / 8
+    b1, b2 = torch.randn(64, device=DEV) * 0.1, torch.randn(64, device=DEV) * 0.1
+    fa = (torch.rand(S, 64, device=DEV) + 0.5).contiguous()
+    fb = (torch.randn(S, 64, device=DEV) * 0.3).contiguous()
+    Y, Z, T, parts = run_layer(csr, X, 64, W1, b1, W2, b2, 1, 1, crp, fold=(fa, fb))
+    seg = torch.repeat_interleave(torch.arange(S, device=DEV), torch.as_tensor(np.diff(crp_h)).to(DEV).long())
+    xb = (X * fa[seg] + fb[seg]).contiguous()
+    z_ref = ops.spmm(csr, xb, ops.SPMM_GIN, 1.0)
+    assert rel(Z, z_ref) < 2e-6
+    y64 = torch.relu(torch.relu(z_ref.double() @ W1.double().t() + b1.double()) @ W2.double().t() + b2.double())
+    assert rel(Y, y64) < 5e-6
+    # statistics -> mean / rstd / fold of THIS layer
+    gamma, beta = torch.rand(64, device=DEV) + 0.5, torch.randn(64, device=DEV)
+    mean = torch.empty(S, 64, device=DEV); rstd = torch.empty(S, 64, device=DEV)
+    stats = torch.empty(2, S, 64, dtype=torch.float64, device=DEV)
+    oa = torch.empty(S, 64, device=DEV); ob = torch.empty(S, 64, device=DEV)
+    _lib.call('bignn_gin_bn_finalize', parts, crp, S, 64, 1e-5, gamma, beta, mean, rstd, stats, oa, ob)
+    for s in range(S):
+        blk = Y[bounds[s]:bounds[s + 1]].double()
+        mu = blk.mean(0)
+        var = blk.var(0, unbiased=False)
+        assert rel(mean[s], mu) < 1e-6
+        assert rel(rstd[s], 1.0 / torch.sqrt(var + 1e-5)) < 1e-6
+        assert rel(stats[0, s], mu) < 1e-12
+        if blk.shape[0] > 1:
+            assert rel(stats[1, s], blk.var(0, unbiased=True)) < 1e-9
+        a_ref = gamma.double() / torch.sqrt(var + 1e-5)
+        assert rel(oa[s], a_ref) < 1e-6 and rel(ob[s], beta.double() - mu * a_ref) < 2e-6
+    # readout with the fold = readout of the materialised BatchNorm output
+    gptr_h = np.unique(np.concatenate([crp_h, np.arange(0, rows, 37, dtype=np.int32), [rows]])).astype(np.int32)
+    G = len(gptr_h) - 1
+    gchunk = np.searchsorted(crp_h, gptr_h[:-1], side='right') - 1
+    gptr = torch.as_tensor(gptr_h).to(DEV)
+    for style in (0, 1):
+        out = torch.empty(G, 64, device=DEV)
+        _lib.call('bignn_readout_fold_fwd', Y, Y.stride(0), gptr, G, 64, style, None, oa, ob,
+                  torch.as_tensor(gchunk.astype(np.int32)).to(DEV), out, out.stride(0), 0)
+        ybn = (Y * oa[seg] + ob[seg]).contiguous()
+        want = torch.empty(G, 64, device=DEV)
+        _lib.call('bignn_readout_fwd', ybn, ybn.stride(0), gptr, G, 64, style, None, want, want.stride(0), 0)
+        assert rel(out, want) < 2e-6
+
+
+def fresh(golden_dir, z):
+    B.set_flags(B.make_flags(device=DEV))
+    data = B.BiGNNData.from_npz(os.path.join(golden_dir, 'drugbank_packed.npz'), device=DEV)
+    model = B.Model(data).to(DEV)
+    sd = {k[4:]: torch.from_numpy(np.asarray(z[k])) for k in z.files if k.startswith('sd0/')}
+    for k in z.files:
+        if k.startswith('sd_init/'):
+            sd[k[len('sd_init/'):]] = torch.from_numpy(np.asarray(z[k]))
+    model.load_state_dict(sd, strict=False)
+    model.train()
+    return data, model
+
+
+def test_fused_stack_step_equals_layer_path_and_golden(golden_dir, step_golden):
+    """one full train step (forward, backward, BatchNorm buffers) with the fused lower level vs the layer-by-layer
+    lower level vs the reference's recorded step."""
+    z = step_golden
+    res = {}
+    for fused_on in (False, True):
+        data, model = fresh(golden_dir, z)
+        eng = BiGNNEngine(data, model, use_cuda_graph=False, fused_lower=fused_on)
+        assert eng.lower_path == ('fused' if fused_on else 'layers')
+        st, P = eng.stage_pairs(z['batch_gids'], z['y_true'].astype(np.float32))
+        from bignn_b200.engine import _StaticPairBatch
+        sb = _StaticPairBatch(data, P, data.device)
+        sb.load(st)
+        model.zero_grad()
+        loss = eng.forward(sb)
+        loss.backward()
+        res[fused_on] = dict(loss=float(loss), init_x=data.interaction_combo_nxgraph.init_x.detach().clone(),
+                             grads={k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None},
+                             bufs={k: v.detach().clone() for k, v in model.state_dict().items() if 'running' in k or 'num_batches' in k})
+    a, b = res[False], res[True]
+    assert abs(b['loss'] - float(z['loss'])) < 1e-5 and abs(a['loss'] - b['loss']) < 2e-6
+    assert rel(b['init_x'], z['init_x']) < 1e-5
+    assert rel(b['init_x'], a['init_x']) < 5e-6
+    worst = 0.0
+    for k in a['grads']:
+        lid = k.split('.')[1]
+        scale = max(float(a['grads'][q].abs().max()) for q in a['grads'] if q.split('.')[1] == lid)
+        err = float((a['grads'][k] - b['grads'][k]).abs().max()) / scale
+        worst = max(worst, err)
+        # the two paths differ by fp32 rounding only; the five train-mode BatchNorms amplify it in the lowest layers
+        assert err < (2e-3 if int(lid) < 5 else 2e-5), (k, err)
+    print('fused vs layer path: worst gradient deviation (layer scale) %.2e' % worst)
+    for k in a['bufs']:
+        assert rel(b['bufs'][k].float(), a['bufs'][k].float()) < 2e-6, k
+        if ('sd1/' + k) in z.files and 'running' in k:
+            assert rel(b['bufs'][k], z['sd1/' + k]) < 1e-5, k
+
+
+def test_fused_stack_eval_mode_and_graph_capture(golden_dir, step_golden):
+    z = step_golden
+    outs = {}
+    for fused_on in (False, True):
+        data, model = fresh(golden_dir, z)
+        eng = BiGNNEngine(data, model, use_cuda_graph=False, fused_lower=fused_on)
+        outs[fused_on] = eng.score_pairs(z['batch_gids']).detach().clone()
+    assert rel(outs[True], outs[False]) < 5e-6
+    # CUDA-graph replay of the fused step = the eager fused step
+    losses = {}
+    for graph in (False, True):
+        data, model = fresh(golden_dir, z)
+        eng = BiGNNEngine(data, model, use_cuda_graph=graph, adam_capturable=True, fused_lower=True)
+        out = []
+        for _ in range(3):
+            st, P = eng.stage_pairs(z['batch_gids'], z['y_true'].astype(np.float32))
+            out.append(eng.read_loss(eng.step_staged(st, P)))
+        losses[graph] = out
+    assert np.allclose(losses[False], losses[True], rtol=0, atol=1e-6), losses

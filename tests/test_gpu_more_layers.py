@@ -252,7 +252,7 @@ def test_drugcombo_architecture_step_vs_oracle():
         st, P = eng.stage_pairs(gids, y.astype(np.float32))
         from bignn_b200.engine import _StaticPairBatch
         sb = _StaticPairBatch(data, P, data.device)
-        sb.ids.copy_(st.ids); sb.y.copy_(st.y); sb.e_ptr.copy_(st.e_ptr); sb.e_idx.copy_(st.e_idx)
+        sb.load(st)
         loss = eng.forward(sb)
         loss.backward()
         res = {}

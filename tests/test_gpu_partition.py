@@ -173,7 +173,7 @@ def test_engine_partition_path_world1_matches_golden(golden_dir, step_golden):
         eng = BiGNNEngine(data, model, use_cuda_graph=False, partition_upper=part)
         st, P = eng.stage_pairs(z['batch_gids'], z['y_true'].astype(np.float32))
         sb = _StaticPairBatch(data, P, data.device, eng.upper)
-        sb.ids.copy_(st.ids); sb.y.copy_(st.y); sb.e_ptr.copy_(st.e_ptr); sb.e_idx.copy_(st.e_idx)
+        sb.load(st)
         loss = eng.forward(sb)
         loss.backward()
         assert abs(float(loss) - float(z['loss'])) < 1e-5

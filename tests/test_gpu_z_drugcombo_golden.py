@@ -62,7 +62,7 @@ def test_drugcombo_step_vs_reference_golden(golden_dir, golden):
         assert eng.n_chunks_total == int(z['n_chunks'])
         st, P = eng.stage_pairs(z['batch_gids'], z['y_true'].astype(np.float32))
         sb = _StaticPairBatch(data, P, data.device)
-        sb.ids.copy_(st.ids); sb.y.copy_(st.y); sb.e_ptr.copy_(st.e_ptr); sb.e_idx.copy_(st.e_idx)
+        sb.load(st)
         loss = eng.forward(sb)
         loss.backward()
         acts = model.acts                   # [None, LoadInteraction, MetaLayer x3, LinkPred, Loss]
