@@ -61,11 +61,11 @@ SIGNATURES = {
     'bignn_bn_rows_bwd_apply': ('i', 'plplpl' 'iii' 'ppp' 'pl' 'i' 's'),
     'bignn_readout_fwd': ('i', 'pl' 'pii' 'i' 'p' 'pli' 's'),
     'bignn_readout_bwd': ('i', 'pli' 'p' 'pii' 'i' 'pl' 'i' 's'),
-    'bignn_readout_fold_fwd': ('i', 'pl' 'pii' 'i' 'p' 'ppp' 'pli' 's'),
+    'bignn_readout_fold_fwd': ('i', 'pl' 'pii' 'i' 'p' 'pppp' 'pli' 's'),
     'bignn_gin_layer_supported': ('i', 'ii'),
     'bignn_gin_layer_stat_records': ('l', 'ii'),
-    'bignn_gin_layer_fwd': ('i', 'iii' 'pp' 'pl' 'pp' 'pip' 'f' 'pppp' 'ii' 'pl' 'pl' 'pl' 'p' 's'),
-    'bignn_gin_bn_finalize': ('i', 'ppii' 'f' 'pp' 'pp' 'p' 'pp' 's'),
+    'bignn_gin_layer_fwd': ('i', 'iii' 'ppip' 'pl' 'ppp' 'pip' 'f' 'pppp' 'ii' 'pl' 'pl' 'pl' 'p' 's'),
+    'bignn_gin_bn_finalize': ('i', 'ppii' 'f' 'p' 'pp' 'p' 'p' 's'),
     'bignn_pair_gather_norm_fwd': ('i', 'pl' 'pii' 'pl' 'p' 's'),
     'bignn_pair_gather_norm_bwd': ('i', 'pl' 'pii' 'pl' 'p' 'pl' 's'),
     'bignn_bce_fwd': ('i', 'ppips'),

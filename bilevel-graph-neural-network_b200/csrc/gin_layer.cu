@@ -21,6 +21,7 @@
 //                     128-bit stores, summing the BatchNorm statistics of the rows they store.
 // mbarriers: z_full/z_empty per slot (producers <-> MMA / epilogue), t_full (epilogue -> MMA), m1/m2 (tcgen05.commit).
 // Weights (hi and lo parts of W1, W2) stay resident in shared memory for every tile of the CTA.
+#include <cstdlib>
 #include "tc_common.cuh"
 
 namespace bignn {
@@ -28,7 +29,11 @@ namespace bignn {
 constexpr int GL_D = 64;                       // output width (and padded input width)
 constexpr int GL_SLOT = 4 * TC_BM * 128;       // [hi ch0][hi ch1][lo ch0][lo ch1], 16 KB each
 constexpr int GL_W = 2 * GL_D * 128;           // one weight part: two K chunks of [64 x 128 B]
-constexpr int GL_SMEM = 2 * GL_SLOT + 4 * GL_W + 1024;
+constexpr int GL_IDX_CAP = 1536;               // neighbour ids of one tile staged in shared memory (beyond: global reads)
+constexpr int GL_IDX_RP = 132;                 // row pointers of one tile (129 used)
+constexpr int GL_IDX_STAGES = 3;
+constexpr int GL_IDX_BYTES = (GL_IDX_RP + GL_IDX_CAP) * 4;
+constexpr int GL_SMEM = 2 * GL_SLOT + 4 * GL_W + GL_IDX_STAGES * GL_IDX_BYTES + 1024;
 constexpr int GL_EPI_WARPS = 4;
 constexpr int GL_NA = 2;                       // rotating main accumulators (as k_gemm_tc<64, .>)
 constexpr int GL_ACC_COLS = (GL_NA + 1) * GL_D;
@@ -49,6 +54,34 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// sum of the three accumulators of 16 columns, corrections first (the order of k_gemm_tc's epilogue)
+__device__ __forceinline__ void load_acc16(uint32_t tb, bool two_main, float (&v)[16]) {
+  uint32_t r0[16], r1[16];
+  tmem_ld16_nowait(tb + (uint32_t)(2 * 64), r0);
+  tmem_ld16_nowait(tb, r1);
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __fadd_rn(__uint_as_float(r1[j]), __uint_as_float(r0[j]));
+  if (two_main) {
+    tmem_ld16_nowait(tb + 64u, r0);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __fadd_rn(__uint_as_float(r0[j]), v[j]);
+  }
+}
+__device__ __forceinline__ float4 sub4(const float4& a, const float4& m) {
+  return make_float4(__fsub_rn(a.x, m.x), __fsub_rn(a.y, m.y), __fsub_rn(a.z, m.z), __fsub_rn(a.w, m.w));
+}
 __device__ __forceinline__ float4 f4z() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 __device__ __forceinline__ void add4(float4& a, const float4& v) {
   a.x = __fadd_rn(a.x, v.x); a.y = __fadd_rn(a.y, v.y); a.z = __fadd_rn(a.z, v.z); a.w = __fadd_rn(a.w, v.w);
@@ -63,10 +96,10 @@ __device__ __forceinline__ uint4 lo_part(const float4& x) {
 }
 
 struct GinLayerArgs {
-  int rows, din, n_tiles;
-  const int32_t* row_ptr; const int32_t* col_idx;
+  int rows, din, n_tiles, nnz, dbg;
+  const int32_t* row_ptr; const int32_t* col_idx; const int32_t* tile_edge_ptr;
   const float* X; int64_t ldx;
-  const float* fold_a; const float* fold_b;          // [S, din] or null
+  const float* fold_mean; const float* fold_a; const float* fold_beta;   // [S, din], [S, din], [din] or null
   const int32_t* chunk_row_ptr; const int32_t* tile_chunk0;
   float self_coef;
   const float* W1; const float* b1; const float* W2; const float* b2;
@@ -101,15 +134,17 @@ template <int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)
 k_gin_layer_fwd(const GinLayerArgs p) {
   constexpr int N_WARPS = THREADS / 32;
-  constexpr int N_PROD_WARPS = N_WARPS - GL_EPI_WARPS - 1;
-  constexpr int N_GROUPS = N_PROD_WARPS * 4;           // 8-lane groups
+  constexpr int N_PROD_WARPS = N_WARPS - GL_EPI_WARPS - 2;   // warp 4 = MMA issuer, warp 5 = index prefetch
+  constexpr int FIRST_PROD = GL_EPI_WARPS + 2;
+  constexpr int N_GROUPS = N_PROD_WARPS * 4;                 // 8-lane groups
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* w1_hi = smem + 2 * GL_SLOT;
   uint8_t* w1_lo = w1_hi + GL_W;
   uint8_t* w2_hi = w1_lo + GL_W;
   uint8_t* w2_lo = w2_hi + GL_W;
-  __shared__ uint64_t z_full[2], z_empty[2], t_full, m1_done, m2_done;
+  int32_t* idx_s = reinterpret_cast<int32_t*>(w2_lo + GL_W);      // [stages][rp 132 | col CAP]
+  __shared__ uint64_t z_full[2], z_empty[2], t_full, m1_done, m2_done, idx_full[GL_IDX_STAGES], idx_empty[GL_IDX_STAGES];
   __shared__ uint32_t tmem_base_s;
   __shared__ float b1_s[GL_D], b2_s[GL_D];
   __shared__ double red_s[2][8][GL_D];
@@ -128,6 +163,8 @@ k_gin_layer_fwd(const GinLayerArgs p) {
     mbar_init(&z_empty[0], GL_EPI_WARPS); mbar_init(&z_empty[1], GL_EPI_WARPS);
     mbar_init(&t_full, GL_EPI_WARPS);
     mbar_init(&m1_done, 1); mbar_init(&m2_done, 1);
+#pragma unroll
+    for (int s = 0; s < GL_IDX_STAGES; ++s) { mbar_init(&idx_full[s], 1); mbar_init(&idx_empty[s], N_PROD_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid < GL_D) {
@@ -156,31 +193,46 @@ k_gin_layer_fwd(const GinLayerArgs p) {
   const uint32_t tmem_d = tmem_base_s;
   const uint32_t acc1 = tmem_d, acc2 = tmem_d + (uint32_t)GL_ACC_COLS;
 
-  if (warp >= GL_EPI_WARPS + 1) {
+  if (warp >= FIRST_PROD) {
     // =============================================================== producers: z tiles
-    const int grp = (warp - GL_EPI_WARPS - 1) * 4 + (lane >> 3);
+    const int grp = (warp - FIRST_PROD) * 4 + (lane >> 3);
     const int l8 = lane & 7;
     const int din4 = (p.din + 3) >> 2;
     const bool ok0 = l8 < din4, ok1 = l8 + 8 < din4;
     const float* __restrict__ X = p.X;
     const int64_t ldx = p.ldx;
+    const bool fold = p.fold_a != nullptr;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const int b = it & 1;
+      const int st = it % GL_IDX_STAGES;
+      const int32_t* rp_s = idx_s + st * (GL_IDX_RP + GL_IDX_CAP);
+      const int32_t* col_s = rp_s + GL_IDX_RP;
+      mbar_wait(&idx_full[st], (it / GL_IDX_STAGES) & 1);
       mbar_wait(&z_empty[b], ((it >> 1) & 1) ^ 1);
       uint8_t* a_hi = smem + b * GL_SLOT;
       uint8_t* a_lo = a_hi + 2 * TC_BM * 128;
       const int m0 = tile * TC_BM;
-      int chunk = p.fold_a ? __ldg(p.tile_chunk0 + tile) : 0;
+      const int e_lo = rp_s[0] & ~3;                        // first staged neighbour id (16-byte aligned start)
+      int chunk = fold ? __ldg(p.tile_chunk0 + tile) : 0;
 #pragma unroll 1
       for (int r = grp; r < TC_BM; r += N_GROUPS) {
         const int grow = m0 + r;
         float4 z0 = f4z(), z1 = f4z();
-        if (grow < p.rows) {
-          const int k0 = __ldg(p.row_ptr + grow), k1 = __ldg(p.row_ptr + grow + 1);
+        if (grow < p.rows && !(p.dbg & 1)) {
+          const int k0 = rp_s[r], k1 = rp_s[r + 1];
           const float* xr = X + (int64_t)grow * ldx;
-          const float4 s0 = ok0 ? ldg4(xr + 4 * l8) : f4z();
-          const float4 s1 = ok1 ? ldg4(xr + 4 * (l8 + 8)) : f4z();
+          float4 s0 = ok0 ? ldg4(xr + 4 * l8) : f4z();
+          float4 s1 = ok1 ? ldg4(xr + 4 * (l8 + 8)) : f4z();
+          // BatchNorm of the producer layer folded in, centred: sum_j (a (y_j - mean) + beta) = a * sum_j (y_j - mean)
+          // + beta * (number of terms): the subtraction happens per loaded value (no cancellation of large sums)
+          float4 mu0 = f4z(), mu1 = f4z();
+          if (fold) {
+            while (grow >= __ldg(p.chunk_row_ptr + chunk + 1)) ++chunk;
+            const float* fm = p.fold_mean + (int64_t)chunk * p.din;
+            if (ok0) mu0 = ldg4(fm + 4 * l8);
+            if (ok1) mu1 = ldg4(fm + 4 * (l8 + 8));
+          }
           float4 a0 = f4z(), a1 = f4z();
           int cnt = 0;
           for (int k = k0; k < k1; k += 4) {
@@ -188,7 +240,9 @@ k_gin_layer_fwd(const GinLayerArgs p) {
             float4 v0[4], v1[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              c[u] = (k + u < k1) ? __ldg(p.col_idx + k + u) : -1;
+              const int kk = k + u;
+              c[u] = -1;
+              if (kk < k1) c[u] = (kk - e_lo < GL_IDX_CAP) ? col_s[kk - e_lo] : __ldg(p.col_idx + kk);
               if (c[u] == grow) c[u] = -1;                       // remove_self_loops (PyG GINConv)
             }
 #pragma unroll
@@ -199,27 +253,25 @@ k_gin_layer_fwd(const GinLayerArgs p) {
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              if (c[u] >= 0) { add4(a0, v0[u]); add4(a1, v1[u]); ++cnt; }
+              if (c[u] >= 0) { add4(a0, sub4(v0[u], mu0)); add4(a1, sub4(v1[u], mu1)); ++cnt; }
             }
           }
           const float sc = p.self_coef;
+          s0 = sub4(s0, mu0); s1 = sub4(s1, mu1);
           z0.x = __fadd_rn(__fmul_rn(sc, s0.x), a0.x); z0.y = __fadd_rn(__fmul_rn(sc, s0.y), a0.y);
           z0.z = __fadd_rn(__fmul_rn(sc, s0.z), a0.z); z0.w = __fadd_rn(__fmul_rn(sc, s0.w), a0.w);
           z1.x = __fadd_rn(__fmul_rn(sc, s1.x), a1.x); z1.y = __fadd_rn(__fmul_rn(sc, s1.y), a1.y);
           z1.z = __fadd_rn(__fmul_rn(sc, s1.z), a1.z); z1.w = __fadd_rn(__fmul_rn(sc, s1.w), a1.w);
-          if (p.fold_a) {
-            // BatchNorm of the producer layer folded in: sum_j (a*y_j + b) = a * sum_j y_j + b * (weights)
-            while (grow >= __ldg(p.chunk_row_ptr + chunk + 1)) ++chunk;
+          if (fold) {
             const float wsum = sc + (float)cnt;
             const float* fa = p.fold_a + (int64_t)chunk * p.din;
-            const float* fb = p.fold_b + (int64_t)chunk * p.din;
             if (ok0) {
-              const float4 A = ldg4(fa + 4 * l8), B = ldg4(fb + 4 * l8);
+              const float4 A = ldg4(fa + 4 * l8), B = ldg4(p.fold_beta + 4 * l8);
               z0.x = fmaf(A.x, z0.x, B.x * wsum); z0.y = fmaf(A.y, z0.y, B.y * wsum);
               z0.z = fmaf(A.z, z0.z, B.z * wsum); z0.w = fmaf(A.w, z0.w, B.w * wsum);
             }
             if (ok1) {
-              const float4 A = ldg4(fa + 4 * (l8 + 8)), B = ldg4(fb + 4 * (l8 + 8));
+              const float4 A = ldg4(fa + 4 * (l8 + 8)), B = ldg4(p.fold_beta + 4 * (l8 + 8));
               z1.x = fmaf(A.x, z1.x, B.x * wsum); z1.y = fmaf(A.y, z1.y, B.y * wsum);
               z1.z = fmaf(A.z, z1.z, B.z * wsum); z1.w = fmaf(A.w, z1.w, B.w * wsum);
             }
@@ -233,7 +285,33 @@ k_gin_layer_fwd(const GinLayerArgs p) {
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core proxy
       __syncwarp();
-      if (lane == 0) mbar_arrive(&z_full[b]);
+      if (lane == 0) { mbar_arrive(&z_full[b]); mbar_arrive(&idx_empty[st]); }
+    }
+  } else if (warp == GL_EPI_WARPS + 1) {
+    // =============================================================== index prefetch: row pointers + neighbour ids of
+    // the tiles ahead, as coalesced 16-byte cp.async copies (the producers' only dependent global hop left is X)
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const int st = it % GL_IDX_STAGES;
+      int32_t* rp_s = idx_s + st * (GL_IDX_RP + GL_IDX_CAP);
+      int32_t* col_s = rp_s + GL_IDX_RP;
+      const int e0 = __ldg(p.tile_edge_ptr + tile) & ~3, e1 = __ldg(p.tile_edge_ptr + tile + 1);
+      mbar_wait(&idx_empty[st], ((it / GL_IDX_STAGES) & 1) ^ 1);
+      const int m0 = tile * TC_BM;
+      const int n_rp = min(TC_BM, p.rows - m0) + 1;                       // row pointers of this tile
+      for (int j = lane * 4; j < GL_IDX_RP; j += 128) {
+        const int left = n_rp - j;
+        cp_async16(smem_u32(rp_s + j), p.row_ptr + m0 + (left > 0 ? j : 0), left >= 4 ? 16u : (left > 0 ? 4u * left : 0u));
+      }
+      const int n_col = min(e1 - e0, GL_IDX_CAP);
+      for (int j = lane * 4; j < n_col; j += 128) {
+        const int left = min(n_col - j, p.nnz - (e0 + j));
+        cp_async16(smem_u32(col_s + j), p.col_idx + e0 + j, left >= 4 ? 16u : 4u * left);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&idx_full[st]);
     }
   } else if (warp == GL_EPI_WARPS) {
     // =============================================================== MMA issuer
@@ -263,7 +341,10 @@ k_gin_layer_fwd(const GinLayerArgs p) {
     const int row = warp * 32 + lane;                       // tile row this thread reads from TMEM
     const int et = tid;                                     // 0..127
     const int c4 = et & 15, rg = et >> 4;                   // copy-out: 16-byte column chunk, row group (8 groups)
-    const int n_main1 = (K1 + 7) / 8 < GL_NA ? (K1 + 7) / 8 : GL_NA;
+    const bool two_main1 = (K1 + 7) / 8 >= GL_NA;
+    const uint32_t row_off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
+    const int row7 = row & 7;
+    const bool store = !(p.dbg & 2);
     int it = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const int b = it & 1;
@@ -272,43 +353,38 @@ k_gin_layer_fwd(const GinLayerArgs p) {
       const int m0 = tile * TC_BM;
       const int rows_here = min(TC_BM, p.rows - m0);
       const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+      const uint8_t* src = a_hi + (c4 >> 3) * (TC_BM * 128);
       // ---------------- first transform done: z may leave (kept for the backward), t goes back in
       mbar_wait(&m1_done, it & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (p.Z) {
+        if (store && c4 < ((p.din + 3) >> 2)) {
 #pragma unroll 4
-        for (int i = 0; i < 16; ++i) {
-          const int r = rg + 8 * i;
-          if (r < rows_here && c4 < ((p.din + 3) >> 2))
-            st4(p.Z + (int64_t)(m0 + r) * p.ldz + 4 * c4,
-                *reinterpret_cast<const float4*>(a_hi + (c4 >> 3) * (TC_BM * 128) + sw128_off(r, c4 & 7)));
+          for (int i = 0; i < 16; ++i) {
+            const int r = rg + 8 * i;
+            if (r < rows_here)
+              st4(p.Z + (int64_t)(m0 + r) * p.ldz + 4 * c4, *reinterpret_cast<const float4*>(src + sw128_off(r, c4 & 7)));
+          }
         }
         named_bar_sync(1, GL_EPI_WARPS * 32);               // every z row is out before any t row comes in
       }
 #pragma unroll 1
       for (int cb = 0; cb < GL_D; cb += 16) {
-        uint32_t r[16];
         float v[16];
-        const uint32_t tb = acc1 + lane_off + (uint32_t)cb;
-        tmem_ld16(tb + (uint32_t)(GL_NA * GL_D), r);        // corrections first (small)
+        load_acc16(acc1 + lane_off + (uint32_t)cb, two_main1, v);
+        if (p.act_inner == BIGNN_ACT_RELU) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-        tmem_ld16(tb, r);
+          for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j] + b1_s[cb + j], 0.f);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __fadd_rn(__uint_as_float(r[j]), v[j]);
-        if (n_main1 == 2) {
-          tmem_ld16(tb + (uint32_t)GL_D, r);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __fadd_rn(__uint_as_float(r[j]), v[j]);
+          for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j] + b1_s[cb + j], p.act_inner);
         }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j] + b1_s[cb + j], p.act_inner);
-        uint8_t* hi = a_hi + (cb >> 5) * (TC_BM * 128);
-        uint8_t* lo = a_lo + (cb >> 5) * (TC_BM * 128);
+        uint8_t* hi = a_hi + (cb >> 5) * (TC_BM * 128) + row_off;
+        uint8_t* lo = a_lo + (cb >> 5) * (TC_BM * 128) + row_off;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const float4 tv = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-          const uint32_t off = sw128_off(row, ((cb & 31) >> 2) + c);
+          const uint32_t off = (uint32_t)(((((cb & 31) >> 2) + c) ^ row7) << 4);
           *reinterpret_cast<float4*>(hi + off) = tv;
           *reinterpret_cast<uint4*>(lo + off) = lo_part(tv);
         }
@@ -319,12 +395,13 @@ k_gin_layer_fwd(const GinLayerArgs p) {
       if (lane == 0) mbar_arrive(&t_full);
       if (p.T) {
         named_bar_sync(1, GL_EPI_WARPS * 32);               // all of t is in the slot; copy it out while the MMA runs
+        if (store) {
 #pragma unroll 4
-        for (int i = 0; i < 16; ++i) {
-          const int r = rg + 8 * i;
-          if (r < rows_here)
-            st4(p.T + (int64_t)(m0 + r) * p.ldt + 4 * c4,
-                *reinterpret_cast<const float4*>(a_hi + (c4 >> 3) * (TC_BM * 128) + sw128_off(r, c4 & 7)));
+          for (int i = 0; i < 16; ++i) {
+            const int r = rg + 8 * i;
+            if (r < rows_here)
+              st4(p.T + (int64_t)(m0 + r) * p.ldt + 4 * c4, *reinterpret_cast<const float4*>(src + sw128_off(r, c4 & 7)));
+          }
         }
       }
       // ---------------- second transform done: y = act(acc + b2) staged in the slot (t has been consumed)
@@ -333,49 +410,62 @@ k_gin_layer_fwd(const GinLayerArgs p) {
       if (p.T) named_bar_sync(1, GL_EPI_WARPS * 32);        // the T copy-out above has read the whole slot
 #pragma unroll 1
       for (int cb = 0; cb < GL_D; cb += 16) {
-        uint32_t r[16];
         float v[16];
-        const uint32_t tb = acc2 + lane_off + (uint32_t)cb;
-        tmem_ld16(tb + (uint32_t)(GL_NA * GL_D), r);
+        load_acc16(acc2 + lane_off + (uint32_t)cb, true, v);
+        if (p.act_outer == BIGNN_ACT_RELU) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-        tmem_ld16(tb, r);
+          for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j] + b2_s[cb + j], 0.f);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __fadd_rn(__uint_as_float(r[j]), v[j]);
-        tmem_ld16(tb + (uint32_t)GL_D, r);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __fadd_rn(__uint_as_float(r[j]), v[j]);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j] + b2_s[cb + j], p.act_outer);
-        uint8_t* hi = a_hi + (cb >> 5) * (TC_BM * 128);
+          for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j] + b2_s[cb + j], p.act_outer);
+        }
+        uint8_t* hi = a_hi + (cb >> 5) * (TC_BM * 128) + row_off;
 #pragma unroll
         for (int c = 0; c < 4; ++c)
-          *reinterpret_cast<float4*>(hi + sw128_off(row, ((cb & 31) >> 2) + c)) =
+          *reinterpret_cast<float4*>(hi + (uint32_t)(((((cb & 31) >> 2) + c) ^ row7) << 4)) =
               make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       named_bar_sync(1, GL_EPI_WARPS * 32);
-      // ---------------- coalesced copy-out
-      const uint8_t* src = a_hi + (c4 >> 3) * (TC_BM * 128);
-#pragma unroll 4
-      for (int i = 0; i < 16; ++i) {
-        const int r = rg + 8 * i;
-        if (r < rows_here)
-          st4(p.Y + (int64_t)(m0 + r) * p.ldy + 4 * c4, *reinterpret_cast<const float4*>(src + sw128_off(r, c4 & 7)));
-      }
-      // ---------------- BatchNorm partial sums of the stored rows, per (tile, chunk) record
+      // ---------------- coalesced copy-out (+ BatchNorm partial sums of the stored rows when the tile lies in one chunk)
+      int chunk = 0, chunk_end = rows_here;
       if (p.stat_parts) {
-        int chunk = __ldg(p.tile_chunk0 + tile);
+        chunk = __ldg(p.tile_chunk0 + tile);
+        chunk_end = __ldg(p.chunk_row_ptr + chunk + 1) - m0;
+      }
+      const bool one_chunk = chunk_end >= rows_here;
+      double s[4] = {0.0, 0.0, 0.0, 0.0}, ss[4] = {0.0, 0.0, 0.0, 0.0};
+      if (store) {
+#pragma unroll 4
+        for (int i = 0; i < 16; ++i) {
+          const int r = rg + 8 * i;
+          if (r < rows_here) {
+            const float4 o = *reinterpret_cast<const float4*>(src + sw128_off(r, c4 & 7));
+            st4(p.Y + (int64_t)(m0 + r) * p.ldy + 4 * c4, o);
+            if (one_chunk) {
+              s[0] += (double)o.x; ss[0] += (double)o.x * (double)o.x;
+              s[1] += (double)o.y; ss[1] += (double)o.y * (double)o.y;
+              s[2] += (double)o.z; ss[2] += (double)o.z * (double)o.z;
+              s[3] += (double)o.w; ss[3] += (double)o.w * (double)o.w;
+            }
+          }
+        }
+      }
+      // ---------------- BatchNorm partial sums per (tile, chunk) record
+      if (p.stat_parts) {
         int lo_r = 0;
         while (lo_r < rows_here) {
-          const int hi_r = min(rows_here, __ldg(p.chunk_row_ptr + chunk + 1) - m0);
-          double s[4] = {0.0, 0.0, 0.0, 0.0}, ss[4] = {0.0, 0.0, 0.0, 0.0};
-          for (int r = lo_r + ((rg - lo_r) & 7); r < hi_r; r += 8) {
-            const float4 o = *reinterpret_cast<const float4*>(src + sw128_off(r, c4 & 7));
-            s[0] += (double)o.x; ss[0] += (double)o.x * (double)o.x;
-            s[1] += (double)o.y; ss[1] += (double)o.y * (double)o.y;
-            s[2] += (double)o.z; ss[2] += (double)o.z * (double)o.z;
-            s[3] += (double)o.w; ss[3] += (double)o.w * (double)o.w;
+          const int hi_r = one_chunk ? rows_here : min(rows_here, __ldg(p.chunk_row_ptr + chunk + 1) - m0);
+          if (!one_chunk) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { s[j] = 0.0; ss[j] = 0.0; }
+            for (int r = lo_r + ((rg - lo_r) & 7); r < hi_r; r += 8) {
+              const float4 o = *reinterpret_cast<const float4*>(src + sw128_off(r, c4 & 7));
+              s[0] += (double)o.x; ss[0] += (double)o.x * (double)o.x;
+              s[1] += (double)o.y; ss[1] += (double)o.y * (double)o.y;
+              s[2] += (double)o.z; ss[2] += (double)o.z * (double)o.z;
+              s[3] += (double)o.w; ss[3] += (double)o.w * (double)o.w;
+            }
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) { red_s[0][rg][4 * c4 + j] = s[j]; red_s[1][rg][4 * c4 + j] = ss[j]; }
@@ -396,6 +486,7 @@ k_gin_layer_fwd(const GinLayerArgs p) {
       if (lane == 0) mbar_arrive(&z_empty[b]);
     }
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) {
@@ -404,12 +495,12 @@ k_gin_layer_fwd(const GinLayerArgs p) {
 }
 
 // ---- per-chunk statistics from the (tile, chunk) records, in tile order (deterministic); also the affine
-// (fold_a, fold_b) = (gamma*rstd, beta - mean*gamma*rstd) that the consumer layer folds into its aggregation.
+// fold_a = gamma*rstd that -- with mean and beta -- the consumer layer folds into its aggregation.
 __global__ void __launch_bounds__(GL_D)
 k_gin_bn_finalize(const double* __restrict__ stat_parts, const int32_t* __restrict__ chunk_row_ptr, int S, float eps,
-                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                  const float* __restrict__ gamma,
                   float* __restrict__ mean, float* __restrict__ rstd, double* __restrict__ mean_d,
-                  double* __restrict__ varu_d, float* __restrict__ fold_a, float* __restrict__ fold_b) {
+                  double* __restrict__ varu_d, float* __restrict__ fold_a) {
   const int c = threadIdx.x;
   for (int s = blockIdx.x; s < S; s += gridDim.x) {
     const int lo = chunk_row_ptr[s], hi = chunk_row_ptr[s + 1];
@@ -435,10 +526,7 @@ k_gin_bn_finalize(const double* __restrict__ stat_parts, const int32_t* __restri
     rstd[i] = r_f;
     mean_d[i] = mu;
     varu_d[i] = n > 1 ? var * ((double)n / (double)(n - 1)) : var;
-    const float g = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
-    const float fa = g * r_f;
-    fold_a[i] = fa;
-    fold_b[i] = be - m_f * fa;
+    fold_a[i] = (gamma ? gamma[c] : 1.f) * r_f;
   }
 }
 
@@ -455,35 +543,41 @@ extern "C" int bignn_gin_layer_supported(int32_t din, int32_t dout) {
 }
 
 extern "C" int bignn_gin_layer_fwd(int32_t rows, int32_t din, int32_t dout, const int32_t* row_ptr,
-                                   const int32_t* col_idx, const float* X, int64_t ldx, const float* fold_a,
-                                   const float* fold_b, const int32_t* chunk_row_ptr, int32_t S,
-                                   const int32_t* tile_chunk0, float self_coef, const float* W1, const float* b1,
-                                   const float* W2, const float* b2, int32_t act_inner, int32_t act_outer, float* Z,
-                                   int64_t ldz, float* T, int64_t ldt, float* Y, int64_t ldy, double* stat_parts,
-                                   void* stream) {
-  if (rows < 0) return BIGNN_EINVAL;
+                                   const int32_t* col_idx, int32_t nnz, const int32_t* tile_edge_ptr, const float* X,
+                                   int64_t ldx, const float* fold_mean, const float* fold_a, const float* fold_beta,
+                                   const int32_t* chunk_row_ptr, int32_t S, const int32_t* tile_chunk0,
+                                   float self_coef, const float* W1, const float* b1, const float* W2, const float* b2,
+                                   int32_t act_inner, int32_t act_outer, float* Z, int64_t ldz, float* T, int64_t ldt,
+                                   float* Y, int64_t ldy, double* stat_parts, void* stream) {
+  if (rows < 0 || nnz < 0) return BIGNN_EINVAL;
   if (rows == 0) return 0;
   if (!bignn_gin_layer_supported(din, dout)) return BIGNN_EINVAL;
   const int din_pad = (din + 3) & ~3;
-  if (!row_ptr || !col_idx || !X || !W1 || !W2 || !Y || ldx < din_pad || ldy < dout) return BIGNN_EINVAL;
-  if (fold_a && (din & 3)) return BIGNN_EINVAL;
-  if ((fold_a != nullptr) != (fold_b != nullptr)) return BIGNN_EINVAL;
-  if ((fold_a || stat_parts) && (!chunk_row_ptr || !tile_chunk0 || S <= 0)) return BIGNN_EINVAL;
+  if (!row_ptr || !col_idx || !tile_edge_ptr || !X || !W1 || !W2 || !Y || ldx < din_pad || ldy < dout) return BIGNN_EINVAL;
+  const bool fold = fold_a != nullptr;
+  if (fold != (fold_mean != nullptr) || fold != (fold_beta != nullptr)) return BIGNN_EINVAL;
+  if (fold && (din & 3)) return BIGNN_EINVAL;
+  if ((fold || stat_parts) && (!chunk_row_ptr || !tile_chunk0 || S <= 0)) return BIGNN_EINVAL;
   if ((Z && ldz < din_pad) || (T && ldt < dout)) return BIGNN_EINVAL;
   if (act_inner < 0 || act_inner > BIGNN_ACT_TANH || act_outer < 0 || act_outer > BIGNN_ACT_TANH) return BIGNN_EINVAL;
   if ((ldx & 3) || (ldy & 3) || !aligned16(X) || !aligned16(Y) || (Z && ((ldz & 3) || !aligned16(Z))) ||
-      (T && ((ldt & 3) || !aligned16(T))) || (fold_a && (!aligned16(fold_a) || !aligned16(fold_b))))
+      (T && ((ldt & 3) || !aligned16(T))) || !aligned16(row_ptr) || !aligned16(col_idx) ||
+      (fold && (!aligned16(fold_a) || !aligned16(fold_mean) || !aligned16(fold_beta))))
     return BIGNN_EALIGN;
-  constexpr int THREADS = 768;
+  constexpr int THREADS = 768;      // 24 warps: 4 epilogue, MMA, index prefetch, 18 producers = 72 row groups
   static bool configured = false;
+  static int dbg = 0;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(k_gin_layer_fwd<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, GL_SMEM);
     if (e != cudaSuccess) return (int)e;
+    const char* d = getenv("BIGNN_GL_DEBUG");     // timing experiments only: 1 = no gathers, 2 = no stores (results invalid)
+    dbg = d ? atoi(d) : 0;
     configured = true;
   }
   GinLayerArgs a;
-  a.rows = rows; a.din = din; a.n_tiles = ceil_div(rows, TC_BM);
-  a.row_ptr = row_ptr; a.col_idx = col_idx; a.X = X; a.ldx = ldx; a.fold_a = fold_a; a.fold_b = fold_b;
+  a.rows = rows; a.din = din; a.n_tiles = ceil_div(rows, TC_BM); a.nnz = nnz; a.dbg = dbg;
+  a.row_ptr = row_ptr; a.col_idx = col_idx; a.tile_edge_ptr = tile_edge_ptr; a.X = X; a.ldx = ldx;
+  a.fold_mean = fold_mean; a.fold_a = fold_a; a.fold_beta = fold_beta;
   a.chunk_row_ptr = chunk_row_ptr; a.tile_chunk0 = tile_chunk0; a.self_coef = self_coef;
   a.W1 = W1; a.b1 = b1; a.W2 = W2; a.b2 = b2; a.act_inner = act_inner; a.act_outer = act_outer;
   a.Z = Z; a.ldz = ldz; a.T = T; a.ldt = ldt; a.Y = Y; a.ldy = ldy; a.stat_parts = stat_parts;
@@ -495,15 +589,14 @@ extern "C" int bignn_gin_layer_fwd(int32_t rows, int32_t din, int32_t dout, cons
 }
 
 extern "C" int bignn_gin_bn_finalize(const double* stat_parts, const int32_t* chunk_row_ptr, int32_t S, int32_t C,
-                                     float eps, const float* gamma, const float* beta, float* mean, float* rstd,
-                                     double* seg_stats_out, float* fold_a, float* fold_b, void* stream) {
+                                     float eps, const float* gamma, float* mean, float* rstd,
+                                     double* seg_stats_out, float* fold_a, void* stream) {
   if (S < 0 || C != GL_D) return BIGNN_EINVAL;
   if (S == 0) return 0;
-  if (!stat_parts || !chunk_row_ptr || !mean || !rstd || !seg_stats_out || !fold_a || !fold_b) return BIGNN_EINVAL;
+  if (!stat_parts || !chunk_row_ptr || !mean || !rstd || !seg_stats_out || !fold_a) return BIGNN_EINVAL;
   int grid = S < 4 * sm_count() ? S : 4 * sm_count();
-  k_gin_bn_finalize<<<grid, GL_D, 0, (cudaStream_t)stream>>>(stat_parts, chunk_row_ptr, S, eps, gamma, beta, mean, rstd,
-                                                            seg_stats_out, seg_stats_out + (int64_t)S * C, fold_a,
-                                                            fold_b);
+  k_gin_bn_finalize<<<grid, GL_D, 0, (cudaStream_t)stream>>>(stat_parts, chunk_row_ptr, S, eps, gamma, mean, rstd,
+                                                            seg_stats_out, seg_stats_out + (int64_t)S * C, fold_a);
   BIGNN_LAUNCH_COUNT(1);
   return last_launch_status();
 }

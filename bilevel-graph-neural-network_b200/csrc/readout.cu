@@ -12,22 +12,29 @@ template <int L>
 __global__ void __launch_bounds__(256)
 k_readout_fwd_v4(const float* __restrict__ X, int64_t ldx, const int32_t* __restrict__ seg_ptr, int G, int D4,
                  int style, const int32_t* __restrict__ dst_row, float* __restrict__ out, int64_t ldo,
-                 const float* __restrict__ fold_a, const float* __restrict__ fold_b,
-                 const int32_t* __restrict__ graph_chunk) {
+                 const float* __restrict__ fold_mean, const float* __restrict__ fold_a,
+                 const float* __restrict__ fold_beta, const int32_t* __restrict__ graph_chunk) {
   const int gpb = blockDim.x / L;
   const int sub = threadIdx.x / L, lane = threadIdx.x % L;
   for (int g = blockIdx.x * gpb + sub; g < G; g += gridDim.x * gpb) {
     const int r0 = __ldg(seg_ptr + g), r1 = __ldg(seg_ptr + g + 1);
     const int n = r1 - r0;
     const int64_t orow = dst_row ? dst_row[g] : g;
+    const int64_t ch = (fold_a && graph_chunk) ? graph_chunk[g] : 0;
     for (int q = lane; q < D4; q += L) {
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      // folded BatchNorm, centred: pool(a (x - mean) + beta) = a * pool(x - mean) + beta * (1 | n)
+      const float4 mu = fold_a ? ldg4(fold_mean + (ch * D4 + q) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       int r = r0;
       for (; r + 4 <= r1; r += 4) {
-        const float4 v0 = ldg4(X + (int64_t)(r + 0) * ldx + 4 * q);
-        const float4 v1 = ldg4(X + (int64_t)(r + 1) * ldx + 4 * q);
-        const float4 v2 = ldg4(X + (int64_t)(r + 2) * ldx + 4 * q);
-        const float4 v3 = ldg4(X + (int64_t)(r + 3) * ldx + 4 * q);
+        float4 v0 = ldg4(X + (int64_t)(r + 0) * ldx + 4 * q);
+        float4 v1 = ldg4(X + (int64_t)(r + 1) * ldx + 4 * q);
+        float4 v2 = ldg4(X + (int64_t)(r + 2) * ldx + 4 * q);
+        float4 v3 = ldg4(X + (int64_t)(r + 3) * ldx + 4 * q);
+        if (fold_a) {
+          v0.x -= mu.x; v0.y -= mu.y; v0.z -= mu.z; v0.w -= mu.w;  v1.x -= mu.x; v1.y -= mu.y; v1.z -= mu.z; v1.w -= mu.w;
+          v2.x -= mu.x; v2.y -= mu.y; v2.z -= mu.z; v2.w -= mu.w;  v3.x -= mu.x; v3.y -= mu.y; v3.z -= mu.z; v3.w -= mu.w;
+        }
         acc.x = (((acc.x + v0.x) + v1.x) + v2.x) + v3.x;
         acc.y = (((acc.y + v0.y) + v1.y) + v2.y) + v3.y;
         acc.z = (((acc.z + v0.z) + v1.z) + v2.z) + v3.z;
@@ -35,7 +42,7 @@ k_readout_fwd_v4(const float* __restrict__ X, int64_t ldx, const int32_t* __rest
       }
       for (; r < r1; ++r) {
         const float4 v = ldg4(X + (int64_t)r * ldx + 4 * q);
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        acc.x += v.x - mu.x; acc.y += v.y - mu.y; acc.z += v.z - mu.z; acc.w += v.w - mu.w;
       }
       if (style == BIGNN_READOUT_MEAN) {
         const float cnt = (float)(n > 1 ? n : 1);      // count.clamp(min=1)
@@ -43,8 +50,7 @@ k_readout_fwd_v4(const float* __restrict__ X, int64_t ldx, const int32_t* __rest
         acc.z = __fdiv_rn(acc.z, cnt); acc.w = __fdiv_rn(acc.w, cnt);
       }
       if (fold_a) {                                    // BatchNorm affine of the pooled rows, folded in
-        const int64_t c = graph_chunk ? graph_chunk[g] : 0;
-        const float4 a = ldg4(fold_a + (c * D4 + q) * 4), b = ldg4(fold_b + (c * D4 + q) * 4);
+        const float4 a = ldg4(fold_a + (ch * D4 + q) * 4), b = ldg4(fold_beta + 4 * q);
         const float w = style == BIGNN_READOUT_MEAN ? (n > 0 ? 1.f : 0.f) : (float)n;
         acc.x = fmaf(a.x, acc.x, b.x * w); acc.y = fmaf(a.y, acc.y, b.y * w);
         acc.z = fmaf(a.z, acc.z, b.z * w); acc.w = fmaf(a.w, acc.w, b.w * w);
@@ -100,16 +106,16 @@ k_readout_bwd(const float* __restrict__ dOut, int64_t ldo, const int32_t* __rest
 using namespace bignn;
 
 extern "C" int bignn_readout_fold_fwd(const float* X, int64_t ldx, const int32_t* seg_ptr, int32_t G, int32_t D,
-                                      int32_t style, const int32_t* dst_row, const float* fold_a,
-                                      const float* fold_b, const int32_t* graph_chunk, float* out, int64_t ldo,
-                                      int32_t col_off, void* stream) {
+                                      int32_t style, const int32_t* dst_row, const float* fold_mean,
+                                      const float* fold_a, const float* fold_beta, const int32_t* graph_chunk,
+                                      float* out, int64_t ldo, int32_t col_off, void* stream) {
   if (G < 0 || D < 0 || col_off < 0) return BIGNN_EINVAL;
   if (G == 0 || D == 0) return 0;
   if (!X || !seg_ptr || !out || ldx < D || ldo < col_off + D) return BIGNN_EINVAL;
   if (style != BIGNN_READOUT_SUM && style != BIGNN_READOUT_MEAN) return BIGNN_EINVAL;
-  if ((fold_a != nullptr) != (fold_b != nullptr)) return BIGNN_EINVAL;
+  if ((fold_a != nullptr) != (fold_mean != nullptr) || (fold_a != nullptr) != (fold_beta != nullptr)) return BIGNN_EINVAL;
   if (fold_a && ((D % 4) || (ldx % 4) || (ldo % 4) || (col_off % 4) || !aligned16(X) || !aligned16(out) ||
-                 !aligned16(fold_a) || !aligned16(fold_b)))
+                 !aligned16(fold_a) || !aligned16(fold_mean) || !aligned16(fold_beta)))
     return BIGNN_EALIGN;
   cudaStream_t st = (cudaStream_t)stream;
   float* o = out + col_off;
@@ -120,11 +126,11 @@ extern "C" int bignn_readout_fold_fwd(const float* X, int64_t ldx, const int32_t
     if (d4 <= 16) {
       int grid = ceil_div(G, 16);
       if (grid > cap) grid = cap;
-      k_readout_fwd_v4<16><<<grid, 256, 0, st>>>(X, ldx, seg_ptr, G, d4, style, dst_row, o, ldo, fold_a, fold_b, graph_chunk);
+      k_readout_fwd_v4<16><<<grid, 256, 0, st>>>(X, ldx, seg_ptr, G, d4, style, dst_row, o, ldo, fold_mean, fold_a, fold_beta, graph_chunk);
     } else {
       int grid = ceil_div(G, 8);
       if (grid > cap) grid = cap;
-      k_readout_fwd_v4<32><<<grid, 256, 0, st>>>(X, ldx, seg_ptr, G, d4, style, dst_row, o, ldo, fold_a, fold_b, graph_chunk);
+      k_readout_fwd_v4<32><<<grid, 256, 0, st>>>(X, ldx, seg_ptr, G, d4, style, dst_row, o, ldo, fold_mean, fold_a, fold_beta, graph_chunk);
     }
   } else {
     int grid = ceil_div(G, 8);
@@ -138,8 +144,8 @@ extern "C" int bignn_readout_fold_fwd(const float* X, int64_t ldx, const int32_t
 extern "C" int bignn_readout_fwd(const float* X, int64_t ldx, const int32_t* seg_ptr, int32_t G, int32_t D,
                                  int32_t style, const int32_t* dst_row, float* out, int64_t ldo,
                                  int32_t col_off, void* stream) {
-  return bignn_readout_fold_fwd(X, ldx, seg_ptr, G, D, style, dst_row, nullptr, nullptr, nullptr, out, ldo, col_off,
-                                stream);
+  return bignn_readout_fold_fwd(X, ldx, seg_ptr, G, D, style, dst_row, nullptr, nullptr, nullptr, nullptr, out, ldo,
+                                col_off, stream);
 }
 
 extern "C" int bignn_readout_bwd(const float* dOut, int64_t ldo, int32_t col_off, const int32_t* dst_row,

@@ -63,8 +63,8 @@ class _GinStack(torch.autograd.Function):
         plan = m.fused_plan()
         A, S, dev = m.A, m.S, x0.device
         _lib.require_device(x0)
-        grad_on = training and torch.is_grad_enabled()
-        X, fa, fb = x0, None, None
+        grad_on = training and any(ctx.needs_input_grad)      # (autograd is off inside forward: ask the ctx)
+        X, fm, fa, fbeta = x0, None, None, None
         saved, levels = [], []
         L = len(spec.layers)
         for li, layer in enumerate(spec.layers):
@@ -78,7 +78,8 @@ class _GinStack(torch.autograd.Function):
             T = torch.empty((A, 64), dtype=torch.float32, device=dev) if grad_on else None
             parts = torch.empty((plan['records'], 2, 64), dtype=torch.float64, device=dev) if training else None
             bn = layer.bn
-            _lib.call('bignn_gin_layer_fwd', A, int(din), 64, m.row_ptr, m.col_idx, X, X.stride(0), fa, fb,
+            _lib.call('bignn_gin_layer_fwd', A, int(din), 64, m.row_ptr, m.col_idx, m.E, plan['tile_edge_ptr'], X,
+                      X.stride(0), fm, fa, fbeta,
                       m.chunk_row_ptr, S, plan['tile_chunk0'], 1.0 + layer._eps_value(), W1.contiguous(), b1, W2.contiguous(),
                       b2, int(a_in), int(a_out), Z, Z.stride(0) if Z is not None else 0, T,
                       T.stride(0) if T is not None else 0, Y, Y.stride(0), parts)
@@ -87,9 +88,9 @@ class _GinStack(torch.autograd.Function):
                 rstd = torch.empty((S, 64), dtype=torch.float32, device=dev)
                 stats = torch.empty((2, S, 64), dtype=torch.float64, device=dev)
                 fa = torch.empty((S, 64), dtype=torch.float32, device=dev)
-                fb = torch.empty((S, 64), dtype=torch.float32, device=dev)
-                _lib.call('bignn_gin_bn_finalize', parts, m.chunk_row_ptr, S, 64, float(bn.eps), gamma, beta, mean,
-                          rstd, stats, fa, fb)
+                _lib.call('bignn_gin_bn_finalize', parts, m.chunk_row_ptr, S, 64, float(bn.eps), gamma, mean, rstd,
+                          stats, fa)
+                fm = mean
                 if spec.sink is not None:
                     spec.sink.append((bn, stats))          # sharded chunks: the engine replays the running updates
                 else:
@@ -97,25 +98,25 @@ class _GinStack(torch.autograd.Function):
                                           bn.num_batches_tracked, bn.momentum)
             else:
                 # eval: running statistics, the same affine for every chunk
-                a1 = gamma * torch.rsqrt(bn.running_var + bn.eps)
-                fa = a1.unsqueeze(0).expand(S, 64).contiguous()
-                fb = (beta - bn.running_mean * a1).unsqueeze(0).expand(S, 64).contiguous()
+                fa = (gamma * torch.rsqrt(bn.running_var + bn.eps)).unsqueeze(0).expand(S, 64).contiguous()
+                fm = bn.running_mean.unsqueeze(0).expand(S, 64).contiguous()
                 mean = rstd = None
+            fbeta = beta
             saved.append((Y, Z, T, mean, rstd, int(a_in), int(a_out), int(din)))
             if spec.multi or li == L - 1:
-                levels.append((li, Y, fa, fb))
+                levels.append((li, Y, fm, fa, fbeta))
             X = Y
         nl = len(levels)
         out_rows = spec.out_rows if spec.out_rows is not None else m.G
         alloc = torch.zeros if spec.dst_row is not None else torch.empty
         out = alloc((out_rows, nl * 64), dtype=torch.float32, device=dev)
-        for k, (li, Y, a, b) in enumerate(levels):
-            _lib.call('bignn_readout_fold_fwd', Y, Y.stride(0), m.seg_ptr, m.G, 64, spec.style, spec.dst_row, a, b,
+        for k, (li, Y, mu, a, b) in enumerate(levels):
+            _lib.call('bignn_readout_fold_fwd', Y, Y.stride(0), m.seg_ptr, m.G, 64, spec.style, spec.dst_row, mu, a, b,
                       plan['graph_chunk'], out, out.stride(0), k * 64)
         if spec.keep_acts:
             spec.last_levels = levels
         ctx.spec, ctx.saved, ctx.params = spec, saved, params
-        ctx.level_of = {li: k for k, (li, _, _, _) in enumerate(levels)}
+        ctx.level_of = {lv[0]: k for k, lv in enumerate(levels)}
         return out
 
     @staticmethod
@@ -174,8 +175,8 @@ def level_activations(spec):
     """BatchNorm outputs of the pooled levels of the last forward (tests only: one elementwise pass each)."""
     m = spec.merged
     outs = []
-    for li, Y, a, b in spec.last_levels:
+    for li, Y, mu, a, b in spec.last_levels:
         seg = torch.repeat_interleave(torch.arange(m.S, device=Y.device),
                                       (m.chunk_row_ptr[1:] - m.chunk_row_ptr[:-1]).long())
-        outs.append(Y * a[seg] + b[seg])
+        outs.append((Y - mu[seg]) * a[seg] + b)
     return outs

@@ -117,8 +117,12 @@ class MergedGraph(object):
             tile0 = np.searchsorted(crp, np.arange(n_tiles, dtype=np.int64) * 128, side='right') - 1
             tile0 = np.clip(tile0, 0, max(self.S - 1, 0))
             gchunk = np.searchsorted(self.chunk_graph_ptr_host, np.arange(self.G, dtype=np.int64), side='right') - 1
+            # first CSR entry of every tile (row_ptr[128 t], row_ptr[A] last): lets the kernel prefetch a tile's
+            # neighbour ids without first waiting for its row pointers
+            pos = torch.as_tensor(np.minimum(np.arange(n_tiles + 1, dtype=np.int64) * 128, self.A)).to(dev)
+            tile_edge = self.row_ptr.index_select(0, pos).contiguous()
             self._fused_plan = dict(tile_chunk0=_i32(tile0, dev), graph_chunk=_i32(np.clip(gchunk, 0, max(self.S - 1, 0)), dev),
-                                    n_tiles=int(n_tiles), records=int(n_tiles + self.S))
+                                    tile_edge_ptr=tile_edge, n_tiles=int(n_tiles), records=int(n_tiles + self.S))
         return self._fused_plan
 
     @property

@@ -250,32 +250,35 @@ int bignn_bn_rows_bwd_apply(const float* X, int64_t ldx, const float* dY, int64_
  * One lower-level GIN layer as ONE launch (SURVEY 8b `gin_layer_fwd`).
  * Replaces model/layers.py:42-57 with type='gin': PyG GINConv (index_select + scatter_add, Linear, act,
  * Linear) -> act -> the statistics pass of BatchNorm1d; the BatchNorm *apply* of this layer is not a pass at
- * all -- it is folded into the aggregation of the layer that consumes it (and into the readout):
- *     z_i = fold_a[c] * ((1+eps) x_i + sum_{j in N(i)} x_j) + fold_b[c] * (1 + eps + deg_i),   c = chunk of row i
+ * all -- it is folded (centred) into the aggregation of the layer that consumes it, and into the readout:
+ *     z_i = fold_a[c] * ((1+eps)(x_i - mean[c]) + sum_{j in N(i)} (x_j - mean[c])) + beta * (1 + eps + deg_i)
  *     t   = act_inner(z W1^T + b1);   Y = act_outer(t W2^T + b2)          (Y = the BatchNorm's INPUT)
- * X [rows, ldx]: the producer layer's Y (or the raw features, fold_a = NULL); rows zero-padded to a multiple of
- * 4 columns.  W1 [64, din], W2 [64, 64] contiguous (nn.Linear layout).  dout must be 64, din <= 64.
- * chunk_row_ptr [S+1]: row ranges that are independent BatchNorm batches (the 128-graph chunks of
- * src/train.py:62-71); tile_chunk0 [ceil(rows/128)]: chunk of the first row of every 128-row tile.
+ * with c = chunk of row i.  X [rows, ldx]: the producer layer's Y (or the raw features, fold_a = NULL); rows
+ * zero-padded to a multiple of 4 columns.  W1 [64, din], W2 [64, 64] contiguous (nn.Linear layout).  dout must
+ * be 64, din <= 64.  nnz = entries of col_idx; tile_edge_ptr [ceil(rows/128)+1] = row_ptr[128 t] (row_ptr[rows]
+ * last).  chunk_row_ptr [S+1]: row ranges that are independent BatchNorm batches (the 128-graph chunks of
+ * src/train.py:62-71; no edge crosses a chunk boundary); tile_chunk0 [ceil(rows/128)]: chunk of the first row
+ * of every 128-row tile.  fold_mean / fold_a [S, din], fold_beta [din].
  * Z [rows, ldz] (aggregated input) and T [rows, ldt] (hidden activations) are optional outputs for the backward.
  * stat_parts (optional): fp64 [bignn_gin_layer_stat_records(rows, S), 2, 64] partial column sums / sums of
  * squares of Y per (tile, chunk), which bignn_gin_bn_finalize adds in tile order (deterministic) into
  * mean / rstd [S, 64], seg_stats_out [2, S, 64] (mean, unbiased variance: the input of
- * bignn_bn_running_update) and the affine fold_a = gamma*rstd, fold_b = beta - mean*fold_a for the consumer.
+ * bignn_bn_running_update) and fold_a = gamma * rstd for the consumer.
  * ------------------------------------------------------------------------- */
 int bignn_gin_layer_supported(int32_t din, int32_t dout);
 int64_t bignn_gin_layer_stat_records(int32_t rows, int32_t S);
 int bignn_gin_layer_fwd(int32_t rows, int32_t din, int32_t dout,
-                        const int32_t* row_ptr, const int32_t* col_idx,
-                        const float* X, int64_t ldx, const float* fold_a, const float* fold_b,
+                        const int32_t* row_ptr, const int32_t* col_idx, int32_t nnz, const int32_t* tile_edge_ptr,
+                        const float* X, int64_t ldx,
+                        const float* fold_mean, const float* fold_a, const float* fold_beta,
                         const int32_t* chunk_row_ptr, int32_t S, const int32_t* tile_chunk0,
                         float self_coef, const float* W1, const float* b1, const float* W2, const float* b2,
                         int32_t act_inner, int32_t act_outer,
                         float* Z, int64_t ldz, float* T, int64_t ldt, float* Y, int64_t ldy,
                         double* stat_parts, void* stream);
 int bignn_gin_bn_finalize(const double* stat_parts, const int32_t* chunk_row_ptr, int32_t S, int32_t C,
-                          float eps, const float* gamma, const float* beta, float* mean, float* rstd,
-                          double* seg_stats_out, float* fold_a, float* fold_b, void* stream);
+                          float eps, const float* gamma, float* mean, float* rstd,
+                          double* seg_stats_out, float* fold_a, void* stream);
 
 /* ---------------------------------------------------------------------------
  * Segment readout (atoms -> one row per drug), rows summed in ascending order.
@@ -288,10 +291,12 @@ int bignn_readout_fwd(const float* X, int64_t ldx, const int32_t* seg_ptr, int32
                       int32_t style, const int32_t* dst_row,
                       float* out, int64_t ldo, int32_t col_off, void* stream);
 /* the same with the BatchNorm affine of the pooled activations folded in (the input is the BatchNorm's INPUT):
- * pool(a*x + b) = a * pool(x) + b * (1 for mean, n for sum);  fold_a / fold_b [S, D], graph_chunk [G]. */
+ * pool(a (x - mean) + beta) = a * pool(x - mean) + beta * (1 for mean, n for sum);
+ * fold_mean / fold_a [S, D], fold_beta [D], graph_chunk [G]. */
 int bignn_readout_fold_fwd(const float* X, int64_t ldx, const int32_t* seg_ptr, int32_t G, int32_t D,
-                           int32_t style, const int32_t* dst_row, const float* fold_a, const float* fold_b,
-                           const int32_t* graph_chunk, float* out, int64_t ldo, int32_t col_off, void* stream);
+                           int32_t style, const int32_t* dst_row, const float* fold_mean, const float* fold_a,
+                           const float* fold_beta, const int32_t* graph_chunk, float* out, int64_t ldo,
+                           int32_t col_off, void* stream);
 int bignn_readout_bwd(const float* dOut, int64_t ldo, int32_t col_off, const int32_t* dst_row,
                       const int32_t* seg_ptr, int32_t G, int32_t D, int32_t style,
                       float* dX, int64_t lddx, int32_t accumulate, void* stream);
