@@ -397,11 +397,12 @@ def algorithmic_bytes(name, a):
         if name == 'bignn_readout_fwd':
             return 4.0 * a[4] * (a[0].shape[0] + a[3])
         if name == 'bignn_gin_layer_fwd':
-            # read X (gather; neighbours are re-read from L1/L2), write Y (+ Z and T when they are kept for the
-            # backward), indices, row pointers
-            rows, din, dout = a[0], a[1], a[2]
-            kept = (1 if a[-4] is not None else 0) + (1 if a[-3] is not None else 0)
-            return 4.0 * rows * (din + dout) + 4.0 * _numel(a[4]) + 4.0 * (rows + 1) + 4.0 * rows * (din * (a[-4] is not None) + dout * (a[-3] is not None))
+            # read X once (neighbour rows of a molecule are re-read from L1/L2), write Y (+ Z and T when they are kept
+            # for the backward), neighbour ids, row pointers
+            rows, din, dout, nnz = a[0], a[1], a[2], a[5]
+            din_pad = (din + 3) // 4 * 4
+            kept = (din_pad if a[22] is not None else 0) + (dout if a[24] is not None else 0)
+            return 4.0 * rows * (din_pad + dout + kept) + 4.0 * nnz + 4.0 * (rows + 1)
         if name == 'bignn_merge_build':
             F, G, A, E = a[4], a[6], a[15], a[16]
             return 4.0 * (A + 1) + 8.0 * E + 4.0 * A + 4.0 * (G + 1) + 8.0 * F * A

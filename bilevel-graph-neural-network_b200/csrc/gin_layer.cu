@@ -34,12 +34,45 @@ constexpr int GL_IDX_RP = 132;                 // row pointers of one tile (129 
 constexpr int GL_IDX_STAGES = 3;
 constexpr int GL_IDX_BYTES = (GL_IDX_RP + GL_IDX_CAP) * 4;
 constexpr int GL_SMEM = 2 * GL_SLOT + 4 * GL_W + GL_IDX_STAGES * GL_IDX_BYTES + 1024;
-constexpr int GL_EPI_WARPS = 4;
-constexpr int GL_NA = 2;                       // rotating main accumulators (as k_gemm_tc<64, .>)
-constexpr int GL_ACC_COLS = (GL_NA + 1) * GL_D;
+constexpr int GL_EPI_WARPS = 4;                // per epilogue phase: one warp per TMEM lane quadrant
+// TMEM: ONE fp32 accumulator of 64 columns per transform (reading TMEM costs 64 B/cycle/SM: three accumulators per
+// transform, as k_gemm_tc keeps them, were 1.6 us of TMEM reads per tile), double buffered: acc1[2], acc2[2]
+constexpr int GL_TMEM_COLS = 256;
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// wait with back-off for the roles that run ahead (producers, index prefetch): a hot try_wait loop of 20 warps
+// takes issue slots from the warps that do the work (ncu: 40 % of all executed instructions were this loop)
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(100);
+  }
+}
+// one non-blocking test of a phase
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -64,20 +97,12 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[1
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// sum of the three accumulators of 16 columns, corrections first (the order of k_gemm_tc's epilogue)
-__device__ __forceinline__ void load_acc16(uint32_t tb, bool two_main, float (&v)[16]) {
-  uint32_t r0[16], r1[16];
-  tmem_ld16_nowait(tb + (uint32_t)(2 * 64), r0);
-  tmem_ld16_nowait(tb, r1);
-  tmem_ld_wait();
+// 32 columns of this thread's accumulator row
+__device__ __forceinline__ void load_acc32(uint32_t tb, float (&v)[32]) {
+  uint32_t r[32];
+  tmem_ld32(tb, r);
 #pragma unroll
-  for (int j = 0; j < 16; ++j) v[j] = __fadd_rn(__uint_as_float(r1[j]), __uint_as_float(r0[j]));
-  if (two_main) {
-    tmem_ld16_nowait(tb + 64u, r0);
-    tmem_ld_wait();
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = __fadd_rn(__uint_as_float(r0[j]), v[j]);
-  }
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
 }
 __device__ __forceinline__ float4 sub4(const float4& a, const float4& m) {
   return make_float4(__fsub_rn(a.x, m.x), __fsub_rn(a.y, m.y), __fsub_rn(a.z, m.z), __fsub_rn(a.w, m.w));
@@ -108,24 +133,35 @@ struct GinLayerArgs {
   double* stat_parts;                                 // [(n_tiles + S)][2][64] or null
 };
 
-// issue the 3xTF32 MMAs of one [128 x K] x [K x 64] product (A in `slot`, B = resident weight parts)
+// issue the 3xTF32 MMAs of one [128 x K] x [K x 64] product (A in `slot`, B = resident weight parts) into ONE
+// accumulator.  tcgen05.mma truncates toward zero whenever it writes the fp32 accumulator (measured: -5.6e-8 relative
+// per accumulation), so the 2^-11-scaled correction products lo*hi + hi*lo of every K step go in FIRST, while the
+// accumulator is small, and the K/8 hi*hi products last: 8 full-magnitude truncations at K = 64 (-4.5e-7, the budget
+// k_gemm_tc spends with its three accumulators).
 __device__ __forceinline__ void issue_gemm(uint32_t tmem_acc, const uint8_t* a_hi, const uint8_t* a_lo,
                                            const uint8_t* b_hi, const uint8_t* b_lo, int K, uint32_t idesc) {
-  int ks = 0;
+  uint32_t accumulate = 0u;
 #pragma unroll
-  for (int ch = 0; ch < 2; ++ch) {
-    if (ch * TC_KC >= K) break;
-    const uint64_t da_hi = umma_desc_k_sw128(smem_u32(a_hi + ch * (TC_BM * 128)));
-    const uint64_t da_lo = umma_desc_k_sw128(smem_u32(a_lo + ch * (TC_BM * 128)));
-    const uint64_t db_hi = umma_desc_k_sw128(smem_u32(b_hi + ch * (GL_D * 128)));
-    const uint64_t db_lo = umma_desc_k_sw128(smem_u32(b_lo + ch * (GL_D * 128)));
+  for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll
-    for (int k = 0; k < TC_KC / 8; ++k, ++ks) {
-      if (ch * TC_KC + k * 8 >= K) break;
-      const uint64_t adv = (uint64_t)((k * 32) >> 4);
-      umma_tf32(tmem_acc + (uint32_t)((ks % GL_NA) * GL_D), da_hi + adv, db_hi + adv, idesc, ks >= GL_NA ? 1u : 0u);
-      umma_tf32(tmem_acc + (uint32_t)(GL_NA * GL_D), da_lo + adv, db_hi + adv, idesc, ks > 0 ? 1u : 0u);
-      umma_tf32(tmem_acc + (uint32_t)(GL_NA * GL_D), da_hi + adv, db_lo + adv, idesc, 1u);
+    for (int ch = 0; ch < 2; ++ch) {
+      if (ch * TC_KC >= K) break;
+      const uint64_t da_hi = umma_desc_k_sw128(smem_u32(a_hi + ch * (TC_BM * 128)));
+      const uint64_t da_lo = umma_desc_k_sw128(smem_u32(a_lo + ch * (TC_BM * 128)));
+      const uint64_t db_hi = umma_desc_k_sw128(smem_u32(b_hi + ch * (GL_D * 128)));
+      const uint64_t db_lo = umma_desc_k_sw128(smem_u32(b_lo + ch * (GL_D * 128)));
+#pragma unroll
+      for (int k = 0; k < TC_KC / 8; ++k) {
+        if (ch * TC_KC + k * 8 >= K) break;
+        const uint64_t adv = (uint64_t)((k * 32) >> 4);
+        if (pass == 0) {
+          umma_tf32(tmem_acc, da_lo + adv, db_hi + adv, idesc, accumulate);
+          umma_tf32(tmem_acc, da_hi + adv, db_lo + adv, idesc, 1u);
+        } else {
+          umma_tf32(tmem_acc, da_hi + adv, db_hi + adv, idesc, 1u);
+        }
+        accumulate = 1u;
+      }
     }
   }
 }
@@ -134,8 +170,10 @@ template <int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)
 k_gin_layer_fwd(const GinLayerArgs p) {
   constexpr int N_WARPS = THREADS / 32;
-  constexpr int N_PROD_WARPS = N_WARPS - GL_EPI_WARPS - 2;   // warp 4 = MMA issuer, warp 5 = index prefetch
-  constexpr int FIRST_PROD = GL_EPI_WARPS + 2;
+  // warps 0-3: epilogue of the first transform (E1), 4-7: epilogue of the second (E2), 8: MMA issuer,
+  // 9: index prefetch, 10..: producers
+  constexpr int MMA_WARP = 2 * GL_EPI_WARPS, IDX_WARP = MMA_WARP + 1, FIRST_PROD = IDX_WARP + 1;
+  constexpr int N_PROD_WARPS = N_WARPS - FIRST_PROD;
   constexpr int N_GROUPS = N_PROD_WARPS * 4;                 // 8-lane groups
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -144,7 +182,8 @@ k_gin_layer_fwd(const GinLayerArgs p) {
   uint8_t* w2_hi = w1_lo + GL_W;
   uint8_t* w2_lo = w2_hi + GL_W;
   int32_t* idx_s = reinterpret_cast<int32_t*>(w2_lo + GL_W);      // [stages][rp 132 | col CAP]
-  __shared__ uint64_t z_full[2], z_empty[2], t_full, m1_done, m2_done, idx_full[GL_IDX_STAGES], idx_empty[GL_IDX_STAGES];
+  __shared__ uint64_t z_full[2], z_empty[2], t_full[2], t_copied[2], acc2_free[2], m1_done[2], m2_done[2],
+      idx_full[GL_IDX_STAGES], idx_empty[GL_IDX_STAGES];
   __shared__ uint32_t tmem_base_s;
   __shared__ float b1_s[GL_D], b2_s[GL_D];
   __shared__ double red_s[2][8][GL_D];
@@ -154,15 +193,18 @@ k_gin_layer_fwd(const GinLayerArgs p) {
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
-                 "r"(512)
+                 "r"(GL_TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 32) {
     mbar_init(&z_full[0], N_PROD_WARPS); mbar_init(&z_full[1], N_PROD_WARPS);
     mbar_init(&z_empty[0], GL_EPI_WARPS); mbar_init(&z_empty[1], GL_EPI_WARPS);
-    mbar_init(&t_full, GL_EPI_WARPS);
-    mbar_init(&m1_done, 1); mbar_init(&m2_done, 1);
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&t_full[b], GL_EPI_WARPS); mbar_init(&t_copied[b], GL_EPI_WARPS); mbar_init(&acc2_free[b], GL_EPI_WARPS);
+      mbar_init(&m1_done[b], 1); mbar_init(&m2_done[b], 1);
+    }
 #pragma unroll
     for (int s = 0; s < GL_IDX_STAGES; ++s) { mbar_init(&idx_full[s], 1); mbar_init(&idx_empty[s], N_PROD_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -191,7 +233,7 @@ k_gin_layer_fwd(const GinLayerArgs p) {
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = tmem_base_s;
-  const uint32_t acc1 = tmem_d, acc2 = tmem_d + (uint32_t)GL_ACC_COLS;
+  const uint32_t acc1 = tmem_d, acc2 = tmem_d + 2u * GL_D;          // acc1[b] = acc1 + 64 b, acc2[b] = acc2 + 64 b
 
   if (warp >= FIRST_PROD) {
     // =============================================================== producers: z tiles
@@ -199,17 +241,25 @@ k_gin_layer_fwd(const GinLayerArgs p) {
     const int l8 = lane & 7;
     const int din4 = (p.din + 3) >> 2;
     const bool ok0 = l8 < din4, ok1 = l8 + 8 < din4;
-    const float* __restrict__ X = p.X;
+    const float* __restrict__ X = p.X + 4 * l8;             // this lane's first column slot
     const int64_t ldx = p.ldx;
     const bool fold = p.fold_a != nullptr;
+    const float sc = p.self_coef;
+    // folded BatchNorm parameters of the chunk being processed (reloaded only when the chunk changes)
+    float4 mu0 = f4z(), mu1 = f4z(), fa0 = f4z(), fa1 = f4z(), be0 = f4z(), be1 = f4z();
+    int cached_chunk = -1;
+    if (fold) {
+      if (ok0) be0 = ldg4(p.fold_beta + 4 * l8);
+      if (ok1) be1 = ldg4(p.fold_beta + 4 * (l8 + 8));
+    }
     int it = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const int b = it & 1;
       const int st = it % GL_IDX_STAGES;
       const int32_t* rp_s = idx_s + st * (GL_IDX_RP + GL_IDX_CAP);
       const int32_t* col_s = rp_s + GL_IDX_RP;
-      mbar_wait(&idx_full[st], (it / GL_IDX_STAGES) & 1);
-      mbar_wait(&z_empty[b], ((it >> 1) & 1) ^ 1);
+      mbar_wait_relaxed(&idx_full[st], (it / GL_IDX_STAGES) & 1);
+      mbar_wait_relaxed(&z_empty[b], ((it >> 1) & 1) ^ 1);
       uint8_t* a_hi = smem + b * GL_SLOT;
       uint8_t* a_lo = a_hi + 2 * TC_BM * 128;
       const int m0 = tile * TC_BM;
@@ -222,59 +272,47 @@ k_gin_layer_fwd(const GinLayerArgs p) {
         if (grow < p.rows && !(p.dbg & 1)) {
           const int k0 = rp_s[r], k1 = rp_s[r + 1];
           const float* xr = X + (int64_t)grow * ldx;
-          float4 s0 = ok0 ? ldg4(xr + 4 * l8) : f4z();
-          float4 s1 = ok1 ? ldg4(xr + 4 * (l8 + 8)) : f4z();
+          float4 s0 = ok0 ? ldg4(xr) : f4z();
+          float4 s1 = ok1 ? ldg4(xr + 32) : f4z();
           // BatchNorm of the producer layer folded in, centred: sum_j (a (y_j - mean) + beta) = a * sum_j (y_j - mean)
           // + beta * (number of terms): the subtraction happens per loaded value (no cancellation of large sums)
-          float4 mu0 = f4z(), mu1 = f4z();
           if (fold) {
             while (grow >= __ldg(p.chunk_row_ptr + chunk + 1)) ++chunk;
-            const float* fm = p.fold_mean + (int64_t)chunk * p.din;
-            if (ok0) mu0 = ldg4(fm + 4 * l8);
-            if (ok1) mu1 = ldg4(fm + 4 * (l8 + 8));
+            if (chunk != cached_chunk) {
+              cached_chunk = chunk;
+              const float* fm = p.fold_mean + (int64_t)chunk * p.din + 4 * l8;
+              const float* fa = p.fold_a + (int64_t)chunk * p.din + 4 * l8;
+              if (ok0) { mu0 = ldg4(fm); fa0 = ldg4(fa); }
+              if (ok1) { mu1 = ldg4(fm + 32); fa1 = ldg4(fa + 32); }
+            }
           }
           float4 a0 = f4z(), a1 = f4z();
           int cnt = 0;
-          for (int k = k0; k < k1; k += 4) {
-            int c[4];
-            float4 v0[4], v1[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int kk = k + u;
-              c[u] = -1;
-              if (kk < k1) c[u] = (kk - e_lo < GL_IDX_CAP) ? col_s[kk - e_lo] : __ldg(p.col_idx + kk);
-              if (c[u] == grow) c[u] = -1;                       // remove_self_loops (PyG GINConv)
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const float* nr = X + (int64_t)(c[u] >= 0 ? c[u] : 0) * ldx;
-              v0[u] = (c[u] >= 0 && ok0) ? ldg4(nr + 4 * l8) : f4z();
-              v1[u] = (c[u] >= 0 && ok1) ? ldg4(nr + 4 * (l8 + 8)) : f4z();
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              if (c[u] >= 0) { add4(a0, sub4(v0[u], mu0)); add4(a1, sub4(v1[u], mu1)); ++cnt; }
-            }
+          for (int k = k0; k < k1; k += 2) {
+            int c0 = (k - e_lo < GL_IDX_CAP) ? col_s[k - e_lo] : __ldg(p.col_idx + k);
+            int c1 = -1;
+            if (k + 1 < k1) c1 = (k + 1 - e_lo < GL_IDX_CAP) ? col_s[k + 1 - e_lo] : __ldg(p.col_idx + k + 1);
+            if (c0 == grow) c0 = -1;                             // remove_self_loops (PyG GINConv)
+            if (c1 == grow) c1 = -1;
+            const float* n0 = X + (int64_t)(c0 >= 0 ? c0 : grow) * ldx;
+            const float* n1 = X + (int64_t)(c1 >= 0 ? c1 : grow) * ldx;
+            float4 v00 = f4z(), v01 = f4z(), v10 = f4z(), v11 = f4z();
+            if (ok0) { v00 = ldg4(n0); v10 = ldg4(n1); }
+            if (ok1) { v01 = ldg4(n0 + 32); v11 = ldg4(n1 + 32); }
+            if (c0 >= 0) { add4(a0, fold ? sub4(v00, mu0) : v00); add4(a1, fold ? sub4(v01, mu1) : v01); ++cnt; }
+            if (c1 >= 0) { add4(a0, fold ? sub4(v10, mu0) : v10); add4(a1, fold ? sub4(v11, mu1) : v11); ++cnt; }
           }
-          const float sc = p.self_coef;
-          s0 = sub4(s0, mu0); s1 = sub4(s1, mu1);
+          if (fold) { s0 = sub4(s0, mu0); s1 = sub4(s1, mu1); }
           z0.x = __fadd_rn(__fmul_rn(sc, s0.x), a0.x); z0.y = __fadd_rn(__fmul_rn(sc, s0.y), a0.y);
           z0.z = __fadd_rn(__fmul_rn(sc, s0.z), a0.z); z0.w = __fadd_rn(__fmul_rn(sc, s0.w), a0.w);
           z1.x = __fadd_rn(__fmul_rn(sc, s1.x), a1.x); z1.y = __fadd_rn(__fmul_rn(sc, s1.y), a1.y);
           z1.z = __fadd_rn(__fmul_rn(sc, s1.z), a1.z); z1.w = __fadd_rn(__fmul_rn(sc, s1.w), a1.w);
           if (fold) {
             const float wsum = sc + (float)cnt;
-            const float* fa = p.fold_a + (int64_t)chunk * p.din;
-            if (ok0) {
-              const float4 A = ldg4(fa + 4 * l8), B = ldg4(p.fold_beta + 4 * l8);
-              z0.x = fmaf(A.x, z0.x, B.x * wsum); z0.y = fmaf(A.y, z0.y, B.y * wsum);
-              z0.z = fmaf(A.z, z0.z, B.z * wsum); z0.w = fmaf(A.w, z0.w, B.w * wsum);
-            }
-            if (ok1) {
-              const float4 A = ldg4(fa + 4 * (l8 + 8)), B = ldg4(p.fold_beta + 4 * (l8 + 8));
-              z1.x = fmaf(A.x, z1.x, B.x * wsum); z1.y = fmaf(A.y, z1.y, B.y * wsum);
-              z1.z = fmaf(A.z, z1.z, B.z * wsum); z1.w = fmaf(A.w, z1.w, B.w * wsum);
-            }
+            z0.x = fmaf(fa0.x, z0.x, be0.x * wsum); z0.y = fmaf(fa0.y, z0.y, be0.y * wsum);
+            z0.z = fmaf(fa0.z, z0.z, be0.z * wsum); z0.w = fmaf(fa0.w, z0.w, be0.w * wsum);
+            z1.x = fmaf(fa1.x, z1.x, be1.x * wsum); z1.y = fmaf(fa1.y, z1.y, be1.y * wsum);
+            z1.z = fmaf(fa1.z, z1.z, be1.z * wsum); z1.w = fmaf(fa1.w, z1.w, be1.w * wsum);
           }
         }
         const uint32_t off = sw128_off(r, l8);
@@ -287,16 +325,22 @@ k_gin_layer_fwd(const GinLayerArgs p) {
       __syncwarp();
       if (lane == 0) { mbar_arrive(&z_full[b]); mbar_arrive(&idx_empty[st]); }
     }
-  } else if (warp == GL_EPI_WARPS + 1) {
+  } else if (warp == IDX_WARP) {
     // =============================================================== index prefetch: row pointers + neighbour ids of
     // the tiles ahead, as coalesced 16-byte cp.async copies (the producers' only dependent global hop left is X)
+    // two tiles in flight: the copies of tile i are issued before those of tile i-1 are waited for, and the first
+    // CSR entry of the NEXT tile (a dependent global load) is fetched one iteration ahead
     int it = 0;
+    int e0n = 0, e1n = 0;
+    if ((int)blockIdx.x < p.n_tiles) { e0n = __ldg(p.tile_edge_ptr + blockIdx.x); e1n = __ldg(p.tile_edge_ptr + blockIdx.x + 1); }
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const int st = it % GL_IDX_STAGES;
       int32_t* rp_s = idx_s + st * (GL_IDX_RP + GL_IDX_CAP);
       int32_t* col_s = rp_s + GL_IDX_RP;
-      const int e0 = __ldg(p.tile_edge_ptr + tile) & ~3, e1 = __ldg(p.tile_edge_ptr + tile + 1);
-      mbar_wait(&idx_empty[st], ((it / GL_IDX_STAGES) & 1) ^ 1);
+      const int e0 = e0n & ~3, e1 = e1n;
+      const int nxt = tile + gridDim.x;
+      if (nxt < p.n_tiles) { e0n = __ldg(p.tile_edge_ptr + nxt); e1n = __ldg(p.tile_edge_ptr + nxt + 1); }
+      mbar_wait_relaxed(&idx_empty[st], ((it / GL_IDX_STAGES) & 1) ^ 1);
       const int m0 = tile * TC_BM;
       const int n_rp = min(TC_BM, p.rows - m0) + 1;                       // row pointers of this tile
       for (int j = lane * 4; j < GL_IDX_RP; j += 128) {
@@ -309,42 +353,69 @@ k_gin_layer_fwd(const GinLayerArgs p) {
         cp_async16(smem_u32(col_s + j), p.col_idx + e0 + j, left >= 4 ? 16u : 4u * left);
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
+      if (it > 0) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");              // the previous tile's copies have landed
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&idx_full[(it - 1) % GL_IDX_STAGES]);
+      }
+    }
+    if (it > 0) {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(&idx_full[st]);
+      if (lane == 0) mbar_arrive(&idx_full[(it - 1) % GL_IDX_STAGES]);
     }
-  } else if (warp == GL_EPI_WARPS) {
-    // =============================================================== MMA issuer
+  } else if (warp == MMA_WARP) {
+    // =============================================================== MMA issuer: whichever transform has its operand
+    // ready is issued next -- the first transform may run up to two tiles ahead of the second (accumulators and
+    // operand slots are double buffered), and neither waits for the other's producer
     const uint32_t idesc = umma_idesc_tf32(TC_BM, GL_D);
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-      const int b = it & 1;
-      const uint8_t* a_hi = smem + b * GL_SLOT;
-      const uint8_t* a_lo = a_hi + 2 * TC_BM * 128;
-      mbar_wait(&z_full[b], (it >> 1) & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (lane == 0) {
-        issue_gemm(acc1, a_hi, a_lo, w1_hi, w1_lo, K1, idesc);
-        umma_commit(&m1_done);
+    const int n_my = p.n_tiles > (int)blockIdx.x ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    int i1 = 0, i2 = 0;                                     // next tile (of this CTA) for the first / second transform
+    while (i2 < n_my) {
+      bool did = false;
+      if (i1 < n_my && i1 - i2 < 2) {                       // acc1[i1 & 1] is free once t of tile i1-2 was consumed
+        const int b = i1 & 1;
+        // (every decision is made by lane 0 and broadcast: the operand descriptors live in uniform registers, so the
+        // warp's state must not diverge)
+        if (__shfl_sync(0xffffffffu, lane == 0 ? (int)mbar_test(&z_full[b], (i1 >> 1) & 1) : 0, 0)) {
+          const uint8_t* a_hi = smem + b * GL_SLOT;
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (lane == 0) {
+            issue_gemm(acc1 + (uint32_t)(b * GL_D), a_hi, a_hi + 2 * TC_BM * 128, w1_hi, w1_lo, K1, idesc);
+            umma_commit(&m1_done[b]);
+          }
+          __syncwarp();
+          ++i1;
+          did = true;
+        }
       }
-      __syncwarp();
-      mbar_wait(&t_full, it & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (lane == 0) {
-        issue_gemm(acc2, a_hi, a_lo, w2_hi, w2_lo, K2, idesc);
-        umma_commit(&m2_done);
+      if (i2 < i1) {
+        const int b = i2 & 1;
+        // E1 has turned acc1 into t inside the slot, E2 has read acc2[b] of tile i2-2
+        if (__shfl_sync(0xffffffffu, lane == 0 ? (int)(mbar_test(&t_full[b], (i2 >> 1) & 1) &&
+                                                        mbar_test(&acc2_free[b], ((i2 >> 1) & 1) ^ 1)) : 0, 0)) {
+          const uint8_t* a_hi = smem + b * GL_SLOT;
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (lane == 0) {
+            issue_gemm(acc2 + (uint32_t)(b * GL_D), a_hi, a_hi + 2 * TC_BM * 128, w2_hi, w2_lo, K2, idesc);
+            umma_commit(&m2_done[b]);
+          }
+          __syncwarp();
+          ++i2;
+          did = true;
+        }
       }
-      __syncwarp();
+      if (!did) __nanosleep(20);
     }
-  } else {
-    // =============================================================== epilogue warps (TMEM lane quadrant = warp)
+  } else if (warp < GL_EPI_WARPS) {
+    // =============================================================== E1: acc1 -> t = act(. + b1) back into the slot
     const int row = warp * 32 + lane;                       // tile row this thread reads from TMEM
     const int et = tid;                                     // 0..127
     const int c4 = et & 15, rg = et >> 4;                   // copy-out: 16-byte column chunk, row group (8 groups)
-    const bool two_main1 = (K1 + 7) / 8 >= GL_NA;
     const uint32_t row_off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
     const int row7 = row & 7;
     const bool store = !(p.dbg & 2);
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const int b = it & 1;
@@ -352,12 +423,10 @@ k_gin_layer_fwd(const GinLayerArgs p) {
       uint8_t* a_lo = a_hi + 2 * TC_BM * 128;
       const int m0 = tile * TC_BM;
       const int rows_here = min(TC_BM, p.rows - m0);
-      const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
       const uint8_t* src = a_hi + (c4 >> 3) * (TC_BM * 128);
-      // ---------------- first transform done: z may leave (kept for the backward), t goes back in
-      mbar_wait(&m1_done, it & 1);
+      mbar_wait(&m1_done[b], (it >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (p.Z) {
+      if (p.Z) {                                            // z leaves (kept for the backward) before t comes in
         if (store && c4 < ((p.din + 3) >> 2)) {
 #pragma unroll 4
           for (int i = 0; i < 16; ++i) {
@@ -366,25 +435,25 @@ k_gin_layer_fwd(const GinLayerArgs p) {
               st4(p.Z + (int64_t)(m0 + r) * p.ldz + 4 * c4, *reinterpret_cast<const float4*>(src + sw128_off(r, c4 & 7)));
           }
         }
-        named_bar_sync(1, GL_EPI_WARPS * 32);               // every z row is out before any t row comes in
+        named_bar_sync(1, GL_EPI_WARPS * 32);
       }
 #pragma unroll 1
-      for (int cb = 0; cb < GL_D; cb += 16) {
-        float v[16];
-        load_acc16(acc1 + lane_off + (uint32_t)cb, two_main1, v);
+      for (int cb = 0; cb < GL_D; cb += 32) {
+        float v[32];
+        load_acc32(acc1 + (uint32_t)(b * GL_D) + lane_off + (uint32_t)cb, v);
         if (p.act_inner == BIGNN_ACT_RELU) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j] + b1_s[cb + j], 0.f);
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + b1_s[cb + j], 0.f);
         } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j] + b1_s[cb + j], p.act_inner);
+          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j] + b1_s[cb + j], p.act_inner);
         }
         uint8_t* hi = a_hi + (cb >> 5) * (TC_BM * 128) + row_off;
         uint8_t* lo = a_lo + (cb >> 5) * (TC_BM * 128) + row_off;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 8; ++c) {
           const float4 tv = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-          const uint32_t off = (uint32_t)(((((cb & 31) >> 2) + c) ^ row7) << 4);
+          const uint32_t off = (uint32_t)((c ^ row7) << 4);
           *reinterpret_cast<float4*>(hi + off) = tv;
           *reinterpret_cast<uint4*>(lo + off) = lo_part(tv);
         }
@@ -392,7 +461,7 @@ k_gin_layer_fwd(const GinLayerArgs p) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(&t_full);
+      if (lane == 0) mbar_arrive(&t_full[b]);
       if (p.T) {
         named_bar_sync(1, GL_EPI_WARPS * 32);               // all of t is in the slot; copy it out while the MMA runs
         if (store) {
@@ -403,30 +472,52 @@ k_gin_layer_fwd(const GinLayerArgs p) {
               st4(p.T + (int64_t)(m0 + r) * p.ldt + 4 * c4, *reinterpret_cast<const float4*>(src + sw128_off(r, c4 & 7)));
           }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_copied[b]);           // E2 may overwrite the slot with y
       }
-      // ---------------- second transform done: y = act(acc + b2) staged in the slot (t has been consumed)
-      mbar_wait(&m2_done, it & 1);
+    }
+  } else {
+    // =============================================================== E2: acc2 -> y = act(. + b2), staged in the slot,
+    // coalesced stores + BatchNorm partial sums
+    const int qw = warp - GL_EPI_WARPS;                     // TMEM lane quadrant (= warp % 4)
+    const int row = qw * 32 + lane;
+    const int et = tid - GL_EPI_WARPS * 32;                 // 0..127
+    const int c4 = et & 15, rg = et >> 4;
+    const uint32_t row_off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
+    const int row7 = row & 7;
+    const bool store = !(p.dbg & 2);
+    const uint32_t lane_off = (uint32_t)(qw * 32) << 16;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const int b = it & 1;
+      uint8_t* a_hi = smem + b * GL_SLOT;
+      const int m0 = tile * TC_BM;
+      const int rows_here = min(TC_BM, p.rows - m0);
+      const uint8_t* src = a_hi + (c4 >> 3) * (TC_BM * 128);
+      mbar_wait(&m2_done[b], (it >> 1) & 1);                // t has been consumed
+      if (p.T) mbar_wait(&t_copied[b], (it >> 1) & 1);      // ... and copied out by E1
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (p.T) named_bar_sync(1, GL_EPI_WARPS * 32);        // the T copy-out above has read the whole slot
 #pragma unroll 1
-      for (int cb = 0; cb < GL_D; cb += 16) {
-        float v[16];
-        load_acc16(acc2 + lane_off + (uint32_t)cb, true, v);
+      for (int cb = 0; cb < GL_D; cb += 32) {
+        float v[32];
+        load_acc32(acc2 + (uint32_t)(b * GL_D) + lane_off + (uint32_t)cb, v);
         if (p.act_outer == BIGNN_ACT_RELU) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j] + b2_s[cb + j], 0.f);
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + b2_s[cb + j], 0.f);
         } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j] + b2_s[cb + j], p.act_outer);
+          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j] + b2_s[cb + j], p.act_outer);
         }
         uint8_t* hi = a_hi + (cb >> 5) * (TC_BM * 128) + row_off;
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-          *reinterpret_cast<float4*>(hi + (uint32_t)(((((cb & 31) >> 2) + c) ^ row7) << 4)) =
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<float4*>(hi + (uint32_t)((c ^ row7) << 4)) =
               make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      named_bar_sync(1, GL_EPI_WARPS * 32);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc2_free[b]);
+      named_bar_sync(2, GL_EPI_WARPS * 32);
       // ---------------- coalesced copy-out (+ BatchNorm partial sums of the stored rows when the tile lies in one chunk)
       int chunk = 0, chunk_end = rows_here;
       if (p.stat_parts) {
@@ -434,6 +525,7 @@ k_gin_layer_fwd(const GinLayerArgs p) {
         chunk_end = __ldg(p.chunk_row_ptr + chunk + 1) - m0;
       }
       const bool one_chunk = chunk_end >= rows_here;
+      // fp64 from the first addition: E[x^2] - mean^2 must survive channels whose mean dwarfs their spread
       double s[4] = {0.0, 0.0, 0.0, 0.0}, ss[4] = {0.0, 0.0, 0.0, 0.0};
       if (store) {
 #pragma unroll 4
@@ -443,10 +535,11 @@ k_gin_layer_fwd(const GinLayerArgs p) {
             const float4 o = *reinterpret_cast<const float4*>(src + sw128_off(r, c4 & 7));
             st4(p.Y + (int64_t)(m0 + r) * p.ldy + 4 * c4, o);
             if (one_chunk) {
-              s[0] += (double)o.x; ss[0] += (double)o.x * (double)o.x;
-              s[1] += (double)o.y; ss[1] += (double)o.y * (double)o.y;
-              s[2] += (double)o.z; ss[2] += (double)o.z * (double)o.z;
-              s[3] += (double)o.w; ss[3] += (double)o.w * (double)o.w;
+              const double ox = (double)o.x, oy = (double)o.y, oz = (double)o.z, ow = (double)o.w;
+              s[0] += ox; ss[0] = fma(ox, ox, ss[0]);
+              s[1] += oy; ss[1] = fma(oy, oy, ss[1]);
+              s[2] += oz; ss[2] = fma(oz, oz, ss[2]);
+              s[3] += ow; ss[3] = fma(ow, ow, ss[3]);
             }
           }
         }
@@ -469,7 +562,7 @@ k_gin_layer_fwd(const GinLayerArgs p) {
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) { red_s[0][rg][4 * c4 + j] = s[j]; red_s[1][rg][4 * c4 + j] = ss[j]; }
-          named_bar_sync(1, GL_EPI_WARPS * 32);
+          named_bar_sync(2, GL_EPI_WARPS * 32);
           {
             const int which = et >> 6, col = et & 63;
             double a = 0.0;
@@ -477,7 +570,7 @@ k_gin_layer_fwd(const GinLayerArgs p) {
             for (int g = 0; g < 8; ++g) a += red_s[which][g][col];
             p.stat_parts[((int64_t)(tile + chunk) * 2 + which) * GL_D + col] = a;
           }
-          named_bar_sync(1, GL_EPI_WARPS * 32);
+          named_bar_sync(2, GL_EPI_WARPS * 32);
           lo_r = hi_r;
           ++chunk;
         }
@@ -490,7 +583,7 @@ k_gin_layer_fwd(const GinLayerArgs p) {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(512) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(GL_TMEM_COLS) : "memory");
   }
 }
 
@@ -564,7 +657,7 @@ extern "C" int bignn_gin_layer_fwd(int32_t rows, int32_t din, int32_t dout, cons
       (T && ((ldt & 3) || !aligned16(T))) || !aligned16(row_ptr) || !aligned16(col_idx) ||
       (fold && (!aligned16(fold_a) || !aligned16(fold_mean) || !aligned16(fold_beta))))
     return BIGNN_EALIGN;
-  constexpr int THREADS = 768;      // 24 warps: 4 epilogue, MMA, index prefetch, 18 producers = 72 row groups
+  constexpr int THREADS = 768;      // 24 warps: 4 + 4 epilogue, MMA, index prefetch, 14 producers = 56 row groups
   static bool configured = false;
   static int dbg = 0;
   if (!configured) {

@@ -83,15 +83,15 @@ def test_fused_layer_matches_unfused_kernels(rows, din, acts):
         t_ref = ops.gemm_tc(z_ref[:, :din].contiguous() if din_pad != din else z_ref, W1, True, b1, acts[0])
     else:
         t_ref = ops.gemm(z_ref[:, :din].contiguous(), W1, False, True, b1, acts[0])
-    assert rel(T, t_ref) < 2e-6
+    assert rel(T, t_ref) < 3e-6
     y_ref = ops.gemm_tc(t_ref, W2, True, b2, acts[1]) if ops.use_tc(rows, 64, 64) else ops.gemm(t_ref, W2, False, True, b2, acts[1])
-    assert rel(Y, y_ref) < 2e-6
+    assert rel(Y, y_ref) < 4e-6
     # fp64 ground truth of the whole layer
     z64 = z_ref[:, :din].double()
     f = {0: lambda v: v, 1: torch.relu, 2: torch.sigmoid, 3: torch.tanh}
     t64 = f[acts[0]](z64 @ W1.double().t() + b1.double())
     y64 = f[acts[1]](t64 @ W2.double().t() + b2.double())
-    assert rel(Y, y64) < 3e-6
+    assert rel(Y, y64) < 4e-6
     # the outputs that are not asked for are not needed either
     Y2, _, _, _ = run_layer(csr, X, din, W1, b1, W2, b2, acts[0], acts[1], crp, keep=False, stats=False, self_coef=1.25)
     assert torch.equal(Y, Y2)
