@@ -3,11 +3,10 @@ the B200 box, gloo in the CPU tests).
 
 Partitioning: the all-drug lower pass is sharded BY DRUG at chunk granularity --
 whole 128-graph chunks of src/train.py:62-71 stay on one rank, so lower-level BatchNorm needs no
-communication and keeps the reference's per-chunk statistics.  The exchange step is the pooled
-drug embeddings: every rank writes its rows of init_x[N, L*D] and the ranks sum the disjoint
-row sets (an all-gather expressed as an all-reduce of zero-padded buffers, which NVSwitch reduces
-in-switch); its backward is the identity because the upper level is evaluated on the full
-init_x by every rank.  Lower-level weight gradients are partial sums over a rank's chunks and are
+communication and keeps the reference's per-chunk statistics.  The exchange step is an ALL-GATHER of
+the pooled drug embeddings (every rank contributes the rows of its shard, every rank receives
+init_x[N, L*D]); its backward takes the rank's own rows (replicated upper level) or REDUCE-SCATTERs
+the partial gradients (row-partitioned upper level).  Lower-level weight gradients are partial sums over a rank's chunks and are
 all-reduced once per step in one flat buffer; BatchNorm running buffers replay the reference's
 sequential per-chunk momentum updates from all-gathered per-chunk statistics.
 """
@@ -65,29 +64,6 @@ def shard_chunks(chunk_weights, world):
         bounds.append(i)
     bounds.append(n)
     return [(bounds[r], bounds[r + 1]) for r in range(world)]
-
-
-class _SumDisjointRows(torch.autograd.Function):
-    """init_x = sum over ranks of zero-padded row blocks (each drug row is written by exactly one
-    rank).  Backward: identity -- every rank evaluates the upper level on the full matrix, so
-    d loss / d (own rows) is simply the matching rows of its own d init_x."""
-
-    @staticmethod
-    def forward(ctx, x, group):
-        x = x.contiguous()
-        with _timed('pooled_rows_all_reduce'):
-            dist.all_reduce(x, op=dist.ReduceOp.SUM, group=group)
-        return x
-
-    @staticmethod
-    def backward(ctx, g):
-        return g, None
-
-
-def sum_disjoint_rows(x, group=None):
-    if not is_dist():
-        return x
-    return _SumDisjointRows.apply(x, group)
 
 
 def all_reduce_grads(params, group=None, extra=None):
@@ -151,31 +127,58 @@ def gather_rows(x_loc, pg):
     return out
 
 
-class _ExchangePooledRows(torch.autograd.Function):
-    """init_x = sum over ranks of zero-padded row blocks (forward: the all-gather of pooled drug
-    embeddings, each row written by exactly one rank).  With a row-partitioned upper level a rank holds
-    d loss / d init_x only for its own interaction-graph rows, so the backward is the same rank sum."""
+class PooledLayout(object):
+    """Where the pooled drug rows of every rank live in the all-gathered [world, n_max, L*D] buffer: rank r's block
+    holds the drugs of its lower-level shard (ascending drug row), `perm[g]` = position of drug row g."""
+
+    def __init__(self, rank, world, n_max, n_loc, perm, group=None):
+        self.rank, self.world, self.n_max, self.n_loc, self.perm, self.group = rank, world, n_max, n_loc, perm, group
+
+
+class _GatherPooledRows(torch.autograd.Function):
+    """The exchange step between the levels: ALL-GATHER of the pooled drug embeddings -- every rank
+    contributes the rows of its lower-level shard, every rank receives init_x [N, L*D].
+    Backward: with a replicated upper level every rank holds the whole d init_x and simply takes the rows of its own
+    block; with a row-partitioned upper level a rank holds d init_x only for its own interaction-graph rows, and the
+    blocks are summed over the ranks with a REDUCE-SCATTER (half the bytes of the all-reduce this replaces)."""
 
     @staticmethod
-    def forward(ctx, x, group):
-        ctx.group = group
-        x = x.contiguous()
-        with _timed('pooled_rows_exchange_fwd'):
-            dist.all_reduce(x, op=dist.ReduceOp.SUM, group=group)
-        return x
+    def forward(ctx, blk, lay, partial_grad):
+        n_max, world = lay.n_max, lay.world
+        D = blk.shape[1]
+        buf = torch.empty((world * n_max, D), dtype=blk.dtype, device=blk.device)
+        mine = buf[lay.rank * n_max:(lay.rank + 1) * n_max]
+        mine.copy_(blk[:n_max])
+        src = mine if blk.is_cuda else mine.clone()            # gloo (CPU tests): no aliasing of in/out
+        with _timed('pooled_rows_all_gather'):
+            dist.all_gather_into_tensor(buf.view(-1), src.reshape(-1), group=lay.group)
+        ctx.lay, ctx.partial, ctx.rows = lay, bool(partial_grad), blk.shape[0]
+        return buf.index_select(0, lay.perm)
 
     @staticmethod
     def backward(ctx, g):
-        g = g.contiguous().clone()
-        with _timed('pooled_rows_exchange_bwd'):
-            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=ctx.group)
-        return g, None
+        lay = ctx.lay
+        n_max, world = lay.n_max, lay.world
+        D = g.shape[1]
+        scat = torch.zeros((world * n_max, D), dtype=g.dtype, device=g.device)
+        scat.index_copy_(0, lay.perm, g.contiguous())
+        if ctx.partial:
+            out = torch.empty((n_max, D), dtype=g.dtype, device=g.device)
+            with _timed('pooled_rows_reduce_scatter'):
+                if g.is_cuda:
+                    dist.reduce_scatter_tensor(out.view(-1), scat.view(-1), op=dist.ReduceOp.SUM, group=lay.group)
+                else:                                          # gloo has no reduce-scatter
+                    dist.all_reduce(scat, op=dist.ReduceOp.SUM, group=lay.group)
+                    out.copy_(scat[lay.rank * n_max:(lay.rank + 1) * n_max])
+        else:
+            out = scat[lay.rank * n_max:(lay.rank + 1) * n_max]
+        gb = torch.zeros((ctx.rows, D), dtype=g.dtype, device=g.device)
+        gb[:n_max] = out
+        return gb, None, None
 
 
-def exchange_pooled_rows(x, group=None):
-    if not is_dist():
-        return x
-    return _ExchangePooledRows.apply(x, group)
+def gather_pooled_rows(blk, lay, partial_grad):
+    return _GatherPooledRows.apply(blk, lay, partial_grad)
 
 
 class _GcnPropagateRows(torch.autograd.Function):

@@ -151,15 +151,42 @@ class BiGNNEngine(object):
             if partition_upper else []
         self._n_pair_rows = self.upper.n_pad if self.upper is not None else data.N
         # a drug that appears in two chunks is overwritten by the later one in the reference
-        # (layers_aggregation.py:72-74); earlier duplicates go to a trash row N
+        # (layers_aggregation.py:72-74); earlier duplicates go to a trash row
         first_later = {}
         for i in range(len(all_rows_in_order) - 1, -1, -1):
             first_later.setdefault(int(all_rows_in_order[i]), i)      # last occurrence wins
         offset = int(sum(len(r) for r in chunk_rows[:lo]))
-        dst = rows.copy()
-        for i in range(len(rows)):
-            if first_later[int(rows[i])] != offset + i:
-                dst[i] = data.N
+        if self.world == 1:
+            dst = rows.copy()
+            for i in range(len(rows)):
+                if first_later[int(rows[i])] != offset + i:
+                    dst[i] = data.N
+            self._pool_rows = data.N + 1
+            self.pooled_layout = None
+        else:
+            # exchange step = ALL-GATHER of pooled drug rows: every rank pools into its own compact block
+            # [n_max (+1 trash), L*D] (drug rows it owns, ascending); block r of the gathered [world, n_max, L*D] holds
+            # rank r's drugs, and `perm` maps drug row -> position in it
+            owned, off = [], 0
+            for (clo, chi) in self.chunk_shards:
+                cnt = int(sum(len(r) for r in chunk_rows[clo:chi]))
+                seg = all_rows_in_order[off:off + cnt]
+                keep = np.asarray([first_later[int(g)] == off + i for i, g in enumerate(seg)], bool) \
+                    if cnt else np.zeros(0, bool)
+                owned.append(np.sort(seg[keep]))
+                off += cnt
+            n_max = max(max(len(o) for o in owned), 1)
+            perm = np.zeros(data.N, np.int64)
+            for r, o in enumerate(owned):
+                perm[o] = r * n_max + np.arange(len(o))
+            mine_sorted = owned[self.rank]
+            dst = np.full(len(rows), n_max, np.int64)                  # trash row of the local block
+            for i in range(len(rows)):
+                if first_later[int(rows[i])] == offset + i:
+                    dst[i] = int(np.searchsorted(mine_sorted, rows[i]))
+            self._pool_rows = n_max + 1
+            self.pooled_layout = bdist.PooledLayout(self.rank, self.world, n_max, len(mine_sorted),
+                                                    torch.as_tensor(perm).to(self.device), group)
         self.dst_row = torch.as_tensor(dst.astype(np.int32)).to(self.device)
         self._all_chunk_ptr = torch.arange(self.n_chunks_total + 1, dtype=torch.int32, device=self.device)
         self._lower_bd = type('LowerBatch', (), {})()
@@ -167,7 +194,7 @@ class BiGNNEngine(object):
         self._lower_bd.merge_higher_level = {}
         self._lower_bd.dataset = data
         self._agg_style, self._multi = agg.style, agg.concat_multi_scale
-        self._stack = fused.StackSpec(list(model.init_layers), agg, self.merged, self.dst_row, data.N + 1,
+        self._stack = fused.StackSpec(list(model.init_layers), agg, self.merged, self.dst_row, self._pool_rows,
                                       self._bn_sink) if self.fused_lower else None
         self._graphs = {}          # P -> (graph, static batch, loss tensor)
         self.max_graphs = 8
@@ -194,10 +221,9 @@ class BiGNNEngine(object):
                 h = layer(h, self._lower_bd, model)
                 acts.append(h)
             pooled = ops.readout(acts if self._multi else [h], m.seg_ptr, m.G, self._agg_style,
-                                 self.dst_row, self.data.N + 1)
-        if self.world > 1:                                            # the exchange step (NCCL)
-            pooled = (bdist.exchange_pooled_rows if self.upper is not None else bdist.sum_disjoint_rows)(
-                pooled, self.group)
+                                 self.dst_row, self._pool_rows)
+        if self.world > 1:                                            # the exchange step (NCCL all-gather)
+            pooled = bdist.gather_pooled_rows(pooled, self.pooled_layout, partial_grad=self.upper is not None)
         return pooled, acts
 
     def _ig(self):

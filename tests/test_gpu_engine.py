@@ -150,3 +150,45 @@ def test_score_pairs_eval_mode_matches_oracle(golden_dir, step_golden, drugbank,
         _, _, pred, _ = O.train_step_forward(om, drugbank, pairs, z['y_true'])
     assert rel(got.view(-1), pred.view(-1)) < 1e-5
     assert model.training
+
+
+@pytest.mark.parametrize('arch', ['gin_gcn', 'drugcombo'])
+def test_loss_trajectory_follows_the_reference(golden_dir, arch):
+    """Consecutive train steps (Adam included, CUDA-graph replay) on the batches the reference itself drew, against the
+    losses the reference recorded for them (tests/golden/*_sampler_seq.npz `losses`).  The first steps agree to fp32
+    rounding; afterwards both architectures are chaotic (Adam's early updates are sign-like and the lower-level
+    gradients ill-conditioned -- DESIGN.md section 2), so the bound grows 4x per step, as it does between two runs of
+    the reference with different thread counts."""
+    if arch == 'drugcombo':
+        B.set_flags(B.make_flags(dataset='drugcombo', higher_level_gnn_type='gat', device=DEV))
+        z = np.load(os.path.join(golden_dir, 'bignn_drugcombo_step.npz'))
+        s = np.load(os.path.join(golden_dir, 'bignn_drugcombo_sampler_seq.npz'))
+        packed = 'drugcombo_packed.npz'
+    else:
+        B.set_flags(B.make_flags(device=DEV))
+        z = np.load(os.path.join(golden_dir, 'bignn_gin_gcn_step.npz'))
+        s = np.load(os.path.join(golden_dir, 'bignn_gin_gcn_sampler_seq.npz'))
+        packed = 'drugbank_packed.npz'
+    try:
+        data = B.BiGNNData.from_npz(os.path.join(golden_dir, packed), device=DEV)
+        model = B.Model(data).to(DEV)
+        sd = {k[4:]: torch.from_numpy(np.asarray(z[k])) for k in z.files if k.startswith('sd0/')}
+        for k in z.files:
+            if k.startswith('sd_init/'):
+                sd[k[len('sd_init/'):]] = torch.from_numpy(np.asarray(z[k]))
+        model.load_state_dict(sd, strict=False)
+        model.train()
+        eng = BiGNNEngine(data, model, use_cuda_graph=True)
+        n = min(8, s['pos'].shape[0])
+        st, P = eng.stage_pairs(z['batch_gids'], z['y_true'].astype(np.float32))
+        got = [eng.read_loss(eng.step_staged(st, P))]
+        for i in range(n):
+            st, P = eng.stage_pairs(np.concatenate([s['pos'][i], s['neg'][i]]), s['y'][i].astype(np.float32))
+            got.append(eng.read_loss(eng.step_staged(st, P)))
+        want = np.concatenate([[float(z['loss'])], s['losses'][:n]])
+        dev = np.abs(np.asarray(got) - want)
+        print(arch, 'loss trajectory deviation from the reference per step:', ' '.join('%.1e' % d for d in dev))
+        bound = (2e-6 if arch == 'drugcombo' else 2e-5) * 4.0 ** np.arange(n + 1)
+        assert dev[0] < 1e-5 and np.all(dev <= np.maximum(bound, 1e-5)), dev
+    finally:
+        B.set_flags(B.make_flags(device=DEV))

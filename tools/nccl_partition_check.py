@@ -25,6 +25,55 @@ def rel(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
 
 
+def trajectory(rank, world, dev, B, BiGNNEngine, gold, n=8):
+    """DrugCombo architecture (MetaLayer upper level, replicated; lower level sharded by drug) and GIN+GCN (upper level
+    row-partitioned): consecutive train steps with Adam on the batches the reference recorded, on `world` ranks, against
+    the reference's own losses AND against the same steps on one rank (run by every rank on its own GPU)."""
+    ok = True
+    for arch in ('drugcombo', 'gin_gcn'):
+        if arch == 'drugcombo':
+            flags = dict(dataset='drugcombo', higher_level_gnn_type='gat', device=dev)
+            z = np.load(os.path.join(gold, 'bignn_drugcombo_step.npz'))
+            s = np.load(os.path.join(gold, 'bignn_drugcombo_sampler_seq.npz'))
+            packed = 'drugcombo_packed.npz'
+        else:
+            flags = dict(device=dev)
+            z = np.load(os.path.join(gold, 'bignn_gin_gcn_step.npz'))
+            s = np.load(os.path.join(gold, 'bignn_gin_gcn_sampler_seq.npz'))
+            packed = 'drugbank_packed.npz'
+        res = {}
+        for w in (1, world):
+            B.set_flags(B.make_flags(**flags))
+            data = B.BiGNNData.from_npz(os.path.join(gold, packed), device=dev)
+            model = B.Model(data).to(dev)
+            sd = {k[4:]: torch.from_numpy(np.asarray(z[k])) for k in z.files if k.startswith('sd0/')}
+            for k in z.files:
+                if k.startswith('sd_init/'):
+                    sd[k[len('sd_init/'):]] = torch.from_numpy(np.asarray(z[k]))
+            model.load_state_dict(sd, strict=False)
+            model.train()
+            eng = BiGNNEngine(data, model, use_cuda_graph=True, rank=rank if w > 1 else 0, world=w)
+            st, P = eng.stage_pairs(z['batch_gids'], z['y_true'].astype(np.float32))
+            got = [eng.read_loss(eng.step_staged(st, P))]
+            m = min(n, s['pos'].shape[0])
+            for i in range(m):
+                st, P = eng.stage_pairs(np.concatenate([s['pos'][i], s['neg'][i]]), s['y'][i].astype(np.float32))
+                got.append(eng.read_loss(eng.step_staged(st, P)))
+            res[w] = np.asarray(got)
+            torch.cuda.synchronize()
+            dist.barrier()
+        want = np.concatenate([[float(z['loss'])], s['losses'][:m]])
+        d_ref = np.abs(res[world] - want)
+        d_one = np.abs(res[world] - res[1])
+        bound = (2e-6 if arch == 'drugcombo' else 2e-5) * 4.0 ** np.arange(m + 1)
+        good = bool(d_ref[0] < 1e-5 and np.all(d_ref <= np.maximum(bound, 1e-5)) and np.all(d_one <= np.maximum(bound, 1e-5)))
+        ok = ok and good
+        print('rank {}/{} trajectory {} {} vs reference [{}] vs one rank [{}]'.format(
+            rank, world, arch, 'OK' if good else 'FAIL', ' '.join('%.1e' % v for v in d_ref),
+            ' '.join('%.1e' % v for v in d_one)), flush=True)
+    return ok
+
+
 def main():
     rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
     torch.cuda.set_device(local)
@@ -73,6 +122,7 @@ def main():
             del eng
             torch.cuda.synchronize()
             dist.barrier()
+    ok = trajectory(rank, world, dev, B, BiGNNEngine, gold) and ok
     print('rank {} RESULT {}'.format(rank, 'PASS' if ok else 'FAIL'), flush=True)
     # no destroy_process_group(): captured graphs still hold NCCL kernels (see bench.py)
     os._exit(0 if ok else 1)
