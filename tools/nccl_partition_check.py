@@ -65,8 +65,13 @@ def trajectory(rank, world, dev, B, BiGNNEngine, gold, n=8):
         want = np.concatenate([[float(z['loss'])], s['losses'][:m]])
         d_ref = np.abs(res[world] - want)
         d_one = np.abs(res[world] - res[1])
-        bound = (2e-6 if arch == 'drugcombo' else 2e-5) * 4.0 ** np.arange(m + 1)
-        good = bool(d_ref[0] < 1e-5 and np.all(d_ref <= np.maximum(bound, 1e-5)) and np.all(d_one <= np.maximum(bound, 1e-5)))
+        # bounds as in tests/test_gpu_engine.py::test_loss_trajectory_follows_the_reference (GIN+GCN is chaotic from
+        # the second step on: Adam's sign-like first updates on noise-level lower-layer gradients)
+        if arch == 'drugcombo':
+            bound = np.maximum(2e-6 * 4.0 ** np.arange(m + 1), 1e-5)
+        else:
+            bound = np.asarray([1e-5, 1e-4] + [2e-2] * (m - 1))
+        good = bool(np.all(d_ref <= bound) and np.all(d_one <= bound))
         ok = ok and good
         print('rank {}/{} trajectory {} {} vs reference [{}] vs one rank [{}]'.format(
             rank, world, arch, 'OK' if good else 'FAIL', ' '.join('%.1e' % v for v in d_ref),
