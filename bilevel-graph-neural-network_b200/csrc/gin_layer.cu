@@ -21,7 +21,9 @@
 //                     128-bit stores, summing the BatchNorm statistics of the rows they store.
 // mbarriers: z_full/z_empty per slot (producers <-> MMA / epilogue), t_full (epilogue -> MMA), m1/m2 (tcgen05.commit).
 // Weights (hi and lo parts of W1, W2) stay resident in shared memory for every tile of the CTA.
+#include <cstdio>
 #include <cstdlib>
+#include <cuda.h>
 #include "tc_common.cuh"
 
 namespace bignn {
@@ -60,13 +62,25 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
     __nanosleep(100);
   }
 }
+// ---- TMA: one [128 rows x 32 floats] box of X lands in shared memory in the K-major SWIZZLE_128B layout (the layout the
+// UMMA descriptors read), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
 // one non-blocking test of a phase
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
   uint32_t done;
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t"
       "}\n"
       : "=r"(done)
@@ -131,6 +145,7 @@ struct GinLayerArgs {
   int act_inner, act_outer;
   float* Z; int64_t ldz; float* T; int64_t ldt; float* Y; int64_t ldy;
   double* stat_parts;                                 // [(n_tiles + S)][2][64] or null
+  long long* trace;                                   // debugging: clock64 stamps of CTA 0's pipeline events (or null)
 };
 
 // issue the 3xTF32 MMAs of one [128 x K] x [K x 64] product (A in `slot`, B = resident weight parts) into ONE
@@ -166,9 +181,16 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_acc, const uint8_t* a_h
   }
 }
 
-template <int THREADS>
+#define GL_TRACE(ev, i) do { if (p.trace && blockIdx.x == 0 && lane == 0 && (i) < 64) p.trace[(i) * 16 + (ev)] = clock64(); } while (0)
+
+// STAGE_X: the tile's own rows of X are brought into shared memory by TMA (cp.async.bulk.tensor, SWIZZLE_128B) and the
+// aggregation reads them there; otherwise every row is gathered straight from global memory / L1.  Measured on B200 at
+// 6 M rows (profiles/r2_summary.md): the kernel is bound by shared-memory bandwidth (the 3xTF32 operands are read three
+// times by the tensor core), so the extra 230 KB of shared-memory traffic per tile of the staged variant costs more than
+// the global-memory latency it removes -- direct gathers are the default, BIGNN_GL_STAGE=1 selects the staged variant.
+template <int THREADS, bool STAGE_X>
 __global__ void __launch_bounds__(THREADS, 1)
-k_gin_layer_fwd(const GinLayerArgs p) {
+k_gin_layer_fwd(const GinLayerArgs p, const __grid_constant__ CUtensorMap tmx) {
   constexpr int N_WARPS = THREADS / 32;
   // warps 0-3: epilogue of the first transform (E1), 4-7: epilogue of the second (E2), 8: MMA issuer,
   // 9: index prefetch, 10..: producers
@@ -182,7 +204,7 @@ k_gin_layer_fwd(const GinLayerArgs p) {
   uint8_t* w2_hi = w1_lo + GL_W;
   uint8_t* w2_lo = w2_hi + GL_W;
   int32_t* idx_s = reinterpret_cast<int32_t*>(w2_lo + GL_W);      // [stages][rp 132 | col CAP]
-  __shared__ uint64_t z_full[2], z_empty[2], t_full[2], t_copied[2], acc2_free[2], m1_done[2], m2_done[2],
+  __shared__ uint64_t x_full[2], z_full[2], z_empty[2], t_full[2], t_copied[2], acc2_free[2], m1_done[2], m2_done[2],
       idx_full[GL_IDX_STAGES], idx_empty[GL_IDX_STAGES];
   __shared__ uint32_t tmem_base_s;
   __shared__ float b1_s[GL_D], b2_s[GL_D];
@@ -202,6 +224,7 @@ k_gin_layer_fwd(const GinLayerArgs p) {
     mbar_init(&z_empty[0], GL_EPI_WARPS); mbar_init(&z_empty[1], GL_EPI_WARPS);
 #pragma unroll
     for (int b = 0; b < 2; ++b) {
+      mbar_init(&x_full[b], 1);
       mbar_init(&t_full[b], GL_EPI_WARPS); mbar_init(&t_copied[b], GL_EPI_WARPS); mbar_init(&acc2_free[b], GL_EPI_WARPS);
       mbar_init(&m1_done[b], 1); mbar_init(&m2_done[b], 1);
     }
@@ -259,21 +282,48 @@ k_gin_layer_fwd(const GinLayerArgs p) {
       const int32_t* rp_s = idx_s + st * (GL_IDX_RP + GL_IDX_CAP);
       const int32_t* col_s = rp_s + GL_IDX_RP;
       mbar_wait_relaxed(&idx_full[st], (it / GL_IDX_STAGES) & 1);
-      mbar_wait_relaxed(&z_empty[b], ((it >> 1) & 1) ^ 1);
+      if (STAGE_X) {
+        // neighbours outside the tile (molecules that straddle a tile boundary) come from global memory: ask for their
+        // rows now, while the tile itself is still in flight, so that the aggregation below finds them in L1/L2
+        const int m0p = tile * TC_BM, e_lop = rp_s[0] & ~3;
+        for (int r = grp; r < TC_BM; r += N_GROUPS) {
+          if (m0p + r >= p.rows) break;
+          for (int k = rp_s[r] + (l8 >> 1); k < rp_s[r + 1]; k += 4) {      // lane pair j of the group: neighbours j, j+4, ..
+            const int c = (k - e_lop < GL_IDX_CAP) ? col_s[k - e_lop] : __ldg(p.col_idx + k);
+            if ((unsigned)(c - m0p) >= (unsigned)TC_BM) {
+              const float* q = p.X + (int64_t)c * ldx + 32 * (l8 & 1);      // the two 128-byte halves of the row
+              if (32 * (l8 & 1) < 4 * din4) asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
+            }
+          }
+        }
+        if (warp == FIRST_PROD) GL_TRACE(14, it);
+        mbar_wait_relaxed(&x_full[b], (it >> 1) & 1);      // the tile's rows of X are staged in the slot's lo region
+      }
+      mbar_wait_relaxed(&z_empty[b], ((it >> 1) & 1) ^ 1);   // E2 has stored the tile that used the slot's hi region
+      if (warp == FIRST_PROD) GL_TRACE(0, it);
       uint8_t* a_hi = smem + b * GL_SLOT;
       uint8_t* a_lo = a_hi + 2 * TC_BM * 128;
+      const uint8_t* xs = a_lo;                             // staged X rows, K-major SWIZZLE_128B (written by TMA)
       const int m0 = tile * TC_BM;
       const int e_lo = rp_s[0] & ~3;                        // first staged neighbour id (16-byte aligned start)
       int chunk = fold ? __ldg(p.tile_chunk0 + tile) : 0;
+      // ---- phase 1: z rows from the staged tile (neighbours outside it: global memory) -> the slot's hi region
 #pragma unroll 1
       for (int r = grp; r < TC_BM; r += N_GROUPS) {
         const int grow = m0 + r;
         float4 z0 = f4z(), z1 = f4z();
         if (grow < p.rows && !(p.dbg & 1)) {
           const int k0 = rp_s[r], k1 = rp_s[r + 1];
-          const float* xr = X + (int64_t)grow * ldx;
-          float4 s0 = ok0 ? ldg4(xr) : f4z();
-          float4 s1 = ok1 ? ldg4(xr + 32) : f4z();
+          float4 s0 = f4z(), s1 = f4z();
+          if (STAGE_X) {
+            const uint32_t soff = sw128_off(r, l8);
+            if (ok0) s0 = *reinterpret_cast<const float4*>(xs + soff);
+            if (ok1) s1 = *reinterpret_cast<const float4*>(xs + TC_BM * 128 + soff);
+          } else {
+            const float* xr = X + (int64_t)grow * ldx;
+            if (ok0) s0 = ldg4(xr);
+            if (ok1) s1 = ldg4(xr + 32);
+          }
           // BatchNorm of the producer layer folded in, centred: sum_j (a (y_j - mean) + beta) = a * sum_j (y_j - mean)
           // + beta * (number of terms): the subtraction happens per loaded value (no cancellation of large sums)
           if (fold) {
@@ -294,11 +344,31 @@ k_gin_layer_fwd(const GinLayerArgs p) {
             if (k + 1 < k1) c1 = (k + 1 - e_lo < GL_IDX_CAP) ? col_s[k + 1 - e_lo] : __ldg(p.col_idx + k + 1);
             if (c0 == grow) c0 = -1;                             // remove_self_loops (PyG GINConv)
             if (c1 == grow) c1 = -1;
-            const float* n0 = X + (int64_t)(c0 >= 0 ? c0 : grow) * ldx;
-            const float* n1 = X + (int64_t)(c1 >= 0 ? c1 : grow) * ldx;
             float4 v00 = f4z(), v01 = f4z(), v10 = f4z(), v11 = f4z();
-            if (ok0) { v00 = ldg4(n0); v10 = ldg4(n1); }
-            if (ok1) { v01 = ldg4(n0 + 32); v11 = ldg4(n1 + 32); }
+            if (c0 >= 0) {
+              const unsigned l0 = (unsigned)(c0 - m0);
+              if (STAGE_X && l0 < (unsigned)TC_BM) {
+                const uint32_t o = sw128_off((int)l0, l8);
+                if (ok0) v00 = *reinterpret_cast<const float4*>(xs + o);
+                if (ok1) v01 = *reinterpret_cast<const float4*>(xs + TC_BM * 128 + o);
+              } else {
+                const float* n0 = X + (int64_t)c0 * ldx;
+                if (ok0) v00 = ldg4(n0);
+                if (ok1) v01 = ldg4(n0 + 32);
+              }
+            }
+            if (c1 >= 0) {
+              const unsigned l1 = (unsigned)(c1 - m0);
+              if (STAGE_X && l1 < (unsigned)TC_BM) {
+                const uint32_t o = sw128_off((int)l1, l8);
+                if (ok0) v10 = *reinterpret_cast<const float4*>(xs + o);
+                if (ok1) v11 = *reinterpret_cast<const float4*>(xs + TC_BM * 128 + o);
+              } else {
+                const float* n1 = X + (int64_t)c1 * ldx;
+                if (ok0) v10 = ldg4(n1);
+                if (ok1) v11 = ldg4(n1 + 32);
+              }
+            }
             if (c0 >= 0) { add4(a0, fold ? sub4(v00, mu0) : v00); add4(a1, fold ? sub4(v01, mu1) : v01); ++cnt; }
             if (c1 >= 0) { add4(a0, fold ? sub4(v10, mu0) : v10); add4(a1, fold ? sub4(v11, mu1) : v11); ++cnt; }
           }
@@ -318,12 +388,34 @@ k_gin_layer_fwd(const GinLayerArgs p) {
         const uint32_t off = sw128_off(r, l8);
         *reinterpret_cast<float4*>(a_hi + off) = z0;                          // raw fp32 = the TF32 hi operand
         *reinterpret_cast<float4*>(a_hi + TC_BM * 128 + off) = z1;
-        *reinterpret_cast<uint4*>(a_lo + off) = lo_part(z0);
-        *reinterpret_cast<uint4*>(a_lo + TC_BM * 128 + off) = lo_part(z1);
+        if (!STAGE_X) {
+          *reinterpret_cast<uint4*>(a_lo + off) = lo_part(z0);
+          *reinterpret_cast<uint4*>(a_lo + TC_BM * 128 + off) = lo_part(z1);
+        }
+        if (p.Z && grow < p.rows && !(p.dbg & 2)) {                           // kept for the backward (dW1 = dT^T z)
+          float* zr = p.Z + (int64_t)grow * p.ldz + 4 * l8;
+          if (ok0) st4(zr, z0);
+          if (ok1) st4(zr + 32, z1);
+        }
+        if (warp == FIRST_PROD) GL_TRACE(11 + (r / N_GROUPS), it);
+      }
+      if (warp == FIRST_PROD) GL_TRACE(1, it);
+      if (STAGE_X) {
+        // every producer has read what it needs from the staged tile: its region now takes the lo parts
+        named_bar_sync(3, N_PROD_WARPS * 32);
+#pragma unroll 1
+        for (int r = grp; r < TC_BM; r += N_GROUPS) {
+          const uint32_t off = sw128_off(r, l8);
+          const float4 z0 = *reinterpret_cast<const float4*>(a_hi + off);       // (this thread's own writes)
+          const float4 z1 = *reinterpret_cast<const float4*>(a_hi + TC_BM * 128 + off);
+          *reinterpret_cast<uint4*>(a_lo + off) = lo_part(z0);
+          *reinterpret_cast<uint4*>(a_lo + TC_BM * 128 + off) = lo_part(z1);
+        }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core proxy
       __syncwarp();
       if (lane == 0) { mbar_arrive(&z_full[b]); mbar_arrive(&idx_empty[st]); }
+      if (warp == FIRST_PROD) GL_TRACE(2, it);
     }
   } else if (warp == IDX_WARP) {
     // =============================================================== index prefetch: row pointers + neighbour ids of
@@ -371,8 +463,30 @@ k_gin_layer_fwd(const GinLayerArgs p) {
     const uint32_t idesc = umma_idesc_tf32(TC_BM, GL_D);
     const int n_my = p.n_tiles > (int)blockIdx.x ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     int i1 = 0, i2 = 0;                                     // next tile (of this CTA) for the first / second transform
+    int ix = 0;                                             // next tile whose rows of X are staged by TMA
+    const bool two_boxes = p.din > TC_KC;
     while (i2 < n_my) {
       bool did = false;
+      if (STAGE_X && ix < n_my && ix - i2 < 2) {
+        // the lo region of slot ix & 1 is free as soon as the second transform of tile ix-2 has completed (E2 stages y
+        // in the hi region only): the TMA latency hides behind E2's stores
+        const int b = ix & 1;
+        if (ix < 2 || __shfl_sync(0xffffffffu, lane == 0 ? (int)mbar_test(&m2_done[b], ((ix - 2) >> 1) & 1) : 0, 0)) {
+          if (lane == 0) {
+            // the tile's own rows of X -> the slot's lo region (free until the producers derive z_lo): the producers
+            // aggregate out of shared memory; only neighbours outside the tile are fetched from global memory
+            uint8_t* dst = smem + b * GL_SLOT + 2 * TC_BM * 128;
+            const int m0 = ((int)blockIdx.x + ix * (int)gridDim.x) * TC_BM;
+            mbar_expect_tx(&x_full[b], (two_boxes ? 2u : 1u) * TC_BM * 128u);
+            tma_load_2d(dst, &tmx, 0, m0, &x_full[b]);
+            if (two_boxes) tma_load_2d(dst + TC_BM * 128, &tmx, TC_KC, m0, &x_full[b]);
+          }
+          GL_TRACE(8, ix);
+          __syncwarp();
+          ++ix;
+          did = true;
+        }
+      }
       if (i1 < n_my && i1 - i2 < 2) {                       // acc1[i1 & 1] is free once t of tile i1-2 was consumed
         const int b = i1 & 1;
         // (every decision is made by lane 0 and broadcast: the operand descriptors live in uniform registers, so the
@@ -384,6 +498,7 @@ k_gin_layer_fwd(const GinLayerArgs p) {
             issue_gemm(acc1 + (uint32_t)(b * GL_D), a_hi, a_hi + 2 * TC_BM * 128, w1_hi, w1_lo, K1, idesc);
             umma_commit(&m1_done[b]);
           }
+          GL_TRACE(9, i1);
           __syncwarp();
           ++i1;
           did = true;
@@ -400,6 +515,7 @@ k_gin_layer_fwd(const GinLayerArgs p) {
             issue_gemm(acc2 + (uint32_t)(b * GL_D), a_hi, a_hi + 2 * TC_BM * 128, w2_hi, w2_lo, K2, idesc);
             umma_commit(&m2_done[b]);
           }
+          GL_TRACE(10, i2);
           __syncwarp();
           ++i2;
           did = true;
@@ -425,18 +541,8 @@ k_gin_layer_fwd(const GinLayerArgs p) {
       const int rows_here = min(TC_BM, p.rows - m0);
       const uint8_t* src = a_hi + (c4 >> 3) * (TC_BM * 128);
       mbar_wait(&m1_done[b], (it >> 1) & 1);
+      if (warp == 0) GL_TRACE(3, it);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (p.Z) {                                            // z leaves (kept for the backward) before t comes in
-        if (store && c4 < ((p.din + 3) >> 2)) {
-#pragma unroll 4
-          for (int i = 0; i < 16; ++i) {
-            const int r = rg + 8 * i;
-            if (r < rows_here)
-              st4(p.Z + (int64_t)(m0 + r) * p.ldz + 4 * c4, *reinterpret_cast<const float4*>(src + sw128_off(r, c4 & 7)));
-          }
-        }
-        named_bar_sync(1, GL_EPI_WARPS * 32);
-      }
 #pragma unroll 1
       for (int cb = 0; cb < GL_D; cb += 32) {
         float v[32];
@@ -462,6 +568,7 @@ k_gin_layer_fwd(const GinLayerArgs p) {
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&t_full[b]);
+      if (warp == 0) GL_TRACE(4, it);
       if (p.T) {
         named_bar_sync(1, GL_EPI_WARPS * 32);               // all of t is in the slot; copy it out while the MMA runs
         if (store) {
@@ -495,6 +602,7 @@ k_gin_layer_fwd(const GinLayerArgs p) {
       const int rows_here = min(TC_BM, p.rows - m0);
       const uint8_t* src = a_hi + (c4 >> 3) * (TC_BM * 128);
       mbar_wait(&m2_done[b], (it >> 1) & 1);                // t has been consumed
+      if (qw == 0) GL_TRACE(5, it);
       if (p.T) mbar_wait(&t_copied[b], (it >> 1) & 1);      // ... and copied out by E1
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
@@ -517,6 +625,7 @@ k_gin_layer_fwd(const GinLayerArgs p) {
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc2_free[b]);
+      if (qw == 0) GL_TRACE(6, it);
       named_bar_sync(2, GL_EPI_WARPS * 32);
       // ---------------- coalesced copy-out (+ BatchNorm partial sums of the stored rows when the tile lies in one chunk)
       int chunk = 0, chunk_end = rows_here;
@@ -577,6 +686,7 @@ k_gin_layer_fwd(const GinLayerArgs p) {
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&z_empty[b]);
+      if (qw == 0) GL_TRACE(7, it);
     }
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -659,13 +769,46 @@ extern "C" int bignn_gin_layer_fwd(int32_t rows, int32_t din, int32_t dout, cons
     return BIGNN_EALIGN;
   constexpr int THREADS = 768;      // 24 warps: 4 + 4 epilogue, MMA, index prefetch, 14 producers = 56 row groups
   static bool configured = false;
-  static int dbg = 0;
+  static int dbg = 0, stage = 0;
+  static long long* trace_dev = nullptr;
+  static const char* trace_path = nullptr;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_gin_layer_fwd<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, GL_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(k_gin_layer_fwd<THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GL_SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(k_gin_layer_fwd<THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GL_SMEM);
     if (e != cudaSuccess) return (int)e;
+    const char* sg = getenv("BIGNN_GL_STAGE");
+    stage = sg ? atoi(sg) : 0;
     const char* d = getenv("BIGNN_GL_DEBUG");     // timing experiments only: 1 = no gathers, 2 = no stores (results invalid)
     dbg = d ? atoi(d) : 0;
+    trace_path = getenv("BIGNN_GL_TRACE");       // debugging: dump CTA 0's pipeline time stamps of every launch to this file
+    if (trace_path && cudaMalloc(&trace_dev, 64 * 16 * sizeof(long long)) != cudaSuccess) trace_dev = nullptr;
     configured = true;
+  }
+  // TMA descriptor of X: [rows, din_pad] fp32, row pitch ldx, boxes of 32 columns x 128 rows, SWIZZLE_128B; columns and
+  // rows outside the tensor read as zeros (the zero padding of the first layer's 49 -> 64 columns comes for free)
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess) return (int)e;
+    if (!fn || q != cudaDriverEntryPointSuccess) return BIGNN_EINVAL;
+    encode = (EncodeFn)fn;
+  }
+  CUtensorMap tmx;
+  {
+    const cuuint64_t gdim[2] = {(cuuint64_t)din_pad, (cuuint64_t)rows};
+    const cuuint64_t gstr[1] = {(cuuint64_t)ldx * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)TC_KC, (cuuint32_t)TC_BM};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(&tmx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)X, gdim, gstr, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return BIGNN_EINVAL;
   }
   GinLayerArgs a;
   a.rows = rows; a.din = din; a.n_tiles = ceil_div(rows, TC_BM); a.nnz = nnz; a.dbg = dbg;
@@ -674,10 +817,28 @@ extern "C" int bignn_gin_layer_fwd(int32_t rows, int32_t din, int32_t dout, cons
   a.chunk_row_ptr = chunk_row_ptr; a.tile_chunk0 = tile_chunk0; a.self_coef = self_coef;
   a.W1 = W1; a.b1 = b1; a.W2 = W2; a.b2 = b2; a.act_inner = act_inner; a.act_outer = act_outer;
   a.Z = Z; a.ldz = ldz; a.T = T; a.ldt = ldt; a.Y = Y; a.ldy = ldy; a.stat_parts = stat_parts;
+  a.trace = trace_dev;
+  if (trace_dev) cudaMemsetAsync(trace_dev, 0, 64 * 16 * sizeof(long long), (cudaStream_t)stream);
   int grid = sm_count();
   if (grid > a.n_tiles) grid = a.n_tiles;
-  k_gin_layer_fwd<THREADS><<<grid, THREADS, GL_SMEM, (cudaStream_t)stream>>>(a);
+  if (stage)
+    k_gin_layer_fwd<THREADS, true><<<grid, THREADS, GL_SMEM, (cudaStream_t)stream>>>(a, tmx);
+  else
+    k_gin_layer_fwd<THREADS, false><<<grid, THREADS, GL_SMEM, (cudaStream_t)stream>>>(a, tmx);
   BIGNN_LAUNCH_COUNT(1);
+  if (trace_dev) {                                   // (debug mode only: synchronises)
+    static long long host[64 * 16];
+    cudaStreamSynchronize((cudaStream_t)stream);
+    cudaMemcpy(host, trace_dev, sizeof(host), cudaMemcpyDeviceToHost);
+    FILE* f = fopen(trace_path, "w");
+    if (f) {
+      for (int i = 0; i < 64; ++i) {
+        for (int e = 0; e < 16; ++e) fprintf(f, "%lld ", host[i * 16 + e]);
+        fprintf(f, "\n");
+      }
+      fclose(f);
+    }
+  }
   return last_launch_status();
 }
 
