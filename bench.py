@@ -22,6 +22,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = 'train drug-pairs/sec'
 UNIT = 'pairs/s'
+LOWER_ONLY_POS = 32768          # positive pairs per step of the lower-level-only workload (scaled pair batch)
 
 
 def parse():
@@ -53,6 +54,13 @@ def parse():
 def workload_config(name):
     from bignn_b200 import synthetic as S
     w = S.WORKLOADS[name]
+    if name.startswith('mol_1m'):
+        # BASELINE config 3: the lower-level-only model (src/train.py:99-107) over large pair batches
+        return dict(workload='LL-GNN, lower level only (GIN x5, multi-scale mean readout, MLP scorer 640-80-10-1, BCE, Adam) '
+                             'on a synthetic dataset of {} shape'.format(name),
+                    name=name, drugs=w['N'], ddi_edges=w['M'], mean_atoms=w['mean_atoms'],
+                    node_feat=int(sum(w['groups'])), pos_pairs_per_step=LOWER_ONLY_POS, neg_pairs_per_step=LOWER_ONLY_POS,
+                    batch_norm_batch='the merged pair batch (one BatchNorm batch per step, as in the reference)')
     arch = ('GIN x5 lower, multi-scale mean readout, MetaLayer x3 upper (one GAT per interaction edge type, summed), '
             'MLP scorer 128-16-3, CE, Adam') if 'drugcombo' in name else \
         ('GIN x5 lower, mean readout (64-dim upper input), GCN x3 upper, MLP scorer, BCE, Adam' if 'ddi_scaled' in name
@@ -73,6 +81,8 @@ def workload_flags(name, device='cuda:0'):
     """drugcombo_shape runs the DrugCombo architecture the reference ships for that dataset
     (src/config.py:74-88,120-123,224): one GAT per interaction edge type through MetaLayer, 3-class CE."""
     import bignn_b200 as B
+    if name.startswith('mol_1m'):
+        return B.make_flags(model='lower_level_gnn', device=device)
     if 'drugcombo' in name:
         return B.make_flags(dataset='drugcombo', higher_level_gnn_type='gat', device=device)
     if 'ddi_scaled' in name:          # BASELINE config 4: 64-dim interaction-graph stage (SURVEY 8d: mean readout, not multi-scale)
@@ -90,7 +100,10 @@ def layer_specs(name):
 # infeasible as a bounded sample on the CPU (~30 s and tens of GB of autograd state per
 # step): each reference-arm step is ONE FULL TRAIN STEP OF THE SAME WORKLOAD AT 1/10 SIZE, and the reported value is
 # the linear extrapolation to full size (the step cost scales with drugs and edges, not with the 128 scored pairs).
-REFERENCE_SAMPLE = {'ddi_scaled': ('ddi_scaled_small', 10.0)}
+REFERENCE_SAMPLE = {'ddi_scaled': ('ddi_scaled_small', 10.0), 'ppi_50k': ('ppi_50k_small', 10.0)}
+# lower-level-only model: the step cost is proportional to the pairs scored, so the reference arm runs the same model on
+# the same kind of data with a smaller pair batch and its pairs/s compare directly (no extrapolation)
+LOWER_ONLY_REFERENCE = ('mol_1m_small', 1024)
 
 
 def run_reference(args, sample_steps=None, device='cpu'):
@@ -101,13 +114,19 @@ def run_reference(args, sample_steps=None, device='cpu'):
     from oracle import bignn_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    lower_only = args.workload.startswith('mol_1m')
     name, scale = REFERENCE_SAMPLE.get(args.workload, (args.workload, 1.0))
+    if lower_only:
+        name, scale = LOWER_ONLY_REFERENCE[0], 1.0
     w = make_workload(name, args.seed)
     ds = O.PackedDataset(w)
     specs = O.parse_specs(layer_specs(args.workload))
     state = O.init_params(specs, ds.num_node_feat, num_labels=int(w['num_labels']), seed=8,
                           num_edge_types=len(ds.etypes) + 1)
-    tr = O.OracleTrainer(ds, specs, state, 64, device=device)
+    if lower_only:
+        tr = O.OracleLowerOnlyTrainer(ds, specs, state, LOWER_ONLY_REFERENCE[1], device=device)
+    else:
+        tr = O.OracleTrainer(ds, specs, state, 64, device=device)
     np.random.seed(8)
     torch.manual_seed(8)
     steps = args.steps if sample_steps is None else sample_steps
@@ -125,7 +144,11 @@ def run_reference(args, sample_steps=None, device='cpu'):
     dt = time.perf_counter() - t0
     measured = pairs / dt
     what = 'torch {} eager fp32'.format('CUDA' if device != 'cpu' else 'CPU')
-    if scale == 1.0:
+    if lower_only:
+        sample = ('{} full train steps of the same model on {} ({} drugs) with {} pairs/step instead of {} (the step cost is '
+                  'proportional to the pairs scored: pairs/s compare directly), {}, {} host threads').format(
+            steps, name, ds.N, pairs // max(steps, 1), 2 * LOWER_ONLY_POS, what, cores)
+    elif scale == 1.0:
         sample = '{} full train steps of the same workload ({} pairs/step), {}, {} host threads'.format(
             steps, pairs // max(steps, 1), what, cores)
     else:
@@ -364,6 +387,78 @@ def run_ours(args):
     return out, (torch, B, peaks, dev, eng, data, model)
 
 
+def run_lower_only(args):
+    """BASELINE config 3: the lower-level-only model over large pair batches on one GPU (engine_lower.LowerOnlyEngine)."""
+    import torch
+    import bignn_b200 as B
+    from bignn_b200.engine_lower import LowerOnlyEngine
+    if int(os.environ.get('WORLD_SIZE', 1)) > 1:
+        if int(os.environ.get('RANK', 0)) == 0:
+            print(json.dumps(dict(impl='ours', unavailable='the lower-level-only workload runs on one GPU in this round')))
+        return None
+    dev = 'cuda:0'
+    torch.cuda.set_device(0)
+    B._lib.load()
+    peaks = {}
+    pk = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    B.set_flags(workload_flags(args.workload, dev))
+    data = B.BiGNNData.from_npz(make_workload(args.workload, args.seed), device=dev)
+    torch.manual_seed(8)
+    np.random.seed(8)
+    model = B.Model(data).to(dev)
+    model.train()
+    eng = LowerOnlyEngine(data, model)
+    sampler = B.RandomSampler(data, LOWER_ONLY_POS)
+    flush = None if args.no_l2_flush else torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    rng = np.random.default_rng(8)
+    for _ in range(max(args.warmup, 3)):
+        loss = eng.train_step(sampler, fast_negatives=True, rng=rng)
+    torch.cuda.synchronize()
+    clocks = ClockSampler(0)
+    clocks.start()
+    # (1) device-resident: the staged batch (unique drug rows, pair positions, labels) is on the host side of nothing --
+    # merged-graph construction from the packed dataset in HBM, forward, backward, Adam
+    staged = eng.last_static_batch
+    P = staged[1].shape[0]
+    n0 = B._lib.launch_count()
+    eng._device_step(staged)
+    eng.launches_per_step = B._lib.launch_count() - n0
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in evs:
+        if flush is not None:
+            flush.fill_(1.0)
+        a.record()
+        eng._device_step(staged)
+        b.record()
+    torch.cuda.synchronize()
+    dev_ms = float(sum(a.elapsed_time(b) for a, b in evs))
+    # (2) end to end: positive sampling (DataLoader), vectorised negatives, staging, step, loss read-back
+    t0 = time.perf_counter()
+    pairs = 0
+    for _ in range(args.steps):
+        if flush is not None:
+            flush.fill_(1.0)
+        loss = float(eng.train_step(sampler, fast_negatives=True, rng=rng))
+        pairs += eng.last_pairs
+    e2e_ms = 1e3 * (time.perf_counter() - t0)
+    clk = clocks.stop()
+    m = eng.last['merged']
+    out = dict(metric=METRIC, value=P * args.steps / (dev_ms * 1e-3), unit=UNIT, n_gpus=1, steps=args.steps,
+               warmup=max(args.warmup, 3), ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling='strong',
+               vs_baseline=None, dtype='f32', data='synthetic', impl='ours', config=workload_config(args.workload),
+               run=dict(l2='flushed between timed steps (256 MiB write)' if flush is not None else 'not flushed',
+                        cuda_graph=False, parallelism='single', lower_path=eng.lower_path,
+                        merged_graph=dict(graphs=m.G, atoms=m.A, directed_bonds=m.E),
+                        negative_sampler='vectorised (engine_lower.fast_negative_pairs; not the reference sample stream)'),
+               e2e=dict(value=pairs / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=eng.h2d_bytes_per_step,
+                        d2h_bytes_per_step=4, ms_per_step=e2e_ms / args.steps),
+               clocks=clk, last_loss=loss)
+    return out, (torch, B, peaks, dev, eng, data, model)
+
+
 def _numel(t):
     return int(t.numel()) if t is not None and hasattr(t, 'numel') else 0
 
@@ -508,7 +603,7 @@ def main():
                    e2e=dict(value=r['value'], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         print(json.dumps(out))
         return
-    res = run_ours(args)
+    res = run_lower_only(args) if args.workload.startswith('mol_1m') else run_ours(args)
     if res is None:
         return
     out, (torch, B, peaks, dev, eng, data, model) = res

@@ -145,6 +145,40 @@ class BiGNNData(object):
     def __getitem__(self, idx):
         return self.data_items[idx]
 
+    # ---- vectorised host lookups (large pair batches: engine_lower.LowerOnlyEngine, scaled benchmarks)
+    def rows_of_gids(self, gids):
+        """gs_map over an int64 array of gids."""
+        if getattr(self, '_gid_lut', None) is None:
+            keys = np.fromiter(self.gs_map.keys(), np.int64, len(self.gs_map))
+            vals = np.fromiter(self.gs_map.values(), np.int64, len(self.gs_map))
+            o = np.argsort(keys)
+            self._gid_lut = (keys[o], vals[o])
+        keys, vals = self._gid_lut
+        g = np.asarray(gids, np.int64)
+        i = np.minimum(np.searchsorted(keys, g), keys.shape[0] - 1)
+        if g.size and not np.array_equal(keys[i], g):
+            raise KeyError('unknown gid in a pair batch')
+        return vals[i]
+
+    def edge_keys_sorted(self):
+        """sorted N*row+col keys of the train interaction graph (both orientations)."""
+        return self._edge_keys
+
+    def labels_of_pairs(self, gid_pairs):
+        """look_up_label over an array of pairs (either orientation; 0 when unknown)."""
+        p = np.asarray(gid_pairs, np.int64)
+        if isinstance(self.pairs, _PairTable):
+            rows = self.rows_of_gids(p.reshape(-1)).reshape(-1, 2)
+            out = np.zeros(p.shape[0], np.int64)
+            for a, b in ((0, 1), (1, 0)):
+                k = rows[:, a] * self.N + rows[:, b]
+                i = np.minimum(np.searchsorted(self.pairs.keys, k), self.pairs.keys.shape[0] - 1)
+                hit = self.pairs.keys[i] == k
+                out = np.where((out == 0) & hit, self.pairs.labels[i], out)
+            return out
+        return np.asarray([0 if l is None else l for l in
+                           (self.look_up_label(int(a), int(b)) for a, b in p.tolist())], np.int64)
+
     def look_up_label(self, gid1, gid2):
         """utils/data/dataset.py:394-403 (None instead of ValueError when unknown)."""
         l = self.pairs.get((gid1, gid2))

@@ -7,20 +7,22 @@ FEATURE_GROUPS = (27, 2, 2, 2, 7, 9)      # six one-hot groups, 49 columns (Drug
 
 
 def molecule_graphs(G, mean_atoms=28.0, seed=0, min_atoms=2, max_atoms=457, sigma=0.45, chord_frac=0.08,
-                    groups=FEATURE_GROUPS):
+                    groups=FEATURE_GROUPS, backbone=False):
     """G molecule-like graphs: sizes ~ clipped log-normal rescaled to `mean_atoms`; edges = random
     spanning tree + round(chord_frac*n) chords (deduplicated, no self loops); features = one-hot
-    groups with a Zipf-ish category skew.  Returns atom_ptr, nbr_ptr, nbr_idx (local ids, sorted), x."""
+    groups with a Zipf-ish category skew.  backbone=True (protein-like representation graphs, SURVEY 8d S-mol for C5):
+    the tree is the residue chain i -- i+1 and the chords are random contacts (chord_frac = 3 gives mean degree ~8).
+    Returns atom_ptr, nbr_ptr, nbr_idx (local ids, sorted), x."""
     rng = np.random.default_rng(seed)
     n = np.exp(rng.normal(np.log(26.0), sigma, G))
     n = np.clip(np.round(n * (mean_atoms / n.mean())), min_atoms, max_atoms).astype(np.int64)
     atom_ptr = np.concatenate([[0], np.cumsum(n)])
     A = int(atom_ptr[-1])
-    # spanning tree: atom i>0 of a graph attaches to a random earlier atom of the same graph
+    # spanning tree: atom i>0 of a graph attaches to a random earlier atom of the same graph (or to i-1: a chain)
     local = np.arange(A) - np.repeat(atom_ptr[:-1], n)
     gid = np.repeat(np.arange(G), n)
     child = np.nonzero(local > 0)[0]
-    parent_local = (rng.random(child.shape[0]) * local[child]).astype(np.int64)
+    parent_local = local[child] - 1 if backbone else (rng.random(child.shape[0]) * local[child]).astype(np.int64)
     src = [local[child]]
     dst = [parent_local]
     eg = [gid[child]]
@@ -76,12 +78,14 @@ def interaction_graph(N, M, seed=0, skew=0.8):
     return pairs, key // N, key % N
 
 
-def bignn_workload(N, M, mean_atoms=28.0, seed=0, groups=FEATURE_GROUPS, max_atoms=457, edge_type_fracs=None):
+def bignn_workload(N, M, mean_atoms=28.0, seed=0, groups=FEATURE_GROUPS, max_atoms=457, edge_type_fracs=None,
+                   min_atoms=2, chord_frac=0.08, backbone=False):
     """A full Bi-GNN dataset dict (keys as tests/golden/drugbank_packed.npz).  With
     `edge_type_fracs` (e.g. {'synergy': 0.68, 'antagonism': 0.32}) every interaction gets one
     edge type: pair labels become 1..T (0 = sampled negative) and per-type directed COOs are added
     as `etype_row/<name>`, `etype_col/<name>` (the DrugCombo layout, utils/data/dataset.py:82-115)."""
-    atom_ptr, nbr_ptr, nbr_idx, x = molecule_graphs(N, mean_atoms, seed, groups=groups, max_atoms=max_atoms)
+    atom_ptr, nbr_ptr, nbr_idx, x = molecule_graphs(N, mean_atoms, seed, groups=groups, max_atoms=max_atoms,
+                                                    min_atoms=min_atoms, chord_frac=chord_frac, backbone=backbone)
     pairs, row, col = interaction_graph(N, M, seed)
     gids = np.arange(N, dtype=np.int64) + 1000          # gids are labels, not row numbers
     train_pairs = gids[pairs]
@@ -115,6 +119,16 @@ WORKLOADS = {
     'ddi_scaled': dict(N=200_000, M=20_000_000, mean_atoms=30.0, groups=FEATURE_GROUPS),
     # the same shape at 1/10 (CPU baseline of the scaled configuration; quick multi-GPU checks)
     'ddi_scaled_small': dict(N=20_000, M=2_000_000, mean_atoms=30.0, groups=FEATURE_GROUPS),
+    # BASELINE config 3 / SURVEY C3: 1 M molecule graphs x ~30 atoms (~65 directed bonds each); lower-level-only model
+    # (pairs drawn from a sparse 2 M-edge interaction list; the model never reads the interaction graph)
+    'mol_1m': dict(N=1_000_000, M=2_000_000, mean_atoms=30.0, groups=FEATURE_GROUPS),
+    'mol_1m_small': dict(N=100_000, M=200_000, mean_atoms=30.0, groups=FEATURE_GROUPS),
+    # BASELINE config 5 / SURVEY C5: 50 k protein-like representation graphs x ~400 residues (chain + random contacts,
+    # mean degree ~8; clipped to [50, 1000] residues) + a 5 M-edge interaction graph
+    'ppi_50k': dict(N=50_000, M=5_000_000, mean_atoms=400.0, groups=FEATURE_GROUPS, min_atoms=50, max_atoms=1000,
+                    chord_frac=3.0, backbone=True),
+    'ppi_50k_small': dict(N=5_000, M=500_000, mean_atoms=400.0, groups=FEATURE_GROUPS, min_atoms=50, max_atoms=1000,
+                          chord_frac=3.0, backbone=True),
 }
 
 

@@ -595,11 +595,13 @@ def lower_only_step_forward(model, ds, batch_gids, y):
     over gids_to_batch_ind rows (model/layers_link_pred.py:52) and the loss."""
     gids = unique_graphs_in_order(np.asarray(batch_gids))
     m = merge_graphs(ds, gids)
-    x = torch.from_numpy(m['x']).to(model.dtype)
-    acts, pooled = model.lower(x, torch.from_numpy(m['edge_index']), torch.from_numpy(m['batch']), len(gids))
+    dev = getattr(model, 'device', 'cpu')
+    x = torch.from_numpy(m['x']).to(model.dtype).to(dev)
+    acts, pooled = model.lower(x, torch.from_numpy(m['edge_index']).to(dev), torch.from_numpy(m['batch']).to(dev),
+                               len(gids))
     to_row = m['gids_to_batch_ind']
-    rows = torch.from_numpy(np.vectorize(to_row.get)(np.asarray(batch_gids)).astype(np.int64))
-    _, pred, loss = model.upper(pooled, None, rows, torch.from_numpy(np.asarray(y)))
+    rows = torch.from_numpy(np.vectorize(to_row.get)(np.asarray(batch_gids)).astype(np.int64)).to(dev)
+    _, pred, loss = model.upper(pooled, None, rows, torch.from_numpy(np.asarray(y)).to(dev))
     return m, acts, pooled, pred, loss
 
 
@@ -651,6 +653,19 @@ class OracleTrainer(object):
         self.model.zero_grad()
         gids, y = self.sample()
         _, _, _, loss = train_step_forward(self.model, self.ds, gids, y, self.bs)
+        loss.backward()
+        adam_step(self.model.P, self.adam)
+        return float(loss.detach()), len(gids)
+
+
+class OracleLowerOnlyTrainer(OracleTrainer):
+    """The lower-level-only model's hot loop (src/train.py:99-107,136-141): sample a pair batch, merge its unique
+    molecule graphs graph by graph, GIN stack + readout + scorer, backward, Adam."""
+
+    def step(self):
+        self.model.zero_grad()
+        gids, y = self.sample()
+        _, _, _, _, loss = lower_only_step_forward(self.model, self.ds, gids, y)
         loss.backward()
         adam_step(self.model.P, self.adam)
         return float(loss.detach()), len(gids)

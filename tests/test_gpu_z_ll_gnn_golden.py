@@ -68,3 +68,59 @@ def test_ll_gnn_step_vs_reference_golden(golden_dir, drugbank):
                 assert rel(sdm[k[4:]], z[k]) < 1e-5, k
     finally:
         B.set_flags(B.make_flags(device=DEV))
+
+
+def test_lower_only_engine_fused_vs_layers_vs_golden(golden_dir, drugbank):
+    """engine_lower.LowerOnlyEngine on the recorded LL-GNN step: the fused lower stack (one BatchNorm batch = the whole
+    merged pair batch) and the layer-by-layer stack against the reference's loss / pooled rows / gradients; then a
+    large pair batch (the engine's reason to exist) with the vectorised negative sampler."""
+    from bignn_b200.engine_lower import LowerOnlyEngine
+    B._lib.load()
+    z = np.load(os.path.join(golden_dir, 'bignn_ll_gnn_step.npz'))
+    try:
+        B.set_flags(B.make_flags(model='lower_level_gnn', device=DEV))
+        data = B.BiGNNData.from_npz(os.path.join(golden_dir, 'drugbank_packed.npz'), device=DEV)
+        res = {}
+        for fused_on in (False, True):
+            model = B.Model(data).to(DEV)
+            sd = {k[4:]: torch.from_numpy(np.asarray(z[k])) for k in z.files if k.startswith('sd0/')}
+            model.load_state_dict(sd, strict=False)
+            model.train()
+            eng = LowerOnlyEngine(data, model, fused_lower=fused_on)
+            assert eng.lower_path == ('fused' if fused_on else 'layers')
+            rows, ids, labels = eng.stage(z['batch_gids'], z['y_true'])
+            model.zero_grad()
+            loss = eng.forward(rows, ids, labels)
+            loss.backward()
+            assert abs(float(loss.detach()) - float(z['loss'])) < 1e-5
+            assert rel(eng.last['pooled'], z['act6']) < 1e-5
+            assert rel(eng.last['scores'].view(-1), z['act7'].reshape(-1)) < 1e-5
+            res[fused_on] = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+            sdm = model.state_dict()
+            for k in z.files:
+                if k.startswith('sd1/') and 'running' in k:
+                    assert rel(sdm[k[4:]], z[k]) < 1e-5, k
+        om = O.OracleModel(O.parse_specs(open(os.path.join(golden_dir, 'bignn_ll_gnn_layers.txt')).read().split()),
+                           O.state_from_npz(z, 'sd0/'), dtype=torch.float64)
+        _, _, _, _, l64 = O.lower_only_step_forward(om, drugbank, z['batch_gids'], z['y_true'])
+        l64.backward()
+        g64 = {k: v.grad.numpy() for k, v in om.params().items()}
+        scale = {}
+        for k, g in g64.items():
+            scale[k.split('.')[1]] = max(scale.get(k.split('.')[1], 0.0), float(np.abs(g).max()))
+        for fused_on in (False, True):
+            for k, g in g64.items():
+                s = scale[k.split('.')[1]]
+                ours = float(np.abs(res[fused_on][k].double().cpu().numpy() - g).max()) / s
+                ref = float(np.abs(z['grad/' + k].astype(np.float64) - g).max()) / s
+                assert ours <= 6.0 * ref + 2e-5, (fused_on, k, ours, ref)
+        # a step over ~2 500 pairs through the public API (positives by the DataLoader mechanism, vectorised negatives)
+        torch.manual_seed(0)
+        model = B.Model(data).to(DEV)
+        model.train()
+        eng = LowerOnlyEngine(data, model)
+        sampler = B.RandomSampler(data, 1280)
+        ls = [float(eng.train_step(sampler, fast_negatives=True, rng=np.random.default_rng(i))) for i in range(12)]
+        assert eng.last_pairs == 2560 and all(np.isfinite(ls)) and np.mean(ls[-3:]) < np.mean(ls[:3])
+    finally:
+        B.set_flags(B.make_flags(device=DEV))

@@ -406,3 +406,50 @@ def test_upper_level_only_model_host_path_matches_reference_golden(cpu_world, go
                 assert err < 5e-5, (k, err)
     finally:
         B.set_flags(B.make_flags(device='cpu'))
+
+
+def test_lower_only_engine_matches_reference_golden_and_fast_negatives(cpu_world, golden_dir):
+    """engine_lower.LowerOnlyEngine (BASELINE config 3's model as one batched step) on the reference's recorded LL-GNN
+    step: same unique-graph order, loss and gradients as the layer-by-layer path; plus the vectorised negative sampler's
+    rejection rules (not the reference's sample stream -- see engine_lower.fast_negative_pairs)."""
+    from bignn_b200.engine_lower import LowerOnlyEngine, fast_negative_pairs
+    try:
+        z = np.load(os.path.join(golden_dir, 'bignn_ll_gnn_step.npz'))
+        B.set_flags(B.make_flags(model='lower_level_gnn', device='cpu'))
+        data = cpu_world
+        model = B.Model(data)
+        load_state(model, z)
+        model.train()
+        eng = LowerOnlyEngine(data, model, fused_lower=False)
+        rows, ids, labels = eng.stage(z['batch_gids'], z['y_true'])
+        assert np.array_equal(data.packed.gids[rows], z['merge_gids'])         # first-appearance order (batch.py:131-136)
+        model.zero_grad()
+        loss = eng.forward(rows, ids, labels)
+        assert abs(float(loss.detach()) - float(z['loss'])) < 1e-5
+        assert rel(eng.last['pooled'].detach().numpy(), z['act6']) < 1e-5
+        loss.backward()
+        scale = {}
+        for k in z.files:
+            if k.startswith('grad/'):
+                scale[k.split('.')[1]] = max(scale.get(k.split('.')[1], 0.0), float(np.abs(z[k]).max()))
+        for k, p in model.named_parameters():
+            if k.startswith('layers.'):
+                err = float(np.abs(p.grad.numpy().astype(np.float64) - z['grad/' + k]).max()) / scale[k.split('.')[1]]
+                assert err < 1e-3, (k, err)
+        # vectorised negatives: right count, drawn among the batch's drugs, no self pair, no duplicate in either
+        # orientation, no known interaction in either orientation
+        pos = data.train_pairs[:3000]
+        neg = fast_negative_pairs(data, pos, np.random.default_rng(0))
+        assert neg.shape == (3000, 2)
+        drugs = set(np.unique(pos).tolist())
+        assert set(np.unique(neg).tolist()) <= drugs and np.all(neg[:, 0] != neg[:, 1])
+        key = np.minimum(neg[:, 0], neg[:, 1]) * 10 ** 9 + np.maximum(neg[:, 0], neg[:, 1])
+        assert np.unique(key).shape[0] == 3000
+        edges = data.edge_set()
+        for a, b in neg.tolist():
+            ra, rb = data.gs_map[a], data.gs_map[b]
+            assert (ra, rb) not in edges and (rb, ra) not in edges
+        assert np.array_equal(data.labels_of_pairs(pos), np.ones(3000, np.int64))
+        assert np.array_equal(data.labels_of_pairs(neg), np.asarray([data.look_up_label(a, b) or 0 for a, b in neg.tolist()]))
+    finally:
+        B.set_flags(B.make_flags(device='cpu'))
