@@ -20,7 +20,7 @@ LIB_DIR = os.path.join(HERE, '_C')
 LIB_PATH = os.path.join(LIB_DIR, 'libbignn_b200.so')
 HEADER = os.path.join(ROOT, 'include', 'bignn_b200.h')
 
-ABI_VERSION = 3          # include/bignn_b200.h BIGNN_ABI_VERSION (3: fused GIN layer, readout with folded BatchNorm)
+ABI_VERSION = 4          # include/bignn_b200.h BIGNN_ABI_VERSION (3: fused GIN layer, folded readout; 4: fused pair decoder)
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC']
@@ -61,7 +61,13 @@ SIGNATURES = {
     'bignn_bn_rows_bwd_apply': ('i', 'plplpl' 'iii' 'ppp' 'pl' 'i' 's'),
     'bignn_readout_fwd': ('i', 'pl' 'pii' 'i' 'p' 'pli' 's'),
     'bignn_readout_bwd': ('i', 'pli' 'p' 'pii' 'i' 'pl' 'i' 's'),
+    'bignn_readout_gated_fwd': ('i', 'plpl' 'pii' 'pl' 's'),
+    'bignn_readout_gated_bwd': ('i', 'plpl' 'pl' 'pii' 'plpl' 's'),
     'bignn_readout_fold_fwd': ('i', 'pl' 'pii' 'i' 'p' 'pppp' 'pli' 's'),
+    'bignn_pair_decoder_supported': ('i', 'iiiii'),
+    'bignn_pair_decoder_workspace_bytes': ('l', 'iiiiii'),
+    'bignn_pair_decoder_fwd': ('i', 'pl' 'piii' 'ppi' 'ppi' 'ppi' 'i' 'pp' 'pl' 'ppp' 'p' 'pl' 's'),
+    'bignn_pair_decoder_bwd': ('i', 'pl' 'piii' 'pi' 'pi' 'pi' 'i' 'pp' 'pl' 'ppp' 'p' 'pl' 'pppppp' 'pl' 's'),
     'bignn_gin_layer_supported': ('i', 'ii'),
     'bignn_gin_layer_stat_records': ('l', 'ii'),
     'bignn_gin_layer_fwd': ('i', 'iii' 'ppip' 'pl' 'ppp' 'pip' 'f' 'pppp' 'ii' 'pl' 'pl' 'pl' 'p' 's'),
@@ -197,7 +203,8 @@ def call(name, *args):
     if codes.endswith('s'):
         cargs.append(torch.cuda.current_stream().cuda_stream)
     out = getattr(lib, name)(*cargs)
-    if res == 'i' and name not in ('bignn_abi_version', 'bignn_gemm_tc_supported', 'bignn_dw_tc_supported', 'bignn_gin_layer_supported') and out != 0:
+    if res == 'i' and name not in ('bignn_abi_version', 'bignn_gemm_tc_supported', 'bignn_dw_tc_supported', 'bignn_gin_layer_supported',
+                                  'bignn_pair_decoder_supported') and out != 0:
         raise RuntimeError('{} failed with status {}: {}'.format(name, out, error_string(out)))
     return out
 

@@ -101,9 +101,95 @@ k_readout_bwd(const float* __restrict__ dOut, int64_t ldo, const int32_t* __rest
   }
 }
 
+// ---- gated ("attention") readout: out[g] = sum over the graph's atoms of sigmoid(gate) * weight
+// (model/layers_aggregation.py:90-94: `sigmoid(gate_func(x)) * weight_func(x)` -> scatter_add), the product is not
+// materialised; rows in ascending order, the product rounded to fp32 before it is added (the unfused arithmetic)
+template <int L>
+__global__ void __launch_bounds__(256)
+k_readout_gated_fwd(const float* __restrict__ Gt, int64_t ldg, const float* __restrict__ W, int64_t ldw,
+                    const int32_t* __restrict__ seg_ptr, int G, int D4, float* __restrict__ out, int64_t ldo) {
+  const int gpb = blockDim.x / L;
+  const int sub = threadIdx.x / L, lane = threadIdx.x % L;
+  for (int g = blockIdx.x * gpb + sub; g < G; g += gridDim.x * gpb) {
+    const int r0 = __ldg(seg_ptr + g), r1 = __ldg(seg_ptr + g + 1);
+    for (int q = lane; q < D4; q += L) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r = r0; r < r1; ++r) {
+        const float4 a = ldg4(Gt + (int64_t)r * ldg + 4 * q), w = ldg4(W + (int64_t)r * ldw + 4 * q);
+        acc.x += __fmul_rn(1.0f / (1.0f + expf(-a.x)), w.x); acc.y += __fmul_rn(1.0f / (1.0f + expf(-a.y)), w.y);
+        acc.z += __fmul_rn(1.0f / (1.0f + expf(-a.z)), w.z); acc.w += __fmul_rn(1.0f / (1.0f + expf(-a.w)), w.w);
+      }
+      st4(out + (int64_t)g * ldo + 4 * q, acc);
+    }
+  }
+}
+
+// dW[r] = dOut[g] * s, dGate[r] = dOut[g] * w * s (1 - s),  s = sigmoid(gate[r]),  for every atom r of graph g
+template <int L>
+__global__ void __launch_bounds__(256)
+k_readout_gated_bwd(const float* __restrict__ Gt, int64_t ldg, const float* __restrict__ W, int64_t ldw,
+                    const float* __restrict__ dOut, int64_t ldo, const int32_t* __restrict__ seg_ptr, int G, int D4,
+                    float* __restrict__ dG, int64_t lddg, float* __restrict__ dW, int64_t lddw) {
+  const int gpb = blockDim.x / L;
+  const int sub = threadIdx.x / L, lane = threadIdx.x % L;
+  for (int g = blockIdx.x * gpb + sub; g < G; g += gridDim.x * gpb) {
+    const int r0 = __ldg(seg_ptr + g), r1 = __ldg(seg_ptr + g + 1);
+    for (int q = lane; q < D4; q += L) {
+      const float4 d = ldg4(dOut + (int64_t)g * ldo + 4 * q);
+      for (int r = r0; r < r1; ++r) {
+        const float4 a = ldg4(Gt + (int64_t)r * ldg + 4 * q), w = ldg4(W + (int64_t)r * ldw + 4 * q);
+        float4 s, ow, og;
+        s.x = 1.0f / (1.0f + expf(-a.x)); s.y = 1.0f / (1.0f + expf(-a.y));
+        s.z = 1.0f / (1.0f + expf(-a.z)); s.w = 1.0f / (1.0f + expf(-a.w));
+        ow.x = d.x * s.x; ow.y = d.y * s.y; ow.z = d.z * s.z; ow.w = d.w * s.w;
+        og.x = d.x * w.x * ((1.0f - s.x) * s.x); og.y = d.y * w.y * ((1.0f - s.y) * s.y);
+        og.z = d.z * w.z * ((1.0f - s.z) * s.z); og.w = d.w * w.w * ((1.0f - s.w) * s.w);
+        st4(dW + (int64_t)r * lddw + 4 * q, ow);
+        st4(dG + (int64_t)r * lddg + 4 * q, og);
+      }
+    }
+  }
+}
+
 }  // namespace bignn
 
 using namespace bignn;
+
+extern "C" int bignn_readout_gated_fwd(const float* gate, int64_t ldg, const float* weight, int64_t ldw,
+                                       const int32_t* seg_ptr, int32_t G, int32_t D, float* out, int64_t ldo,
+                                       void* stream) {
+  if (G < 0 || D < 0) return BIGNN_EINVAL;
+  if (G == 0 || D == 0) return 0;
+  if (!gate || !weight || !seg_ptr || !out || ldg < D || ldw < D || ldo < D) return BIGNN_EINVAL;
+  if ((D & 3) || (ldg & 3) || (ldw & 3) || (ldo & 3) || !aligned16(gate) || !aligned16(weight) || !aligned16(out))
+    return BIGNN_EALIGN;
+  int grid = ceil_div(G, 16);
+  const int cap = sm_count() * 8;
+  if (grid > cap) grid = cap;
+  k_readout_gated_fwd<16><<<grid, 256, 0, (cudaStream_t)stream>>>(gate, ldg, weight, ldw, seg_ptr, G, D / 4, out, ldo);
+  BIGNN_LAUNCH_COUNT(1);
+  return last_launch_status();
+}
+
+extern "C" int bignn_readout_gated_bwd(const float* gate, int64_t ldg, const float* weight, int64_t ldw,
+                                       const float* dOut, int64_t ldo, const int32_t* seg_ptr, int32_t G, int32_t D,
+                                       float* dGate, int64_t lddg, float* dWeight, int64_t lddw, void* stream) {
+  if (G < 0 || D < 0) return BIGNN_EINVAL;
+  if (G == 0 || D == 0) return 0;
+  if (!gate || !weight || !dOut || !seg_ptr || !dGate || !dWeight || ldg < D || ldw < D || ldo < D || lddg < D ||
+      lddw < D)
+    return BIGNN_EINVAL;
+  if ((D & 3) || (ldg & 3) || (ldw & 3) || (ldo & 3) || (lddg & 3) || (lddw & 3) || !aligned16(gate) ||
+      !aligned16(weight) || !aligned16(dOut) || !aligned16(dGate) || !aligned16(dWeight))
+    return BIGNN_EALIGN;
+  int grid = ceil_div(G, 16);
+  const int cap = sm_count() * 8;
+  if (grid > cap) grid = cap;
+  k_readout_gated_bwd<16><<<grid, 256, 0, (cudaStream_t)stream>>>(gate, ldg, weight, ldw, dOut, ldo, seg_ptr, G, D / 4,
+                                                                 dGate, lddg, dWeight, lddw);
+  BIGNN_LAUNCH_COUNT(1);
+  return last_launch_status();
+}
 
 extern "C" int bignn_readout_fold_fwd(const float* X, int64_t ldx, const int32_t* seg_ptr, int32_t G, int32_t D,
                                       int32_t style, const int32_t* dst_row, const float* fold_mean,

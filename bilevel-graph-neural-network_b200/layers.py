@@ -159,6 +159,10 @@ class Loss(nn.Module):
             raise ValueError('Unknown loss layer type {}'.format(type))
 
     def forward(self, ins, batch_data, _):
+        fused = getattr(batch_data, 'fused_loss', None)
+        if fused is not None and fused[0] is ins:          # computed by the fused pair decoder on these very scores
+            batch_data.fused_loss = None
+            return fused[1]
         if self.type == 'CE':
             return ops.cross_entropy(ins, batch_data.y_true_device(as_int=True))
         y_true = batch_data.y_true_device()

@@ -64,8 +64,7 @@ class GMNAggregatorPairs(nn.Module):
         atoms = (graph.chunk_row_ptr, graph.S)
         w = self.weight_func(x, seg=atoms)
         gate = self.gate_func(x, seg=atoms)
-        prod = ops.gate_mul(gate, w)
-        emb = ops.readout([prod], graph.seg_ptr, graph.G, 'sum')
+        emb = ops.gated_readout(gate, w, graph.seg_ptr, graph.G)       # sigmoid(gate) * w summed per graph, one launch
         return self.mlp_graph(emb, seg=(graph.chunk_graph_ptr, graph.S))
 
 

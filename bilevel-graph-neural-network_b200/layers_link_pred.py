@@ -43,6 +43,41 @@ class LinkPred(nn.Module):
 
     _calc_mlp_dims = staticmethod(hidden_widths)
 
+    def _fused_head(self, ins, model, batch_data):
+        """(head code, target tensor or None) when the fused decoder kernel covers this scorer + the loss layer that
+        follows it; None -> the layer-by-layer path (BIGNN_NO_FUSED_DECODER=1 forces it)."""
+        import os
+        if self.type != 'mlp_concat' or os.environ.get('BIGNN_NO_FUSED_DECODER') or not ins.is_cuda:
+            return None
+        mlp = self.mlp_concat
+        if mlp.bn or mlp.activation.code != ops.ACT_CODES['relu']:
+            return None
+        if not ops.pair_decoder_supported(ins.shape[1], [l.out_features for l in mlp.layers]):
+            return None
+        if any(l.bias is None for l in mlp.layers):
+            return None
+        loss_layer = model.layers[-1] if getattr(model, 'layers', None) is not None else None
+        kind = getattr(loss_layer, 'type', None)
+        if self.multi_label_pred:
+            if kind != 'CE':
+                return None
+            head = 2
+        else:
+            if kind not in ('BCE', 'BCEWithLogits'):
+                return None
+            # the scorer itself applies the sigmoid (layers_link_pred.py:65): the Loss layer sees probabilities for
+            # 'BCE'; with 'BCEWithLogits' the reference feeds those probabilities to the logits loss -- not fusable
+            if kind != 'BCE':
+                return None
+            head = 0
+        if not model.training or not hasattr(batch_data, 'y_true_device'):
+            return head, None
+        try:
+            target = batch_data.y_true_device(as_int=(head == 2))
+        except Exception:
+            return head, None
+        return head, target
+
     def forward(self, ins, batch_data, model):
         graph = getattr(batch_data, 'merge_higher_level', {}).get('merge')
         if getattr(graph, 'partitioned', False):
@@ -51,6 +86,17 @@ class LinkPred(nn.Module):
             ins = bdist.gather_rows_for_replicated_consumer(ins, graph)
         rows, entry_csr = batch_data.pair_rows_device(ins.shape[0], higher=get_flags().higher_level_layers,
                                                       unique=self.batch_unique_graphs)
+        fused = self._fused_head(ins, model, batch_data)
+        if fused is not None:
+            # gather + normalise + concat + MLP + head + LOSS in one launch (forward) / one launch (backward); the
+            # Loss layer that follows picks the loss up from the batch
+            head, target = fused
+            lins = self.mlp_concat.layers
+            params = [t for lin in lins for t in (lin.weight, lin.bias)]
+            scores, loss = ops.pair_decoder(ins, rows, entry_csr, head, target, params)
+            batch_data.fused_loss = (scores, loss) if target is not None else None
+            batch_data.assign_link_preds(scores)
+            return scores
         z = ops.pair_gather_norm(ins, rows, entry_csr)                 # [P, 2D] = [norm(h_a) || norm(h_b)]
         sigmoid = ops.ACT_CODES['sigmoid']
         if self.type == 'dot_product':

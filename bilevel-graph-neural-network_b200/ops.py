@@ -137,7 +137,8 @@ def gemm(a, b, ta=False, tb=False, bias=None, act=0, out=None):
 
 import os as _os
 
-TC_MIN_ROWS = 512      # below this a 128-row tensor-core tile grid cannot fill the SMs; SIMT path
+TC_MIN_ROWS = 8192     # below this the dense transforms run as fp32 FMA (SIMT): a 128-row tensor-core tile grid cannot fill the SMs, and the
+                       # small upper-level graphs of the reference datasets (1 309 / 3 242 drugs) then keep exact fp32 products (forward gates 1e-5)
 _NO_TC = bool(_os.environ.get('BIGNN_NO_TC'))      # debugging switch: route the transforms to the SIMT kernels
 
 
@@ -389,6 +390,37 @@ class _Readout(torch.autograd.Function):
         return (None, None, None, None, None) + tuple(grads)
 
 
+class _GatedReadout(torch.autograd.Function):
+    """out[g] = sum over the atoms of graph g of sigmoid(gate) * weight (the gated / "attention" readout of
+    model/layers_aggregation.py:90-94), product and segment sum in one launch each way."""
+
+    @staticmethod
+    def forward(ctx, gate, w, seg_ptr, G):
+        gate, w = _f32c(gate), _f32c(w)
+        _lib.require_device(gate, w)
+        D = w.shape[1]
+        out = torch.empty((G, D), dtype=torch.float32, device=w.device)
+        _lib.call('bignn_readout_gated_fwd', gate, gate.stride(0), w, w.stride(0), seg_ptr, int(G), D, out, out.stride(0))
+        ctx.seg, ctx.G = seg_ptr, int(G)
+        ctx.save_for_backward(gate, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        gate, w = ctx.saved_tensors
+        dout = _f32c(dout)
+        dg, dw = torch.empty_like(gate), torch.empty_like(w)
+        _lib.call('bignn_readout_gated_bwd', gate, gate.stride(0), w, w.stride(0), dout, dout.stride(0), ctx.seg, ctx.G,
+                  w.shape[1], dg, dg.stride(0), dw, dw.stride(0))
+        return dg, dw, None, None
+
+
+def gated_readout(gate, w, seg_ptr, G):
+    if w.shape[1] % 4 != 0 or not w.is_cuda:
+        return readout([gate_mul(gate, w)], seg_ptr, G, 'sum')
+    return _GatedReadout.apply(gate, w, seg_ptr, G)
+
+
 class _PairGatherNorm(torch.autograd.Function):
     """z[p] = [normalize(h[ids[p,0]]) || normalize(h[ids[p,1]])]; the backward adds the
     per-entry gradients per drug through the entry CSR (deterministic, no atomics)."""
@@ -415,6 +447,89 @@ class _PairGatherNorm(torch.autograd.Function):
                   drows.stride(0))
         dh = spmm(ctx.entry_csr, drows, SPMM_SUM)
         return dh, None, None
+
+
+_PD_WS = {}          # device -> persistent zero-initialised workspace of the fused pair decoder (holds its counter)
+
+
+def _pair_decoder_ws(nbytes, device):
+    ws = _PD_WS.get(device)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=device)
+        _PD_WS[device] = ws
+    return ws
+
+
+def pair_decoder_supported(D, widths):
+    """widths = output widths of the scorer's Linear layers (2 or 3 of them)."""
+    if len(widths) not in (2, 3):
+        return False
+    w = list(widths) + [0] * (3 - len(widths))
+    return bool(_lib.call('bignn_pair_decoder_supported', int(D), len(widths), int(w[0]), int(w[1]), int(w[2])))
+
+
+class _PairDecoder(torch.autograd.Function):
+    """(scores, loss) = fused gather + normalise + concat + MLP + head + loss; see bignn_pair_decoder_fwd.
+    args: h, ids, entry_csr, head, y (float) or labels (int32) or None, then W0, b0, W1, b1[, W2, b2]."""
+
+    @staticmethod
+    def forward(ctx, h, ids, entry_csr, head, target, *params):
+        h = _f32c(h)
+        _lib.require_device(h, ids)
+        nl = len(params) // 2
+        Ws = [p.contiguous() for p in params[0::2]]
+        bs = list(params[1::2])
+        P, D = ids.shape[0], h.shape[1]
+        n = [w.shape[0] for w in Ws] + [0] * (3 - nl)
+        n_out = Ws[-1].shape[0]
+        dev = h.device
+        scores = torch.empty((P, n_out), dtype=torch.float32, device=dev)
+        nrm = torch.empty((P, 2), dtype=torch.float32, device=dev)
+        h1 = torch.empty((P, n[0]), dtype=torch.float32, device=dev)
+        h2 = torch.empty((P, n[1]), dtype=torch.float32, device=dev) if nl == 3 else None
+        loss = torch.empty((), dtype=torch.float32, device=dev) if target is not None else None
+        wsb = _lib.call('bignn_pair_decoder_workspace_bytes', P, D, nl, n[0], n[1], n[2])
+        ws = _pair_decoder_ws(wsb, dev)
+        y = target if (target is not None and head != 2) else None
+        labels = target if (target is not None and head == 2) else None
+        _lib.call('bignn_pair_decoder_fwd', h, h.stride(0), ids, P, D, nl, Ws[0], bs[0], n[0], Ws[1], bs[1], n[1],
+                  Ws[2] if nl == 3 else None, bs[2] if nl == 3 else None, n[2], int(head), y, labels, scores,
+                  scores.stride(0), nrm, h1, h2, loss, ws, int(ws.numel()))
+        ctx.entry_csr, ctx.head, ctx.nl, ctx.n, ctx.has_b = entry_csr, int(head), nl, n, [b is not None for b in bs]
+        ctx.save_for_backward(h, ids, target, scores, nrm, h1, h2, *Ws)
+        ctx.mark_non_differentiable(scores)
+        if loss is None:
+            return scores, scores.new_zeros(())
+        return scores, loss
+
+    @staticmethod
+    def backward(ctx, _dscores, dloss):
+        h, ids, target, scores, nrm, h1, h2, *Ws = ctx.saved_tensors
+        nl, n, head = ctx.nl, ctx.n, ctx.head
+        P, D = ids.shape[0], h.shape[1]
+        dev = h.device
+        dloss = _f32c(dloss)
+        drows = torch.empty((2 * P, D), dtype=torch.float32, device=dev)
+        dWs = [torch.empty_like(w) for w in Ws]
+        dbs = [torch.empty(w.shape[0], dtype=torch.float32, device=dev) for w in Ws]
+        wsb = _lib.call('bignn_pair_decoder_workspace_bytes', P, D, nl, n[0], n[1], n[2])
+        ws = _pair_decoder_ws(wsb, dev)
+        y = target if head != 2 else None
+        labels = target if head == 2 else None
+        _lib.call('bignn_pair_decoder_bwd', h, h.stride(0), ids, P, D, nl, Ws[0], n[0], Ws[1], n[1],
+                  Ws[2] if nl == 3 else None, n[2], head, y, labels, scores, scores.stride(0), nrm, h1, h2, dloss, drows,
+                  drows.stride(0), dWs[0], dbs[0], dWs[1], dbs[1], dWs[2] if nl == 3 else None,
+                  dbs[2] if nl == 3 else None, ws, int(ws.numel()))
+        dh = spmm(ctx.entry_csr, drows, SPMM_SUM)
+        grads = []
+        for l in range(nl):
+            grads += [dWs[l], dbs[l] if ctx.has_b[l] else None]
+        return (dh, None, None, None, None) + tuple(grads)
+
+
+def pair_decoder(h, ids, entry_csr, head, target, params):
+    """Returns (scores [P, n_out], loss scalar).  head: 0 sigmoid+BCE, 1 logits+BCEWithLogits, 2 logits+CE."""
+    return _PairDecoder.apply(h, ids, entry_csr, int(head), target, *params)
 
 
 class _BCE(torch.autograd.Function):

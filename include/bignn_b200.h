@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define BIGNN_ABI_VERSION 3
+#define BIGNN_ABI_VERSION 4
 
 /* argument errors */
 #define BIGNN_EINVAL   (-1)   /* bad size / null pointer / unsupported flag */
@@ -247,6 +247,36 @@ int bignn_bn_rows_bwd_apply(const float* X, int64_t ldx, const float* dY, int64_
                             int32_t input_act, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Fused gather-and-score edge decoder + loss head (SURVEY 8b `pair_decoder_fwd/bwd`).
+ * Replaces model/layers_link_pred.py:43-65 (F.normalize, gather of the two embedding rows of every pair, concat,
+ * the mlp_concat MLP, sigmoid) and model/layers.py:79-89 (BCELoss / BCEWithLogitsLoss / CrossEntropyLoss, mean):
+ * forward ONE launch, backward ONE launch (+ bignn_spmm_f32 in SUM mode over the entry CSR, the transpose of the
+ * gather, to add the per-entry row gradients per drug).
+ * ids [P,2] rows of H [*, ldh] (D columns).  The scorer has n_layers = 2 or 3 Linear layers (nn.Linear layout
+ * W_l [n_l, n_{l-1}], n_0 = 2D), ReLU after all but the last.  head: 0 = sigmoid + BCE (y float [P]),
+ * 1 = logits + BCEWithLogits (y), 2 = logits + cross entropy (labels int32 [P]).  Limits: 2D <= 256, n1 <= 16, later
+ * widths <= 32 (bignn_pair_decoder_supported).  scores [P, lds] receives the LinkPred output (probabilities for head 0,
+ * logits otherwise); nrm [P,2], h1 [P,n1], h2 [P,n2] are kept for the backward; loss (optional) the mean loss.
+ * workspace: bignn_pair_decoder_workspace_bytes, ZERO-INITIALISED ONCE by the caller and then reused across calls (it
+ * holds the completion counter of the deterministic last-CTA reduction, which the kernels reset themselves).
+ * ------------------------------------------------------------------------- */
+int bignn_pair_decoder_supported(int32_t D, int32_t n_layers, int32_t n1, int32_t n2, int32_t n3);
+int64_t bignn_pair_decoder_workspace_bytes(int32_t P, int32_t D, int32_t n_layers, int32_t n1, int32_t n2, int32_t n3);
+int bignn_pair_decoder_fwd(const float* H, int64_t ldh, const int32_t* ids, int32_t P, int32_t D, int32_t n_layers,
+                           const float* W0, const float* b0, int32_t n1, const float* W1, const float* b1, int32_t n2,
+                           const float* W2, const float* b2, int32_t n3, int32_t head,
+                           const float* y, const int32_t* labels, float* scores, int64_t lds,
+                           float* nrm, float* h1, float* h2, float* loss,
+                           void* workspace, int64_t workspace_bytes, void* stream);
+int bignn_pair_decoder_bwd(const float* H, int64_t ldh, const int32_t* ids, int32_t P, int32_t D, int32_t n_layers,
+                           const float* W0, int32_t n1, const float* W1, int32_t n2, const float* W2, int32_t n3,
+                           int32_t head, const float* y, const int32_t* labels,
+                           const float* scores, int64_t lds, const float* nrm, const float* h1, const float* h2,
+                           const float* dloss, float* drows, int64_t lddr,
+                           float* dW0, float* db0, float* dW1, float* db1, float* dW2, float* db2,
+                           void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------
  * One lower-level GIN layer as ONE launch (SURVEY 8b `gin_layer_fwd`).
  * Replaces model/layers.py:42-57 with type='gin': PyG GINConv (index_select + scatter_add, Linear, act,
  * Linear) -> act -> the statistics pass of BatchNorm1d; the BatchNorm *apply* of this layer is not a pass at
@@ -297,6 +327,13 @@ int bignn_readout_fold_fwd(const float* X, int64_t ldx, const int32_t* seg_ptr, 
                            int32_t style, const int32_t* dst_row, const float* fold_mean, const float* fold_a,
                            const float* fold_beta, const int32_t* graph_chunk, float* out, int64_t ldo,
                            int32_t col_off, void* stream);
+/* gated ("attention") readout, model/layers_aggregation.py:90-94 (GMNAggregatorPairs): out[g] = sum over the atoms of
+ * graph g of sigmoid(gate) * weight -- product and sum in one launch; backward (dGate, dWeight) in one launch.  D % 4 == 0. */
+int bignn_readout_gated_fwd(const float* gate, int64_t ldg, const float* weight, int64_t ldw,
+                            const int32_t* seg_ptr, int32_t G, int32_t D, float* out, int64_t ldo, void* stream);
+int bignn_readout_gated_bwd(const float* gate, int64_t ldg, const float* weight, int64_t ldw,
+                            const float* dOut, int64_t ldo, const int32_t* seg_ptr, int32_t G, int32_t D,
+                            float* dGate, int64_t lddg, float* dWeight, int64_t lddw, void* stream);
 int bignn_readout_bwd(const float* dOut, int64_t ldo, int32_t col_off, const int32_t* dst_row,
                       const int32_t* seg_ptr, int32_t G, int32_t D, int32_t style,
                       float* dX, int64_t lddx, int32_t accumulate, void* stream);

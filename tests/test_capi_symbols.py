@@ -24,7 +24,7 @@ def test_library_builds_loads_and_exports_header():
         assert hasattr(lib, n), n
     assert set(names) == set(B._lib.SIGNATURES.keys())
     lib.bignn_abi_version.restype = ctypes.c_int
-    assert lib.bignn_abi_version() == B._lib.ABI_VERSION == 3
+    assert lib.bignn_abi_version() == B._lib.ABI_VERSION == 4
     lib.bignn_error_string.restype = ctypes.c_char_p
     assert b'invalid' in lib.bignn_error_string(-1)
 
