@@ -206,8 +206,8 @@ k_dw_tc(int M, int Np, int Nq, const float* __restrict__ P, int64_t ldp, const f
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Ring variant (BIGNN_DW_BM=32 selects it; NOT the default -- written after the round's GPU budget was spent, to be
-// measured first): ncu on k_dw_tc<64,3> shows no dominant stall, 23 % tensor-pipe activity and one 32 KB tile in flight
+// Ring variant (the default since round 2; BIGNN_DW_BM=64 / 128 select the kernels above): ncu on k_dw_tc<64,3> shows
+// no dominant stall, 23 % tensor-pipe activity and one 32 KB tile in flight
 // per CTA, i.e. the kernel waits for data.  Here the operand tiles are 32-row stages in an NST-deep cp.async ring
 // (NST-2 tiles in flight beyond the one being split) and the lo operand is double buffered, so the hi/lo split of
 // tile i+1 overlaps the MMAs of tile i (one mbarrier per lo buffer; a stage is refilled only after the MMAs that
@@ -425,12 +425,13 @@ k_dw_cs_reduce(const double* __restrict__ ws, int parts, int cols, float* __rest
   }
 }
 
-static int dw_bm() {   // rows per tile: 64 (two CTAs per SM, default), 128 (BIGNN_DW_BM=128) or the 32-row ring (=32)
+static int dw_bm() {   // rows per tile: the 32-row 4-stage ring (default since round 2: 2.55 vs 2.37 TB/s at 2 M rows,
+                       // profiles/r2_summary.md), 64 (two CTAs per SM, BIGNN_DW_BM=64) or 128 (BIGNN_DW_BM=128)
   static int bm = 0;
   if (bm == 0) {
     const char* e = getenv("BIGNN_DW_BM");
-    const int v = e ? atoi(e) : 64;
-    bm = (v == 128 || v == 32) ? v : 64;
+    const int v = e ? atoi(e) : 32;
+    bm = (v == 128 || v == 64) ? v : 32;
   }
   return bm;
 }

@@ -59,6 +59,30 @@ def run_step(data, model, z):
     return bd, loss
 
 
+def report_gradient_errors(tag, model, g64, z, scale):
+    """per-parameter gradient errors on the layer's gradient scale: this path vs the reference's fp32 values, this path
+    vs the fp64 oracle, the reference's fp32 values vs the fp64 oracle.  Printed (pytest -s) and written to
+    gpurun_out/grad_errors_<tag>.txt so that the distance from north_star's 1e-5 is on record."""
+    rows = []
+    for k, p in model.named_parameters():
+        if not k.startswith('layers.') or p.grad is None:
+            continue
+        s = scale[k.split('.')[1]]
+        g = p.grad.double().cpu().numpy()
+        rows.append((k, float(np.abs(g - z['grad/' + k].astype(np.float64)).max()) / s,
+                     float(np.abs(g - g64[k]).max()) / s,
+                     float(np.abs(z['grad/' + k].astype(np.float64) - g64[k]).max()) / s))
+    lines = ['%-44s %12s %12s %12s' % ('parameter (errors / layer gradient scale)', 'vs ref fp32', 'vs fp64', 'ref vs fp64')]
+    lines += ['%-44s %12.3e %12.3e %12.3e' % r for r in rows]
+    text = '\n'.join(lines)
+    print(text)
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
+    if os.path.isdir(out):
+        with open(os.path.join(out, 'grad_errors_%s.txt' % tag), 'w') as f:
+            f.write(text + '\n')
+    return rows
+
+
 def test_step_forward_and_gradients(world, step_golden, drugbank, gin_gcn_specs):
     z = step_golden
     data, model = world
@@ -82,6 +106,7 @@ def test_step_forward_and_gradients(world, step_golden, drugbank, gin_gcn_specs)
     for k, g in g64.items():
         lid = k.split('.')[1]
         scale[lid] = max(scale.get(lid, 0.0), float(np.abs(g).max()))
+    report_gradient_errors('gin_gcn', model, g64, z, scale)
     worst = 0.0
     for k, p in model.named_parameters():
         if not k.startswith('layers.'):
@@ -138,9 +163,12 @@ def test_gin_gat_step_vs_golden(golden_dir, drugbank):
     assert not unexpected
     bd, loss = run_step(data, model, z)
     assert rel(data.interaction_combo_nxgraph.init_x, z['init_x']) < 1e-5
-    for l in range(3):
-        # 2e-5: three GAT layers on top of 3xTF32 transforms (1.06e-5 measured; the GCN stack meets 1e-5)
-        assert rel(model.acts[l + 2], z['upper/act%d' % (l + 2)]) < 2e-5
+    errs = [rel(model.acts[l + 2], z['upper/act%d' % (l + 2)]) for l in range(3)]
+    print('GIN+GAT golden: upper activations vs the reference', ['%.2e' % e for e in errs])
+    for e in errs:
+        # round 1 needed 2e-5 here (1.06e-5 measured with the 1 309-row upper transforms as 3xTF32); they now run
+        # as fp32 FMA (ops.TC_MIN_ROWS) and the stack has to meet north_star's 1e-5
+        assert e < 1e-5
     assert abs(float(loss) - float(z['loss'])) < 1e-5
     loss.backward()
     specs = O.parse_specs(lines)
@@ -151,6 +179,7 @@ def test_gin_gat_step_vs_golden(golden_dir, drugbank):
     scale = {}
     for k, g in g64.items():
         scale[k.split('.')[1]] = max(scale.get(k.split('.')[1], 0.0), float(np.abs(g).max()))
+    report_gradient_errors('gin_gat', model, g64, z, scale)
     for k, p in model.named_parameters():
         if k.startswith('layers.'):
             s = scale[k.split('.')[1]]
