@@ -192,8 +192,8 @@ def entry_csr(ids_host, n_rows, device):
     flat = np.asarray(ids_host, np.int64).reshape(-1)
     order = np.argsort(flat, kind='stable')
     ptr = np.zeros(n_rows + 1, np.int64)
-    np.add.at(ptr, flat + 1, 1)
-    return CSR(_i32(np.cumsum(ptr), device), _i32(order, device), n_rows)
+    np.cumsum(np.bincount(flat, minlength=n_rows), out=ptr[1:])
+    return CSR(_i32(ptr, device), _i32(order, device), n_rows)
 
 
 class RowPartition(object):

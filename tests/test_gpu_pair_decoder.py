@@ -75,7 +75,7 @@ def test_fused_decoder_vs_fp64_torch(P, N, D, widths, head):
         assert abs(float(loss) - float(l64)) < 2e-6 * max(1.0, abs(float(l64)))
         assert rel(hd.grad, h64.grad) < 5e-6
         for a, b in zip(Wd + bd, W64 + b64):
-            assert rel(a.grad, b.grad) < 5e-6
+            assert rel(a.grad, b.grad) < 1e-5          # (fp32 sums over up to 5 000 pairs, per warp then in warp order)
     # scores only (evaluation: no targets)
     s2, _ = ops.pair_decoder(hd.detach(), idd, csr, head, None, [t.detach() for wb in zip(Wd, bd) for t in wb])
     assert torch.equal(s2, scores)

@@ -36,13 +36,14 @@ for D, act in [(49, 'tanh'), (64, 'relu'), (64, 'identity'), (320, 'sigmoid')]:
     want2 = O._act(act, O.gcn_conv(h, ei, {'l.conv.weight': torch.eye(D), 'l.conv.bias': bias}, 'l'))
     if not torch.equal(want, want2):
         print('ORACLE not reproducible for', D, act, float((want - want2).abs().max()))
-    first = None
+    first = {}                      # per kernel variant (row-sequential / work-item plan): each is deterministic in itself
     worst = 0.0
     for it in range(R):
         if it % 8 == 0:             # a fresh CSR (and a fresh, poisoned deg^-1/2 buffer) every few iterations
             rp = torch.as_tensor(ptr.astype(np.int32)).to(DEV)
             ci = torch.as_tensor(ds.ddi_col.astype(np.int32)).to(DEV)
-            csr = ops.CSR(rp, ci, n, row_ptr_host=ptr if it % 16 == 0 else None)
+            planned = it % 16 == 0
+            csr = ops.CSR(rp, ci, n, row_ptr_host=ptr if planned else None)
             d = torch.full((n,), float('nan'), device=DEV)
             _lib.call('bignn_gcn_dinv', csr.row_ptr, csr.col_idx, n, d)
             csr._dinv = d
@@ -50,15 +51,14 @@ for D, act in [(49, 'tanh'), (64, 'relu'), (64, 'identity'), (320, 'sigmoid')]:
         out = torch.full((n, D), float('nan'), device=DEV)
         ops.spmm(csr, hd, ops.SPMM_GCN, 0.0, csr.dinv(), bd, ops.act_code(act), out=out)
         got = out.cpu()
-        if first is None:
-            first = got
+        first.setdefault(planned, got)
         err = float((got - want).abs().max() / want.abs().max())
         worst = max(worst, err)
-        if not torch.equal(got, first) or err >= 2e-6 or not bool(torch.isfinite(got).all()):
+        if not torch.equal(got, first[planned]) or err >= 2e-6 or not bool(torch.isfinite(got).all()):
             bad += 1
             dd = (got - want).abs()
             print('DEVIATION D={} act={} iteration {}: err {:.3g}, bit-equal to first run: {}, finite: {}, worst element {}'
-                  .format(D, act, it, err, torch.equal(got, first), bool(torch.isfinite(got).all()),
+                  .format(D, act, it, err, torch.equal(got, first[planned]), bool(torch.isfinite(got).all()),
                           np.unravel_index(int(dd.argmax()), dd.shape)), flush=True)
     print('D={} act={}: {} runs, worst error vs oracle {:.3g}'.format(D, act, R, worst), flush=True)
 print('flake hunt: {} deviating runs'.format(bad))
