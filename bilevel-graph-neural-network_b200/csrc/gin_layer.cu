@@ -39,7 +39,7 @@ constexpr int GL_SMEM = 2 * GL_SLOT + 4 * GL_W + GL_IDX_STAGES * GL_IDX_BYTES + 
 constexpr int GL_EPI_WARPS = 4;                // per epilogue phase: one warp per TMEM lane quadrant
 // TMEM: ONE fp32 accumulator of 64 columns per transform (reading TMEM costs 64 B/cycle/SM: three accumulators per
 // transform, as k_gemm_tc keeps them, were 1.6 us of TMEM reads per tile), double buffered: acc1[2], acc2[2]
-constexpr int GL_TMEM_COLS = 256;
+constexpr int GL_TMEM_COLS = 256;              // TMEM_A variant: + t_hi / t_lo [2][64] each = all 512 columns
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -148,6 +148,55 @@ struct GinLayerArgs {
   long long* trace;                                   // debugging: clock64 stamps of CTA 0's pipeline events (or null)
 };
 
+// tcgen05.mma with the A operand in TENSOR MEMORY (lane = row, one 32-bit column per K element), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 consecutive columns of this thread's TMEM lane <- 32 registers
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+// the second transform with t in tensor memory: t_hi at columns [tmem_t, +64), t_lo at [tmem_t + 64, +64)
+__device__ __forceinline__ void issue_gemm_ts(uint32_t tmem_acc, uint32_t tmem_t, const uint8_t* b_hi, const uint8_t* b_lo,
+                                              uint32_t idesc) {
+  uint32_t accumulate = 0u;
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+      const uint64_t db_hi = umma_desc_k_sw128(smem_u32(b_hi + ch * (GL_D * 128)));
+      const uint64_t db_lo = umma_desc_k_sw128(smem_u32(b_lo + ch * (GL_D * 128)));
+#pragma unroll
+      for (int k = 0; k < TC_KC / 8; ++k) {
+        const uint64_t adv = (uint64_t)((k * 32) >> 4);
+        const uint32_t col = (uint32_t)(ch * TC_KC + k * 8);
+        if (pass == 0) {
+          umma_tf32_ts(tmem_acc, tmem_t + 64u + col, db_hi + adv, idesc, accumulate);      // t_lo * W_hi
+          umma_tf32_ts(tmem_acc, tmem_t + col, db_lo + adv, idesc, 1u);                    // t_hi * W_lo
+        } else {
+          umma_tf32_ts(tmem_acc, tmem_t + col, db_hi + adv, idesc, 1u);                    // t_hi * W_hi
+        }
+        accumulate = 1u;
+      }
+    }
+  }
+}
+
 // issue the 3xTF32 MMAs of one [128 x K] x [K x 64] product (A in `slot`, B = resident weight parts) into ONE
 // accumulator.  tcgen05.mma truncates toward zero whenever it writes the fp32 accumulator (measured: -5.6e-8 relative
 // per accumulation), so the 2^-11-scaled correction products lo*hi + hi*lo of every K step go in FIRST, while the
@@ -188,7 +237,10 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_acc, const uint8_t* a_h
 // 6 M rows (profiles/r2_summary.md): the kernel is bound by shared-memory bandwidth (the 3xTF32 operands are read three
 // times by the tensor core), so the extra 230 KB of shared-memory traffic per tile of the staged variant costs more than
 // the global-memory latency it removes -- direct gathers are the default, BIGNN_GL_STAGE=1 selects the staged variant.
-template <int THREADS, bool STAGE_X>
+// TMEM_A: the hidden activations t go from E1 straight into TENSOR MEMORY (tcgen05.st) and the second transform reads
+// its A operand there (tcgen05.mma [d], [a_tmem], b_desc): per tile 64 KB of shared-memory writes and 96 KB of
+// shared-memory operand reads less (BIGNN_GL_TMEM_A=0 selects the all-shared-memory variant).
+template <int THREADS, bool STAGE_X, bool TMEM_A>
 __global__ void __launch_bounds__(THREADS, 1)
 k_gin_layer_fwd(const GinLayerArgs p, const __grid_constant__ CUtensorMap tmx) {
   constexpr int N_WARPS = THREADS / 32;
@@ -215,7 +267,7 @@ k_gin_layer_fwd(const GinLayerArgs p, const __grid_constant__ CUtensorMap tmx) {
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
-                 "r"(GL_TMEM_COLS)
+                 "r"(TMEM_A ? 512 : GL_TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -257,6 +309,7 @@ k_gin_layer_fwd(const GinLayerArgs p, const __grid_constant__ CUtensorMap tmx) {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = tmem_base_s;
   const uint32_t acc1 = tmem_d, acc2 = tmem_d + 2u * GL_D;          // acc1[b] = acc1 + 64 b, acc2[b] = acc2 + 64 b
+  const uint32_t tmem_t = tmem_d + 4u * GL_D;                       // TMEM_A: t[b] = tmem_t + 128 b (hi 64 columns, lo 64)
 
   if (warp >= FIRST_PROD) {
     // =============================================================== producers: z tiles
@@ -512,7 +565,8 @@ k_gin_layer_fwd(const GinLayerArgs p, const __grid_constant__ CUtensorMap tmx) {
           const uint8_t* a_hi = smem + b * GL_SLOT;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if (lane == 0) {
-            issue_gemm(acc2 + (uint32_t)(b * GL_D), a_hi, a_hi + 2 * TC_BM * 128, w2_hi, w2_lo, K2, idesc);
+            if (TMEM_A) issue_gemm_ts(acc2 + (uint32_t)(b * GL_D), tmem_t + (uint32_t)(b * 2 * GL_D), w2_hi, w2_lo, idesc);
+            else issue_gemm(acc2 + (uint32_t)(b * GL_D), a_hi, a_hi + 2 * TC_BM * 128, w2_hi, w2_lo, K2, idesc);
             umma_commit(&m2_done[b]);
           }
           GL_TRACE(10, i2);
@@ -541,6 +595,7 @@ k_gin_layer_fwd(const GinLayerArgs p, const __grid_constant__ CUtensorMap tmx) {
       const int rows_here = min(TC_BM, p.rows - m0);
       const uint8_t* src = a_hi + (c4 >> 3) * (TC_BM * 128);
       mbar_wait(&m1_done[b], (it >> 1) & 1);
+      if (TMEM_A && it >= 2) mbar_wait(&m2_done[b], ((it - 2) >> 1) & 1);   // t[b] of tile it-2 has been consumed
       if (warp == 0) GL_TRACE(3, it);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
@@ -556,14 +611,33 @@ k_gin_layer_fwd(const GinLayerArgs p, const __grid_constant__ CUtensorMap tmx) {
         }
         uint8_t* hi = a_hi + (cb >> 5) * (TC_BM * 128) + row_off;
         uint8_t* lo = a_lo + (cb >> 5) * (TC_BM * 128) + row_off;
+        if (TMEM_A) {
+          // t -> tensor memory (this thread's lane = its row): raw fp32 = the TF32 hi operand, then the lo part
+          uint32_t q[32];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 tv = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-          const uint32_t off = (uint32_t)((c ^ row7) << 4);
-          *reinterpret_cast<float4*>(hi + off) = tv;
-          *reinterpret_cast<uint4*>(lo + off) = lo_part(tv);
+          for (int j = 0; j < 32; ++j) q[j] = __float_as_uint(v[j]);
+          tmem_st32(tmem_t + (uint32_t)(b * 2 * GL_D) + lane_off + (uint32_t)cb, q);
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            q[j] = __float_as_uint(v[j] - __uint_as_float(__float_as_uint(v[j]) & 0xffffe000u)) & 0xffffe000u;
+          tmem_st32(tmem_t + (uint32_t)(b * 2 * GL_D) + 64u + lane_off + (uint32_t)cb, q);
+          if (p.T) {                                         // kept for the backward: staged for coalesced stores
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              *reinterpret_cast<float4*>(hi + (uint32_t)((c ^ row7) << 4)) =
+                  make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 tv = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+            const uint32_t off = (uint32_t)((c ^ row7) << 4);
+            *reinterpret_cast<float4*>(hi + off) = tv;
+            *reinterpret_cast<uint4*>(lo + off) = lo_part(tv);
+          }
         }
       }
+      if (TMEM_A) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -693,7 +767,7 @@ k_gin_layer_fwd(const GinLayerArgs p, const __grid_constant__ CUtensorMap tmx) {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(GL_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TMEM_A ? 512 : GL_TMEM_COLS) : "memory");
   }
 }
 
@@ -786,13 +860,19 @@ extern "C" int bignn_gin_layer_fwd(int32_t rows, int32_t din, int32_t dout, cons
     return BIGNN_EALIGN;
   constexpr int THREADS = 768;      // 24 warps: 4 + 4 epilogue, MMA, index prefetch, 14 producers = 56 row groups
   static bool configured = false;
-  static int dbg = 0, stage = 0;
+  static int dbg = 0, stage = 0, tmem_a = 0;
   static long long* trace_dev = nullptr;
   static const char* trace_path = nullptr;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_gin_layer_fwd<THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GL_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(k_gin_layer_fwd<THREADS, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GL_SMEM);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(k_gin_layer_fwd<THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GL_SMEM);
+      e = cudaFuncSetAttribute(k_gin_layer_fwd<THREADS, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GL_SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(k_gin_layer_fwd<THREADS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GL_SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(k_gin_layer_fwd<THREADS, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GL_SMEM);
+    const char* ta = getenv("BIGNN_GL_TMEM_A");
+    tmem_a = ta ? atoi(ta) : 1;      // default: the second transform reads t from tensor memory
     if (e != cudaSuccess) return (int)e;
     const char* sg = getenv("BIGNN_GL_STAGE");
     stage = sg ? atoi(sg) : 0;
@@ -838,10 +918,14 @@ extern "C" int bignn_gin_layer_fwd(int32_t rows, int32_t din, int32_t dout, cons
   if (trace_dev) cudaMemsetAsync(trace_dev, 0, 64 * 16 * sizeof(long long), (cudaStream_t)stream);
   int grid = sm_count();
   if (grid > a.n_tiles) grid = a.n_tiles;
-  if (stage)
-    k_gin_layer_fwd<THREADS, true><<<grid, THREADS, GL_SMEM, (cudaStream_t)stream>>>(a, tmx);
+  if (stage && tmem_a)
+    k_gin_layer_fwd<THREADS, true, true><<<grid, THREADS, GL_SMEM, (cudaStream_t)stream>>>(a, tmx);
+  else if (stage)
+    k_gin_layer_fwd<THREADS, true, false><<<grid, THREADS, GL_SMEM, (cudaStream_t)stream>>>(a, tmx);
+  else if (tmem_a)
+    k_gin_layer_fwd<THREADS, false, true><<<grid, THREADS, GL_SMEM, (cudaStream_t)stream>>>(a, tmx);
   else
-    k_gin_layer_fwd<THREADS, false><<<grid, THREADS, GL_SMEM, (cudaStream_t)stream>>>(a, tmx);
+    k_gin_layer_fwd<THREADS, false, false><<<grid, THREADS, GL_SMEM, (cudaStream_t)stream>>>(a, tmx);
   BIGNN_LAUNCH_COUNT(1);
   if (trace_dev) {                                   // (debug mode only: synchronises)
     static long long host[64 * 16];

@@ -279,9 +279,11 @@ k_pair_decoder_bwd(const PairDecoderBwdArgs g) {
       }
     }
   }
-  // ---- per-warp partials -> workspace; the last CTA adds them in warp order
+  // ---- per-warp partials -> shared memory, added in warp order into ONE partial per CTA; the last CTA to finish adds
+  // the per-CTA partials in CTA order (deterministic; two short levels instead of one long one)
+  extern __shared__ float part_s[];                 // [PD_WARPS][ws_stride]
   {
-    float* o = g.ws + (int64_t)gw * g.ws_stride;
+    float* o = part_s + (int64_t)w * g.ws_stride;
     int off = 0;
 #pragma unroll
     for (int j = 0; j < PD_MAX_N1; ++j)
@@ -305,16 +307,23 @@ k_pair_decoder_bwd(const PairDecoderBwdArgs g) {
     off += n_out * wl_in;
     if (lane < n_out) o[off + lane] = dbl;
   }
+  __syncthreads();
+  const int total = (int)g.ws_stride;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < PD_WARPS; ++i) s += part_s[(int64_t)i * g.ws_stride + e];
+    g.ws[(int64_t)blockIdx.x * g.ws_stride + e] = s;
+  }
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) is_last = (atomicAdd(a.counter, 1u) == gridDim.x - 1);
   __syncthreads();
   if (is_last) {
     __threadfence();
-    const int total = (int)g.ws_stride;
     for (int e = threadIdx.x; e < total; e += blockDim.x) {
       float s = 0.f;
-      for (int i = 0; i < n_warps; ++i) s += g.ws[(int64_t)i * g.ws_stride + e];
+      for (int i = 0; i < (int)gridDim.x; ++i) s += g.ws[(int64_t)i * g.ws_stride + e];
       // scatter into the caller's gradient tensors
       int off = e;
       if (off < n1 * 2 * D) { g.dW[0][off] = s; continue; }
@@ -433,7 +442,14 @@ extern "C" int bignn_pair_decoder_bwd(const float* H, int64_t ldh, const int32_t
   g.dW[0] = dW0; g.dW[1] = dW1; g.dW[2] = dW2; g.db[0] = db0; g.db[1] = db1; g.db[2] = db2;
   g.ws_stride = pd_params(n, n_layers, D);
   g.ws = (float*)((uint8_t*)workspace + 16 + (int64_t)grid * PD_WARPS * 8);
-  k_pair_decoder_bwd<<<grid, PD_WARPS * 32, 0, (cudaStream_t)stream>>>(g);
+  const int smem = PD_WARPS * (int)g.ws_stride * (int)sizeof(float);
+  static int configured_smem = 0;
+  if (smem > configured_smem) {
+    cudaError_t e = cudaFuncSetAttribute(k_pair_decoder_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    configured_smem = smem;
+  }
+  k_pair_decoder_bwd<<<grid, PD_WARPS * 32, smem, (cudaStream_t)stream>>>(g);
   BIGNN_LAUNCH_COUNT(1);
   return last_launch_status();
 }

@@ -78,7 +78,49 @@ k_readout_fwd_scalar(const float* __restrict__ X, int64_t ldx, const int32_t* __
   }
 }
 
-// dX[r, :] (+)= dOut[dst_row[g], :] / n      for every row r of graph g
+// dX[r, :] (+)= dOut[dst_row[g], :] / n      for every row r of graph g -- 128-bit accesses, 16 lanes per graph, four
+// rows in flight (the accumulate form reads before it writes: one row at a time is a chain of 30 dependent round trips)
+__global__ void __launch_bounds__(256)
+k_readout_bwd_v4(const float* __restrict__ dOut, int64_t ldo, const int32_t* __restrict__ dst_row,
+                 const int32_t* __restrict__ seg_ptr, int G, int D4, int style, float* __restrict__ dX, int64_t lddx,
+                 int accumulate) {
+  const int gpb = blockDim.x / 16;
+  const int sub = threadIdx.x / 16, lane = threadIdx.x % 16;
+  for (int g = blockIdx.x * gpb + sub; g < G; g += gridDim.x * gpb) {
+    const int r0 = __ldg(seg_ptr + g), r1 = __ldg(seg_ptr + g + 1);
+    const int n = r1 - r0;
+    const int64_t orow = dst_row ? dst_row[g] : g;
+    const float cnt = (float)(n > 1 ? n : 1);
+    for (int q = lane; q < D4; q += 16) {
+      float4 v = ldg4(dOut + orow * ldo + 4 * q);
+      if (style == BIGNN_READOUT_MEAN) {
+        v.x = __fdiv_rn(v.x, cnt); v.y = __fdiv_rn(v.y, cnt); v.z = __fdiv_rn(v.z, cnt); v.w = __fdiv_rn(v.w, cnt);
+      }
+      int r = r0;
+      if (accumulate) {
+        for (; r + 4 <= r1; r += 4) {
+          float4 o[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) o[u] = *reinterpret_cast<const float4*>(dX + (int64_t)(r + u) * lddx + 4 * q);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            o[u].x += v.x; o[u].y += v.y; o[u].z += v.z; o[u].w += v.w;
+            st4(dX + (int64_t)(r + u) * lddx + 4 * q, o[u]);
+          }
+        }
+        for (; r < r1; ++r) {
+          float4 o = *reinterpret_cast<const float4*>(dX + (int64_t)r * lddx + 4 * q);
+          o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
+          st4(dX + (int64_t)r * lddx + 4 * q, o);
+        }
+      } else {
+        for (; r < r1; ++r) st4(dX + (int64_t)r * lddx + 4 * q, v);
+      }
+    }
+  }
+}
+
+// scalar form (D % 4 != 0 or unaligned)
 __global__ void __launch_bounds__(256)
 k_readout_bwd(const float* __restrict__ dOut, int64_t ldo, const int32_t* __restrict__ dst_row,
               const int32_t* __restrict__ seg_ptr, int G, int D, int style, float* __restrict__ dX, int64_t lddx,
@@ -241,10 +283,18 @@ extern "C" int bignn_readout_bwd(const float* dOut, int64_t ldo, int32_t col_off
   if (G == 0 || D == 0) return 0;
   if (!dOut || !seg_ptr || !dX || lddx < D || ldo < col_off + D) return BIGNN_EINVAL;
   if (style != BIGNN_READOUT_SUM && style != BIGNN_READOUT_MEAN) return BIGNN_EINVAL;
-  int grid = ceil_div(G, 8);
   const int cap = sm_count() * 8;
+  const float* d = dOut + col_off;
+  if ((D % 4 == 0) && (ldo % 4 == 0) && (lddx % 4 == 0) && (col_off % 4 == 0) && aligned16(dOut) && aligned16(dX)) {
+    int grid = ceil_div(G, 16);
+    if (grid > cap) grid = cap;
+    k_readout_bwd_v4<<<grid, 256, 0, (cudaStream_t)stream>>>(d, ldo, dst_row, seg_ptr, G, D / 4, style, dX, lddx, accumulate);
+    BIGNN_LAUNCH_COUNT(1);
+    return last_launch_status();
+  }
+  int grid = ceil_div(G, 8);
   if (grid > cap) grid = cap;
-  k_readout_bwd<<<grid, 256, 0, (cudaStream_t)stream>>>(dOut + col_off, ldo, dst_row, seg_ptr, G, D, style, dX, lddx, accumulate);
+  k_readout_bwd<<<grid, 256, 0, (cudaStream_t)stream>>>(d, ldo, dst_row, seg_ptr, G, D, style, dX, lddx, accumulate);
   BIGNN_LAUNCH_COUNT(1);
   return last_launch_status();
 }

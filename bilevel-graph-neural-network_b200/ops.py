@@ -137,7 +137,7 @@ def gemm(a, b, ta=False, tb=False, bias=None, act=0, out=None):
 
 import os as _os
 
-TC_MIN_ROWS = 8192     # below this the dense transforms run as fp32 FMA (SIMT): a 128-row tensor-core tile grid cannot fill the SMs, and the
+TC_MIN_ROWS = int(_os.environ.get('BIGNN_TC_MIN_ROWS', 8192))     # below this the dense transforms run as fp32 FMA (SIMT): a 128-row tensor-core tile grid cannot fill the SMs, and the
                        # small upper-level graphs of the reference datasets (1 309 / 3 242 drugs) then keep exact fp32 products (forward gates 1e-5)
 _NO_TC = bool(_os.environ.get('BIGNN_NO_TC'))      # debugging switch: route the transforms to the SIMT kernels
 

@@ -119,7 +119,8 @@ def test_engine_step_with_and_without_fused_decoder(golden_dir, step_golden):
     assert a['launches'] < b['launches'] - 10
     for k in a['grads']:
         if int(k.split('.')[1]) >= 7:                       # upper level + scorer: well conditioned
-            sc = float(b['grads'][k].abs().max())
+            # (on the gradient scale of the layer: a bias in front of a BatchNorm has a true gradient of exactly 0)
+            sc = max(float(b['grads'][q].abs().max()) for q in b['grads'] if q.split('.')[1] == k.split('.')[1])
             assert float((a['grads'][k] - b['grads'][k]).abs().max()) <= 2e-5 * max(sc, 1e-12), k
     print('launches per step: fused decoder %d, layer-by-layer decoder %d' % (a['launches'], b['launches']))
 
