@@ -5,11 +5,14 @@ Tolerances: forward quantities 1e-5 relative (max-norm).  Gradients: the referen
 gradients sit up to 3.5e-4 from an fp64 run of the same code in the lower layers (ill-conditioned
 through five BatchNorms; measured in this test), so an fp32 path with another summation order
 cannot be within 1e-5 of them (the reference run with 2 instead of 8 CPU threads moves the same
-gradients by 4e-3).  The gate is therefore: error against the fp64 oracle no larger than 6x the
-reference's own fp32 error against it (+1e-5), per parameter, on the layer's gradient scale.
+gradients by 4e-3).  The gate is therefore: error against the fp64 oracle no larger than the
+reference's own fp32 error against it (+1e-5), per parameter, on the layer's gradient scale; the per-parameter
+errors are printed and written to gpurun_out/grad_errors_*.txt (copied to profiles/).
 The dense transforms run on the tensor cores as 3xTF32, whose accumulation truncates toward zero
 (a ~3e-7 relative bias per transform, profiles/acc_probe.py) where fp32 FMA rounds to nearest."""
-GRAD_GATE = 6.0
+GRAD_GATE = 1.0          # round 1: 6.0.  Measured in round 2 (profiles/r2_grad_errors_gin_gcn.txt): this path sits 2.5-10x CLOSER to
+                         # the fp64 oracle than the reference's own fp32 values do (worst ratio 0.45), so the gate is the reference's
+                         # own error (+1e-5 for parameters whose gradients are at rounding level)
 import os
 
 import numpy as np
