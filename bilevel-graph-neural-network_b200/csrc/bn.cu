@@ -67,21 +67,43 @@ k_bn_reduce_part(const float* __restrict__ X, int64_t ldx, const float* __restri
   }
 }
 
-__global__ void __launch_bounds__(256)
+// sum of the `parts` partials of (segment s, channel c): 8 threads walk contiguous slices of the parts, slices added
+// in slice order (deterministic; a single thread walking 256 parts of an S = 1 batch took 100 us)
+constexpr int BN_FIN_SL = 8;
+__device__ __forceinline__ void bn_sum_parts(const double* __restrict__ ws_a, const double* __restrict__ ws_b, int s,
+                                             int c, int C, int parts, double (*red)[BN_FIN_SL][33], double& a, double& b) {
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int per = (parts + BN_FIN_SL - 1) / BN_FIN_SL;
+  const int p0 = ty * per, p1 = min(parts, p0 + per);
+  double ta = 0.0, tb = 0.0;
+  if (c < C) {
+#pragma unroll 8
+    for (int p = p0; p < p1; ++p) {
+      ta += ws_a[((int64_t)s * parts + p) * C + c];
+      tb += ws_b[((int64_t)s * parts + p) * C + c];
+    }
+  }
+  red[0][ty][tx] = ta;
+  red[1][ty][tx] = tb;
+  __syncthreads();
+  a = 0.0; b = 0.0;
+#pragma unroll
+  for (int g = 0; g < BN_FIN_SL; ++g) { a += red[0][g][tx]; b += red[1][g][tx]; }
+}
+
+// grid (S, ceil(C / 32)), block 32 x BN_FIN_SL
+__global__ void __launch_bounds__(32 * BN_FIN_SL)
 k_bn_finalize(const double* __restrict__ ws_a, const double* __restrict__ ws_b,
               const int32_t* __restrict__ seg_row_ptr, int S, int C, int parts, float eps,
               float* __restrict__ mean, float* __restrict__ rstd,
               double* __restrict__ mean_d, double* __restrict__ varu_d) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (int64_t)S * C) return;
-  const int s = (int)(i / C), c = (int)(i % C);
+  __shared__ double red[2][BN_FIN_SL][33];
+  const int s = blockIdx.x, c = blockIdx.y * 32 + (threadIdx.x & 31);
+  double a, b;
+  bn_sum_parts(ws_a, ws_b, s, c, C, parts, red, a, b);
+  if (threadIdx.x >= 32 || c >= C) return;
+  const int64_t i = (int64_t)s * C + c;
   const int n = seg_row_ptr[s + 1] - seg_row_ptr[s];
-  double a = 0.0, b = 0.0;
-#pragma unroll 8
-  for (int p = 0; p < parts; ++p) {
-    a += ws_a[((int64_t)s * parts + p) * C + c];
-    b += ws_b[((int64_t)s * parts + p) * C + c];
-  }
   double mu = 0.0, var = 0.0;
   if (n > 0) {
     mu = a / n;
@@ -181,32 +203,43 @@ k_bn_eval(const float* __restrict__ X, int64_t ldx, float* __restrict__ Y, int64
 }
 
 // per segment sums of the backward reduction; also the parameter gradients
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * BN_FIN_SL)
 k_bn_bwd_finalize(const double* __restrict__ ws_a, const double* __restrict__ ws_b, int S, int C, int parts,
                   double* __restrict__ seg_a, double* __restrict__ seg_b) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (int64_t)S * C) return;
-  const int s = (int)(i / C), c = (int)(i % C);
-  double a = 0.0, b = 0.0;
-#pragma unroll 8
-  for (int p = 0; p < parts; ++p) {
-    a += ws_a[((int64_t)s * parts + p) * C + c];
-    b += ws_b[((int64_t)s * parts + p) * C + c];
-  }
-  seg_a[i] = a;
-  seg_b[i] = b;
+  __shared__ double red[2][BN_FIN_SL][33];
+  const int s = blockIdx.x, c = blockIdx.y * 32 + (threadIdx.x & 31);
+  double a, b;
+  bn_sum_parts(ws_a, ws_b, s, c, C, parts, red, a, b);
+  if (threadIdx.x >= 32 || c >= C) return;
+  seg_a[(int64_t)s * C + c] = a;
+  seg_b[(int64_t)s * C + c] = b;
 }
 
-__global__ void __launch_bounds__(256)
+// dgamma / dbeta = sums over the segments: 32 channels x 32 contiguous slices of segments per CTA, slices added in
+// slice order (one thread per channel walking all S segments took 188 us at S = 1 563 -- 1.5 ms of the C4 step)
+__global__ void __launch_bounds__(1024)
 k_bn_bwd_params(const double* __restrict__ seg_a, const double* __restrict__ seg_b, int S, int C,
                 float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  __shared__ double red[2][32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  const int per = (S + 31) / 32;
+  const int s0 = ty * per, s1 = min(S, s0 + per);
   double a = 0.0, b = 0.0;
+  if (c < C) {
 #pragma unroll 8
-  for (int s = 0; s < S; ++s) { a += seg_a[(int64_t)s * C + c]; b += seg_b[(int64_t)s * C + c]; }
-  if (dbeta) dbeta[c] = (float)a;
-  if (dgamma) dgamma[c] = (float)b;
+    for (int s = s0; s < s1; ++s) { a += seg_a[(int64_t)s * C + c]; b += seg_b[(int64_t)s * C + c]; }
+  }
+  red[0][ty][tx] = a;
+  red[1][ty][tx] = b;
+  __syncthreads();
+  if (ty < 2 && c < C) {
+    double t = 0.0;
+#pragma unroll 8
+    for (int g = 0; g < 32; ++g) t += red[ty][g][tx];
+    float* out = ty ? dgamma : dbeta;
+    if (out) out[c] = (float)t;
+  }
 }
 
 template <int IN_ACT>
@@ -484,7 +517,7 @@ extern "C" int bignn_bn_seg_fwd(const float* X, int64_t ldx, float* Y, int64_t l
   double* varu_d = mean_d + (int64_t)S * C;
   dim3 grid(S * parts, ceil_div(C, 32));
   launch_bn_reduce(false, S * parts, st, X, ldx, nullptr, 0, seg_row_ptr, C, parts, nullptr, nullptr, ws_a, ws_b, 0);
-  k_bn_finalize<<<(int)ceil_div<int64_t>((int64_t)S * C, 256), 256, 0, st>>>(ws_a, ws_b, seg_row_ptr, S, C, parts, eps, mean, rstd, mean_d, varu_d);
+  k_bn_finalize<<<dim3(S, ceil_div(C, 32)), 32 * BN_FIN_SL, 0, st>>>(ws_a, ws_b, seg_row_ptr, S, C, parts, eps, mean, rstd, mean_d, varu_d);
   BIGNN_LAUNCH_COUNT(2);
   if (running_mean && running_var) {
     k_bn_running<<<ceil_div(C, 64), 64, 0, st>>>(mean_d, varu_d, seg_row_ptr, S, C, (double)momentum, running_mean, running_var, num_batches_tracked);
@@ -540,8 +573,8 @@ extern "C" int bignn_bn_seg_bwd(const float* X, int64_t ldx, const float* dY, in
   double* seg_b = seg_a + (int64_t)S * C;
   dim3 grid(S * parts, ceil_div(C, 32));
   launch_bn_reduce(true, S * parts, st, X, ldx, dY, lddy, seg_row_ptr, C, parts, mean, rstd, ws_a, ws_b, 0);
-  k_bn_bwd_finalize<<<(int)ceil_div<int64_t>((int64_t)S * C, 256), 256, 0, st>>>(ws_a, ws_b, S, C, parts, seg_a, seg_b);
-  k_bn_bwd_params<<<ceil_div(C, 256), 256, 0, st>>>(seg_a, seg_b, S, C, dgamma, dbeta);
+  k_bn_bwd_finalize<<<dim3(S, ceil_div(C, 32)), 32 * BN_FIN_SL, 0, st>>>(ws_a, ws_b, S, C, parts, seg_a, seg_b);
+  k_bn_bwd_params<<<ceil_div(C, 32), 1024, 0, st>>>(seg_a, seg_b, S, C, dgamma, dbeta);
   launch_bn_bwd_apply(grid, st, input_act, X, ldx, dY, lddy, dX, lddx, seg_row_ptr, C, parts, gamma, mean, rstd, seg_a,
                       seg_b, 0, 0);
   BIGNN_LAUNCH_COUNT(4);

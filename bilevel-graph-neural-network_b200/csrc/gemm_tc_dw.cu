@@ -3,11 +3,11 @@
 // Replaces autograd's dW = dY^T X / X^T dY and db = sum dY of nn.Linear / `x @ weight`
 // (model/layers.py:26-30, PyG GCNConv/GATConv).
 //
-// A row tile [128 rows x 64 floats] staged as two [rows x 128 B] blocks is the canonical MN-major UMMA
+// A row tile [BM rows x 64 floats] staged as two [rows x 128 B] blocks is the canonical MN-major UMMA
 // operand (MN = feature, K = row).  For 32-bit MN-major operands the only legal shared-memory layout is
 // SWIZZLE_128B_BASE32B: 4-row groups (SBO = 512 B) whose four 32-byte chunks are XOR-permuted with
-// the row index; the two 32-feature blocks are LBO = 16 KB apart; one K step (8 TF32) = two groups.  Per 128-row tile 16 K-steps x 3 products
-// (hi*hi + lo*hi + hi*lo) accumulate into TMEM; accumulators persist across all tiles of the CTA and
+// the row index; the two 32-feature blocks are LBO = BM * 128 B apart; one K step (8 TF32) = two groups.  Per 32-row
+// tile 4 K-steps x 3 products (hi*hi + lo*hi + hi*lo) accumulate into TMEM; accumulators persist across all tiles of the CTA and
 // the per-CTA partial [64 x 64] goes to a workspace that a fixed-order reduction sums (deterministic).
 // The MMA runs with M = 128: rows 64..127 of D come from the Q blocks that follow P in shared memory
 // and are ignored (a 64-row MMA costs the same tensor time and has a scattered TMEM layout).
@@ -19,10 +19,6 @@ namespace bignn {
 constexpr int DW_F = 64;                       // padded feature width of both operands
 constexpr int DW_MMA_M = 128;                  // MMA M (features of P in rows 0..63; rows 64..127 ignored)
 
-// Two configurations of the row tile (= K extent per tile) BM and the number NA of rotating accumulators:
-//   <64, 3>   96 KB of shared memory and (3+1)*64 = 256 TMEM columns per CTA -> TWO CTAs per SM, whose phases
-//             (cp.async fill, hi/lo split on the SIMT pipes, MMAs on the tensor pipe) overlap each other;
-//   <128, 4>  192 KB, 512 TMEM columns, one CTA per SM (the first version; BIGNN_DW_BM=128 selects it).
 __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr, int blk_bytes) {
   // MN-major, SWIZZLE_128B_BASE32B (layout type 1): LBO = distance between 32-feature blocks,
   // SBO = distance between 4-row groups
@@ -41,174 +37,10 @@ __device__ __forceinline__ uint32_t umma_idesc_tf32_mn(int M, int N) {
          ((uint32_t)(M >> 4) << 24);
 }
 
-// smem: 2 x [P_hi][Q_hi] (double buffered: the next tile streams in while this one is multiplied)
-//       + [P_lo][Q_lo], each DW_TILE bytes
-template <int BM, int DW_NA>
-__global__ void __launch_bounds__(TC_THREADS, (BM == 64 ? 2 : 1))
-k_dw_tc(int M, int Np, int Nq, const float* __restrict__ P, int64_t ldp, const float* __restrict__ Q, int64_t ldq,
-        int colsum_of, float* __restrict__ ws_dw, double* __restrict__ ws_cs) {
-  constexpr int DW_BLK = BM * 128;               // one [BM rows x 128 B] block (32 features)
-  constexpr int DW_TILE = 2 * DW_BLK;            // one operand tile (64 features)
-  constexpr int NCHUNK = 4 * BM * 8;             // 16-byte chunks of both operand tiles
-  constexpr int LOG_OP = (BM == 64 ? 10 : 11);   // chunks per operand = 2 * BM * 8
-  static_assert((DW_NA + 1) * DW_F <= (BM == 64 ? 256 : 512), "TMEM columns");
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* p_lo = smem + 4 * DW_TILE;
-  __shared__ uint64_t mma_bar;
-  __shared__ uint32_t tmem_base_s;
-  __shared__ double cs_red[4][DW_F];
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n_tiles = (M + BM - 1) / BM;
-  constexpr int TMEM_COLS = (DW_NA + 1) * DW_F <= 256 ? 256 : 512;   // power of two >= (DW_NA + 1) * 64
-
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
-                 "r"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  if (tid == 32) {
-    mbar_init(&mma_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  const uint32_t smem_s = smem_u32(smem);
-  // both operand tiles: 2 x 2048 sixteen-byte chunks; zero fill beyond M rows / N features
-  auto prefetch_tile = [&](int tile, int buf) {
-    const int m0 = tile * BM;
-    const uint32_t hi_s = smem_s + buf * 2 * DW_TILE;
-#pragma unroll 1
-    for (int j = tid; j < NCHUNK; j += TC_THREADS) {
-      const int op = j >> LOG_OP, idx = j & ((1 << LOG_OP) - 1);           // op 0 = P, 1 = Q
-      const int blk = idx >> (LOG_OP - 1), r = (idx & ((1 << (LOG_OP - 1)) - 1)) >> 3, c = idx & 7;
-      const int gm = m0 + r, gf = blk * 32 + c * 4;
-      const int nf = op ? Nq : Np;
-      const bool ok = gm < M && gf < nf;
-      const float* base = op ? Q + (int64_t)gm * ldq : P + (int64_t)gm * ldp;
-      cp_async16(hi_s + op * DW_TILE + blk * DW_BLK + sw32b_off(r, c), ok ? base + gf : (op ? Q : P), ok ? 16u : 0u);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-  int tile = blockIdx.x;
-  int buf = 0;
-  if (tile < n_tiles) prefetch_tile(tile, 0);
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_d = tmem_base_s;
-  const uint32_t idesc = umma_idesc_tf32_mn(DW_MMA_M, DW_F);
-
-  double cs = 0.0;                                     // this thread's column-sum share
-  const int cs_col = tid & 63, cs_rg = tid >> 6;
-  uint32_t phase = 0;
-  int ks = 0;                                          // K steps issued so far (across tiles)
-  for (; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
-    uint8_t* p_hi = smem + buf * 2 * DW_TILE;
-    uint8_t* q_hi = p_hi + DW_TILE;
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    // the other hi buffer was last read by the previous tile's MMAs, which have completed: refill it now
-    if (tile + gridDim.x < n_tiles) prefetch_tile(tile + gridDim.x, buf ^ 1);
-    // ---- lo = tf32(x - hi(x)) for the chunks this thread copied
-#pragma unroll 4
-    for (int j = tid; j < NCHUNK; j += TC_THREADS) {
-      const int op = j >> LOG_OP, idx = j & ((1 << LOG_OP) - 1);
-      const uint32_t off = op * DW_TILE + (idx >> (LOG_OP - 1)) * DW_BLK +
-                           sw32b_off((idx & ((1 << (LOG_OP - 1)) - 1)) >> 3, idx & 7);
-      const float4 x = *reinterpret_cast<const float4*>(p_hi + off);
-      uint4 l;
-      l.x = __float_as_uint(x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u)) & 0xffffe000u;
-      l.y = __float_as_uint(x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u)) & 0xffffe000u;
-      l.z = __float_as_uint(x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u)) & 0xffffe000u;
-      l.w = __float_as_uint(x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u)) & 0xffffe000u;
-      *reinterpret_cast<uint4*>(p_lo + off) = l;
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    if (tid == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint64_t dp_hi = umma_desc_mn_sw128(smem_u32(p_hi), DW_BLK), dp_lo = umma_desc_mn_sw128(smem_u32(p_lo), DW_BLK);
-      const uint64_t dq_hi = umma_desc_mn_sw128(smem_u32(q_hi), DW_BLK),
-                     dq_lo = umma_desc_mn_sw128(smem_u32(p_lo + DW_TILE), DW_BLK);
-#pragma unroll 1
-      for (int k = 0; k < BM / 8; ++k, ++ks) {
-        const uint64_t adv = (uint64_t)((k * 1024) >> 4);       // next 8-row group
-        umma_tf32(tmem_d + (uint32_t)((ks % DW_NA) * DW_F), dp_hi + adv, dq_hi + adv, idesc, ks >= DW_NA ? 1u : 0u);
-        umma_tf32(tmem_d + (uint32_t)(DW_NA * DW_F), dp_lo + adv, dq_hi + adv, idesc, ks > 0 ? 1u : 0u);
-        umma_tf32(tmem_d + (uint32_t)(DW_NA * DW_F), dp_hi + adv, dq_lo + adv, idesc, 1u);
-      }
-      umma_commit(&mma_bar);
-    } else if (tid >= 32) {
-      ks += BM / 8;
-    }
-    // ---- column sums of the chosen operand from the raw tile (while the tensor core runs)
-    if (colsum_of >= 0) {
-      const uint8_t* t0 = p_hi + (colsum_of ? DW_TILE : 0) + (cs_col >> 5) * DW_BLK;
-      const int c = (cs_col & 31) >> 2, e = cs_col & 3;
-      float s = 0.f;
-#pragma unroll 4
-      for (int r = cs_rg; r < BM; r += 4) s += *reinterpret_cast<const float*>(t0 + sw32b_off(r, c) + e * 4);
-      cs += (double)s;
-    }
-    mbar_wait(&mma_bar, phase);
-    phase ^= 1;
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    __syncthreads();                                     // every thread is done reading the raw tile
-  }
-  ks = __shfl_sync(0xffffffffu, ks, 0);                  // warp 0: lane 0 counted while issuing
-  // ---- per-CTA partials: D rows 0..63 live in TMEM lanes 0..63 (warps with quadrant 0 and 1)
-  const int n_steps = ((n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * (BM / 8);
-  {
-    const int q = warp & 3;
-    if (q < 2) {
-      const int row = q * 32 + lane;                     // output feature of P
-#pragma unroll 1
-      for (int cb = (warp >> 2) * 32; cb < DW_F; cb += 64) {
-        uint32_t r[32];
-        float v[32];
-        const uint32_t tbase = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)cb;
-        if (n_steps > 0) {
-          tmem_ld32(tbase + (uint32_t)(DW_NA * DW_F), r);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0.f;
-        }
-#pragma unroll 1
-        for (int a = 0; a < DW_NA; ++a) {
-          if (a >= n_steps) break;
-          tmem_ld32(tbase + (uint32_t)(a * DW_F), r);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __fadd_rn(__uint_as_float(r[j]), v[j]);
-        }
-        if (row < Np) {
-          float* dst = ws_dw + ((int64_t)blockIdx.x * Np + row) * Nq;
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (cb + j < Nq) dst[cb + j] = v[j];
-        }
-      }
-    }
-  }
-  if (colsum_of >= 0) {
-    cs_red[cs_rg][cs_col] = cs;
-    __syncthreads();
-    const int ncs = colsum_of ? Nq : Np;
-    if (tid < ncs) ws_cs[(int64_t)blockIdx.x * ncs + tid] = ((cs_red[0][tid] + cs_red[1][tid]) + cs_red[2][tid]) + cs_red[3][tid];
-  }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TMEM_COLS) : "memory");
-  }
-}
-
 // ---------------------------------------------------------------------------------------------------------------
-// Ring variant (the default since round 2; BIGNN_DW_BM=64 / 128 select the kernels above): ncu on k_dw_tc<64,3> shows
-// no dominant stall, 23 % tensor-pipe activity and one 32 KB tile in flight
-// per CTA, i.e. the kernel waits for data.  Here the operand tiles are 32-row stages in an NST-deep cp.async ring
+// The kernel.  Its predecessors (128-row tiles, one CTA per SM: 1.22 ms per call at 6 M rows; 64-row double-buffered
+// tiles, two CTAs per SM: 0.89 ms, ncu: no dominant stall, 23 % tensor-pipe activity, one 32 KB tile in flight per CTA,
+// i.e. waiting for data) lost to this one and were removed in round 2.  Here the operand tiles are 32-row stages in an NST-deep cp.async ring
 // (NST-2 tiles in flight beyond the one being split) and the lo operand is double buffered, so the hi/lo split of
 // tile i+1 overlaps the MMAs of tile i (one mbarrier per lo buffer; a stage is refilled only after the MMAs that
 // read it have committed).  96 KB of shared memory and 256 TMEM columns per CTA -> two CTAs per SM.
@@ -384,62 +216,53 @@ k_dw_tc_ring(int M, int Np, int Nq, const float* __restrict__ P, int64_t ldp, co
   }
 }
 
-// fixed-order sums over the per-CTA partials
+// fixed-order sums over the per-CTA partials: blocks [0, dw_blocks) finish 32 elements of dW each, the blocks after
+// them 32 column sums (the bias gradient) each -- one launch for both
 __global__ void __launch_bounds__(256)
-k_dw_reduce(const float* __restrict__ ws_dw, int parts, int total, float* __restrict__ out) {
-  __shared__ float red[8][33];
-  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
-  const int i = blockIdx.x * 32 + tx;
-  float s = 0.f;
-  if (i < total) {
-#pragma unroll 4
-    for (int z = ty; z < parts; z += 8) s += __ldg(ws_dw + (int64_t)z * total + i);
-  }
-  red[ty][tx] = s;
-  __syncthreads();
-  if (ty == 0 && i < total) {
-    float t = 0.f;
-#pragma unroll
-    for (int g = 0; g < 8; ++g) t += red[g][tx];
-    out[i] = t;
-  }
-}
-
-__global__ void __launch_bounds__(256)
-k_dw_cs_reduce(const double* __restrict__ ws, int parts, int cols, float* __restrict__ out) {
+k_dw_reduce(const float* __restrict__ ws_dw, int parts, int total, float* __restrict__ out, int dw_blocks,
+            const double* __restrict__ ws_cs, int cols, float* __restrict__ cs_out) {
   __shared__ double red[8][33];
   const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
-  const int c = blockIdx.x * 32 + tx;
-  double s = 0.0;
-  if (c < cols) {
+  if ((int)blockIdx.x < dw_blocks) {
+    float* redf = reinterpret_cast<float*>(&red[0][0]);
+    const int i = blockIdx.x * 32 + tx;
+    float s = 0.f;
+    if (i < total) {
 #pragma unroll 4
-    for (int p = ty; p < parts; p += 8) s += ws[(int64_t)p * cols + c];
-  }
-  red[ty][tx] = s;
-  __syncthreads();
-  if (ty == 0 && c < cols) {
-    double t = 0.0;
+      for (int z = ty; z < parts; z += 8) s += __ldg(ws_dw + (int64_t)z * total + i);
+    }
+    redf[ty * 33 + tx] = s;
+    __syncthreads();
+    if (ty == 0 && i < total) {
+      float t = 0.f;
 #pragma unroll
-    for (int g = 0; g < 8; ++g) t += red[g][tx];
-    out[c] = (float)t;
+      for (int g = 0; g < 8; ++g) t += redf[g * 33 + tx];
+      out[i] = t;
+    }
+  } else {
+    const int c = ((int)blockIdx.x - dw_blocks) * 32 + tx;
+    double s = 0.0;
+    if (c < cols) {
+#pragma unroll 4
+      for (int q = ty; q < parts; q += 8) s += ws_cs[(int64_t)q * cols + c];
+    }
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && c < cols) {
+      double t = 0.0;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) t += red[g][tx];
+      cs_out[c] = (float)t;
+    }
   }
 }
 
-static int dw_bm() {   // rows per tile: the 32-row 4-stage ring (default since round 2: 2.55 vs 2.37 TB/s at 2 M rows,
-                       // profiles/r2_summary.md), 64 (two CTAs per SM, BIGNN_DW_BM=64) or 128 (BIGNN_DW_BM=128)
-  static int bm = 0;
-  if (bm == 0) {
-    const char* e = getenv("BIGNN_DW_BM");
-    const int v = e ? atoi(e) : 32;
-    bm = (v == 128 || v == 64) ? v : 32;
-  }
-  return bm;
-}
+constexpr int DW_BM = 32, DW_NST = 4, DW_ACC = 3;      // rows per stage, ring depth, rotating hi*hi accumulators
+constexpr int DW_SMEM = 6 * DW_NST * DW_BM * 128 + 1024;
 
 static int dw_grid(int M) {
-  const int bm = dw_bm();
-  const int n_tiles = ceil_div(M, bm);
-  int g = sm_count() * (bm == 128 ? 1 : 2);
+  const int n_tiles = ceil_div(M, DW_BM);
+  const int g = sm_count() * 2;
   return g > n_tiles ? n_tiles : g;
 }
 
@@ -471,26 +294,14 @@ extern "C" int bignn_dw_tc_f32(int32_t M, int32_t Np, int32_t Nq, const float* P
   double* ws_cs = (double*)((uint8_t*)workspace + (((int64_t)grid * Np * Nq * sizeof(float) + 15) & ~(int64_t)15));
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_dw_tc<64, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * 2 * 64 * 128 + 1024);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(k_dw_tc<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * 2 * 128 * 128 + 1024);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(k_dw_tc_ring<32, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * 4 * 32 * 128 + 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_dw_tc_ring<DW_BM, DW_NST, DW_ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  if (dw_bm() == 32)
-    k_dw_tc_ring<32, 4, 3><<<grid, TC_THREADS, 6 * 4 * 32 * 128 + 1024, st>>>(M, Np, Nq, P, ldp, Q, ldq, colsum_of < 0 ? -1 : colsum_of, ws_dw, ws_cs);
-  else if (dw_bm() == 64)
-    k_dw_tc<64, 3><<<grid, TC_THREADS, 6 * 2 * 64 * 128 + 1024, st>>>(M, Np, Nq, P, ldp, Q, ldq, colsum_of < 0 ? -1 : colsum_of, ws_dw, ws_cs);
-  else
-    k_dw_tc<128, 4><<<grid, TC_THREADS, 6 * 2 * 128 * 128 + 1024, st>>>(M, Np, Nq, P, ldp, Q, ldq, colsum_of < 0 ? -1 : colsum_of, ws_dw, ws_cs);
-  k_dw_reduce<<<ceil_div(Np * Nq, 32), 256, 0, st>>>(ws_dw, grid, Np * Nq, D);
+  k_dw_tc_ring<DW_BM, DW_NST, DW_ACC><<<grid, TC_THREADS, DW_SMEM, st>>>(M, Np, Nq, P, ldp, Q, ldq, colsum_of < 0 ? -1 : colsum_of, ws_dw, ws_cs);
+  const int ncs = colsum_of < 0 ? 0 : (colsum_of ? Nq : Np);
+  const int dw_blocks = ceil_div(Np * Nq, 32);
+  k_dw_reduce<<<dw_blocks + ceil_div(ncs, 32), 256, 0, st>>>(ws_dw, grid, Np * Nq, D, dw_blocks, ws_cs, ncs, colsum);
   BIGNN_LAUNCH_COUNT(2);
-  if (colsum_of >= 0) {
-    const int ncs = colsum_of ? Nq : Np;
-    k_dw_cs_reduce<<<ceil_div(ncs, 32), 256, 0, st>>>(ws_cs, grid, ncs, colsum);
-    BIGNN_LAUNCH_COUNT(1);
-  }
   return last_launch_status();
 }

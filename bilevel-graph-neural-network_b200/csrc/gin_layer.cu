@@ -31,10 +31,13 @@ namespace bignn {
 constexpr int GL_D = 64;                       // output width (and padded input width)
 constexpr int GL_SLOT = 4 * TC_BM * 128;       // [hi ch0][hi ch1][lo ch0][lo ch1], 16 KB each
 constexpr int GL_W = 2 * GL_D * 128;           // one weight part: two K chunks of [64 x 128 B]
-constexpr int GL_IDX_CAP = 1536;               // neighbour ids of one tile staged in shared memory (beyond: global reads)
+constexpr int GL_IDX_CAP = 1280;               // neighbour ids of one tile staged in shared memory (beyond: global reads)
 constexpr int GL_IDX_RP = 132;                 // row pointers of one tile (129 used)
+constexpr int GL_IDX_META = 132;               // chunk id of every row of the tile (128) + the tile's first chunk
+constexpr int GL_IDX_FOLD = 4 * GL_D;          // folded BatchNorm mean[2][64], scale[2][64] of the tile's first two chunks
+constexpr int GL_IDX_STAGE = GL_IDX_RP + GL_IDX_META + GL_IDX_FOLD + GL_IDX_CAP;      // ints per stage
 constexpr int GL_IDX_STAGES = 3;
-constexpr int GL_IDX_BYTES = (GL_IDX_RP + GL_IDX_CAP) * 4;
+constexpr int GL_IDX_BYTES = GL_IDX_STAGE * 4;
 constexpr int GL_SMEM = 2 * GL_SLOT + 4 * GL_W + GL_IDX_STAGES * GL_IDX_BYTES + 1024;
 constexpr int GL_EPI_WARPS = 4;                // per epilogue phase: one warp per TMEM lane quadrant
 // TMEM: ONE fp32 accumulator of 64 columns per transform (reading TMEM costs 64 B/cycle/SM: three accumulators per
@@ -111,12 +114,30 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[1
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// 32 columns of this thread's accumulator row
-__device__ __forceinline__ void load_acc32(uint32_t tb, float (&v)[32]) {
-  uint32_t r[32];
-  tmem_ld32(tb, r);
+// GL_EC = 16 columns of this thread's accumulator row per epilogue step (32 would need 64 + 32 live registers in E1:
+// the kernel runs 1024 threads at 64 registers)
+constexpr int GL_EC = 16;
+__device__ __forceinline__ void load_acc16(uint32_t tb, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(tb)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+}
+// 16 consecutive columns of this thread's TMEM lane <- 16 registers
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
 }
 __device__ __forceinline__ float4 sub4(const float4& a, const float4& m) {
   return make_float4(__fsub_rn(a.x, m.x), __fsub_rn(a.y, m.y), __fsub_rn(a.z, m.z), __fsub_rn(a.w, m.w));
@@ -135,7 +156,7 @@ __device__ __forceinline__ uint4 lo_part(const float4& x) {
 }
 
 struct GinLayerArgs {
-  int rows, din, n_tiles, nnz, dbg;
+  int rows, din, n_tiles, nnz, dbg, S;
   const int32_t* row_ptr; const int32_t* col_idx; const int32_t* tile_edge_ptr;
   const float* X; int64_t ldx;
   const float* fold_mean; const float* fold_a; const float* fold_beta;   // [S, din], [S, din], [din] or null
@@ -240,7 +261,7 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_acc, const uint8_t* a_h
 // TMEM_A: the hidden activations t go from E1 straight into TENSOR MEMORY (tcgen05.st) and the second transform reads
 // its A operand there (tcgen05.mma [d], [a_tmem], b_desc): per tile 64 KB of shared-memory writes and 96 KB of
 // shared-memory operand reads less (BIGNN_GL_TMEM_A=0 selects the all-shared-memory variant).
-template <int THREADS, bool STAGE_X, bool TMEM_A>
+template <int THREADS, bool STAGE_X, bool TMEM_A, int GL_U>
 __global__ void __launch_bounds__(THREADS, 1)
 k_gin_layer_fwd(const GinLayerArgs p, const __grid_constant__ CUtensorMap tmx) {
   constexpr int N_WARPS = THREADS / 32;
@@ -259,7 +280,7 @@ k_gin_layer_fwd(const GinLayerArgs p, const __grid_constant__ CUtensorMap tmx) {
   __shared__ uint64_t x_full[2], z_full[2], z_empty[2], t_full[2], t_copied[2], acc2_free[2], m1_done[2], m2_done[2],
       idx_full[GL_IDX_STAGES], idx_empty[GL_IDX_STAGES];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float b1_s[GL_D], b2_s[GL_D];
+  __shared__ __align__(16) float b1_s[GL_D], b2_s[GL_D], beta_s[GL_D];
   __shared__ double red_s[2][8][GL_D];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -287,6 +308,7 @@ k_gin_layer_fwd(const GinLayerArgs p, const __grid_constant__ CUtensorMap tmx) {
   if (tid < GL_D) {
     b1_s[tid] = p.b1 ? __ldg(p.b1 + tid) : 0.f;
     b2_s[tid] = p.b2 ? __ldg(p.b2 + tid) : 0.f;
+    beta_s[tid] = (p.fold_beta && tid < p.din) ? __ldg(p.fold_beta + tid) : 0.f;
   }
   // ---- weights: W[n][k] (nn.Linear layout) split once per CTA into the K-major SWIZZLE_128B B operands
 #pragma unroll 1
@@ -321,19 +343,18 @@ k_gin_layer_fwd(const GinLayerArgs p, const __grid_constant__ CUtensorMap tmx) {
     const int64_t ldx = p.ldx;
     const bool fold = p.fold_a != nullptr;
     const float sc = p.self_coef;
-    // folded BatchNorm parameters of the chunk being processed (reloaded only when the chunk changes)
-    float4 mu0 = f4z(), mu1 = f4z(), fa0 = f4z(), fa1 = f4z(), be0 = f4z(), be1 = f4z();
-    int cached_chunk = -1;
-    if (fold) {
-      if (ok0) be0 = ldg4(p.fold_beta + 4 * l8);
-      if (ok1) be1 = ldg4(p.fold_beta + 4 * (l8 + 8));
-    }
+    // The folded BatchNorm parameters of a row's chunk come from the index stage (its chunk id, and mean / scale of the
+    // tile's first two chunks, are put there by the index warp): the producers' only global loads are rows of X.  (With
+    // the chunk lookup and the parameters fetched from global memory here, every row iteration was a chain of three to
+    // four dependent L2 round trips -- the 28 KB of L1 left beside the operand slots does not keep them.)
     int it = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const int b = it & 1;
       const int st = it % GL_IDX_STAGES;
-      const int32_t* rp_s = idx_s + st * (GL_IDX_RP + GL_IDX_CAP);
-      const int32_t* col_s = rp_s + GL_IDX_RP;
+      const int32_t* rp_s = idx_s + st * GL_IDX_STAGE;
+      const int32_t* meta_s = rp_s + GL_IDX_RP;
+      const float* fold_s = reinterpret_cast<const float*>(meta_s + GL_IDX_META);
+      const int32_t* col_s = meta_s + GL_IDX_META + GL_IDX_FOLD;
       mbar_wait_relaxed(&idx_full[st], (it / GL_IDX_STAGES) & 1);
       if (STAGE_X) {
         // neighbours outside the tile (molecules that straddle a tile boundary) come from global memory: ask for their
@@ -359,10 +380,12 @@ k_gin_layer_fwd(const GinLayerArgs p, const __grid_constant__ CUtensorMap tmx) {
       const uint8_t* xs = a_lo;                             // staged X rows, K-major SWIZZLE_128B (written by TMA)
       const int m0 = tile * TC_BM;
       const int e_lo = rp_s[0] & ~3;                        // first staged neighbour id (16-byte aligned start)
-      int chunk = fold ? __ldg(p.tile_chunk0 + tile) : 0;
       // ---- phase 1: z rows from the staged tile (neighbours outside it: global memory) -> the slot's hi region
+      // 128 rows over N_GROUPS (56) groups = two or three rows per group: which groups take three rotates from tile to
+      // tile, so that no warp is the slow one on every tile (the slots let a warp run one tile ahead)
+      const int grp_t = (grp + it * (TC_BM % N_GROUPS)) % N_GROUPS;
 #pragma unroll 1
-      for (int r = grp; r < TC_BM; r += N_GROUPS) {
+      for (int r = grp_t; r < TC_BM; r += N_GROUPS) {
         const int grow = m0 + r;
         float4 z0 = f4z(), z1 = f4z();
         if (grow < p.rows && !(p.dbg & 1)) {
@@ -379,51 +402,53 @@ k_gin_layer_fwd(const GinLayerArgs p, const __grid_constant__ CUtensorMap tmx) {
           }
           // BatchNorm of the producer layer folded in, centred: sum_j (a (y_j - mean) + beta) = a * sum_j (y_j - mean)
           // + beta * (number of terms): the subtraction happens per loaded value (no cancellation of large sums)
+          float4 mu0 = f4z(), mu1 = f4z();
+          int chunk = 0, cslot = 0;
           if (fold) {
-            while (grow >= __ldg(p.chunk_row_ptr + chunk + 1)) ++chunk;
-            if (chunk != cached_chunk) {
-              cached_chunk = chunk;
+            chunk = meta_s[r];
+            cslot = chunk - meta_s[TC_BM];
+            if (cslot < 2) {
+              const float* fm = fold_s + cslot * GL_D + 4 * l8;
+              if (ok0) mu0 = *reinterpret_cast<const float4*>(fm);
+              if (ok1) mu1 = *reinterpret_cast<const float4*>(fm + 32);
+            } else {                                            // (a tile that spans more than two chunks)
               const float* fm = p.fold_mean + (int64_t)chunk * p.din + 4 * l8;
-              const float* fa = p.fold_a + (int64_t)chunk * p.din + 4 * l8;
-              if (ok0) { mu0 = ldg4(fm); fa0 = ldg4(fa); }
-              if (ok1) { mu1 = ldg4(fm + 32); fa1 = ldg4(fa + 32); }
+              if (ok0) mu0 = ldg4(fm);
+              if (ok1) mu1 = ldg4(fm + 32);
             }
           }
           float4 a0 = f4z(), a1 = f4z();
           int cnt = 0;
-          for (int k = k0; k < k1; k += 2) {
-            int c0 = (k - e_lo < GL_IDX_CAP) ? col_s[k - e_lo] : __ldg(p.col_idx + k);
-            int c1 = -1;
-            if (k + 1 < k1) c1 = (k + 1 - e_lo < GL_IDX_CAP) ? col_s[k + 1 - e_lo] : __ldg(p.col_idx + k + 1);
-            if (c0 == grow) c0 = -1;                             // remove_self_loops (PyG GINConv)
-            if (c1 == grow) c1 = -1;
-            float4 v00 = f4z(), v01 = f4z(), v10 = f4z(), v11 = f4z();
-            if (c0 >= 0) {
-              const unsigned l0 = (unsigned)(c0 - m0);
-              if (STAGE_X && l0 < (unsigned)TC_BM) {
-                const uint32_t o = sw128_off((int)l0, l8);
-                if (ok0) v00 = *reinterpret_cast<const float4*>(xs + o);
-                if (ok1) v01 = *reinterpret_cast<const float4*>(xs + TC_BM * 128 + o);
-              } else {
-                const float* n0 = X + (int64_t)c0 * ldx;
-                if (ok0) v00 = ldg4(n0);
-                if (ok1) v01 = ldg4(n0 + 32);
+          // GL_U neighbour rows in flight per group: molecule graphs have degree <= 4, so one round of loads per row
+          // (the sums stay in ascending neighbour order: bit-identical to bignn_spmm_f32)
+          for (int k = k0; k < k1; k += GL_U) {
+            int c[GL_U];
+            float4 v0[GL_U], v1[GL_U];
+#pragma unroll
+            for (int j = 0; j < GL_U; ++j) {
+              c[j] = -1;
+              if (k + j < k1) c[j] = (k + j - e_lo < GL_IDX_CAP) ? col_s[k + j - e_lo] : __ldg(p.col_idx + k + j);
+              if (c[j] == grow) c[j] = -1;                       // remove_self_loops (PyG GINConv)
+            }
+#pragma unroll
+            for (int j = 0; j < GL_U; ++j) {
+              v0[j] = f4z(); v1[j] = f4z();
+              if (c[j] >= 0) {
+                const unsigned lj = (unsigned)(c[j] - m0);
+                if (STAGE_X && lj < (unsigned)TC_BM) {
+                  const uint32_t o = sw128_off((int)lj, l8);
+                  if (ok0) v0[j] = *reinterpret_cast<const float4*>(xs + o);
+                  if (ok1) v1[j] = *reinterpret_cast<const float4*>(xs + TC_BM * 128 + o);
+                } else {
+                  const float* nj = X + (int64_t)c[j] * ldx;
+                  if (ok0) v0[j] = ldg4(nj);
+                  if (ok1) v1[j] = ldg4(nj + 32);
+                }
               }
             }
-            if (c1 >= 0) {
-              const unsigned l1 = (unsigned)(c1 - m0);
-              if (STAGE_X && l1 < (unsigned)TC_BM) {
-                const uint32_t o = sw128_off((int)l1, l8);
-                if (ok0) v10 = *reinterpret_cast<const float4*>(xs + o);
-                if (ok1) v11 = *reinterpret_cast<const float4*>(xs + TC_BM * 128 + o);
-              } else {
-                const float* n1 = X + (int64_t)c1 * ldx;
-                if (ok0) v10 = ldg4(n1);
-                if (ok1) v11 = ldg4(n1 + 32);
-              }
-            }
-            if (c0 >= 0) { add4(a0, fold ? sub4(v00, mu0) : v00); add4(a1, fold ? sub4(v01, mu1) : v01); ++cnt; }
-            if (c1 >= 0) { add4(a0, fold ? sub4(v10, mu0) : v10); add4(a1, fold ? sub4(v11, mu1) : v11); ++cnt; }
+#pragma unroll
+            for (int j = 0; j < GL_U; ++j)
+              if (c[j] >= 0) { add4(a0, fold ? sub4(v0[j], mu0) : v0[j]); add4(a1, fold ? sub4(v1[j], mu1) : v1[j]); ++cnt; }
           }
           if (fold) { s0 = sub4(s0, mu0); s1 = sub4(s1, mu1); }
           z0.x = __fadd_rn(__fmul_rn(sc, s0.x), a0.x); z0.y = __fadd_rn(__fmul_rn(sc, s0.y), a0.y);
@@ -432,6 +457,18 @@ k_gin_layer_fwd(const GinLayerArgs p, const __grid_constant__ CUtensorMap tmx) {
           z1.z = __fadd_rn(__fmul_rn(sc, s1.z), a1.z); z1.w = __fadd_rn(__fmul_rn(sc, s1.w), a1.w);
           if (fold) {
             const float wsum = sc + (float)cnt;
+            float4 fa0 = f4z(), fa1 = f4z();
+            if (cslot < 2) {
+              const float* fa = fold_s + (2 + cslot) * GL_D + 4 * l8;
+              if (ok0) fa0 = *reinterpret_cast<const float4*>(fa);
+              if (ok1) fa1 = *reinterpret_cast<const float4*>(fa + 32);
+            } else {
+              const float* fa = p.fold_a + (int64_t)chunk * p.din + 4 * l8;
+              if (ok0) fa0 = ldg4(fa);
+              if (ok1) fa1 = ldg4(fa + 32);
+            }
+            const float4 be0 = *reinterpret_cast<const float4*>(beta_s + 4 * l8);          // (zeros beyond din)
+            const float4 be1 = *reinterpret_cast<const float4*>(beta_s + 4 * (l8 + 8));
             z0.x = fmaf(fa0.x, z0.x, be0.x * wsum); z0.y = fmaf(fa0.y, z0.y, be0.y * wsum);
             z0.z = fmaf(fa0.z, z0.z, be0.z * wsum); z0.w = fmaf(fa0.w, z0.w, be0.w * wsum);
             z1.x = fmaf(fa1.x, z1.x, be1.x * wsum); z1.y = fmaf(fa1.y, z1.y, be1.y * wsum);
@@ -457,7 +494,7 @@ k_gin_layer_fwd(const GinLayerArgs p, const __grid_constant__ CUtensorMap tmx) {
         // every producer has read what it needs from the staged tile: its region now takes the lo parts
         named_bar_sync(3, N_PROD_WARPS * 32);
 #pragma unroll 1
-        for (int r = grp; r < TC_BM; r += N_GROUPS) {
+        for (int r = grp_t; r < TC_BM; r += N_GROUPS) {
           const uint32_t off = sw128_off(r, l8);
           const float4 z0 = *reinterpret_cast<const float4*>(a_hi + off);       // (this thread's own writes)
           const float4 z1 = *reinterpret_cast<const float4*>(a_hi + TC_BM * 128 + off);
@@ -475,18 +512,46 @@ k_gin_layer_fwd(const GinLayerArgs p, const __grid_constant__ CUtensorMap tmx) {
     // the tiles ahead, as coalesced 16-byte cp.async copies (the producers' only dependent global hop left is X)
     // two tiles in flight: the copies of tile i are issued before those of tile i-1 are waited for, and the first
     // CSR entry of the NEXT tile (a dependent global load) is fetched one iteration ahead
+    const bool fold = p.fold_a != nullptr;
     int it = 0;
-    int e0n = 0, e1n = 0;
-    if ((int)blockIdx.x < p.n_tiles) { e0n = __ldg(p.tile_edge_ptr + blockIdx.x); e1n = __ldg(p.tile_edge_ptr + blockIdx.x + 1); }
+    int e0n = 0, e1n = 0, c0n = 0;
+    if ((int)blockIdx.x < p.n_tiles) {
+      e0n = __ldg(p.tile_edge_ptr + blockIdx.x); e1n = __ldg(p.tile_edge_ptr + blockIdx.x + 1);
+      if (fold) c0n = __ldg(p.tile_chunk0 + blockIdx.x);
+    }
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const int st = it % GL_IDX_STAGES;
-      int32_t* rp_s = idx_s + st * (GL_IDX_RP + GL_IDX_CAP);
-      int32_t* col_s = rp_s + GL_IDX_RP;
-      const int e0 = e0n & ~3, e1 = e1n;
+      int32_t* rp_s = idx_s + st * GL_IDX_STAGE;
+      int32_t* meta_s = rp_s + GL_IDX_RP;
+      float* fold_s = reinterpret_cast<float*>(meta_s + GL_IDX_META);
+      int32_t* col_s = meta_s + GL_IDX_META + GL_IDX_FOLD;
+      const int e0 = e0n & ~3, e1 = e1n, chunk0 = c0n;
       const int nxt = tile + gridDim.x;
-      if (nxt < p.n_tiles) { e0n = __ldg(p.tile_edge_ptr + nxt); e1n = __ldg(p.tile_edge_ptr + nxt + 1); }
+      if (nxt < p.n_tiles) {
+        e0n = __ldg(p.tile_edge_ptr + nxt); e1n = __ldg(p.tile_edge_ptr + nxt + 1);
+        if (fold) c0n = __ldg(p.tile_chunk0 + nxt);
+      }
       mbar_wait_relaxed(&idx_empty[st], ((it / GL_IDX_STAGES) & 1) ^ 1);
       const int m0 = tile * TC_BM;
+      if (fold) {
+        // mean and scale of the tile's first two chunks (64 x 16-byte copies), and every row's chunk id
+        for (int j = lane; j < 64; j += 32) {
+          const int which = j >> 5, d = (j >> 4) & 1, q = j & 15;          // which: 0 mean, 1 scale
+          const int ch = min(chunk0 + d, p.S - 1);
+          const float* src = (which ? p.fold_a : p.fold_mean) + (int64_t)ch * p.din + 4 * q;
+          cp_async16(smem_u32(fold_s + (2 * which + d) * GL_D + 4 * q), 4 * q < p.din ? src : p.fold_mean, 4 * q < p.din ? 16u : 0u);
+        }
+        int c = chunk0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int grow = m0 + 4 * lane + j;
+          if (grow < p.rows) {
+            while (grow >= __ldg(p.chunk_row_ptr + c + 1)) ++c;
+          }
+          meta_s[4 * lane + j] = c;
+        }
+        if (lane == 0) meta_s[TC_BM] = chunk0;
+      }
       const int n_rp = min(TC_BM, p.rows - m0) + 1;                       // row pointers of this tile
       for (int j = lane * 4; j < GL_IDX_RP; j += 128) {
         const int left = n_rp - j;
@@ -599,39 +664,40 @@ k_gin_layer_fwd(const GinLayerArgs p, const __grid_constant__ CUtensorMap tmx) {
       if (warp == 0) GL_TRACE(3, it);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-      for (int cb = 0; cb < GL_D; cb += 32) {
-        float v[32];
-        load_acc32(acc1 + (uint32_t)(b * GL_D) + lane_off + (uint32_t)cb, v);
+      for (int cb = 0; cb < GL_D; cb += GL_EC) {
+        float v[GL_EC];
+        load_acc16(acc1 + (uint32_t)(b * GL_D) + lane_off + (uint32_t)cb, v);
         if (p.act_inner == BIGNN_ACT_RELU) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + b1_s[cb + j], 0.f);
+          for (int j = 0; j < GL_EC; ++j) v[j] = fmaxf(v[j] + b1_s[cb + j], 0.f);
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j] + b1_s[cb + j], p.act_inner);
+          for (int j = 0; j < GL_EC; ++j) v[j] = apply_act(v[j] + b1_s[cb + j], p.act_inner);
         }
         uint8_t* hi = a_hi + (cb >> 5) * (TC_BM * 128) + row_off;
         uint8_t* lo = a_lo + (cb >> 5) * (TC_BM * 128) + row_off;
+        const int c0 = (cb & 31) >> 2;                       // first 16-byte chunk of these columns in the 128-byte row
         if (TMEM_A) {
           // t -> tensor memory (this thread's lane = its row): raw fp32 = the TF32 hi operand, then the lo part
-          uint32_t q[32];
+          uint32_t q[GL_EC];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) q[j] = __float_as_uint(v[j]);
-          tmem_st32(tmem_t + (uint32_t)(b * 2 * GL_D) + lane_off + (uint32_t)cb, q);
+          for (int j = 0; j < GL_EC; ++j) q[j] = __float_as_uint(v[j]);
+          tmem_st16(tmem_t + (uint32_t)(b * 2 * GL_D) + lane_off + (uint32_t)cb, q);
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
+          for (int j = 0; j < GL_EC; ++j)
             q[j] = __float_as_uint(v[j] - __uint_as_float(__float_as_uint(v[j]) & 0xffffe000u)) & 0xffffe000u;
-          tmem_st32(tmem_t + (uint32_t)(b * 2 * GL_D) + 64u + lane_off + (uint32_t)cb, q);
+          tmem_st16(tmem_t + (uint32_t)(b * 2 * GL_D) + 64u + lane_off + (uint32_t)cb, q);
           if (p.T) {                                         // kept for the backward: staged for coalesced stores
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-              *reinterpret_cast<float4*>(hi + (uint32_t)((c ^ row7) << 4)) =
+            for (int c = 0; c < GL_EC / 4; ++c)
+              *reinterpret_cast<float4*>(hi + (uint32_t)(((c0 + c) ^ row7) << 4)) =
                   make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
           }
         } else {
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
+          for (int c = 0; c < GL_EC / 4; ++c) {
             const float4 tv = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-            const uint32_t off = (uint32_t)((c ^ row7) << 4);
+            const uint32_t off = (uint32_t)(((c0 + c) ^ row7) << 4);
             *reinterpret_cast<float4*>(hi + off) = tv;
             *reinterpret_cast<uint4*>(lo + off) = lo_part(tv);
           }
@@ -668,6 +734,13 @@ k_gin_layer_fwd(const GinLayerArgs p, const __grid_constant__ CUtensorMap tmx) {
     const int row7 = row & 7;
     const bool store = !(p.dbg & 2);
     const uint32_t lane_off = (uint32_t)(qw * 32) << 16;
+    // the tile's first chunk and where that chunk ends: two dependent global loads, fetched one and two tiles ahead
+    int c_cur = 0, cend_cur = 0, c_nxt = 0;
+    if (p.stat_parts && (int)blockIdx.x < p.n_tiles) {
+      c_cur = __ldg(p.tile_chunk0 + blockIdx.x);
+      cend_cur = __ldg(p.chunk_row_ptr + c_cur + 1);
+      if ((int)(blockIdx.x + gridDim.x) < p.n_tiles) c_nxt = __ldg(p.tile_chunk0 + blockIdx.x + gridDim.x);
+    }
     int it = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const int b = it & 1;
@@ -675,25 +748,32 @@ k_gin_layer_fwd(const GinLayerArgs p, const __grid_constant__ CUtensorMap tmx) {
       const int m0 = tile * TC_BM;
       const int rows_here = min(TC_BM, p.rows - m0);
       const uint8_t* src = a_hi + (c4 >> 3) * (TC_BM * 128);
+      const int chunk_first = c_cur, chunk_first_end = cend_cur;
+      if (p.stat_parts) {                                    // (values used in the next iteration)
+        c_cur = c_nxt;
+        if ((int)(tile + gridDim.x) < p.n_tiles) cend_cur = __ldg(p.chunk_row_ptr + c_nxt + 1);
+        if ((int)(tile + 2 * gridDim.x) < p.n_tiles) c_nxt = __ldg(p.tile_chunk0 + tile + 2 * gridDim.x);
+      }
       mbar_wait(&m2_done[b], (it >> 1) & 1);                // t has been consumed
       if (qw == 0) GL_TRACE(5, it);
       if (p.T) mbar_wait(&t_copied[b], (it >> 1) & 1);      // ... and copied out by E1
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-      for (int cb = 0; cb < GL_D; cb += 32) {
-        float v[32];
-        load_acc32(acc2 + (uint32_t)(b * GL_D) + lane_off + (uint32_t)cb, v);
+      for (int cb = 0; cb < GL_D; cb += GL_EC) {
+        float v[GL_EC];
+        load_acc16(acc2 + (uint32_t)(b * GL_D) + lane_off + (uint32_t)cb, v);
         if (p.act_outer == BIGNN_ACT_RELU) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + b2_s[cb + j], 0.f);
+          for (int j = 0; j < GL_EC; ++j) v[j] = fmaxf(v[j] + b2_s[cb + j], 0.f);
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j] + b2_s[cb + j], p.act_outer);
+          for (int j = 0; j < GL_EC; ++j) v[j] = apply_act(v[j] + b2_s[cb + j], p.act_outer);
         }
         uint8_t* hi = a_hi + (cb >> 5) * (TC_BM * 128) + row_off;
+        const int c0 = (cb & 31) >> 2;
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
-          *reinterpret_cast<float4*>(hi + (uint32_t)((c ^ row7) << 4)) =
+        for (int c = 0; c < GL_EC / 4; ++c)
+          *reinterpret_cast<float4*>(hi + (uint32_t)(((c0 + c) ^ row7) << 4)) =
               make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -704,8 +784,8 @@ k_gin_layer_fwd(const GinLayerArgs p, const __grid_constant__ CUtensorMap tmx) {
       // ---------------- coalesced copy-out (+ BatchNorm partial sums of the stored rows when the tile lies in one chunk)
       int chunk = 0, chunk_end = rows_here;
       if (p.stat_parts) {
-        chunk = __ldg(p.tile_chunk0 + tile);
-        chunk_end = __ldg(p.chunk_row_ptr + chunk + 1) - m0;
+        chunk = chunk_first;
+        chunk_end = chunk_first_end - m0;
       }
       const bool one_chunk = chunk_end >= rows_here;
       // fp64 from the first addition: E[x^2] - mean^2 must survive channels whose mean dwarfs their spread
@@ -858,29 +938,39 @@ extern "C" int bignn_gin_layer_fwd(int32_t rows, int32_t din, int32_t dout, cons
       (T && ((ldt & 3) || !aligned16(T))) || !aligned16(row_ptr) || !aligned16(col_idx) ||
       (fold && (!aligned16(fold_a) || !aligned16(fold_mean) || !aligned16(fold_beta))))
     return BIGNN_EALIGN;
-  constexpr int THREADS = 768;      // 24 warps: 4 + 4 epilogue, MMA, index prefetch, 14 producers = 56 row groups
-  static bool configured = false;
-  static int dbg = 0, stage = 0, tmem_a = 0;
+  // variants (template parameters): threads per CTA (1024 = 32 warps at 64 registers: 4 + 4 epilogue, MMA, index prefetch,
+  // 22 producers = 88 row groups; 768 = 14 producers at 80 registers), TMA staging of X, t in tensor memory, neighbour
+  // rows in flight per producer group
+  typedef void (*Kern)(GinLayerArgs, CUtensorMap);
+  static Kern kern = nullptr;
+  static int threads = 1024;
+  static int dbg = 0;
   static long long* trace_dev = nullptr;
   static const char* trace_path = nullptr;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_gin_layer_fwd<THREADS, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GL_SMEM);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(k_gin_layer_fwd<THREADS, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GL_SMEM);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(k_gin_layer_fwd<THREADS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GL_SMEM);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(k_gin_layer_fwd<THREADS, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GL_SMEM);
+  if (!kern) {
     const char* ta = getenv("BIGNN_GL_TMEM_A");
-    tmem_a = ta ? atoi(ta) : 1;      // default: the second transform reads t from tensor memory
-    if (e != cudaSuccess) return (int)e;
+    const int tmem_a = ta ? atoi(ta) : 1;      // default: the second transform reads t from tensor memory
     const char* sg = getenv("BIGNN_GL_STAGE");
-    stage = sg ? atoi(sg) : 0;
+    const int stage = sg ? atoi(sg) : 0;
+    const char* th = getenv("BIGNN_GL_THREADS");
+    threads = (th && atoi(th) == 768) ? 768 : 1024;
+    const char* us = getenv("BIGNN_GL_U");
+    const int u = us ? atoi(us) : 3;
+    Kern k = nullptr;
+#define GL_PICK(TH, ST, TA, UU) if (threads == TH && stage == ST && tmem_a == TA && u == UU) k = k_gin_layer_fwd<TH, ST, TA, UU>;
+#define GL_PICK_U(TH, TA) GL_PICK(TH, 0, TA, 2) GL_PICK(TH, 0, TA, 3) GL_PICK(TH, 0, TA, 4)
+    GL_PICK_U(1024, 1) GL_PICK_U(1024, 0) GL_PICK_U(768, 1) GL_PICK_U(768, 0)
+    GL_PICK(1024, 1, 1, 2) GL_PICK(1024, 1, 0, 2) GL_PICK(768, 1, 1, 2) GL_PICK(768, 1, 0, 2)
+#undef GL_PICK_U
+#undef GL_PICK
+    if (!k) return BIGNN_EINVAL;               // (an unsupported combination of the BIGNN_GL_* variables)
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, GL_SMEM);
+    if (e != cudaSuccess) return (int)e;
     const char* d = getenv("BIGNN_GL_DEBUG");     // timing experiments only: 1 = no gathers, 2 = no stores (results invalid)
     dbg = d ? atoi(d) : 0;
     trace_path = getenv("BIGNN_GL_TRACE");       // debugging: dump CTA 0's pipeline time stamps of every launch to this file
     if (trace_path && cudaMalloc(&trace_dev, 64 * 16 * sizeof(long long)) != cudaSuccess) trace_dev = nullptr;
-    configured = true;
+    kern = k;
   }
   // TMA descriptor of X: [rows, din_pad] fp32, row pitch ldx, boxes of 32 columns x 128 rows, SWIZZLE_128B; columns and
   // rows outside the tensor read as zeros (the zero padding of the first layer's 49 -> 64 columns comes for free)
@@ -908,7 +998,7 @@ extern "C" int bignn_gin_layer_fwd(int32_t rows, int32_t din, int32_t dout, cons
     if (r != CUDA_SUCCESS) return BIGNN_EINVAL;
   }
   GinLayerArgs a;
-  a.rows = rows; a.din = din; a.n_tiles = ceil_div(rows, TC_BM); a.nnz = nnz; a.dbg = dbg;
+  a.rows = rows; a.din = din; a.n_tiles = ceil_div(rows, TC_BM); a.nnz = nnz; a.dbg = dbg; a.S = S;
   a.row_ptr = row_ptr; a.col_idx = col_idx; a.tile_edge_ptr = tile_edge_ptr; a.X = X; a.ldx = ldx;
   a.fold_mean = fold_mean; a.fold_a = fold_a; a.fold_beta = fold_beta;
   a.chunk_row_ptr = chunk_row_ptr; a.tile_chunk0 = tile_chunk0; a.self_coef = self_coef;
@@ -918,14 +1008,7 @@ extern "C" int bignn_gin_layer_fwd(int32_t rows, int32_t din, int32_t dout, cons
   if (trace_dev) cudaMemsetAsync(trace_dev, 0, 64 * 16 * sizeof(long long), (cudaStream_t)stream);
   int grid = sm_count();
   if (grid > a.n_tiles) grid = a.n_tiles;
-  if (stage && tmem_a)
-    k_gin_layer_fwd<THREADS, true, true><<<grid, THREADS, GL_SMEM, (cudaStream_t)stream>>>(a, tmx);
-  else if (stage)
-    k_gin_layer_fwd<THREADS, true, false><<<grid, THREADS, GL_SMEM, (cudaStream_t)stream>>>(a, tmx);
-  else if (tmem_a)
-    k_gin_layer_fwd<THREADS, false, true><<<grid, THREADS, GL_SMEM, (cudaStream_t)stream>>>(a, tmx);
-  else
-    k_gin_layer_fwd<THREADS, false, false><<<grid, THREADS, GL_SMEM, (cudaStream_t)stream>>>(a, tmx);
+  kern<<<grid, threads, GL_SMEM, (cudaStream_t)stream>>>(a, tmx);
   BIGNN_LAUNCH_COUNT(1);
   if (trace_dev) {                                   // (debug mode only: synchronises)
     static long long host[64 * 16];
