@@ -83,9 +83,20 @@ def test_gradients_match_reference(oracle_step, step_golden):
     z = step_golden
     model = oracle_step[0]
     n = 0
+    # error on the gradient scale of the parameter's LAYER: a bias in front of an identity activation + BatchNorm has a
+    # true gradient of exactly 0 (layers.4 / layers.9 here) and the reference's own value is 1e-8 of rounding noise that
+    # differs from one CPU model to the next -- on its own scale it cannot be compared, on the layer's it is 1e-7
+    scale = {}
+    for k in z.files:
+        if k.startswith('grad/'):
+            lk = '.'.join(k[5:].split('.')[:2])
+            scale[lk] = max(scale.get(lk, 0.0), float(np.abs(z[k]).max()))
     for k, v in model.params().items():
         g = z['grad/' + k]
-        assert rel(v.grad.numpy(), g) < 2e-5, k
+        own = float(np.abs(g).max())
+        lay = scale['.'.join(k.split('.')[:2])]
+        err = float(np.abs(v.grad.numpy().astype(np.float64) - g).max())
+        assert err < 2e-5 * (own if own > 1e-4 * lay else lay), k
         n += 1
     assert n == len([k for k in z.files if k.startswith('grad/')])
 
