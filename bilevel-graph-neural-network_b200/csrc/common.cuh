@@ -35,6 +35,13 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 __device__ __forceinline__ float4 ldg4(const float* p) {
   return __ldg(reinterpret_cast<const float4*>(p));
 }
+// the same without allocating the line in L1 (the fused layer kernel leaves L1 only 28 KB beside its operand slots)
+__device__ __forceinline__ float4 ldg4_na(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
 // streaming 128-bit store: outputs are written once and not re-read by this kernel
 __device__ __forceinline__ void st4(float* p, float4 v) {
   *reinterpret_cast<float4*>(p) = v;

@@ -441,8 +441,13 @@ k_gin_layer_fwd(const GinLayerArgs p, const __grid_constant__ CUtensorMap tmx) {
                   if (ok1) v1[j] = *reinterpret_cast<const float4*>(xs + TC_BM * 128 + o);
                 } else {
                   const float* nj = X + (int64_t)c[j] * ldx;
-                  if (ok0) v0[j] = ldg4(nj);
-                  if (ok1) v1[j] = ldg4(nj + 32);
+                  if (p.dbg & 4) {                                        // (experiment: gathers that bypass L1 allocation)
+                    if (ok0) v0[j] = ldg4_na(nj);
+                    if (ok1) v1[j] = ldg4_na(nj + 32);
+                  } else {
+                    if (ok0) v0[j] = ldg4(nj);
+                    if (ok1) v1[j] = ldg4(nj + 32);
+                  }
                 }
               }
             }
@@ -943,7 +948,7 @@ extern "C" int bignn_gin_layer_fwd(int32_t rows, int32_t din, int32_t dout, cons
   // rows in flight per producer group
   typedef void (*Kern)(GinLayerArgs, CUtensorMap);
   static Kern kern = nullptr;
-  static int threads = 1024;
+  static int threads = 768;
   static int dbg = 0;
   static long long* trace_dev = nullptr;
   static const char* trace_path = nullptr;
@@ -953,13 +958,16 @@ extern "C" int bignn_gin_layer_fwd(int32_t rows, int32_t din, int32_t dout, cons
     const char* sg = getenv("BIGNN_GL_STAGE");
     const int stage = sg ? atoi(sg) : 0;
     const char* th = getenv("BIGNN_GL_THREADS");
-    threads = (th && atoi(th) == 768) ? 768 : 1024;
+    // 768 is the default: measured on B200 at 6 M rows 2.30 ms against 2.57 ms for 1024 threads, whose 64-register budget
+    // makes ptxas spill (72 bytes per thread with three neighbour rows in flight; profiles/r2_summary.md)
+    threads = th ? atoi(th) : 768;
     const char* us = getenv("BIGNN_GL_U");
     const int u = us ? atoi(us) : 3;
     Kern k = nullptr;
 #define GL_PICK(TH, ST, TA, UU) if (threads == TH && stage == ST && tmem_a == TA && u == UU) k = k_gin_layer_fwd<TH, ST, TA, UU>;
 #define GL_PICK_U(TH, TA) GL_PICK(TH, 0, TA, 2) GL_PICK(TH, 0, TA, 3) GL_PICK(TH, 0, TA, 4)
     GL_PICK_U(1024, 1) GL_PICK_U(1024, 0) GL_PICK_U(768, 1) GL_PICK_U(768, 0)
+    GL_PICK(832, 0, 1, 2) GL_PICK(832, 0, 1, 3) GL_PICK(896, 0, 1, 2) GL_PICK(896, 0, 1, 3)
     GL_PICK(1024, 1, 1, 2) GL_PICK(1024, 1, 0, 2) GL_PICK(768, 1, 1, 2) GL_PICK(768, 1, 0, 2)
 #undef GL_PICK_U
 #undef GL_PICK

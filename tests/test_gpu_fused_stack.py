@@ -222,10 +222,24 @@ def test_fused_stack_step_equals_layer_path_and_golden(golden_dir, step_golden, 
             for k, g in self.grads.items():
                 yield k, type('P', (), {'grad': g})()
     rows = report_gradient_errors('gin_gcn_fused_engine', _M(b['grads']), g64, z, scale)
+    # ReLU-mask audit (tools/acc_diag3.py): the fused kernels compute every transform as 3xTF32 on the tensor cores,
+    # the layer path uses fp32 FMA below 8 192 rows; an element whose fp64 pre-activation is below fp32 rounding can
+    # land on the other side of the ReLU (measured on B200: 4 of 2 356 224 outputs of layer 3, |pre-activation| <=
+    # 7.9e-7, none anywhere else), and every gradient at or below that layer then moves by that atom's contribution
+    # (1.5e-3 of the layer scale) -- the reference's own fp32 run is exposed to the same coin flip.  So: no flip may
+    # happen above rounding level, layers above the highest flipped one hold 3x the reference's own fp32 error against
+    # fp64, layers at or below it 2.5e-3.
+    from tools.acc_diag3 import relu_mask_audit
+    data, model = fresh(golden_dir, z)
+    audit = relu_mask_audit(BiGNNEngine(data, model, use_cuda_graph=False, fused_lower=True))
+    top_flip = max([li for li, nt, ny, w in audit if nt + ny] + [-1])
+    assert all(w < 5e-6 for li, nt, ny, w in audit), audit
+    assert sum(nt + ny for li, nt, ny, w in audit) <= 16, audit
     for k, vs_ref, ours, ref in rows:
-        # 3x the reference's own error: a ReLU mask can flip at an element whose pre-activation is at rounding level
-        # (tests/test_gpu_z_ll_gnn_golden.py), which the reference's fp32 run is just as exposed to
-        assert ours <= 3.0 * ref + 1e-5, (k, ours, ref)
+        allow = 3.0 * ref + 1e-5
+        if int(k.split('.')[1]) <= top_flip:
+            allow = max(allow, 2.5e-3)
+        assert ours <= allow, (k, ours, ref, audit)
     for k in a['bufs']:
         assert rel(b['bufs'][k].float(), a['bufs'][k].float()) < 2e-6, k
         if ('sd1/' + k) in z.files and 'running' in k:
