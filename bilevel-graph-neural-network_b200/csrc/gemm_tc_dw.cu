@@ -51,15 +51,13 @@ k_dw_tc_ring(int M, int Np, int Nq, const float* __restrict__ P, int64_t ldp, co
   constexpr int DW_BLK = BM * 128;
   constexpr int DW_TILE = 2 * DW_BLK;
   constexpr int STAGE = 2 * DW_TILE;               // [P][Q]
-  constexpr int NCHUNK = 4 * BM * 8;
-  constexpr int LOG_OP = (BM == 32 ? 9 : (BM == 64 ? 10 : 11));
   static_assert((DW_NA + 1) * DW_F <= 256 && NST >= 3, "two CTAs per SM");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* lo_base = smem + NST * STAGE;           // two lo buffers of STAGE bytes
   __shared__ uint64_t mma_bar[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ double cs_red[4][DW_F];
+  __shared__ double cs_red[16][DW_F];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_tiles = (M + BM - 1) / BM;
@@ -78,19 +76,25 @@ k_dw_tc_ring(int M, int Np, int Nq, const float* __restrict__ P, int64_t ldp, co
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   const uint32_t smem_s = smem_u32(smem);
+  // this thread's four 16-byte chunks of every stage: row pr, chunk pc of the blocks (P | Q) x (features 0-31 | 32-63).
+  // Everything that does not depend on the tile is computed once (ncu, r2: the index arithmetic of the copy loop was a
+  // third of the 375 instructions a warp executed per 32-row tile, at 49 % issue utilisation)
+  static_assert(BM == 32 && TC_THREADS == 256, "chunk mapping: 8 chunks per row, 32 rows, 4 blocks");
+  const int pr = tid >> 3, pc = tid & 7;
+  const uint32_t soff = sw32b_off(pr, pc);
+  const bool colok0 = pc * 4 < Np, colok1 = 32 + pc * 4 < Np, colok2 = pc * 4 < Nq, colok3 = 32 + pc * 4 < Nq;
+  const float* gp = P + (int64_t)pr * ldp + pc * 4;
+  const float* gq = Q + (int64_t)pr * ldq + pc * 4;
   auto prefetch_tile = [&](int i, int stage) {       // i = this CTA's tile index
     const int m0 = ((int)blockIdx.x + i * (int)gridDim.x) * BM;
-    const uint32_t hi_s = smem_s + stage * STAGE;
-#pragma unroll 1
-    for (int j = tid; j < NCHUNK; j += TC_THREADS) {
-      const int op = j >> LOG_OP, idx = j & ((1 << LOG_OP) - 1);
-      const int blk = idx >> (LOG_OP - 1), r = (idx & ((1 << (LOG_OP - 1)) - 1)) >> 3, c = idx & 7;
-      const int gm = m0 + r, gf = blk * 32 + c * 4;
-      const int nf = op ? Nq : Np;
-      const bool ok = gm < M && gf < nf;
-      const float* base = op ? Q + (int64_t)gm * ldq : P + (int64_t)gm * ldp;
-      cp_async16(hi_s + op * DW_TILE + blk * DW_BLK + sw32b_off(r, c), ok ? base + gf : (op ? Q : P), ok ? 16u : 0u);
-    }
+    const uint32_t d = smem_s + stage * STAGE + soff;
+    const bool rowok = m0 + pr < M;
+    const float* sp = gp + (int64_t)m0 * ldp;
+    const float* sq = gq + (int64_t)m0 * ldq;
+    cp_async16(d, (rowok && colok0) ? sp : P, (rowok && colok0) ? 16u : 0u);
+    cp_async16(d + DW_BLK, (rowok && colok1) ? sp + 32 : P, (rowok && colok1) ? 16u : 0u);
+    cp_async16(d + DW_TILE, (rowok && colok2) ? sq : Q, (rowok && colok2) ? 16u : 0u);
+    cp_async16(d + DW_TILE + DW_BLK, (rowok && colok3) ? sq + 32 : Q, (rowok && colok3) ? 16u : 0u);
   };
   // prologue: tiles 0 .. NST-3 in flight, one commit group per tile (empty groups keep the count uniform)
 #pragma unroll
@@ -104,8 +108,12 @@ k_dw_tc_ring(int M, int Np, int Nq, const float* __restrict__ P, int64_t ldp, co
   const uint32_t tmem_d = tmem_base_s;
   const uint32_t idesc = umma_idesc_tf32_mn(DW_MMA_M, DW_F);
 
-  double cs = 0.0;
-  const int cs_col = tid & 63, cs_rg = tid >> 6;
+  // column sums (the bias gradient): thread = (16-byte column group, row group); fp32 over 8 tiles (16 values), then fp64
+  double cs[4] = {0.0, 0.0, 0.0, 0.0};
+  float4 csf = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int cs_cg = tid & 15, cs_rg = tid >> 4;
+  const uint32_t cs_off0 = (cs_cg >> 3) * DW_BLK + sw32b_off(cs_rg, cs_cg & 7);
+  const uint32_t cs_off1 = (cs_cg >> 3) * DW_BLK + sw32b_off(cs_rg + 16, cs_cg & 7);
   uint32_t ph0 = 0, ph1 = 0;
   int ks = 0;
   for (int i = 0; i < my_tiles; ++i) {
@@ -121,11 +129,9 @@ k_dw_tc_ring(int M, int Np, int Nq, const float* __restrict__ P, int64_t ldp, co
     if (i + NST - 2 < my_tiles) prefetch_tile(i + NST - 2, (i + NST - 2) % NST);     // = the stage of tile i-2
     asm volatile("cp.async.commit_group;" ::: "memory");
     // ---- lo = tf32(x - hi(x)) for the chunks this thread copied
-#pragma unroll 4
-    for (int j = tid; j < NCHUNK; j += TC_THREADS) {
-      const int op = j >> LOG_OP, idx = j & ((1 << LOG_OP) - 1);
-      const uint32_t off = op * DW_TILE + (idx >> (LOG_OP - 1)) * DW_BLK +
-                           sw32b_off((idx & ((1 << (LOG_OP - 1)) - 1)) >> 3, idx & 7);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t off = (uint32_t)((k >> 1) * DW_TILE + (k & 1) * DW_BLK) + soff;
       const float4 x = *reinterpret_cast<const float4*>(p_hi + off);
       uint4 l;
       l.x = __float_as_uint(x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u)) & 0xffffe000u;
@@ -153,14 +159,17 @@ k_dw_tc_ring(int M, int Np, int Nq, const float* __restrict__ P, int64_t ldp, co
       ks += BM / 8;
     }
     if (colsum_of >= 0) {                              // from the raw tile, while the tensor core runs
-      const uint8_t* t0 = p_hi + (colsum_of ? DW_TILE : 0) + (cs_col >> 5) * DW_BLK;
-      const int c = (cs_col & 31) >> 2, e = cs_col & 3;
-      float s = 0.f;
-#pragma unroll 4
-      for (int r = cs_rg; r < BM; r += 4) s += *reinterpret_cast<const float*>(t0 + sw32b_off(r, c) + e * 4);
-      cs += (double)s;
+      const uint8_t* t0 = p_hi + (colsum_of ? DW_TILE : 0);
+      const float4 a = *reinterpret_cast<const float4*>(t0 + cs_off0);
+      const float4 b = *reinterpret_cast<const float4*>(t0 + cs_off1);
+      csf.x += a.x + b.x; csf.y += a.y + b.y; csf.z += a.z + b.z; csf.w += a.w + b.w;
+      if ((i & 7) == 7) {
+        cs[0] += (double)csf.x; cs[1] += (double)csf.y; cs[2] += (double)csf.z; cs[3] += (double)csf.w;
+        csf = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
   }
+  cs[0] += (double)csf.x; cs[1] += (double)csf.y; cs[2] += (double)csf.z; cs[3] += (double)csf.w;
   // drain: the MMAs of the last two tiles
   for (int i = (my_tiles >= 2 ? my_tiles - 2 : 0); i < my_tiles; ++i) {
     if ((i & 1) == 0) { mbar_wait(&mma_bar[0], ph0); ph0 ^= 1; } else { mbar_wait(&mma_bar[1], ph1); ph1 ^= 1; }
@@ -203,10 +212,16 @@ k_dw_tc_ring(int M, int Np, int Nq, const float* __restrict__ P, int64_t ldp, co
     }
   }
   if (colsum_of >= 0) {
-    cs_red[cs_rg][cs_col] = cs;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) cs_red[cs_rg][4 * cs_cg + j] = cs[j];
     __syncthreads();
     const int ncs = colsum_of ? Nq : Np;
-    if (tid < ncs) ws_cs[(int64_t)blockIdx.x * ncs + tid] = ((cs_red[0][tid] + cs_red[1][tid]) + cs_red[2][tid]) + cs_red[3][tid];
+    if (tid < ncs) {
+      double t = 0.0;
+#pragma unroll
+      for (int g = 0; g < 16; ++g) t += cs_red[g][tid];
+      ws_cs[(int64_t)blockIdx.x * ncs + tid] = t;
+    }
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -948,7 +948,7 @@ extern "C" int bignn_gin_layer_fwd(int32_t rows, int32_t din, int32_t dout, cons
   // rows in flight per producer group
   typedef void (*Kern)(GinLayerArgs, CUtensorMap);
   static Kern kern = nullptr;
-  static int threads = 768;
+  static int threads = 896;
   static int dbg = 0;
   static long long* trace_dev = nullptr;
   static const char* trace_path = nullptr;
@@ -958,11 +958,12 @@ extern "C" int bignn_gin_layer_fwd(int32_t rows, int32_t din, int32_t dout, cons
     const char* sg = getenv("BIGNN_GL_STAGE");
     const int stage = sg ? atoi(sg) : 0;
     const char* th = getenv("BIGNN_GL_THREADS");
-    // 768 is the default: measured on B200 at 6 M rows 2.30 ms against 2.57 ms for 1024 threads, whose 64-register budget
-    // makes ptxas spill (72 bytes per thread with three neighbour rows in flight; profiles/r2_summary.md)
-    threads = th ? atoi(th) : 768;
+    // 896 threads (18 producer warps, 71 registers, no spills) with two neighbour rows in flight per group is the
+    // default: measured on B200 at 6 M rows, keeping z and t (profiles/r2_summary.md): 896/U2 2.24 ms, 832/U2 2.26,
+    // 768/U2 2.30, 768/U3 2.39, 1024/U2 2.41, 1024/U3 2.57 (64 registers: ptxas spills 72 bytes per thread)
+    threads = th ? atoi(th) : 896;
     const char* us = getenv("BIGNN_GL_U");
-    const int u = us ? atoi(us) : 3;
+    const int u = us ? atoi(us) : 2;
     Kern k = nullptr;
 #define GL_PICK(TH, ST, TA, UU) if (threads == TH && stage == ST && tmem_a == TA && u == UU) k = k_gin_layer_fwd<TH, ST, TA, UU>;
 #define GL_PICK_U(TH, TA) GL_PICK(TH, 0, TA, 2) GL_PICK(TH, 0, TA, 3) GL_PICK(TH, 0, TA, 4)
