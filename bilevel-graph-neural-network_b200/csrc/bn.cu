@@ -9,6 +9,8 @@
 // sequentially in segment order in fp64 (as torch's CPU kernel does) so the 11
 // momentum updates per step of the reference are reproduced.
 // HBM-bound: forward reads X twice (stats, apply) and writes Y once.
+#include <cooperative_groups.h>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace bignn {
@@ -463,6 +465,131 @@ static void launch_bn_apply(int nblk, cudaStream_t st, const float* X, int64_t l
   k_bn_apply<<<grid, 256, 0, st>>>(X, ldx, Y, ldy, seg_row_ptr, C, parts, gamma, beta, mean, rstd, rows);
 }
 
+
+// ---- chunk-resident BatchNorm backward (round 2): ONE thread-block cluster of 4 (or 8) CTAs per segment (chunk).  The two passes
+// of the backward -- the sums (sum dy, sum dy*xhat), then dx -- both walk the chunk's rows of X and dY; as separate
+// grid-wide kernels the second pass finds nothing of a 1.5 GB tensor in the 126 MB L2 (7.7 GB of DRAM traffic per call
+// at 6 M rows x 64).  Here a cluster does both passes back to back on its own chunk: every CTA sums its share of the
+// rows, the CTAs exchange their [2][64] fp64 partials through distributed shared memory (added in rank order:
+// deterministic), and the second pass re-reads rows that were touched microseconds ago.  One CTA per SM (1 024 threads,
+// the dynamic shared-memory request keeps a second one out), so at most 148 / 4 chunks (2 MB of X + dY each; dX leaves with streaming stores) are in
+// flight and the re-reads hit L2: DRAM traffic = X + dY + dX once each.  C = 64 only (the path's channel width).
+namespace cg = cooperative_groups;
+constexpr int BNC_C = 64;
+// (shared-memory request: 1 024-thread CTAs one per SM, 512-thread CTAs two per SM)
+constexpr int bnc_smem(int threads) { return threads >= 1024 ? 120 * 1024 : 100 * 1024; }
+
+template <int IN_ACT, int BNC_THREADS, int BNC_CL>
+__global__ void __cluster_dims__(BNC_CL, 1, 1) __launch_bounds__(BNC_THREADS, BNC_THREADS >= 1024 ? 1 : 2)
+k_bn_bwd_chunk(const float* __restrict__ X, int64_t ldx, const float* __restrict__ dY, int64_t lddy,
+               float* __restrict__ dX, int64_t lddx, const int32_t* __restrict__ seg_row_ptr,
+               const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
+               double* __restrict__ seg_a, double* __restrict__ seg_b) {
+  constexpr int BNC_RPB = BNC_THREADS / 16, BNC_WARPS = BNC_THREADS / 32;
+  extern __shared__ double bnc_sm[];
+  double* red = bnc_sm;                              // [2][BNC_WARPS][64]
+  double* cta_sum = red + 2 * BNC_WARPS * BNC_C;     // [2][64]  (read by the other CTAs of the cluster)
+  double* tot = cta_sum + 2 * BNC_C;                 // [2][64]
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned rank = cluster.block_rank();
+  const int s = blockIdx.x / BNC_CL;
+  const int lane16 = threadIdx.x & 15, ty = threadIdx.x >> 4, warp = threadIdx.x >> 5;
+  const int c = 4 * lane16;
+  const int ra = seg_row_ptr[s], n = seg_row_ptr[s + 1] - ra;
+  const int r0 = ra + (int)(((int64_t)n * rank) / BNC_CL), r1 = ra + (int)(((int64_t)n * (rank + 1)) / BNC_CL);
+  const float4 mu = ldg4(mean + (int64_t)s * BNC_C + c), rs = ldg4(rstd + (int64_t)s * BNC_C + c);
+  // ---- pass 1: this CTA's rows (same per-element formulas as k_bn_reduce_part_v4<true>)
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+#pragma unroll 4
+  for (int r = r0 + ty; r < r1; r += BNC_RPB) {
+    const float4 x = ldg4(X + (int64_t)r * ldx + c);
+    const float4 g = ldg4(dY + (int64_t)r * lddy + c);
+    a0 += (double)g.x; a1 += (double)g.y; a2 += (double)g.z; a3 += (double)g.w;
+    b0 += (double)g.x * (double)((x.x - mu.x) * rs.x); b1 += (double)g.y * (double)((x.y - mu.y) * rs.y);
+    b2 += (double)g.z * (double)((x.z - mu.z) * rs.z); b3 += (double)g.w * (double)((x.w - mu.w) * rs.w);
+  }
+  // the two row groups of a warp (lanes l and l + 16 own the same channels), then the warps in order, then the CTAs
+  a0 += __shfl_down_sync(0xffffffffu, a0, 16); a1 += __shfl_down_sync(0xffffffffu, a1, 16);
+  a2 += __shfl_down_sync(0xffffffffu, a2, 16); a3 += __shfl_down_sync(0xffffffffu, a3, 16);
+  b0 += __shfl_down_sync(0xffffffffu, b0, 16); b1 += __shfl_down_sync(0xffffffffu, b1, 16);
+  b2 += __shfl_down_sync(0xffffffffu, b2, 16); b3 += __shfl_down_sync(0xffffffffu, b3, 16);
+  if ((threadIdx.x & 31) < 16) {
+    double* pa = red + (int64_t)warp * BNC_C + c;
+    double* pb = red + (int64_t)(BNC_WARPS + warp) * BNC_C + c;
+    pa[0] = a0; pa[1] = a1; pa[2] = a2; pa[3] = a3;
+    pb[0] = b0; pb[1] = b1; pb[2] = b2; pb[3] = b3;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * BNC_C) {
+    const int which = threadIdx.x >> 6, ch = threadIdx.x & 63;
+    double t = 0.0;
+#pragma unroll 8
+    for (int w = 0; w < BNC_WARPS; ++w) t += red[(int64_t)(which * BNC_WARPS + w) * BNC_C + ch];
+    cta_sum[threadIdx.x] = t;
+  }
+  cluster.sync();
+  if (threadIdx.x < 2 * BNC_C) {
+    double t = 0.0;
+#pragma unroll
+    for (unsigned q = 0; q < (unsigned)BNC_CL; ++q) t += *cluster.map_shared_rank(cta_sum + threadIdx.x, q);
+    tot[threadIdx.x] = t;
+    if (rank == 0) (threadIdx.x < BNC_C ? seg_a : seg_b)[(int64_t)s * BNC_C + (threadIdx.x & 63)] = t;
+  }
+  cluster.sync();                    // every remote read of cta_sum is done (a CTA may exit now); tot is visible
+  if (n <= 0) return;
+  // ---- pass 2: dx of the same rows (L2 hits)
+  const double cnt = (double)n;
+  const float4 ga = gamma ? ldg4(gamma + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+  const float4 gm = make_float4((float)(tot[c] / cnt), (float)(tot[c + 1] / cnt), (float)(tot[c + 2] / cnt),
+                                (float)(tot[c + 3] / cnt));
+  const float4 dg = make_float4((float)(tot[BNC_C + c] / cnt), (float)(tot[BNC_C + c + 1] / cnt),
+                                (float)(tot[BNC_C + c + 2] / cnt), (float)(tot[BNC_C + c + 3] / cnt));
+  const float4 sc = make_float4(rs.x * ga.x, rs.y * ga.y, rs.z * ga.z, rs.w * ga.w);
+#pragma unroll 4
+  for (int r = r0 + ty; r < r1; r += BNC_RPB) {
+    const float4 x = __ldcs(reinterpret_cast<const float4*>(X + (int64_t)r * ldx + c));      // last use: evict first
+    const float4 g = __ldcs(reinterpret_cast<const float4*>(dY + (int64_t)r * lddy + c));
+    __stcs(reinterpret_cast<float4*>(dX + (int64_t)r * lddx + c),      // streaming: must not push the chunks in flight out of L2
+        make_float4(bn_bwd_one<IN_ACT>(x.x, g.x, mu.x, rs.x, gm.x, dg.x, sc.x),
+                    bn_bwd_one<IN_ACT>(x.y, g.y, mu.y, rs.y, gm.y, dg.y, sc.y),
+                    bn_bwd_one<IN_ACT>(x.z, g.z, mu.z, rs.z, gm.z, dg.z, sc.z),
+                    bn_bwd_one<IN_ACT>(x.w, g.w, mu.w, rs.w, gm.w, dg.w, sc.w)));
+  }
+}
+
+template <int IN_ACT, int THREADS, int CL>
+static cudaError_t launch_bn_bwd_chunk_v(cudaStream_t st, int S, const float* X, int64_t ldx, const float* dY, int64_t lddy,
+                                         float* dX, int64_t lddx, const int32_t* seg_row_ptr, const float* gamma,
+                                         const float* mean, const float* rstd, double* seg_a, double* seg_b) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_bn_bwd_chunk<IN_ACT, THREADS, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         bnc_smem(THREADS));
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  k_bn_bwd_chunk<IN_ACT, THREADS, CL><<<S * CL, THREADS, bnc_smem(THREADS), st>>>(X, ldx, dY, lddy, dX, lddx, seg_row_ptr,
+                                                                                 gamma, mean, rstd, seg_a, seg_b);
+  return cudaSuccess;
+}
+
+template <int IN_ACT>
+static cudaError_t launch_bn_bwd_chunk(cudaStream_t st, int S, const float* X, int64_t ldx, const float* dY, int64_t lddy,
+                                       float* dX, int64_t lddx, const int32_t* seg_row_ptr, const float* gamma,
+                                       const float* mean, const float* rstd, double* seg_a, double* seg_b) {
+  // 1 024-thread CTAs (one per SM), four per chunk: 37 chunks x (X + dY = 2 MB) in flight.  Measured on B200 at 6 M rows /
+  // 1 562 chunks (profiles/r2_summary.md): 1.11 ms against 1.39 ms for the two grid-wide passes; 8 CTAs per chunk 1.32 ms
+  // (15 clusters fit = 120 of 148 SMs), 512-thread CTAs two per SM x 8 per chunk 1.19 ms, x 4 per chunk 1.37 ms (74
+  // chunks in flight no longer fit in L2).  BIGNN_BN_CL_VARIANT selects the others.
+  const char* v = getenv("BIGNN_BN_CL_VARIANT");
+  switch (v ? atoi(v) : 2) {
+    case 0: return launch_bn_bwd_chunk_v<IN_ACT, 1024, 8>(st, S, X, ldx, dY, lddy, dX, lddx, seg_row_ptr, gamma, mean, rstd, seg_a, seg_b);
+    case 1: return launch_bn_bwd_chunk_v<IN_ACT, 512, 8>(st, S, X, ldx, dY, lddy, dX, lddx, seg_row_ptr, gamma, mean, rstd, seg_a, seg_b);
+    case 3: return launch_bn_bwd_chunk_v<IN_ACT, 512, 4>(st, S, X, ldx, dY, lddy, dX, lddx, seg_row_ptr, gamma, mean, rstd, seg_a, seg_b);
+    default: return launch_bn_bwd_chunk_v<IN_ACT, 1024, 4>(st, S, X, ldx, dY, lddy, dX, lddx, seg_row_ptr, gamma, mean, rstd, seg_a, seg_b);
+  }
+}
+
 static void launch_bn_bwd_apply(dim3 grid, cudaStream_t st, int in_act, const float* X, int64_t ldx, const float* dY,
                                 int64_t lddy, float* dX, int64_t lddx, const int32_t* seg_row_ptr, int C, int parts,
                                 const float* gamma, const float* mean, const float* rstd, const double* seg_a,
@@ -572,6 +699,23 @@ extern "C" int bignn_bn_seg_bwd(const float* X, int64_t ldx, const float* dY, in
   double* seg_a = ws_b + (int64_t)S * parts * C;
   double* seg_b = seg_a + (int64_t)S * C;
   dim3 grid(S * parts, ceil_div(C, 32));
+  // many chunks of 64 channels (the lower level of an all-drug pass): one cluster per chunk does both passes while the
+  // chunk is in L2 (BIGNN_BN_CLUSTER=0: the two grid-wide passes below)
+  const char* cl = getenv("BIGNN_BN_CLUSTER");
+  if (C == BNC_C && S >= 24 && (int64_t)S * 8 <= 2147483647LL && !(cl && atoi(cl) == 0) &&
+      bn_tpr(C, X, ldx, dY, lddy, dX, lddx) > 0 && aligned16(mean) && aligned16(rstd) && (!gamma || aligned16(gamma))) {
+    cudaError_t e;
+    switch (input_act) {
+      case BIGNN_ACT_RELU: e = launch_bn_bwd_chunk<BIGNN_ACT_RELU>(st, S, X, ldx, dY, lddy, dX, lddx, seg_row_ptr, gamma, mean, rstd, seg_a, seg_b); break;
+      case BIGNN_ACT_SIGMOID: e = launch_bn_bwd_chunk<BIGNN_ACT_SIGMOID>(st, S, X, ldx, dY, lddy, dX, lddx, seg_row_ptr, gamma, mean, rstd, seg_a, seg_b); break;
+      case BIGNN_ACT_TANH: e = launch_bn_bwd_chunk<BIGNN_ACT_TANH>(st, S, X, ldx, dY, lddy, dX, lddx, seg_row_ptr, gamma, mean, rstd, seg_a, seg_b); break;
+      default: e = launch_bn_bwd_chunk<BIGNN_ACT_IDENTITY>(st, S, X, ldx, dY, lddy, dX, lddx, seg_row_ptr, gamma, mean, rstd, seg_a, seg_b);
+    }
+    if (e != cudaSuccess) return (int)e;
+    k_bn_bwd_params<<<ceil_div(C, 32), 1024, 0, st>>>(seg_a, seg_b, S, C, dgamma, dbeta);
+    BIGNN_LAUNCH_COUNT(2);
+    return last_launch_status();
+  }
   launch_bn_reduce(true, S * parts, st, X, ldx, dY, lddy, seg_row_ptr, C, parts, mean, rstd, ws_a, ws_b, 0);
   k_bn_bwd_finalize<<<dim3(S, ceil_div(C, 32)), 32 * BN_FIN_SL, 0, st>>>(ws_a, ws_b, S, C, parts, seg_a, seg_b);
   k_bn_bwd_params<<<ceil_div(C, 32), 1024, 0, st>>>(seg_a, seg_b, S, C, dgamma, dbeta);

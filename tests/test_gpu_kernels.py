@@ -352,6 +352,48 @@ def test_seg_batch_norm_vs_torch(sizes, C):
     assert rel(ops.bn_eval(x.to(DEV), gd.detach(), bd.detach(), rm, rv), bn(x.double())) < 2e-6
 
 
+@pytest.mark.parametrize('act', ['identity', 'relu'])
+def test_seg_batch_norm_backward_cluster_path(act, monkeypatch):
+    """many ragged chunks x 64 channels: the chunk-resident backward (one 8-CTA cluster per chunk, both passes while the
+    chunk is in L2; bignn_bn_seg_bwd takes it from 24 chunks on) against the two grid-wide passes and against torch."""
+    g = torch.Generator().manual_seed(77)
+    sizes = [int(v) for v in torch.randint(2, 4200, (61,), generator=g)] + [3, 9, 4097]
+    n, C, S = sum(sizes), 64, len(sizes)
+    x = (torch.randn(n, C, generator=g) * 2 + 1)
+    if act == 'relu':
+        x = x.relu()
+    gamma = torch.rand(C, generator=g) + 0.5
+    beta = torch.randn(C, generator=g)
+    dy = torch.randn(n, C, generator=g)
+    ptr = np.concatenate([[0], np.cumsum(sizes)])
+    bn = torch.nn.BatchNorm1d(C).double()
+    with torch.no_grad():
+        bn.weight.copy_(gamma)
+        bn.bias.copy_(beta)
+    xr = x.double().requires_grad_(True)
+    want = torch.cat([bn(xr[ptr[i]:ptr[i + 1]]) for i in range(S)])
+    want.backward(dy.double())
+    want_dx = xr.grad * (x > 0).double() if act == 'relu' else xr.grad      # input_act: derivative of the producer's ReLU
+    seg = torch.as_tensor(ptr.astype(np.int32)).to(DEV)
+    res = {}
+    for mode in ('1', '0'):
+        monkeypatch.setenv('BIGNN_BN_CLUSTER', mode)
+        xd = x.to(DEV).requires_grad_(True)
+        gd = gamma.to(DEV).requires_grad_(True)
+        bd = beta.to(DEV).requires_grad_(True)
+        n0 = B._lib.launch_count()
+        got = ops.seg_batch_norm(xd, gd, bd, seg, S, torch.zeros(C, device=DEV), torch.ones(C, device=DEV),
+                                 torch.zeros((), dtype=torch.int64, device=DEV), 1e-5, 0.1, None, ops.ACT_CODES[act])
+        n1 = B._lib.launch_count()
+        got.backward(dy.to(DEV))
+        res[mode] = (xd.grad.clone(), gd.grad.clone(), bd.grad.clone(), B._lib.launch_count() - n1)
+        assert rel(xd.grad, want_dx) < 2e-5
+        assert rel(gd.grad, bn.weight.grad) < 5e-6 and rel(bd.grad, bn.bias.grad) < 5e-6
+    assert res['1'][3] == 2 and res['0'][3] == 4            # cluster path: chunk kernel + parameter gradients
+    assert rel(res['1'][0], res['0'][0]) < 1e-6
+    assert rel(res['1'][1], res['0'][1]) < 1e-6 and rel(res['1'][2], res['0'][2]) < 1e-6
+
+
 # ----------------------------------------------------------------------------- readout
 @pytest.mark.parametrize('style', ['avg_pool', 'sum'])
 @pytest.mark.parametrize('D', [64, 49])
