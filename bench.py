@@ -571,19 +571,37 @@ def kernel_profile(torch, B, eng, steps=3, on_start=None):
                 note='eager pass with CUDA events around every C-ABI call (not the CUDA-graph replay that `value` times)')
 
 
+# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) over the algorithmic bytes of the same launch, from
+# the committed `ncu --set full` captures (profiles/r2_summary.md); a run without a profiler cannot read DRAM counters, so
+# `roofline.traffic` = this measured ratio x the algorithmic bytes of the launch being reported
+NCU_TRAFFIC = [
+    ('bignn_gin_layer_fwd[rows=6', 0.999,
+     'profiles/r2_summary.md: ncu --set full of k_gin_layer_fwd<896,..> at 6 000 245 rows x 64 keeping z and t: dram read '
+     '1.612 GB + write 4.602 GB = 6.214 GB = 0.999 x algorithmic; scaled to this launch'),
+    ('bignn_dw_tc_f32[M=6', 1.003,
+     'profiles/r2_summary.md: ncu --set full of k_dw_tc_ring at 6 000 000 rows: dram read 3.073 GB + write 0.009 GB = '
+     '1.003 x algorithmic; scaled to this launch'),
+]
+
+
 def step_roofline(prof, peaks):
     """`roofline` of the dominant kernel of the TIMED step: the C-ABI entry with the largest share of the step's device
     time; achieved = its algorithmic bytes per call / its average call duration (CUDA events in the eager pass)."""
     peak = peaks.get('hbm_gbs', 6650.0)
     for e in prof.get('top', []):
         if 'achieved_gbs' in e:
+            traffic, src = None, ('dram bytes of this kernel: see the ncu --set full summary under profiles/ '
+                                  '(not measurable inside an un-profiled run)')
+            for prefix, ratio, cite in NCU_TRAFFIC:
+                if e['entry'].startswith(prefix):
+                    traffic = ratio * e['algorithmic_bytes_per_call']
+                    src = cite
             return dict(kernel=e['entry'], bound='hbm', achieved=e['achieved_gbs'], peak=peak, unit='GB/s',
-                        frac=round(e['achieved_gbs'] / peak, 4), traffic=None, share_of_step=e['share'],
+                        frac=round(e['achieved_gbs'] / peak, 4), traffic=traffic, share_of_step=e['share'],
                         ms_per_launch=e['ms_per_call'], algorithmic_bytes=e['algorithmic_bytes_per_call'],
                         peak_source='MEASURED_PEAKS.json hbm_gbs (measured copy peak)' if 'hbm_gbs' in peaks
                         else 'fallback 6650 GB/s',
-                        traffic_note='dram bytes of this kernel: see the ncu --set full summary under profiles/ '
-                                     '(not measurable inside an un-profiled run)')
+                        traffic_note=src)
     return None
 
 

@@ -261,9 +261,15 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_acc, const uint8_t* a_h
 // TMEM_A: the hidden activations t go from E1 straight into TENSOR MEMORY (tcgen05.st) and the second transform reads
 // its A operand there (tcgen05.mma [d], [a_tmem], b_desc): per tile 64 KB of shared-memory writes and 96 KB of
 // shared-memory operand reads less (BIGNN_GL_TMEM_A=0 selects the all-shared-memory variant).
-template <int THREADS, bool STAGE_X, bool TMEM_A, int GL_U>
+// EARLY (round 2, default with TMEM_A): the slot's hi region -- the z operand -- is given back to the producers as soon as the
+// FIRST transform has read it (its tcgen05.commit), not when E2 has copied y out: t lives in tensor memory, and T / Y are
+// staged for their coalesced copy-out in the slot's LO region.  The producers gather the rows of tile i+2 while E1 / E2
+// still work on tile i, and derive the lo parts (shared memory -> shared memory, their own writes) only once E2 has let
+// go of the lo region.  Before, a slot was held for gather + both epilogues (12.9 us per two tiles, profiles/r2_summary.md).
+template <int THREADS, bool STAGE_X, bool TMEM_A, int GL_U, bool EARLY>
 __global__ void __launch_bounds__(THREADS, 1)
 k_gin_layer_fwd(const GinLayerArgs p, const __grid_constant__ CUtensorMap tmx) {
+  static_assert(!EARLY || (TMEM_A && !STAGE_X), "EARLY needs t in tensor memory and no TMA staging in the lo region");
   constexpr int N_WARPS = THREADS / 32;
   // warps 0-3: epilogue of the first transform (E1), 4-7: epilogue of the second (E2), 8: MMA issuer,
   // 9: index prefetch, 10..: producers
@@ -373,7 +379,14 @@ k_gin_layer_fwd(const GinLayerArgs p, const __grid_constant__ CUtensorMap tmx) {
         if (warp == FIRST_PROD) GL_TRACE(14, it);
         mbar_wait_relaxed(&x_full[b], (it >> 1) & 1);      // the tile's rows of X are staged in the slot's lo region
       }
-      mbar_wait_relaxed(&z_empty[b], ((it >> 1) & 1) ^ 1);   // E2 has stored the tile that used the slot's hi region
+      if (EARLY) {
+        if (it >= 2) {                                       // the first transform of tile it-2 has read the hi region
+          mbar_wait_relaxed(&m1_done[b], ((it - 2) >> 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+      } else {
+        mbar_wait_relaxed(&z_empty[b], ((it >> 1) & 1) ^ 1); // E2 has stored the tile that used the slot's hi region
+      }
       if (warp == FIRST_PROD) GL_TRACE(0, it);
       uint8_t* a_hi = smem + b * GL_SLOT;
       uint8_t* a_lo = a_hi + 2 * TC_BM * 128;
@@ -483,7 +496,7 @@ k_gin_layer_fwd(const GinLayerArgs p, const __grid_constant__ CUtensorMap tmx) {
         const uint32_t off = sw128_off(r, l8);
         *reinterpret_cast<float4*>(a_hi + off) = z0;                          // raw fp32 = the TF32 hi operand
         *reinterpret_cast<float4*>(a_hi + TC_BM * 128 + off) = z1;
-        if (!STAGE_X) {
+        if (!STAGE_X && !EARLY) {
           *reinterpret_cast<uint4*>(a_lo + off) = lo_part(z0);
           *reinterpret_cast<uint4*>(a_lo + TC_BM * 128 + off) = lo_part(z1);
         }
@@ -498,6 +511,18 @@ k_gin_layer_fwd(const GinLayerArgs p, const __grid_constant__ CUtensorMap tmx) {
       if (STAGE_X) {
         // every producer has read what it needs from the staged tile: its region now takes the lo parts
         named_bar_sync(3, N_PROD_WARPS * 32);
+#pragma unroll 1
+        for (int r = grp_t; r < TC_BM; r += N_GROUPS) {
+          const uint32_t off = sw128_off(r, l8);
+          const float4 z0 = *reinterpret_cast<const float4*>(a_hi + off);       // (this thread's own writes)
+          const float4 z1 = *reinterpret_cast<const float4*>(a_hi + TC_BM * 128 + off);
+          *reinterpret_cast<uint4*>(a_lo + off) = lo_part(z0);
+          *reinterpret_cast<uint4*>(a_lo + TC_BM * 128 + off) = lo_part(z1);
+        }
+      }
+      if (EARLY) {
+        // the lo region is E1's / E2's staging buffer until E2 has copied tile it-2 out
+        mbar_wait_relaxed(&z_empty[b], ((it >> 1) & 1) ^ 1);
 #pragma unroll 1
         for (int r = grp_t; r < TC_BM; r += N_GROUPS) {
           const uint32_t off = sw128_off(r, l8);
@@ -663,7 +688,8 @@ k_gin_layer_fwd(const GinLayerArgs p, const __grid_constant__ CUtensorMap tmx) {
       uint8_t* a_lo = a_hi + 2 * TC_BM * 128;
       const int m0 = tile * TC_BM;
       const int rows_here = min(TC_BM, p.rows - m0);
-      const uint8_t* src = a_hi + (c4 >> 3) * (TC_BM * 128);
+      uint8_t* stg = EARLY ? a_lo : a_hi;                   // where T is staged for its coalesced copy-out
+      const uint8_t* src = stg + (c4 >> 3) * (TC_BM * 128);
       mbar_wait(&m1_done[b], (it >> 1) & 1);
       if (TMEM_A && it >= 2) mbar_wait(&m2_done[b], ((it - 2) >> 1) & 1);   // t[b] of tile it-2 has been consumed
       if (warp == 0) GL_TRACE(3, it);
@@ -679,7 +705,7 @@ k_gin_layer_fwd(const GinLayerArgs p, const __grid_constant__ CUtensorMap tmx) {
 #pragma unroll
           for (int j = 0; j < GL_EC; ++j) v[j] = apply_act(v[j] + b1_s[cb + j], p.act_inner);
         }
-        uint8_t* hi = a_hi + (cb >> 5) * (TC_BM * 128) + row_off;
+        uint8_t* hi = (TMEM_A ? stg : a_hi) + (cb >> 5) * (TC_BM * 128) + row_off;
         uint8_t* lo = a_lo + (cb >> 5) * (TC_BM * 128) + row_off;
         const int c0 = (cb & 31) >> 2;                       // first 16-byte chunk of these columns in the 128-byte row
         if (TMEM_A) {
@@ -752,7 +778,8 @@ k_gin_layer_fwd(const GinLayerArgs p, const __grid_constant__ CUtensorMap tmx) {
       uint8_t* a_hi = smem + b * GL_SLOT;
       const int m0 = tile * TC_BM;
       const int rows_here = min(TC_BM, p.rows - m0);
-      const uint8_t* src = a_hi + (c4 >> 3) * (TC_BM * 128);
+      uint8_t* stg = EARLY ? a_hi + 2 * TC_BM * 128 : a_hi;  // where y is staged (EARLY: the slot's lo region)
+      const uint8_t* src = stg + (c4 >> 3) * (TC_BM * 128);
       const int chunk_first = c_cur, chunk_first_end = cend_cur;
       if (p.stat_parts) {                                    // (values used in the next iteration)
         c_cur = c_nxt;
@@ -774,7 +801,7 @@ k_gin_layer_fwd(const GinLayerArgs p, const __grid_constant__ CUtensorMap tmx) {
 #pragma unroll
           for (int j = 0; j < GL_EC; ++j) v[j] = apply_act(v[j] + b2_s[cb + j], p.act_outer);
         }
-        uint8_t* hi = a_hi + (cb >> 5) * (TC_BM * 128) + row_off;
+        uint8_t* hi = stg + (cb >> 5) * (TC_BM * 128) + row_off;
         const int c0 = (cb & 31) >> 2;
 #pragma unroll
         for (int c = 0; c < GL_EC / 4; ++c)
@@ -965,7 +992,11 @@ extern "C" int bignn_gin_layer_fwd(int32_t rows, int32_t din, int32_t dout, cons
     const char* us = getenv("BIGNN_GL_U");
     const int u = us ? atoi(us) : 2;
     Kern k = nullptr;
-#define GL_PICK(TH, ST, TA, UU) if (threads == TH && stage == ST && tmem_a == TA && u == UU) k = k_gin_layer_fwd<TH, ST, TA, UU>;
+    const char* ea = getenv("BIGNN_GL_EARLY");
+    const int early = (ea ? atoi(ea) : 1) && tmem_a && !stage;
+#define GL_PICK(TH, ST, TA, UU) \
+    if (threads == TH && stage == ST && tmem_a == TA && u == UU) \
+      k = early ? k_gin_layer_fwd<TH, ST, TA, UU, (TA && !ST)> : k_gin_layer_fwd<TH, ST, TA, UU, false>;
     // the measured variants (profiles/r2_summary.md); everything else lost and is not compiled
     GL_PICK(896, 0, 1, 2) GL_PICK(832, 0, 1, 2) GL_PICK(768, 0, 1, 2) GL_PICK(768, 0, 1, 3) GL_PICK(1024, 0, 1, 3)
     GL_PICK(768, 0, 0, 2) GL_PICK(768, 1, 1, 2)
