@@ -266,10 +266,16 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_acc, const uint8_t* a_h
 // staged for their coalesced copy-out in the slot's LO region.  The producers gather the rows of tile i+2 while E1 / E2
 // still work on tile i, and derive the lo parts (shared memory -> shared memory, their own writes) only once E2 has let
 // go of the lo region.  Before, a slot was held for gather + both epilogues (12.9 us per two tiles, profiles/r2_summary.md).
-template <int THREADS, bool STAGE_X, bool TMEM_A, int GL_U, bool EARLY>
+// LEAN (round 2): the producers' row loop written for the common case (64 input columns, no debug switches): every load
+// is unconditional (a missing second neighbour reads the row itself again, an L1 hit, and is dropped by a predicated
+// add), no column predicates.  The general loop executes ~490 mostly dependent instructions per row iteration, which --
+// not the DRAM latency behind it -- is what a producer warp spends its 2.1 us per iteration on (an L2 prefetch of the
+// next rows changed nothing, more code made it slower; profiles/r2_summary.md).  Same arithmetic in the same order.
+template <int THREADS, bool STAGE_X, bool TMEM_A, int GL_U, bool EARLY, bool LEAN>
 __global__ void __launch_bounds__(THREADS, 1)
 k_gin_layer_fwd(const GinLayerArgs p, const __grid_constant__ CUtensorMap tmx) {
   static_assert(!EARLY || (TMEM_A && !STAGE_X), "EARLY needs t in tensor memory and no TMA staging in the lo region");
+  static_assert(!LEAN || !STAGE_X, "LEAN gathers from global memory");
   constexpr int N_WARPS = THREADS / 32;
   // warps 0-3: epilogue of the first transform (E1), 4-7: epilogue of the second (E2), 8: MMA issuer,
   // 9: index prefetch, 10..: producers
@@ -397,6 +403,75 @@ k_gin_layer_fwd(const GinLayerArgs p, const __grid_constant__ CUtensorMap tmx) {
       // 128 rows over N_GROUPS (56) groups = two or three rows per group: which groups take three rotates from tile to
       // tile, so that no warp is the slow one on every tile (the slots let a warp run one tile ahead)
       const int grp_t = (grp + it * (TC_BM % N_GROUPS)) % N_GROUPS;
+      if (LEAN) {
+#pragma unroll 1
+        for (int r = grp_t; r < TC_BM; r += N_GROUPS) {
+          const int grow = m0 + r;
+          float4 z0 = f4z(), z1 = f4z();
+          if (grow < p.rows) {
+            const int k0 = rp_s[r], k1 = rp_s[r + 1];
+            const float* xr = X + (int64_t)grow * ldx;
+            float4 s0 = ldg4(xr), s1 = ldg4(xr + 32);
+            float4 mu0 = f4z(), mu1 = f4z(), fa0 = f4z(), fa1 = f4z();       // (no fold: v - 0 = v exactly)
+            if (fold) {
+              const int chunk = meta_s[r];
+              const int cslot = chunk - meta_s[TC_BM];
+              if (cslot < 2) {
+                const float* fm = fold_s + cslot * GL_D + 4 * l8;
+                mu0 = *reinterpret_cast<const float4*>(fm);
+                mu1 = *reinterpret_cast<const float4*>(fm + 32);
+                fa0 = *reinterpret_cast<const float4*>(fm + 2 * GL_D);
+                fa1 = *reinterpret_cast<const float4*>(fm + 2 * GL_D + 32);
+              } else {                                            // (a tile that spans more than two chunks)
+                const float* fm = p.fold_mean + (int64_t)chunk * p.din + 4 * l8;
+                const float* fa = p.fold_a + (int64_t)chunk * p.din + 4 * l8;
+                mu0 = ldg4(fm); mu1 = ldg4(fm + 32);
+                fa0 = ldg4(fa); fa1 = ldg4(fa + 32);
+              }
+            }
+            float4 a0 = f4z(), a1 = f4z();
+            int cnt = 0;
+            for (int k = k0; k < k1; k += 2) {                    // ascending neighbour order, two rows in flight
+              const int ia = k - e_lo;
+              const int ca = ia < GL_IDX_CAP ? col_s[ia] : __ldg(p.col_idx + k);
+              int cb = grow;                                      // no second neighbour: the row itself, dropped below
+              if (k + 1 < k1) cb = ia + 1 < GL_IDX_CAP ? col_s[ia + 1] : __ldg(p.col_idx + k + 1);
+              const float* pa = X + (int64_t)ca * ldx;
+              const float* pb = X + (int64_t)cb * ldx;
+              const float4 va0 = ldg4(pa), va1 = ldg4(pa + 32), vb0 = ldg4(pb), vb1 = ldg4(pb + 32);
+              if (ca != grow) { add4(a0, sub4(va0, mu0)); add4(a1, sub4(va1, mu1)); ++cnt; }   // remove_self_loops
+              if (cb != grow) { add4(a0, sub4(vb0, mu0)); add4(a1, sub4(vb1, mu1)); ++cnt; }
+            }
+            s0 = sub4(s0, mu0); s1 = sub4(s1, mu1);
+            z0.x = __fadd_rn(__fmul_rn(sc, s0.x), a0.x); z0.y = __fadd_rn(__fmul_rn(sc, s0.y), a0.y);
+            z0.z = __fadd_rn(__fmul_rn(sc, s0.z), a0.z); z0.w = __fadd_rn(__fmul_rn(sc, s0.w), a0.w);
+            z1.x = __fadd_rn(__fmul_rn(sc, s1.x), a1.x); z1.y = __fadd_rn(__fmul_rn(sc, s1.y), a1.y);
+            z1.z = __fadd_rn(__fmul_rn(sc, s1.z), a1.z); z1.w = __fadd_rn(__fmul_rn(sc, s1.w), a1.w);
+            if (fold) {
+              const float wsum = sc + (float)cnt;
+              const float4 be0 = *reinterpret_cast<const float4*>(beta_s + 4 * l8);
+              const float4 be1 = *reinterpret_cast<const float4*>(beta_s + 4 * (l8 + 8));
+              z0.x = fmaf(fa0.x, z0.x, be0.x * wsum); z0.y = fmaf(fa0.y, z0.y, be0.y * wsum);
+              z0.z = fmaf(fa0.z, z0.z, be0.z * wsum); z0.w = fmaf(fa0.w, z0.w, be0.w * wsum);
+              z1.x = fmaf(fa1.x, z1.x, be1.x * wsum); z1.y = fmaf(fa1.y, z1.y, be1.y * wsum);
+              z1.z = fmaf(fa1.z, z1.z, be1.z * wsum); z1.w = fmaf(fa1.w, z1.w, be1.w * wsum);
+            }
+          }
+          const uint32_t off = sw128_off(r, l8);
+          *reinterpret_cast<float4*>(a_hi + off) = z0;
+          *reinterpret_cast<float4*>(a_hi + TC_BM * 128 + off) = z1;
+          if (!EARLY) {
+            *reinterpret_cast<uint4*>(a_lo + off) = lo_part(z0);
+            *reinterpret_cast<uint4*>(a_lo + TC_BM * 128 + off) = lo_part(z1);
+          }
+          if (p.Z && grow < p.rows) {
+            float* zr = p.Z + (int64_t)grow * p.ldz + 4 * l8;
+            st4(zr, z0);
+            st4(zr + 32, z1);
+          }
+          if (warp == FIRST_PROD) GL_TRACE(11 + (r / N_GROUPS), it);
+        }
+      } else {
 #pragma unroll 1
       for (int r = grp_t; r < TC_BM; r += N_GROUPS) {
         const int grow = m0 + r;
@@ -506,6 +581,7 @@ k_gin_layer_fwd(const GinLayerArgs p, const __grid_constant__ CUtensorMap tmx) {
           if (ok1) st4(zr + 32, z1);
         }
         if (warp == FIRST_PROD) GL_TRACE(11 + (r / N_GROUPS), it);
+      }
       }
       if (warp == FIRST_PROD) GL_TRACE(1, it);
       if (STAGE_X) {
@@ -974,7 +1050,7 @@ extern "C" int bignn_gin_layer_fwd(int32_t rows, int32_t din, int32_t dout, cons
   // 22 producers = 88 row groups; 768 = 14 producers at 80 registers), TMA staging of X, t in tensor memory, neighbour
   // rows in flight per producer group
   typedef void (*Kern)(GinLayerArgs, CUtensorMap);
-  static Kern kern = nullptr;
+  static Kern kern = nullptr, kern_lean = nullptr;
   static int threads = 896;
   static int dbg = 0;
   static long long* trace_dev = nullptr;
@@ -991,12 +1067,16 @@ extern "C" int bignn_gin_layer_fwd(int32_t rows, int32_t din, int32_t dout, cons
     threads = th ? atoi(th) : 896;
     const char* us = getenv("BIGNN_GL_U");
     const int u = us ? atoi(us) : 2;
-    Kern k = nullptr;
+    Kern k = nullptr, kl = nullptr;
     const char* ea = getenv("BIGNN_GL_EARLY");
     const int early = (ea ? atoi(ea) : 1) && tmem_a && !stage;
-#define GL_PICK(TH, ST, TA, UU) \
-    if (threads == TH && stage == ST && tmem_a == TA && u == UU) \
-      k = early ? k_gin_layer_fwd<TH, ST, TA, UU, (TA && !ST)> : k_gin_layer_fwd<TH, ST, TA, UU, false>;
+    const char* le = getenv("BIGNN_GL_LEAN");
+    const int lean = (le ? atoi(le) : 1) && early;
+#define GL_PICK(TH, ST, TA, UU)                                                                              \
+    if (threads == TH && stage == ST && tmem_a == TA && u == UU) {                                             \
+      k = early ? k_gin_layer_fwd<TH, ST, TA, UU, (TA && !ST), false> : k_gin_layer_fwd<TH, ST, TA, UU, false, false>; \
+      kl = lean ? k_gin_layer_fwd<TH, ST, TA, UU, (TA && !ST), (TA && !ST)> : k;                              \
+    }
     // the measured variants (profiles/r2_summary.md); everything else lost and is not compiled
     GL_PICK(896, 0, 1, 2) GL_PICK(832, 0, 1, 2) GL_PICK(768, 0, 1, 2) GL_PICK(768, 0, 1, 3) GL_PICK(1024, 0, 1, 3)
     GL_PICK(768, 0, 0, 2) GL_PICK(768, 1, 1, 2)
@@ -1004,11 +1084,16 @@ extern "C" int bignn_gin_layer_fwd(int32_t rows, int32_t din, int32_t dout, cons
     if (!k) return BIGNN_EINVAL;               // (an unsupported combination of the BIGNN_GL_* variables)
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, GL_SMEM);
     if (e != cudaSuccess) return (int)e;
+    if (kl != k) {
+      e = cudaFuncSetAttribute(kl, cudaFuncAttributeMaxDynamicSharedMemorySize, GL_SMEM);
+      if (e != cudaSuccess) return (int)e;
+    }
     const char* d = getenv("BIGNN_GL_DEBUG");     // timing experiments only: 1 = no gathers, 2 = no stores (results invalid)
     dbg = d ? atoi(d) : 0;
     trace_path = getenv("BIGNN_GL_TRACE");       // debugging: dump CTA 0's pipeline time stamps of every launch to this file
     if (trace_path && cudaMalloc(&trace_dev, 64 * 16 * sizeof(long long)) != cudaSuccess) trace_dev = nullptr;
     kern = k;
+    kern_lean = kl;
   }
   // TMA descriptor of X: [rows, din_pad] fp32, row pitch ldx, boxes of 32 columns x 128 rows, SWIZZLE_128B; columns and
   // rows outside the tensor read as zeros (the zero padding of the first layer's 49 -> 64 columns comes for free)
@@ -1046,7 +1131,8 @@ extern "C" int bignn_gin_layer_fwd(int32_t rows, int32_t din, int32_t dout, cons
   if (trace_dev) cudaMemsetAsync(trace_dev, 0, 64 * 16 * sizeof(long long), (cudaStream_t)stream);
   int grid = sm_count();
   if (grid > a.n_tiles) grid = a.n_tiles;
-  kern<<<grid, threads, GL_SMEM, (cudaStream_t)stream>>>(a, tmx);
+  // the lean producer loop covers 64 input columns without debug switches; everything else takes the general one
+  (din == GL_D && dbg == 0 ? kern_lean : kern)<<<grid, threads, GL_SMEM, (cudaStream_t)stream>>>(a, tmx);
   BIGNN_LAUNCH_COUNT(1);
   if (trace_dev) {                                   // (debug mode only: synchronises)
     static long long host[64 * 16];
