@@ -77,6 +77,15 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, in
       "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// ---- TMA store: one staged [128 rows x 32 floats] box (K-major SWIZZLE_128B, the layout the epilogues stage in) -> global
+// memory, rows / columns outside the tensor clipped by the hardware; bulk async-group completion
+__device__ __forceinline__ void tma_store_2d(const void* src, const CUtensorMap* tm, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tm), "r"(smem_u32(src)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 // one non-blocking test of a phase
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
   uint32_t done;
@@ -157,6 +166,7 @@ __device__ __forceinline__ uint4 lo_part(const float4& x) {
 
 struct GinLayerArgs {
   int rows, din, n_tiles, nnz, dbg, S;
+  int tma_out;                                        // T / Y tiles leave shared memory as TMA bulk tensor stores
   const int32_t* row_ptr; const int32_t* col_idx; const int32_t* tile_edge_ptr;
   const float* X; int64_t ldx;
   const float* fold_mean; const float* fold_a; const float* fold_beta;   // [S, din], [S, din], [din] or null
@@ -273,7 +283,8 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_acc, const uint8_t* a_h
 // next rows changed nothing, more code made it slower; profiles/r2_summary.md).  Same arithmetic in the same order.
 template <int THREADS, bool STAGE_X, bool TMEM_A, int GL_U, bool EARLY, bool LEAN>
 __global__ void __launch_bounds__(THREADS, 1)
-k_gin_layer_fwd(const GinLayerArgs p, const __grid_constant__ CUtensorMap tmx) {
+k_gin_layer_fwd(const GinLayerArgs p, const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy,
+                const __grid_constant__ CUtensorMap tmt) {
   static_assert(!EARLY || (TMEM_A && !STAGE_X), "EARLY needs t in tensor memory and no TMA staging in the lo region");
   static_assert(!LEAN || !STAGE_X, "LEAN gathers from global memory");
   constexpr int N_WARPS = THREADS / 32;
@@ -818,7 +829,14 @@ k_gin_layer_fwd(const GinLayerArgs p, const __grid_constant__ CUtensorMap tmx) {
       if (warp == 0) GL_TRACE(4, it);
       if (p.T) {
         named_bar_sync(1, GL_EPI_WARPS * 32);               // all of t is in the slot; copy it out while the MMA runs
-        if (store) {
+        if (p.tma_out) {
+          if (et == 0 && store) {                            // two boxes of 32 columns; the smem source is free once read
+            tma_store_2d(stg, &tmt, 0, m0);
+            tma_store_2d(stg + TC_BM * 128, &tmt, TC_KC, m0);
+            tma_store_commit();
+            tma_store_wait_read();
+          }
+        } else if (store) {
 #pragma unroll 4
           for (int i = 0; i < 16; ++i) {
             const int r = rg + 8 * i;
@@ -884,11 +902,18 @@ k_gin_layer_fwd(const GinLayerArgs p, const __grid_constant__ CUtensorMap tmx) {
           *reinterpret_cast<float4*>(hi + (uint32_t)(((c0 + c) ^ row7) << 4)) =
               make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
       }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // (the staged tile may leave through TMA)
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc2_free[b]);
       if (qw == 0) GL_TRACE(6, it);
       named_bar_sync(2, GL_EPI_WARPS * 32);
+      if (p.tma_out && et == 0 && store) {
+        tma_store_2d(stg, &tmy, 0, m0);
+        tma_store_2d(stg + TC_BM * 128, &tmy, TC_KC, m0);
+        tma_store_commit();
+      }
+      if (!STAGE_X && qw == 0) GL_TRACE(8, it);
       // ---------------- coalesced copy-out (+ BatchNorm partial sums of the stored rows when the tile lies in one chunk)
       int chunk = 0, chunk_end = rows_here;
       if (p.stat_parts) {
@@ -904,7 +929,7 @@ k_gin_layer_fwd(const GinLayerArgs p, const __grid_constant__ CUtensorMap tmx) {
           const int r = rg + 8 * i;
           if (r < rows_here) {
             const float4 o = *reinterpret_cast<const float4*>(src + sw128_off(r, c4 & 7));
-            st4(p.Y + (int64_t)(m0 + r) * p.ldy + 4 * c4, o);
+            if (!p.tma_out) st4(p.Y + (int64_t)(m0 + r) * p.ldy + 4 * c4, o);
             if (one_chunk) {
               const double ox = (double)o.x, oy = (double)o.y, oz = (double)o.z, ow = (double)o.w;
               s[0] += ox; ss[0] = fma(ox, ox, ss[0]);
@@ -915,6 +940,7 @@ k_gin_layer_fwd(const GinLayerArgs p, const __grid_constant__ CUtensorMap tmx) {
           }
         }
       }
+      if (!STAGE_X && qw == 0) GL_TRACE(14, it);
       // ---------------- BatchNorm partial sums per (tile, chunk) record
       if (p.stat_parts) {
         int lo_r = 0;
@@ -946,6 +972,7 @@ k_gin_layer_fwd(const GinLayerArgs p, const __grid_constant__ CUtensorMap tmx) {
           ++chunk;
         }
       }
+      if (p.tma_out && et == 0 && store) tma_store_wait_read();     // the staging region may be overwritten
       __syncwarp();
       if (lane == 0) mbar_arrive(&z_empty[b]);
       if (qw == 0) GL_TRACE(7, it);
@@ -1049,7 +1076,7 @@ extern "C" int bignn_gin_layer_fwd(int32_t rows, int32_t din, int32_t dout, cons
   // variants (template parameters): threads per CTA (1024 = 32 warps at 64 registers: 4 + 4 epilogue, MMA, index prefetch,
   // 22 producers = 88 row groups; 768 = 14 producers at 80 registers), TMA staging of X, t in tensor memory, neighbour
   // rows in flight per producer group
-  typedef void (*Kern)(GinLayerArgs, CUtensorMap);
+  typedef void (*Kern)(GinLayerArgs, CUtensorMap, CUtensorMap, CUtensorMap);
   static Kern kern = nullptr, kern_lean = nullptr;
   static int threads = 896;
   static int dbg = 0;
@@ -1120,7 +1147,27 @@ extern "C" int bignn_gin_layer_fwd(int32_t rows, int32_t din, int32_t dout, cons
                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return BIGNN_EINVAL;
   }
+  // Y and T as [rows, 64] tensors for the epilogues' TMA stores (same boxes and swizzle as the staging layout)
+  static int tma_out_env = -1;
+  if (tma_out_env < 0) { const char* to = getenv("BIGNN_GL_TMA_OUT"); tma_out_env = to ? atoi(to) : 1; }
+  CUtensorMap tmy = tmx, tmt = tmx;
+  int tma_out = tma_out_env && dout == GL_D;
+  if (tma_out) {
+    const cuuint64_t gdim[2] = {(cuuint64_t)dout, (cuuint64_t)rows};
+    const cuuint32_t box[2] = {(cuuint32_t)TC_KC, (cuuint32_t)TC_BM};
+    const cuuint32_t estr[2] = {1, 1};
+    const cuuint64_t gy[1] = {(cuuint64_t)ldy * sizeof(float)};
+    CUresult r = encode(&tmy, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)Y, gdim, gy, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS && T) {
+      const cuuint64_t gt[1] = {(cuuint64_t)ldt * sizeof(float)};
+      r = encode(&tmt, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)T, gdim, gt, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS) tma_out = 0;                      // (pitches TMA cannot express: the epilogues store themselves)
+  }
   GinLayerArgs a;
+  a.tma_out = tma_out;
   a.rows = rows; a.din = din; a.n_tiles = ceil_div(rows, TC_BM); a.nnz = nnz; a.dbg = dbg; a.S = S;
   a.row_ptr = row_ptr; a.col_idx = col_idx; a.tile_edge_ptr = tile_edge_ptr; a.X = X; a.ldx = ldx;
   a.fold_mean = fold_mean; a.fold_a = fold_a; a.fold_beta = fold_beta;
@@ -1132,7 +1179,7 @@ extern "C" int bignn_gin_layer_fwd(int32_t rows, int32_t din, int32_t dout, cons
   int grid = sm_count();
   if (grid > a.n_tiles) grid = a.n_tiles;
   // the lean producer loop covers 64 input columns without debug switches; everything else takes the general one
-  (din == GL_D && dbg == 0 ? kern_lean : kern)<<<grid, threads, GL_SMEM, (cudaStream_t)stream>>>(a, tmx);
+  (din == GL_D && dbg == 0 ? kern_lean : kern)<<<grid, threads, GL_SMEM, (cudaStream_t)stream>>>(a, tmx, tmy, tmt);
   BIGNN_LAUNCH_COUNT(1);
   if (trace_dev) {                                   // (debug mode only: synchronises)
     static long long host[64 * 16];

@@ -18,6 +18,7 @@ d = np.diff(rows, axis=0)
 print('period per tile (us): ' + ' '.join('%s %.2f' % (n, v) for n, v in zip(names, np.nanmean(d, axis=0))))
 r = rows
 print('producer warp detail (us): idx ready+prefetch -> x_full wait %.2f | x_full -> row iteration 1 done %.2f | it 2 %.2f | it 3 %.2f' % (np.nanmean(r[:, 0] - r[:, 14]), np.nanmean(r[:, 11] - r[:, 0]), np.nanmean(r[:, 12] - r[:, 11]), np.nanmean(r[:, 13] - r[:, 12])))
+print('E2 detail (us): acc2 read -> staged (barrier) %.2f | copy-out loop %.2f | statistics + barriers %.2f' % (np.nanmean(r[:, 8] - r[:, 6]), np.nanmean(r[:, 14] - r[:, 8]), np.nanmean(r[:, 7] - r[:, 14])))
 print('mean stage times (us): TMA->x_full %.2f | aggregate %.2f | lo+fence %.2f | z_full->MMA1 issue %.2f | MMA1 issue->m1 seen %.2f | E1 %.2f | t_full->MMA2 issue %.2f | MMA2 issue->m2 seen %.2f | E2 tmem+stage %.2f | E2 copy-out+stats %.2f | z_empty->next TMA %.2f' % (
     np.nanmean(r[:, 0] - r[:, 8]), np.nanmean(r[:, 1] - r[:, 0]), np.nanmean(r[:, 2] - r[:, 1]), np.nanmean(r[:, 9] - r[:, 2]),
     np.nanmean(r[:, 3] - r[:, 9]), np.nanmean(r[:, 4] - r[:, 3]), np.nanmean(r[:, 10] - r[:, 4]), np.nanmean(r[:, 5] - r[:, 10]),
