@@ -62,7 +62,9 @@ k_gemm_tc(int M, int N, int K, const float* __restrict__ A, int64_t lda, const f
   constexpr int ACC_COLS = (NA + 1) * NPAD;
   constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : (ACC_COLS <= 64 ? 64 : (ACC_COLS <= 128 ? 128 : 256));
   static_assert(ACC_COLS <= 256, "two CTAs per SM share the 512 TMEM columns");
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // (aligned through an OFFSET from the __shared__ array: a round trip through uintptr_t makes every access below a
+  // generic LD / ST instead of LDS / STS)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* a_hi = smem;                            // [KCH][128 x 128 B]  raw fp32 rows
   uint8_t* a_lo = a_hi + KCH * A_BYTES;            // [LO_CH][128 x 128 B]
   uint8_t* b_hi = a_lo + LO_CH * A_BYTES;          // [KCH][NPAD x 128 B]

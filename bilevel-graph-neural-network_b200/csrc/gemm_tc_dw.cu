@@ -53,7 +53,9 @@ k_dw_tc_ring(int M, int Np, int Nq, const float* __restrict__ P, int64_t ldp, co
   constexpr int STAGE = 2 * DW_TILE;               // [P][Q]
   static_assert((DW_NA + 1) * DW_F <= 256 && NST >= 3, "two CTAs per SM");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // (aligned through an OFFSET from the __shared__ array: a round trip through uintptr_t makes every access below a
+  // generic LD / ST instead of LDS / STS)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* lo_base = smem + NST * STAGE;           // two lo buffers of STAGE bytes
   __shared__ uint64_t mma_bar[2];
   __shared__ uint32_t tmem_base_s;

@@ -294,7 +294,9 @@ k_gin_layer_fwd(const GinLayerArgs p, const __grid_constant__ CUtensorMap tmx, c
   constexpr int N_PROD_WARPS = N_WARPS - FIRST_PROD;
   constexpr int N_GROUPS = N_PROD_WARPS * 4;                 // 8-lane groups
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // (aligned through an OFFSET from the __shared__ array: a round trip through uintptr_t makes every access below a
+  // generic LD / ST instead of LDS / STS)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* w1_hi = smem + 2 * GL_SLOT;
   uint8_t* w1_lo = w1_hi + GL_W;
   uint8_t* w2_hi = w1_lo + GL_W;
