@@ -575,33 +575,64 @@ def kernel_profile(torch, B, eng, steps=3, on_start=None):
 # the committed `ncu --set full` captures (profiles/r2_summary.md); a run without a profiler cannot read DRAM counters, so
 # `roofline.traffic` = this measured ratio x the algorithmic bytes of the launch being reported
 NCU_TRAFFIC = [
-    ('bignn_gin_layer_fwd[rows=6', 0.999,
+    ('bignn_gin_layer_fwd', 0.999,
      'profiles/r2_summary.md: ncu --set full of k_gin_layer_fwd<896,..> at 6 000 245 rows x 64 keeping z and t: dram read '
      '1.612 GB + write 4.602 GB = 6.214 GB = 0.999 x algorithmic; scaled to this launch'),
-    ('bignn_dw_tc_f32[M=6', 1.003,
+    ('bignn_dw_tc_f32', 1.003,
      'profiles/r2_summary.md: ncu --set full of k_dw_tc_ring at 6 000 000 rows: dram read 3.073 GB + write 0.009 GB = '
      '1.003 x algorithmic; scaled to this launch'),
 ]
 
 
 def step_roofline(prof, peaks):
-    """`roofline` of the dominant kernel of the TIMED step: the C-ABI entry with the largest share of the step's device
-    time; achieved = its algorithmic bytes per call / its average call duration (CUDA events in the eager pass)."""
+    """`roofline` of the dominant kernel of the TIMED step: the C-ABI entry point with the largest share of the step's
+    device time SUMMED OVER ITS CALLS (the first lower layer has 49 input columns, the others 64: one kernel, two shapes
+    -- grouped the way the ncu launch list groups them); achieved = its algorithmic bytes / its time over those calls
+    (CUDA events in the eager pass)."""
     peak = peaks.get('hbm_gbs', 6650.0)
+    groups = {}
     for e in prof.get('top', []):
-        if 'achieved_gbs' in e:
-            traffic, src = None, ('dram bytes of this kernel: see the ncu --set full summary under profiles/ '
-                                  '(not measurable inside an un-profiled run)')
-            for prefix, ratio, cite in NCU_TRAFFIC:
-                if e['entry'].startswith(prefix):
-                    traffic = ratio * e['algorithmic_bytes_per_call']
-                    src = cite
-            return dict(kernel=e['entry'], bound='hbm', achieved=e['achieved_gbs'], peak=peak, unit='GB/s',
-                        frac=round(e['achieved_gbs'] / peak, 4), traffic=traffic, share_of_step=e['share'],
-                        ms_per_launch=e['ms_per_call'], algorithmic_bytes=e['algorithmic_bytes_per_call'],
-                        peak_source='MEASURED_PEAKS.json hbm_gbs (measured copy peak)' if 'hbm_gbs' in peaks
-                        else 'fallback 6650 GB/s',
-                        traffic_note=src)
+        if 'achieved_gbs' not in e:
+            continue
+        g = groups.setdefault(e['entry'].split('[')[0], dict(ms=0.0, nbytes=0.0, calls=0, share=0.0, shapes=[]))
+        g['ms'] += e['ms_per_call'] * e['calls_per_step']
+        g['nbytes'] += e['algorithmic_bytes_per_call'] * e['calls_per_step']
+        g['calls'] += e['calls_per_step']
+        g['share'] += e['share']
+        g['shapes'].append(e['entry'])
+    if not groups:
+        return None
+    name, g = max(groups.items(), key=lambda kv: kv[1]['share'])
+    ach = g['nbytes'] / (g['ms'] * 1e-3) / 1e9
+    traffic, src = None, ('dram bytes of this kernel: see the ncu --set full summary under profiles/ '
+                          '(not measurable inside an un-profiled run)')
+    for prefix, ratio, cite in NCU_TRAFFIC:
+        if name.startswith(prefix):
+            traffic = ratio * g['nbytes'] / g['calls']
+            src = cite
+    out = dict(kernel=name, shapes=g['shapes'], bound='hbm', achieved=round(ach, 1), peak=peak, unit='GB/s',
+               frac=round(ach / peak, 4), traffic=traffic, share_of_step=round(g['share'], 4),
+               ms_per_launch=round(g['ms'] / g['calls'], 5), launches_per_step=g['calls'],
+               algorithmic_bytes=g['nbytes'] / g['calls'],
+               peak_source='MEASURED_PEAKS.json hbm_gbs (measured copy peak)' if 'hbm_gbs' in peaks
+               else 'fallback 6650 GB/s', traffic_note=src)
+    return out
+
+
+def l2_gather_line(prof, eng):
+    """The upper-level SpMM is not an HBM kernel: its feature matrix (drugs x 64 x 4 B) is L2-resident and every
+    neighbour is a 256-byte gather out of L2.  Reported beside `roofline`: gathered bytes per launch / launch time."""
+    for e in prof.get('top', []):
+        if e['entry'].startswith('bignn_spmm_planned_rows_f32') or e['entry'].startswith('bignn_spmm_planned_f32'):
+            try:
+                nnz = int(eng.data.interaction_combo_nxgraph.csr.nnz)
+            except Exception:
+                return None
+            gathered = 4.0 * 64 * nnz
+            return dict(kernel=e['entry'], gathered_bytes_per_launch=gathered, ms_per_launch=e['ms_per_call'],
+                        l2_gather_gbs=round(gathered / (e['ms_per_call'] * 1e-3) / 1e9, 1), share_of_step=e['share'],
+                        note='L2-resident operand: bound by L2 gather bandwidth, not by HBM (its algorithmic HBM bytes '
+                             'are the index stream and one pass over the drugs x 64 matrix)')
     return None
 
 
@@ -651,6 +682,12 @@ def main():
     if not args.skip_rooflines:
         if prof is not None:
             out['roofline'] = step_roofline(prof, peaks)
+            try:
+                g = l2_gather_line(prof, eng)
+                if g is not None:
+                    out['upper_spmm_l2_gather'] = g
+            except Exception as e:
+                out['upper_spmm_l2_gather'] = dict(error=repr(e)[:200])
         # the kernel BASELINE's metric names (segment SpMM) on a > L2 molecule-like graph, stand-alone
         out['roofline_segment_spmm'] = spmm_roofline(torch, B, args.spmm_rows, peaks, dev)
     if not args.skip_gpu_eager:
