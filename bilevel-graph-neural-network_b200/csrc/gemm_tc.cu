@@ -87,16 +87,23 @@ k_gemm_tc(int M, int N, int K, const float* __restrict__ A, int64_t lda, const f
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   const uint32_t a_hi_s = smem_u32(a_hi);
+  // this thread's chunks of a tile: 16-byte chunk pc of rows pr, pr + 32, pr + 64, pr + 96 of every K chunk.  Everything
+  // that does not depend on the tile is computed once (as in k_dw_tc_ring, where the per-chunk index arithmetic was a
+  // third of the instructions a warp executed per tile): r & 7 is the same for the four rows, so the swizzled offset
+  // advances by 4 KB per step
+  static_assert(TC_THREADS == 256 && TC_BM == 128, "chunk mapping");
+  const int pr = tid >> 3, pc = tid & 7;
+  const uint32_t soff = sw128_off(pr, pc);
+  const float* gp = A + (int64_t)pr * lda + pc * 4;
   auto prefetch_tile = [&](int tile) {
     const int m0 = tile * TC_BM;
-#pragma unroll 1
-    for (int j = tid; j < kch_used * 1024; j += TC_THREADS) {
-      const int ch = j >> 10, idx = j & 1023;
-      const int r = idx >> 3, c = idx & 7;
-      const int gm = m0 + r, gk = ch * TC_KC + c * 4;
-      const bool ok = gm < M && gk < K;
-      const float* src = ok ? A + (int64_t)gm * lda + gk : A;
-      cp_async16(a_hi_s + ch * A_BYTES + sw128_off(r, c), src, ok ? 16u : 0u);     // src_bytes 0 -> zero fill
+    const float* g0 = gp + (int64_t)m0 * lda;
+#pragma unroll
+    for (int i = 0; i < KCH * 4; ++i) {
+      if (i >= kch_used * 4) break;
+      const int ch = i >> 2, rr = (i & 3) * 32;
+      const bool ok = (m0 + pr + rr < M) && (ch * TC_KC + pc * 4 < K);
+      cp_async16(a_hi_s + soff + i * 4096, ok ? g0 + (int64_t)rr * lda + ch * TC_KC : A, ok ? 16u : 0u);   // 0 -> zero fill
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
@@ -130,10 +137,10 @@ k_gemm_tc(int M, int N, int K, const float* __restrict__ A, int64_t lda, const f
     const int m0 = tile * TC_BM;
     // ---- this thread's cp.async chunks have landed; derive the lo operand from them (same chunks)
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-#pragma unroll 4
-    for (int j = tid; j < kch_used * 1024; j += TC_THREADS) {
-      const int ch = j >> 10, idx = j & 1023;
-      const uint32_t off = ch * A_BYTES + sw128_off(idx >> 3, idx & 7);
+#pragma unroll
+    for (int i = 0; i < KCH * 4; ++i) {
+      if (i >= kch_used * 4) break;
+      const uint32_t off = soff + i * 4096;
       const float4 x = *reinterpret_cast<const float4*>(a_hi + off);
       uint4 l;
       l.x = __float_as_uint(x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u)) & 0xffffe000u;
