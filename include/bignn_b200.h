@@ -214,7 +214,9 @@ int bignn_bn_eval_fwd(const float* X, int64_t ldx, float* Y, int64_t ldy, int32_
 /* dX, and dgamma/dbeta ACCUMULATED over segments in segment order (written, not added).
  * input_act (BIGNN_ACT_*): X is the output of that activation (model/layers.py:55-57 applies act, then bn); its
  * derivative is folded into dX, so dX is the gradient w.r.t. the activation's INPUT (BIGNN_ACT_IDENTITY = plain
- * BatchNorm backward).  Saves the separate elementwise pass over [rows, C]. */
+ * BatchNorm backward).  Saves the separate elementwise pass over [rows, C].
+ * From 24 segments of 64 channels on (the all-drug lower level) one thread-block cluster per segment does both passes
+ * while the segment is L2-resident (csrc/bn.cu k_bn_bwd_chunk; same results bit for bit, 2 launches instead of 4). */
 int bignn_bn_seg_bwd(const float* X, int64_t ldx, const float* dY, int64_t lddy,
                      float* dX, int64_t lddx,
                      const int32_t* seg_row_ptr, int32_t S, int32_t C, int32_t parts,
