@@ -167,17 +167,31 @@ class BiGNNData(object):
     def labels_of_pairs(self, gid_pairs):
         """look_up_label over an array of pairs (either orientation; 0 when unknown)."""
         p = np.asarray(gid_pairs, np.int64)
+        if p.shape[0] == 0:
+            return np.zeros(0, np.int64)
         if isinstance(self.pairs, _PairTable):
-            rows = self.rows_of_gids(p.reshape(-1)).reshape(-1, 2)
-            out = np.zeros(p.shape[0], np.int64)
-            for a, b in ((0, 1), (1, 0)):
-                k = rows[:, a] * self.N + rows[:, b]
-                i = np.minimum(np.searchsorted(self.pairs.keys, k), self.pairs.keys.shape[0] - 1)
-                hit = self.pairs.keys[i] == k
-                out = np.where((out == 0) & hit, self.pairs.labels[i], out)
-            return out
-        return np.asarray([0 if l is None else l for l in
-                           (self.look_up_label(int(a), int(b)) for a, b in p.tolist())], np.int64)
+            keys, labels = self.pairs.keys, self.pairs.labels
+        else:
+            # the dict of tuples as a sorted key table, built once (a Python loop with two dict probes per pair holds
+            # the GIL for 85 ms per 65 536-pair batch: the host threads of engine_lower.PairPrefetcher then serialise)
+            if getattr(self, '_pairs_tab', None) is None or self._pairs_tab[2] != len(self.pairs):
+                pk = np.asarray(list(self.pairs.keys()), np.int64).reshape(-1, 2)
+                pl = np.asarray(list(self.pairs.values()), np.int64)
+                rows = self.rows_of_gids(pk.reshape(-1)).reshape(-1, 2)
+                key = rows[:, 0] * self.N + rows[:, 1]
+                o = np.argsort(key, kind='stable')
+                self._pairs_tab = (key[o], pl[o], len(self.pairs))
+            keys, labels = self._pairs_tab[0], self._pairs_tab[1]
+        if keys.shape[0] == 0:
+            return np.zeros(p.shape[0], np.int64)
+        rows = self.rows_of_gids(p.reshape(-1)).reshape(-1, 2)
+        out = np.zeros(p.shape[0], np.int64)
+        for a, b in ((0, 1), (1, 0)):
+            k = rows[:, a] * self.N + rows[:, b]
+            i = np.minimum(np.searchsorted(keys, k), keys.shape[0] - 1)
+            hit = keys[i] == k
+            out = np.where((out == 0) & hit, labels[i], out)
+        return out
 
     def look_up_label(self, gid1, gid2):
         """utils/data/dataset.py:394-403 (None instead of ValueError when unknown)."""

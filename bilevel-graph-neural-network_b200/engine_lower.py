@@ -89,6 +89,53 @@ class FastPairSampler(object):
         return pos, None, None                      # (the engine derives the batch's drugs itself)
 
 
+class PairPrefetcher(object):
+    """Prepares the pair batches of the coming steps on host threads while the device runs.
+
+    At 32 768 + 32 768 pairs per step the host side of a step (vectorised negatives 65 ms, labels 49 ms, unique drugs in
+    first-appearance order 43 ms -- all of it binary searches and sorts that release the GIL) costs seven times the
+    device step (22 ms on B200).  Positives are taken from `sampler` in order on the calling thread; batch i's negatives
+    come from a generator seeded with (seed, i), so the stream of batches does not depend on the number of workers.
+    `next()` returns ((rows, ids, labels), number of pairs) of the next step, in order."""
+
+    def __init__(self, engine, sampler, workers=None, depth=None, seed=0):
+        import collections
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+        self.eng, self.sampler, self.seed = engine, sampler, int(seed)
+        self.workers = int(workers) if workers else max(1, min(16, (os.cpu_count() or 2) - 1))
+        self.depth = int(depth) if depth else 2 * self.workers
+        self.pool = ThreadPoolExecutor(self.workers)
+        self.q = collections.deque()
+        self.n = 0
+        d = engine.data                     # build the lazily cached lookup tables before any worker needs them
+        d.rows_of_gids(np.zeros(0, np.int64))
+        d.edge_keys_sorted()
+
+    def prepare(self, pos, i):
+        d = self.eng.data
+        neg = fast_negative_pairs(d, pos, np.random.default_rng([self.seed, int(i)]))
+        gids = np.concatenate([pos, neg]) if neg.shape[0] else pos
+        labels = np.concatenate([d.labels_of_pairs(pos), np.zeros(neg.shape[0], np.int64)])
+        return self.eng.stage(gids, labels), int(gids.shape[0])
+
+    def _fill(self):
+        while len(self.q) < self.depth:
+            pos = np.asarray(self.sampler.sample_next_training_batch()[0], np.int64)
+            self.q.append(self.pool.submit(self.prepare, pos, self.n))
+            self.n += 1
+
+    def next(self):
+        self._fill()
+        out = self.q.popleft().result()
+        self._fill()
+        return out
+
+    def close(self):
+        self.pool.shutdown(wait=False, cancel_futures=True)
+        self.q.clear()
+
+
 class _LowerPairBatch(object):
     """What LinkPred / Loss read of a batch in the lower-level-only model."""
 
@@ -177,6 +224,13 @@ class LowerOnlyEngine(object):
     def step_pairs(self, batch_gids, labels):
         self.last_static_batch = self.stage(batch_gids, labels)
         return self._device_step(self.last_static_batch)
+
+    def train_step_prefetched(self, prefetcher):
+        """one step on the next batch of a PairPrefetcher (host preparation of later batches overlaps this step)."""
+        staged, n = prefetcher.next()
+        self.last_pairs = n
+        self.last_static_batch = staged
+        return self._device_step(staged)
 
     def train_step(self, sampler, fast_negatives=None, rng=None):
         """sample positives (the reference's DataLoader mechanism), negatives, labels; run one step.

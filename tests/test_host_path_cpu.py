@@ -453,3 +453,32 @@ def test_lower_only_engine_matches_reference_golden_and_fast_negatives(cpu_world
         assert np.array_equal(data.labels_of_pairs(neg), np.asarray([data.look_up_label(a, b) or 0 for a, b in neg.tolist()]))
     finally:
         B.set_flags(B.make_flags(device='cpu'))
+
+
+def test_pair_prefetcher_stream_is_independent_of_the_worker_count(golden_dir):
+    """engine_lower.PairPrefetcher: batches prepared by 4 host threads = the same batches prepared one by one, in order
+    (positives from the sampler in order, batch i's negatives from a generator seeded with (seed, i))."""
+    import bignn_b200 as B
+    from bignn_b200.engine_lower import PairPrefetcher, FastPairSampler, LowerOnlyEngine
+    B.set_flags(B.make_flags(model='lower_level_gnn', device='cpu'))
+    data = B.BiGNNData.from_npz(os.path.join(golden_dir, 'drugbank_packed.npz'), device='cpu')
+
+    class Stub(object):
+        stage = LowerOnlyEngine.stage
+
+    res = {}
+    for workers in (1, 4):
+        eng = Stub()
+        eng.data = data
+        pre = PairPrefetcher(eng, FastPairSampler(data, 512, seed=3), workers=workers, depth=6, seed=11)
+        res[workers] = [pre.next() for _ in range(9)]
+        pre.close()
+    for (a, na), (b, nb) in zip(res[1], res[4]):
+        assert na == nb and na > 512
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    rows, ids, labels = res[4][0][0]
+    assert ids.shape == (labels.shape[0], 2) and ids.max() == rows.shape[0] - 1
+    assert labels[:512].min() >= 0 and (labels[512:] == 0).all()
+    assert len(np.unique(rows)) == rows.shape[0]
+    B.set_flags(B.make_flags(device='cpu'))
