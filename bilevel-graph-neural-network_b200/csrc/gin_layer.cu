@@ -8,19 +8,25 @@
 // nn.Linear launches, two activation launches and the BatchNorm statistics pass.  Traffic per layer: the
 // rows of X once (neighbour rows of a molecule are re-read from L1/L2), the rows of Y once, the CSR.
 //
-// Persistent, warp-specialised, one CTA per SM, 128-row tiles, two operand slots in shared memory:
-//   * producer warps  aggregate the tile's rows straight from global memory (8 lanes per row, two 128-bit
-//                     column slots per lane, 4 neighbour rows in flight, ascending neighbour order, unfused
-//                     mul/add: the arithmetic of bignn_spmm_f32's GIN mode) and write z into the slot as the
-//                     K-major SWIZZLE_128B A operand, raw fp32 (= the TF32 hi part) plus the lo part;
-//   * one MMA warp    issues tcgen05.mma kind::tf32 (3xTF32: hi*hi over two rotating TMEM accumulators,
-//                     lo*hi + hi*lo into a third) for z W1^T, then -- once the epilogue warps have turned the
-//                     first accumulator into t inside the same slot -- for t W2^T;
-//   * epilogue warps  (one per TMEM lane quadrant) read the accumulators with tcgen05.ld, add bias, apply the
-//                     activation, write t back as an operand, and finally stage y in the slot for coalesced
-//                     128-bit stores, summing the BatchNorm statistics of the rows they store.
-// mbarriers: z_full/z_empty per slot (producers <-> MMA / epilogue), t_full (epilogue -> MMA), m1/m2 (tcgen05.commit).
-// Weights (hi and lo parts of W1, W2) stay resident in shared memory for every tile of the CTA.
+// Persistent, warp-specialised, one CTA per SM (896 threads by default), 128-row tiles, two operand slots in shared memory:
+//   * producer warps  (18) aggregate the tile's rows straight from global memory (8 lanes per row, two 128-bit
+//                     column slots per lane, two neighbour rows in flight, ascending neighbour order, unfused
+//                     mul/add: the arithmetic of bignn_spmm_f32's GIN mode) and write z into the slot's hi region as
+//                     the K-major SWIZZLE_128B A operand, raw fp32 (= the TF32 hi part); the lo part follows in a
+//                     second, shared-memory-only pass once the lo region is free (EARLY, below);
+//   * index warp      prefetches row pointers, neighbour ids, chunk ids and the folded BatchNorm parameters of the
+//                     tiles ahead with cp.async into a 3-stage ring;
+//   * one MMA warp    issues tcgen05.mma kind::tf32 (3xTF32: corrections lo*hi + hi*lo first, then hi*hi, one TMEM
+//                     accumulator of 64 columns per transform, double buffered) for z W1^T, then -- once E1 has put
+//                     t into TENSOR MEMORY -- for t W2^T with the A operand read from TMEM;
+//   * E1 / E2         (4 warps each, one per TMEM lane quadrant) read the accumulators with tcgen05.ld, add bias, apply
+//                     the activation; E1 stores t to TMEM (tcgen05.st) and stages T, E2 stages Y, both in the slot's lo
+//                     region, from where the tiles leave as TMA bulk tensor stores; E2 adds the fp64 BatchNorm partial
+//                     sums of the staged rows.
+// mbarriers: z_full per slot (producers -> MMA), m1_done (tcgen05.commit of the first transform: the hi region is free
+// again, and E1 may start), z_empty (E2 -> producers: the lo region is free), t_full / t_copied / acc2_free (epilogues <->
+// MMA), m2_done.  Weights (hi and lo parts of W1, W2) stay resident in shared memory for every tile of the CTA.
+// Measured history of the variants: profiles/r2_summary.md section 3.
 #include <cstdio>
 #include <cstdlib>
 #include <cuda.h>
