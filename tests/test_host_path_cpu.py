@@ -482,3 +482,30 @@ def test_pair_prefetcher_stream_is_independent_of_the_worker_count(golden_dir):
     assert labels[:512].min() >= 0 and (labels[512:] == 0).all()
     assert len(np.unique(rows)) == rows.shape[0]
     B.set_flags(B.make_flags(device='cpu'))
+
+
+def test_bench_roofline_groups_the_dominant_kernel_by_entry_point():
+    """bench.step_roofline: the dominant kernel of the timed step is the C-ABI entry point with the largest share summed
+    over its calls (the fused layer kernel runs with 49 and with 64 input columns: one kernel, two shapes), achieved =
+    its algorithmic bytes / its time over those calls; checked on the committed line of the final round-2 tree."""
+    import importlib.util
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('bench_mod', os.path.join(root, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    line = json.load(open(os.path.join(root, 'profiles', 'r2_bench_n1_c4_final.json')))
+    r = bench.step_roofline(line['kernel_profile'], {'hbm_gbs': 6535.4})
+    assert r['kernel'] == 'bignn_gin_layer_fwd' and len(r['shapes']) == 2 and r['launches_per_step'] == 5
+    top = {e['entry']: e for e in line['kernel_profile']['top']}
+    ms = sum(top[s]['ms_per_call'] * top[s]['calls_per_step'] for s in r['shapes'])
+    nb = sum(top[s]['algorithmic_bytes_per_call'] * top[s]['calls_per_step'] for s in r['shapes'])
+    assert abs(r['achieved'] - nb / (ms * 1e-3) / 1e9) < 0.1
+    assert abs(r['frac'] - r['achieved'] / 6535.4) < 1e-4 and 0.4 < r['frac'] < 0.7
+    assert abs(r['share_of_step'] - sum(top[s]['share'] for s in r['shapes'])) < 1e-3
+    assert r['traffic'] is not None and abs(r['traffic'] / r['algorithmic_bytes'] - 0.999) < 1e-6
+    # every other entry point has a smaller summed share
+    groups = {}
+    for e in line['kernel_profile']['top']:
+        groups[e['entry'].split('[')[0]] = groups.get(e['entry'].split('[')[0], 0.0) + e['share']
+    assert max(groups, key=groups.get) == 'bignn_gin_layer_fwd'
